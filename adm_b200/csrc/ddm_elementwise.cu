@@ -1,0 +1,403 @@
+// HBM-bound DDM-const kernels: fused q_sample (K1), fused C/eps loss forward+backward (K2), sampler update (K3),
+// EDM preconditioning edges, plus library bookkeeping (error string, launch counter).
+// All are single-pass, 128-bit vectorised, grid sized as a multiple of the SM count.
+#include "adm_internal.h"
+#include <cuda_bf16.h>
+#include <atomic>
+
+namespace adm {
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static inline int ew_grid(long long work_items, int threads, int per_sm) {
+    long long blocks = (work_items + threads - 1) / threads;
+    const long long cap = 1LL * num_sms() * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return static_cast<int>(blocks);
+}
+
+// ------------------------------------------------------------------------------------------------ K1 q_sample
+// x_t = x0 + C*t + sqrt(t)*noise with C = -x0.  One float4 per thread per iteration; t is per-sample.
+__global__ void __launch_bounds__(256) qsample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                                                      const float* __restrict__ t, float* __restrict__ xt,
+                                                      long long batch, long long chw) {
+    const long long total = batch * chw;
+    const long long stride = 1LL * gridDim.x * blockDim.x;
+    if ((chw & 3) == 0) {
+        const long long n4 = total >> 2;
+        const float4* x4 = reinterpret_cast<const float4*>(x0);
+        const float4* e4 = reinterpret_cast<const float4*>(noise);
+        float4* o4 = reinterpret_cast<float4*>(xt);
+        for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            const long long b = (i << 2) / chw;
+            const float tb = __ldg(t + b);
+            const float st = sqrtf(tb);
+            const float4 x = __ldcs(x4 + i), e = __ldcs(e4 + i);
+            float4 o;
+            // keep the reference's evaluation order: (x0 + C*t) + sqrt(t)*noise
+            // (no FMA contraction: bit-identical to the reference's separate mul / add kernels)
+            o.x = __fadd_rn(__fadd_rn(x.x, __fmul_rn(-x.x, tb)), __fmul_rn(st, e.x));
+            o.y = __fadd_rn(__fadd_rn(x.y, __fmul_rn(-x.y, tb)), __fmul_rn(st, e.y));
+            o.z = __fadd_rn(__fadd_rn(x.z, __fmul_rn(-x.z, tb)), __fmul_rn(st, e.z));
+            o.w = __fadd_rn(__fadd_rn(x.w, __fmul_rn(-x.w, tb)), __fmul_rn(st, e.w));
+            __stcs(o4 + i, o);
+        }
+    } else {
+        for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += stride) {
+            const float tb = __ldg(t + i / chw);
+            const float x = x0[i];
+            xt[i] = __fadd_rn(__fadd_rn(x, __fmul_rn(-x, tb)), __fmul_rn(sqrtf(tb), noise[i]));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K2 loss fwd+bwd
+// grid = (blocks_per_sample, B).  Each block reduces its slice of one sample, then one atomicAdd per block.
+__global__ void __launch_bounds__(256) ddm_loss_kernel(const float* __restrict__ cp, const float* __restrict__ ep,
+                                                       const float* __restrict__ x0, const float* __restrict__ noise,
+                                                       const float* __restrict__ t, float eps, int weighting,
+                                                       int use_l1, float grad_scale, float* __restrict__ loss,
+                                                       float* __restrict__ dcp, float* __restrict__ dep,
+                                                       long long batch, long long chw) {
+    const long long b = blockIdx.y;
+    const float tb = __ldg(t + b);
+    float w1 = 1.f, w2 = 1.f;
+    if (weighting) {
+        const float q = tb * tb - tb + 1.f;
+        w1 = q / tb;
+        w2 = q / (1.f - tb + eps);
+    }
+    const float inv_b = grad_scale / static_cast<float>(batch);
+    const float l1c = use_l1 ? 1.f / static_cast<float>(chw) : 0.f;
+    const float half = use_l1 ? 0.5f : 1.f;
+    const float* cpb = cp + b * chw;
+    const float* epb = ep + b * chw;
+    const float* xb = x0 + b * chw;
+    const float* nb = noise + b * chw;
+    float sse1 = 0.f, sse2 = 0.f, sae1 = 0.f, sae2 = 0.f;
+    const long long stride = 1LL * gridDim.x * blockDim.x;
+    const bool vec = (chw & 3) == 0;
+    const long long cnt = vec ? (chw >> 2) : chw;
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < cnt; i += stride) {
+        float c[4], e[4], x[4], n[4];
+        int m = 1;
+        if (vec) {
+            const float4 c4 = __ldcs(reinterpret_cast<const float4*>(cpb) + i);
+            const float4 e4 = __ldcs(reinterpret_cast<const float4*>(epb) + i);
+            const float4 x4 = __ldcs(reinterpret_cast<const float4*>(xb) + i);
+            const float4 n4 = __ldcs(reinterpret_cast<const float4*>(nb) + i);
+            c[0] = c4.x; c[1] = c4.y; c[2] = c4.z; c[3] = c4.w;
+            e[0] = e4.x; e[1] = e4.y; e[2] = e4.z; e[3] = e4.w;
+            x[0] = x4.x; x[1] = x4.y; x[2] = x4.z; x[3] = x4.w;
+            n[0] = n4.x; n[1] = n4.y; n[2] = n4.z; n[3] = n4.w;
+            m = 4;
+        } else {
+            c[0] = cpb[i]; e[0] = epb[i]; x[0] = xb[i]; n[0] = nb[i];
+        }
+        float g1[4], g2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < m) {
+                const float d1 = c[j] - (-x[j]);  // target1 = C = -x0
+                const float d2 = e[j] - n[j];     // target2 = noise
+                sse1 += d1 * d1;
+                sse2 += d2 * d2;
+                sae1 += fabsf(d1);
+                sae2 += fabsf(d2);
+                const float s1 = (d1 > 0.f) - (d1 < 0.f), s2 = (d2 > 0.f) - (d2 < 0.f);
+                g1[j] = inv_b * half * w1 * (2.f * d1 + l1c * s1);
+                g2[j] = inv_b * half * w2 * (2.f * d2 + l1c * s2);
+            }
+        }
+        if (dcp != nullptr) {
+            if (vec) {
+                __stcs(reinterpret_cast<float4*>(dcp + b * chw) + i, make_float4(g1[0], g1[1], g1[2], g1[3]));
+                __stcs(reinterpret_cast<float4*>(dep + b * chw) + i, make_float4(g2[0], g2[1], g2[2], g2[3]));
+            } else {
+                dcp[b * chw + i] = g1[0];
+                dep[b * chw + i] = g2[0];
+            }
+        }
+    }
+    float part = half * (w1 * (sse1 + l1c * sae1) + w2 * (sse2 + l1c * sae2));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    __shared__ float warp_sums[8];
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < (blockDim.x >> 5); ++i) s += warp_sums[i];
+        atomicAdd(loss + b, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K3 sampler step
+template <typename S>
+__global__ void __launch_bounds__(256) sampler_step_kernel(const S* __restrict__ x, const float* __restrict__ cp,
+                                                           const float* __restrict__ ep, S* __restrict__ xn,
+                                                           double t_cur, double t_next, double clip, int do_clip,
+                                                           int last, double scale_input, long long numel) {
+    const S tc = static_cast<S>(t_cur), tn = static_cast<S>(t_next);
+    const S sc = static_cast<S>(sqrt(t_cur)), sn = static_cast<S>(sqrt(t_next));
+    const S lo = static_cast<S>(-clip), hi = static_cast<S>(clip);
+    const long long stride = 1LL * gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < numel; i += stride) {
+        const S c = static_cast<S>(cp[i]), e = static_cast<S>(ep[i]);
+        S x0 = x[i] - c * tc - e * sc;
+        if (do_clip) x0 = x0 < lo ? lo : (x0 > hi ? hi : x0);
+        S v = x0 + c * tn + e * sn;
+        if (last) {
+            v = v < lo ? lo : (v > hi ? hi : v);
+            if (scale_input != 1.0) v = v / static_cast<S>(scale_input);
+            v = (v + static_cast<S>(1)) * static_cast<S>(0.5);
+        }
+        xn[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) sampler_step_stoch_kernel(const float* __restrict__ x,
+                                                                 const float* __restrict__ cp,
+                                                                 const float* __restrict__ ep,
+                                                                 const float* __restrict__ z, float* __restrict__ xn,
+                                                                 float t, float s, float clip, int do_clip,
+                                                                 long long numel) {
+    const float st = sqrtf(t);
+    const float sigma = sqrtf(s * (t - s) / t);
+    const long long stride = 1LL * gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < numel; i += stride) {
+        const float xi = x[i], e = ep[i];
+        float x0 = xi - cp[i] * t - st * e;
+        if (do_clip) x0 = fminf(fmaxf(x0, -clip), clip);
+        const float c = -x0;
+        const float mean = xi + c * (t - s) - c * t - s / st * e;
+        xn[i] = mean + sigma * z[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ EDM edges
+__device__ __forceinline__ float edm_c_in(float s) { return 1.f / sqrtf((1.f - s) * (1.f - s) + s); }
+
+// NCHW fp32 -> NHWC bf16 (ld_out channels, zero padded), scaled by c_in(sigma_b).  One thread per pixel.
+__global__ void __launch_bounds__(256) unet_input_kernel(const float* __restrict__ x, const float* __restrict__ sigma,
+                                                         int scalar_sigma, __nv_bfloat16* __restrict__ out, int n,
+                                                         int c, int hw, int ld_out) {
+    const long long total = 1LL * n * hw;
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+        const int b = static_cast<int>(i / hw), p = static_cast<int>(i % hw);
+        const float cin = edm_c_in(__ldg(sigma + (scalar_sigma ? 0 : b)));
+        __nv_bfloat16* o = out + i * ld_out;
+        for (int ch = 0; ch < ld_out; ++ch) {
+            const float v = ch < c ? cin * x[(1LL * b * c + ch) * hw + p] : 0.f;
+            o[ch] = __float2bfloat16(v);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) unet_output_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
+                                                          int ldf, const float* __restrict__ x,
+                                                          const float* __restrict__ sigma, int scalar_sigma,
+                                                          float* __restrict__ d1, float* __restrict__ d2, int n, int c,
+                                                          int hw) {
+    const long long total = 1LL * n * c * hw;
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+        const int p = static_cast<int>(i % hw);
+        const int ch = static_cast<int>((i / hw) % c);
+        const int b = static_cast<int>(i / (1LL * hw * c));
+        const float s = __ldg(sigma + (scalar_sigma ? 0 : b));
+        const float q = s * s - s + 1.f;
+        const float c_skip1 = (s - 1.f) / q, c_skip2 = sqrtf(s) / q;
+        const float c_out1 = sqrtf(s / q), c_out2 = (1.f - s) / sqrtf(q);
+        const long long fi = (1LL * b * hw + p) * ldf + ch;
+        const float xv = x[i];
+        d1[i] = c_skip1 * xv + c_out1 * f1[fi];
+        d2[i] = c_skip2 * xv + c_out2 * f2[fi];
+    }
+}
+
+__global__ void __launch_bounds__(256) unet_output_bwd_kernel(const float* __restrict__ dd1,
+                                                              const float* __restrict__ dd2,
+                                                              const float* __restrict__ sigma,
+                                                              __nv_bfloat16* __restrict__ df1,
+                                                              __nv_bfloat16* __restrict__ df2, int n, int c, int hw,
+                                                              int ld_out) {
+    const long long total = 1LL * n * hw;
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+        const int b = static_cast<int>(i / hw), p = static_cast<int>(i % hw);
+        const float s = __ldg(sigma + b);
+        const float q = s * s - s + 1.f;
+        const float c_out1 = sqrtf(s / q), c_out2 = (1.f - s) / sqrtf(q);
+        for (int ch = 0; ch < ld_out; ++ch) {
+            float a = 0.f, d = 0.f;
+            if (ch < c) {
+                const long long si = (1LL * b * c + ch) * hw + p;
+                a = c_out1 * dd1[si];
+                d = c_out2 * dd2[si];
+            }
+            df1[i * ld_out + ch] = __float2bfloat16(a);
+            df2[i * ld_out + ch] = __float2bfloat16(d);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+// w [cout][cin][k][k] fp32 -> bf16 [cout][k*k][kpad]; source 2 channels start at pad64(c1).
+__global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __restrict__ w,
+                                                               __nv_bfloat16* __restrict__ o, int cout, int c1, int c2,
+                                                               int kk, int p1, int kpad) {
+    const long long total = 1LL * cout * kk * kpad;
+    const int cin = c1 + c2;
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+        const int kc = static_cast<int>(i % kpad);
+        const int tap = static_cast<int>((i / kpad) % kk);
+        const int co = static_cast<int>(i / (1LL * kpad * kk));
+        int ci = -1;
+        if (kc < c1) ci = kc;
+        else if (kc >= p1 && kc - p1 < c2) ci = c1 + kc - p1;
+        const float v = ci >= 0 ? w[(1LL * co * cin + ci) * kk + tap] : 0.f;
+        o[i] = __float2bfloat16(v);
+    }
+}
+__global__ void __launch_bounds__(256) unpack_conv_wgrad_kernel(const float* __restrict__ g, float* __restrict__ o,
+                                                                int cout, int c1, int c2, int kk, int p1, int kpad,
+                                                                int accumulate) {
+    const int cin = c1 + c2;
+    const long long total = 1LL * cout * cin * kk;
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+        const int tap = static_cast<int>(i % kk);
+        const int ci = static_cast<int>((i / kk) % cin);
+        const int co = static_cast<int>(i / (1LL * kk * cin));
+        const int kc = ci < c1 ? ci : p1 + (ci - c1);
+        const float v = g[(1LL * co * kk + tap) * kpad + kc];
+        o[i] = accumulate ? o[i] + v : v;
+    }
+}
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d,
+                                                            long long n) {
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < n; i += 1LL * gridDim.x * blockDim.x)
+        d[i] = __float2bfloat16(s[i]);
+}
+
+}  // namespace adm
+
+using namespace adm;
+
+extern "C" {
+
+const char* adm_last_error(void) { return get_error(); }
+int adm_version(void) { return 100; }
+long long adm_launch_count(void) { return g_launches.load(); }
+
+int adm_qsample(const float* x0, const float* noise, const float* t, float* x_t, long long batch, long long chw,
+                void* stream) {
+    if (batch <= 0 || chw <= 0) { set_error("qsample: empty input"); return ADM_ERR_SHAPE; }
+    const long long items = (chw & 3) == 0 ? batch * chw / 4 : batch * chw;
+    qsample_kernel<<<ew_grid(items, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x0, noise, t, x_t, batch,
+                                                                                          chw);
+    ADM_CHECK_LAUNCH("qsample");
+    return 0;
+}
+
+int adm_ddm_loss(const float* c_pred, const float* eps_pred, const float* x0, const float* noise, const float* t,
+                 float eps, int weighting, int use_l1, float grad_scale, float* loss_per_sample, float* d_c_pred,
+                 float* d_eps_pred, long long batch, long long chw, void* stream) {
+    if (batch <= 0 || chw <= 0 || batch > 65535) { set_error("ddm_loss: bad batch %lld", batch); return ADM_ERR_SHAPE; }
+    if ((d_c_pred == nullptr) != (d_eps_pred == nullptr)) { set_error("ddm_loss: pass both gradients or neither"); return ADM_ERR_SHAPE; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaMemsetAsync(loss_per_sample, 0, sizeof(float) * batch, s);
+    const long long items = (chw & 3) == 0 ? chw / 4 : chw;
+    long long bx = (items + 255) / 256;
+    const long long cap = (8LL * num_sms() + batch - 1) / batch;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    dim3 grid(static_cast<unsigned>(bx), static_cast<unsigned>(batch));
+    ddm_loss_kernel<<<grid, 256, 0, s>>>(c_pred, eps_pred, x0, noise, t, eps, weighting, use_l1, grad_scale,
+                                         loss_per_sample, d_c_pred, d_eps_pred, batch, chw);
+    ADM_CHECK_LAUNCH("ddm_loss");
+    return 0;
+}
+
+int adm_sampler_step(const void* x, const float* c_pred, const float* eps_pred, void* x_next, double t_cur,
+                     double t_next, double clip, int do_clip, int last, double scale_input, int state_f64,
+                     long long numel, void* stream) {
+    if (numel <= 0) { set_error("sampler_step: empty input"); return ADM_ERR_SHAPE; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int grid = ew_grid(numel, 256, 8);
+    if (state_f64)
+        sampler_step_kernel<double><<<grid, 256, 0, s>>>(static_cast<const double*>(x), c_pred, eps_pred,
+                                                         static_cast<double*>(x_next), t_cur, t_next, clip, do_clip,
+                                                         last, scale_input, numel);
+    else
+        sampler_step_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), c_pred, eps_pred,
+                                                        static_cast<float*>(x_next), t_cur, t_next, clip, do_clip,
+                                                        last, scale_input, numel);
+    ADM_CHECK_LAUNCH("sampler_step");
+    return 0;
+}
+
+int adm_sampler_step_stochastic(const float* x, const float* c_pred, const float* eps_pred, const float* z,
+                                float* x_next, double t_cur, double s, double clip, int do_clip, long long numel,
+                                void* stream) {
+    if (numel <= 0) { set_error("sampler_step_stochastic: empty input"); return ADM_ERR_SHAPE; }
+    sampler_step_stoch_kernel<<<ew_grid(numel, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, c_pred, eps_pred, z, x_next, static_cast<float>(t_cur), static_cast<float>(s), static_cast<float>(clip),
+        do_clip, numel);
+    ADM_CHECK_LAUNCH("sampler_step_stochastic");
+    return 0;
+}
+
+int adm_unet_input(const float* x_nchw, const float* sigma, int sigma_is_scalar, void* x_nhwc, int n, int c, int h,
+                   int w, int ld_out, void* stream) {
+    if (ld_out < c || ld_out % 8) { set_error("unet_input: ld_out must be >= c and a multiple of 8"); return ADM_ERR_SHAPE; }
+    unet_input_kernel<<<ew_grid(1LL * n * h * w, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x_nchw, sigma, sigma_is_scalar, static_cast<__nv_bfloat16*>(x_nhwc), n, c, h * w, ld_out);
+    ADM_CHECK_LAUNCH("unet_input");
+    return 0;
+}
+
+int adm_unet_output(const float* f1, const float* f2, int ldf, const float* x_nchw, const float* sigma,
+                    int sigma_is_scalar, float* d1, float* d2, int n, int c, int h, int w, void* stream) {
+    unet_output_kernel<<<ew_grid(1LL * n * c * h * w, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        f1, f2, ldf, x_nchw, sigma, sigma_is_scalar, d1, d2, n, c, h * w);
+    ADM_CHECK_LAUNCH("unet_output");
+    return 0;
+}
+
+int adm_unet_output_bwd(const float* dd1, const float* dd2, const float* sigma, void* df1, void* df2, int n, int c,
+                        int h, int w, int ld_out, void* stream) {
+    unet_output_bwd_kernel<<<ew_grid(1LL * n * h * w, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        dd1, dd2, sigma, static_cast<__nv_bfloat16*>(df1), static_cast<__nv_bfloat16*>(df2), n, c, h * w, ld_out);
+    ADM_CHECK_LAUNCH("unet_output_bwd");
+    return 0;
+}
+
+int adm_pack_conv_weight(const float* w, void* wpk, int cout, int c1, int c2, int ksize, void* stream) {
+    const int p1 = (c1 + 63) / 64 * 64;
+    const int kpad = p1 + (c2 > 0 ? (c2 + 63) / 64 * 64 : 0);
+    pack_conv_weight_kernel<<<ew_grid(1LL * cout * ksize * ksize * kpad, 256, 8), 256, 0,
+                              static_cast<cudaStream_t>(stream)>>>(w, static_cast<__nv_bfloat16*>(wpk), cout, c1, c2,
+                                                                   ksize * ksize, p1, kpad);
+    ADM_CHECK_LAUNCH("pack_conv_weight");
+    return 0;
+}
+
+int adm_unpack_conv_wgrad(const float* dw_packed, float* dw, int cout, int c1, int c2, int ksize, int accumulate,
+                          void* stream) {
+    const int p1 = (c1 + 63) / 64 * 64;
+    const int kpad = p1 + (c2 > 0 ? (c2 + 63) / 64 * 64 : 0);
+    unpack_conv_wgrad_kernel<<<ew_grid(1LL * cout * (c1 + c2) * ksize * ksize, 256, 8), 256, 0,
+                               static_cast<cudaStream_t>(stream)>>>(dw_packed, dw, cout, c1, c2, ksize * ksize, p1,
+                                                                    kpad, accumulate);
+    ADM_CHECK_LAUNCH("unpack_conv_wgrad");
+    return 0;
+}
+
+int adm_cast_f32_bf16(const float* src, void* dst, long long numel, void* stream) {
+    cast_f32_bf16_kernel<<<ew_grid(numel, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, static_cast<__nv_bfloat16*>(dst), numel);
+    ADM_CHECK_LAUNCH("cast_f32_bf16");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,308 @@
+// Host side of the tcgen05 GEMM engine: tensor-map construction, tile-shape selection, launches, and the C-ABI entry
+// points declared in include/adm_b200.h.  No torch types; raw device pointers + sizes + a cudaStream_t.
+#include "tc_gemm.cuh"
+#include "adm_internal.h"
+#include <cudaTypedefs.h>
+#include <limits.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace adm {
+
+static PFN_cuTensorMapEncodeTiled g_encode = nullptr;
+static int g_num_sms = 0;
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+static int init_driver() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || fn == nullptr) {
+        set_error("cuTensorMapEncodeTiled unavailable: %s", cudaGetErrorString(e));
+        return ADM_ERR_CUDA;
+    }
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+    return 0;
+}
+
+// bf16 tensor map, 128B swizzle, zero OOB fill.  dims/box innermost first; strides in ELEMENTS for dims 1..rank-1.
+static int encode_map(CUtensorMap* m, const void* ptr, int rank, const long long* dims, const long long* strides,
+                      const int* box) {
+    cuuint64_t gd[5];
+    cuuint64_t gs[4];
+    cuuint32_t bx[5];
+    cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) {
+        gd[i] = static_cast<cuuint64_t>(dims[i]);
+        bx[i] = static_cast<cuuint32_t>(box[i]);
+        es[i] = 1;
+        if (i > 0) gs[i - 1] = static_cast<cuuint64_t>(strides[i - 1]) * 2;
+        if (dims[i] <= 0 || box[i] <= 0 || box[i] > 256) {
+            set_error("tensor map: bad dim/box at %d (dim %lld box %d)", i, dims[i], box[i]);
+            return ADM_ERR_SHAPE;
+        }
+    }
+    for (int i = 0; i + 1 < rank; ++i)
+        if (gs[i] % 16 != 0) {
+            set_error("tensor map: stride %d = %llu B not a multiple of 16", i, (unsigned long long)gs[i]);
+            return ADM_ERR_SHAPE;
+        }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) {
+        set_error("tensor map: base pointer not 16 B aligned");
+        return ADM_ERR_SHAPE;
+    }
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gd, gs, bx, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+        return ADM_ERR_CUDA;
+    }
+    return 0;
+}
+
+template <int MODE>
+static int launch(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const GemmParams& p,
+                  cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             GEMM_SMEM_TOTAL);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return ADM_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    const long long tiles = 1LL * p.batches * p.splits * p.m_tiles * p.n_tiles;
+    if (tiles <= 0 || tiles > INT_MAX) {
+        set_error("gemm: bad tile count %lld", tiles);
+        return ADM_ERR_SHAPE;
+    }
+    const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+    tc_gemm_kernel<MODE><<<grid, GEMM_THREADS, GEMM_SMEM_TOTAL, stream>>>(a, a2, b, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("tc_gemm launch: %s", cudaGetErrorString(e));
+        return ADM_ERR_CUDA;
+    }
+    count_launch();
+    return 0;
+}
+
+// Largest multiple of 16 that is <= cap and divides ceil16(n); falls back to the smallest cover.
+static int pick_bn(int n, int cap, int multiple) {
+    const int n16 = (n + multiple - 1) / multiple * multiple;
+    for (int bn = cap / multiple * multiple; bn >= multiple; bn -= multiple)
+        if (n16 % bn == 0) return bn;
+    return multiple;
+}
+
+// Pixel box (bw, bh, bni) covering `pixels` output pixels of an H x W image batch.
+static int pick_box(int n, int h, int w, int pixels, int* bw, int* bh, int* bni) {
+    if (w >= pixels) {
+        if (w % pixels != 0) return -1;
+        *bw = pixels; *bh = 1; *bni = 1;
+        return 0;
+    }
+    if (pixels % w != 0) return -1;
+    *bw = w;
+    const int rows = pixels / w;
+    if (h >= rows) {
+        if (h % rows != 0) return -1;
+        *bh = rows; *bni = 1;
+        return 0;
+    }
+    if (rows % h != 0) return -1;
+    *bh = h;
+    *bni = rows / h;
+    (void)n;
+    return 0;
+}
+
+static inline int pad64(int c) { return (c + 63) / 64 * 64; }
+
+static void init_params(GemmParams* p) {
+    memset(p, 0, sizeof(*p));
+    p->batches = 1; p->splits = 1; p->bdiv = 1; p->ntaps = 1; p->alpha = 1.f;
+    p->tiles_w = 1; p->tiles_h = 1; p->bni = 1; p->bw = 1; p->bh = 1;
+    p->n_split = INT_MAX;
+}
+
+static int nhwc_map(CUtensorMap* m, const void* ptr, int c, long long ld, int n, int h, int w, int bw, int bh,
+                    int bni) {
+    const long long dims[4] = {c, w, h, n};
+    const long long strides[3] = {ld, ld * w, ld * w * h};
+    const int box[4] = {64, bw, bh, bni};
+    return encode_map(m, ptr, 4, dims, strides, box);
+}
+
+}  // namespace adm
+
+using namespace adm;
+
+extern "C" {
+
+int adm_conv_fprop(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int h, int w,
+                   const void* wpk, int nout, int ntaps, void* out, int out_mode, long long ldc, const float* bias,
+                   const void* residual, long long ldr, float alpha, void* stream) {
+    if (int e = init_driver()) return e;
+    if (ntaps != 1 && ntaps != 9) { set_error("conv_fprop: ntaps must be 1 or 9"); return ADM_ERR_SHAPE; }
+    if (c1 <= 0 || c1 % 8 || (x2 && (c2 <= 0 || c2 % 8))) { set_error("conv_fprop: channels must be multiples of 8"); return ADM_ERR_SHAPE; }
+    GemmParams p;
+    init_params(&p);
+    if (pick_box(n, h, w, 128, &p.bw, &p.bh, &p.bni)) { set_error("conv_fprop: unsupported H x W = %d x %d", h, w); return ADM_ERR_SHAPE; }
+    p.H = h; p.W = w;
+    p.tiles_w = w / p.bw; p.tiles_h = h / p.bh;
+    p.m_tiles = p.tiles_w * p.tiles_h * ((n + p.bni - 1) / p.bni);
+    p.bn = pick_bn(nout, 256, 16);
+    p.n_tiles = (nout + p.bn - 1) / p.bn;
+    p.ntaps = ntaps;
+    p.cchunks1 = pad64(c1) / 64;
+    p.cchunks = p.cchunks1 + (x2 ? pad64(c2) / 64 : 0);
+    p.k_total = p.k_iters = ntaps * p.cchunks;
+    p.M = n * h * w; p.N = nout;
+    p.C = out; p.ldc = ldc; p.bias = bias; p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = ldr;
+    p.alpha = alpha; p.out_mode = out_mode;
+    CUtensorMap ma, ma2, mb;
+    if (int e = nhwc_map(&ma, x1, c1, ld1, n, h, w, p.bw, p.bh, p.bni)) return e;
+    if (x2) { if (int e = nhwc_map(&ma2, x2, c2, ld2, n, h, w, p.bw, p.bh, p.bni)) return e; } else ma2 = ma;
+    const long long kpad = 1LL * ntaps * p.cchunks * 64;
+    const long long bd[2] = {kpad, nout};
+    const long long bs[1] = {kpad};
+    const int bb[2] = {64, p.bn};
+    if (int e = encode_map(&mb, wpk, 2, bd, bs, bb)) return e;
+    return launch<GEMM_CONV>(ma, ma2, mb, p, static_cast<cudaStream_t>(stream));
+}
+
+int adm_conv_dgrad(const void* dy, int cout, long long ld_dy, int n, int h, int w, const void* wpk, int kpad,
+                   int ntaps, void* dx, int n_valid, long long ldc, const void* residual, long long ldr, float alpha,
+                   void* stream) {
+    if (int e = init_driver()) return e;
+    if (ntaps != 1 && ntaps != 9) { set_error("conv_dgrad: ntaps must be 1 or 9"); return ADM_ERR_SHAPE; }
+    if (kpad % 64) { set_error("conv_dgrad: kpad must be a multiple of 64"); return ADM_ERR_SHAPE; }
+    GemmParams p;
+    init_params(&p);
+    if (pick_box(n, h, w, 128, &p.bw, &p.bh, &p.bni)) { set_error("conv_dgrad: unsupported H x W = %d x %d", h, w); return ADM_ERR_SHAPE; }
+    p.H = h; p.W = w;
+    p.tiles_w = w / p.bw; p.tiles_h = h / p.bh;
+    p.m_tiles = p.tiles_w * p.tiles_h * ((n + p.bni - 1) / p.bni);
+    p.bn = pick_bn(kpad, 256, 64);
+    p.n_tiles = kpad / p.bn;
+    p.ntaps = ntaps;
+    p.cchunks1 = p.cchunks = pad64(cout) / 64;
+    p.k_total = p.k_iters = ntaps * p.cchunks;
+    p.b_mn = 1;
+    p.M = n * h * w; p.N = n_valid;
+    p.C = dx; p.ldc = ldc; p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = ldr;
+    p.alpha = alpha; p.out_mode = OUT_BF16;
+    CUtensorMap ma, mb;
+    if (int e = nhwc_map(&ma, dy, cout, ld_dy, n, h, w, p.bw, p.bh, p.bni)) return e;
+    const long long bd[3] = {kpad, ntaps, cout};
+    const long long bs[2] = {kpad, 1LL * kpad * ntaps};
+    const int bb[3] = {64, 1, 64};
+    if (int e = encode_map(&mb, wpk, 3, bd, bs, bb)) return e;
+    return launch<GEMM_CONV>(ma, ma, mb, p, static_cast<cudaStream_t>(stream));
+}
+
+int adm_conv_wgrad(const void* dy, int cout, long long ld_dy, const void* x1, int c1, long long ld1, const void* x2,
+                   int c2, long long ld2, int n, int h, int w, int ntaps, float* dw, void* stream) {
+    if (int e = init_driver()) return e;
+    if (ntaps != 1 && ntaps != 9) { set_error("conv_wgrad: ntaps must be 1 or 9"); return ADM_ERR_SHAPE; }
+    GemmParams p;
+    init_params(&p);
+    const long long pixels = 1LL * n * h * w;
+    // K box of 64 pixels; tiny tensors (e.g. Linear with batch < 64) use a short box and rely on zero OOB fill.
+    if (pick_box(n, h, w, 64, &p.bw, &p.bh, &p.bni)) { set_error("conv_wgrad: unsupported H x W = %d x %d", h, w); return ADM_ERR_SHAPE; }
+    p.H = h; p.W = w;
+    p.tiles_w = w / p.bw; p.tiles_h = h / p.bh;
+    p.k_total = p.tiles_w * p.tiles_h * ((n + p.bni - 1) / p.bni);
+    const int kpad = pad64(c1) + (x2 ? pad64(c2) : 0);
+    p.M = cout; p.N = kpad;
+    p.m_tiles = (cout + 127) / 128;
+    p.bn = x2 ? pick_bn(pad64(c1), 256, 64) : pick_bn(kpad, 256, 64);
+    if (x2 && pad64(c2) % p.bn) p.bn = 64;
+    p.n_tiles = kpad / p.bn;
+    p.n_split = x2 ? pad64(c1) : INT_MAX;
+    p.ntaps = ntaps;
+    p.batches = ntaps; p.bdiv = ntaps; p.c_col_lo = kpad;
+    p.a_mn = 1; p.b_mn = 1;
+    // split K (pixels) so that the grid covers the machine a few times over
+    const int base_tiles = ntaps * p.m_tiles * p.n_tiles;
+    int splits = (4 * num_sms() + base_tiles - 1) / base_tiles;
+    if (splits > p.k_total) splits = p.k_total;
+    if (splits < 1) splits = 1;
+    p.k_iters = (p.k_total + splits - 1) / splits;
+    p.splits = (p.k_total + p.k_iters - 1) / p.k_iters;
+    p.C = dw; p.ldc = 1LL * ntaps * kpad; p.out_mode = OUT_F32_ATOMIC;
+    (void)pixels;
+    CUtensorMap ma, mb, mb2;
+    if (int e = nhwc_map(&ma, dy, cout, ld_dy, n, h, w, p.bw, p.bh, p.bni)) return e;
+    if (int e = nhwc_map(&mb, x1, c1, ld1, n, h, w, p.bw, p.bh, p.bni)) return e;
+    if (x2) { if (int e = nhwc_map(&mb2, x2, c2, ld2, n, h, w, p.bw, p.bh, p.bni)) return e; } else mb2 = mb;
+    return launch<GEMM_WGRAD>(ma, mb2, mb, p, static_cast<cudaStream_t>(stream));
+}
+
+int adm_device_error(void) {
+    int v = 0;
+    if (cudaMemcpyFromSymbol(&v, g_device_error, sizeof(int)) != cudaSuccess) return -1;
+    return v;
+}
+
+int adm_gemm_batched(const adm_gemm_desc* d, void* stream) {
+    if (int e = init_driver()) return e;
+    GemmParams p;
+    init_params(&p);
+    p.M = d->m; p.N = d->n;
+    p.m_tiles = (d->m + 127) / 128;
+    p.bn = d->b.mn_major ? pick_bn(d->n, 256, 64) : pick_bn(d->n, 256, 16);
+    p.n_tiles = (d->n + p.bn - 1) / p.bn;
+    p.k_total = (d->k + 63) / 64;
+    p.batches = d->batches; p.bdiv = d->bdiv > 0 ? d->bdiv : 1;
+    p.a_mn = d->a.mn_major; p.b_mn = d->b.mn_major;
+    p.a_c0 = d->a.c0; p.a_c0_lo = d->a.c0_lo; p.a_c1 = d->a.c1; p.a_c1_lo = d->a.c1_lo; p.a_bhi = d->a.bhi; p.a_blo = d->a.blo;
+    p.b_c0 = d->b.c0; p.b_c0_lo = d->b.c0_lo; p.b_c1 = d->b.c1; p.b_c1_lo = d->b.c1_lo; p.b_bhi = d->b.bhi; p.b_blo = d->b.blo;
+    int splits = d->splits > 0 ? d->splits : 1;
+    if (splits > p.k_total) splits = p.k_total;
+    p.k_iters = (p.k_total + splits - 1) / splits;
+    p.splits = (p.k_total + p.k_iters - 1) / p.k_iters;
+    if (p.splits > 1 && d->out_mode != OUT_F32_ATOMIC) { set_error("gemm_batched: split-K needs the atomic fp32 output mode"); return ADM_ERR_SHAPE; }
+    p.C = d->c; p.ldc = d->ldc; p.c_bhi = d->c_bhi; p.c_blo = d->c_blo; p.c_col_lo = d->c_col_lo;
+    p.bias = d->bias; p.residual = static_cast<const __nv_bfloat16*>(d->residual); p.ldr = d->ldr;
+    p.alpha = d->alpha; p.out_mode = d->out_mode;
+    CUtensorMap ma, mb;
+    {
+        const long long dims[3] = {d->a.dim0, d->a.dim1, d->a.dim2};
+        const long long str[2] = {d->a.stride1, d->a.stride2};
+        const int box[3] = {64, d->a.mn_major ? 64 : 128, 1};
+        if (int e = encode_map(&ma, d->a.ptr, 3, dims, str, box)) return e;
+    }
+    {
+        const long long dims[3] = {d->b.dim0, d->b.dim1, d->b.dim2};
+        const long long str[2] = {d->b.stride1, d->b.stride2};
+        const int box[3] = {64, d->b.mn_major ? 64 : p.bn, 1};
+        if (int e = encode_map(&mb, d->b.ptr, 3, dims, str, box)) return e;
+    }
+    return launch<GEMM_PLAIN>(ma, ma, mb, p, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

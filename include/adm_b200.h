@@ -1,0 +1,128 @@
+/*
+ * adm_b200.h — C ABI of libadm_b200.so: the sm_100a kernels behind the DDM-const training step and sampler.
+ *
+ * This is the drop-in boundary for the hot path of zacz08/ADM.  The reference has no FFI of its own for this path
+ * (every op goes through torch.nn.functional -> ATen); its only native-op precedent is
+ * unet/op/upfirdn2d.cpp:8-19 + unet/op/upfirdn2d.py:10-16 (a torch extension taking tensors, launched on the current
+ * stream).  We keep that contract — enqueue on the caller's stream, never synchronise, never allocate — but with a plain
+ * C signature: raw device pointers, sizes, a cudaStream_t passed as void*.  Each entry point below cites the reference
+ * code it replaces.  All functions return 0 on success or a negative ADM_ERR_* code; adm_last_error() returns the
+ * message.  There is no CPU path: every pointer must be a CUDA device pointer.
+ *
+ * Internal activation layout: NHWC bf16 ("pixel-major"): element (n,h,w,c) at ((n*H+h)*W+w)*ld + c, ld >= C, ld % 8 == 0.
+ * Reference layout at the API edge: NCHW fp32 contiguous (unet/uncond_unet.py:616).
+ */
+#ifndef ADM_B200_H
+#define ADM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADM_OK 0
+#define ADM_ERR_SHAPE (-1) /* unsupported / inconsistent shape */
+#define ADM_ERR_DTYPE (-2) /* unsupported dtype or architecture */
+#define ADM_ERR_CUDA (-3)  /* CUDA runtime / driver error */
+
+/* ---------------------------------------------------------------- library */
+const char* adm_last_error(void);      /* message of the last failing call on this thread */
+int adm_device_error(void);            /* nonzero if a kernel hit its deadlock guard (device-side flag) */
+long long adm_launch_count(void);      /* number of kernels this library has launched in this process */
+int adm_version(void);
+
+/* ---------------------------------------------------------------- DDM elementwise (fp32 / fp64, NCHW)
+ * K1  q_sample, ddm/ddm_const.py:284-287 with C = -x0 (:319):  x_t = x0 - t*x0 + sqrt(t)*noise
+ *     x0, noise, x_t: [B, chw] fp32; t: [B] fp32.                                                        */
+int adm_qsample(const float* x0, const float* noise, const float* t, float* x_t, long long batch, long long chw,
+                void* stream);
+
+/* K2  C/eps regression loss, forward + backward in one pass.  ddm/ddm_const.py:335-344,358 + ddm/loss.py:300-312
+ *     (MSE_Loss reduction='sum' over CHW): loss_b = w1_b*SSE(C_pred, -x0) + w2_b*SSE(eps_pred, noise)
+ *     [+ use_l1: w*mean|.| terms and /2, ddm_const.py:345-348],  w1 = (t^2-t+1)/t, w2 = (t^2-t+1)/(1-t+eps) when
+ *     weighting != 0 else 1.  Writes per-sample loss [B] (caller sums / B) and, if non-null, the gradients of
+ *     (sum_b loss_b)/B * grad_scale w.r.t. C_pred and eps_pred.                                           */
+int adm_ddm_loss(const float* c_pred, const float* eps_pred, const float* x0, const float* noise, const float* t,
+                 float eps, int weighting, int use_l1, float grad_scale, float* loss_per_sample, float* d_c_pred,
+                 float* d_eps_pred, long long batch, long long chw, void* stream);
+
+/* K3  deterministic sampler update, ddm/ddm_const.py:452-455 (and final :471-476 when last != 0):
+ *     x0 = x - C*t_cur - eps*sqrt(t_cur); clamp(+-clip); x' = x0 + C*t_next + eps*sqrt(t_next)
+ *     last != 0: x' = (clamp(x', +-clip)/scale_input + 1)/2.   State is fp64 (state_f64 != 0) or fp32.   */
+int adm_sampler_step(const void* x, const float* c_pred, const float* eps_pred, void* x_next, double t_cur,
+                     double t_next, double clip, int do_clip, int last, double scale_input, int state_f64,
+                     long long numel, void* stream);
+/*     stochastic variant, ddm/ddm_const.py:404-413 + :296-303: x0 -> clamp -> C=-x0;
+ *     mean = x + C*(t-s) - C*t - s/sqrt(t)*eps; x' = mean + sqrt(s*(t-s)/t) * z                            */
+int adm_sampler_step_stochastic(const float* x, const float* c_pred, const float* eps_pred, const float* z,
+                                float* x_next, double t_cur, double s, double clip, int do_clip, long long numel,
+                                void* stream);
+
+/* ---------------------------------------------------------------- EDM preconditioning edges
+ * unet/uncond_unet.py:616-628: x_in = c_in(sigma_b) * x, NCHW fp32 -> NHWC bf16 with ld_out channels (zero padded). */
+int adm_unet_input(const float* x_nchw, const float* sigma, int sigma_is_scalar, void* x_nhwc, int n, int c, int h,
+                   int w, int ld_out, void* stream);
+/* unet/uncond_unet.py:621-624,631-632: D1 = c_skip1*x + c_out1*F1, D2 = c_skip2*x + c_out2*F2.
+ * F1/F2: NHWC fp32 [pixels][ldf]; x, D1, D2: NCHW fp32.                                                    */
+int adm_unet_output(const float* f1, const float* f2, int ldf, const float* x_nchw, const float* sigma,
+                    int sigma_is_scalar, float* d1, float* d2, int n, int c, int h, int w, void* stream);
+/* backward of the above w.r.t. F: dF = c_out * dD, NCHW fp32 -> NHWC bf16 [pixels][ld_out] (zero padded). */
+int adm_unet_output_bwd(const float* dd1, const float* dd2, const float* sigma, void* df1, void* df2, int n, int c,
+                        int h, int w, int ld_out, void* stream);
+
+/* ---------------------------------------------------------------- tcgen05 GEMM engine
+ * conv3x3 / conv1x1 forward as implicit GEMM (replaces F.conv2d at unet/uncond_unet.py:100,110 and nn.Conv2d in
+ * decouple1/2 :500-507).  x1 (and optionally x2: fused channel concat, :570-571) NHWC bf16; wpk = packed weights
+ * bf16 [nout][ntaps][pad64(c1)+pad64(c2)] (adm_pack_conv_weight); out [n*h*w][ldc] bf16 (out_mode 0) / fp32 (1);
+ * epilogue: out = alpha*acc + bias[col] + residual[row][col].                                              */
+int adm_conv_fprop(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int h, int w,
+                   const void* wpk, int nout, int ntaps, void* out, int out_mode, long long ldc, const float* bias,
+                   const void* residual, long long ldr, float alpha, void* stream);
+/* data gradient: dx[pix][0:n_valid] = alpha * conv^T(dy) + residual, reading the SAME packed weights through a
+ * (Cin, tap, Cout) view with reversed taps; kpad = padded input channels of the forward conv.              */
+int adm_conv_dgrad(const void* dy, int cout, long long ld_dy, int n, int h, int w, const void* wpk, int kpad,
+                   int ntaps, void* dx, int n_valid, long long ldc, const void* residual, long long ldr, float alpha,
+                   void* stream);
+/* weight gradient, accumulated (atomic fp32) into dw [cout][ntaps][kpad] (packed layout, zero it first). */
+int adm_conv_wgrad(const void* dy, int cout, long long ld_dy, const void* x1, int c1, long long ld1, const void* x2,
+                   int c2, long long ld2, int n, int h, int w, int ntaps, float* dw, void* stream);
+
+/* Generic batched GEMM C[b] = alpha * A[b] * B[b]^T (+bias, +residual) on 3-D bf16 tensor views.  Used for Linear
+ * (unet/uncond_unet.py:62-66), and the attention products (:207-208).  An operand is K-major (dim0 = K) or MN-major
+ * (dim0 = M or N); batch bt splits into b_hi = bt / bdiv, b_lo = bt % bdiv and each operand's start coordinate is
+ * (c0 + b_lo*c0_lo, c1 + b_lo*c1_lo, b_hi*bhi + b_lo*blo).                                                 */
+typedef struct adm_operand {
+    const void* ptr;
+    int mn_major;
+    long long dim0, dim1, dim2;  /* extents, innermost first */
+    long long stride1, stride2;  /* element strides of dim1, dim2 */
+    int c0, c0_lo, c1, c1_lo, bhi, blo;
+} adm_operand;
+typedef struct adm_gemm_desc {
+    adm_operand a, b;
+    int m, n, k;        /* per-batch problem */
+    int batches, bdiv;
+    int splits;         /* split-K factor (needs out_mode 2) */
+    void* c;
+    int out_mode;       /* 0 bf16, 1 fp32, 2 fp32 atomic accumulate */
+    long long ldc, c_bhi, c_blo;
+    int c_col_lo;
+    const float* bias;
+    const void* residual;
+    long long ldr;
+    float alpha;
+} adm_gemm_desc;
+int adm_gemm_batched(const adm_gemm_desc* desc, void* stream);
+
+/* ---------------------------------------------------------------- weight packing (derived bf16 caches of the fp32 masters)
+ * w fp32 [cout][c1+c2][k][k] (reference layout, unet/uncond_unet.py:85) -> bf16 [cout][k*k][pad64(c1)+pad64(c2)] */
+int adm_pack_conv_weight(const float* w, void* wpk, int cout, int c1, int c2, int ksize, void* stream);
+/* inverse for gradients: packed fp32 [cout][k*k][kpad] -> reference layout fp32 [cout][c1+c2][k][k] (overwrite
+ * when accumulate == 0, add otherwise)                                                                    */
+int adm_unpack_conv_wgrad(const float* dw_packed, float* dw, int cout, int c1, int c2, int ksize, int accumulate,
+                          void* stream);
+int adm_cast_f32_bf16(const float* src, void* dst, long long numel, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADM_B200_H */

@@ -1,0 +1,271 @@
+"""Bring-up checks for the CUDA kernels, one case per subprocess so a device-side trap cannot poison later cases.
+
+    python tests/gpu_checks/check_kernels.py            # run every case (each in its own process), write a log
+    python tests/gpu_checks/check_kernels.py CASE       # run one case in-process
+
+This is a development tool for `gpurun`; the graded parity tests live in tests/test_*.py.
+"""
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+CASES = {}
+
+
+def case(fn):
+    CASES[fn.__name__] = fn
+    return fn
+
+
+def _rel(a, b):
+    import torch
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item(), (a - b).abs().max().item()
+
+
+def _report(name, got, ref, tol):
+    r, m = _rel(got, ref)
+    ok = r < tol
+    print(f"  {name}: rel={r:.3e} maxabs={m:.3e} tol={tol:g} {'OK' if ok else 'FAIL'}", flush=True)
+    return ok
+
+
+def _bf(x):
+    import torch
+    return x.to(torch.bfloat16)
+
+
+@case
+def gemm_nt_basic():
+    import torch
+    from adm_b200 import ops
+    torch.manual_seed(0)
+    ok = True
+    for (m, n, k) in [(128, 64, 64), (256, 192, 128), (300, 200, 136), (8, 768, 192), (1024, 1152, 384)]:
+        a = _bf(torch.randn(m, k, device="cuda"))
+        b = _bf(torch.randn(n, k, device="cuda"))
+        bias = torch.randn(n, device="cuda")
+        c = ops.gemm_nt(a, b, bias=bias)
+        torch.cuda.synchronize()
+        ref = a.float() @ b.float().t() + bias
+        ok &= _report(f"nt {m}x{n}x{k}", c, ref, 1e-5)
+        c2 = ops.gemm_nt(a, b, out_dtype=torch.bfloat16)
+        ok &= _report(f"nt bf16 {m}x{n}x{k}", c2, a.float() @ b.float().t(), 5e-3)
+    return ok
+
+
+@case
+def gemm_nn_tn():
+    import torch
+    from adm_b200 import ops
+    torch.manual_seed(1)
+    ok = True
+    for (m, n, k) in [(128, 64, 64), (256, 192, 128), (200, 128, 72), (128, 384, 768)]:
+        a = _bf(torch.randn(m, k, device="cuda"))
+        b = _bf(torch.randn(k, n, device="cuda"))
+        c = ops.gemm_nn(a, b)
+        torch.cuda.synchronize()
+        ok &= _report(f"nn {m}x{n}x{k}", c, a.float() @ b.float(), 1e-5)
+        at = _bf(torch.randn(k, m, device="cuda"))
+        c = ops.gemm_tn(at, b)
+        torch.cuda.synchronize()
+        ok &= _report(f"tn {m}x{n}x{k}", c, at.float().t() @ b.float(), 1e-5)
+        c = ops.gemm_tn(at, b, splits=2)
+        torch.cuda.synchronize()
+        ok &= _report(f"tn split2 {m}x{n}x{k}", c, at.float().t() @ b.float(), 1e-5)
+    return ok
+
+
+def _conv_ref(x_nhwc, w, bias=None, residual=None, pad=1):
+    import torch
+    import torch.nn.functional as F
+    y = F.conv2d(x_nhwc.float().permute(0, 3, 1, 2), w.float(), bias, padding=pad).permute(0, 2, 3, 1)
+    if residual is not None:
+        y = y + residual.float()
+    return y
+
+
+@case
+def conv_fprop_3x3():
+    import torch
+    from adm_b200 import ops
+    torch.manual_seed(2)
+    ok = True
+    for (n, hw, cin, cout) in [(2, 16, 64, 192), (1, 32, 128, 96), (8, 8, 192, 384), (16, 4, 64, 192), (3, 16, 64, 48),
+                               (2, 32, 8, 192)]:
+        x = _bf(torch.randn(n, hw, hw, cin, device="cuda"))
+        w = _bf(torch.randn(cout, cin, 3, 3, device="cuda") / (3 * cin ** 0.5)).float()
+        bias = torch.randn(cout, device="cuda")
+        res = _bf(torch.randn(n, hw, hw, cout, device="cuda"))
+        wpk = ops.pack_conv_weight(w)
+        y = ops.conv_fprop(x, wpk, bias=bias, residual=res, out_dtype=torch.float32)
+        torch.cuda.synchronize()
+        ok &= _report(f"fprop n{n} {hw}x{hw} {cin}->{cout}", y, _conv_ref(x, w, bias, res), 1e-5)
+        y = ops.conv_fprop(x, wpk, bias=bias)
+        ok &= _report(f"fprop bf16 n{n} {hw}x{hw} {cin}->{cout}", y, _conv_ref(x, w, bias), 5e-3)
+    return ok
+
+
+@case
+def conv_fprop_concat_1x1():
+    import torch
+    from adm_b200 import ops
+    torch.manual_seed(3)
+    ok = True
+    n, hw, c1, c2, cout = 2, 16, 128, 64, 192
+    x1 = _bf(torch.randn(n, hw, hw, c1, device="cuda"))
+    x2 = _bf(torch.randn(n, hw, hw, c2, device="cuda"))
+    for k in (3, 1):
+        w = _bf(torch.randn(cout, c1 + c2, k, k, device="cuda") / (k * (c1 + c2) ** 0.5)).float()
+        wpk = ops.pack_conv_weight(w, c1, c2)
+        y = ops.conv_fprop(x1, wpk, x2=x2, out_dtype=torch.float32)
+        torch.cuda.synchronize()
+        ref = _conv_ref(torch.cat([x1, x2], -1), w, pad=k // 2)
+        ok &= _report(f"concat k{k}", y, ref, 1e-5)
+    # channel-slice view as input (ld > C)
+    big = _bf(torch.randn(n, hw, hw, c1 + c2, device="cuda"))
+    w = _bf(torch.randn(cout, c2, 1, 1, device="cuda") / c2 ** 0.5).float()
+    y = ops.conv_fprop(big[..., c1:], ops.pack_conv_weight(w), out_dtype=torch.float32)
+    ok &= _report("slice view 1x1", y, _conv_ref(big[..., c1:], w, pad=0), 1e-5)
+    # tiny cout (out_conv: 192 -> 3)
+    w = _bf(torch.randn(3, c1, 3, 3, device="cuda") / (3 * c1 ** 0.5)).float()
+    y = ops.conv_fprop(x1, ops.pack_conv_weight(w), out_dtype=torch.float32)
+    ok &= _report("cout=3", y, _conv_ref(x1, w), 1e-5)
+    return ok
+
+
+@case
+def conv_dgrad_wgrad():
+    import torch
+    import torch.nn.functional as F
+    from adm_b200 import ops
+    torch.manual_seed(4)
+    ok = True
+    for (n, hw, cin, cout, k) in [(2, 16, 64, 128, 3), (8, 8, 192, 384, 3), (16, 4, 128, 64, 3), (2, 32, 64, 192, 1),
+                                  (4, 16, 128, 3, 3)]:
+        x = _bf(torch.randn(n, hw, hw, cin, device="cuda"))
+        w = _bf(torch.randn(cout, cin, k, k, device="cuda") / (k * cin ** 0.5)).float()
+        ldy = (cout + 7) // 8 * 8
+        dy_full = _bf(torch.randn(n, hw, hw, ldy, device="cuda"))
+        dy = dy_full[..., :cout]
+        xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+        wr = w.clone().requires_grad_(True)
+        yr = F.conv2d(xr, wr, padding=k // 2)
+        yr.backward(dy.float().permute(0, 3, 1, 2))
+        wpk = ops.pack_conv_weight(w)
+        dx = ops.conv_dgrad(dy, wpk, n_valid=cin)
+        torch.cuda.synchronize()
+        ok &= _report(f"dgrad n{n} {hw} {cin}->{cout} k{k}", dx, xr.grad.permute(0, 2, 3, 1), 5e-3)
+        dwp = ops.conv_wgrad(dy, x, ntaps=k * k)
+        dw = ops.unpack_conv_wgrad(dwp, cin, 0, k)
+        torch.cuda.synchronize()
+        ok &= _report(f"wgrad n{n} {hw} {cin}->{cout} k{k}", dw, wr.grad, 1e-4)
+    # concat wgrad
+    n, hw, c1, c2, cout = 2, 16, 128, 64, 192
+    x1 = _bf(torch.randn(n, hw, hw, c1, device="cuda"))
+    x2 = _bf(torch.randn(n, hw, hw, c2, device="cuda"))
+    dy = _bf(torch.randn(n, hw, hw, cout, device="cuda"))
+    wr = torch.zeros(cout, c1 + c2, 3, 3, device="cuda", requires_grad=True)
+    F.conv2d(torch.cat([x1, x2], -1).float().permute(0, 3, 1, 2), wr, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    dw = ops.unpack_conv_wgrad(ops.conv_wgrad(dy, x1, x2=x2, ntaps=9), c1, c2, 3)
+    torch.cuda.synchronize()
+    ok &= _report("wgrad concat", dw, wr.grad, 1e-4)
+    return ok
+
+
+@case
+def elementwise():
+    import torch
+    from adm_b200 import ops
+    torch.manual_seed(5)
+    ok = True
+    b = 8
+    x0 = torch.rand(b, 3, 32, 32, device="cuda") * 2 - 1
+    noise = torch.randn_like(x0)
+    t = torch.rand(b, device="cuda") * (1 - 1e-4) + 1e-4
+    tt = t.reshape(b, 1, 1, 1)
+    xt = ops.qsample(x0, noise, t)
+    ref = x0 + (-1 * x0) * tt + torch.sqrt(tt) * noise
+    ok &= bool((xt == ref).all().item())
+    print("  qsample bit-exact:", bool((xt == ref).all().item()), flush=True)
+    cp = torch.randn_like(x0).requires_grad_(True)
+    ep = torch.randn_like(x0).requires_grad_(True)
+    for use_l1 in (False, True):
+        w1 = (t ** 2 - t + 1) / t
+        w2 = (t ** 2 - t + 1) / (1 - t + 1e-4)
+        ls = w1 * ((cp - (-x0)) ** 2).sum([1, 2, 3]) + w2 * ((ep - noise) ** 2).sum([1, 2, 3])
+        if use_l1:
+            ls = ls + w1 * (cp + x0).abs().mean([1, 2, 3]) + w2 * (ep - noise).abs().mean([1, 2, 3])
+            ls = ls / 2
+        loss_ref = ls.sum() / b
+        gc, ge = torch.autograd.grad(loss_ref, [cp, ep])
+        lps, dc, de = ops.ddm_loss(cp.detach(), ep.detach(), x0, noise, t, 1e-4, True, use_l1)
+        ok &= _report(f"loss l1={use_l1}", lps, ls.detach(), 1e-5)
+        ok &= _report(f"dC l1={use_l1}", dc, gc, 1e-5)
+        ok &= _report(f"dEps l1={use_l1}", de, ge, 1e-5)
+    x = torch.randn(b, 3, 32, 32, device="cuda", dtype=torch.float64)
+    c, e = cp.detach(), ep.detach()
+    tc, tn = 0.7778, 0.6667
+    x0r = (x - c.double() * tc - e.double() * tc ** 0.5).clamp(-1, 1)
+    ref = x0r + c.double() * tn + e.double() * tn ** 0.5
+    ok &= _report("sampler f64", ops.sampler_step(x, c, e, tc, tn), ref, 1e-12)
+    ok &= _report("sampler f64 last", ops.sampler_step(x, c, e, tc, 0.0, last=True), (x0r.clamp(-1, 1) + 1) * 0.5, 1e-12)
+    ok &= _report("sampler f32", ops.sampler_step(x.float(), c, e, tc, tn), ref, 1e-6)
+    sig = t
+    xin = ops.unet_input(x0, sig)
+    cin = 1 / torch.sqrt((1 - tt) ** 2 + tt)
+    ok &= _report("unet_input", xin[..., :3], (cin * x0).permute(0, 2, 3, 1), 5e-3)
+    ok &= bool((xin[..., 3:] == 0).all().item())
+    f1 = torch.randn(b, 32, 32, 4, device="cuda")
+    f2 = torch.randn(b, 32, 32, 4, device="cuda")
+    d1, d2 = ops.unet_output(f1, f2, x0, sig)
+    q = tt ** 2 - tt + 1
+    r1 = (tt - 1) / q * x0 + torch.sqrt(tt / q) * f1[..., :3].permute(0, 3, 1, 2)
+    r2 = tt.sqrt() / q * x0 + (1 - tt) / q.sqrt() * f2[..., :3].permute(0, 3, 1, 2)
+    ok &= _report("unet_output D1", d1, r1, 1e-6)
+    ok &= _report("unet_output D2", d2, r2, 1e-6)
+    g1, g2 = ops.unet_output_bwd(d1, d2, sig)
+    ok &= _report("unet_output_bwd", g1[..., :3], (torch.sqrt(tt / q) * d1).permute(0, 2, 3, 1), 5e-3)
+    return ok
+
+
+def main():
+    if len(sys.argv) > 1:
+        import torch
+        from adm_b200 import _lib
+        name = sys.argv[1]
+        t0 = time.time()
+        ok = CASES[name]()
+        torch.cuda.synchronize()
+        derr = _lib.load().adm_device_error()
+        print(f"[{name}] {'PASS' if ok and derr == 0 else 'FAIL'} device_error={derr} ({time.time() - t0:.1f}s)",
+              flush=True)
+        sys.exit(0 if ok and derr == 0 else 1)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    log = open(os.path.join(ROOT, "gpurun_out", "check_kernels.log"), "w")
+    failed = []
+    for name in CASES:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), name], capture_output=True, text=True,
+                               timeout=300)
+            out = r.stdout + r.stderr[-3000:]
+            code = r.returncode
+        except subprocess.TimeoutExpired as e:
+            out = f"[{name}] TIMEOUT\n{e.stdout or ''}"
+            code = -9
+        log.write(out + "\n")
+        log.flush()
+        print(out, flush=True)
+        if code != 0:
+            failed.append(name)
+    print("FAILED:", failed, flush=True)
+    log.write(f"FAILED: {failed}\n")
+    sys.exit(1 if failed else 0)
+
+
+if __name__ == "__main__":
+    main()
