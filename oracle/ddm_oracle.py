@@ -304,8 +304,9 @@ def p_losses(model_fn: Callable, x_start, t, noise, eps=1e-4, weighting=True, us
     c_pred, noise_pred = model_fn(x_noisy, t, **model_kwargs)
     loss, ls = ddm_loss(c_pred, noise_pred, x_start, noise, t, eps, weighting, use_l1)
     n = x_start[0].numel() * x_start.shape[0]
+    # ddm_const.py:359-363 — note the reference divides the (already batch-averaged) loss by B*C*H*W again
     return loss, {"train/loss_simple": ls.detach().sum() / n, "train/loss_vlb": torch.zeros(()),
-                  "train/loss": loss.detach() / x_start[0].numel()}
+                  "train/loss": loss.detach() / n}
 
 
 def t_steps_deterministic(n, sigma_min=1e-2, sigma_max=1.0):

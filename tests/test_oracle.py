@@ -1,0 +1,84 @@
+"""CPU: pins oracle/ddm_oracle.py against the golden vectors recorded from the unmodified reference
+(tests/golden/make_golden.py)."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import ddm_oracle as O
+from tests.golden.make_golden import TINY, CIFAR, inputs, checksum
+
+
+def _load(golden_dir, name):
+    return json.load(open(os.path.join(golden_dir, name)))
+
+
+def _close(a, b, rel=1e-5):
+    assert abs(a - b) <= rel * max(1.0, abs(b)), (a, b)
+
+
+def test_state_dict_layout_matches_reference(golden_dir):
+    for name, cfg in (("unet_tiny.json", TINY), ("unet_cifar.json", CIFAR)):
+        g = _load(golden_dir, name)
+        shapes, _ = O.unet_layout(cfg)
+        assert {k: list(v) for k, v in shapes.items()} == g["state_dict_shapes"]
+    assert len(_load(golden_dir, "unet_cifar.json")["state_dict_shapes"]) == 829
+
+
+def test_tiny_step_matches_reference(golden_dir):
+    g = _load(golden_dir, "unet_tiny.json")
+    sd = {k: v.requires_grad_(not k.endswith("resample_filter")) for k, v in O.make_state_dict(TINY, 0).items()}
+    x, t, noise, aug = inputs(TINY, g["batch"], 1)
+    fn = lambda xx, tt, **kw: O.edm_precond_forward(sd, TINY, xx, tt, **kw)
+    xn = O.q_sample(x, noise, t)
+    c_pred, e_pred = fn(xn, t, augment_labels=aug)
+    loss, ls = O.ddm_loss(c_pred, e_pred, x, noise, t)
+    _close(loss.item(), g["loss"])
+    for got, ref in ((checksum(c_pred), g["c_pred"]), (checksum(e_pred), g["eps_pred"])):
+        _close(got["sum"], ref["sum"], 1e-4)
+        _close(got["abssum"], ref["abssum"])
+        for a, b in zip(got["probes"], ref["probes"]):
+            _close(a, b, 1e-4)
+    loss.backward()
+    for name, ref in g["grad_norms"].items():
+        _close(sd[name].grad.double().norm().item(), ref, 1e-4)
+
+
+def test_tiny_sampler_matches_reference(golden_dir):
+    g = _load(golden_dir, "unet_tiny.json")
+    ref = torch.load(os.path.join(golden_dir, "sample_tiny.pt"))
+    sd = O.make_state_dict(TINY, 0)
+    gen = torch.Generator().manual_seed(7)
+    x_T = torch.randn(g["batch"], 3, 16, 16, generator=gen, dtype=torch.float64)
+    with torch.no_grad():
+        img = O.sample_fn_d(lambda xx, tt: O.edm_precond_forward(sd, TINY, xx, tt), x_T, g["sample_steps"])
+    assert img.dtype == torch.float64 and img.min() >= 0 and img.max() <= 1
+    assert (img - ref).abs().max().item() < 1e-5
+
+
+def test_cifar_forward_matches_reference(golden_dir):
+    g = _load(golden_dir, "unet_cifar.json")
+    sd = O.make_state_dict(CIFAR, 0)
+    x, t, noise, aug = inputs(CIFAR, g["batch"], 1)
+    with torch.no_grad():
+        c_pred, e_pred = O.edm_precond_forward(sd, CIFAR, O.q_sample(x, noise, t), t, augment_labels=aug)
+        loss, _ = O.ddm_loss(c_pred, e_pred, x, noise, t)
+    _close(loss.item(), g["loss"])
+    _close(checksum(c_pred)["abssum"], g["c_pred"]["abssum"])
+    _close(checksum(e_pred)["abssum"], g["eps_pred"]["abssum"])
+
+
+def test_const2_plumbing_crosscheck(golden_dir):
+    """The importable sibling class reproduced the restated step exactly when given its three formulas."""
+    g = _load(golden_dir, "const2_step.json")
+    _close(g["loss_restated"], g["loss_ref"], 1e-6)
+    _close(g["loss_dict"]["train/loss"], g["loss_ref"] / (4 * 3 * 16 * 16), 1e-5)
+
+
+def test_t_steps():
+    ts = O.t_steps_deterministic(10)
+    assert ts.shape == (11,) and ts[0] == 1.0 and ts[-1] == 0.0
+    assert abs(ts[-2].item() - 1e-4) < 1e-12  # sigma_min ** 2 (ddm_const.py:429)
+    assert abs(ts[1].item() - (1 + (1e-4 - 1) / 9)) < 1e-12
+    assert O.t_steps_deterministic(1).tolist() == [1.0, 0.0]  # documented deviation from the reference's NaN
