@@ -18,6 +18,7 @@ c_i = C.c_int
 c_ll = C.c_longlong
 c_f = C.c_float
 c_d = C.c_double
+c_ull = C.c_ulonglong
 
 
 class Operand(C.Structure):
@@ -50,9 +51,27 @@ SIGNATURES = {
     "adm_conv_dgrad": (c_i, [c_p, c_i, c_ll, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_i, c_ll, c_p, c_ll, c_f, c_p]),
     "adm_conv_wgrad": (c_i, [c_p, c_i, c_ll, c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_i, c_p, c_p]),
     "adm_gemm_batched": (c_i, [C.POINTER(GemmDesc), c_p]),
-    "adm_pack_conv_weight": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
-    "adm_unpack_conv_wgrad": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "adm_pack_conv_weight": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "adm_unpack_conv_wgrad": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "adm_cast_f32_bf16": (c_i, [c_p, c_p, c_ll, c_p]),
+    "adm_chan_sums": (c_i, [c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_p, c_p]),
+    "adm_gn_apply": (c_i, [c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_ll, c_i,
+                           c_f, c_ull, c_i, c_p, c_ll, c_p]),
+    "adm_gn_bwd": (c_i, [c_p, c_ll, c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p,
+                         c_ll, c_i, c_f, c_ull, c_i, c_p, c_p, c_p, c_p, c_ll, c_p, c_ll, c_i, c_p, c_ll, c_p, c_ll,
+                         c_p]),
+    "adm_col_sums": (c_i, [c_p, c_ll, c_ll, c_i, c_p, c_p]),
+    "adm_add_bf16": (c_i, [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_p, c_ll, c_ll, c_i, c_p]),
+    "adm_resample": (c_i, [c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_p, c_ll, c_p]),
+    "adm_silu": (c_i, [c_p, c_p, c_p, c_ll, c_p]),
+    "adm_silu_bwd": (c_i, [c_p, c_p, c_p, c_p, c_ll, c_p]),
+    "adm_softmax_fwd": (c_i, [c_p, c_p, c_ll, c_i, c_p]),
+    "adm_softmax_bwd": (c_i, [c_p, c_p, c_p, c_f, c_ll, c_i, c_p]),
+    "adm_spatial_att_fwd": (c_i, [c_p, c_ll, c_p, c_ll, c_p, c_p, c_i, c_i, c_i, c_p, c_ll, c_p, c_p, c_p]),
+    "adm_spatial_att_bwd": (c_i, [c_p, c_ll, c_p, c_ll, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_ll, c_p, c_p, c_p]),
+    "adm_sq_norm": (c_i, [c_p, c_ll, c_p, c_p]),
+    "adm_adamw": (c_i, [c_p, c_p, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_p, c_p, c_p]),
+    "adm_set_seed_counter": (c_i, [c_p]),
 }
 
 

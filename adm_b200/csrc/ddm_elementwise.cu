@@ -245,7 +245,8 @@ __global__ void __launch_bounds__(256) unet_output_bwd_kernel(const float* __res
 // w [cout][cin][k][k] fp32 -> bf16 [cout][k*k][kpad]; source 2 channels start at pad64(c1).
 __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __restrict__ w,
                                                                __nv_bfloat16* __restrict__ o, int cout, int c1, int c2,
-                                                               int kk, int p1, int kpad) {
+                                                               int kk, int p1, int kpad,
+                                                               const int* __restrict__ row_perm) {
     const long long total = 1LL * cout * kk * kpad;
     const int cin = c1 + c2;
     for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
@@ -255,13 +256,14 @@ __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __re
         int ci = -1;
         if (kc < c1) ci = kc;
         else if (kc >= p1 && kc - p1 < c2) ci = c1 + kc - p1;
-        const float v = ci >= 0 ? w[(1LL * co * cin + ci) * kk + tap] : 0.f;
+        const int src = row_perm != nullptr ? row_perm[co] : co;  // packed row co holds reference row src
+        const float v = ci >= 0 ? w[(1LL * src * cin + ci) * kk + tap] : 0.f;
         o[i] = __float2bfloat16(v);
     }
 }
 __global__ void __launch_bounds__(256) unpack_conv_wgrad_kernel(const float* __restrict__ g, float* __restrict__ o,
                                                                 int cout, int c1, int c2, int kk, int p1, int kpad,
-                                                                int accumulate) {
+                                                                int accumulate, const int* __restrict__ row_perm) {
     const int cin = c1 + c2;
     const long long total = 1LL * cout * cin * kk;
     for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
@@ -270,7 +272,8 @@ __global__ void __launch_bounds__(256) unpack_conv_wgrad_kernel(const float* __r
         const int co = static_cast<int>(i / (1LL * kk * cin));
         const int kc = ci < c1 ? ci : p1 + (ci - c1);
         const float v = g[(1LL * co * kk + tap) * kpad + kc];
-        o[i] = accumulate ? o[i] + v : v;
+        const long long dst = row_perm != nullptr ? ((1LL * row_perm[co] * cin + ci) * kk + tap) : i;
+        o[dst] = accumulate ? o[dst] + v : v;
     }
 }
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d,
@@ -372,23 +375,24 @@ int adm_unet_output_bwd(const float* dd1, const float* dd2, const float* sigma, 
     return 0;
 }
 
-int adm_pack_conv_weight(const float* w, void* wpk, int cout, int c1, int c2, int ksize, void* stream) {
+int adm_pack_conv_weight(const float* w, void* wpk, int cout, int c1, int c2, int ksize, const int* row_perm,
+                         void* stream) {
     const int p1 = (c1 + 63) / 64 * 64;
     const int kpad = p1 + (c2 > 0 ? (c2 + 63) / 64 * 64 : 0);
     pack_conv_weight_kernel<<<ew_grid(1LL * cout * ksize * ksize * kpad, 256, 8), 256, 0,
                               static_cast<cudaStream_t>(stream)>>>(w, static_cast<__nv_bfloat16*>(wpk), cout, c1, c2,
-                                                                   ksize * ksize, p1, kpad);
+                                                                   ksize * ksize, p1, kpad, row_perm);
     ADM_CHECK_LAUNCH("pack_conv_weight");
     return 0;
 }
 
 int adm_unpack_conv_wgrad(const float* dw_packed, float* dw, int cout, int c1, int c2, int ksize, int accumulate,
-                          void* stream) {
+                          const int* row_perm, void* stream) {
     const int p1 = (c1 + 63) / 64 * 64;
     const int kpad = p1 + (c2 > 0 ? (c2 + 63) / 64 * 64 : 0);
     unpack_conv_wgrad_kernel<<<ew_grid(1LL * cout * (c1 + c2) * ksize * ksize, 256, 8), 256, 0,
                                static_cast<cudaStream_t>(stream)>>>(dw_packed, dw, cout, c1, c2, ksize * ksize, p1,
-                                                                    kpad, accumulate);
+                                                                    kpad, accumulate, row_perm);
     ADM_CHECK_LAUNCH("unpack_conv_wgrad");
     return 0;
 }

@@ -1,0 +1,724 @@
+// GroupNorm family on NHWC bf16 (HBM-bound), replacing torch.nn.functional.group_norm + silu + addcmul + dropout +
+// the depthwise 2x2 resample of the reference (unet/uncond_unet.py:128, :191-200, :105-108).
+//
+//   K7  chan_sums      : per-(n, c) sum and sum-of-squares over H*W (optionally over a fused channel concat of two
+//                        tensors).  Group statistics are derived from these on the fly by the consumers.
+//   K7b gn_apply       : y = act(x * A[n,c] + B[n,c]) with A/B folding mean, rstd, gamma, beta and the adaptive
+//                        (1 + scale), shift of UNetBlock; optional Philox dropout; optional 2x2 avg-pool / nearest-up
+//                        fused into the store.
+//   K8  gn_bwd_reduce  : S1[n,c] = sum_p dv, S2[n,c] = sum_p dv * xhat        (dv = grad at the pre-activation)
+//       gn_bwd_params  : dgamma, dbeta, d(scale), d(shift) from S1/S2
+//       gn_bwd_apply   : dx = rstd * (dv*g' - mean_g(dv*g') - xhat * mean_g(dv*g'*xhat)) (+ residual gradient)
+//   plus col_sums (bias gradients), resample (skip path) and silu for the embedding MLP.
+// All kernels process 8 channels (one 16-byte vector) per thread and keep a thread on a fixed channel vector so the
+// per-channel partials live in registers.
+#include "adm_internal.h"
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace adm {
+
+struct Vec8 {
+    float v[8];
+};
+__device__ __forceinline__ Vec8 load8(const __nv_bfloat16* p) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    Vec8 r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+        r.v[2 * i] = __bfloat162float(b.x);
+        r.v[2 * i + 1] = __bfloat162float(b.y);
+    }
+    return r;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const Vec8& r) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 b = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&b);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Philox4x32-10 (counter-based, stateless): 128-bit counter, 64-bit key -> 4 x 32 random bits.
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+// keep-mask scale for the 8 channels of vector `vec_index`: 0 or 1/(1-p).
+__device__ __forceinline__ void dropout_scales(unsigned long long seed, unsigned long long vec_index, float p,
+                                               float (&s)[8]) {
+    const uint4 r = philox4x32(make_uint4(static_cast<uint32_t>(vec_index), static_cast<uint32_t>(vec_index >> 32),
+                                          0x5eedu, 0u),
+                               make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    const float keep = 1.f / (1.f - p);
+    const uint32_t thr = static_cast<uint32_t>(p * 65536.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        s[2 * i] = ((w[i] & 0xFFFFu) >= thr) ? keep : 0.f;
+        s[2 * i + 1] = ((w[i] >> 16) >= thr) ? keep : 0.f;
+    }
+}
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
+__device__ __forceinline__ float silu_grad(float v) {
+    const float s = 1.f / (1.f + __expf(-v));
+    return s * (1.f + v * (1.f - s));
+}
+
+static inline int threads_for(int nvec) {  // a multiple of nvec (threads keep a fixed channel vector), <= 256
+    if (nvec >= 256) return 256;
+    return nvec * (256 / nvec);
+}
+
+// ------------------------------------------------------------------------------------------------ chan_sums
+// grid (chunks, N); sums [N][C][2] accumulated atomically (zeroed by the host wrapper).
+__global__ void __launch_bounds__(256) chan_sums_kernel(const __nv_bfloat16* __restrict__ x1, int c1, long long ld1,
+                                                        const __nv_bfloat16* __restrict__ x2, int c2, long long ld2,
+                                                        int hw, float* __restrict__ sums) {
+    const int C = c1 + c2, V = C >> 3, V1 = c1 >> 3;
+    const int n = blockIdx.y;
+    const int tpv = blockDim.x / V;  // pixel lanes (V <= blockDim) ; for V > blockDim handled by the loop below
+    extern __shared__ float sm[];    // [blockDim][16]
+    if (V <= static_cast<int>(blockDim.x)) {
+        const int v = threadIdx.x % V, lane = threadIdx.x / V;
+        float s[8], q[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+        if (lane < tpv) {
+            const __nv_bfloat16* base = v < V1 ? x1 + 1LL * n * hw * ld1 + v * 8 : x2 + 1LL * n * hw * ld2 + (v - V1) * 8;
+            const long long ld = v < V1 ? ld1 : ld2;
+            for (int p = blockIdx.x * tpv + lane; p < hw; p += gridDim.x * tpv) {
+                const Vec8 a = load8(base + p * ld);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { s[i] += a.v[i]; q[i] += a.v[i] * a.v[i]; }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sm[threadIdx.x * 16 + i] = s[i]; sm[threadIdx.x * 16 + 8 + i] = q[i]; }
+        __syncthreads();
+        // thread t < V*8 reduces channel t over the pixel lanes
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const int vv = c >> 3, i = c & 7;
+            float a = 0.f, b = 0.f;
+            for (int l = 0; l < tpv; ++l) {
+                a += sm[(l * V + vv) * 16 + i];
+                b += sm[(l * V + vv) * 16 + 8 + i];
+            }
+            atomicAdd(sums + (1LL * n * C + c) * 2, a);
+            atomicAdd(sums + (1LL * n * C + c) * 2 + 1, b);
+        }
+    } else {
+        // wide tensors (C > 2048): each thread walks several channel vectors
+        for (int v = threadIdx.x; v < V; v += blockDim.x) {
+            float s[8], q[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+            const __nv_bfloat16* base = v < V1 ? x1 + 1LL * n * hw * ld1 + v * 8 : x2 + 1LL * n * hw * ld2 + (v - V1) * 8;
+            const long long ld = v < V1 ? ld1 : ld2;
+            for (int p = blockIdx.x; p < hw; p += gridDim.x) {
+                const Vec8 a = load8(base + p * ld);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { s[i] += a.v[i]; q[i] += a.v[i] * a.v[i]; }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                atomicAdd(sums + (1LL * n * C + v * 8 + i) * 2, s[i]);
+                atomicAdd(sums + (1LL * n * C + v * 8 + i) * 2 + 1, q[i]);
+            }
+        }
+    }
+}
+
+// Per-channel affine of sample n into shared memory: y = x * A[c] + B[c]; also mean/rstd per channel's group.
+// sums: [N][C][2]; params: [N][2C] (scale | shift) or null.
+__device__ __forceinline__ void group_affine_to_smem(const float* __restrict__ sums, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, const float* __restrict__ params,
+                                                     long long ldp, int n, int C, int G, int hw, float eps, float* sA, float* sB,
+                                                     float* sMean, float* sRstd) {
+    const int cpg = C / G;
+    const float inv_cnt = 1.f / (static_cast<float>(cpg) * static_cast<float>(hw));
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        float s = 0.f, q = 0.f;
+        for (int j = 0; j < cpg; ++j) {
+            s += sums[(1LL * n * C + g * cpg + j) * 2];
+            q += sums[(1LL * n * C + g * cpg + j) * 2 + 1];
+        }
+        const float mean = s * inv_cnt;
+        const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        const float ga = gamma[c], be = beta[c];
+        float a = rstd * ga, b = be - mean * rstd * ga;
+        if (params != nullptr) {
+            const float sc = 1.f + params[n * ldp + c], sh = params[n * ldp + C + c];
+            a *= sc;
+            b = b * sc + sh;
+        }
+        sA[c] = a;
+        sB[c] = b;
+        if (sMean != nullptr) { sMean[c] = mean; sRstd[c] = rstd; }
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------ gn_apply (forward)
+// resample: 0 none, 1 down (2x2 average of the activated values), 2 up (nearest x2).  grid (chunks, N).
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int c1, long long ld1,
+                                                       const __nv_bfloat16* __restrict__ x2, int c2, long long ld2,
+                                                       int H, int W, int G, float eps, const float* __restrict__ sums,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ params, long long ldp, int act, float drop_p,
+                                                       unsigned long long seed, int resample,
+                                                       __nv_bfloat16* __restrict__ out, long long ldo,
+                                                       const unsigned long long* __restrict__ seed_dev) {
+    if (seed_dev != nullptr) seed += *seed_dev * 0x9E3779B97F4A7C15ull;
+
+    extern __shared__ float sm[];
+    const int C = c1 + c2, V = C >> 3, V1 = c1 >> 3;
+    float* sA = sm;
+    float* sB = sm + C;
+    const int n = blockIdx.y, hw = H * W;
+    group_affine_to_smem(sums, gamma, beta, params, ldp, n, C, G, hw, eps, sA, sB, nullptr, nullptr);
+    const int Ho = resample == 1 ? H / 2 : (resample == 2 ? H * 2 : H);
+    const int Wo = resample == 1 ? W / 2 : (resample == 2 ? W * 2 : W);
+    const int iter_hw = resample == 1 ? Ho * Wo : hw;  // iterate over output pixels when pooling, input otherwise
+    const long long total = 1LL * iter_hw * V;
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+        const int v = static_cast<int>(i % V);
+        const int p = static_cast<int>(i / V);
+        const __nv_bfloat16* base = v < V1 ? x1 + 1LL * n * hw * ld1 + v * 8 : x2 + 1LL * n * hw * ld2 + (v - V1) * 8;
+        const long long ld = v < V1 ? ld1 : ld2;
+        float a[8], b[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a[j] = sA[v * 8 + j]; b[j] = sB[v * 8 + j]; }
+        Vec8 o;
+        if (resample == 1) {
+            const int ho = p / Wo, wo = p % Wo;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] = 0.f;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const int pi = (2 * ho + (d >> 1)) * W + 2 * wo + (d & 1);
+                const Vec8 xv = load8(base + pi * ld);
+                float ds[8];
+                if (drop_p > 0.f) dropout_scales(seed, (1ULL * n * hw + pi) * V + v, drop_p, ds);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float y = xv.v[j] * a[j] + b[j];
+                    if (act) y = silu_f(y);
+                    if (drop_p > 0.f) y *= ds[j];
+                    o.v[j] += 0.25f * y;
+                }
+            }
+            store8(out + (1LL * n * Ho * Wo + p) * ldo + v * 8, o);
+        } else {
+            const Vec8 xv = load8(base + p * ld);
+            float ds[8];
+            if (drop_p > 0.f) dropout_scales(seed, (1ULL * n * hw + p) * V + v, drop_p, ds);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float y = xv.v[j] * a[j] + b[j];
+                if (act) y = silu_f(y);
+                if (drop_p > 0.f) y *= ds[j];
+                o.v[j] = y;
+            }
+            if (resample == 0) {
+                store8(out + (1LL * n * hw + p) * ldo + v * 8, o);
+            } else {
+                const int h = p / W, w = p % W;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    const long long po = 1LL * (2 * h + (d >> 1)) * Wo + 2 * w + (d & 1);
+                    store8(out + (1LL * n * Ho * Wo + po) * ldo + v * 8, o);
+                }
+            }
+        }
+    }
+}
+
+// dv (gradient at the pre-activation v = x*A+B) for input pixel p, channel vector v, given dy at the op's output.
+__device__ __forceinline__ void grad_preact(const __nv_bfloat16* __restrict__ dy, long long ldy, int n, int H, int W,
+                                            int p, int v, int V, int resample, int act, float drop_p,
+                                            unsigned long long seed, const Vec8& xv, const float* a, const float* b,
+                                            float (&dv)[8]) {
+    const int hw = H * W;
+    Vec8 g;
+    if (resample == 0) {
+        g = load8(dy + (1LL * n * hw + p) * ldy + v * 8);
+    } else if (resample == 1) {
+        const int h = p / W, w = p % W, Wo = W / 2, Ho = H / 2;
+        g = load8(dy + (1LL * n * Ho * Wo + (h >> 1) * Wo + (w >> 1)) * ldy + v * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.v[j] *= 0.25f;
+    } else {
+        const int h = p / W, w = p % W, Wo = W * 2, Ho = H * 2;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.v[j] = 0.f;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const long long po = 1LL * (2 * h + (d >> 1)) * Wo + 2 * w + (d & 1);
+            const Vec8 t = load8(dy + (1LL * n * Ho * Wo + po) * ldy + v * 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g.v[j] += t.v[j];
+        }
+    }
+    float ds[8];
+    if (drop_p > 0.f) dropout_scales(seed, (1ULL * n * hw + p) * V + v, drop_p, ds);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float d = g.v[j];
+        if (drop_p > 0.f) d *= ds[j];
+        if (act) d *= silu_grad(xv.v[j] * a[j] + b[j]);
+        dv[j] = d;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ gn_bwd_reduce
+// bsums [N][C][2]: S1 = sum_p dv, S2 = sum_p dv * xhat.  grid (chunks, N), blockDim multiple of V.
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, long long ldy,
+                                                            const __nv_bfloat16* __restrict__ x1, int c1, long long ld1,
+                                                            const __nv_bfloat16* __restrict__ x2, int c2, long long ld2,
+                                                            int H, int W, int G, float eps,
+                                                            const float* __restrict__ sums,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta,
+                                                            const float* __restrict__ params, long long ldp, int act, float drop_p,
+                                                            unsigned long long seed, int resample,
+                                                            float* __restrict__ bsums,
+                                                            const unsigned long long* __restrict__ seed_dev) {
+    if (seed_dev != nullptr) seed += *seed_dev * 0x9E3779B97F4A7C15ull;
+    extern __shared__ float sm[];
+    const int C = c1 + c2, V = C >> 3, V1 = c1 >> 3;
+    float* sA = sm;
+    float* sB = sA + C;
+    float* sMean = sB + C;
+    float* sRstd = sMean + C;
+    float* red = sRstd + C;  // [blockDim][16]
+    const int n = blockIdx.y, hw = H * W;
+    group_affine_to_smem(sums, gamma, beta, params, ldp, n, C, G, hw, eps, sA, sB, sMean, sRstd);
+    const int tpv = blockDim.x / V;
+    const int v = threadIdx.x % V, lane = threadIdx.x / V;
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    if (lane < tpv) {
+        const __nv_bfloat16* base = v < V1 ? x1 + 1LL * n * hw * ld1 + v * 8 : x2 + 1LL * n * hw * ld2 + (v - V1) * 8;
+        const long long ld = v < V1 ? ld1 : ld2;
+        float a[8], b[8], mu[8], rs[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a[j] = sA[v * 8 + j]; b[j] = sB[v * 8 + j]; mu[j] = sMean[v * 8 + j]; rs[j] = sRstd[v * 8 + j];
+        }
+        for (int p = blockIdx.x * tpv + lane; p < hw; p += gridDim.x * tpv) {
+            const Vec8 xv = load8(base + p * ld);
+            float dv[8];
+            grad_preact(dy, ldy, n, H, W, p, v, V, resample, act, drop_p, seed, xv, a, b, dv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s1[j] += dv[j];
+                s2[j] += dv[j] * (xv.v[j] - mu[j]) * rs[j];
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { red[threadIdx.x * 16 + j] = s1[j]; red[threadIdx.x * 16 + 8 + j] = s2[j]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int vv = c >> 3, j = c & 7;
+        float a = 0.f, b = 0.f;
+        for (int l = 0; l < tpv; ++l) {
+            a += red[(l * V + vv) * 16 + j];
+            b += red[(l * V + vv) * 16 + 8 + j];
+        }
+        atomicAdd(bsums + (1LL * n * C + c) * 2, a);
+        atomicAdd(bsums + (1LL * n * C + c) * 2 + 1, b);
+    }
+}
+
+// dgamma[c] += sum_n (1+sc) S2, dbeta[c] += sum_n (1+sc) S1, dparams[n][c] = gamma*S2 + beta*S1, dparams[n][C+c] = S1
+__global__ void __launch_bounds__(256) gn_bwd_params_kernel(const float* __restrict__ bsums,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta,
+                                                            const float* __restrict__ params, long long ldp, int N, int C,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            float* __restrict__ dparams, long long ld_dparams) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+        float dg = 0.f, db = 0.f;
+        const float ga = gamma[c], be = beta[c];
+        for (int n = 0; n < N; ++n) {
+            const float s1 = bsums[(1LL * n * C + c) * 2], s2 = bsums[(1LL * n * C + c) * 2 + 1];
+            const float sc = params != nullptr ? 1.f + params[n * ldp + c] : 1.f;
+            dg += sc * s2;
+            db += sc * s1;
+            if (dparams != nullptr) {
+                dparams[n * ld_dparams + c] = ga * s2 + be * s1;
+                dparams[n * ld_dparams + C + c] = s1;
+            }
+        }
+        dgamma[c] += dg;
+        dbeta[c] += db;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ gn_bwd_apply
+// add: optional gradient to accumulate into dx (skip path).  add_mode 0: same resolution; 1: `add` lives at half
+// resolution and is spread as add/4 (block had a 2x2 avg-pool skip); 2: `add` lives at double resolution and is summed
+// over its 2x2 patch (block had a nearest-up skip).
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, long long ldy,
+                                                           const __nv_bfloat16* __restrict__ x1, int c1, long long ld1,
+                                                           const __nv_bfloat16* __restrict__ x2, int c2, long long ld2,
+                                                           int H, int W, int G, float eps,
+                                                           const float* __restrict__ sums,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta,
+                                                           const float* __restrict__ params, long long ldp, int act, float drop_p,
+                                                           unsigned long long seed, int resample,
+                                                           const float* __restrict__ bsums,
+                                                           const __nv_bfloat16* __restrict__ add, long long ldadd,
+                                                           int add_mode, __nv_bfloat16* __restrict__ dx1, long long ldx1,
+                                                           __nv_bfloat16* __restrict__ dx2, long long ldx2,
+                                                           const unsigned long long* __restrict__ seed_dev) {
+    if (seed_dev != nullptr) seed += *seed_dev * 0x9E3779B97F4A7C15ull;
+    extern __shared__ float sm[];
+    const int C = c1 + c2, V = C >> 3, V1 = c1 >> 3;
+    float* sA = sm;
+    float* sB = sA + C;
+    float* sMean = sB + C;
+    float* sRstd = sMean + C;
+    float* sG = sRstd + C;   // gamma' = gamma * (1 + scale)
+    float* sM1 = sG + C;     // mean_g(dv * gamma')
+    float* sM2 = sM1 + C;    // mean_g(dv * gamma' * xhat)
+    const int n = blockIdx.y, hw = H * W, cpg = C / G;
+    group_affine_to_smem(sums, gamma, beta, params, ldp, n, C, G, hw, eps, sA, sB, sMean, sRstd);
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+        sG[c] = gamma[c] * (params != nullptr ? 1.f + params[n * ldp + c] : 1.f);
+    __syncthreads();
+    const float inv_cnt = 1.f / (static_cast<float>(cpg) * static_cast<float>(hw));
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        float m1 = 0.f, m2 = 0.f;
+        for (int j = 0; j < cpg; ++j) {
+            const int cc = g * cpg + j;
+            m1 += sG[cc] * bsums[(1LL * n * C + cc) * 2];
+            m2 += sG[cc] * bsums[(1LL * n * C + cc) * 2 + 1];
+        }
+        sM1[c] = m1 * inv_cnt;
+        sM2[c] = m2 * inv_cnt;
+    }
+    __syncthreads();
+    const long long total = 1LL * hw * V;
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+        const int v = static_cast<int>(i % V);
+        const int p = static_cast<int>(i / V);
+        const bool first = v < V1;
+        const __nv_bfloat16* base = first ? x1 + 1LL * n * hw * ld1 + v * 8 : x2 + 1LL * n * hw * ld2 + (v - V1) * 8;
+        const long long ld = first ? ld1 : ld2;
+        const Vec8 xv = load8(base + p * ld);
+        float a[8], b[8], dv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a[j] = sA[v * 8 + j]; b[j] = sB[v * 8 + j]; }
+        grad_preact(dy, ldy, n, H, W, p, v, V, resample, act, drop_p, seed, xv, a, b, dv);
+        Vec8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = v * 8 + j;
+            const float xhat = (xv.v[j] - sMean[c]) * sRstd[c];
+            o.v[j] = sRstd[c] * (dv[j] * sG[c] - sM1[c] - xhat * sM2[c]);
+        }
+        if (add != nullptr) {  // skip-path gradient, laid out over the full (concatenated) channel range
+            const int h = p / W, w = p % W;
+            if (add_mode == 0) {
+                const Vec8 t = load8(add + (1LL * n * hw + p) * ldadd + v * 8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o.v[j] += t.v[j];
+            } else if (add_mode == 1) {
+                const Vec8 t = load8(add + (1LL * n * (H / 2) * (W / 2) + (h >> 1) * (W / 2) + (w >> 1)) * ldadd + v * 8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o.v[j] += 0.25f * t.v[j];
+            } else {
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    const long long po = 1LL * (2 * h + (d >> 1)) * (2 * W) + 2 * w + (d & 1);
+                    const Vec8 t = load8(add + (1LL * n * 4 * hw + po) * ldadd + v * 8);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o.v[j] += t.v[j];
+                }
+            }
+        }
+        if (first) store8(dx1 + (1LL * n * hw + p) * ldx1 + v * 8, o);
+        else store8(dx2 + (1LL * n * hw + p) * ldx2 + (v - V1) * 8, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ col_sums (bias grad)
+// out[c] += sum over rows of x[row][c]; x bf16 [rows][ld].  grid (chunks).
+__global__ void __launch_bounds__(256) col_sums_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
+                                                       long long rows, int C_total, float* __restrict__ out) {
+    extern __shared__ float sm[];  // [blockDim][8]
+    const int col0 = blockIdx.y * 2048;
+    const int C = min(2048, C_total - col0);
+    x += col0;
+    out += col0;
+    const int V = C >> 3;
+    const int tpv = blockDim.x / V;
+    const int v = threadIdx.x % V, lane = threadIdx.x / V;
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    if (lane < tpv && tpv > 0) {
+        for (long long r = blockIdx.x * 1LL * tpv + lane; r < rows; r += 1LL * gridDim.x * tpv) {
+            const Vec8 a = load8(x + r * ld + v * 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] += a.v[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm[threadIdx.x * 8 + j] = s[j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f;
+        for (int l = 0; l < tpv; ++l) a += sm[(l * V + (c >> 3)) * 8 + (c & 7)];
+        atomicAdd(out + c, a);
+    }
+}
+
+// out = a + b (+ c), bf16 rows of C channels with independent row strides.
+__global__ void __launch_bounds__(256) add_bf16_kernel(const __nv_bfloat16* __restrict__ a, long long lda,
+                                                       const __nv_bfloat16* __restrict__ b, long long ldb,
+                                                       const __nv_bfloat16* __restrict__ c, long long ldc,
+                                                       __nv_bfloat16* __restrict__ out, long long ldo, long long rows,
+                                                       int C) {
+    const int V = C >> 3;
+    const long long total = rows * V;
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+        const long long r = i / V;
+        const int v = static_cast<int>(i % V);
+        Vec8 x = load8(a + r * lda + v * 8);
+        const Vec8 y = load8(b + r * ldb + v * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x.v[j] += y.v[j];
+        if (c != nullptr) {
+            const Vec8 z = load8(c + r * ldc + v * 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x.v[j] += z.v[j];
+        }
+        store8(out + r * ldo + v * 8, x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ resample (skip path)
+// mode 1: 2x2 average pool; mode 2: nearest x2.  NHWC bf16.
+__global__ void __launch_bounds__(256) resample_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int N, int H,
+                                                       int W, int C, int mode, __nv_bfloat16* __restrict__ out,
+                                                       long long ldo) {
+    const int V = C >> 3;
+    const int Ho = mode == 1 ? H / 2 : H * 2, Wo = mode == 1 ? W / 2 : W * 2;
+    const long long total = 1LL * N * Ho * Wo * V;
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+        const int v = static_cast<int>(i % V);
+        long long r = i / V;
+        const int wo = static_cast<int>(r % Wo);
+        r /= Wo;
+        const int ho = static_cast<int>(r % Ho);
+        const int n = static_cast<int>(r / Ho);
+        Vec8 o;
+        if (mode == 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] = 0.f;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const Vec8 t = load8(x + ((1LL * n * H + 2 * ho + (d >> 1)) * W + 2 * wo + (d & 1)) * ldx + v * 8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o.v[j] += 0.25f * t.v[j];
+            }
+        } else {
+            o = load8(x + ((1LL * n * H + (ho >> 1)) * W + (wo >> 1)) * ldx + v * 8);
+        }
+        store8(out + ((1LL * n * Ho + ho) * Wo + wo) * ldo + v * 8, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ silu (embedding MLP)
+__global__ void __launch_bounds__(256) silu_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                   __nv_bfloat16* __restrict__ y_bf16, long long n) {
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < n; i += 1LL * gridDim.x * blockDim.x) {
+        const float v = silu_f(x[i]);
+        if (y != nullptr) y[i] = v;
+        if (y_bf16 != nullptr) y_bf16[i] = __float2bfloat16(v);
+    }
+}
+__global__ void __launch_bounds__(256) silu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                       float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
+                                                       long long n) {
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < n; i += 1LL * gridDim.x * blockDim.x) {
+        const float v = dy[i] * silu_grad(x[i]);
+        if (dx != nullptr) dx[i] = v;
+        if (dx_bf16 != nullptr) dx_bf16[i] = __float2bfloat16(v);
+    }
+}
+
+static const unsigned long long* g_seed_dev = nullptr;
+
+static int grid_for(long long work, int threads, int n_batch) {
+    long long blocks = (work + threads - 1) / threads;
+    long long cap = (4LL * num_sms() + n_batch - 1) / n_batch;
+    if (cap < 1) cap = 1;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return static_cast<int>(blocks);
+}
+
+}  // namespace adm
+
+using namespace adm;
+typedef __nv_bfloat16 bf16;
+
+#define ADM_REQUIRE(cond, msg)        \
+    do {                              \
+        if (!(cond)) {                \
+            set_error(msg);           \
+            return ADM_ERR_SHAPE;     \
+        }                             \
+    } while (0)
+
+extern "C" {
+
+int adm_set_seed_counter(const unsigned long long* dev_counter) {
+    g_seed_dev = dev_counter;
+    return 0;
+}
+
+int adm_chan_sums(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int hw,
+                  float* sums, void* stream) {
+    const int C = c1 + c2;
+    ADM_REQUIRE(c1 > 0 && c1 % 8 == 0 && c2 % 8 == 0 && (x2 != nullptr || c2 == 0), "chan_sums: channels must be multiples of 8");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaMemsetAsync(sums, 0, sizeof(float) * 2 * n * C, s);
+    const int V = C / 8;
+    const int threads = threads_for(V);
+    const int tpv = V <= threads ? threads / V : 1;
+    dim3 grid(grid_for(hw, tpv, n), n);
+    chan_sums_kernel<<<grid, threads, threads * 16 * sizeof(float), s>>>(static_cast<const bf16*>(x1), c1, ld1,
+                                                                        static_cast<const bf16*>(x2), c2, ld2, hw, sums);
+    ADM_CHECK_LAUNCH("chan_sums");
+    return 0;
+}
+
+int adm_gn_apply(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int h, int w,
+                 int groups, float eps, const float* sums, const float* gamma, const float* beta, const float* params,
+                 long long ld_params, int act, float drop_p, unsigned long long seed, int resample, void* out, long long ldo, void* stream) {
+    const int C = c1 + c2;
+    ADM_REQUIRE(c1 > 0 && c1 % 8 == 0 && c2 % 8 == 0 && C % groups == 0, "gn_apply: bad channels / groups");
+    ADM_REQUIRE(resample == 0 || (resample == 1 && h % 2 == 0 && w % 2 == 0) || resample == 2, "gn_apply: bad resample");
+    ADM_REQUIRE(C <= 4096, "gn_apply: C too large for the shared-memory affine table");
+    const long long work = 1LL * (resample == 1 ? (h / 2) * (w / 2) : h * w) * (C / 8);
+    dim3 grid(grid_for(work, 256, n), n);
+    gn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(x1), c1, ld1, static_cast<const bf16*>(x2), c2, ld2, h, w, groups, eps, sums, gamma,
+        beta, params, ld_params, act, drop_p, seed, resample, static_cast<bf16*>(out), ldo, g_seed_dev);
+    ADM_CHECK_LAUNCH("gn_apply");
+    return 0;
+}
+
+int adm_gn_bwd(const void* dy, long long ldy, const void* x1, int c1, long long ld1, const void* x2, int c2,
+               long long ld2, int n, int h, int w, int groups, float eps, const float* sums, const float* gamma,
+               const float* beta, const float* params, long long ld_params, int act, float drop_p,
+               unsigned long long seed, int resample, float* bsums, float* dgamma, float* dbeta, float* dparams, long long ld_dparams, const void* add,
+               long long ldadd, int add_mode, void* dx1, long long ldx1, void* dx2, long long ldx2, void* stream) {
+    const int C = c1 + c2;
+    ADM_REQUIRE(c1 > 0 && c1 % 8 == 0 && c2 % 8 == 0 && C % groups == 0, "gn_bwd: bad channels / groups");
+    ADM_REQUIRE(C <= 2048, "gn_bwd: C too large");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bf16* dyp = static_cast<const bf16*>(dy);
+    const bf16* x1p = static_cast<const bf16*>(x1);
+    const bf16* x2p = static_cast<const bf16*>(x2);
+    cudaMemsetAsync(bsums, 0, sizeof(float) * 2 * n * C, s);
+    const int V = C / 8;
+    const int threads = threads_for(V);
+    const int tpv = threads / V;
+    {
+        dim3 grid(grid_for(h * w, tpv, n), n);
+        const size_t smem = (4 * C + threads * 16) * sizeof(float);
+        gn_bwd_reduce_kernel<<<grid, threads, smem, s>>>(dyp, ldy, x1p, c1, ld1, x2p, c2, ld2, h, w, groups, eps, sums,
+                                                         gamma, beta, params, ld_params, act, drop_p, seed, resample, bsums, g_seed_dev);
+        ADM_CHECK_LAUNCH("gn_bwd_reduce");
+    }
+    if (dgamma != nullptr) {
+        gn_bwd_params_kernel<<<(C + 255) / 256, 256, 0, s>>>(bsums, gamma, beta, params, ld_params, n, C, dgamma, dbeta, dparams,
+                                                             ld_dparams);
+        ADM_CHECK_LAUNCH("gn_bwd_params");
+    }
+    if (dx1 != nullptr) {
+        dim3 grid(grid_for(1LL * h * w * V, 256, n), n);
+        gn_bwd_apply_kernel<<<grid, 256, 7 * C * sizeof(float), s>>>(
+            dyp, ldy, x1p, c1, ld1, x2p, c2, ld2, h, w, groups, eps, sums, gamma, beta, params, ld_params, act, drop_p,
+            seed, resample, bsums, static_cast<const bf16*>(add), ldadd, add_mode, static_cast<bf16*>(dx1), ldx1,
+            static_cast<bf16*>(dx2), ldx2, g_seed_dev);
+        ADM_CHECK_LAUNCH("gn_bwd_apply");
+    }
+    return 0;
+}
+
+int adm_col_sums(const void* x, long long ld, long long rows, int c, float* out, void* stream) {
+    ADM_REQUIRE(c > 0 && c % 8 == 0, "col_sums: C must be a multiple of 8");
+    const int chunks = (c + 2047) / 2048;
+    // all chunks but the last are 2048 wide (V = 256 -> 256 threads); size the block for the narrowest chunk
+    const int last = c - (chunks - 1) * 2048;
+    const int threads = chunks > 1 ? 256 : threads_for(last / 8);
+    ADM_REQUIRE(chunks == 1 || last % 8 == 0, "col_sums: bad width");
+    const int tpv = threads / ((chunks > 1 ? 2048 : last) / 8);
+    dim3 grid(grid_for(rows, tpv > 0 ? tpv : 1, chunks), chunks);
+    col_sums_kernel<<<grid, threads, threads * 8 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(x), ld, rows, c, out);
+    ADM_CHECK_LAUNCH("col_sums");
+    return 0;
+}
+
+int adm_add_bf16(const void* a, long long lda, const void* b, long long ldb, const void* c, long long ldc, void* out,
+                 long long ldo, long long rows, int ch, void* stream) {
+    ADM_REQUIRE(ch > 0 && ch % 8 == 0, "add_bf16: channels must be a multiple of 8");
+    add_bf16_kernel<<<grid_for(rows * (ch / 8), 256, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(a), lda, static_cast<const bf16*>(b), ldb, static_cast<const bf16*>(c), ldc,
+        static_cast<bf16*>(out), ldo, rows, ch);
+    ADM_CHECK_LAUNCH("add_bf16");
+    return 0;
+}
+
+int adm_resample(const void* x, long long ldx, int n, int h, int w, int c, int mode, void* out, long long ldo,
+                 void* stream) {
+    ADM_REQUIRE(c % 8 == 0 && (mode == 1 || mode == 2), "resample: bad arguments");
+    ADM_REQUIRE(mode == 2 || (h % 2 == 0 && w % 2 == 0), "resample: odd size");
+    const long long total = 1LL * n * (mode == 1 ? (h / 2) * (w / 2) : 4 * h * w) * (c / 8);
+    resample_kernel<<<grid_for(total, 256, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(x), ldx, n, h, w, c, mode, static_cast<bf16*>(out), ldo);
+    ADM_CHECK_LAUNCH("resample");
+    return 0;
+}
+
+int adm_silu(const float* x, float* y, void* y_bf16, long long numel, void* stream) {
+    silu_kernel<<<grid_for(numel, 256, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, static_cast<bf16*>(y_bf16),
+                                                                                       numel);
+    ADM_CHECK_LAUNCH("silu");
+    return 0;
+}
+
+int adm_silu_bwd(const float* x, const float* dy, float* dx, void* dx_bf16, long long numel, void* stream) {
+    silu_bwd_kernel<<<grid_for(numel, 256, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, dy, dx, static_cast<bf16*>(dx_bf16), numel);
+    ADM_CHECK_LAUNCH("silu_bwd");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,233 @@
+"""B200-native DDM-const diffusion module: mirror of the reference's ``ddm.ddm_const.DDPM``.
+
+Math follows /root/reference/ddm/ddm_const.py (the sqrt(t) noise schedule): forward :274-281, q_sample :284-287,
+p_losses :305-364, sample :367-378, sample_fn_d :425-476, sample_fn_s :381-422.  Plumbing (constructor signature
+``DDPM(model, *, image_size, ..., cfg=..., **model_cfg)``, ``training_step(batch)``) follows the importable upstream API
+in /root/reference/ddm/ddm_const_2.py:43-118,149-170, which is what the in-tree scripts call
+(train_uncond_dpm.py:44-46,264-267).
+
+The arithmetic runs in hand-written sm_100a kernels: K1 q_sample, the UNet engine, K2 fused loss forward+backward,
+K3 fused sampler update.  There is no CPU fallback.
+
+Deviations from the reference, all documented in DESIGN.md:
+  * the LPIPS term (perceptual_weight) is identically 0: the reference cannot construct LPIPS offline and its own
+    ``p_losses`` crashes without it; ``loss_vlb`` is reported as 0;
+  * ``sampling_timesteps == 1`` uses t_steps = [sigma_max, 0] instead of the reference's NaN;
+  * ``p_losses`` / ``sample`` take optional explicit randomness (``noise=``, ``x_T=``) for parity tests.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .utils import default, unnormalize_to_zero_to_one
+
+
+class _DDMLossFn(torch.autograd.Function):
+    """K2: per-sample weighted SSE loss and its gradients in one pass over the four tensors."""
+
+    @staticmethod
+    def forward(ctx, c_pred, eps_pred, x0, noise, t, eps, weighting, use_l1):
+        need = c_pred.requires_grad or eps_pred.requires_grad
+        lps, dc, de = ops.ddm_loss(c_pred.detach(), eps_pred.detach(), x0, noise, t, eps, weighting, use_l1,
+                                   need_grad=need)
+        ctx.dc, ctx.de = dc, de
+        ctx.mark_non_differentiable(lps)
+        return lps.sum() / x0.shape[0], lps
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_lps):
+        dc, de = ctx.dc, ctx.de
+        ctx.dc = ctx.de = None
+        if dc is None:
+            return (None,) * 8
+        return dc * g_loss, de * g_loss, None, None, None, None, None, None
+
+
+class DDPM(nn.Module):
+    def __init__(self, model, *, image_size, sampling_timesteps=None, loss_type="l2", objective="pred_noise",
+                 beta_schedule="cosine", clip_x_start=True, input_keys=["image"], start_dist="normal",
+                 sample_type="deterministic", perceptual_weight=1., use_l1=False, **kwargs):
+        ckpt_path = kwargs.pop("ckpt_path", None)
+        ignore_keys = kwargs.pop("ignore_keys", [])
+        only_model = kwargs.pop("only_model", False)
+        cfg = kwargs.pop("cfg", None)
+        super().__init__()
+        self.model = model
+        self.channels = self.model.channels
+        self.self_condition = self.model.self_condition
+        self.input_keys = input_keys
+        self.cfg = cfg if cfg is not None else {}
+        g = self.cfg.get
+        self.scale_input = g("scale_input", 1)
+        self.register_buffer("eps", torch.tensor(g("eps", 1e-4)))
+        self._eps = float(g("eps", 1e-4))
+        self.sigma_min = g("sigma_min", 1e-2)
+        self.sigma_max = g("sigma_max", 1)
+        self.weighting_loss = g("weighting_loss", False)
+        self.clip_x_start = clip_x_start
+        self.image_size = image_size
+        self.objective = objective
+        self.start_dist = start_dist
+        assert start_dist in ["normal", "uniform"]
+        self.loss_type = loss_type
+        self.sampling_timesteps = default(sampling_timesteps, 10)
+        self.use_l1 = use_l1
+        self.perceptual_weight = perceptual_weight  # LPIPS term is 0 here (see module docstring)
+        self.sample_type = g("sample_type", sample_type if sample_type in ("deterministic", "stochastic")
+                             else "deterministic")
+        self.use_augment = g("use_augment", False)
+        self.augment = None
+        if self.use_augment:
+            from .augment import AugmentPipe
+            self.augment = AugmentPipe(p=0.15, xflip=1e8, yflip=1, scale=1, rotate_frac=1, aniso=1, translate_frac=1)
+        if ckpt_path is not None:
+            self.init_from_ckpt(ckpt_path, ignore_keys, only_model)
+
+    # -------------------------------------------------------------------------------------------- checkpoints
+    def init_from_ckpt(self, path, ignore_keys=list(), only_model=False, use_ema=False):
+        """ddm_const.py:187-214: accepts Trainer checkpoints ({'model': ..., 'ema': ...}) or bare state_dicts."""
+        sd = torch.load(path, map_location="cpu")
+        if "ema" in sd and use_ema:
+            sd = {(k[10:] if k.startswith("ema_model.") else k): v for k, v in sd["ema"].items()}
+        elif "model" in sd:
+            sd = sd["model"]
+        for k in list(sd.keys()):
+            if any(k.startswith(ik) for ik in ignore_keys):
+                del sd[k]
+        target = self.model if only_model else self
+        missing, unexpected = target.load_state_dict(sd, strict=False)
+        print(f"Restored from {path} with {len(missing)} missing and {len(unexpected)} unexpected keys")
+
+    # -------------------------------------------------------------------------------------------- training
+    def get_input(self, batch, return_first_stage_outputs=False, return_original_cond=False):
+        assert "image" in self.input_keys
+        if len(self.input_keys) > len(batch.keys()):
+            x, *_ = batch.values()
+        else:
+            x = batch.values()
+        return x
+
+    def training_step(self, batch, *args, **kwargs):
+        z, *_ = self.get_input(batch)
+        cond = batch["cond"] if "cond" in batch else None
+        return self(z, cond) if cond is not None else self(z)
+
+    def forward(self, x, *args, **kwargs):
+        if not x.is_cuda:
+            raise RuntimeError("adm_b200.DDPM runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if self.scale_input != 1:
+            x = x * self.scale_input
+        t = torch.rand(x.shape[0], device=x.device) * (1. - self._eps) + self._eps
+        return self.p_losses(x, t, *args, **kwargs)
+
+    def q_sample(self, x_start, noise, t, C=None):
+        """K1.  C is implied (-x_start, ddm_const.py:319) and only accepted for signature compatibility."""
+        return ops.qsample(x_start, noise, t)
+
+    def pred_x0_from_xt(self, xt, noise, C, t):
+        time = t.reshape(C.shape[0], *((1,) * (len(C.shape) - 1)))
+        return xt - C * time - torch.sqrt(time) * noise
+
+    def p_losses(self, x_start, t, *args, noise=None, **kwargs):
+        if noise is None:
+            if self.start_dist == "normal":
+                noise = torch.randn_like(x_start)
+            elif self.start_dist == "uniform":
+                noise = 2 * torch.rand_like(x_start) - 1.
+            else:
+                raise NotImplementedError(f"{self.start_dist} is not supported !")
+        if self.use_augment and self.augment is not None and "augment_labels" not in kwargs:
+            x_start, aug_label = self.augment(x_start)
+            kwargs["augment_labels"] = aug_label
+        x_start = x_start.contiguous().float()
+        x_noisy = ops.qsample(x_start, noise, t)
+        c_pred, noise_pred = self.model(x_noisy, t, *args, **kwargs)
+        loss, lps = _DDMLossFn.apply(c_pred, noise_pred, x_start, noise, t, self._eps, bool(self.weighting_loss),
+                                     bool(self.use_l1))
+        n = float(x_start.numel())
+        with torch.no_grad():
+            loss_dict = {"train/loss_simple": lps.sum() / n,
+                         "train/loss_vlb": torch.zeros((), device=x_start.device),
+                         "train/loss": loss.detach() / n}
+        return loss, loss_dict
+
+    # -------------------------------------------------------------------------------------------- sampling
+    def t_steps(self, n=None):
+        """ddm_const.py:429-436 in float64 on the host."""
+        n = self.sampling_timesteps if n is None else n
+        smin = float(self.sigma_min) ** 2
+        smax = float(self.sigma_max)
+        if n == 1:
+            ts = [smax]
+        else:
+            ts = [smax + i / (n - 1) * (smin - smax) for i in range(n)]
+        return ts + [0.0]
+
+    @torch.no_grad()
+    def sample(self, batch_size=16, up_scale=1, cond=None, denoise=True, x_T=None, z_list=None):
+        image_size, channels = self.image_size, self.channels
+        if cond is not None:
+            batch_size = cond.shape[0]
+        shape = (batch_size, channels, image_size[0], image_size[1])
+        if self.sample_type == "stochastic":
+            return self.sample_fn_s(shape, unnormalize=True, cond=cond, x_T=x_T, z_list=z_list)
+        return self.sample_fn_d(shape, unnormalize=True, cond=cond, x_T=x_T)
+
+    @torch.no_grad()
+    def sample_fn_d(self, shape, up_scale=1, unnormalize=True, cond=None, denoise=False, x_T=None):
+        device = self.eps.device
+        ts = self.t_steps()
+        if x_T is None:
+            x_T = torch.randn(shape, device=device, dtype=torch.float64)
+        x = (x_T.to(device=device, dtype=torch.float64) * ts[0]).contiguous()
+        was_training = self.model.training
+        self.model.eval()
+        clip = 1. * self.scale_input
+        n = len(ts) - 1
+        for i, (t_cur, t_next) in enumerate(zip(ts[:-1], ts[1:])):
+            tc = torch.tensor(t_cur, device=device, dtype=torch.float64)
+            pred = self.model(x, tc, cond) if cond is not None else self.model(x, tc)
+            c, noise = pred[:2]
+            last = i == n - 1
+            if last and not unnormalize:
+                x = ops.sampler_step(x, c, noise, t_cur, t_next, clip, self.clip_x_start, False, self.scale_input)
+                x = x.clamp_(-clip, clip) / self.scale_input if self.scale_input != 1 else x.clamp_(-clip, clip)
+            else:
+                x = ops.sampler_step(x, c, noise, t_cur, t_next, clip, self.clip_x_start, last, self.scale_input)
+        self.model.train(was_training)
+        return x
+
+    @torch.no_grad()
+    def sample_fn_s(self, shape, up_scale=1, unnormalize=True, cond=None, denoise=False, x_T=None, z_list=None):
+        device = self.eps.device
+        n = self.sampling_timesteps
+        smin2, smax2 = float(self.sigma_min) ** 2, float(self.sigma_max) ** 2
+        ts = [smax2 + i / (n - 1) * (smin2 - smax2) for i in range(n)] + [0.0]
+        steps = [ts[i] - ts[i + 1] for i in range(n)]
+        if x_T is None:
+            x_T = torch.randn(shape, device=device) if self.start_dist == "normal" else 2 * torch.rand(shape, device=device) - 1.
+        img = x_T.to(device=device, dtype=torch.float32).contiguous()
+        was_training = self.model.training
+        self.model.eval()
+        clip = 1. * self.scale_input
+        cur = 1.0
+        for i, s in enumerate(steps):
+            if i == n - 1:
+                s = cur
+            tc = torch.tensor(cur, device=device, dtype=torch.float64)
+            pred = self.model(img, tc, cond) if cond is not None else self.model(img, tc)
+            c, noise = pred[:2]
+            z = z_list[i].to(device) if z_list is not None else torch.randn_like(img)
+            img = ops.sampler_step_stochastic(img, c, noise, z, cur, s, clip, self.clip_x_start)
+            cur = cur - s
+        self.model.train(was_training)
+        img = img.clamp_(-clip, clip)
+        if self.scale_input != 1:
+            img = img / self.scale_input
+        if unnormalize:
+            img = unnormalize_to_zero_to_one(img)
+        return img

@@ -125,26 +125,28 @@ def unet_output_bwd(dd1, dd2, sigma, ld_out=8):
 
 
 # ------------------------------------------------------------------------------------------------ GEMM engine
-def pack_conv_weight(w, c1=None, c2=0):
+def pack_conv_weight(w, c1=None, c2=0, row_perm=None, out=None):
     """fp32 [cout, c1+c2, k, k] -> bf16 [cout, k*k, pad64(c1)+pad64(c2)]."""
     _need_cuda(w)
     cout, cin, k, _ = w.shape
     c1 = cin if c1 is None else c1
     assert c1 + c2 == cin
     kpad = pad64(c1) + (pad64(c2) if c2 else 0)
-    out = torch.empty(cout, k * k, kpad, device=w.device, dtype=BF16)
-    check(_lib.load().adm_pack_conv_weight(_ptr(w.contiguous().float()), _ptr(out), cout, c1, c2, k, _stream()),
+    if out is None:
+        out = torch.empty(cout, k * k, kpad, device=w.device, dtype=BF16)
+    assert w.is_contiguous() and w.dtype == F32
+    check(_lib.load().adm_pack_conv_weight(_ptr(w), _ptr(out), cout, c1, c2, k, _ptr(row_perm), _stream()),
           "pack_conv_weight")
     return out
 
 
-def unpack_conv_wgrad(dw_packed, c1, c2, k, out=None, accumulate=False):
+def unpack_conv_wgrad(dw_packed, c1, c2, k, out=None, accumulate=False, row_perm=None):
     cout = dw_packed.shape[0]
     if out is None:
         out = torch.empty(cout, c1 + c2, k, k, device=dw_packed.device, dtype=F32)
         accumulate = False
-    check(_lib.load().adm_unpack_conv_wgrad(_ptr(dw_packed), _ptr(out), cout, c1, c2, k, int(accumulate), _stream()),
-          "unpack_conv_wgrad")
+    check(_lib.load().adm_unpack_conv_wgrad(_ptr(dw_packed), _ptr(out), cout, c1, c2, k, int(accumulate),
+                                            _ptr(row_perm), _stream()), "unpack_conv_wgrad")
     return out
 
 
@@ -156,7 +158,8 @@ def cast_bf16(x):
     return out
 
 
-def conv_fprop(x1, wpk, x2=None, bias=None, residual=None, alpha=1.0, out_dtype=BF16, out=None, nout=None):
+def conv_fprop(x1, wpk, x2=None, bias=None, residual=None, alpha=1.0, out_dtype=BF16, out=None, nout=None,
+               keep_pad=False):
     """Implicit-GEMM conv (3x3 pad 1 or 1x1) on NHWC bf16.  wpk: [nout, taps, kpad] bf16."""
     _need_cuda(x1, wpk)
     p1, c1, ld1, n, h, w = _nhwc(x1)
@@ -180,7 +183,7 @@ def conv_fprop(x1, wpk, x2=None, bias=None, residual=None, alpha=1.0, out_dtype=
     check(_lib.load().adm_conv_fprop(p1, c1, ld1, p2, c2, ld2, n, h, w, _ptr(wpk), nout, ntaps, _ptr(out),
                                      0 if out.dtype == BF16 else 1, ldc, _ptr(bias), _ptr(residual), ldr, float(alpha),
                                      _stream()), "conv_fprop")
-    return out[..., :nout] if out.shape[-1] != nout else out
+    return out[..., :nout] if (out.shape[-1] != nout and not keep_pad) else out
 
 
 def conv_dgrad(dy, wpk, n_valid=None, residual=None, alpha=1.0, out=None):
@@ -275,3 +278,222 @@ def gemm_tn(a, b, out_dtype=F32, alpha=1.0, out=None, splits=1):
     d.alpha = float(alpha)
     check(_lib.load().adm_gemm_batched(d, _stream()), "gemm_tn")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ GroupNorm family
+def _src(x):
+    """(ptr, C, ld) of an NHWC / [rows, C] bf16 view (or (None, 0, 0))."""
+    if x is None:
+        return None, 0, 0
+    assert x.dtype == BF16 and x.stride(-1) == 1
+    return x.data_ptr(), x.shape[-1], x.stride(-2)
+
+
+def chan_sums(x1, x2=None):
+    """fp32 [N, C1+C2, 2]: per-(sample, channel) sum and sum of squares over H*W."""
+    _need_cuda(x1)
+    n, h, w, _ = x1.shape
+    p1, c1, ld1 = _src(x1)
+    p2, c2, ld2 = _src(x2)
+    sums = torch.empty(n, c1 + c2, 2, device=x1.device, dtype=F32)
+    check(_lib.load().adm_chan_sums(p1, c1, ld1, p2, c2, ld2, n, h * w, _ptr(sums), _stream()), "chan_sums")
+    return sums
+
+
+def gn_apply(x1, x2, sums, gamma, beta, groups, eps=1e-5, params=None, act=True, drop_p=0.0, seed=0, resample=0):
+    n, h, w, _ = x1.shape
+    p1, c1, ld1 = _src(x1)
+    p2, c2, ld2 = _src(x2)
+    ho, wo = (h // 2, w // 2) if resample == 1 else ((2 * h, 2 * w) if resample == 2 else (h, w))
+    out = torch.empty(n, ho, wo, c1 + c2, device=x1.device, dtype=BF16)
+    ldp = params.stride(0) if params is not None else 0
+    check(_lib.load().adm_gn_apply(p1, c1, ld1, p2, c2, ld2, n, h, w, groups, float(eps), _ptr(sums), _ptr(gamma),
+                                   _ptr(beta), _ptr(params), ldp, int(act), float(drop_p), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                   int(resample),
+                                   _ptr(out), out.stride(2), _stream()), "gn_apply")
+    return out
+
+
+def gn_bwd(dy, x1, x2, sums, gamma, beta, groups, eps=1e-5, params=None, act=True, drop_p=0.0, seed=0, resample=0,
+           dgamma=None, dbeta=None, dparams=None, add=None, add_mode=0, need_dx=True):
+    """Returns (dx1, dx2).  dgamma/dbeta are accumulated in place; dparams ([N, 2C] view) is overwritten."""
+    n, h, w, _ = x1.shape
+    p1, c1, ld1 = _src(x1)
+    p2, c2, ld2 = _src(x2)
+    assert dy.dtype == BF16 and dy.stride(-1) == 1
+    bsums = torch.empty(n, c1 + c2, 2, device=x1.device, dtype=F32)
+    dx1 = torch.empty(n, h, w, c1, device=x1.device, dtype=BF16) if need_dx else None
+    dx2 = torch.empty(n, h, w, c2, device=x1.device, dtype=BF16) if (need_dx and x2 is not None) else None
+    ldp = params.stride(0) if params is not None else 0
+    lddp = dparams.stride(0) if dparams is not None else 0
+    check(_lib.load().adm_gn_bwd(_ptr(dy), dy.stride(-2), p1, c1, ld1, p2, c2, ld2, n, h, w, groups, float(eps),
+                                 _ptr(sums), _ptr(gamma), _ptr(beta), _ptr(params), ldp, int(act), float(drop_p),
+                                 int(seed) & 0xFFFFFFFFFFFFFFFF, int(resample), _ptr(bsums), _ptr(dgamma), _ptr(dbeta), _ptr(dparams), lddp,
+                                 _ptr(add), add.stride(-2) if add is not None else 0, int(add_mode), _ptr(dx1),
+                                 dx1.stride(2) if dx1 is not None else 0, _ptr(dx2),
+                                 dx2.stride(2) if dx2 is not None else 0, _stream()), "gn_bwd")
+    return dx1, dx2
+
+
+def col_sums(x, out):
+    """out[c] += sum over rows of x[..., c]; x bf16 with contiguous last dim and uniform row stride."""
+    c = x.shape[-1]
+    rows = x.numel() // c
+    check(_lib.load().adm_col_sums(_ptr(x), x.stride(-2), rows, c, _ptr(out), _stream()), "col_sums")
+    return out
+
+
+def resample(x, mode):
+    n, h, w, c = x.shape
+    ho, wo = (h // 2, w // 2) if mode == 1 else (2 * h, 2 * w)
+    out = torch.empty(n, ho, wo, c, device=x.device, dtype=BF16)
+    check(_lib.load().adm_resample(_ptr(x), x.stride(2), n, h, w, c, mode, _ptr(out), out.stride(2), _stream()),
+          "resample")
+    return out
+
+
+def add_bf16(a, b, c=None):
+    """a + b (+ c) on NHWC bf16 views (any pixel stride)."""
+    out = torch.empty(a.shape, device=a.device, dtype=BF16)
+    ch = a.shape[-1]
+    rows = a.numel() // ch
+    check(_lib.load().adm_add_bf16(_ptr(a), a.stride(-2), _ptr(b), b.stride(-2), _ptr(c),
+                                   c.stride(-2) if c is not None else 0, _ptr(out), out.stride(-2), rows, ch,
+                                   _stream()), "add_bf16")
+    return out
+
+
+def silu(x, want_f32=True, want_bf16=True):
+    x = x.contiguous()
+    y = torch.empty_like(x) if want_f32 else None
+    yb = torch.empty(x.shape, device=x.device, dtype=BF16) if want_bf16 else None
+    check(_lib.load().adm_silu(_ptr(x), _ptr(y), _ptr(yb), x.numel(), _stream()), "silu")
+    return y, yb
+
+
+def silu_bwd(x, dy, want_f32=True, want_bf16=True):
+    x, dy = x.contiguous(), dy.contiguous()
+    dx = torch.empty_like(x) if want_f32 else None
+    dxb = torch.empty(x.shape, device=x.device, dtype=BF16) if want_bf16 else None
+    check(_lib.load().adm_silu_bwd(_ptr(x), _ptr(dy), _ptr(dx), _ptr(dxb), x.numel(), _stream()), "silu_bwd")
+    return dx, dxb
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def softmax_fwd(s):
+    rows, length = s.numel() // s.shape[-1], s.shape[-1]
+    p = torch.empty(s.shape, device=s.device, dtype=BF16)
+    check(_lib.load().adm_softmax_fwd(_ptr(s), _ptr(p), rows, length, _stream()), "softmax_fwd")
+    return p
+
+
+def softmax_bwd(p, dp, scale):
+    rows, length = p.numel() // p.shape[-1], p.shape[-1]
+    ds = torch.empty(p.shape, device=p.device, dtype=BF16)
+    check(_lib.load().adm_softmax_bwd(_ptr(p), _ptr(dp), _ptr(ds), float(scale), rows, length, _stream()),
+          "softmax_bwd")
+    return ds
+
+
+def _gemm(desc_kw, a_op, b_op, what):
+    d = GemmDesc()
+    d.a, d.b = a_op, b_op
+    for k, v in desc_kw.items():
+        setattr(d, k, v)
+    check(_lib.load().adm_gemm_batched(d, _stream()), what)
+
+
+def attention_fwd(qkv, heads):
+    """qkv: [N, H, W, 3C] bf16 laid out as (q | k | v), each [heads, d].  Returns (a [N,H,W,C], p [N*heads,HW,HW])."""
+    n, h, w, c3 = qkv.shape
+    c, hw = c3 // 3, h * w
+    d = c // heads
+    assert qkv.is_contiguous()
+    s = torch.empty(n * heads, hw, hw, device=qkv.device, dtype=F32)
+    qk_dims, qk_str = (c3, hw, n), (c3, c3 * hw)
+    _gemm(dict(m=hw, n=hw, k=d, batches=n * heads, bdiv=heads, splits=1, c=s.data_ptr(), out_mode=1, ldc=hw,
+               c_bhi=heads * hw * hw, c_blo=hw * hw, c_col_lo=0, alpha=1.0 / d ** 0.5),
+          _operand(qkv, 0, qk_dims, qk_str, c0=0, c0_lo=d, bhi=1),
+          _operand(qkv, 0, qk_dims, qk_str, c0=c, c0_lo=d, bhi=1), "attn QK^T")
+    p = softmax_fwd(s)
+    a = torch.empty(n, h, w, c, device=qkv.device, dtype=BF16)
+    _gemm(dict(m=hw, n=d, k=hw, batches=n * heads, bdiv=heads, splits=1, c=a.data_ptr(), out_mode=0, ldc=c,
+               c_bhi=hw * c, c_blo=0, c_col_lo=d, alpha=1.0),
+          _operand(p, 0, (hw, hw, n * heads), (hw, hw * hw), bhi=heads, blo=1),
+          _operand(qkv, 1, qk_dims, qk_str, c0=2 * c, c0_lo=d, bhi=1), "attn PV")
+    return a, p
+
+
+def attention_bwd(da, qkv, p, heads):
+    """Returns dqkv [N,H,W,3C] bf16."""
+    n, h, w, c3 = qkv.shape
+    c, hw = c3 // 3, h * w
+    d = c // heads
+    assert da.is_contiguous() and qkv.is_contiguous()
+    dqkv = torch.empty_like(qkv)
+    qk_dims, qk_str = (c3, hw, n), (c3, c3 * hw)
+    a_dims, a_str = (c, hw, n), (c, c * hw)
+    p_dims, p_str = (hw, hw, n * heads), (hw, hw * hw)
+    nb = n * heads
+    esz = 2
+    # dV[k, d] = sum_q P[q, k] dA[q, d]
+    _gemm(dict(m=hw, n=d, k=hw, batches=nb, bdiv=heads, splits=1, c=dqkv.data_ptr() + 2 * c * esz, out_mode=0,
+               ldc=c3, c_bhi=hw * c3, c_blo=0, c_col_lo=d, alpha=1.0),
+          _operand(p, 1, p_dims, p_str, bhi=heads, blo=1),
+          _operand(da, 1, a_dims, a_str, c0=0, c0_lo=d, bhi=1), "attn dV")
+    # dP[q, k] = sum_d dA[q, d] V[k, d]
+    dp = torch.empty(nb, hw, hw, device=qkv.device, dtype=F32)
+    _gemm(dict(m=hw, n=hw, k=d, batches=nb, bdiv=heads, splits=1, c=dp.data_ptr(), out_mode=1, ldc=hw,
+               c_bhi=heads * hw * hw, c_blo=hw * hw, c_col_lo=0, alpha=1.0),
+          _operand(da, 0, a_dims, a_str, c0=0, c0_lo=d, bhi=1),
+          _operand(qkv, 0, qk_dims, qk_str, c0=2 * c, c0_lo=d, bhi=1), "attn dP")
+    ds = softmax_bwd(p, dp, 1.0 / d ** 0.5)
+    # dQ[q, d] = sum_k dS[q, k] K[k, d]
+    _gemm(dict(m=hw, n=d, k=hw, batches=nb, bdiv=heads, splits=1, c=dqkv.data_ptr(), out_mode=0, ldc=c3,
+               c_bhi=hw * c3, c_blo=0, c_col_lo=d, alpha=1.0),
+          _operand(ds, 0, p_dims, p_str, bhi=heads, blo=1),
+          _operand(qkv, 1, qk_dims, qk_str, c0=c, c0_lo=d, bhi=1), "attn dQ")
+    # dK[k, d] = sum_q dS[q, k] Q[q, d]
+    _gemm(dict(m=hw, n=d, k=hw, batches=nb, bdiv=heads, splits=1, c=dqkv.data_ptr() + c * esz, out_mode=0, ldc=c3,
+               c_bhi=hw * c3, c_blo=0, c_col_lo=d, alpha=1.0),
+          _operand(ds, 1, p_dims, p_str, bhi=heads, blo=1),
+          _operand(qkv, 1, qk_dims, qk_str, c0=0, c0_lo=d, bhi=1), "attn dK")
+    return dqkv
+
+
+def spatial_att_fwd(h, res, w_map, scalars):
+    n, hh, ww, c = h.shape
+    out = torch.empty(n, hh, ww, c, device=h.device, dtype=BF16)
+    att = torch.empty(n, hh * ww, device=h.device, dtype=F32)
+    o = torch.empty_like(att)
+    check(_lib.load().adm_spatial_att_fwd(_ptr(h), h.stride(2), _ptr(res), res.stride(2), _ptr(w_map), _ptr(scalars),
+                                          n, hh * ww, c, _ptr(out), out.stride(2), _ptr(att), _ptr(o), _stream()),
+          "spatial_att_fwd")
+    return out, att, o
+
+
+def spatial_att_bwd(dy, h, w_map, scalars, att, o, dw_map, dscalars):
+    n, hh, ww, c = h.shape
+    dh = torch.empty(n, hh, ww, c, device=h.device, dtype=BF16)
+    check(_lib.load().adm_spatial_att_bwd(_ptr(dy), dy.stride(2), _ptr(h), h.stride(2), _ptr(w_map), _ptr(scalars),
+                                          _ptr(att), _ptr(o), n, hh * ww, c, _ptr(dh), dh.stride(2), _ptr(dw_map),
+                                          _ptr(dscalars), _stream()), "spatial_att_bwd")
+    return dh
+
+
+# ------------------------------------------------------------------------------------------------ optimizer
+def sq_norm(g, out):
+    check(_lib.load().adm_sq_norm(_ptr(g), g.numel(), _ptr(out), _stream()), "sq_norm")
+    return out
+
+
+def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, max_norm=0.0, sqnorm=None,
+          hyper_dev=None):
+    check(_lib.load().adm_adamw(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(beta1), float(beta2),
+                                float(eps), float(weight_decay), int(step), float(grad_scale), float(max_norm),
+                                _ptr(sqnorm), _ptr(hyper_dev), _stream()), "adamw")
+
+
+def set_seed_counter(t):
+    """t: CUDA int64 tensor with one element (or None)."""
+    check(_lib.load().adm_set_seed_counter(_ptr(t)), "set_seed_counter")

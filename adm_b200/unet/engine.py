@@ -1,0 +1,456 @@
+"""Fused sm_100a execution engine for the two-decoder DhariwalUNet (forward + hand-written backward).
+
+Follows /root/reference/unet/uncond_unet.py: EDMPrecond.forward :614-635, DhariwalUNet.forward :544-581,
+UNetBlock.forward :189-211, SpatialAtt.forward :27-37, with this data layout:
+
+* activations NHWC bf16 (channels innermost, so one 64-channel slab of a pixel row is one 128 B TMA/UMMA swizzle row);
+* weights: fp32 masters stay in the reference layout inside the nn.Modules; bf16 packed copies [Cout][tap][Cin] are derived
+  caches, rebuilt when a parameter's version changes;
+* channel concats (torch.cat([x, skip]), :570-571) are never materialised: GroupNorm kernels and the GEMM engine take two
+  sources;
+* per-(sample, channel) sum / sum-of-squares tables carry the GroupNorm statistics.
+
+Gradients are accumulated straight into ``param.grad`` (fp32, reference layout) by ``backward`` — the engine plays the
+role of autograd's AccumulateGrad for its own parameters.
+"""
+from __future__ import annotations
+
+import itertools
+from types import SimpleNamespace as NS
+
+import torch
+
+from .. import ops
+from ..ops import BF16, F32, pad64
+
+
+def _groups(c):
+    return min(32, c // 4)
+
+
+class UNetEngine:
+    def __init__(self, net):
+        self.net = net
+        self._cache = {}
+        self._epoch = 0
+        self._seed_iter = itertools.count(1)
+        self.base_seed = 0x1234
+        # ordered block table + offsets into the batched affine GEMM
+        self.block_list = []
+        off = 0
+        for sec in ("enc", "dec", "dec2"):
+            for name, m in getattr(net, sec).items():
+                if hasattr(m, "affine"):
+                    self.block_list.append((f"{sec}.{name}", m, off))
+                    off += m.affine.out_features
+        self.affine_total = off
+        self._perm = {}
+
+    # ------------------------------------------------------------------------------------------ weight caches
+    def invalidate(self):
+        """Call after parameters were updated through raw pointers (the fused optimizer)."""
+        self._epoch += 1
+
+    def _cached(self, key, params, build):
+        ver = tuple((p.data_ptr(), p._version) for p in params) + (self._epoch,)
+        hit = self._cache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        val = build(hit[1] if hit is not None else None)
+        self._cache[key] = (ver, val)
+        return val
+
+    def _dev(self):
+        return self.net.map_layer0.weight.device
+
+    def conv_w(self, conv, c1=None, c2=0, perm=None):
+        w = conv.weight
+        return self._cached(("cw", id(conv)), [w],
+                            lambda old: ops.pack_conv_weight(w.detach(), c1, c2, row_perm=perm, out=old))
+
+    def lin_w(self, lin):
+        w = lin.weight
+        return self._cached(("lw", id(lin)), [w], lambda old: ops.cast_bf16(w.detach()))
+
+    def aug_w(self):
+        w = self.net.map_augment.weight  # [mc, augment_dim] -> zero padded to 16 columns
+
+        def build(old):
+            wp = torch.zeros(w.shape[0], 16, device=w.device, dtype=F32)
+            wp[:, :w.shape[1]] = w.detach()
+            return ops.cast_bf16(wp)
+        return self._cached(("aug",), [w], build)
+
+    def affine_all(self):
+        ps = [m.affine.weight for _, m, _ in self.block_list] + [m.affine.bias for _, m, _ in self.block_list]
+
+        def build(old):
+            wall = old[0] if old is not None else torch.empty(self.affine_total, self.net.emb_channels,
+                                                                device=self._dev(), dtype=BF16)
+            for _, m, off in self.block_list:
+                o = m.affine.out_features
+                ops._lib.check(ops._lib.load().adm_cast_f32_bf16(m.affine.weight.data_ptr(), wall[off:off + o].data_ptr(),
+                                                                 m.affine.weight.numel(), ops._stream()), "cast")
+            ball = torch.cat([m.affine.bias.detach() for _, m, _ in self.block_list])
+            return wall, ball
+        return self._cached(("affine_all",), ps, build)
+
+    def qkv_perm(self, c, heads):
+        """packed row (which, head, d) <- reference row head*3d + d*3 + which (uncond_unet.py:205)."""
+        key = (c, heads)
+        if key not in self._perm:
+            d = c // heads
+            which, hh, dd = torch.meshgrid(torch.arange(3), torch.arange(heads), torch.arange(d), indexing="ij")
+            perm = (hh * 3 * d + dd * 3 + which).reshape(-1)
+            self._perm[key] = (perm.to(self._dev(), torch.int32), perm.to(self._dev(), torch.int64))
+        return self._perm[key]
+
+    # ------------------------------------------------------------------------------------------ gradient helpers
+    @staticmethod
+    def _grad(p):
+        if p.grad is None:
+            p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+        return p.grad
+
+    def _conv_param_grads(self, conv, dy, x1, x2=None, perm=None, dy_cols=None):
+        """dW (tcgen05 wgrad, packed) -> reference layout; db via column sums."""
+        k = conv.weight.shape[-1]
+        c1 = x1.shape[-1]
+        c2 = x2.shape[-1] if x2 is not None else 0
+        cin_ref = conv.weight.shape[1]
+        dwp = ops.conv_wgrad(dy, x1, x2=x2, ntaps=k * k)
+        if x2 is None and c1 != cin_ref:  # zero-padded network input (3 -> 8 channels)
+            c1 = cin_ref
+        ops.unpack_conv_wgrad(dwp, c1, c2, k, out=self._grad(conv.weight), accumulate=True,
+                              row_perm=perm[0] if perm is not None else None)
+        if conv.bias is not None:
+            self._bias_grad(conv.bias, dy if dy_cols is None else dy_cols, perm)
+
+    def _bias_grad(self, bias, dy, perm=None):
+        g = self._grad(bias)
+        c = dy.shape[-1]
+        if perm is None and c == g.numel():
+            ops.col_sums(dy, g)
+        else:
+            tmp = torch.zeros(c, device=dy.device, dtype=F32)
+            ops.col_sums(dy, tmp)
+            if perm is not None:
+                g.index_add_(0, perm[1], tmp)
+            else:
+                g.add_(tmp[:g.numel()])
+
+    # ------------------------------------------------------------------------------------------ UNetBlock
+    def block_fwd(self, blk, x1, x2, params, training, seed, save):
+        c = NS(blk=blk, x1=x1, x2=x2, params=params, seed=seed)
+        cin1 = x1.shape[-1]
+        cin2 = x2.shape[-1] if x2 is not None else 0
+        cin, cout = cin1 + cin2, blk.out_channels
+        mode = 1 if blk.down else (2 if blk.up else 0)
+        c.mode = mode
+        c.drop_p = float(blk.dropout) if training else 0.0
+        c.sums0 = ops.chan_sums(x1, x2)
+        c.a0 = ops.gn_apply(x1, x2, c.sums0, blk.norm0.weight, blk.norm0.bias, _groups(cin), blk.norm0.eps,
+                            act=True, resample=mode)
+        # after the fused concat-GroupNorm the conv sees ONE tensor a0 with cin channels
+        c.h0 = ops.conv_fprop(c.a0, self.conv_w(blk.conv0), bias=blk.conv0.bias)
+        c.sums1 = ops.chan_sums(c.h0)
+        c.a1 = ops.gn_apply(c.h0, None, c.sums1, blk.norm1.weight, blk.norm1.bias, _groups(cout), blk.norm1.eps,
+                            params=params, act=True, drop_p=c.drop_p, seed=seed)
+        if blk.skip is not None and blk.skip.weight is not None:
+            res = ops.conv_fprop(x1, self.conv_w(blk.skip, cin1, cin2), x2=x2, bias=blk.skip.bias)
+        elif mode:
+            res = ops.resample(x1, mode)
+        else:
+            res = x1
+        c.h1 = ops.conv_fprop(c.a1, self.conv_w(blk.conv1), bias=blk.conv1.bias, residual=res)
+        out = c.h1
+        if blk.num_heads:
+            perm = self.qkv_perm(cout, blk.num_heads)
+            c.sums2 = ops.chan_sums(c.h1)
+            c.a2 = ops.gn_apply(c.h1, None, c.sums2, blk.norm2.weight, blk.norm2.bias, _groups(cout), blk.norm2.eps,
+                                act=False)
+            bq = self._cached(("qkvb", id(blk)), [blk.qkv.bias], lambda old: blk.qkv.bias.detach()[perm[1]].contiguous())
+            c.qkv = ops.conv_fprop(c.a2, self.conv_w(blk.qkv, perm=perm[0]), bias=bq)
+            c.att, c.p = ops.attention_fwd(c.qkv, blk.num_heads)
+            out = ops.conv_fprop(c.att, self.conv_w(blk.proj), bias=blk.proj.bias, residual=c.h1)
+        if save is not None:
+            save.append(c)
+        return out
+
+    def block_bwd(self, c, dout, dparams):
+        """dout: gradient at the block output.  Returns (dx1, dx2)."""
+        blk = c.blk
+        cin1 = c.x1.shape[-1]
+        cin2 = c.x2.shape[-1] if c.x2 is not None else 0
+        cin, cout = cin1 + cin2, blk.out_channels
+        if blk.num_heads:
+            perm = self.qkv_perm(cout, blk.num_heads)
+            self._conv_param_grads(blk.proj, dout, c.att)
+            datt = ops.conv_dgrad(dout, self.conv_w(blk.proj))
+            dqkv = ops.attention_bwd(datt, c.qkv, c.p, blk.num_heads)
+            self._conv_param_grads(blk.qkv, dqkv, c.a2, perm=perm)
+            da2 = ops.conv_dgrad(dqkv, self.conv_w(blk.qkv, perm=perm[0]))
+            dh1, _ = ops.gn_bwd(da2, c.h1, None, c.sums2, blk.norm2.weight, blk.norm2.bias, _groups(cout),
+                                blk.norm2.eps, act=False, dgamma=self._grad(blk.norm2.weight),
+                                dbeta=self._grad(blk.norm2.bias), add=dout, add_mode=0)
+        else:
+            dh1 = dout
+        # h1 = conv1(a1) + b1 + skip(x)
+        self._conv_param_grads(blk.conv1, dh1, c.a1)
+        da1 = ops.conv_dgrad(dh1, self.conv_w(blk.conv1))
+        dh0, _ = ops.gn_bwd(da1, c.h0, None, c.sums1, blk.norm1.weight, blk.norm1.bias, _groups(cout), blk.norm1.eps,
+                            params=c.params, act=True, drop_p=c.drop_p, seed=c.seed,
+                            dgamma=self._grad(blk.norm1.weight), dbeta=self._grad(blk.norm1.bias), dparams=dparams)
+        # h0 = conv0(a0) + b0
+        self._conv_param_grads(blk.conv0, dh0, c.a0)
+        da0 = ops.conv_dgrad(dh0, self.conv_w(blk.conv0))
+        if blk.skip is not None and blk.skip.weight is not None:
+            self._conv_param_grads(blk.skip, dh1, c.x1, c.x2)
+            add = ops.conv_dgrad(dh1, self.conv_w(blk.skip, cin1, cin2))
+            add_mode = 0
+        else:
+            add, add_mode = dh1, c.mode
+        return ops.gn_bwd(da0, c.x1, c.x2, c.sums0, blk.norm0.weight, blk.norm0.bias, _groups(cin), blk.norm0.eps,
+                          act=True, resample=c.mode, dgamma=self._grad(blk.norm0.weight),
+                          dbeta=self._grad(blk.norm0.bias), add=add, add_mode=add_mode)
+
+    # ------------------------------------------------------------------------------------------ embedding MLP
+    def embed_fwd(self, c_noise, aug, save):
+        net = self.net
+        e = NS()
+        pe = net.map_noise(c_noise)  # host glue on [B, mc]
+        e.aug16 = None
+        if net.map_augment is not None and aug is not None:
+            a16 = torch.zeros(aug.shape[0], 16, device=aug.device, dtype=F32)
+            a16[:, :aug.shape[1]] = aug
+            e.aug16 = ops.cast_bf16(a16)
+            pe = pe + ops.gemm_nt(e.aug16, self.aug_w())
+        e.pe_b = ops.cast_bf16(pe)
+        e.e0 = ops.gemm_nt(e.pe_b, self.lin_w(net.map_layer0), bias=net.map_layer0.bias)
+        _, e.s0b = ops.silu(e.e0, want_f32=False)
+        e.e1 = ops.gemm_nt(e.s0b, self.lin_w(net.map_layer1), bias=net.map_layer1.bias)
+        _, e.embb = ops.silu(e.e1, want_f32=False)
+        wall, ball = self.affine_all()
+        params_all = ops.gemm_nt(e.embb, wall, bias=ball)  # [B, sum 2*Cout] fp32: every block's (scale | shift)
+        if save is not None:
+            save.append(e)
+        return params_all
+
+    def _linear_grads(self, lin, dyb, xb):
+        """dW = dy^T x (MN-major x MN-major GEMM), db = column sums; dyb/xb bf16 [B, out] / [B, in]."""
+        dw = ops.gemm_tn(dyb, xb)
+        g = self._grad(lin.weight)
+        if dw.shape == g.shape:
+            g.add_(dw)
+        else:
+            g.add_(dw[:, :g.shape[1]])
+        if lin.bias is not None:
+            ops.col_sums(dyb, self._grad(lin.bias))
+
+    def embed_bwd(self, e, dparams_all):
+        net = self.net
+        dpb = ops.cast_bf16(dparams_all)
+        wall, _ = self.affine_all()
+        dwall = ops.gemm_tn(dpb, e.embb)  # [sum 2*Cout, emb]
+        for _, m, off in self.block_list:
+            o = m.affine.out_features
+            ops.unpack_conv_wgrad(dwall[off:off + o], net.emb_channels, 0, 1, out=self._grad(m.affine.weight),
+                                  accumulate=True)
+            ops.col_sums(dpb[:, off:off + o], self._grad(m.affine.bias))
+        demb = ops.gemm_nn(dpb, wall)
+        _, de1b = ops.silu_bwd(e.e1, demb, want_f32=False)
+        self._linear_grads(net.map_layer1, de1b, e.s0b)
+        ds0 = ops.gemm_nn(de1b, self.lin_w(net.map_layer1))
+        _, de0b = ops.silu_bwd(e.e0, ds0, want_f32=False)
+        self._linear_grads(net.map_layer0, de0b, e.pe_b)
+        if e.aug16 is not None:
+            dpe = ops.gemm_nn(de0b, self.lin_w(net.map_layer0))
+            self._linear_grads(net.map_augment, ops.cast_bf16(dpe), e.aug16)
+
+    # ------------------------------------------------------------------------------------------ decouple branch
+    def decouple_fwd(self, seq, x, save):
+        conv, sa = seq[0], seq[1]
+        d = NS(seq=seq, x=x)
+        d.wkey = ("dcw", id(conv))
+        wpk = self._cached(d.wkey, [conv.weight], lambda old: ops.pack_conv_weight(conv.weight.detach(), out=old))
+        d.h = ops.conv_fprop(x, wpk, bias=conv.bias)
+        d.w_map = sa.map.weight.detach().reshape(-1)
+        d.scal = torch.cat([sa.map.bias.detach(), sa.q_conv.weight.detach().reshape(-1), sa.q_conv.bias.detach(),
+                            sa.k_conv.weight.detach().reshape(-1), sa.k_conv.bias.detach()])
+        out, d.att, d.o = ops.spatial_att_fwd(d.h, x, d.w_map, d.scal)
+        if save is not None:
+            save.append(d)
+        return out
+
+    def decouple_bwd(self, d, dy):
+        """Returns the gradient w.r.t. the bottleneck x of this branch (conv path + identity path)."""
+        conv, sa = d.seq[0], d.seq[1]
+        c = d.x.shape[-1]
+        dw_map = torch.zeros(c, device=dy.device, dtype=F32)
+        dscal = torch.zeros(5, device=dy.device, dtype=F32)
+        dh = ops.spatial_att_bwd(dy, d.h, d.w_map, d.scal, d.att, d.o, dw_map, dscal)
+        self._grad(sa.map.weight).add_(dw_map.reshape(sa.map.weight.shape))
+        self._grad(sa.map.bias).add_(dscal[0:1])
+        self._grad(sa.q_conv.weight).add_(dscal[1:2].reshape(1, 1, 1, 1))
+        self._grad(sa.q_conv.bias).add_(dscal[2:3])
+        self._grad(sa.k_conv.weight).add_(dscal[3:4].reshape(1, 1, 1, 1))
+        self._grad(sa.k_conv.bias).add_(dscal[4:5])
+        dwp = ops.conv_wgrad(dh, d.x, ntaps=9)
+        ops.unpack_conv_wgrad(dwp, c, 0, 3, out=self._grad(conv.weight), accumulate=True)
+        ops.col_sums(dh, self._grad(conv.bias))
+        wpk = self._cache[d.wkey][1]
+        return ops.conv_dgrad(dh, wpk, residual=dy)
+
+    # ------------------------------------------------------------------------------------------ whole network
+    def _run_fwd(self, xin, c_noise, aug, training, tape):
+        net = self.net
+        save = tape.items if tape is not None else None
+        step_seed = (self.base_seed * 1000003 + next(self._seed_iter)) if training else 0
+        emb_save = [] if tape is not None else None
+        params_all = self.embed_fwd(c_noise, aug, emb_save)
+        boff = {id(m): off for _, m, off in self.block_list}
+        if tape is not None:
+            tape.emb = emb_save[0]
+            tape.dparams_all = torch.zeros_like(params_all)
+
+        def run_block(m, x1, x2, idx):
+            off = boff[id(m)]
+            return self.block_fwd(m, x1, x2, params_all[:, off:off + m.affine.out_features], training,
+                                  step_seed * 4099 + idx, save)
+
+        x = xin
+        skips = []
+        idx = 0
+        for name, m in net.enc.items():
+            if hasattr(m, "affine"):
+                x = run_block(m, x, None, idx)
+            else:
+                x = ops.conv_fprop(x, self.conv_w(m, c1=m.in_channels), bias=m.bias)
+                if tape is not None:
+                    tape.first = NS(conv=m, x=xin)
+            idx += 1
+            skips.append(x)
+        outs = []
+        for dec, dname, norm, oconv in ((net.dec, "decouple1", net.out_norm, net.out_conv),
+                                        (net.dec2, "decouple2", net.out_norm2, net.out_conv2)):
+            h = self.decouple_fwd(getattr(net, dname), x, save)
+            sk = list(skips)
+            for name, m in dec.items():
+                x2 = sk.pop() if h.shape[-1] != m.in_channels else None
+                h = run_block(m, h, x2, idx)
+                idx += 1
+            o = NS(x=h, norm=norm, conv=oconv)
+            o.sums = ops.chan_sums(h)
+            o.a = ops.gn_apply(h, None, o.sums, norm.weight, norm.bias, _groups(h.shape[-1]), norm.eps, act=True)
+            f = ops.conv_fprop(o.a, self.conv_w(oconv), bias=oconv.bias, out_dtype=F32, keep_pad=True)
+            if save is not None:
+                save.append(o)
+            outs.append(f)  # [N,H,W,4] fp32, channels >= img_channels are zero
+        if tape is not None:
+            tape.n_skips = len(skips)
+        return outs[0], outs[1]
+
+    def forward(self, x, sigma, aug=None, training=False, need_grad=False):
+        """EDMPrecond.forward.  x NCHW float, sigma [B] or scalar.  Returns (D_x, D_y, tape)."""
+        if not x.is_cuda:
+            raise RuntimeError("adm_b200: the UNet runs on CUDA (sm_100a) only; there is no CPU fallback")
+        x = x.to(F32).contiguous()
+        n = x.shape[0]
+        sigma = sigma.to(F32).reshape(-1)
+        if sigma.numel() == 1:
+            sigma = sigma.expand(n)
+        sigma = sigma.contiguous()
+        tape = NS(items=[], x=x, sigma=sigma) if need_grad else None
+        xin = ops.unet_input(x, sigma, ld_out=8)
+        f1, f2 = self._run_fwd(xin, sigma.log(), aug, training, tape)
+        d1, d2 = ops.unet_output(f1, f2, x, sigma)
+        return d1, d2, tape
+
+    def forward_raw(self, xin_nchw, noise_labels, aug=None):
+        """DhariwalUNet.forward on an already scaled input; returns (F_x, F_y) NCHW fp32 (inference only)."""
+        n = xin_nchw.shape[0]
+        ones = torch.full((n,), 1.0, device=xin_nchw.device)  # c_in(1) == 1: reuse the input kernel as a layout change
+        xin = ops.unet_input(xin_nchw.to(F32).contiguous(), ones, ld_out=8)
+        f1, f2 = self._run_fwd(xin, noise_labels.to(F32).reshape(-1).expand(n).contiguous(), aug, False, None)
+        c = self.net.out_channels
+        return (f1[..., :c].permute(0, 3, 1, 2).contiguous(), f2[..., :c].permute(0, 3, 1, 2).contiguous())
+
+    def backward(self, tape, dd1, dd2):
+        """Accumulates parameter gradients for upstream gradients (dD_x, dD_y), NCHW fp32."""
+        net = self.net
+        c_img = net.out_channels
+        df1, df2 = ops.unet_output_bwd(dd1.contiguous().float(), dd2.contiguous().float(), tape.sigma, ld_out=8)
+        items = tape.items
+        boff = {id(m): off for _, m, off in self.block_list}
+        dskips = [None] * tape.n_skips
+        dbott = None
+        pos = len(items)
+        for df in (df2, df1):  # decoders in reverse order of execution
+            pos -= 1
+            o = items[pos]
+            dfv = df[..., :c_img]
+            self._conv_param_grads(o.conv, dfv, o.a, dy_cols=df)
+            da = ops.conv_dgrad(dfv, self.conv_w(o.conv))
+            dh, _ = ops.gn_bwd(da, o.x, None, o.sums, o.norm.weight, o.norm.bias, _groups(o.x.shape[-1]), o.norm.eps,
+                               act=True, dgamma=self._grad(o.norm.weight), dbeta=self._grad(o.norm.bias))
+            si = 0  # forward pops skips from the end, so walking the decoder backwards meets skips[0], skips[1], ...
+            while not hasattr(items[pos - 1], "seq"):
+                pos -= 1
+                c = items[pos]
+                off = boff[id(c.blk)]
+                dx1, dx2 = self.block_bwd(c, dh, tape.dparams_all[:, off:off + c.blk.affine.out_features])
+                if c.x2 is not None:
+                    dskips[si] = dx2 if dskips[si] is None else ops.add_bf16(dskips[si], dx2)
+                    si += 1
+                dh = dx1
+            pos -= 1
+            dx = self.decouple_bwd(items[pos], dh)
+            dbott = dx if dbott is None else ops.add_bf16(dbott, dx)
+        # encoder, last block first; skips[i] is the output of encoder entry i
+        enc = list(net.enc.values())
+        d = dbott
+        for i in range(len(enc) - 1, -1, -1):
+            g = d if dskips[i] is None else ops.add_bf16(d, dskips[i])
+            m = enc[i]
+            if hasattr(m, "affine"):
+                pos -= 1
+                c = items[pos]
+                off = boff[id(m)]
+                d, _ = self.block_bwd(c, g, tape.dparams_all[:, off:off + m.affine.out_features])
+            else:
+                self._conv_param_grads(m, g, tape.first.x)
+        assert pos == 0, pos
+        self.embed_bwd(tape.emb, tape.dparams_all)
+
+
+class _UNetFn(torch.autograd.Function):
+    """One autograd node for the whole preconditioned UNet.  ``anchor`` only exists to make autograd call backward;
+    parameter gradients are accumulated into ``.grad`` by the engine itself."""
+
+    @staticmethod
+    def forward(ctx, anchor, engine, x, sigma, aug, training):
+        d1, d2, tape = engine.forward(x, sigma, aug, training=training, need_grad=True)
+        ctx.engine, ctx.tape = engine, tape
+        return d1, d2
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        tape, ctx.tape = ctx.tape, None
+        if tape is None:
+            raise RuntimeError("adm_b200 UNet: backward through the same forward twice is not supported")
+        if g1 is None:
+            g1 = torch.zeros_like(tape.x)
+        if g2 is None:
+            g2 = torch.zeros_like(tape.x)
+        ctx.engine.backward(tape, g1, g2)
+        return None, None, None, None, None, None
+
+
+def unet_apply(engine, x, sigma, aug=None):
+    net = engine.net
+    want_grad = torch.is_grad_enabled() and any(p.requires_grad for p in net.parameters())
+    if not want_grad:
+        d1, d2, _ = engine.forward(x, sigma, aug, training=net.training, need_grad=False)
+        return d1, d2
+    anchor = torch.zeros((), device=x.device, requires_grad=True)
+    return _UNetFn.apply(anchor, engine, x, sigma, aug, net.training)

@@ -115,12 +115,77 @@ int adm_gemm_batched(const adm_gemm_desc* desc, void* stream);
 
 /* ---------------------------------------------------------------- weight packing (derived bf16 caches of the fp32 masters)
  * w fp32 [cout][c1+c2][k][k] (reference layout, unet/uncond_unet.py:85) -> bf16 [cout][k*k][pad64(c1)+pad64(c2)] */
-int adm_pack_conv_weight(const float* w, void* wpk, int cout, int c1, int c2, int ksize, void* stream);
+int adm_pack_conv_weight(const float* w, void* wpk, int cout, int c1, int c2, int ksize, const int* row_perm,
+                         void* stream);
+/*   row_perm (optional, device int[cout]): packed row r holds reference row row_perm[r] — used to store the qkv
+ *   projection as (q | k | v) x heads x d instead of the reference's interleaved (head, d, {q,k,v}) order (:205). */
 /* inverse for gradients: packed fp32 [cout][k*k][kpad] -> reference layout fp32 [cout][c1+c2][k][k] (overwrite
  * when accumulate == 0, add otherwise)                                                                    */
 int adm_unpack_conv_wgrad(const float* dw_packed, float* dw, int cout, int c1, int c2, int ksize, int accumulate,
-                          void* stream);
+                          const int* row_perm, void* stream);
 int adm_cast_f32_bf16(const float* src, void* dst, long long numel, void* stream);
+
+/* ---------------------------------------------------------------- GroupNorm family (NHWC bf16, HBM-bound)
+ * Replaces torch.nn.functional.group_norm (unet/uncond_unet.py:128) and the elementwise chain around it in
+ * UNetBlock.forward (:191, :193-196, :200): silu, addcmul(shift, norm, scale+1), dropout, plus the depthwise 2x2
+ * resample of Conv2d.forward (:105-108) when it directly follows.  x1 (+ optional x2 = fused torch.cat, :570-571).
+ * sums: fp32 [n][c1+c2][2] = per-(sample, channel) sum and sum of squares.                                  */
+/* Optional device-resident u64 step counter mixed into every dropout seed (lets a captured CUDA graph draw fresh
+ * masks per replay); NULL disables. */
+int adm_set_seed_counter(const unsigned long long* dev_counter);
+int adm_chan_sums(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int hw,
+                  float* sums, void* stream);
+/* y = act(GN(x) [* (1 + scale) + shift]) with params = [n][ld_params] holding (scale | shift) or NULL; act 1 = SiLU;
+ * drop_p > 0 applies Philox dropout keyed by seed; resample 0 none / 1 2x2 average / 2 nearest x2.          */
+int adm_gn_apply(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int h, int w,
+                 int groups, float eps, const float* sums, const float* gamma, const float* beta, const float* params,
+                 long long ld_params, int act, float drop_p, unsigned long long seed, int resample, void* out,
+                 long long ldo, void* stream);
+/* Backward of adm_gn_apply.  dy: gradient at the op's output (its resolution).  Accumulates dgamma/dbeta (+=), writes
+ * dparams [n][ld_dparams] = (dscale | dshift), and dx1/dx2 (+ `add`, a skip-path gradient over the full channel range:
+ * add_mode 0 same resolution, 1 half resolution spread /4, 2 double resolution summed 2x2).  bsums: fp32 scratch
+ * [n][c][2].  dgamma == NULL skips the parameter gradients, dx1 == NULL skips the data gradient.             */
+int adm_gn_bwd(const void* dy, long long ldy, const void* x1, int c1, long long ld1, const void* x2, int c2,
+               long long ld2, int n, int h, int w, int groups, float eps, const float* sums, const float* gamma,
+               const float* beta, const float* params, long long ld_params, int act, float drop_p,
+               unsigned long long seed, int resample, float* bsums, float* dgamma, float* dbeta, float* dparams,
+               long long ld_dparams, const void* add, long long ldadd, int add_mode, void* dx1, long long ldx1,
+               void* dx2, long long ldx2, void* stream);
+/* out[c] += sum_rows x[row][c] (bias gradients, unet/uncond_unet.py:111-112 backward). */
+int adm_col_sums(const void* x, long long ld, long long rows, int c, float* out, void* stream);
+/* out = a + b (+ c): gradient fan-in of the skip connections (torch autograd's implicit adds, unet/uncond_unet.py:563-564) */
+int adm_add_bf16(const void* a, long long lda, const void* b, long long ldb, const void* c, long long ldc, void* out,
+                 long long ldo, long long rows, int ch, void* stream);
+/* skip-path resample of Conv2d(kernel=0, up/down) (unet/uncond_unet.py:181-182,105-108): mode 1 avg 2x2, 2 nearest x2 */
+int adm_resample(const void* x, long long ldx, int n, int h, int w, int c, int mode, void* out, long long ldo,
+                 void* stream);
+/* silu of the embedding MLP (unet/uncond_unet.py:549,556): y fp32 and/or bf16 copies (either may be NULL) */
+int adm_silu(const float* x, float* y, void* y_bf16, long long numel, void* stream);
+int adm_silu_bwd(const float* x, const float* dy, float* dx, void* dx_bf16, long long numel, void* stream);
+
+/* ---------------------------------------------------------------- attention pieces
+ * softmax over the key axis of S = Q^T K / sqrt(d) (unet/uncond_unet.py:207); P bf16 [rows][len], len <= 1024.
+ * backward: dS = scale * P * (dP - sum_j dP_j P_j).                                                           */
+int adm_softmax_fwd(const float* s, void* p, long long rows, int len, void* stream);
+int adm_softmax_bwd(const void* p, const float* dp, void* ds, float scale, long long rows, int len, void* stream);
+/* SpatialAtt + residual of the decouple branches (unet/uncond_unet.py:27-37, :566-567):
+ * out = softsign(softmax(q k^T) att) * h + res with att = h . w_map + b; scalars = {b_map, wq, bq, wk, bk}.   */
+int adm_spatial_att_fwd(const void* h, long long ldh, const void* res, long long ldr, const float* w_map,
+                        const float* scalars, int n, int hw, int c, void* out, long long ldo, float* att_save,
+                        float* o_save, void* stream);
+int adm_spatial_att_bwd(const void* dy, long long ldy, const void* h, long long ldh, const float* w_map,
+                        const float* scalars, const float* att_save, const float* o_save, int n, int hw, int c,
+                        void* dh, long long lddh, float* dw_map, float* dscalars, void* stream);
+
+/* ---------------------------------------------------------------- optimizer over the flat parameter arena
+ * train_uncond_dpm.py:292 (clip_grad_norm_ 1.0) + :179-180,296 (AdamW).  out += sum g^2.                      */
+int adm_sq_norm(const float* g, long long numel, float* out, void* stream);
+/* g_eff = g * grad_scale * min(1, max_norm / (sqrt(*sqnorm) * grad_scale + 1e-6)); torch.optim.AdamW update. */
+int adm_adamw(float* p, const float* g, float* m, float* v, long long numel, float lr, float beta1, float beta2,
+              float eps, float weight_decay, int step, float grad_scale, float max_norm, const float* sqnorm,
+              const float* hyper_dev, void* stream);
+/*   hyper_dev (optional, device fp32[3] = {lr, 1-beta1^step, sqrt(1-beta2^step)}) overrides lr/step so that a captured
+ *   CUDA graph of the step can be replayed with fresh values.                                                 */
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,343 @@
+"""Bring-up checks (dev tool for gpurun): GroupNorm / attention / SpatialAtt kernels against torch, then the whole
+UNet engine (forward, loss, per-parameter gradient cosine) against the oracle.  One subprocess per case."""
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+CASES = {}
+
+
+def case(fn):
+    CASES[fn.__name__] = fn
+    return fn
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item(), (a - b).abs().max().item()
+
+
+def _report(name, got, ref, tol):
+    r, m = _rel(got, ref)
+    ok = r < tol
+    print(f"  {name}: rel={r:.3e} maxabs={m:.3e} tol={tol:g} {'OK' if ok else 'FAIL'}", flush=True)
+    return ok
+
+
+@case
+def groupnorm():
+    import torch
+    import torch.nn.functional as F
+    from adm_b200 import ops
+    torch.manual_seed(0)
+    ok = True
+    for (n, hw, c1, c2, resample, act, use_params, drop) in [(4, 16, 192, 0, 0, True, True, 0.0),
+                                                             (4, 16, 384, 192, 0, True, False, 0.0),
+                                                             (2, 16, 64, 0, 1, True, False, 0.0),
+                                                             (2, 8, 128, 0, 2, True, False, 0.0),
+                                                             (3, 8, 384, 0, 0, False, False, 0.0),
+                                                             (2, 32, 8, 0, 0, True, False, 0.0)]:
+        c = c1 + c2
+        g = min(32, c // 4)
+        x1 = (torch.randn(n, hw, hw, c1, device="cuda") * 1.5 + 0.3).bfloat16()
+        x2 = (torch.randn(n, hw, hw, c2, device="cuda") * 0.7 - 0.2).bfloat16() if c2 else None
+        gamma = 1 + 0.1 * torch.randn(c, device="cuda")
+        beta = 0.1 * torch.randn(c, device="cuda")
+        pfull = 0.3 * torch.randn(n, 2 * c + 40, device="cuda")
+        params = pfull[:, 8:8 + 2 * c] if use_params else None
+        sums = ops.chan_sums(x1, x2)
+        y = ops.gn_apply(x1, x2, sums, gamma, beta, g, 1e-5, params=params, act=act, resample=resample)
+        xr = (torch.cat([x1, x2], -1) if c2 else x1).float().permute(0, 3, 1, 2).requires_grad_(True)
+        gr = gamma.clone().requires_grad_(True)
+        br = beta.clone().requires_grad_(True)
+        pr = params.clone().requires_grad_(True) if use_params else None
+        v = F.group_norm(xr, g, gr, br, 1e-5)
+        if use_params:
+            sc, sh = pr[:, :c].reshape(n, c, 1, 1), pr[:, c:].reshape(n, c, 1, 1)
+            v = torch.addcmul(sh, v, sc + 1)
+        if act:
+            v = F.silu(v)
+        if resample == 1:
+            v = F.avg_pool2d(v, 2)
+        elif resample == 2:
+            v = F.interpolate(v, scale_factor=2, mode="nearest")
+        tag = f"n{n} hw{hw} c{c1}+{c2} rs{resample} act{act} p{use_params}"
+        ok &= _report(f"gn_apply {tag}", y, v.permute(0, 2, 3, 1), 6e-3)
+        dy = torch.randn_like(v).bfloat16()
+        add = torch.randn(n, hw, hw, c, device="cuda").bfloat16()
+        v.backward(dy.float())
+        dgamma = torch.zeros(c, device="cuda")
+        dbeta = torch.zeros(c, device="cuda")
+        dpfull = torch.zeros_like(pfull)
+        dparams = dpfull[:, 8:8 + 2 * c] if use_params else None
+        dx1, dx2 = ops.gn_bwd(dy.permute(0, 2, 3, 1).contiguous(), x1, x2, sums, gamma, beta, g, 1e-5, params=params,
+                              act=act, resample=resample, dgamma=dgamma, dbeta=dbeta, dparams=dparams, add=add,
+                              add_mode=0)
+        dx = torch.cat([dx1, dx2], -1) if c2 else dx1
+        ok &= _report(f"gn_bwd dx {tag}", dx, xr.grad.permute(0, 2, 3, 1) + add.float(), 1e-2)
+        ok &= _report(f"gn_bwd dgamma {tag}", dgamma, gr.grad, 1e-2)
+        ok &= _report(f"gn_bwd dbeta {tag}", dbeta, br.grad, 1e-2)
+        if use_params:
+            ok &= _report(f"gn_bwd dparams {tag}", dparams, pr.grad, 1e-2)
+    # dropout: keep-rate and fwd/bwd mask consistency
+    n, hw, c = 2, 16, 192
+    x = torch.randn(n, hw, hw, c, device="cuda").bfloat16()
+    sums = ops.chan_sums(x)
+    gamma, beta = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
+    y0 = ops.gn_apply(x, None, sums, gamma, beta, 32, act=False)
+    y1 = ops.gn_apply(x, None, sums, gamma, beta, 32, act=False, drop_p=0.1, seed=77)
+    keep = (y1 != 0).float().mean().item()
+    print(f"  dropout keep-rate {keep:.4f} (expect ~0.9)")
+    ok &= abs(keep - 0.9) < 0.01
+    ok &= _report("dropout scale", y1[y1 != 0], (y0.float() / 0.9)[y1 != 0], 1e-2)
+    dy = torch.ones_like(y0)
+    dx_nodrop, _ = ops.gn_bwd(dy, x, None, sums, gamma, beta, 32, act=False, drop_p=0.0, dgamma=None)
+    # with dy = mask-consistent gradient: bwd(drop) on ones == bwd(nodrop) on the mask itself
+    mask = (y1 != 0).to(torch.bfloat16) / 0.9
+    dx_a, _ = ops.gn_bwd(dy, x, None, sums, gamma, beta, 32, act=False, drop_p=0.1, seed=77, dgamma=None)
+    dx_b, _ = ops.gn_bwd(mask.bfloat16(), x, None, sums, gamma, beta, 32, act=False, dgamma=None)
+    ok &= _report("dropout bwd mask", dx_a, dx_b, 2e-2)
+    return ok
+
+
+@case
+def small_ops():
+    import torch
+    import torch.nn.functional as F
+    from adm_b200 import ops
+    torch.manual_seed(1)
+    ok = True
+    x = torch.randn(4, 16, 16, 192, device="cuda").bfloat16()
+    ok &= _report("resample down", ops.resample(x, 1), F.avg_pool2d(x.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1), 5e-3)
+    ok &= _report("resample up", ops.resample(x, 2), F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2).permute(0, 2, 3, 1), 1e-6)
+    out = torch.zeros(192, device="cuda")
+    ok &= _report("col_sums", ops.col_sums(x, out), x.float().sum((0, 1, 2)), 1e-5)
+    wide = torch.randn(128, 4600 * 8, device="cuda").bfloat16()
+    out = torch.zeros(4600 * 8, device="cuda")
+    ok &= _report("col_sums wide", ops.col_sums(wide, out), wide.float().sum(0), 1e-5)
+    sl = wide[:, 1024:1024 + 768]
+    out = torch.zeros(768, device="cuda")
+    ok &= _report("col_sums slice", ops.col_sums(sl, out), sl.float().sum(0), 1e-5)
+    a, b, c = (torch.randn(2, 8, 8, 64, device="cuda").bfloat16() for _ in range(3))
+    ok &= _report("add3", ops.add_bf16(a, b, c), a.float() + b.float() + c.float(), 5e-3)
+    e = torch.randn(8, 768, device="cuda")
+    y, yb = ops.silu(e)
+    ok &= _report("silu", y, F.silu(e), 1e-6)
+    er = e.clone().requires_grad_(True)
+    g = torch.randn_like(e)
+    F.silu(er).backward(g)
+    dx, _ = ops.silu_bwd(e, g)
+    ok &= _report("silu_bwd", dx, er.grad, 1e-5)
+    s = torch.randn(6 * 4, 256, 256, device="cuda") * 3
+    p = ops.softmax_fwd(s)
+    ok &= _report("softmax", p, s.softmax(-1), 5e-3)
+    dp = torch.randn_like(s)
+    pr = p.float().requires_grad_(True)
+    sr = s.clone().requires_grad_(True)
+    sm = sr.softmax(-1)
+    sm.backward(dp)
+    ds = ops.softmax_bwd(p, dp, 0.125)
+    ok &= _report("softmax_bwd", ds, sr.grad * 0.125, 1e-2)
+    # optimizer
+    n = 1000003
+    pz = torch.randn(n, device="cuda")
+    g = torch.randn(n, device="cuda") * 0.01
+    pref = pz.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pref], lr=1e-3, weight_decay=1e-2, betas=(0.9, 0.99), eps=1e-8)
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for step in (1, 2, 3):
+        pref.grad = g.clone()
+        total = torch.nn.utils.clip_grad_norm_([pref], 1.0)
+        opt.step()
+        sq = torch.zeros(1, device="cuda")
+        ops.sq_norm(g, sq)
+        ops.adamw(pz, g, m, v, 1e-3, 0.9, 0.99, 1e-8, 1e-2, step, grad_scale=1.0, max_norm=1.0, sqnorm=sq)
+    ok &= _report("sq_norm", sq.sqrt(), total.reshape(1), 1e-5)
+    ok &= _report("adamw+clip 3 steps", pz, pref.detach(), 1e-5)
+    return ok
+
+
+@case
+def attention():
+    import torch
+    import numpy as np
+    from adm_b200 import ops
+    torch.manual_seed(2)
+    ok = True
+    for (n, hw_side, c) in [(4, 16, 384), (8, 8, 128), (16, 4, 384)]:
+        heads = c // 64
+        hw = hw_side * hw_side
+        qkv = (torch.randn(n, hw_side, hw_side, 3 * c, device="cuda") * 0.8).bfloat16()
+        a, p = ops.attention_fwd(qkv, heads)
+        qr = qkv.float().requires_grad_(True)
+        q, k, v = (qr[..., i * c:(i + 1) * c].reshape(n, hw, heads, 64).permute(0, 2, 1, 3) for i in range(3))
+        w = (q @ k.transpose(-1, -2) / np.sqrt(64)).softmax(-1)
+        ar = (w @ v).permute(0, 2, 1, 3).reshape(n, hw_side, hw_side, c)
+        ok &= _report(f"attn fwd n{n} hw{hw} c{c}", a, ar, 1e-2)
+        da = torch.randn_like(ar).bfloat16()
+        ar.backward(da.float())
+        dqkv = ops.attention_bwd(da, qkv, p, heads)
+        ok &= _report(f"attn bwd n{n} hw{hw} c{c}", dqkv, qr.grad, 2e-2)
+    return ok
+
+
+@case
+def spatial_att():
+    import torch
+    import torch.nn.functional as F
+    from adm_b200 import ops
+    torch.manual_seed(3)
+    ok = True
+    for (n, side, c) in [(8, 4, 384), (4, 8, 128)]:
+        h = torch.randn(n, side, side, c, device="cuda").bfloat16()
+        res = torch.randn(n, side, side, c, device="cuda").bfloat16()
+        w_map = (torch.randn(c, device="cuda") / c ** 0.5)
+        scal = torch.tensor([0.1, 0.8, -0.2, 1.1, 0.3], device="cuda")
+        out, att, o = ops.spatial_att_fwd(h, res, w_map, scal)
+        hr = h.float().requires_grad_(True)
+        wr = w_map.clone().requires_grad_(True)
+        sr = scal.clone().requires_grad_(True)
+        a = (hr * wr).sum(-1).reshape(n, side * side, 1) + sr[0]
+        q = a * sr[1] + sr[2]
+        k = (a * sr[3] + sr[4]).transpose(1, 2)
+        oo = F.softmax(q @ k, dim=-1) @ a
+        ref = F.softsign(oo).reshape(n, side, side, 1) * hr + res.float()
+        ok &= _report(f"spatial_att fwd {side}x{side}", out, ref, 5e-3)
+        dy = torch.randn_like(ref).bfloat16()
+        ref.backward(dy.float())
+        dw = torch.zeros(c, device="cuda")
+        ds = torch.zeros(5, device="cuda")
+        dh = ops.spatial_att_bwd(dy, h, w_map, scal, att, o, dw, ds)
+        ok &= _report(f"spatial_att dh {side}x{side}", dh, hr.grad, 1e-2)
+        ok &= _report(f"spatial_att dw_map {side}x{side}", dw, wr.grad, 1e-2)
+        ok &= _report(f"spatial_att dscal {side}x{side}", ds, sr.grad, 1e-2)
+    return ok
+
+
+def _unet_case(cfg, batch, seed_in, cos_tol):
+    import torch
+    from oracle import ddm_oracle as O
+    from adm_b200.unet.uncond_unet import EDMPrecond
+    from adm_b200.ddm.ddm_const import DDPM
+    from tests.golden.make_golden import inputs
+    dev = "cuda"
+    sd = O.make_state_dict(cfg, seed=0)
+    kw = {k: v for k, v in cfg.items() if k not in ("img_resolution", "img_channels", "label_dim")}
+    net = EDMPrecond(img_resolution=cfg["img_resolution"], img_channels=3, sigma_data=1.0, model_type="DhariwalUNet", **kw)
+    missing, unexpected = net.load_state_dict(sd, strict=True)
+    net = net.to(dev)
+    net.eval()  # dropout off for parity
+    model_cfg = dict(image_size=[cfg["img_resolution"]] * 2, sampling_timesteps=5, eps=1e-4, sigma_max=1, sigma_min=0.01,
+                     weighting_loss=True, use_l1=False, use_augment=False)
+    dpm = DDPM(model=net, cfg=model_cfg, **model_cfg).to(dev)
+    x, t, noise, aug = (a.to(dev) for a in inputs(cfg, batch, seed_in))
+    t0 = time.time()
+    loss, ld = dpm.p_losses(x, t, noise=noise, augment_labels=aug)
+    loss.backward()
+    torch.cuda.synchronize()
+    print(f"  engine fwd+bwd {time.time() - t0:.2f}s loss={loss.item():.4f}", flush=True)
+    # oracle on the GPU in fp32 (same torch ops as the CPU oracle) for speed
+    sdr = {k: v.to(dev).requires_grad_(not k.endswith("resample_filter")) for k, v in sd.items()}
+    xn = O.q_sample(x, noise, t)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    c_ref, e_ref = O.edm_precond_forward(sdr, cfg, xn, t, augment_labels=aug)
+    loss_ref, _ = O.ddm_loss(c_ref, e_ref, x, noise, t)
+    loss_ref.backward()
+    ok = True
+    with torch.no_grad():
+        c_pred, e_pred = net(xn, t, augment_labels=aug)
+    ok &= _report("C_pred", c_pred, c_ref, 2e-2)
+    ok &= _report("eps_pred", e_pred, e_ref, 2e-2)
+    rel = abs(loss.item() - loss_ref.item()) / abs(loss_ref.item())
+    print(f"  loss {loss.item():.5f} vs oracle {loss_ref.item():.5f} rel={rel:.3e} (tol 1e-2)", flush=True)
+    ok &= rel < 1e-2
+    worst = []
+    for name, p in net.named_parameters():
+        gref = sdr[name].grad
+        if p.grad is None:
+            worst.append((-1.0, name, "no grad"))
+            continue
+        a, b = p.grad.flatten().double(), gref.flatten().double()
+        cos = (a @ b / (a.norm() * b.norm() + 1e-30)).item()
+        ratio = (a.norm() / (b.norm() + 1e-30)).item()
+        worst.append((cos, name, f"norm ratio {ratio:.4f}"))
+    worst.sort(key=lambda z: z[0])
+    for cos, name, info in worst[:12]:
+        print(f"  grad cos {cos:.5f}  {name}  {info}", flush=True)
+    nbad = sum(1 for w in worst if w[0] < cos_tol)
+    print(f"  params {len(worst)}, below cos {cos_tol}: {nbad}; min cos {worst[0][0]:.5f}", flush=True)
+    ok &= nbad == 0
+    return ok, dpm, sd
+
+
+@case
+def unet_tiny():
+    from tests.golden.make_golden import TINY
+    ok, dpm, sd = _unet_case(TINY, 8, 1, 0.999)
+    # sampler parity (PSNR vs the fp64-state oracle trajectory with the same kernels' model replaced by the oracle net)
+    import torch
+    from oracle import ddm_oracle as O
+    g = torch.Generator().manual_seed(7)
+    x_T = torch.randn(8, 3, 16, 16, generator=g, dtype=torch.float64).cuda()
+    img = dpm.sample(batch_size=8, x_T=x_T)
+    sdr = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref = O.sample_fn_d(lambda xx, tt: O.edm_precond_forward(sdr, TINY, xx, tt), x_T, 5)
+    mse = ((img - ref) ** 2).mean().item()
+    psnr = 10 * torch.log10(torch.tensor(1.0 / max(mse, 1e-20))).item()
+    print(f"  sampler PSNR vs oracle: {psnr:.2f} dB (need >= 40)", flush=True)
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "sample_tiny.pt")).cuda()
+    mse_g = ((img - gold) ** 2).mean().item()
+    print(f"  sampler PSNR vs reference golden: {10 * torch.log10(torch.tensor(1.0 / max(mse_g, 1e-20))).item():.2f} dB")
+    return ok and psnr >= 40
+
+
+@case
+def unet_cifar():
+    from tests.golden.make_golden import CIFAR
+    cfg = dict(CIFAR)
+    ok, _, _ = _unet_case(cfg, 8, 1, 0.999)
+    return ok
+
+
+def main():
+    if len(sys.argv) > 1 and sys.argv[1] != "--all":
+        import torch
+        from adm_b200 import _lib
+        name = sys.argv[1]
+        t0 = time.time()
+        ok = CASES[name]()
+        torch.cuda.synchronize()
+        derr = _lib.load().adm_device_error()
+        print(f"[{name}] {'PASS' if ok and derr == 0 else 'FAIL'} device_error={derr} ({time.time() - t0:.1f}s)",
+              flush=True)
+        sys.exit(0 if ok and derr == 0 else 1)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    log = open(os.path.join(ROOT, "gpurun_out", "check_unet.log"), "w")
+    failed = []
+    for name in CASES:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), name], capture_output=True, text=True,
+                               timeout=600)
+            out = r.stdout + r.stderr[-4000:]
+            code = r.returncode
+        except subprocess.TimeoutExpired as e:
+            out = f"[{name}] TIMEOUT\n{e.stdout or ''}"
+            code = -9
+        log.write(out + "\n")
+        log.flush()
+        print(out, flush=True)
+        if code != 0:
+            failed.append(name)
+    print("FAILED:", failed, flush=True)
+    log.write(f"FAILED: {failed}\n")
+    sys.exit(1 if failed else 0)
+
+
+if __name__ == "__main__":
+    main()
