@@ -1,0 +1,226 @@
+"""Data-parallel training step around the DDPM module: flat parameter/gradient arenas, bucketed NCCL all-reduce
+overlapped with the engine's backward, fused clip + AdamW over the arena.
+
+Mirrors the step body of the reference Trainer (/root/reference/train_uncond_dpm.py:247-310): micro-batch loop,
+``clip_grad_norm_(1.0)`` (:292), AdamW(lr, weight_decay=1e-4) (:179-180), warm-up + polynomial LambdaLR (:169-182).
+Semantics we define explicitly (the reference's DDP wiring is accidental): gradients are the MEAN over
+ranks of per-rank gradients, reduced once per optimizer step (not per micro-batch).
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def completion_order(net):
+    """Parameters of EDMPrecond in the order their gradients are finalised by UNetEngine.backward."""
+    m = net.model
+    order = []
+
+    def block_params(blk):
+        names = []
+        if blk.num_heads:
+            names += ["proj", "qkv", "norm2"]
+        names += ["conv1", "norm1", "conv0", "skip", "norm0"]
+        for nme in names:
+            sub = getattr(blk, nme, None)
+            if sub is not None:
+                order.extend(p for p in sub.parameters())
+
+    for dec, dname, norm, oconv in ((m.dec2, "decouple2", m.out_norm2, m.out_conv2),
+                                    (m.dec, "decouple1", m.out_norm, m.out_conv)):
+        order.extend(oconv.parameters())
+        order.extend(norm.parameters())
+        for blk in reversed(list(dec.values())):
+            block_params(blk)
+        order.extend(getattr(m, dname).parameters())
+    for blk in reversed(list(m.enc.values())):
+        if hasattr(blk, "affine"):
+            block_params(blk)
+        else:
+            order.extend(blk.parameters())
+    for sec in (m.dec2, m.dec, m.enc):
+        for blk in sec.values():
+            if hasattr(blk, "affine"):
+                order.extend(blk.affine.parameters())
+    order.extend(m.map_layer1.parameters())
+    order.extend(m.map_layer0.parameters())
+    if m.map_augment is not None:
+        order.extend(m.map_augment.parameters())
+    seen, out = set(), []
+    for p in order:
+        if id(p) not in seen:
+            seen.add(id(p))
+            out.append(p)
+    rest = [p for p in net.parameters() if id(p) not in seen]
+    return out + rest
+
+
+class ParamArena:
+    """Re-homes every parameter (and its .grad) of a module into two flat fp32 buffers, in gradient-completion order."""
+
+    def __init__(self, module, order=None, align=4):
+        params = order if order is not None else list(module.parameters())
+        dev = params[0].device
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + align - 1) // align * align
+        self.params = params
+        self.offsets = offs
+        self.numel = total
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grads = torch.zeros(total, device=dev, dtype=torch.float32)
+        for p, o in zip(params, offs):
+            view = self.flat[o:o + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.grads[o:o + p.numel()].view(p.shape)
+
+    def rebind_grads(self):
+        """If someone set .grad to None (optimizer.zero_grad(set_to_none=True)), point it back into the arena."""
+        for p, o in zip(self.params, self.offsets):
+            g = p.grad
+            if g is None or g.data_ptr() != self.grads.data_ptr() + 4 * o:
+                p.grad = self.grads[o:o + p.numel()].view(p.shape)
+
+    def zero_grad(self):
+        self.grads.zero_()
+
+
+def lr_lambda(step, train_num_steps, lr, min_lr, warmup=5000):
+    """train_uncond_dpm.py:169-177: linear warm-up to 1 over `warmup` steps, then (1 - iter/total)^0.96 with a floor."""
+    if step < warmup:
+        return (step + 1) / warmup
+    return max(min_lr / lr, (1 - (step - warmup) / max(1, train_num_steps - warmup)) ** 0.96)
+
+
+class TrainStep:
+    """One data-parallel optimizer step of DDM-const training on this rank's GPU."""
+
+    def __init__(self, dpm, lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=1.0,
+                 grad_accum=1, bucket_mb=64, process_group=None, lr_schedule=None):
+        self.dpm = dpm
+        self.net = dpm.model
+        self.engine = self.net.model.engine
+        self.arena = ParamArena(self.net, completion_order(self.net))
+        self.m = torch.zeros_like(self.arena.flat)
+        self.v = torch.zeros_like(self.arena.flat)
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.max_grad_norm = max_grad_norm
+        self.grad_accum = grad_accum
+        self.step_count = 0
+        self.lr_schedule = lr_schedule
+        dev = self.arena.flat.device
+        self.sqnorm = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.hyper = torch.zeros(3, device=dev, dtype=torch.float32)
+        self.hyper_host = torch.zeros(3, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(3)
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.pg = process_group
+        # gradient buckets in completion order
+        n = self.arena.numel
+        per = max(1, bucket_mb * (1 << 20) // 4)
+        self.buckets = [(s, min(n, s + per)) for s in range(0, n, per)]
+        self.comm_stream = torch.cuda.Stream(device=dev) if (self.world > 1 and dev.type == "cuda") else None
+        self._param_end = {}
+        for p, o in zip(self.arena.params, self.arena.offsets):
+            self._param_end[id(p)] = o + p.numel()
+        self.engine.invalidate()
+
+    # ------------------------------------------------------------------------------------------ gradient reduction
+    # The arena is laid out in gradient-completion order, so "everything below offset X is final" grows monotonically
+    # during backward.  Each bucket is all-reduced (NCCL, sum) on a side stream the moment it is entirely final, which
+    # overlaps the transfer over NVLink with the rest of the backward pass.  1/world is folded into the AdamW kernel.
+    def _arm(self):
+        self._done_upto, self._next_bucket = 0, 0
+        self.engine.grad_hook = self._on_grads if self.world > 1 else None
+
+    def _on_grads(self, params):
+        for p in params:
+            e = self._param_end.get(id(p))
+            if e is not None and e > self._done_upto:
+                self._done_upto = e
+        self._flush(self._done_upto)
+
+    def _flush(self, upto):
+        if self._next_bucket >= len(self.buckets) or self.buckets[self._next_bucket][1] > upto:
+            return
+        if self.comm_stream is None:  # host tensors (gloo tests): reduce synchronously
+            while self._next_bucket < len(self.buckets) and self.buckets[self._next_bucket][1] <= upto:
+                s, e = self.buckets[self._next_bucket]
+                dist.all_reduce(self.arena.grads[s:e], op=dist.ReduceOp.SUM, group=self.pg)
+                self._next_bucket += 1
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            while self._next_bucket < len(self.buckets) and self.buckets[self._next_bucket][1] <= upto:
+                s, e = self.buckets[self._next_bucket]
+                dist.all_reduce(self.arena.grads[s:e], op=dist.ReduceOp.SUM, group=self.pg)
+                self._next_bucket += 1
+
+    def _allreduce(self):
+        """Reduce whatever the overlapped path has not launched yet, then join the side stream."""
+        if self.world == 1:
+            return
+        self._flush(self.arena.numel)
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self.engine.grad_hook = None
+
+    # ------------------------------------------------------------------------------------------ the step
+    def _set_hyper(self):
+        step = self.step_count
+        lr = self.lr * (self.lr_schedule(step - 1) if self.lr_schedule is not None else 1.0)
+        self.hyper_host[0] = lr
+        self.hyper_host[1] = 1.0 - self.betas[0] ** step
+        self.hyper_host[2] = math.sqrt(1.0 - self.betas[1] ** step)
+        self.hyper.copy_(self.hyper_host, non_blocking=True)
+
+    def optimizer_step(self):
+        self.step_count += 1
+        self._set_hyper()
+        self.device_update()
+
+    def device_update(self):
+        """Everything after backward that runs on the device (capturable in a CUDA graph)."""
+        a = self.arena
+        self._allreduce()
+        gscale = 1.0 / (self.world * self.grad_accum)
+        self.sqnorm.zero_()
+        ops.sq_norm(a.grads, self.sqnorm)
+        ops.adamw(a.flat, a.grads, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                  max(1, self.step_count), grad_scale=gscale, max_norm=self.max_grad_norm, sqnorm=self.sqnorm,
+                  hyper_dev=self.hyper)
+        a.zero_grad()
+        self.engine.invalidate()
+
+    def micro_step(self, x, t=None, noise=None, last=True, **kw):
+        """forward + backward of one micro-batch; returns the (detached) loss tensor.  Gradient reduction is armed only
+        on the last micro-batch of an accumulation window."""
+        self.arena.rebind_grads()
+        if last:
+            self._arm()
+        else:
+            self.engine.grad_hook = None
+        if t is None:
+            loss, _ = self.dpm(x, **kw)
+        else:
+            loss, _ = self.dpm.p_losses(x, t, noise=noise, **kw)
+        loss.backward()
+        return loss.detach()
+
+    def __call__(self, batches):
+        """batches: list of `grad_accum` image tensors (this rank's shard).  Returns the mean loss tensor."""
+        total = None
+        for i, x in enumerate(batches):
+            l = self.micro_step(x, last=(i == len(batches) - 1))
+            total = l if total is None else total + l
+        self.optimizer_step()
+        return total / len(batches)

@@ -45,6 +45,7 @@ class UNetEngine:
                     off += m.affine.out_features
         self.affine_total = off
         self._perm = {}
+        self.grad_hook = None  # callable(list_of_params) invoked as soon as those gradients are final (DP overlap)
 
     # ------------------------------------------------------------------------------------------ weight caches
     def invalidate(self):
@@ -106,6 +107,17 @@ class UNetEngine:
         return self._perm[key]
 
     # ------------------------------------------------------------------------------------------ gradient helpers
+    def _notify(self, *modules, skip_affine=True):
+        if self.grad_hook is None:
+            return
+        ps = []
+        for m in modules:
+            for name, p in m.named_parameters():
+                if skip_affine and name.startswith("affine."):
+                    continue
+                ps.append(p)
+        self.grad_hook(ps)
+
     @staticmethod
     def _grad(p):
         if p.grad is None:
@@ -393,18 +405,21 @@ class UNetEngine:
             da = ops.conv_dgrad(dfv, self.conv_w(o.conv))
             dh, _ = ops.gn_bwd(da, o.x, None, o.sums, o.norm.weight, o.norm.bias, _groups(o.x.shape[-1]), o.norm.eps,
                                act=True, dgamma=self._grad(o.norm.weight), dbeta=self._grad(o.norm.bias))
+            self._notify(o.conv, o.norm)
             si = 0  # forward pops skips from the end, so walking the decoder backwards meets skips[0], skips[1], ...
             while not hasattr(items[pos - 1], "seq"):
                 pos -= 1
                 c = items[pos]
                 off = boff[id(c.blk)]
                 dx1, dx2 = self.block_bwd(c, dh, tape.dparams_all[:, off:off + c.blk.affine.out_features])
+                self._notify(c.blk)
                 if c.x2 is not None:
                     dskips[si] = dx2 if dskips[si] is None else ops.add_bf16(dskips[si], dx2)
                     si += 1
                 dh = dx1
             pos -= 1
             dx = self.decouple_bwd(items[pos], dh)
+            self._notify(items[pos].seq)
             dbott = dx if dbott is None else ops.add_bf16(dbott, dx)
         # encoder, last block first; skips[i] is the output of encoder entry i
         enc = list(net.enc.values())
@@ -419,8 +434,10 @@ class UNetEngine:
                 d, _ = self.block_bwd(c, g, tape.dparams_all[:, off:off + m.affine.out_features])
             else:
                 self._conv_param_grads(m, g, tape.first.x)
+            self._notify(m)
         assert pos == 0, pos
         self.embed_bwd(tape.emb, tape.dparams_all)
+        self._notify(net, skip_affine=False)
 
 
 class _UNetFn(torch.autograd.Function):
