@@ -82,79 +82,24 @@ static inline int threads_for(int nvec) {  // a multiple of nvec (threads keep a
     return nvec * (256 / nvec);
 }
 
-// ------------------------------------------------------------------------------------------------ chan_sums
-// grid (chunks, N); sums [N][C][2] accumulated atomically (zeroed by the host wrapper).
-__global__ void __launch_bounds__(256) chan_sums_kernel(const __nv_bfloat16* __restrict__ x1, int c1, long long ld1,
-                                                        const __nv_bfloat16* __restrict__ x2, int c2, long long ld2,
-                                                        int hw, float* __restrict__ sums) {
-    const int C = c1 + c2, V = C >> 3, V1 = c1 >> 3;
-    const int n = blockIdx.y;
-    const int tpv = blockDim.x / V;  // pixel lanes (V <= blockDim) ; for V > blockDim handled by the loop below
-    extern __shared__ float sm[];    // [blockDim][16]
-    if (V <= static_cast<int>(blockDim.x)) {
-        const int v = threadIdx.x % V, lane = threadIdx.x / V;
-        float s[8], q[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-        if (lane < tpv) {
-            const __nv_bfloat16* base = v < V1 ? x1 + 1LL * n * hw * ld1 + v * 8 : x2 + 1LL * n * hw * ld2 + (v - V1) * 8;
-            const long long ld = v < V1 ? ld1 : ld2;
-            for (int p = blockIdx.x * tpv + lane; p < hw; p += gridDim.x * tpv) {
-                const Vec8 a = load8(base + p * ld);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { s[i] += a.v[i]; q[i] += a.v[i] * a.v[i]; }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { sm[threadIdx.x * 16 + i] = s[i]; sm[threadIdx.x * 16 + 8 + i] = q[i]; }
-        __syncthreads();
-        // thread t < V*8 reduces channel t over the pixel lanes
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            const int vv = c >> 3, i = c & 7;
-            float a = 0.f, b = 0.f;
-            for (int l = 0; l < tpv; ++l) {
-                a += sm[(l * V + vv) * 16 + i];
-                b += sm[(l * V + vv) * 16 + 8 + i];
-            }
-            atomicAdd(sums + (1LL * n * C + c) * 2, a);
-            atomicAdd(sums + (1LL * n * C + c) * 2 + 1, b);
-        }
-    } else {
-        // wide tensors (C > 2048): each thread walks several channel vectors
-        for (int v = threadIdx.x; v < V; v += blockDim.x) {
-            float s[8], q[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-            const __nv_bfloat16* base = v < V1 ? x1 + 1LL * n * hw * ld1 + v * 8 : x2 + 1LL * n * hw * ld2 + (v - V1) * 8;
-            const long long ld = v < V1 ? ld1 : ld2;
-            for (int p = blockIdx.x; p < hw; p += gridDim.x) {
-                const Vec8 a = load8(base + p * ld);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { s[i] += a.v[i]; q[i] += a.v[i] * a.v[i]; }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                atomicAdd(sums + (1LL * n * C + v * 8 + i) * 2, s[i]);
-                atomicAdd(sums + (1LL * n * C + v * 8 + i) * 2 + 1, q[i]);
-            }
-        }
-    }
-}
-
-// Per-channel affine of sample n into shared memory: y = x * A[c] + B[c]; also mean/rstd per channel's group.
-// sums: [N][C][2]; params: [N][2C] (scale | shift) or null.
-__device__ __forceinline__ void group_affine_to_smem(const float* __restrict__ sums, const float* __restrict__ gamma,
-                                                     const float* __restrict__ beta, const float* __restrict__ params,
-                                                     long long ldp, int n, int C, int G, int hw, float eps, float* sA, float* sB,
-                                                     float* sMean, float* sRstd) {
+// ------------------------------------------------------------------------------------------------ gn_stats
+// Pass 1 of GroupNorm: per-(n, c) sum / sum of squares (atomics into `sums`), and — in the LAST block of each sample
+// (ticket counter) — the per-(n, c) coefficient table coef[n][c] = {A, B, mean, rstd} with y = x*A + B folding
+// mean, rstd, gamma, beta and the adaptive (1 + scale), shift.  grid (chunks, N); blockDim is a multiple of V = C/8 so
+// each thread stays on one channel vector and keeps its partials in registers.
+__device__ __forceinline__ void gn_finish_coef(const float* __restrict__ sums, const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, const float* __restrict__ params,
+                                               long long ldp, int n, int C, int G, int hw, float eps,
+                                               float4* __restrict__ coef) {
     const int cpg = C / G;
     const float inv_cnt = 1.f / (static_cast<float>(cpg) * static_cast<float>(hw));
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int g = c / cpg;
         float s = 0.f, q = 0.f;
         for (int j = 0; j < cpg; ++j) {
-            s += sums[(1LL * n * C + g * cpg + j) * 2];
-            q += sums[(1LL * n * C + g * cpg + j) * 2 + 1];
+            const float2 t = __ldcg(reinterpret_cast<const float2*>(sums) + (1LL * n * C + g * cpg + j));
+            s += t.x;
+            q += t.y;
         }
         const float mean = s * inv_cnt;
         const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
@@ -166,31 +111,88 @@ __device__ __forceinline__ void group_affine_to_smem(const float* __restrict__ s
             a *= sc;
             b = b * sc + sh;
         }
-        sA[c] = a;
-        sB[c] = b;
-        if (sMean != nullptr) { sMean[c] = mean; sRstd[c] = rstd; }
+        coef[1LL * n * C + c] = make_float4(a, b, mean, rstd);
     }
+}
+
+__global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int c1, long long ld1,
+                                                       const __nv_bfloat16* __restrict__ x2, int c2, long long ld2,
+                                                       int hw, float* __restrict__ sums, unsigned int* __restrict__ tickets,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ params, long long ldp, int G, float eps,
+                                                       float4* __restrict__ coef) {
+    const int C = c1 + c2, V = C >> 3, V1 = c1 >> 3;
+    const int n = blockIdx.y;
+    const int tpv = blockDim.x / V;
+    extern __shared__ float sm[];  // [blockDim][16]
+    __shared__ int s_last;
+    const int v = threadIdx.x % V, lane = threadIdx.x / V;
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+    if (lane < tpv) {
+        const __nv_bfloat16* base = v < V1 ? x1 + 1LL * n * hw * ld1 + v * 8 : x2 + 1LL * n * hw * ld2 + (v - V1) * 8;
+        const long long ld = v < V1 ? ld1 : ld2;
+        const int step = gridDim.x * tpv;
+        int p = blockIdx.x * tpv + lane;
+        for (; p + 3 * step < hw; p += 4 * step) {  // 4 independent 16 B loads in flight
+            const Vec8 a0 = load8(base + p * ld), a1 = load8(base + (p + step) * ld);
+            const Vec8 a2 = load8(base + (p + 2 * step) * ld), a3 = load8(base + (p + 3 * step) * ld);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                s[i] += (a0.v[i] + a1.v[i]) + (a2.v[i] + a3.v[i]);
+                q[i] += (a0.v[i] * a0.v[i] + a1.v[i] * a1.v[i]) + (a2.v[i] * a2.v[i] + a3.v[i] * a3.v[i]);
+            }
+        }
+        for (; p < hw; p += step) {
+            const Vec8 a = load8(base + p * ld);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s[i] += a.v[i]; q[i] += a.v[i] * a.v[i]; }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sm[threadIdx.x * 16 + i] = s[i]; sm[threadIdx.x * 16 + 8 + i] = q[i]; }
     __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int vv = c >> 3, i = c & 7;
+        float a = 0.f, b = 0.f;
+        for (int l = 0; l < tpv; ++l) {
+            a += sm[(l * V + vv) * 16 + i];
+            b += sm[(l * V + vv) * 16 + 8 + i];
+        }
+        atomicAdd(sums + (1LL * n * C + c) * 2, a);
+        atomicAdd(sums + (1LL * n * C + c) * 2 + 1, b);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(tickets + n, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        gn_finish_coef(sums, gamma, beta, params, ldp, n, C, G, hw, eps, coef);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ gn_apply (forward)
-// resample: 0 none, 1 down (2x2 average of the activated values), 2 up (nearest x2).  grid (chunks, N).
+// y = act(x*A + B) (+ dropout) (+ 2x2 avg-pool / nearest-up on the store).  grid (chunks, N).
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int c1, long long ld1,
                                                        const __nv_bfloat16* __restrict__ x2, int c2, long long ld2,
-                                                       int H, int W, int G, float eps, const float* __restrict__ sums,
-                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       const float* __restrict__ params, long long ldp, int act, float drop_p,
-                                                       unsigned long long seed, int resample,
+                                                       int H, int W, const float4* __restrict__ coef, int act,
+                                                       float drop_p, unsigned long long seed, int resample,
                                                        __nv_bfloat16* __restrict__ out, long long ldo,
                                                        const unsigned long long* __restrict__ seed_dev) {
     if (seed_dev != nullptr) seed += *seed_dev * 0x9E3779B97F4A7C15ull;
-
     extern __shared__ float sm[];
     const int C = c1 + c2, V = C >> 3, V1 = c1 >> 3;
     float* sA = sm;
     float* sB = sm + C;
     const int n = blockIdx.y, hw = H * W;
-    group_affine_to_smem(sums, gamma, beta, params, ldp, n, C, G, hw, eps, sA, sB, nullptr, nullptr);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float4 t = coef[1LL * n * C + c];
+        sA[c] = t.x;
+        sB[c] = t.y;
+    }
+    __syncthreads();
     const int Ho = resample == 1 ? H / 2 : (resample == 2 ? H * 2 : H);
     const int Wo = resample == 1 ? W / 2 : (resample == 2 ? W * 2 : W);
     const int iter_hw = resample == 1 ? Ho * Wo : hw;  // iterate over output pixels when pooling, input otherwise
@@ -206,19 +208,17 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
         Vec8 o;
         if (resample == 1) {
             const int ho = p / Wo, wo = p % Wo;
+            Vec8 xv[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) xv[d] = load8(base + ((2 * ho + (d >> 1)) * W + 2 * wo + (d & 1)) * ld);
 #pragma unroll
             for (int j = 0; j < 8; ++j) o.v[j] = 0.f;
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
-                const int pi = (2 * ho + (d >> 1)) * W + 2 * wo + (d & 1);
-                const Vec8 xv = load8(base + pi * ld);
-                float ds[8];
-                if (drop_p > 0.f) dropout_scales(seed, (1ULL * n * hw + pi) * V + v, drop_p, ds);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    float y = xv.v[j] * a[j] + b[j];
+                    float y = xv[d].v[j] * a[j] + b[j];
                     if (act) y = silu_f(y);
-                    if (drop_p > 0.f) y *= ds[j];
                     o.v[j] += 0.25f * y;
                 }
             }
@@ -264,15 +264,12 @@ __device__ __forceinline__ void grad_preact(const __nv_bfloat16* __restrict__ dy
         for (int j = 0; j < 8; ++j) g.v[j] *= 0.25f;
     } else {
         const int h = p / W, w = p % W, Wo = W * 2, Ho = H * 2;
+        Vec8 t[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g.v[j] = 0.f;
+        for (int d = 0; d < 4; ++d)
+            t[d] = load8(dy + (1LL * n * Ho * Wo + 1LL * (2 * h + (d >> 1)) * Wo + 2 * w + (d & 1)) * ldy + v * 8);
 #pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            const long long po = 1LL * (2 * h + (d >> 1)) * Wo + 2 * w + (d & 1);
-            const Vec8 t = load8(dy + (1LL * n * Ho * Wo + po) * ldy + v * 8);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) g.v[j] += t.v[j];
-        }
+        for (int j = 0; j < 8; ++j) g.v[j] = (t[0].v[j] + t[1].v[j]) + (t[2].v[j] + t[3].v[j]);
     }
     float ds[8];
     if (drop_p > 0.f) dropout_scales(seed, (1ULL * n * hw + p) * V + v, drop_p, ds);
@@ -286,28 +283,28 @@ __device__ __forceinline__ void grad_preact(const __nv_bfloat16* __restrict__ dy
 }
 
 // ------------------------------------------------------------------------------------------------ gn_bwd_reduce
-// bsums [N][C][2]: S1 = sum_p dv, S2 = sum_p dv * xhat.  grid (chunks, N), blockDim multiple of V.
+// bsums [N][C][2]: S1 = sum_p dv, S2 = sum_p dv * xhat.  The last block of each sample turns them into
+//   bcoef[n][c] = {gamma' = gamma (1 + scale), mean_g(dv gamma'), mean_g(dv gamma' xhat), 0}
+// and the parameter gradients: dgamma[c] += (1+sc) S2, dbeta[c] += (1+sc) S1, dparams[n] = (gamma S2 + beta S1 | S1).
 __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, long long ldy,
                                                             const __nv_bfloat16* __restrict__ x1, int c1, long long ld1,
                                                             const __nv_bfloat16* __restrict__ x2, int c2, long long ld2,
-                                                            int H, int W, int G, float eps,
-                                                            const float* __restrict__ sums,
+                                                            int H, int W, int G, const float4* __restrict__ coef,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta,
-                                                            const float* __restrict__ params, long long ldp, int act, float drop_p,
-                                                            unsigned long long seed, int resample,
-                                                            float* __restrict__ bsums,
+                                                            const float* __restrict__ params, long long ldp, int act,
+                                                            float drop_p, unsigned long long seed, int resample,
+                                                            float* __restrict__ bsums, unsigned int* __restrict__ tickets,
+                                                            float4* __restrict__ bcoef, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, float* __restrict__ dparams,
+                                                            long long ld_dparams,
                                                             const unsigned long long* __restrict__ seed_dev) {
     if (seed_dev != nullptr) seed += *seed_dev * 0x9E3779B97F4A7C15ull;
     extern __shared__ float sm[];
+    __shared__ int s_last;
     const int C = c1 + c2, V = C >> 3, V1 = c1 >> 3;
-    float* sA = sm;
-    float* sB = sA + C;
-    float* sMean = sB + C;
-    float* sRstd = sMean + C;
-    float* red = sRstd + C;  // [blockDim][16]
+    float* red = sm;  // [blockDim][16]
     const int n = blockIdx.y, hw = H * W;
-    group_affine_to_smem(sums, gamma, beta, params, ldp, n, C, G, hw, eps, sA, sB, sMean, sRstd);
     const int tpv = blockDim.x / V;
     const int v = threadIdx.x % V, lane = threadIdx.x / V;
     float s1[8], s2[8];
@@ -319,9 +316,23 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const __nv_bfloat16*
         float a[8], b[8], mu[8], rs[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            a[j] = sA[v * 8 + j]; b[j] = sB[v * 8 + j]; mu[j] = sMean[v * 8 + j]; rs[j] = sRstd[v * 8 + j];
+            const float4 t = coef[1LL * n * C + v * 8 + j];
+            a[j] = t.x; b[j] = t.y; mu[j] = t.z; rs[j] = t.w;
         }
-        for (int p = blockIdx.x * tpv + lane; p < hw; p += gridDim.x * tpv) {
+        const int step = gridDim.x * tpv;
+        int p = blockIdx.x * tpv + lane;
+        for (; p + step < hw; p += 2 * step) {  // two pixels in flight
+            const Vec8 xa = load8(base + p * ld), xb = load8(base + (p + step) * ld);
+            float da[8], db[8];
+            grad_preact(dy, ldy, n, H, W, p, v, V, resample, act, drop_p, seed, xa, a, b, da);
+            grad_preact(dy, ldy, n, H, W, p + step, v, V, resample, act, drop_p, seed, xb, a, b, db);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s1[j] += da[j] + db[j];
+                s2[j] += da[j] * (xa.v[j] - mu[j]) * rs[j] + db[j] * (xb.v[j] - mu[j]) * rs[j];
+            }
+        }
+        for (; p < hw; p += step) {
             const Vec8 xv = load8(base + p * ld);
             float dv[8];
             grad_preact(dy, ldy, n, H, W, p, v, V, resample, act, drop_p, seed, xv, a, b, dv);
@@ -345,47 +356,51 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const __nv_bfloat16*
         atomicAdd(bsums + (1LL * n * C + c) * 2, a);
         atomicAdd(bsums + (1LL * n * C + c) * 2 + 1, b);
     }
-}
-
-// dgamma[c] += sum_n (1+sc) S2, dbeta[c] += sum_n (1+sc) S1, dparams[n][c] = gamma*S2 + beta*S1, dparams[n][C+c] = S1
-__global__ void __launch_bounds__(256) gn_bwd_params_kernel(const float* __restrict__ bsums,
-                                                            const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta,
-                                                            const float* __restrict__ params, long long ldp, int N, int C,
-                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                            float* __restrict__ dparams, long long ld_dparams) {
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
-        float dg = 0.f, db = 0.f;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(tickets + n, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // ---- per-sample epilogue (one block per sample): gamma' S1 / gamma' S2 into smem, then group means
+    float* gs1 = sm;       // [C]
+    float* gs2 = sm + C;   // [C]
+    const int cpg = C / G;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float2 t = __ldcg(reinterpret_cast<const float2*>(bsums) + (1LL * n * C + c));
         const float ga = gamma[c], be = beta[c];
-        for (int n = 0; n < N; ++n) {
-            const float s1 = bsums[(1LL * n * C + c) * 2], s2 = bsums[(1LL * n * C + c) * 2 + 1];
-            const float sc = params != nullptr ? 1.f + params[n * ldp + c] : 1.f;
-            dg += sc * s2;
-            db += sc * s1;
-            if (dparams != nullptr) {
-                dparams[n * ld_dparams + c] = ga * s2 + be * s1;
-                dparams[n * ld_dparams + C + c] = s1;
-            }
+        const float sc = params != nullptr ? 1.f + params[n * ldp + c] : 1.f;
+        gs1[c] = ga * sc * t.x;
+        gs2[c] = ga * sc * t.y;
+        if (dgamma != nullptr) {
+            atomicAdd(dgamma + c, sc * t.y);
+            atomicAdd(dbeta + c, sc * t.x);
         }
-        dgamma[c] += dg;
-        dbeta[c] += db;
+        if (dparams != nullptr) {
+            dparams[n * ld_dparams + c] = ga * t.y + be * t.x;
+            dparams[n * ld_dparams + C + c] = t.x;
+        }
+    }
+    __syncthreads();
+    const float inv_cnt = 1.f / (static_cast<float>(cpg) * static_cast<float>(hw));
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        float m1 = 0.f, m2 = 0.f;
+        for (int j = 0; j < cpg; ++j) { m1 += gs1[g * cpg + j]; m2 += gs2[g * cpg + j]; }
+        const float sc = params != nullptr ? 1.f + params[n * ldp + c] : 1.f;
+        bcoef[1LL * n * C + c] = make_float4(gamma[c] * sc, m1 * inv_cnt, m2 * inv_cnt, 0.f);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ gn_bwd_apply
-// add: optional gradient to accumulate into dx (skip path).  add_mode 0: same resolution; 1: `add` lives at half
-// resolution and is spread as add/4 (block had a 2x2 avg-pool skip); 2: `add` lives at double resolution and is summed
-// over its 2x2 patch (block had a nearest-up skip).
+// dx = rstd * (dv*gamma' - M1 - xhat*M2) (+ add).  add: optional skip-path gradient over the full channel range;
+// add_mode 0: same resolution; 1: half resolution, spread as add/4; 2: double resolution, summed over the 2x2 patch.
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, long long ldy,
                                                            const __nv_bfloat16* __restrict__ x1, int c1, long long ld1,
                                                            const __nv_bfloat16* __restrict__ x2, int c2, long long ld2,
-                                                           int H, int W, int G, float eps,
-                                                           const float* __restrict__ sums,
-                                                           const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta,
-                                                           const float* __restrict__ params, long long ldp, int act, float drop_p,
+                                                           int H, int W, const float4* __restrict__ coef,
+                                                           const float4* __restrict__ bcoef, int act, float drop_p,
                                                            unsigned long long seed, int resample,
-                                                           const float* __restrict__ bsums,
                                                            const __nv_bfloat16* __restrict__ add, long long ldadd,
                                                            int add_mode, __nv_bfloat16* __restrict__ dx1, long long ldx1,
                                                            __nv_bfloat16* __restrict__ dx2, long long ldx2,
@@ -397,25 +412,15 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __nv_bfloat16* 
     float* sB = sA + C;
     float* sMean = sB + C;
     float* sRstd = sMean + C;
-    float* sG = sRstd + C;   // gamma' = gamma * (1 + scale)
-    float* sM1 = sG + C;     // mean_g(dv * gamma')
-    float* sM2 = sM1 + C;    // mean_g(dv * gamma' * xhat)
-    const int n = blockIdx.y, hw = H * W, cpg = C / G;
-    group_affine_to_smem(sums, gamma, beta, params, ldp, n, C, G, hw, eps, sA, sB, sMean, sRstd);
-    for (int c = threadIdx.x; c < C; c += blockDim.x)
-        sG[c] = gamma[c] * (params != nullptr ? 1.f + params[n * ldp + c] : 1.f);
-    __syncthreads();
-    const float inv_cnt = 1.f / (static_cast<float>(cpg) * static_cast<float>(hw));
+    float* sG = sRstd + C;
+    float* sM1 = sG + C;
+    float* sM2 = sM1 + C;
+    const int n = blockIdx.y, hw = H * W;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c / cpg;
-        float m1 = 0.f, m2 = 0.f;
-        for (int j = 0; j < cpg; ++j) {
-            const int cc = g * cpg + j;
-            m1 += sG[cc] * bsums[(1LL * n * C + cc) * 2];
-            m2 += sG[cc] * bsums[(1LL * n * C + cc) * 2 + 1];
-        }
-        sM1[c] = m1 * inv_cnt;
-        sM2[c] = m2 * inv_cnt;
+        const float4 t = coef[1LL * n * C + c];
+        const float4 u = bcoef[1LL * n * C + c];
+        sA[c] = t.x; sB[c] = t.y; sMean[c] = t.z; sRstd[c] = t.w;
+        sG[c] = u.x; sM1[c] = u.y; sM2[c] = u.z;
     }
     __syncthreads();
     const long long total = 1LL * hw * V;
@@ -426,6 +431,24 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __nv_bfloat16* 
         const __nv_bfloat16* base = first ? x1 + 1LL * n * hw * ld1 + v * 8 : x2 + 1LL * n * hw * ld2 + (v - V1) * 8;
         const long long ld = first ? ld1 : ld2;
         const Vec8 xv = load8(base + p * ld);
+        Vec8 addv;
+        if (add != nullptr) {  // issue the skip-gradient loads early
+            const int h = p / W, w = p % W;
+            if (add_mode == 0) {
+                addv = load8(add + (1LL * n * hw + p) * ldadd + v * 8);
+            } else if (add_mode == 1) {
+                addv = load8(add + (1LL * n * (H / 2) * (W / 2) + (h >> 1) * (W / 2) + (w >> 1)) * ldadd + v * 8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) addv.v[j] *= 0.25f;
+            } else {
+                Vec8 t[4];
+#pragma unroll
+                for (int d = 0; d < 4; ++d)
+                    t[d] = load8(add + (1LL * n * 4 * hw + 1LL * (2 * h + (d >> 1)) * (2 * W) + 2 * w + (d & 1)) * ldadd + v * 8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) addv.v[j] = (t[0].v[j] + t[1].v[j]) + (t[2].v[j] + t[3].v[j]);
+            }
+        }
         float a[8], b[8], dv[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { a[j] = sA[v * 8 + j]; b[j] = sB[v * 8 + j]; }
@@ -437,25 +460,9 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __nv_bfloat16* 
             const float xhat = (xv.v[j] - sMean[c]) * sRstd[c];
             o.v[j] = sRstd[c] * (dv[j] * sG[c] - sM1[c] - xhat * sM2[c]);
         }
-        if (add != nullptr) {  // skip-path gradient, laid out over the full (concatenated) channel range
-            const int h = p / W, w = p % W;
-            if (add_mode == 0) {
-                const Vec8 t = load8(add + (1LL * n * hw + p) * ldadd + v * 8);
+        if (add != nullptr) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o.v[j] += t.v[j];
-            } else if (add_mode == 1) {
-                const Vec8 t = load8(add + (1LL * n * (H / 2) * (W / 2) + (h >> 1) * (W / 2) + (w >> 1)) * ldadd + v * 8);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o.v[j] += 0.25f * t.v[j];
-            } else {
-#pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    const long long po = 1LL * (2 * h + (d >> 1)) * (2 * W) + 2 * w + (d & 1);
-                    const Vec8 t = load8(add + (1LL * n * 4 * hw + po) * ldadd + v * 8);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) o.v[j] += t.v[j];
-                }
-            }
+            for (int j = 0; j < 8; ++j) o.v[j] += addv.v[j];
         }
         if (first) store8(dx1 + (1LL * n * hw + p) * ldx1 + v * 8, o);
         else store8(dx2 + (1LL * n * hw + p) * ldx2 + (v - V1) * 8, o);
@@ -573,7 +580,7 @@ static const unsigned long long* g_seed_dev = nullptr;
 
 static int grid_for(long long work, int threads, int n_batch) {
     long long blocks = (work + threads - 1) / threads;
-    long long cap = (4LL * num_sms() + n_batch - 1) / n_batch;
+    long long cap = (8LL * num_sms() + n_batch - 1) / n_batch;
     if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
@@ -600,43 +607,49 @@ int adm_set_seed_counter(const unsigned long long* dev_counter) {
     return 0;
 }
 
-int adm_chan_sums(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int hw,
-                  float* sums, void* stream) {
+int adm_gn_stats(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int hw,
+                 int groups, float eps, const float* gamma, const float* beta, const float* params,
+                 long long ld_params, float* work, float* coef, void* stream) {
     const int C = c1 + c2;
-    ADM_REQUIRE(c1 > 0 && c1 % 8 == 0 && c2 % 8 == 0 && (x2 != nullptr || c2 == 0), "chan_sums: channels must be multiples of 8");
+    ADM_REQUIRE(c1 > 0 && c1 % 8 == 0 && c2 % 8 == 0 && (x2 != nullptr || c2 == 0) && C % groups == 0,
+                "gn_stats: channels must be multiples of 8 and divisible by groups");
+    ADM_REQUIRE(C <= 2048, "gn_stats: C too large");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    cudaMemsetAsync(sums, 0, sizeof(float) * 2 * n * C, s);
+    cudaMemsetAsync(work, 0, sizeof(float) * (2LL * n * C + n), s);
     const int V = C / 8;
     const int threads = threads_for(V);
-    const int tpv = V <= threads ? threads / V : 1;
+    const int tpv = threads / V;
     dim3 grid(grid_for(hw, tpv, n), n);
-    chan_sums_kernel<<<grid, threads, threads * 16 * sizeof(float), s>>>(static_cast<const bf16*>(x1), c1, ld1,
-                                                                        static_cast<const bf16*>(x2), c2, ld2, hw, sums);
-    ADM_CHECK_LAUNCH("chan_sums");
+    gn_stats_kernel<<<grid, threads, threads * 16 * sizeof(float), s>>>(
+        static_cast<const bf16*>(x1), c1, ld1, static_cast<const bf16*>(x2), c2, ld2, hw, work,
+        reinterpret_cast<unsigned int*>(work + 2LL * n * C), gamma, beta, params, ld_params, groups, eps,
+        reinterpret_cast<float4*>(coef));
+    ADM_CHECK_LAUNCH("gn_stats");
     return 0;
 }
 
 int adm_gn_apply(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int h, int w,
-                 int groups, float eps, const float* sums, const float* gamma, const float* beta, const float* params,
-                 long long ld_params, int act, float drop_p, unsigned long long seed, int resample, void* out, long long ldo, void* stream) {
+                 const float* coef, int act, float drop_p, unsigned long long seed, int resample, void* out,
+                 long long ldo, void* stream) {
     const int C = c1 + c2;
-    ADM_REQUIRE(c1 > 0 && c1 % 8 == 0 && c2 % 8 == 0 && C % groups == 0, "gn_apply: bad channels / groups");
+    ADM_REQUIRE(c1 > 0 && c1 % 8 == 0 && c2 % 8 == 0, "gn_apply: channels must be multiples of 8");
     ADM_REQUIRE(resample == 0 || (resample == 1 && h % 2 == 0 && w % 2 == 0) || resample == 2, "gn_apply: bad resample");
     ADM_REQUIRE(C <= 4096, "gn_apply: C too large for the shared-memory affine table");
     const long long work = 1LL * (resample == 1 ? (h / 2) * (w / 2) : h * w) * (C / 8);
-    dim3 grid(grid_for(work, 256, n), n);
+    dim3 grid(grid_for(work, 256 * 2, n), n);
     gn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const bf16*>(x1), c1, ld1, static_cast<const bf16*>(x2), c2, ld2, h, w, groups, eps, sums, gamma,
-        beta, params, ld_params, act, drop_p, seed, resample, static_cast<bf16*>(out), ldo, g_seed_dev);
+        static_cast<const bf16*>(x1), c1, ld1, static_cast<const bf16*>(x2), c2, ld2, h, w,
+        reinterpret_cast<const float4*>(coef), act, drop_p, seed, resample, static_cast<bf16*>(out), ldo, g_seed_dev);
     ADM_CHECK_LAUNCH("gn_apply");
     return 0;
 }
 
 int adm_gn_bwd(const void* dy, long long ldy, const void* x1, int c1, long long ld1, const void* x2, int c2,
-               long long ld2, int n, int h, int w, int groups, float eps, const float* sums, const float* gamma,
+               long long ld2, int n, int h, int w, int groups, const float* coef, const float* gamma,
                const float* beta, const float* params, long long ld_params, int act, float drop_p,
-               unsigned long long seed, int resample, float* bsums, float* dgamma, float* dbeta, float* dparams, long long ld_dparams, const void* add,
-               long long ldadd, int add_mode, void* dx1, long long ldx1, void* dx2, long long ldx2, void* stream) {
+               unsigned long long seed, int resample, float* work, float* bcoef, float* dgamma, float* dbeta,
+               float* dparams, long long ld_dparams, const void* add, long long ldadd, int add_mode, void* dx1,
+               long long ldx1, void* dx2, long long ldx2, void* stream) {
     const int C = c1 + c2;
     ADM_REQUIRE(c1 > 0 && c1 % 8 == 0 && c2 % 8 == 0 && C % groups == 0, "gn_bwd: bad channels / groups");
     ADM_REQUIRE(C <= 2048, "gn_bwd: C too large");
@@ -644,28 +657,26 @@ int adm_gn_bwd(const void* dy, long long ldy, const void* x1, int c1, long long 
     const bf16* dyp = static_cast<const bf16*>(dy);
     const bf16* x1p = static_cast<const bf16*>(x1);
     const bf16* x2p = static_cast<const bf16*>(x2);
-    cudaMemsetAsync(bsums, 0, sizeof(float) * 2 * n * C, s);
+    cudaMemsetAsync(work, 0, sizeof(float) * (2LL * n * C + n), s);
     const int V = C / 8;
     const int threads = threads_for(V);
     const int tpv = threads / V;
     {
-        dim3 grid(grid_for(h * w, tpv, n), n);
-        const size_t smem = (4 * C + threads * 16) * sizeof(float);
-        gn_bwd_reduce_kernel<<<grid, threads, smem, s>>>(dyp, ldy, x1p, c1, ld1, x2p, c2, ld2, h, w, groups, eps, sums,
-                                                         gamma, beta, params, ld_params, act, drop_p, seed, resample, bsums, g_seed_dev);
+        dim3 grid(grid_for(h * w, tpv * 2, n), n);
+        size_t smem = threads * 16 * sizeof(float);
+        if (smem < 2 * C * sizeof(float)) smem = 2 * C * sizeof(float);
+        gn_bwd_reduce_kernel<<<grid, threads, smem, s>>>(
+            dyp, ldy, x1p, c1, ld1, x2p, c2, ld2, h, w, groups, reinterpret_cast<const float4*>(coef), gamma, beta,
+            params, ld_params, act, drop_p, seed, resample, work, reinterpret_cast<unsigned int*>(work + 2LL * n * C),
+            reinterpret_cast<float4*>(bcoef), dgamma, dbeta, dparams, ld_dparams, g_seed_dev);
         ADM_CHECK_LAUNCH("gn_bwd_reduce");
     }
-    if (dgamma != nullptr) {
-        gn_bwd_params_kernel<<<(C + 255) / 256, 256, 0, s>>>(bsums, gamma, beta, params, ld_params, n, C, dgamma, dbeta, dparams,
-                                                             ld_dparams);
-        ADM_CHECK_LAUNCH("gn_bwd_params");
-    }
     if (dx1 != nullptr) {
-        dim3 grid(grid_for(1LL * h * w * V, 256, n), n);
+        dim3 grid(grid_for(1LL * h * w * V, 256 * 2, n), n);
         gn_bwd_apply_kernel<<<grid, 256, 7 * C * sizeof(float), s>>>(
-            dyp, ldy, x1p, c1, ld1, x2p, c2, ld2, h, w, groups, eps, sums, gamma, beta, params, ld_params, act, drop_p,
-            seed, resample, bsums, static_cast<const bf16*>(add), ldadd, add_mode, static_cast<bf16*>(dx1), ldx1,
-            static_cast<bf16*>(dx2), ldx2, g_seed_dev);
+            dyp, ldy, x1p, c1, ld1, x2p, c2, ld2, h, w, reinterpret_cast<const float4*>(coef),
+            reinterpret_cast<const float4*>(bcoef), act, drop_p, seed, resample, static_cast<const bf16*>(add), ldadd,
+            add_mode, static_cast<bf16*>(dx1), ldx1, static_cast<bf16*>(dx2), ldx2, g_seed_dev);
         ADM_CHECK_LAUNCH("gn_bwd_apply");
     }
     return 0;

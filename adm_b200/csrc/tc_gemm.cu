@@ -246,13 +246,24 @@ int adm_conv_wgrad(const void* dy, int cout, long long ld_dy, const void* x1, in
     p.ntaps = ntaps;
     p.batches = ntaps; p.bdiv = ntaps; p.c_col_lo = kpad;
     p.a_mn = 1; p.b_mn = 1;
-    // split K (pixels) so that the grid covers the machine a few times over
+    // split K (pixels): pick the split that minimises waves x (k-iterations per tile + epilogue cost) for the
+    // persistent grid — fewer, fuller waves beat "more tiles" (wave quantisation), and fewer splits mean fewer atomics.
     const int base_tiles = ntaps * p.m_tiles * p.n_tiles;
-    int splits = (4 * num_sms() + base_tiles - 1) / base_tiles;
-    if (splits > p.k_total) splits = p.k_total;
-    if (splits < 1) splits = 1;
-    p.k_iters = (p.k_total + splits - 1) / splits;
-    p.splits = (p.k_total + p.k_iters - 1) / p.k_iters;
+    {
+        const int sms = num_sms();
+        const int epi = 6;  // epilogue cost of one tile in k-iteration units (fp32 vector atomics)
+        long long best_cost = -1;
+        int best_s = 1;
+        for (int s = 1; s <= p.k_total && s <= 64; ++s) {
+            const int k_per = (p.k_total + s - 1) / s;
+            const int s_eff = (p.k_total + k_per - 1) / k_per;
+            const long long waves = (1LL * base_tiles * s_eff + sms - 1) / sms;
+            const long long cost = waves * (k_per + epi);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = s_eff; }
+        }
+        p.k_iters = (p.k_total + best_s - 1) / best_s;
+        p.splits = (p.k_total + p.k_iters - 1) / p.k_iters;
+    }
     p.C = dw; p.ldc = 1LL * ntaps * kpad; p.out_mode = OUT_F32_ATOMIC;
     (void)pixels;
     CUtensorMap ma, mb, mb2;

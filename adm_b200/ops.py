@@ -289,47 +289,52 @@ def _src(x):
     return x.data_ptr(), x.shape[-1], x.stride(-2)
 
 
-def chan_sums(x1, x2=None):
-    """fp32 [N, C1+C2, 2]: per-(sample, channel) sum and sum of squares over H*W."""
+def gn_stats(x1, x2, gamma, beta, groups, eps=1e-5, params=None):
+    """GroupNorm pass 1 over the (fused concat of) x1, x2: returns coef fp32 [N, C, 4] = {A, B, mean, rstd}."""
     _need_cuda(x1)
     n, h, w, _ = x1.shape
     p1, c1, ld1 = _src(x1)
     p2, c2, ld2 = _src(x2)
-    sums = torch.empty(n, c1 + c2, 2, device=x1.device, dtype=F32)
-    check(_lib.load().adm_chan_sums(p1, c1, ld1, p2, c2, ld2, n, h * w, _ptr(sums), _stream()), "chan_sums")
-    return sums
+    c = c1 + c2
+    work = torch.empty(2 * n * c + n, device=x1.device, dtype=F32)
+    coef = torch.empty(n, c, 4, device=x1.device, dtype=F32)
+    ldp = params.stride(0) if params is not None else 0
+    check(_lib.load().adm_gn_stats(p1, c1, ld1, p2, c2, ld2, n, h * w, groups, float(eps), _ptr(gamma), _ptr(beta),
+                                   _ptr(params), ldp, _ptr(work), _ptr(coef), _stream()), "gn_stats")
+    return coef
 
 
-def gn_apply(x1, x2, sums, gamma, beta, groups, eps=1e-5, params=None, act=True, drop_p=0.0, seed=0, resample=0):
+def gn_apply(x1, x2, coef, act=True, drop_p=0.0, seed=0, resample=0):
     n, h, w, _ = x1.shape
     p1, c1, ld1 = _src(x1)
     p2, c2, ld2 = _src(x2)
     ho, wo = (h // 2, w // 2) if resample == 1 else ((2 * h, 2 * w) if resample == 2 else (h, w))
     out = torch.empty(n, ho, wo, c1 + c2, device=x1.device, dtype=BF16)
-    ldp = params.stride(0) if params is not None else 0
-    check(_lib.load().adm_gn_apply(p1, c1, ld1, p2, c2, ld2, n, h, w, groups, float(eps), _ptr(sums), _ptr(gamma),
-                                   _ptr(beta), _ptr(params), ldp, int(act), float(drop_p), int(seed) & 0xFFFFFFFFFFFFFFFF,
-                                   int(resample),
-                                   _ptr(out), out.stride(2), _stream()), "gn_apply")
+    check(_lib.load().adm_gn_apply(p1, c1, ld1, p2, c2, ld2, n, h, w, _ptr(coef), int(act), float(drop_p),
+                                   int(seed) & 0xFFFFFFFFFFFFFFFF, int(resample), _ptr(out), out.stride(2), _stream()),
+          "gn_apply")
     return out
 
 
-def gn_bwd(dy, x1, x2, sums, gamma, beta, groups, eps=1e-5, params=None, act=True, drop_p=0.0, seed=0, resample=0,
+def gn_bwd(dy, x1, x2, coef, gamma, beta, groups, params=None, act=True, drop_p=0.0, seed=0, resample=0,
            dgamma=None, dbeta=None, dparams=None, add=None, add_mode=0, need_dx=True):
     """Returns (dx1, dx2).  dgamma/dbeta are accumulated in place; dparams ([N, 2C] view) is overwritten."""
     n, h, w, _ = x1.shape
     p1, c1, ld1 = _src(x1)
     p2, c2, ld2 = _src(x2)
+    c = c1 + c2
     assert dy.dtype == BF16 and dy.stride(-1) == 1
-    bsums = torch.empty(n, c1 + c2, 2, device=x1.device, dtype=F32)
+    work = torch.empty(2 * n * c + n, device=x1.device, dtype=F32)
+    bcoef = torch.empty(n, c, 4, device=x1.device, dtype=F32)
     dx1 = torch.empty(n, h, w, c1, device=x1.device, dtype=BF16) if need_dx else None
     dx2 = torch.empty(n, h, w, c2, device=x1.device, dtype=BF16) if (need_dx and x2 is not None) else None
     ldp = params.stride(0) if params is not None else 0
     lddp = dparams.stride(0) if dparams is not None else 0
-    check(_lib.load().adm_gn_bwd(_ptr(dy), dy.stride(-2), p1, c1, ld1, p2, c2, ld2, n, h, w, groups, float(eps),
-                                 _ptr(sums), _ptr(gamma), _ptr(beta), _ptr(params), ldp, int(act), float(drop_p),
-                                 int(seed) & 0xFFFFFFFFFFFFFFFF, int(resample), _ptr(bsums), _ptr(dgamma), _ptr(dbeta), _ptr(dparams), lddp,
-                                 _ptr(add), add.stride(-2) if add is not None else 0, int(add_mode), _ptr(dx1),
+    check(_lib.load().adm_gn_bwd(_ptr(dy), dy.stride(-2), p1, c1, ld1, p2, c2, ld2, n, h, w, groups, _ptr(coef),
+                                 _ptr(gamma), _ptr(beta), _ptr(params), ldp, int(act), float(drop_p),
+                                 int(seed) & 0xFFFFFFFFFFFFFFFF, int(resample), _ptr(work), _ptr(bcoef), _ptr(dgamma),
+                                 _ptr(dbeta), _ptr(dparams), lddp, _ptr(add),
+                                 add.stride(-2) if add is not None else 0, int(add_mode), _ptr(dx1),
                                  dx1.stride(2) if dx1 is not None else 0, _ptr(dx2),
                                  dx2.stride(2) if dx2 is not None else 0, _stream()), "gn_bwd")
     return dx1, dx2

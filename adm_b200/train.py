@@ -131,6 +131,11 @@ class TrainStep:
         for p, o in zip(self.arena.params, self.arena.offsets):
             self._param_end[id(p)] = o + p.numel()
         self.engine.invalidate()
+        # device-resident step counter mixed into every dropout seed (fresh masks per CUDA-graph replay)
+        self.seed_counter = torch.zeros(1, device=dev, dtype=torch.int64) if dev.type == "cuda" else None
+        if self.seed_counter is not None:
+            ops.set_seed_counter(self.seed_counter)
+        self.graph = None
 
     # ------------------------------------------------------------------------------------------ gradient reduction
     # The arena is laid out in gradient-completion order, so "everything below offset X is final" grows monotonically
@@ -175,18 +180,57 @@ class TrainStep:
         self.engine.grad_hook = None
 
     # ------------------------------------------------------------------------------------------ the step
-    def _set_hyper(self):
+    def _fill_hyper_host(self):
         step = self.step_count
         lr = self.lr * (self.lr_schedule(step - 1) if self.lr_schedule is not None else 1.0)
         self.hyper_host[0] = lr
         self.hyper_host[1] = 1.0 - self.betas[0] ** step
         self.hyper_host[2] = math.sqrt(1.0 - self.betas[1] ** step)
-        self.hyper.copy_(self.hyper_host, non_blocking=True)
 
     def optimizer_step(self):
         self.step_count += 1
-        self._set_hyper()
+        self._fill_hyper_host()
+        self.hyper.copy_(self.hyper_host, non_blocking=True)
+        if self.seed_counter is not None:
+            self.seed_counter.add_(1)
         self.device_update()
+
+    # ------------------------------------------------------------------------------------------ CUDA graph
+    def capture(self, x_example, warmup=2):
+        """Captures one full step (forward, backward, [all-reduce], clip + AdamW, weight re-pack) on `x_example`'s
+        shape into a CUDA graph.  Per-step scalars (lr, bias corrections, dropout seed counter) live in device memory."""
+        assert self.grad_accum == 1, "graph capture covers the single-micro-batch step"
+        self.static_x = x_example.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.micro_step(self.static_x)
+                self.optimizer_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.step_count += 1
+        self._fill_hyper_host()
+        g = torch.cuda.CUDAGraph()
+        from . import _lib
+        l0 = _lib.load().adm_launch_count()
+        with torch.cuda.graph(g):
+            self.hyper.copy_(self.hyper_host, non_blocking=True)
+            self.seed_counter.add_(1)
+            self.static_loss = self.micro_step(self.static_x)
+            self.device_update()
+        self.launches_per_step = _lib.load().adm_launch_count() - l0  # kernels of ours inside one replay
+        self.graph = g
+        return g
+
+    def replay(self, x=None):
+        """One optimizer step through the captured graph; `x` (device or pinned host) is copied into the static input."""
+        if x is not None:
+            self.static_x.copy_(x, non_blocking=True)
+        self.step_count += 1
+        self._fill_hyper_host()
+        self.graph.replay()
+        return self.static_loss
 
     def device_update(self):
         """Everything after backward that runs on the device (capturable in a CUDA graph)."""

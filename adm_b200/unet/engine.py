@@ -160,14 +160,12 @@ class UNetEngine:
         mode = 1 if blk.down else (2 if blk.up else 0)
         c.mode = mode
         c.drop_p = float(blk.dropout) if training else 0.0
-        c.sums0 = ops.chan_sums(x1, x2)
-        c.a0 = ops.gn_apply(x1, x2, c.sums0, blk.norm0.weight, blk.norm0.bias, _groups(cin), blk.norm0.eps,
-                            act=True, resample=mode)
+        c.sums0 = ops.gn_stats(x1, x2, blk.norm0.weight, blk.norm0.bias, _groups(cin), blk.norm0.eps)
+        c.a0 = ops.gn_apply(x1, x2, c.sums0, act=True, resample=mode)
         # after the fused concat-GroupNorm the conv sees ONE tensor a0 with cin channels
         c.h0 = ops.conv_fprop(c.a0, self.conv_w(blk.conv0), bias=blk.conv0.bias)
-        c.sums1 = ops.chan_sums(c.h0)
-        c.a1 = ops.gn_apply(c.h0, None, c.sums1, blk.norm1.weight, blk.norm1.bias, _groups(cout), blk.norm1.eps,
-                            params=params, act=True, drop_p=c.drop_p, seed=seed)
+        c.sums1 = ops.gn_stats(c.h0, None, blk.norm1.weight, blk.norm1.bias, _groups(cout), blk.norm1.eps, params=params)
+        c.a1 = ops.gn_apply(c.h0, None, c.sums1, act=True, drop_p=c.drop_p, seed=seed)
         if blk.skip is not None and blk.skip.weight is not None:
             res = ops.conv_fprop(x1, self.conv_w(blk.skip, cin1, cin2), x2=x2, bias=blk.skip.bias)
         elif mode:
@@ -178,9 +176,8 @@ class UNetEngine:
         out = c.h1
         if blk.num_heads:
             perm = self.qkv_perm(cout, blk.num_heads)
-            c.sums2 = ops.chan_sums(c.h1)
-            c.a2 = ops.gn_apply(c.h1, None, c.sums2, blk.norm2.weight, blk.norm2.bias, _groups(cout), blk.norm2.eps,
-                                act=False)
+            c.sums2 = ops.gn_stats(c.h1, None, blk.norm2.weight, blk.norm2.bias, _groups(cout), blk.norm2.eps)
+            c.a2 = ops.gn_apply(c.h1, None, c.sums2, act=False)
             bq = self._cached(("qkvb", id(blk)), [blk.qkv.bias], lambda old: blk.qkv.bias.detach()[perm[1]].contiguous())
             c.qkv = ops.conv_fprop(c.a2, self.conv_w(blk.qkv, perm=perm[0]), bias=bq)
             c.att, c.p = ops.attention_fwd(c.qkv, blk.num_heads)
@@ -203,14 +200,14 @@ class UNetEngine:
             self._conv_param_grads(blk.qkv, dqkv, c.a2, perm=perm)
             da2 = ops.conv_dgrad(dqkv, self.conv_w(blk.qkv, perm=perm[0]))
             dh1, _ = ops.gn_bwd(da2, c.h1, None, c.sums2, blk.norm2.weight, blk.norm2.bias, _groups(cout),
-                                blk.norm2.eps, act=False, dgamma=self._grad(blk.norm2.weight),
+                                act=False, dgamma=self._grad(blk.norm2.weight),
                                 dbeta=self._grad(blk.norm2.bias), add=dout, add_mode=0)
         else:
             dh1 = dout
         # h1 = conv1(a1) + b1 + skip(x)
         self._conv_param_grads(blk.conv1, dh1, c.a1)
         da1 = ops.conv_dgrad(dh1, self.conv_w(blk.conv1))
-        dh0, _ = ops.gn_bwd(da1, c.h0, None, c.sums1, blk.norm1.weight, blk.norm1.bias, _groups(cout), blk.norm1.eps,
+        dh0, _ = ops.gn_bwd(da1, c.h0, None, c.sums1, blk.norm1.weight, blk.norm1.bias, _groups(cout),
                             params=c.params, act=True, drop_p=c.drop_p, seed=c.seed,
                             dgamma=self._grad(blk.norm1.weight), dbeta=self._grad(blk.norm1.bias), dparams=dparams)
         # h0 = conv0(a0) + b0
@@ -222,7 +219,7 @@ class UNetEngine:
             add_mode = 0
         else:
             add, add_mode = dh1, c.mode
-        return ops.gn_bwd(da0, c.x1, c.x2, c.sums0, blk.norm0.weight, blk.norm0.bias, _groups(cin), blk.norm0.eps,
+        return ops.gn_bwd(da0, c.x1, c.x2, c.sums0, blk.norm0.weight, blk.norm0.bias, _groups(cin),
                           act=True, resample=c.mode, dgamma=self._grad(blk.norm0.weight),
                           dbeta=self._grad(blk.norm0.bias), add=add, add_mode=add_mode)
 
@@ -352,8 +349,8 @@ class UNetEngine:
                 h = run_block(m, h, x2, idx)
                 idx += 1
             o = NS(x=h, norm=norm, conv=oconv)
-            o.sums = ops.chan_sums(h)
-            o.a = ops.gn_apply(h, None, o.sums, norm.weight, norm.bias, _groups(h.shape[-1]), norm.eps, act=True)
+            o.sums = ops.gn_stats(h, None, norm.weight, norm.bias, _groups(h.shape[-1]), norm.eps)
+            o.a = ops.gn_apply(h, None, o.sums, act=True)
             f = ops.conv_fprop(o.a, self.conv_w(oconv), bias=oconv.bias, out_dtype=F32, keep_pad=True)
             if save is not None:
                 save.append(o)
@@ -403,7 +400,7 @@ class UNetEngine:
             dfv = df[..., :c_img]
             self._conv_param_grads(o.conv, dfv, o.a, dy_cols=df)
             da = ops.conv_dgrad(dfv, self.conv_w(o.conv))
-            dh, _ = ops.gn_bwd(da, o.x, None, o.sums, o.norm.weight, o.norm.bias, _groups(o.x.shape[-1]), o.norm.eps,
+            dh, _ = ops.gn_bwd(da, o.x, None, o.sums, o.norm.weight, o.norm.bias, _groups(o.x.shape[-1]),
                                act=True, dgamma=self._grad(o.norm.weight), dbeta=self._grad(o.norm.bias))
             self._notify(o.conv, o.norm)
             si = 0  # forward pops skips from the end, so walking the decoder backwards meets skips[0], skips[1], ...

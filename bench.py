@@ -184,7 +184,17 @@ def run_ours(args):
     x_dev = 2 * torch.rand(B, 3, 32, 32, device=device, generator=gen) - 1
     x_host = (2 * torch.rand(B, 3, 32, 32) - 1).pin_memory()
 
+    use_graph = not args.no_graph
+    if use_graph:
+        try:
+            step.capture(x_dev)
+        except Exception as e:  # keep measuring eagerly, and say so in the JSON line
+            print(f"[bench] CUDA graph capture failed ({e!r}); running eagerly", file=sys.stderr, flush=True)
+            use_graph = False
+
     def one_step(x):
+        if use_graph:
+            return step.replay(x)
         loss = step.micro_step(x)
         step.optimizer_step()
         return loss
@@ -210,7 +220,7 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
-    launches = (lib.adm_launch_count() - l0) // args.steps
+    launches = step.launches_per_step if use_graph else (lib.adm_launch_count() - l0) // args.steps
     clk = clocks.stop() if rank == 0 else None
     # ---- end to end through the public API: pinned host batch -> device each step, loss read back each step
     barrier()
@@ -218,7 +228,7 @@ def run_ours(args):
     e2.record()
     loss_host = 0.0
     for _ in range(args.steps):
-        xb = x_host.to(device, non_blocking=True)
+        xb = x_host if use_graph else x_host.to(device, non_blocking=True)  # graph path copies H2D into its static input
         loss = one_step(xb)
         loss_host = float(loss.item())
     e3.record()
@@ -263,7 +273,8 @@ def run_ours(args):
                                "(configs/cifar10/ddm_uncond_const_uncond_unet.yaml), fwd+bwd+clip+AdamW, dropout 0.1",
                    "global_batch": B * world, "batch_per_gpu": B, "parallelism": f"dp{world}", "grad_accum": 1,
                    "augment": "off (AugmentPipe is host-side data glue, SURVEY 8f-4)",
-                   "l2": "activation working set >> 126 MB L2 (no flush needed)", "timing": "cuda events, max over ranks"},
+                   "l2": "activation working set >> 126 MB L2 (no flush needed)", "timing": "cuda events, max over ranks",
+                   "launch": "one CUDA graph per step" if use_graph else "eager launches"},
         "e2e": {"value": B * world / (ms_e2e / 1000), "unit": "img/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "last_loss": loss_host},
         "gpu_launches": int(launches),
@@ -291,6 +302,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

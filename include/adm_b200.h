@@ -129,28 +129,32 @@ int adm_cast_f32_bf16(const float* src, void* dst, long long numel, void* stream
  * Replaces torch.nn.functional.group_norm (unet/uncond_unet.py:128) and the elementwise chain around it in
  * UNetBlock.forward (:191, :193-196, :200): silu, addcmul(shift, norm, scale+1), dropout, plus the depthwise 2x2
  * resample of Conv2d.forward (:105-108) when it directly follows.  x1 (+ optional x2 = fused torch.cat, :570-571).
- * sums: fp32 [n][c1+c2][2] = per-(sample, channel) sum and sum of squares.                                  */
+                                                                                                              */
 /* Optional device-resident u64 step counter mixed into every dropout seed (lets a captured CUDA graph draw fresh
  * masks per replay); NULL disables. */
 int adm_set_seed_counter(const unsigned long long* dev_counter);
-int adm_chan_sums(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int hw,
-                  float* sums, void* stream);
-/* y = act(GN(x) [* (1 + scale) + shift]) with params = [n][ld_params] holding (scale | shift) or NULL; act 1 = SiLU;
- * drop_p > 0 applies Philox dropout keyed by seed; resample 0 none / 1 2x2 average / 2 nearest x2.          */
+int adm_gn_stats(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int hw,
+                 int groups, float eps, const float* gamma, const float* beta, const float* params,
+                 long long ld_params, float* work, float* coef, void* stream);
+/*   Pass 1: per-(sample, channel) sum / sum of squares, then the coefficient table coef[n][c] = {A, B, mean, rstd}
+ *   (fp32 x4) with GN(x)[*(1+scale)+shift] = x*A + B; params = [n][ld_params] holding (scale | shift) or NULL.
+ *   work: fp32 scratch of 2*n*C + n elements (zeroed by the call).                                             */
+/* y = act(x*A + B); act 1 = SiLU; drop_p > 0 applies Philox dropout keyed by seed; resample 0 none / 1 2x2 average /
+ * 2 nearest x2.                                                                                              */
 int adm_gn_apply(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int h, int w,
-                 int groups, float eps, const float* sums, const float* gamma, const float* beta, const float* params,
-                 long long ld_params, int act, float drop_p, unsigned long long seed, int resample, void* out,
+                 const float* coef, int act, float drop_p, unsigned long long seed, int resample, void* out,
                  long long ldo, void* stream);
-/* Backward of adm_gn_apply.  dy: gradient at the op's output (its resolution).  Accumulates dgamma/dbeta (+=), writes
- * dparams [n][ld_dparams] = (dscale | dshift), and dx1/dx2 (+ `add`, a skip-path gradient over the full channel range:
- * add_mode 0 same resolution, 1 half resolution spread /4, 2 double resolution summed 2x2).  bsums: fp32 scratch
- * [n][c][2].  dgamma == NULL skips the parameter gradients, dx1 == NULL skips the data gradient.             */
+/* Backward of gn_stats + gn_apply.  dy: gradient at the op's output (its resolution).  Accumulates dgamma/dbeta (+=,
+ * atomics), writes dparams [n][ld_dparams] = (dscale | dshift), and dx1/dx2 (+ `add`, a skip-path gradient over the
+ * full channel range: add_mode 0 same resolution, 1 half resolution spread /4, 2 double resolution summed 2x2).
+ * work: fp32 scratch 2*n*C + n; bcoef: fp32 scratch 4*n*C.  dgamma == NULL skips the parameter gradients,
+ * dx1 == NULL skips the data gradient.                                                                       */
 int adm_gn_bwd(const void* dy, long long ldy, const void* x1, int c1, long long ld1, const void* x2, int c2,
-               long long ld2, int n, int h, int w, int groups, float eps, const float* sums, const float* gamma,
+               long long ld2, int n, int h, int w, int groups, const float* coef, const float* gamma,
                const float* beta, const float* params, long long ld_params, int act, float drop_p,
-               unsigned long long seed, int resample, float* bsums, float* dgamma, float* dbeta, float* dparams,
-               long long ld_dparams, const void* add, long long ldadd, int add_mode, void* dx1, long long ldx1,
-               void* dx2, long long ldx2, void* stream);
+               unsigned long long seed, int resample, float* work, float* bcoef, float* dgamma, float* dbeta,
+               float* dparams, long long ld_dparams, const void* add, long long ldadd, int add_mode, void* dx1,
+               long long ldx1, void* dx2, long long ldx2, void* stream);
 /* out[c] += sum_rows x[row][c] (bias gradients, unet/uncond_unet.py:111-112 backward). */
 int adm_col_sums(const void* x, long long ld, long long rows, int c, float* out, void* stream);
 /* out = a + b (+ c): gradient fan-in of the skip connections (torch autograd's implicit adds, unet/uncond_unet.py:563-564) */

@@ -49,8 +49,8 @@ def groupnorm():
         beta = 0.1 * torch.randn(c, device="cuda")
         pfull = 0.3 * torch.randn(n, 2 * c + 40, device="cuda")
         params = pfull[:, 8:8 + 2 * c] if use_params else None
-        sums = ops.chan_sums(x1, x2)
-        y = ops.gn_apply(x1, x2, sums, gamma, beta, g, 1e-5, params=params, act=act, resample=resample)
+        sums = ops.gn_stats(x1, x2, gamma, beta, g, 1e-5, params=params)
+        y = ops.gn_apply(x1, x2, sums, act=act, resample=resample)
         xr = (torch.cat([x1, x2], -1) if c2 else x1).float().permute(0, 3, 1, 2).requires_grad_(True)
         gr = gamma.clone().requires_grad_(True)
         br = beta.clone().requires_grad_(True)
@@ -74,7 +74,7 @@ def groupnorm():
         dbeta = torch.zeros(c, device="cuda")
         dpfull = torch.zeros_like(pfull)
         dparams = dpfull[:, 8:8 + 2 * c] if use_params else None
-        dx1, dx2 = ops.gn_bwd(dy.permute(0, 2, 3, 1).contiguous(), x1, x2, sums, gamma, beta, g, 1e-5, params=params,
+        dx1, dx2 = ops.gn_bwd(dy.permute(0, 2, 3, 1).contiguous(), x1, x2, sums, gamma, beta, g, params=params,
                               act=act, resample=resample, dgamma=dgamma, dbeta=dbeta, dparams=dparams, add=add,
                               add_mode=0)
         dx = torch.cat([dx1, dx2], -1) if c2 else dx1
@@ -86,10 +86,10 @@ def groupnorm():
     # dropout: keep-rate and fwd/bwd mask consistency
     n, hw, c = 2, 16, 192
     x = torch.randn(n, hw, hw, c, device="cuda").bfloat16()
-    sums = ops.chan_sums(x)
     gamma, beta = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
-    y0 = ops.gn_apply(x, None, sums, gamma, beta, 32, act=False)
-    y1 = ops.gn_apply(x, None, sums, gamma, beta, 32, act=False, drop_p=0.1, seed=77)
+    sums = ops.gn_stats(x, None, gamma, beta, 32)
+    y0 = ops.gn_apply(x, None, sums, act=False)
+    y1 = ops.gn_apply(x, None, sums, act=False, drop_p=0.1, seed=77)
     keep = (y1 != 0).float().mean().item()
     print(f"  dropout keep-rate {keep:.4f} (expect ~0.9)")
     ok &= abs(keep - 0.9) < 0.01
