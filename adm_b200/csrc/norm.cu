@@ -43,37 +43,49 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const Vec8& r) {
     *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// Philox4x32-10 (counter-based, stateless): 128-bit counter, 64-bit key -> 4 x 32 random bits.
-__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-        key.x += 0x9E3779B9u;
-        key.y += 0xBB67AE85u;
-    }
-    return ctr;
+// Counter-based dropout mask: a 64-bit mix of (seed, vector index) is expanded to four 32-bit words (murmur-style
+// finalisers), each giving two 16-bit uniforms.  Stateless, so backward regenerates exactly the forward mask.
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+    h ^= h >> 16;
+    h *= 0x85EBCA6Bu;
+    h ^= h >> 13;
+    h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
 }
 // keep-mask scale for the 8 channels of vector `vec_index`: 0 or 1/(1-p).
 __device__ __forceinline__ void dropout_scales(unsigned long long seed, unsigned long long vec_index, float p,
                                                float (&s)[8]) {
-    const uint4 r = philox4x32(make_uint4(static_cast<uint32_t>(vec_index), static_cast<uint32_t>(vec_index >> 32),
-                                          0x5eedu, 0u),
-                               make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-    const float keep = 1.f / (1.f - p);
+    const unsigned long long z = (vec_index + seed) * 0x9E3779B97F4A7C15ull;
+    const uint32_t base = mix32(static_cast<uint32_t>(z) ^ static_cast<uint32_t>(z >> 32) ^ static_cast<uint32_t>(seed >> 20));
+    const float keep = __frcp_rn(1.f - p);
     const uint32_t thr = static_cast<uint32_t>(p * 65536.f);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        s[2 * i] = ((w[i] & 0xFFFFu) >= thr) ? keep : 0.f;
-        s[2 * i + 1] = ((w[i] >> 16) >= thr) ? keep : 0.f;
+        uint32_t w = (base + static_cast<uint32_t>(i) * 0x9E3779B9u) * 0x85EBCA6Bu;
+        w ^= w >> 15;
+        w *= 0xC2B2AE35u;
+        w ^= w >> 16;
+        s[2 * i] = ((w & 0xFFFFu) >= thr) ? keep : 0.f;
+        s[2 * i + 1] = ((w >> 16) >= thr) ? keep : 0.f;
     }
 }
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
+// sigmoid via the hardware tanh (1 MUFU op, no division): s = 0.5 * tanh(0.5 v) + 0.5; |err| ~ 2^-12, far below bf16.
+__device__ __forceinline__ float sigmoid_fast(float v) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
+    return fmaf(t, 0.5f, 0.5f);
+}
+__device__ __forceinline__ float silu_f(float v) { return v * sigmoid_fast(v); }
 __device__ __forceinline__ float silu_grad(float v) {
-    const float s = 1.f / (1.f + __expf(-v));
+    const float s = sigmoid_fast(v);
+    return fmaf(v * s, 1.f - s, s);
+}
+// full-precision variants for the fp32 embedding MLP
+__device__ __forceinline__ float silu_precise(float v) { return v * __frcp_rn(1.f + __expf(-v)); }
+__device__ __forceinline__ float silu_grad_precise(float v) {
+    const float s = __frcp_rn(1.f + __expf(-v));
     return s * (1.f + v * (1.f - s));
 }
 
@@ -174,59 +186,72 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __re
 }
 
 // ------------------------------------------------------------------------------------------------ gn_apply (forward)
-// y = act(x*A + B) (+ dropout) (+ 2x2 avg-pool / nearest-up on the store).  grid (chunks, N).
-__global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int c1, long long ld1,
+// y = act(x*A + B) (+ dropout) (+ 2x2 avg-pool / nearest-up on the store).  grid (chunks, N); blockDim is a multiple of
+// V = C/8: a thread owns ONE channel vector (its 16 coefficients live in registers) and walks pixels with a fixed stride,
+// so the inner loop has no integer division and consecutive threads touch consecutive 16 B chunks.
+__global__ void __launch_bounds__(256, 4) gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int c1, long long ld1,
                                                        const __nv_bfloat16* __restrict__ x2, int c2, long long ld2,
                                                        int H, int W, const float4* __restrict__ coef, int act,
                                                        float drop_p, unsigned long long seed, int resample,
                                                        __nv_bfloat16* __restrict__ out, long long ldo,
                                                        const unsigned long long* __restrict__ seed_dev) {
     if (seed_dev != nullptr) seed += *seed_dev * 0x9E3779B97F4A7C15ull;
-    extern __shared__ float sm[];
     const int C = c1 + c2, V = C >> 3, V1 = c1 >> 3;
-    float* sA = sm;
-    float* sB = sm + C;
     const int n = blockIdx.y, hw = H * W;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float4 t = coef[1LL * n * C + c];
-        sA[c] = t.x;
-        sB[c] = t.y;
-    }
-    __syncthreads();
-    const int Ho = resample == 1 ? H / 2 : (resample == 2 ? H * 2 : H);
-    const int Wo = resample == 1 ? W / 2 : (resample == 2 ? W * 2 : W);
-    const int iter_hw = resample == 1 ? Ho * Wo : hw;  // iterate over output pixels when pooling, input otherwise
-    const long long total = 1LL * iter_hw * V;
-    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
-        const int v = static_cast<int>(i % V);
-        const int p = static_cast<int>(i / V);
-        const __nv_bfloat16* base = v < V1 ? x1 + 1LL * n * hw * ld1 + v * 8 : x2 + 1LL * n * hw * ld2 + (v - V1) * 8;
-        const long long ld = v < V1 ? ld1 : ld2;
-        float a[8], b[8];
+    const int tpv = blockDim.x / V;
+    const int v = threadIdx.x % V, lane = threadIdx.x / V;
+    if (lane >= tpv) return;
+    float a[8], b[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { a[j] = sA[v * 8 + j]; b[j] = sB[v * 8 + j]; }
-        Vec8 o;
-        if (resample == 1) {
-            const int ho = p / Wo, wo = p % Wo;
+    for (int j = 0; j < 8; ++j) {
+        const float4 t = coef[1LL * n * C + v * 8 + j];
+        a[j] = t.x;
+        b[j] = t.y;
+    }
+    const __nv_bfloat16* base = v < V1 ? x1 + 1LL * n * hw * ld1 + v * 8 : x2 + 1LL * n * hw * ld2 + (v - V1) * 8;
+    const long long ld = v < V1 ? ld1 : ld2;
+    const int step = gridDim.x * tpv;
+    if (resample == 1) {
+        const int Ho = H / 2, Wo = W / 2;
+        __nv_bfloat16* ob = out + 1LL * n * Ho * Wo * ldo + v * 8;
+        for (int p = blockIdx.x * tpv + lane; p < Ho * Wo; p += step) {
+            const int ho = p / Wo, wo = p - ho * Wo;
             Vec8 xv[4];
 #pragma unroll
             for (int d = 0; d < 4; ++d) xv[d] = load8(base + ((2 * ho + (d >> 1)) * W + 2 * wo + (d & 1)) * ld);
+            Vec8 o;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o.v[j] = 0.f;
+            for (int j = 0; j < 8; ++j) {
+                float acc = 0.f;
 #pragma unroll
-            for (int d = 0; d < 4; ++d) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int d = 0; d < 4; ++d) {
                     float y = xv[d].v[j] * a[j] + b[j];
                     if (act) y = silu_f(y);
-                    o.v[j] += 0.25f * y;
+                    acc += y;
                 }
+                o.v[j] = 0.25f * acc;
             }
-            store8(out + (1LL * n * Ho * Wo + p) * ldo + v * 8, o);
-        } else {
-            const Vec8 xv = load8(base + p * ld);
+            store8(ob + p * ldo, o);
+        }
+        return;
+    }
+    const int Wo = 2 * W;
+    __nv_bfloat16* ob = out + 1LL * n * (resample == 2 ? 4 * hw : hw) * ldo + v * 8;
+    const unsigned long long vec0 = 1ULL * n * hw * V + v;
+    int p = blockIdx.x * tpv + lane;
+    for (; p < hw; p += 2 * step) {  // two pixels per iteration: both loads issued before the math
+        const bool has2 = p + step < hw;
+        const Vec8 xa = load8(base + p * ld);
+        Vec8 xb = xa;
+        if (has2) xb = load8(base + (p + step) * ld);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !has2) break;
+            const int pp = p + u * step;
+            const Vec8& xv = u == 0 ? xa : xb;
             float ds[8];
-            if (drop_p > 0.f) dropout_scales(seed, (1ULL * n * hw + p) * V + v, drop_p, ds);
+            if (drop_p > 0.f) dropout_scales(seed, vec0 + 1ULL * pp * V, drop_p, ds);
+            Vec8 o;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 float y = xv.v[j] * a[j] + b[j];
@@ -235,44 +260,40 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
                 o.v[j] = y;
             }
             if (resample == 0) {
-                store8(out + (1LL * n * hw + p) * ldo + v * 8, o);
+                store8(ob + pp * ldo, o);
             } else {
-                const int h = p / W, w = p % W;
+                const int h = pp / W, w = pp - h * W;
 #pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    const long long po = 1LL * (2 * h + (d >> 1)) * Wo + 2 * w + (d & 1);
-                    store8(out + (1LL * n * Ho * Wo + po) * ldo + v * 8, o);
-                }
+                for (int d = 0; d < 4; ++d) store8(ob + (1LL * (2 * h + (d >> 1)) * Wo + 2 * w + (d & 1)) * ldo, o);
             }
         }
     }
 }
 
-// dv (gradient at the pre-activation v = x*A+B) for input pixel p, channel vector v, given dy at the op's output.
-__device__ __forceinline__ void grad_preact(const __nv_bfloat16* __restrict__ dy, long long ldy, int n, int H, int W,
-                                            int p, int v, int V, int resample, int act, float drop_p,
-                                            unsigned long long seed, const Vec8& xv, const float* a, const float* b,
-                                            float (&dv)[8]) {
-    const int hw = H * W;
+// dv (gradient at the pre-activation v = x*A+B) for input pixel p (h, w), channel vector v.
+__device__ __forceinline__ void grad_preact(const __nv_bfloat16* __restrict__ dyb, long long ldy, int H, int W, int p,
+                                            int resample, int act, float drop_p, unsigned long long seed,
+                                            unsigned long long vec_index, const Vec8& xv, const float* a,
+                                            const float* b, float (&dv)[8]) {
     Vec8 g;
     if (resample == 0) {
-        g = load8(dy + (1LL * n * hw + p) * ldy + v * 8);
-    } else if (resample == 1) {
-        const int h = p / W, w = p % W, Wo = W / 2, Ho = H / 2;
-        g = load8(dy + (1LL * n * Ho * Wo + (h >> 1) * Wo + (w >> 1)) * ldy + v * 8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g.v[j] *= 0.25f;
+        g = load8(dyb + p * ldy);
     } else {
-        const int h = p / W, w = p % W, Wo = W * 2, Ho = H * 2;
-        Vec8 t[4];
+        const int h = p / W, w = p - h * W;
+        if (resample == 1) {
+            g = load8(dyb + ((h >> 1) * (W >> 1) + (w >> 1)) * ldy);
 #pragma unroll
-        for (int d = 0; d < 4; ++d)
-            t[d] = load8(dy + (1LL * n * Ho * Wo + 1LL * (2 * h + (d >> 1)) * Wo + 2 * w + (d & 1)) * ldy + v * 8);
+            for (int j = 0; j < 8; ++j) g.v[j] *= 0.25f;
+        } else {
+            Vec8 t[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g.v[j] = (t[0].v[j] + t[1].v[j]) + (t[2].v[j] + t[3].v[j]);
+            for (int d = 0; d < 4; ++d) t[d] = load8(dyb + (1LL * (2 * h + (d >> 1)) * (2 * W) + 2 * w + (d & 1)) * ldy);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g.v[j] = (t[0].v[j] + t[1].v[j]) + (t[2].v[j] + t[3].v[j]);
+        }
     }
     float ds[8];
-    if (drop_p > 0.f) dropout_scales(seed, (1ULL * n * hw + p) * V + v, drop_p, ds);
+    if (drop_p > 0.f) dropout_scales(seed, vec_index, drop_p, ds);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         float d = g.v[j];
@@ -284,9 +305,11 @@ __device__ __forceinline__ void grad_preact(const __nv_bfloat16* __restrict__ dy
 
 // ------------------------------------------------------------------------------------------------ gn_bwd_reduce
 // bsums [N][C][2]: S1 = sum_p dv, S2 = sum_p dv * xhat.  The last block of each sample turns them into
-//   bcoef[n][c] = {gamma' = gamma (1 + scale), mean_g(dv gamma'), mean_g(dv gamma' xhat), 0}
+//   bcoef[n][c] = {K1, K2, K3, 0} with dx = dv*K1 + x*K2 + K3
+//     (K1 = rstd*gamma', K2 = -rstd^2*M2, K3 = -rstd*M1 + mean*rstd^2*M2, gamma' = gamma (1 + scale),
+//      M1 = mean_g(gamma' S1), M2 = mean_g(gamma' S2))
 // and the parameter gradients: dgamma[c] += (1+sc) S2, dbeta[c] += (1+sc) S1, dparams[n] = (gamma S2 + beta S1 | S1).
-__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, long long ldy,
+__global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, long long ldy,
                                                             const __nv_bfloat16* __restrict__ x1, int c1, long long ld1,
                                                             const __nv_bfloat16* __restrict__ x2, int c2, long long ld2,
                                                             int H, int W, int G, const float4* __restrict__ coef,
@@ -307,44 +330,53 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const __nv_bfloat16*
     const int n = blockIdx.y, hw = H * W;
     const int tpv = blockDim.x / V;
     const int v = threadIdx.x % V, lane = threadIdx.x / V;
-    float s1[8], s2[8];
+    float s1[8], sx[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    for (int j = 0; j < 8; ++j) s1[j] = sx[j] = 0.f;
     if (lane < tpv) {
         const __nv_bfloat16* base = v < V1 ? x1 + 1LL * n * hw * ld1 + v * 8 : x2 + 1LL * n * hw * ld2 + (v - V1) * 8;
         const long long ld = v < V1 ? ld1 : ld2;
-        float a[8], b[8], mu[8], rs[8];
+        const int out_hw = resample == 1 ? hw / 4 : (resample == 2 ? hw * 4 : hw);
+        const __nv_bfloat16* dyb = dy + 1LL * n * out_hw * ldy + v * 8;
+        const unsigned long long vec0 = 1ULL * n * hw * V + v;
+        float a[8], b[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float4 t = coef[1LL * n * C + v * 8 + j];
-            a[j] = t.x; b[j] = t.y; mu[j] = t.z; rs[j] = t.w;
+            a[j] = t.x; b[j] = t.y;
         }
         const int step = gridDim.x * tpv;
         int p = blockIdx.x * tpv + lane;
         for (; p + step < hw; p += 2 * step) {  // two pixels in flight
             const Vec8 xa = load8(base + p * ld), xb = load8(base + (p + step) * ld);
             float da[8], db[8];
-            grad_preact(dy, ldy, n, H, W, p, v, V, resample, act, drop_p, seed, xa, a, b, da);
-            grad_preact(dy, ldy, n, H, W, p + step, v, V, resample, act, drop_p, seed, xb, a, b, db);
+            grad_preact(dyb, ldy, H, W, p, resample, act, drop_p, seed, vec0 + 1ULL * p * V, xa, a, b, da);
+            grad_preact(dyb, ldy, H, W, p + step, resample, act, drop_p, seed, vec0 + 1ULL * (p + step) * V, xb, a, b, db);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 s1[j] += da[j] + db[j];
-                s2[j] += da[j] * (xa.v[j] - mu[j]) * rs[j] + db[j] * (xb.v[j] - mu[j]) * rs[j];
+                sx[j] += da[j] * xa.v[j] + db[j] * xb.v[j];
             }
         }
         for (; p < hw; p += step) {
             const Vec8 xv = load8(base + p * ld);
             float dv[8];
-            grad_preact(dy, ldy, n, H, W, p, v, V, resample, act, drop_p, seed, xv, a, b, dv);
+            grad_preact(dyb, ldy, H, W, p, resample, act, drop_p, seed, vec0 + 1ULL * p * V, xv, a, b, dv);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 s1[j] += dv[j];
-                s2[j] += dv[j] * (xv.v[j] - mu[j]) * rs[j];
+                sx[j] += dv[j] * xv.v[j];
             }
+        }
+        // S2 = sum dv * xhat = rstd * (sum dv*x - mean * sum dv)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 t = coef[1LL * n * C + v * 8 + j];
+            sx[j] = t.w * (sx[j] - t.z * s1[j]);
         }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { red[threadIdx.x * 16 + j] = s1[j]; red[threadIdx.x * 16 + 8 + j] = s2[j]; }
+    for (int j = 0; j < 8; ++j) { red[threadIdx.x * 16 + j] = s1[j]; red[threadIdx.x * 16 + 8 + j] = sx[j]; }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int vv = c >> 3, j = c & 7;
@@ -387,15 +419,20 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const __nv_bfloat16*
         const int g = c / cpg;
         float m1 = 0.f, m2 = 0.f;
         for (int j = 0; j < cpg; ++j) { m1 += gs1[g * cpg + j]; m2 += gs2[g * cpg + j]; }
+        m1 *= inv_cnt;
+        m2 *= inv_cnt;
         const float sc = params != nullptr ? 1.f + params[n * ldp + c] : 1.f;
-        bcoef[1LL * n * C + c] = make_float4(gamma[c] * sc, m1 * inv_cnt, m2 * inv_cnt, 0.f);
+        const float4 t = coef[1LL * n * C + c];
+        const float mean = t.z, rstd = t.w;
+        bcoef[1LL * n * C + c] = make_float4(rstd * gamma[c] * sc, -rstd * rstd * m2, -rstd * m1 + mean * rstd * rstd * m2, 0.f);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ gn_bwd_apply
-// dx = rstd * (dv*gamma' - M1 - xhat*M2) (+ add).  add: optional skip-path gradient over the full channel range;
+// dx = dv*K1 + x*K2 + K3 (+ add).  add: optional skip-path gradient over the full channel range;
 // add_mode 0: same resolution; 1: half resolution, spread as add/4; 2: double resolution, summed over the 2x2 patch.
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, long long ldy,
+// Same thread mapping as gn_apply (one channel vector per thread, coefficients in registers, no division in the loop).
+__global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, long long ldy,
                                                            const __nv_bfloat16* __restrict__ x1, int c1, long long ld1,
                                                            const __nv_bfloat16* __restrict__ x2, int c2, long long ld2,
                                                            int H, int W, const float4* __restrict__ coef,
@@ -406,66 +443,62 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __nv_bfloat16* 
                                                            __nv_bfloat16* __restrict__ dx2, long long ldx2,
                                                            const unsigned long long* __restrict__ seed_dev) {
     if (seed_dev != nullptr) seed += *seed_dev * 0x9E3779B97F4A7C15ull;
-    extern __shared__ float sm[];
     const int C = c1 + c2, V = C >> 3, V1 = c1 >> 3;
-    float* sA = sm;
-    float* sB = sA + C;
-    float* sMean = sB + C;
-    float* sRstd = sMean + C;
-    float* sG = sRstd + C;
-    float* sM1 = sG + C;
-    float* sM2 = sM1 + C;
     const int n = blockIdx.y, hw = H * W;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float4 t = coef[1LL * n * C + c];
-        const float4 u = bcoef[1LL * n * C + c];
-        sA[c] = t.x; sB[c] = t.y; sMean[c] = t.z; sRstd[c] = t.w;
-        sG[c] = u.x; sM1[c] = u.y; sM2[c] = u.z;
+    const int tpv = blockDim.x / V;
+    const int v = threadIdx.x % V, lane = threadIdx.x / V;
+    if (lane >= tpv) return;
+    float a[8], b[8], k1[8], k2[8], k3[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 t = coef[1LL * n * C + v * 8 + j];
+        const float4 u = bcoef[1LL * n * C + v * 8 + j];
+        a[j] = t.x; b[j] = t.y;
+        k1[j] = u.x; k2[j] = u.y; k3[j] = u.z;
     }
-    __syncthreads();
-    const long long total = 1LL * hw * V;
-    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
-        const int v = static_cast<int>(i % V);
-        const int p = static_cast<int>(i / V);
-        const bool first = v < V1;
-        const __nv_bfloat16* base = first ? x1 + 1LL * n * hw * ld1 + v * 8 : x2 + 1LL * n * hw * ld2 + (v - V1) * 8;
-        const long long ld = first ? ld1 : ld2;
+    const bool first = v < V1;
+    const __nv_bfloat16* base = first ? x1 + 1LL * n * hw * ld1 + v * 8 : x2 + 1LL * n * hw * ld2 + (v - V1) * 8;
+    const long long ld = first ? ld1 : ld2;
+    __nv_bfloat16* ob = first ? dx1 + 1LL * n * hw * ldx1 + v * 8 : dx2 + 1LL * n * hw * ldx2 + (v - V1) * 8;
+    const long long ldo = first ? ldx1 : ldx2;
+    const int out_hw = resample == 1 ? hw / 4 : (resample == 2 ? hw * 4 : hw);
+    const __nv_bfloat16* dyb = dy + 1LL * n * out_hw * ldy + v * 8;
+    const int add_hw = add_mode == 1 ? hw / 4 : (add_mode == 2 ? hw * 4 : hw);
+    const __nv_bfloat16* addb = add != nullptr ? add + 1LL * n * add_hw * ldadd + v * 8 : nullptr;
+    const unsigned long long vec0 = 1ULL * n * hw * V + v;
+    const int step = gridDim.x * tpv;
+    for (int p = blockIdx.x * tpv + lane; p < hw; p += step) {
         const Vec8 xv = load8(base + p * ld);
         Vec8 addv;
-        if (add != nullptr) {  // issue the skip-gradient loads early
-            const int h = p / W, w = p % W;
+        if (addb != nullptr) {  // issue the skip-gradient loads before the math
             if (add_mode == 0) {
-                addv = load8(add + (1LL * n * hw + p) * ldadd + v * 8);
-            } else if (add_mode == 1) {
-                addv = load8(add + (1LL * n * (H / 2) * (W / 2) + (h >> 1) * (W / 2) + (w >> 1)) * ldadd + v * 8);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) addv.v[j] *= 0.25f;
+                addv = load8(addb + p * ldadd);
             } else {
-                Vec8 t[4];
+                const int h = p / W, w = p - h * W;
+                if (add_mode == 1) {
+                    addv = load8(addb + ((h >> 1) * (W >> 1) + (w >> 1)) * ldadd);
 #pragma unroll
-                for (int d = 0; d < 4; ++d)
-                    t[d] = load8(add + (1LL * n * 4 * hw + 1LL * (2 * h + (d >> 1)) * (2 * W) + 2 * w + (d & 1)) * ldadd + v * 8);
+                    for (int j = 0; j < 8; ++j) addv.v[j] *= 0.25f;
+                } else {
+                    Vec8 t[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) addv.v[j] = (t[0].v[j] + t[1].v[j]) + (t[2].v[j] + t[3].v[j]);
+                    for (int d = 0; d < 4; ++d)
+                        t[d] = load8(addb + (1LL * (2 * h + (d >> 1)) * (2 * W) + 2 * w + (d & 1)) * ldadd);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) addv.v[j] = (t[0].v[j] + t[1].v[j]) + (t[2].v[j] + t[3].v[j]);
+                }
             }
         }
-        float a[8], b[8], dv[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { a[j] = sA[v * 8 + j]; b[j] = sB[v * 8 + j]; }
-        grad_preact(dy, ldy, n, H, W, p, v, V, resample, act, drop_p, seed, xv, a, b, dv);
+        float dv[8];
+        grad_preact(dyb, ldy, H, W, p, resample, act, drop_p, seed, vec0 + 1ULL * p * V, xv, a, b, dv);
         Vec8 o;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = v * 8 + j;
-            const float xhat = (xv.v[j] - sMean[c]) * sRstd[c];
-            o.v[j] = sRstd[c] * (dv[j] * sG[c] - sM1[c] - xhat * sM2[c]);
-        }
-        if (add != nullptr) {
+        for (int j = 0; j < 8; ++j) o.v[j] = dv[j] * k1[j] + xv.v[j] * k2[j] + k3[j];
+        if (addb != nullptr) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) o.v[j] += addv.v[j];
         }
-        if (first) store8(dx1 + (1LL * n * hw + p) * ldx1 + v * 8, o);
-        else store8(dx2 + (1LL * n * hw + p) * ldx2 + (v - V1) * 8, o);
+        store8(ob + p * ldo, o);
     }
 }
 
@@ -561,7 +594,7 @@ __global__ void __launch_bounds__(256) resample_kernel(const __nv_bfloat16* __re
 __global__ void __launch_bounds__(256) silu_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                    __nv_bfloat16* __restrict__ y_bf16, long long n) {
     for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < n; i += 1LL * gridDim.x * blockDim.x) {
-        const float v = silu_f(x[i]);
+        const float v = silu_precise(x[i]);
         if (y != nullptr) y[i] = v;
         if (y_bf16 != nullptr) y_bf16[i] = __float2bfloat16(v);
     }
@@ -570,7 +603,7 @@ __global__ void __launch_bounds__(256) silu_bwd_kernel(const float* __restrict__
                                                        float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
                                                        long long n) {
     for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < n; i += 1LL * gridDim.x * blockDim.x) {
-        const float v = dy[i] * silu_grad(x[i]);
+        const float v = dy[i] * silu_grad_precise(x[i]);
         if (dx != nullptr) dx[i] = v;
         if (dx_bf16 != nullptr) dx_bf16[i] = __float2bfloat16(v);
     }
@@ -634,10 +667,11 @@ int adm_gn_apply(const void* x1, int c1, long long ld1, const void* x2, int c2, 
     const int C = c1 + c2;
     ADM_REQUIRE(c1 > 0 && c1 % 8 == 0 && c2 % 8 == 0, "gn_apply: channels must be multiples of 8");
     ADM_REQUIRE(resample == 0 || (resample == 1 && h % 2 == 0 && w % 2 == 0) || resample == 2, "gn_apply: bad resample");
-    ADM_REQUIRE(C <= 4096, "gn_apply: C too large for the shared-memory affine table");
-    const long long work = 1LL * (resample == 1 ? (h / 2) * (w / 2) : h * w) * (C / 8);
-    dim3 grid(grid_for(work, 256 * 2, n), n);
-    gn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+    ADM_REQUIRE(C <= 2048, "gn_apply: C too large");
+    const int threads = threads_for(C / 8);
+    const int tpv = threads / (C / 8);
+    dim3 grid(grid_for(resample == 1 ? (h / 2) * (w / 2) : h * w, tpv * 2, n), n);
+    gn_apply_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const bf16*>(x1), c1, ld1, static_cast<const bf16*>(x2), c2, ld2, h, w,
         reinterpret_cast<const float4*>(coef), act, drop_p, seed, resample, static_cast<bf16*>(out), ldo, g_seed_dev);
     ADM_CHECK_LAUNCH("gn_apply");
@@ -672,8 +706,8 @@ int adm_gn_bwd(const void* dy, long long ldy, const void* x1, int c1, long long 
         ADM_CHECK_LAUNCH("gn_bwd_reduce");
     }
     if (dx1 != nullptr) {
-        dim3 grid(grid_for(1LL * h * w * V, 256 * 2, n), n);
-        gn_bwd_apply_kernel<<<grid, 256, 7 * C * sizeof(float), s>>>(
+        dim3 grid(grid_for(h * w, tpv * 2, n), n);
+        gn_bwd_apply_kernel<<<grid, threads, 0, s>>>(
             dyp, ldy, x1p, c1, ld1, x2p, c2, ld2, h, w, reinterpret_cast<const float4*>(coef),
             reinterpret_cast<const float4*>(bcoef), act, drop_p, seed, resample, static_cast<const bf16*>(add), ldadd,
             add_mode, static_cast<bf16*>(dx1), ldx1, static_cast<bf16*>(dx2), ldx2, g_seed_dev);
