@@ -257,8 +257,13 @@ def _unet_case(cfg, batch, seed_in, cos_tol):
     print(f"  loss {loss.item():.5f} vs oracle {loss_ref.item():.5f} rel={rel:.3e} (tol 1e-2)", flush=True)
     ok &= rel < 1e-2
     worst = []
+    gmax = max(float(sdr[name].grad.norm()) for name, _ in net.named_parameters())
     for name, p in net.named_parameters():
         gref = sdr[name].grad
+        if float(gref.norm()) < 1e-7 * gmax:
+            # analytically zero gradient (SpatialAtt.k_conv.bias: softmax is shift invariant); check ours is tiny too
+            assert p.grad is None or float(p.grad.norm()) < 1e-3 * gmax, name
+            continue
         if p.grad is None:
             worst.append((-1.0, name, "no grad"))
             continue

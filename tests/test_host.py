@@ -1,0 +1,108 @@
+"""CPU: host-side logic of the drop-in mirror — state_dict layout, config -> object resolution, samplers' time grid,
+parameter arena / gradient-completion order."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import ddm_oracle as O
+from tests.golden.make_golden import CIFAR, TINY
+
+REF = "/root/reference"
+
+
+def _net(cfg):
+    from adm_b200.unet.uncond_unet import EDMPrecond
+    kw = {k: v for k, v in cfg.items() if k not in ("img_resolution", "img_channels", "label_dim")}
+    return EDMPrecond(img_resolution=cfg["img_resolution"], img_channels=3, sigma_data=1.0, model_type="DhariwalUNet", **kw)
+
+
+@pytest.mark.parametrize("name,cfg", [("unet_tiny.json", TINY), ("unet_cifar.json", CIFAR)])
+def test_state_dict_layout_equals_reference(golden_dir, name, cfg):
+    ref = json.load(open(os.path.join(golden_dir, name)))["state_dict_shapes"]
+    ours = {k: list(v.shape) for k, v in _net(cfg).state_dict().items()}
+    assert ours == ref
+    assert list(ours) == list(ref)  # same key ORDER as the reference module (checkpoint round trips)
+
+
+def test_load_reference_style_state_dict_and_attributes():
+    net = _net(TINY)
+    sd = O.make_state_dict(TINY, 3)
+    missing, unexpected = net.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    assert torch.equal(net.model.enc["16x16_conv"].weight, sd["model.enc.16x16_conv.weight"])
+    assert net.channels == 3 and net.self_condition is None and net.img_resolution == 16
+
+
+def test_construct_by_reference_class_names():
+    from adm_b200.ddm.utils import construct_class_by_name
+    from adm_b200.unet.uncond_unet import EDMPrecond
+    from adm_b200.ddm.ddm_const import DDPM
+    unet_cfg = dict(class_name="unet.uncond_unet.EDMPrecond", img_resolution=16, img_channels=3, sigma_data=1.0,
+                    model_type="DhariwalUNet", model_channels=64, channel_mult=[1, 2], channel_mult_emb=4, num_blocks=1,
+                    attn_resolutions=[8], dropout=0.1, label_dropout=0, augment_dim=9)
+    unet = construct_class_by_name(**unet_cfg)
+    assert isinstance(unet, EDMPrecond)
+    model_cfg = dict(class_name="ddm.ddm_const.DDPM", image_size=[16, 16], ckpt_path=None, ignore_keys=[],
+                     only_model=False, sampling_timesteps=10, loss_type="l2", start_dist="normal", perceptual_weight=1.0,
+                     eps=1e-4, sigma_max=1, sigma_min=0.01, ldm=False, weighting_loss=True, use_l1=False,
+                     use_augment=False, unet=unet_cfg)
+    dpm = construct_class_by_name(model=unet, cfg=model_cfg, **model_cfg)  # train_uncond_dpm.py:44-46
+    assert isinstance(dpm, DDPM)
+    assert dpm.image_size == [16, 16] and dpm.sampling_timesteps == 10 and dpm.weighting_loss
+    assert "eps" in dpm.state_dict() and len(dpm.state_dict()) == 1 + len(unet.state_dict())
+    with pytest.raises(AssertionError):
+        construct_class_by_name(model=unet, cfg=model_cfg, **{**model_cfg, "start_dist": "laplace"})
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_reference_yaml_builds_our_classes():
+    import yaml
+    from adm_b200.ddm.utils import construct_class_by_name
+    cfg = yaml.load(open(os.path.join(REF, "configs/cifar10/ddm_uncond_const_uncond_unet.yaml")), Loader=yaml.FullLoader)
+    model_cfg = cfg["model"]
+    model_cfg["use_augment"] = False  # AugmentPipe is host-side data glue
+    unet = construct_class_by_name(**model_cfg["unet"])
+    dpm = construct_class_by_name(model=unet, cfg=model_cfg, **model_cfg)
+    assert sum(p.numel() for p in unet.parameters()) == 216_141_136
+    assert len(unet.state_dict()) == 829
+    assert dpm.sigma_min == 0.01 and dpm.sampling_timesteps == 10
+
+
+def test_t_steps_match_oracle():
+    from adm_b200.ddm.ddm_const import DDPM
+    net = _net(TINY)
+    for n in (1, 2, 10, 50):
+        cfg = dict(image_size=[16, 16], sampling_timesteps=n, sigma_min=0.01, sigma_max=1)
+        dpm = DDPM(model=net, cfg=cfg, **cfg)
+        ours = torch.tensor(dpm.t_steps(), dtype=torch.float64)
+        assert torch.allclose(ours, O.t_steps_deterministic(n), rtol=0, atol=1e-15)
+
+
+def test_completion_order_and_arena():
+    from adm_b200.train import ParamArena, completion_order
+    net = _net(TINY)
+    order = completion_order(net)
+    assert len(order) == len(list(net.parameters())) == len({id(p) for p in order})
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    arena = ParamArena(net, order)
+    assert arena.numel >= sum(p.numel() for p in order)
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, before[k])  # re-homing keeps values and the state_dict layout
+    p0 = order[0]
+    assert p0.data_ptr() == arena.flat.data_ptr() and p0.grad.data_ptr() == arena.grads.data_ptr()
+    p0.grad = None
+    arena.rebind_grads()
+    assert p0.grad.data_ptr() == arena.grads.data_ptr()
+    # out_conv2 finishes first, the batched affine + mapping layers last
+    names = {id(p): n for n, p in net.named_parameters()}
+    assert names[id(order[0])].startswith("model.out_conv2")
+    assert names[id(order[-1])].startswith("model.map_augment")
+
+
+def test_lr_schedule():
+    from adm_b200.train import lr_lambda
+    assert lr_lambda(0, 800000, 1e-4, 5e-6) == pytest.approx(1 / 5000)
+    assert lr_lambda(4999, 800000, 1e-4, 5e-6) == pytest.approx(1.0)
+    assert lr_lambda(800000, 800000, 1e-4, 5e-6) == pytest.approx(0.05)
