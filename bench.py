@@ -184,7 +184,8 @@ def run_ours(args):
     x_dev = 2 * torch.rand(B, 3, 32, 32, device=device, generator=gen) - 1
     x_host = (2 * torch.rand(B, 3, 32, 32) - 1).pin_memory()
 
-    use_graph = not args.no_graph
+    # multi-rank: NCCL collectives on the side stream are launched eagerly (graph capture of them is not validated)
+    use_graph = (not args.no_graph) and (world == 1 or args.graph_dp)
     if use_graph:
         try:
             step.capture(x_dev)
@@ -303,6 +304,7 @@ def main():
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--graph-dp", action="store_true", help="also capture the multi-rank step (NCCL inside the graph)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
