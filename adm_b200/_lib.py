@@ -57,7 +57,9 @@ SIGNATURES = {
     "adm_gn_stats": (c_i, [c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_ll, c_p, c_p, c_p]),
     "adm_gn_apply": (c_i, [c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_p, c_i, c_f, c_ull, c_i, c_p, c_ll, c_p]),
     "adm_gn_bwd": (c_i, [c_p, c_ll, c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_ll, c_i,
-                         c_f, c_ull, c_i, c_p, c_p, c_p, c_p, c_p, c_ll, c_p, c_ll, c_i, c_p, c_ll, c_p, c_ll, c_p]),
+                         c_f, c_ull, c_i, c_p, c_p, c_p, c_p, c_p, c_ll, c_p, c_ll, c_i, c_p, c_ll, c_p, c_ll, c_p, c_p]),
+    "adm_gn_forward": (c_i, [c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_ll, c_p, c_p, c_i,
+                             c_f, c_ull, c_i, c_p, c_ll, c_p]),
     "adm_col_sums": (c_i, [c_p, c_ll, c_ll, c_i, c_p, c_p]),
     "adm_add_bf16": (c_i, [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_p, c_ll, c_ll, c_i, c_p]),
     "adm_resample": (c_i, [c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_p, c_ll, c_p]),

@@ -15,6 +15,11 @@
 #include "adm_internal.h"
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace adm {
 
@@ -609,6 +614,511 @@ __global__ void __launch_bounds__(256) silu_bwd_kernel(const float* __restrict__
     }
 }
 
+
+// ================================================================================================ fused cluster kernels
+// One thread-block CLUSTER per sample (K = 1, 2, 4 or 8 CTAs; per-channel partials are exchanged through distributed
+// shared memory), so the statistics pass and the apply pass of a GroupNorm live in ONE kernel separated by a cluster
+// barrier instead of two kernels separated by a grid-wide dependency: no atomics, no memset, no ticket, and the second
+// read of the sample comes from L2/L1.  Each thread owns one 8-channel vector (coefficients in registers) and streams
+// its pixels through a private 4-deep cp.async ring in shared memory, so ~100 KB per SM are in flight without holding
+// registers for them.  Used when the batch is large enough to fill the SMs (see gn_cluster_size); the multi-block
+// kernels above remain the general path.
+constexpr int GNF_STAGES = 4;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                     static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+                 "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ Vec8 unpack8(const uint4 u) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    Vec8 r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        r.v[2 * i] = __uint_as_float(w[i] << 16);
+        r.v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+    return r;
+}
+// Dropout keep-scales from ONE mixed 32-bit word per vector: four odd multipliers spread it into eight 16-bit uniforms.
+__device__ __forceinline__ void dropout_scales_fast(unsigned long long seed, unsigned long long vec_index, float p,
+                                                    float (&s)[8]) {
+    dropout_scales(seed, vec_index, p, s);
+}
+// tanh-form SiLU on a pre-halved pre-activation h = v/2:  silu(v) = h*tanh(h) + h,
+// silu'(v) = 0.5 * (1 + T + h * (1 - T^2)), T = tanh(h).
+__device__ __forceinline__ float tanh_fast(float h) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return t;
+}
+
+__global__ void __launch_bounds__(512, 1) gn_fwd_fused_kernel(
+    const __nv_bfloat16* __restrict__ x1, int c1, long long ld1, const __nv_bfloat16* __restrict__ x2, int c2,
+    long long ld2, int H, int W, int G, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float* __restrict__ params, long long ldp, float4* __restrict__ coef, int act, float drop_p,
+    unsigned long long seed, int resample, __nv_bfloat16* __restrict__ out, long long ldo,
+    const unsigned long long* __restrict__ seed_dev) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int K = static_cast<int>(cluster.num_blocks()), r = static_cast<int>(cluster.block_rank());
+    if (seed_dev != nullptr) seed += *seed_dev * 0x9E3779B97F4A7C15ull;
+    const int C = c1 + c2, V = C >> 3, V1 = c1 >> 3;
+    const int n = blockIdx.x / K, hw = H * W;
+    const int tpv = blockDim.x / V;
+    const int v = threadIdx.x % V, lane = threadIdx.x / V;
+    const bool active = lane < tpv;
+    extern __shared__ __align__(16) float sm[];
+    float* chan = sm;          // [2C] this CTA's per-channel (sum, sum of squares)
+    float* tot = sm + 2 * C;   // [2C] cluster totals
+    float* tabA = sm + 4 * C;  // [C]
+    float* tabB = sm + 5 * C;  // [C]
+    float* red = sm + 6 * C;   // [blockDim][16]; re-used as the cp.async ring [STAGES][blockDim] of uint4 in pass 2
+    const __nv_bfloat16* base = v < V1 ? x1 + 1LL * n * hw * ld1 + v * 8 : x2 + 1LL * n * hw * ld2 + (v - V1) * 8;
+    const long long ld = v < V1 ? ld1 : ld2;
+    const int step = K * tpv;
+    const int p0 = r * tpv + lane;
+    // ---- pass 1: per-channel sums over this CTA's pixels (eight 16 B loads in flight per thread)
+    {
+        float s[8], q[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+        if (active) {
+            int p = p0;
+            for (; p + 7 * step < hw; p += 8 * step) {
+                uint4 raw[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) raw[u] = *reinterpret_cast<const uint4*>(base + (p + u * step) * ld);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const Vec8 t = unpack8(raw[u]);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { s[i] += t.v[i]; q[i] = fmaf(t.v[i], t.v[i], q[i]); }
+                }
+            }
+            for (; p < hw; p += step) {
+                const Vec8 t = load8(base + p * ld);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { s[i] += t.v[i]; q[i] = fmaf(t.v[i], t.v[i], q[i]); }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { red[threadIdx.x * 16 + i] = s[i]; red[threadIdx.x * 16 + 8 + i] = q[i]; }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int vv = c >> 3, i = c & 7;
+        float a = 0.f, b = 0.f;
+        for (int l = 0; l < tpv; ++l) {
+            a += red[(l * V + vv) * 16 + i];
+            b += red[(l * V + vv) * 16 + 8 + i];
+        }
+        chan[2 * c] = a;
+        chan[2 * c + 1] = b;
+    }
+    cluster.sync();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int rr = 0; rr < K; ++rr) {
+            const float* rc = cluster.map_shared_rank(chan, rr);
+            a += rc[2 * c];
+            b += rc[2 * c + 1];
+        }
+        tot[2 * c] = a;
+        tot[2 * c + 1] = b;
+    }
+    cluster.sync();  // every remote read of `chan` is done; also orders `tot` inside the CTA
+    {
+        const int cpg = C / G;
+        const float inv_cnt = 1.f / (static_cast<float>(cpg) * static_cast<float>(hw));
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const int g0 = (c / cpg) * cpg;
+            float s = 0.f, q = 0.f;
+            for (int j = 0; j < cpg; ++j) { s += tot[2 * (g0 + j)]; q += tot[2 * (g0 + j) + 1]; }
+            const float mean = s * inv_cnt;
+            const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + eps);
+            const float ga = gamma[c], be = beta[c];
+            float a = rstd * ga, b = be - mean * rstd * ga;
+            if (params != nullptr) {
+                const float sc = 1.f + params[n * ldp + c], sh = params[n * ldp + C + c];
+                a *= sc;
+                b = b * sc + sh;
+            }
+            tabA[c] = a;
+            tabB[c] = b;
+            if (r == 0) coef[1LL * n * C + c] = make_float4(a, b, mean, rstd);
+        }
+    }
+    __syncthreads();
+    if (!active || out == nullptr) return;
+    // ---- pass 2: y = act(x*A + B) (+ dropout) (+ resample on the store); second read of x hits L2
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] = tabA[v * 8 + j]; b[j] = tabB[v * 8 + j]; }
+    if (resample == 1) {
+        const int Ho = H / 2, Wo = W / 2;
+        __nv_bfloat16* ob = out + 1LL * n * Ho * Wo * ldo + v * 8;
+        for (int p = p0; p < Ho * Wo; p += step) {
+            const int ho = p / Wo, wo = p - ho * Wo;
+            Vec8 xv[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) xv[d] = load8(base + ((2 * ho + (d >> 1)) * W + 2 * wo + (d & 1)) * ld);
+            Vec8 o;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float acc = 0.f;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    float y = xv[d].v[j] * a[j] + b[j];
+                    if (act) y = silu_f(y);
+                    acc += y;
+                }
+                o.v[j] = 0.25f * acc;
+            }
+            store8(ob + p * ldo, o);
+        }
+        return;
+    }
+    if (act) {  // halve the coefficients once: silu(v) = h*tanh(h) + h with h = v/2
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a[j] *= 0.5f; b[j] *= 0.5f; }
+    }
+    const int Wo = 2 * W;
+    __nv_bfloat16* ob = out + 1LL * n * (resample == 2 ? 4 * hw : hw) * ldo + v * 8;
+    const unsigned long long vec0 = 1ULL * n * hw * V + v;
+    uint4* ring = reinterpret_cast<uint4*>(red);  // [STAGES][blockDim]; `red` is dead (all threads passed the barriers)
+    int pf = p0;
+#pragma unroll
+    for (int st = 0; st < GNF_STAGES; ++st) {
+        if (pf < hw) cp_async16(ring + st * blockDim.x + threadIdx.x, base + pf * ld);
+        cp_async_commit();
+        pf += step;
+    }
+    int st = 0;
+    for (int p = p0; p < hw; p += step) {
+        cp_async_wait<GNF_STAGES - 1>();
+        uint4* slot = ring + st * blockDim.x + threadIdx.x;
+        const Vec8 xv = unpack8(*slot);
+        if (pf < hw) cp_async16(slot, base + pf * ld);
+        cp_async_commit();
+        pf += step;
+        if (++st == GNF_STAGES) st = 0;
+        float ds[8];
+        if (drop_p > 0.f) dropout_scales_fast(seed, vec0 + 1ULL * p * V, drop_p, ds);
+        Vec8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float y = fmaf(xv.v[j], a[j], b[j]);
+            if (act) y = fmaf(y, tanh_fast(y), y);
+            if (drop_p > 0.f) y *= ds[j];
+            o.v[j] = y;
+        }
+        if (resample == 0) {
+            store8(ob + p * ldo, o);
+        } else {
+            const int h = p / W, w = p - h * W;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) store8(ob + (1LL * (2 * h + (d >> 1)) * Wo + 2 * w + (d & 1)) * ldo, o);
+        }
+    }
+}
+
+// dv (gradient at the pre-activation) from an already loaded upstream-gradient vector g; a/b are pre-halved when act.
+__device__ __forceinline__ void dv_from(const Vec8& g, const Vec8& xv, const float* a, const float* b, int act,
+                                        float drop_p, unsigned long long seed, unsigned long long vec_index,
+                                        float (&dv)[8]) {
+    float ds[8];
+    if (drop_p > 0.f) dropout_scales_fast(seed, vec_index, drop_p, ds);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float d = g.v[j];
+        if (drop_p > 0.f) d *= ds[j];
+        if (act) {
+            const float h = fmaf(xv.v[j], a[j], b[j]);
+            const float T = tanh_fast(h);
+            const float w = fmaf(h, fmaf(-T, T, 1.f), T);
+            d *= fmaf(w, 0.5f, 0.5f);
+        }
+        dv[j] = d;
+    }
+}
+
+// Backward twin: pass 1 = S1/S2 reduction, cluster exchange, parameter gradients and the {K1,K2,K3} table;
+// pass 2 = dx (+ skip-path gradient `add`), optionally also the column sums of dx1 (the bias gradient of the conv
+// that produced x1) accumulated into dbias1[c1].
+__global__ void __launch_bounds__(512, 1) gn_bwd_fused_kernel(
+    const __nv_bfloat16* __restrict__ dy, long long ldy, const __nv_bfloat16* __restrict__ x1, int c1, long long ld1,
+    const __nv_bfloat16* __restrict__ x2, int c2, long long ld2, int H, int W, int G,
+    const float4* __restrict__ coef, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float* __restrict__ params, long long ldp, int act, float drop_p, unsigned long long seed, int resample,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dparams, long long ld_dparams,
+    const __nv_bfloat16* __restrict__ add, long long ldadd, int add_mode, __nv_bfloat16* __restrict__ dx1,
+    long long ldx1, __nv_bfloat16* __restrict__ dx2, long long ldx2, float* __restrict__ dbias1,
+    const unsigned long long* __restrict__ seed_dev) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int K = static_cast<int>(cluster.num_blocks()), r = static_cast<int>(cluster.block_rank());
+    if (seed_dev != nullptr) seed += *seed_dev * 0x9E3779B97F4A7C15ull;
+    const int C = c1 + c2, V = C >> 3, V1 = c1 >> 3;
+    const int n = blockIdx.x / K, hw = H * W;
+    const int tpv = blockDim.x / V;
+    const int v = threadIdx.x % V, lane = threadIdx.x / V;
+    const bool active = lane < tpv;
+    extern __shared__ __align__(16) float sm[];
+    float* chan = sm;          // [2C] this CTA's raw (sum dv, sum dv*x)
+    float* tot = sm + 2 * C;   // [2C] cluster totals -> (gamma' S1, gamma' S2)
+    float* tab = sm + 4 * C;   // [3C] k1, k2, k3
+    float* red = sm + 7 * C;   // [blockDim][16] reduction scratch
+    uint4* ring = reinterpret_cast<uint4*>(sm + 7 * C + 16 * blockDim.x);  // [STAGES][3][blockDim] cp.async ring
+    const bool first = v < V1;
+    const __nv_bfloat16* base = first ? x1 + 1LL * n * hw * ld1 + v * 8 : x2 + 1LL * n * hw * ld2 + (v - V1) * 8;
+    const long long ld = first ? ld1 : ld2;
+    const int out_hw = resample == 1 ? hw / 4 : (resample == 2 ? hw * 4 : hw);
+    const __nv_bfloat16* dyb = dy + 1LL * n * out_hw * ldy + v * 8;
+    const unsigned long long vec0 = 1ULL * n * hw * V + v;
+    const int step = K * tpv;
+    const int p0 = r * tpv + lane;
+    const bool piped = resample == 0 && (add == nullptr || add_mode == 0);  // the common, fully pipelined shape
+    float a[8], b[8];      // pre-activation coefficients (as stored)
+    float ah[8], bh[8];    // halved when act (tanh-form SiLU); used by the pipelined path
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 t = coef[1LL * n * C + v * 8 + j];
+            a[j] = t.x;
+            b[j] = t.y;
+            ah[j] = act ? 0.5f * t.x : t.x;
+            bh[j] = act ? 0.5f * t.y : t.y;
+        }
+    }
+    // ---- pass 1
+    {
+        float s1[8], sx[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s1[j] = sx[j] = 0.f;
+        if (active && piped) {
+            int pf = p0;
+#pragma unroll
+            for (int st = 0; st < GNF_STAGES; ++st) {
+                if (pf < hw) {
+                    cp_async16(ring + (st * 3 + 0) * blockDim.x + threadIdx.x, base + pf * ld);
+                    cp_async16(ring + (st * 3 + 1) * blockDim.x + threadIdx.x, dyb + pf * ldy);
+                }
+                cp_async_commit();
+                pf += step;
+            }
+            int st = 0;
+            for (int p = p0; p < hw; p += step) {
+                cp_async_wait<GNF_STAGES - 1>();
+                uint4* sx_ = ring + (st * 3 + 0) * blockDim.x + threadIdx.x;
+                uint4* sd_ = ring + (st * 3 + 1) * blockDim.x + threadIdx.x;
+                const Vec8 xv = unpack8(*sx_), g = unpack8(*sd_);
+                if (pf < hw) {
+                    cp_async16(sx_, base + pf * ld);
+                    cp_async16(sd_, dyb + pf * ldy);
+                }
+                cp_async_commit();
+                pf += step;
+                if (++st == GNF_STAGES) st = 0;
+                float dv[8];
+                dv_from(g, xv, ah, bh, act, drop_p, seed, vec0 + 1ULL * p * V, dv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    s1[j] += dv[j];
+                    sx[j] = fmaf(dv[j], xv.v[j], sx[j]);
+                }
+            }
+            cp_async_wait<0>();
+        } else if (active) {
+            for (int p = p0; p < hw; p += step) {
+                const Vec8 xv = load8(base + p * ld);
+                float dv[8];
+                grad_preact(dyb, ldy, H, W, p, resample, act, drop_p, seed, vec0 + 1ULL * p * V, xv, a, b, dv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    s1[j] += dv[j];
+                    sx[j] += dv[j] * xv.v[j];
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { red[threadIdx.x * 16 + j] = s1[j]; red[threadIdx.x * 16 + 8 + j] = sx[j]; }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int vv = c >> 3, j = c & 7;
+        float s = 0.f, q = 0.f;
+        for (int l = 0; l < tpv; ++l) {
+            s += red[(l * V + vv) * 16 + j];
+            q += red[(l * V + vv) * 16 + 8 + j];
+        }
+        chan[2 * c] = s;
+        chan[2 * c + 1] = q;
+    }
+    cluster.sync();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f, q = 0.f;
+        for (int rr = 0; rr < K; ++rr) {
+            const float* rc = cluster.map_shared_rank(chan, rr);
+            s += rc[2 * c];
+            q += rc[2 * c + 1];
+        }
+        const float4 t = coef[1LL * n * C + c];
+        const float S1 = s, S2 = t.w * (q - t.z * s);  // sum dv*xhat = rstd * (sum dv*x - mean * sum dv)
+        const float ga = gamma[c], be = beta[c];
+        const float sc = params != nullptr ? 1.f + params[n * ldp + c] : 1.f;
+        tot[2 * c] = ga * sc * S1;
+        tot[2 * c + 1] = ga * sc * S2;
+        if (r == 0) {
+            if (dgamma != nullptr) {
+                atomicAdd(dgamma + c, sc * S2);
+                atomicAdd(dbeta + c, sc * S1);
+            }
+            if (dparams != nullptr) {
+                dparams[n * ld_dparams + c] = ga * S2 + be * S1;
+                dparams[n * ld_dparams + C + c] = S1;
+            }
+        }
+    }
+    cluster.sync();
+    if (dx1 == nullptr) return;
+    {
+        const int cpg = C / G;
+        const float inv_cnt = 1.f / (static_cast<float>(cpg) * static_cast<float>(hw));
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const int g0 = (c / cpg) * cpg;
+            float m1 = 0.f, m2 = 0.f;
+            for (int j = 0; j < cpg; ++j) { m1 += tot[2 * (g0 + j)]; m2 += tot[2 * (g0 + j) + 1]; }
+            m1 *= inv_cnt;
+            m2 *= inv_cnt;
+            const float sc = params != nullptr ? 1.f + params[n * ldp + c] : 1.f;
+            const float4 t = coef[1LL * n * C + c];
+            const float mean = t.z, rstd = t.w;
+            tab[c] = rstd * gamma[c] * sc;
+            tab[C + c] = -rstd * rstd * m2;
+            tab[2 * C + c] = -rstd * m1 + mean * rstd * rstd * m2;
+        }
+    }
+    __syncthreads();
+    // ---- pass 2
+    float bs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bs[j] = 0.f;
+    if (active) {
+        float k1[8], k2[8], k3[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            k1[j] = tab[v * 8 + j];
+            k2[j] = tab[C + v * 8 + j];
+            k3[j] = tab[2 * C + v * 8 + j];
+        }
+        __nv_bfloat16* ob = first ? dx1 + 1LL * n * hw * ldx1 + v * 8 : dx2 + 1LL * n * hw * ldx2 + (v - V1) * 8;
+        const long long ldo = first ? ldx1 : ldx2;
+        const int add_hw = add_mode == 1 ? hw / 4 : (add_mode == 2 ? hw * 4 : hw);
+        const __nv_bfloat16* addb = add != nullptr ? add + 1LL * n * add_hw * ldadd + v * 8 : nullptr;
+        const bool want_bs = dbias1 != nullptr && first;
+        if (piped) {
+            int pf = p0;
+#pragma unroll
+            for (int st = 0; st < GNF_STAGES; ++st) {
+                if (pf < hw) {
+                    cp_async16(ring + (st * 3 + 0) * blockDim.x + threadIdx.x, base + pf * ld);
+                    cp_async16(ring + (st * 3 + 1) * blockDim.x + threadIdx.x, dyb + pf * ldy);
+                    if (addb != nullptr) cp_async16(ring + (st * 3 + 2) * blockDim.x + threadIdx.x, addb + pf * ldadd);
+                }
+                cp_async_commit();
+                pf += step;
+            }
+            int st = 0;
+            for (int p = p0; p < hw; p += step) {
+                cp_async_wait<GNF_STAGES - 1>();
+                uint4* sx_ = ring + (st * 3 + 0) * blockDim.x + threadIdx.x;
+                uint4* sd_ = ring + (st * 3 + 1) * blockDim.x + threadIdx.x;
+                uint4* sa_ = ring + (st * 3 + 2) * blockDim.x + threadIdx.x;
+                const Vec8 xv = unpack8(*sx_), g = unpack8(*sd_);
+                Vec8 addv;
+                if (addb != nullptr) addv = unpack8(*sa_);
+                if (pf < hw) {
+                    cp_async16(sx_, base + pf * ld);
+                    cp_async16(sd_, dyb + pf * ldy);
+                    if (addb != nullptr) cp_async16(sa_, addb + pf * ldadd);
+                }
+                cp_async_commit();
+                pf += step;
+                if (++st == GNF_STAGES) st = 0;
+                float dv[8];
+                dv_from(g, xv, ah, bh, act, drop_p, seed, vec0 + 1ULL * p * V, dv);
+                Vec8 o;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o.v[j] = fmaf(dv[j], k1[j], fmaf(xv.v[j], k2[j], k3[j]));
+                if (addb != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o.v[j] += addv.v[j];
+                }
+                if (want_bs) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) bs[j] += o.v[j];
+                }
+                store8(ob + p * ldo, o);
+            }
+        } else {
+            for (int p = p0; p < hw; p += step) {
+                const Vec8 xv = load8(base + p * ld);
+                Vec8 addv;
+                if (addb != nullptr) {
+                    if (add_mode == 0) {
+                        addv = load8(addb + p * ldadd);
+                    } else {
+                        const int h = p / W, w = p - h * W;
+                        if (add_mode == 1) {
+                            addv = load8(addb + ((h >> 1) * (W >> 1) + (w >> 1)) * ldadd);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) addv.v[j] *= 0.25f;
+                        } else {
+                            Vec8 t[4];
+#pragma unroll
+                            for (int d = 0; d < 4; ++d)
+                                t[d] = load8(addb + (1LL * (2 * h + (d >> 1)) * (2 * W) + 2 * w + (d & 1)) * ldadd);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) addv.v[j] = (t[0].v[j] + t[1].v[j]) + (t[2].v[j] + t[3].v[j]);
+                        }
+                    }
+                }
+                float dv[8];
+                grad_preact(dyb, ldy, H, W, p, resample, act, drop_p, seed, vec0 + 1ULL * p * V, xv, a, b, dv);
+                Vec8 o;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o.v[j] = dv[j] * k1[j] + xv.v[j] * k2[j] + k3[j];
+                if (addb != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o.v[j] += addv.v[j];
+                }
+                if (want_bs) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) bs[j] += o.v[j];
+                }
+                store8(ob + p * ldo, o);
+            }
+        }
+    }
+    if (dbias1 != nullptr) {  // column sums of dx1 -> bias gradient of the conv that produced x1
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = bs[j];
+        __syncthreads();
+        for (int c = threadIdx.x; c < c1; c += blockDim.x) {
+            float s = 0.f;
+            for (int l = 0; l < tpv; ++l) s += red[(l * V + (c >> 3)) * 8 + (c & 7)];
+            atomicAdd(dbias1 + c, s);
+        }
+    }
+}
+
 static const unsigned long long* g_seed_dev = nullptr;
 
 static int grid_for(long long work, int threads, int n_batch) {
@@ -618,6 +1128,53 @@ static int grid_for(long long work, int threads, int n_batch) {
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return static_cast<int>(blocks);
+}
+
+
+// Cluster size for the one-cluster-per-sample kernels: the smallest K in {1,2,4,8} with n*K CTAs covering >= 60 % of
+// the SMs; 0 when even K = 8 cannot (small batches use the multi-block kernels).  ADM_GN_PATH=general|fused overrides.
+static int gn_cluster_size(int n) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("ADM_GN_PATH");
+        forced = e == nullptr ? 0 : (strcmp(e, "general") == 0 ? 1 : (strcmp(e, "fused") == 0 ? 2 : 0));
+    }
+    if (forced == 1) return 0;
+    const int want = (num_sms() * 6 + 9) / 10;
+    int k = 1;
+    while (k < 8 && n * k < want) k *= 2;
+    return (n * k >= want || forced == 2) ? k : 0;
+}
+
+static int gn_fused_threads(int V, int hw, int k) {
+    int tpv = 512 / V;
+    const int per_cta = (hw + k - 1) / k;
+    if (tpv > per_cta) tpv = per_cta;
+    if (tpv < 1) tpv = 1;
+    return tpv * V;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_cluster(void (*kern)(KArgs...), int grid, int block, size_t smem, int k, cudaStream_t s,
+                                  Args... args) {
+    static bool attr_set = false;  // per kernel instantiation
+    if (!attr_set) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = k;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
 }  // namespace adm
@@ -678,19 +1235,67 @@ int adm_gn_apply(const void* x1, int c1, long long ld1, const void* x2, int c2, 
     return 0;
 }
 
+int adm_gn_forward(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int h, int w,
+                   int groups, float eps, const float* gamma, const float* beta, const float* params,
+                   long long ld_params, float* work, float* coef, int act, float drop_p, unsigned long long seed,
+                   int resample, void* out, long long ldo, void* stream) {
+    const int C = c1 + c2;
+    ADM_REQUIRE(c1 > 0 && c1 % 8 == 0 && c2 % 8 == 0 && (x2 != nullptr || c2 == 0) && C % groups == 0,
+                "gn_forward: channels must be multiples of 8 and divisible by groups");
+    ADM_REQUIRE(C <= 2048, "gn_forward: C too large");
+    ADM_REQUIRE(resample == 0 || (resample == 1 && h % 2 == 0 && w % 2 == 0) || resample == 2, "gn_forward: bad resample");
+    const int k = gn_cluster_size(n);
+    if (k == 0) {
+        int rc = adm_gn_stats(x1, c1, ld1, x2, c2, ld2, n, h * w, groups, eps, gamma, beta, params, ld_params, work, coef,
+                              stream);
+        if (rc != 0 || out == nullptr) return rc;
+        return adm_gn_apply(x1, c1, ld1, x2, c2, ld2, n, h, w, coef, act, drop_p, seed, resample, out, ldo, stream);
+    }
+    const int V = C / 8;
+    const int threads = gn_fused_threads(V, h * w, k);
+    const size_t smem = sizeof(float) * (6 * C + 16 * threads);  // ring (4 x 16 B per thread) aliases the scratch
+    cudaError_t e = launch_cluster(gn_fwd_fused_kernel, n * k, threads, smem, k, static_cast<cudaStream_t>(stream),
+                                   static_cast<const bf16*>(x1), c1, ld1, static_cast<const bf16*>(x2), c2, ld2, h, w,
+                                   groups, eps, gamma, beta, params, ld_params, reinterpret_cast<float4*>(coef), act,
+                                   drop_p, seed, resample, static_cast<bf16*>(out), ldo, g_seed_dev);
+    if (e != cudaSuccess) {
+        set_error("gn_forward launch: %s", cudaGetErrorString(e));
+        return ADM_ERR_CUDA;
+    }
+    ADM_CHECK_LAUNCH("gn_forward");
+    return 0;
+}
+
 int adm_gn_bwd(const void* dy, long long ldy, const void* x1, int c1, long long ld1, const void* x2, int c2,
                long long ld2, int n, int h, int w, int groups, const float* coef, const float* gamma,
                const float* beta, const float* params, long long ld_params, int act, float drop_p,
                unsigned long long seed, int resample, float* work, float* bcoef, float* dgamma, float* dbeta,
                float* dparams, long long ld_dparams, const void* add, long long ldadd, int add_mode, void* dx1,
-               long long ldx1, void* dx2, long long ldx2, void* stream) {
+               long long ldx1, void* dx2, long long ldx2, float* dbias1, void* stream) {
     const int C = c1 + c2;
     ADM_REQUIRE(c1 > 0 && c1 % 8 == 0 && c2 % 8 == 0 && C % groups == 0, "gn_bwd: bad channels / groups");
     ADM_REQUIRE(C <= 2048, "gn_bwd: C too large");
+    ADM_REQUIRE(dbias1 == nullptr || dx1 != nullptr, "gn_bwd: dbias1 needs dx1");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bf16* dyp = static_cast<const bf16*>(dy);
     const bf16* x1p = static_cast<const bf16*>(x1);
     const bf16* x2p = static_cast<const bf16*>(x2);
+    const int kc = gn_cluster_size(n);
+    if (kc > 0) {
+        const int threads = gn_fused_threads(C / 8, h * w, kc);
+        const size_t smem = sizeof(float) * (7 * C + 16 * threads) + 16 * GNF_STAGES * 3 * threads;
+        cudaError_t e = launch_cluster(
+            gn_bwd_fused_kernel, n * kc, threads, smem, kc, s, dyp, ldy, x1p, c1, ld1, x2p, c2, ld2, h, w, groups,
+            reinterpret_cast<const float4*>(coef), gamma, beta, params, ld_params, act, drop_p, seed, resample, dgamma,
+            dbeta, dparams, ld_dparams, static_cast<const bf16*>(add), ldadd, add_mode, static_cast<bf16*>(dx1), ldx1,
+            static_cast<bf16*>(dx2), ldx2, dbias1, g_seed_dev);
+        if (e != cudaSuccess) {
+            set_error("gn_bwd (fused) launch: %s", cudaGetErrorString(e));
+            return ADM_ERR_CUDA;
+        }
+        ADM_CHECK_LAUNCH("gn_bwd_fused");
+        return 0;
+    }
     cudaMemsetAsync(work, 0, sizeof(float) * (2LL * n * C + n), s);
     const int V = C / 8;
     const int threads = threads_for(V);
@@ -712,6 +1317,7 @@ int adm_gn_bwd(const void* dy, long long ldy, const void* x1, int c1, long long 
             reinterpret_cast<const float4*>(bcoef), act, drop_p, seed, resample, static_cast<const bf16*>(add), ldadd,
             add_mode, static_cast<bf16*>(dx1), ldx1, static_cast<bf16*>(dx2), ldx2, g_seed_dev);
         ADM_CHECK_LAUNCH("gn_bwd_apply");
+        if (dbias1 != nullptr) return adm_col_sums(dx1, ldx1, 1LL * n * h * w, c1, dbias1, stream);
     }
     return 0;
 }

@@ -316,9 +316,30 @@ def gn_apply(x1, x2, coef, act=True, drop_p=0.0, seed=0, resample=0):
     return out
 
 
+def gn_forward(x1, x2, gamma, beta, groups, eps=1e-5, params=None, act=True, drop_p=0.0, seed=0, resample=0):
+    """GroupNorm statistics + apply in one call (one cluster-per-sample kernel when the batch fills the SMs).
+    Returns (coef [N, C, 4], y)."""
+    _need_cuda(x1)
+    n, h, w, _ = x1.shape
+    p1, c1, ld1 = _src(x1)
+    p2, c2, ld2 = _src(x2)
+    c = c1 + c2
+    work = torch.empty(2 * n * c + n, device=x1.device, dtype=F32)
+    coef = torch.empty(n, c, 4, device=x1.device, dtype=F32)
+    ho, wo = (h // 2, w // 2) if resample == 1 else ((2 * h, 2 * w) if resample == 2 else (h, w))
+    out = torch.empty(n, ho, wo, c, device=x1.device, dtype=BF16)
+    ldp = params.stride(0) if params is not None else 0
+    check(_lib.load().adm_gn_forward(p1, c1, ld1, p2, c2, ld2, n, h, w, groups, float(eps), _ptr(gamma), _ptr(beta),
+                                     _ptr(params), ldp, _ptr(work), _ptr(coef), int(act), float(drop_p),
+                                     int(seed) & 0xFFFFFFFFFFFFFFFF, int(resample), _ptr(out), out.stride(2),
+                                     _stream()), "gn_forward")
+    return coef, out
+
+
 def gn_bwd(dy, x1, x2, coef, gamma, beta, groups, params=None, act=True, drop_p=0.0, seed=0, resample=0,
-           dgamma=None, dbeta=None, dparams=None, add=None, add_mode=0, need_dx=True):
-    """Returns (dx1, dx2).  dgamma/dbeta are accumulated in place; dparams ([N, 2C] view) is overwritten."""
+           dgamma=None, dbeta=None, dparams=None, add=None, add_mode=0, need_dx=True, dbias1=None):
+    """Returns (dx1, dx2).  dgamma/dbeta are accumulated in place; dparams ([N, 2C] view) is overwritten;
+    dbias1 (fp32 [c1]) += column sums of dx1."""
     n, h, w, _ = x1.shape
     p1, c1, ld1 = _src(x1)
     p2, c2, ld2 = _src(x2)
@@ -336,7 +357,7 @@ def gn_bwd(dy, x1, x2, coef, gamma, beta, groups, params=None, act=True, drop_p=
                                  _ptr(dbeta), _ptr(dparams), lddp, _ptr(add),
                                  add.stride(-2) if add is not None else 0, int(add_mode), _ptr(dx1),
                                  dx1.stride(2) if dx1 is not None else 0, _ptr(dx2),
-                                 dx2.stride(2) if dx2 is not None else 0, _stream()), "gn_bwd")
+                                 dx2.stride(2) if dx2 is not None else 0, _ptr(dbias1), _stream()), "gn_bwd")
     return dx1, dx2
 
 

@@ -160,12 +160,12 @@ class UNetEngine:
         mode = 1 if blk.down else (2 if blk.up else 0)
         c.mode = mode
         c.drop_p = float(blk.dropout) if training else 0.0
-        c.sums0 = ops.gn_stats(x1, x2, blk.norm0.weight, blk.norm0.bias, _groups(cin), blk.norm0.eps)
-        c.a0 = ops.gn_apply(x1, x2, c.sums0, act=True, resample=mode)
+        c.sums0, c.a0 = ops.gn_forward(x1, x2, blk.norm0.weight, blk.norm0.bias, _groups(cin), blk.norm0.eps, act=True,
+                                       resample=mode)
         # after the fused concat-GroupNorm the conv sees ONE tensor a0 with cin channels
         c.h0 = ops.conv_fprop(c.a0, self.conv_w(blk.conv0), bias=blk.conv0.bias)
-        c.sums1 = ops.gn_stats(c.h0, None, blk.norm1.weight, blk.norm1.bias, _groups(cout), blk.norm1.eps, params=params)
-        c.a1 = ops.gn_apply(c.h0, None, c.sums1, act=True, drop_p=c.drop_p, seed=seed)
+        c.sums1, c.a1 = ops.gn_forward(c.h0, None, blk.norm1.weight, blk.norm1.bias, _groups(cout), blk.norm1.eps,
+                                       params=params, act=True, drop_p=c.drop_p, seed=seed)
         if blk.skip is not None and blk.skip.weight is not None:
             res = ops.conv_fprop(x1, self.conv_w(blk.skip, cin1, cin2), x2=x2, bias=blk.skip.bias)
         elif mode:
@@ -176,8 +176,8 @@ class UNetEngine:
         out = c.h1
         if blk.num_heads:
             perm = self.qkv_perm(cout, blk.num_heads)
-            c.sums2 = ops.gn_stats(c.h1, None, blk.norm2.weight, blk.norm2.bias, _groups(cout), blk.norm2.eps)
-            c.a2 = ops.gn_apply(c.h1, None, c.sums2, act=False)
+            c.sums2, c.a2 = ops.gn_forward(c.h1, None, blk.norm2.weight, blk.norm2.bias, _groups(cout), blk.norm2.eps,
+                                           act=False)
             bq = self._cached(("qkvb", id(blk)), [blk.qkv.bias], lambda old: blk.qkv.bias.detach()[perm[1]].contiguous())
             c.qkv = ops.conv_fprop(c.a2, self.conv_w(blk.qkv, perm=perm[0]), bias=bq)
             c.att, c.p = ops.attention_fwd(c.qkv, blk.num_heads)
@@ -349,8 +349,7 @@ class UNetEngine:
                 h = run_block(m, h, x2, idx)
                 idx += 1
             o = NS(x=h, norm=norm, conv=oconv)
-            o.sums = ops.gn_stats(h, None, norm.weight, norm.bias, _groups(h.shape[-1]), norm.eps)
-            o.a = ops.gn_apply(h, None, o.sums, act=True)
+            o.sums, o.a = ops.gn_forward(h, None, norm.weight, norm.bias, _groups(h.shape[-1]), norm.eps, act=True)
             f = ops.conv_fprop(o.a, self.conv_w(oconv), bias=oconv.bias, out_dtype=F32, keep_pad=True)
             if save is not None:
                 save.append(o)

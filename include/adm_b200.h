@@ -154,7 +154,16 @@ int adm_gn_bwd(const void* dy, long long ldy, const void* x1, int c1, long long 
                const float* beta, const float* params, long long ld_params, int act, float drop_p,
                unsigned long long seed, int resample, float* work, float* bcoef, float* dgamma, float* dbeta,
                float* dparams, long long ld_dparams, const void* add, long long ldadd, int add_mode, void* dx1,
-               long long ldx1, void* dx2, long long ldx2, void* stream);
+               long long ldx1, void* dx2, long long ldx2, float* dbias1, void* stream);
+/*   dbias1 (optional, fp32 [c1]): += column sums of dx1 — the bias gradient of the conv that produced x1
+ *   (unet/uncond_unet.py:111-112 backward), so no separate pass over dx1 is needed.
+ * adm_gn_forward = gn_stats + gn_apply in one call.  When the batch fills the SMs it runs ONE kernel with a
+ * thread-block cluster per sample (statistics exchanged through distributed shared memory, apply pass re-reading the
+ * sample from L2); adm_gn_bwd does the same for the backward pair.  out == NULL computes the coefficient table only. */
+int adm_gn_forward(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int h, int w,
+                   int groups, float eps, const float* gamma, const float* beta, const float* params,
+                   long long ld_params, float* work, float* coef, int act, float drop_p, unsigned long long seed,
+                   int resample, void* out, long long ldo, void* stream);
 /* out[c] += sum_rows x[row][c] (bias gradients, unet/uncond_unet.py:111-112 backward). */
 int adm_col_sums(const void* x, long long ld, long long rows, int c, float* out, void* stream);
 /* out = a + b (+ c): gradient fan-in of the skip connections (torch autograd's implicit adds, unet/uncond_unet.py:563-564) */

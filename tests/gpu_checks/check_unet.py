@@ -40,7 +40,15 @@ def groupnorm():
                                                              (2, 16, 64, 0, 1, True, False, 0.0),
                                                              (2, 8, 128, 0, 2, True, False, 0.0),
                                                              (3, 8, 384, 0, 0, False, False, 0.0),
-                                                             (2, 32, 8, 0, 0, True, False, 0.0)]:
+                                                             (2, 32, 8, 0, 0, True, False, 0.0),
+                                                             # batches >= 12: the one-cluster-per-sample fused kernels
+                                                             (16, 8, 192, 0, 0, True, True, 0.0),     # K = 8
+                                                             (32, 16, 384, 192, 0, True, False, 0.0), # K = 4, concat
+                                                             (64, 8, 64, 0, 1, True, False, 0.0),     # K = 2, avg-pool
+                                                             (16, 8, 128, 0, 2, True, True, 0.0),     # nearest-up
+                                                             (128, 4, 768, 0, 0, False, False, 0.0),  # K = 1, C > threads
+                                                             (128, 2, 384, 384, 0, True, True, 0.0),  # hw < lanes
+                                                             (24, 32, 96, 0, 0, True, False, 0.0)]:
         c = c1 + c2
         g = min(32, c // 4)
         x1 = (torch.randn(n, hw, hw, c1, device="cuda") * 1.5 + 0.3).bfloat16()
@@ -49,8 +57,7 @@ def groupnorm():
         beta = 0.1 * torch.randn(c, device="cuda")
         pfull = 0.3 * torch.randn(n, 2 * c + 40, device="cuda")
         params = pfull[:, 8:8 + 2 * c] if use_params else None
-        sums = ops.gn_stats(x1, x2, gamma, beta, g, 1e-5, params=params)
-        y = ops.gn_apply(x1, x2, sums, act=act, resample=resample)
+        sums, y = ops.gn_forward(x1, x2, gamma, beta, g, 1e-5, params=params, act=act, resample=resample)
         xr = (torch.cat([x1, x2], -1) if c2 else x1).float().permute(0, 3, 1, 2).requires_grad_(True)
         gr = gamma.clone().requires_grad_(True)
         br = beta.clone().requires_grad_(True)
@@ -73,34 +80,42 @@ def groupnorm():
         dgamma = torch.zeros(c, device="cuda")
         dbeta = torch.zeros(c, device="cuda")
         dpfull = torch.zeros_like(pfull)
+        dbias1 = torch.ones(c1, device="cuda")  # accumulated into (+=)
         dparams = dpfull[:, 8:8 + 2 * c] if use_params else None
         dx1, dx2 = ops.gn_bwd(dy.permute(0, 2, 3, 1).contiguous(), x1, x2, sums, gamma, beta, g, params=params,
                               act=act, resample=resample, dgamma=dgamma, dbeta=dbeta, dparams=dparams, add=add,
-                              add_mode=0)
+                              add_mode=0, dbias1=dbias1)
         dx = torch.cat([dx1, dx2], -1) if c2 else dx1
+        ok &= _report(f"gn_bwd dbias1 {tag}", dbias1 - 1.0, dx1.float().sum((0, 1, 2)), 2e-3)
         ok &= _report(f"gn_bwd dx {tag}", dx, xr.grad.permute(0, 2, 3, 1) + add.float(), 1e-2)
         ok &= _report(f"gn_bwd dgamma {tag}", dgamma, gr.grad, 1e-2)
         ok &= _report(f"gn_bwd dbeta {tag}", dbeta, br.grad, 1e-2)
         if use_params:
             ok &= _report(f"gn_bwd dparams {tag}", dparams, pr.grad, 1e-2)
-    # dropout: keep-rate and fwd/bwd mask consistency
-    n, hw, c = 2, 16, 192
-    x = torch.randn(n, hw, hw, c, device="cuda").bfloat16()
-    gamma, beta = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
-    sums = ops.gn_stats(x, None, gamma, beta, 32)
-    y0 = ops.gn_apply(x, None, sums, act=False)
-    y1 = ops.gn_apply(x, None, sums, act=False, drop_p=0.1, seed=77)
-    keep = (y1 != 0).float().mean().item()
-    print(f"  dropout keep-rate {keep:.4f} (expect ~0.9)")
-    ok &= abs(keep - 0.9) < 0.01
-    ok &= _report("dropout scale", y1[y1 != 0], (y0.float() / 0.9)[y1 != 0], 1e-2)
-    dy = torch.ones_like(y0)
-    dx_nodrop, _ = ops.gn_bwd(dy, x, None, sums, gamma, beta, 32, act=False, drop_p=0.0, dgamma=None)
-    # with dy = mask-consistent gradient: bwd(drop) on ones == bwd(nodrop) on the mask itself
-    mask = (y1 != 0).to(torch.bfloat16) / 0.9
-    dx_a, _ = ops.gn_bwd(dy, x, None, sums, gamma, beta, 32, act=False, drop_p=0.1, seed=77, dgamma=None)
-    dx_b, _ = ops.gn_bwd(mask.bfloat16(), x, None, sums, gamma, beta, 32, act=False, dgamma=None)
-    ok &= _report("dropout bwd mask", dx_a, dx_b, 2e-2)
+    # dropout: keep-rate and fwd/bwd mask consistency (n = 2: multi-block kernels, n = 32: fused cluster kernels)
+    for n in (2, 32):
+        hw, c = 16, 192
+        x = torch.randn(n, hw, hw, c, device="cuda").bfloat16()
+        gamma, beta = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
+        sums, y0 = ops.gn_forward(x, None, gamma, beta, 32, act=False)
+        _, y1 = ops.gn_forward(x, None, gamma, beta, 32, act=False, drop_p=0.1, seed=77)
+        keep = (y1 != 0).float().mean().item()
+        print(f"  dropout keep-rate {keep:.4f} (expect ~0.9)")
+        ok &= abs(keep - 0.9) < 0.01
+        ok &= _report("dropout scale", y1[y1 != 0], (y0.float() / 0.9)[y1 != 0], 1e-2)
+        dy = torch.ones_like(y0)
+        # with dy = mask-consistent gradient: bwd(drop) on ones == bwd(nodrop) on the mask itself
+        mask = (y1 != 0).to(torch.bfloat16) / 0.9
+        dx_a, _ = ops.gn_bwd(dy, x, None, sums, gamma, beta, 32, act=False, drop_p=0.1, seed=77, dgamma=None)
+        dx_b, _ = ops.gn_bwd(mask.bfloat16(), x, None, sums, gamma, beta, 32, act=False, dgamma=None)
+        ok &= _report("dropout bwd mask", dx_a, dx_b, 2e-2)
+    # the two-kernel entry points stay available (and agree with the fused call)
+    x = torch.randn(16, 8, 8, 192, device="cuda").bfloat16()
+    sums_f, y_f = ops.gn_forward(x, None, gamma, beta, 32, act=True)
+    sums_s = ops.gn_stats(x, None, gamma, beta, 32)
+    y_s = ops.gn_apply(x, None, sums_s, act=True)
+    ok &= _report("gn_stats vs fused coef", sums_s, sums_f, 1e-4)
+    ok &= _report("gn_apply vs fused", y_s, y_f, 4e-3)
     return ok
 
 

@@ -78,6 +78,10 @@ def main():
         coef = ops.gn_stats(xs[0], None, gamma, beta, g, 1e-5, params=params)
         ms = timeit(lambda i: ops.gn_apply(xs[i % nbuf], None, coef, act=True, drop_p=0.1, seed=i))
         report(f"gn_apply+silu+dropout [{n},{hw},{hw},{c}]", 4 * elems, ms, "read x; write y")
+        ms = timeit(lambda i: ops.gn_forward(xs[i % nbuf], None, gamma, beta, g, 1e-5, params=params, act=True,
+                                             drop_p=0.1, seed=i))
+        report(f"gn_forward stats+apply+silu+dropout [{n},{hw},{hw},{c}]", 6 * elems, ms,
+               "read x (stats), read x again (L2), write y")
         dg, db = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
         dp = torch.zeros(n, 2 * c, device=dev)
         ms = timeit(lambda i: ops.gn_bwd(dys[i % nbuf], xs[i % nbuf], None, coef, gamma, beta, g, params=params, act=True,
