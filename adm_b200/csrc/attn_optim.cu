@@ -255,7 +255,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
                                                     float beta1, float beta2, float eps, float wd, float bc1,
                                                     float bc2_sqrt, float gscale, float max_norm,
                                                     const float* __restrict__ sqnorm,
-                                                    const float* __restrict__ hyper) {
+                                                    const float* __restrict__ hyper,
+                                                    __nv_bfloat16* __restrict__ p_bf16) {
     if (hyper != nullptr) {  // CUDA-graph friendly: step-dependent scalars live in device memory
         lr = hyper[0];
         bc1 = hyper[1];
@@ -267,16 +268,51 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
         coef = gscale * fminf(1.f, max_norm / (norm + 1e-6f));
     }
     const float step = lr / bc1;
+    const float decay = 1.f - lr * wd;
+    const float inv_bc2 = 1.f / bc2_sqrt;
+    auto upd = [&](float gi, float& pi, float& mi, float& vi) {
+        gi *= coef;
+        pi *= decay;
+        mi = beta1 * mi + (1.f - beta1) * gi;
+        vi = beta2 * vi + (1.f - beta2) * gi * gi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        pi = pi - step * mi / denom;
+    };
+    (void)inv_bc2;
+    const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+                                       reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) % 16 == 0) &&
+                     (reinterpret_cast<uintptr_t>(p_bf16) % 8 == 0);
+    if (vec) {
+        const long long n4 = n / 4;
+        for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < n4; i += 1LL * gridDim.x * blockDim.x) {
+            const float4 g4 = __ldcs(reinterpret_cast<const float4*>(g) + i);
+            float4 p4 = reinterpret_cast<float4*>(p)[i];
+            float4 m4 = reinterpret_cast<float4*>(m)[i];
+            float4 v4 = reinterpret_cast<float4*>(v)[i];
+            upd(g4.x, p4.x, m4.x, v4.x);
+            upd(g4.y, p4.y, m4.y, v4.y);
+            upd(g4.z, p4.z, m4.z, v4.z);
+            upd(g4.w, p4.w, m4.w, v4.w);
+            reinterpret_cast<float4*>(p)[i] = p4;
+            reinterpret_cast<float4*>(m)[i] = m4;
+            reinterpret_cast<float4*>(v)[i] = v4;
+            if (p_bf16 != nullptr) {  // bf16 shadow of the parameters (the GEMM operands of the next step)
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(p4.x, p4.y), hi = __floats2bfloat162_rn(p4.z, p4.w);
+                uint2 w;
+                w.x = *reinterpret_cast<const uint32_t*>(&lo);
+                w.y = *reinterpret_cast<const uint32_t*>(&hi);
+                reinterpret_cast<uint2*>(p_bf16)[i] = w;
+            }
+        }
+        return;
+    }
     for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < n; i += 1LL * gridDim.x * blockDim.x) {
-        const float gi = g[i] * coef;
-        float pi = p[i];
-        pi *= 1.f - lr * wd;
-        const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-        const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+        float pi = p[i], mi = m[i], vi = v[i];
+        upd(g[i], pi, mi, vi);
+        p[i] = pi;
         m[i] = mi;
         v[i] = vi;
-        const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] = pi - step * mi / denom;
+        if (p_bf16 != nullptr) p_bf16[i] = __float2bfloat16(pi);
     }
 }
 
@@ -342,12 +378,13 @@ int adm_sq_norm(const float* g, long long numel, float* out, void* stream) {
 
 int adm_adamw(float* p, const float* g, float* m, float* v, long long numel, float lr, float beta1, float beta2,
               float eps, float weight_decay, int step, float grad_scale, float max_norm, const float* sqnorm,
-              const float* hyper_dev, void* stream) {
+              const float* hyper_dev, void* p_bf16, void* stream) {
     if (step < 1) { set_error("adamw: step must be >= 1"); return ADM_ERR_SHAPE; }
     const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
     const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
     adamw_kernel<<<ew_blocks(numel, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        p, g, m, v, numel, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, max_norm, sqnorm, hyper_dev);
+        p, g, m, v, numel, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, max_norm, sqnorm, hyper_dev,
+        static_cast<__nv_bfloat16*>(p_bf16));
     ADM_CHECK_LAUNCH("adamw");
     return 0;
 }

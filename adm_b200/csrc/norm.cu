@@ -860,7 +860,7 @@ __global__ void __launch_bounds__(512, 1) gn_bwd_fused_kernel(
     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dparams, long long ld_dparams,
     const __nv_bfloat16* __restrict__ add, long long ldadd, int add_mode, __nv_bfloat16* __restrict__ dx1,
     long long ldx1, __nv_bfloat16* __restrict__ dx2, long long ldx2, float* __restrict__ dbias1,
-    const unsigned long long* __restrict__ seed_dev) {
+    float* __restrict__ dbias1b, const unsigned long long* __restrict__ seed_dev) {
     cg::cluster_group cluster = cg::this_cluster();
     const int K = static_cast<int>(cluster.num_blocks()), r = static_cast<int>(cluster.block_rank());
     if (seed_dev != nullptr) seed += *seed_dev * 0x9E3779B97F4A7C15ull;
@@ -1115,6 +1115,7 @@ __global__ void __launch_bounds__(512, 1) gn_bwd_fused_kernel(
             float s = 0.f;
             for (int l = 0; l < tpv; ++l) s += red[(l * V + (c >> 3)) * 8 + (c & 7)];
             atomicAdd(dbias1 + c, s);
+            if (dbias1b != nullptr) atomicAdd(dbias1b + c, s);
         }
     }
 }
@@ -1271,11 +1272,12 @@ int adm_gn_bwd(const void* dy, long long ldy, const void* x1, int c1, long long 
                const float* beta, const float* params, long long ld_params, int act, float drop_p,
                unsigned long long seed, int resample, float* work, float* bcoef, float* dgamma, float* dbeta,
                float* dparams, long long ld_dparams, const void* add, long long ldadd, int add_mode, void* dx1,
-               long long ldx1, void* dx2, long long ldx2, float* dbias1, void* stream) {
+               long long ldx1, void* dx2, long long ldx2, float* dbias1, float* dbias1b, void* stream) {
     const int C = c1 + c2;
     ADM_REQUIRE(c1 > 0 && c1 % 8 == 0 && c2 % 8 == 0 && C % groups == 0, "gn_bwd: bad channels / groups");
     ADM_REQUIRE(C <= 2048, "gn_bwd: C too large");
-    ADM_REQUIRE(dbias1 == nullptr || dx1 != nullptr, "gn_bwd: dbias1 needs dx1");
+    ADM_REQUIRE((dbias1 == nullptr || dx1 != nullptr) && (dbias1b == nullptr || dbias1 != nullptr),
+                "gn_bwd: dbias1 needs dx1 (and dbias1b needs dbias1)");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bf16* dyp = static_cast<const bf16*>(dy);
     const bf16* x1p = static_cast<const bf16*>(x1);
@@ -1288,7 +1290,7 @@ int adm_gn_bwd(const void* dy, long long ldy, const void* x1, int c1, long long 
             gn_bwd_fused_kernel, n * kc, threads, smem, kc, s, dyp, ldy, x1p, c1, ld1, x2p, c2, ld2, h, w, groups,
             reinterpret_cast<const float4*>(coef), gamma, beta, params, ld_params, act, drop_p, seed, resample, dgamma,
             dbeta, dparams, ld_dparams, static_cast<const bf16*>(add), ldadd, add_mode, static_cast<bf16*>(dx1), ldx1,
-            static_cast<bf16*>(dx2), ldx2, dbias1, g_seed_dev);
+            static_cast<bf16*>(dx2), ldx2, dbias1, dbias1b, g_seed_dev);
         if (e != cudaSuccess) {
             set_error("gn_bwd (fused) launch: %s", cudaGetErrorString(e));
             return ADM_ERR_CUDA;
@@ -1317,7 +1319,11 @@ int adm_gn_bwd(const void* dy, long long ldy, const void* x1, int c1, long long 
             reinterpret_cast<const float4*>(bcoef), act, drop_p, seed, resample, static_cast<const bf16*>(add), ldadd,
             add_mode, static_cast<bf16*>(dx1), ldx1, static_cast<bf16*>(dx2), ldx2, g_seed_dev);
         ADM_CHECK_LAUNCH("gn_bwd_apply");
-        if (dbias1 != nullptr) return adm_col_sums(dx1, ldx1, 1LL * n * h * w, c1, dbias1, stream);
+        if (dbias1 != nullptr) {
+            int rc = adm_col_sums(dx1, ldx1, 1LL * n * h * w, c1, dbias1, stream);
+            if (rc != 0 || dbias1b == nullptr) return rc;
+            return adm_col_sums(dx1, ldx1, 1LL * n * h * w, c1, dbias1b, stream);
+        }
     }
     return 0;
 }

@@ -178,18 +178,33 @@ class DDPM(nn.Module):
         return self.sample_fn_d(shape, unnormalize=True, cond=cond, x_T=x_T)
 
     @torch.no_grad()
-    def sample_fn_d(self, shape, up_scale=1, unnormalize=True, cond=None, denoise=False, x_T=None):
+    def sample_fn_d(self, shape, up_scale=1, unnormalize=True, cond=None, denoise=False, x_T=None, use_graph=None):
+        """ddm_const.py:425-476.  The whole N-step loop (N UNet forwards + N fused K3 updates) is captured once per
+        (shape, N) into a CUDA graph and replayed: the per-step times are host constants baked into the kernels'
+        arguments, the start noise is copied into the graph's static input."""
         device = self.eps.device
         ts = self.t_steps()
         if x_T is None:
             x_T = torch.randn(shape, device=device, dtype=torch.float64)
-        x = (x_T.to(device=device, dtype=torch.float64) * ts[0]).contiguous()
+        x_T = x_T.to(device=device, dtype=torch.float64)
         was_training = self.model.training
         self.model.eval()
+        if use_graph is None:
+            use_graph = cond is None and x_T.is_cuda and not torch.cuda.is_current_stream_capturing()
+        try:
+            if use_graph:
+                return self._sample_d_graph(x_T, ts, unnormalize)
+            t_dev = torch.tensor(ts, device=device, dtype=torch.float64)
+            return self._sample_d_loop(x_T, ts, t_dev, unnormalize, cond)
+        finally:
+            self.model.train(was_training)
+
+    def _sample_d_loop(self, x_T, ts, t_dev, unnormalize, cond=None):
+        x = (x_T * ts[0]).contiguous()
         clip = 1. * self.scale_input
         n = len(ts) - 1
         for i, (t_cur, t_next) in enumerate(zip(ts[:-1], ts[1:])):
-            tc = torch.tensor(t_cur, device=device, dtype=torch.float64)
+            tc = t_dev[i]
             pred = self.model(x, tc, cond) if cond is not None else self.model(x, tc)
             c, noise = pred[:2]
             last = i == n - 1
@@ -198,8 +213,36 @@ class DDPM(nn.Module):
                 x = x.clamp_(-clip, clip) / self.scale_input if self.scale_input != 1 else x.clamp_(-clip, clip)
             else:
                 x = ops.sampler_step(x, c, noise, t_cur, t_next, clip, self.clip_x_start, last, self.scale_input)
-        self.model.train(was_training)
         return x
+
+    def _model_signature(self):
+        eng = getattr(getattr(self.model, "model", None), "engine", None)
+        return eng.signature() if eng is not None else None
+
+    def _sample_d_graph(self, x_T, ts, unnormalize):
+        key = (tuple(x_T.shape), tuple(ts), bool(unnormalize), bool(self.clip_x_start), float(self.scale_input))
+        cache = self.__dict__.setdefault("_sample_graphs", {})
+        ent = cache.get(key)
+        sig = self._model_signature()
+        if ent is None:
+            t_dev = torch.tensor(ts, device=x_T.device, dtype=torch.float64)
+            static_in = x_T.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up outside capture: fills the engine's weight caches
+                self._sample_d_loop(static_in, ts[:2] + [0.0] if len(ts) > 2 else ts, t_dev, unnormalize)
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = self._sample_d_loop(static_in, ts, t_dev, unnormalize)
+            ent = cache[key] = dict(graph=g, x=static_in, out=static_out, t=t_dev, sig=sig)
+        elif ent["sig"] != sig:
+            # parameters changed since capture: one eager forward re-derives the cached bf16 operands in place
+            self.model(ent["x"], ent["t"][0])
+            ent["sig"] = sig
+        ent["x"].copy_(x_T)
+        ent["graph"].replay()
+        return ent["out"].clone()
 
     @torch.no_grad()
     def sample_fn_s(self, shape, up_scale=1, unnormalize=True, cond=None, denoise=False, x_T=None, z_list=None):

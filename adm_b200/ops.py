@@ -158,6 +158,13 @@ def cast_bf16(x):
     return out
 
 
+def cast_bf16_into(src, dst):
+    """dst (bf16, contiguous) <- src (fp32, contiguous), same numel."""
+    assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
+    check(_lib.load().adm_cast_f32_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "cast_f32_bf16")
+    return dst
+
+
 def conv_fprop(x1, wpk, x2=None, bias=None, residual=None, alpha=1.0, out_dtype=BF16, out=None, nout=None,
                keep_pad=False):
     """Implicit-GEMM conv (3x3 pad 1 or 1x1) on NHWC bf16.  wpk: [nout, taps, kpad] bf16."""
@@ -261,8 +268,9 @@ def gemm_nn(a, b, out_dtype=F32, alpha=1.0, out=None):
     return out
 
 
-def gemm_tn(a, b, out_dtype=F32, alpha=1.0, out=None, splits=1):
-    """C[M,N] = alpha * A[K,M]^T @ B[K,N]; both row-major, both consumed MN-major (the wgrad shape)."""
+def gemm_tn(a, b, out_dtype=F32, alpha=1.0, out=None, splits=1, accumulate=False):
+    """C[M,N] = alpha * A[K,M]^T @ B[K,N]; both row-major, both consumed MN-major (the wgrad shape).
+    accumulate: C += (fp32 atomics) into the given `out`."""
     _need_cuda(a, b)
     assert a.dtype == BF16 and b.dtype == BF16 and a.stride(1) == 1 and b.stride(1) == 1
     k, m = a.shape
@@ -274,7 +282,9 @@ def gemm_tn(a, b, out_dtype=F32, alpha=1.0, out=None, splits=1):
     d.a = _operand(a, 1, (m, k, 1), (a.stride(0), a.stride(0) * k))
     d.b = _operand(b, 1, (n, k, 1), (b.stride(0), b.stride(0) * k))
     d.m, d.n, d.k, d.batches, d.bdiv, d.splits = m, n, k, 1, 1, splits
-    d.c, d.out_mode, d.ldc = out.data_ptr(), (2 if splits > 1 else (0 if out.dtype == BF16 else 1)), out.stride(0)
+    atomic = splits > 1 or accumulate
+    assert not atomic or out.dtype == F32
+    d.c, d.out_mode, d.ldc = out.data_ptr(), (2 if atomic else (0 if out.dtype == BF16 else 1)), out.stride(0)
     d.alpha = float(alpha)
     check(_lib.load().adm_gemm_batched(d, _stream()), "gemm_tn")
     return out
@@ -337,7 +347,7 @@ def gn_forward(x1, x2, gamma, beta, groups, eps=1e-5, params=None, act=True, dro
 
 
 def gn_bwd(dy, x1, x2, coef, gamma, beta, groups, params=None, act=True, drop_p=0.0, seed=0, resample=0,
-           dgamma=None, dbeta=None, dparams=None, add=None, add_mode=0, need_dx=True, dbias1=None):
+           dgamma=None, dbeta=None, dparams=None, add=None, add_mode=0, need_dx=True, dbias1=None, dbias1b=None):
     """Returns (dx1, dx2).  dgamma/dbeta are accumulated in place; dparams ([N, 2C] view) is overwritten;
     dbias1 (fp32 [c1]) += column sums of dx1."""
     n, h, w, _ = x1.shape
@@ -357,7 +367,8 @@ def gn_bwd(dy, x1, x2, coef, gamma, beta, groups, params=None, act=True, drop_p=
                                  _ptr(dbeta), _ptr(dparams), lddp, _ptr(add),
                                  add.stride(-2) if add is not None else 0, int(add_mode), _ptr(dx1),
                                  dx1.stride(2) if dx1 is not None else 0, _ptr(dx2),
-                                 dx2.stride(2) if dx2 is not None else 0, _ptr(dbias1), _stream()), "gn_bwd")
+                                 dx2.stride(2) if dx2 is not None else 0, _ptr(dbias1), _ptr(dbias1b), _stream()),
+          "gn_bwd")
     return dx1, dx2
 
 
@@ -514,10 +525,10 @@ def sq_norm(g, out):
 
 
 def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, max_norm=0.0, sqnorm=None,
-          hyper_dev=None):
+          hyper_dev=None, p_bf16=None):
     check(_lib.load().adm_adamw(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(beta1), float(beta2),
                                 float(eps), float(weight_decay), int(step), float(grad_scale), float(max_norm),
-                                _ptr(sqnorm), _ptr(hyper_dev), _stream()), "adamw")
+                                _ptr(sqnorm), _ptr(hyper_dev), _ptr(p_bf16), _stream()), "adamw")
 
 
 def set_seed_counter(t):

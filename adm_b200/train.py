@@ -44,10 +44,12 @@ def completion_order(net):
             block_params(blk)
         else:
             order.extend(blk.parameters())
-    for sec in (m.dec2, m.dec, m.enc):
-        for blk in sec.values():
-            if hasattr(blk, "affine"):
-                order.extend(blk.affine.parameters())
+    # every block's affine (time-embedding) weight, then every bias, back to back in the engine's block order:
+    # their gradients all come from ONE grouped GEMM at the end of backward, and the contiguous layout lets that GEMM
+    # (and the forward one) address them as a single [sum 2*Cout, emb] matrix inside the arena.
+    affine = [blk.affine for sec in (m.enc, m.dec, m.dec2) for blk in sec.values() if hasattr(blk, "affine")]
+    order.extend(a.weight for a in affine)
+    order.extend(a.bias for a in affine)
     order.extend(m.map_layer1.parameters())
     order.extend(m.map_layer0.parameters())
     if m.map_augment is not None:
@@ -64,9 +66,15 @@ def completion_order(net):
 class ParamArena:
     """Re-homes every parameter (and its .grad) of a module into two flat fp32 buffers, in gradient-completion order."""
 
-    def __init__(self, module, order=None, align=4):
+    def __init__(self, module, order=None, align=8, channels_last=()):
+        """channels_last: conv weights [Cout, Cin, k, k] to store physically as [Cout][k][k][Cin] — the packed operand
+        order of the GEMM engine.  They keep their logical (reference) shape as a permuted view, so state_dict /
+        load_state_dict are unaffected, and on CUDA they get a bf16 shadow (written by the fused AdamW kernel) plus a
+        packed view of their gradient: ``p._adm_pack = (bf16 [Cout, k*k, Cin], fp32 grad [Cout, k*k, Cin], version,
+        fp32 flat slice)``."""
         params = order if order is not None else list(module.parameters())
         dev = params[0].device
+        cl = {id(p) for p in channels_last}
         offs, total = [], 0
         for p in params:
             offs.append(total)
@@ -76,18 +84,56 @@ class ParamArena:
         self.numel = total
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
         self.grads = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.shadow = torch.zeros(total, device=dev, dtype=torch.bfloat16) if (cl and dev.type == "cuda") else None
+        self._grad_views = []
         for p, o in zip(params, offs):
-            view = self.flat[o:o + p.numel()].view(p.shape)
+            n = p.numel()
+            if id(p) in cl:
+                co, ci, kh, kw = p.shape
+                view = self.flat[o:o + n].view(co, kh, kw, ci).permute(0, 3, 1, 2)
+                gview = self.grads[o:o + n].view(co, kh, kw, ci).permute(0, 3, 1, 2)
+            else:
+                view = self.flat[o:o + n].view(p.shape)
+                gview = self.grads[o:o + n].view(p.shape)
             view.copy_(p.data)
             p.data = view
-            p.grad = self.grads[o:o + p.numel()].view(p.shape)
+            p.grad = gview
+            self._grad_views.append(gview)
+            if id(p) in cl and self.shadow is not None:
+                p._adm_pack = (self.shadow[o:o + n].view(co, kh * kw, ci), self.grads[o:o + n].view(co, kh * kw, ci),
+                               p._version, self.flat[o:o + n])
+        self.refresh_shadow()
+
+    def refresh_shadow(self):
+        """Re-derive the bf16 shadow from the fp32 masters (after construction or an out-of-band parameter write)."""
+        if self.shadow is not None:
+            ops.cast_bf16_into(self.flat, self.shadow)
+            for p in self.params:
+                pk = getattr(p, "_adm_pack", None)
+                if pk is not None:
+                    p._adm_pack = (pk[0], pk[1], p._version, pk[3])
+
+    def slice_of(self, params):
+        """(offset, numel) of a run of parameters that sit back to back in the arena, else None."""
+        idx = {id(p): i for i, p in enumerate(self.params)}
+        first = idx.get(id(params[0]))
+        if first is None:
+            return None
+        o = self.offsets[first]
+        end = o
+        for j, p in enumerate(params):
+            i = idx.get(id(p))
+            if i != first + j or self.offsets[i] != end:
+                return None
+            end += p.numel()
+        return o, end - o
 
     def rebind_grads(self):
         """If someone set .grad to None (optimizer.zero_grad(set_to_none=True)), point it back into the arena."""
-        for p, o in zip(self.params, self.offsets):
+        for p, o, gv in zip(self.params, self.offsets, self._grad_views):
             g = p.grad
             if g is None or g.data_ptr() != self.grads.data_ptr() + 4 * o:
-                p.grad = self.grads[o:o + p.numel()].view(p.shape)
+                p.grad = gv
 
     def zero_grad(self):
         self.grads.zero_()
@@ -108,7 +154,8 @@ class TrainStep:
         self.dpm = dpm
         self.net = dpm.model
         self.engine = self.net.model.engine
-        self.arena = ParamArena(self.net, completion_order(self.net))
+        self.arena = ParamArena(self.net, completion_order(self.net), channels_last=self.engine.packable_params())
+        self._bind_affine()
         self.m = torch.zeros_like(self.arena.flat)
         self.v = torch.zeros_like(self.arena.flat)
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
@@ -136,6 +183,28 @@ class TrainStep:
         if self.seed_counter is not None:
             ops.set_seed_counter(self.seed_counter)
         self.graph = None
+
+    def _bind_affine(self):
+        """Hand the engine ONE [sum 2*Cout, emb] view of all affine weights (bf16 shadow), biases and their gradients."""
+        a, eng = self.arena, self.engine
+        eng.affine_pack = None
+        if a.shadow is None:
+            return
+        mods = [m.affine for _, m, _ in eng.block_list]
+        ws, bs = a.slice_of([m.weight for m in mods]), a.slice_of([m.bias for m in mods])
+        if ws is None or bs is None:
+            return
+        emb = mods[0].in_features
+        t = ws[1] // emb
+        assert t == eng.affine_total and bs[1] == t
+        eng.affine_pack = (a.shadow[ws[0]:ws[0] + ws[1]].view(t, emb), a.flat[bs[0]:bs[0] + t],
+                           a.grads[ws[0]:ws[0] + ws[1]].view(t, emb), a.grads[bs[0]:bs[0] + t],
+                           a.flat[ws[0]:ws[0] + ws[1]], tuple(m.weight._version for m in mods))
+
+    def refresh(self):
+        """Call after parameters were written outside the fused optimizer (load_state_dict, manual edits)."""
+        self.arena.refresh_shadow()
+        self.engine.invalidate()
 
     # ------------------------------------------------------------------------------------------ gradient reduction
     # The arena is laid out in gradient-completion order, so "everything below offset X is final" grows monotonically
@@ -241,7 +310,7 @@ class TrainStep:
         ops.sq_norm(a.grads, self.sqnorm)
         ops.adamw(a.flat, a.grads, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
                   max(1, self.step_count), grad_scale=gscale, max_norm=self.max_grad_norm, sqnorm=self.sqnorm,
-                  hyper_dev=self.hyper)
+                  hyper_dev=self.hyper, p_bf16=a.shadow)
         a.zero_grad()
         self.engine.invalidate()
 

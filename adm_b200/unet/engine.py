@@ -46,6 +46,41 @@ class UNetEngine:
         self.affine_total = off
         self._perm = {}
         self.grad_hook = None  # callable(list_of_params) invoked as soon as those gradients are final (DP overlap)
+        # set by the training arena (adm_b200.train.TrainStep): (wall bf16 [T, emb], ball fp32 [T], dwall fp32, dball fp32,
+        # fp32 master slice of wall, parameter versions)
+        # when every block's affine weight / bias are laid out back to back in the parameter arena
+        self.affine_pack = None
+
+    # ------------------------------------------------------------------------------------------ arena fast paths
+    def packable_params(self):
+        """Conv weights this engine consumes in the plain packed order [Cout][tap][Cin] with no row permutation and
+        no channel padding: an arena may store exactly that order (channels-last) and attach a bf16 shadow
+        (``weight._adm_pack = (bf16 [Cout, taps, Cin], fp32 grad [Cout, taps, Cin])``) so that neither a re-pack of the
+        weights nor an un-pack of their gradients is needed."""
+        net = self.net
+        convs = []
+        for _, m, _ in self.block_list:
+            convs += [m.conv0, m.conv1]
+            if m.skip is not None and m.skip.weight is not None:
+                convs.append(m.skip)
+            if m.num_heads:
+                convs.append(m.proj)
+        convs += [net.out_conv, net.out_conv2, net.decouple1[0], net.decouple2[0]]
+        chans = {m.in_channels for _, m, _ in self.block_list} | {m.out_channels for _, m, _ in self.block_list}
+        if any(c % 64 for c in chans):
+            return []
+        return [c.weight for c in convs if c.weight.shape[1] % 64 == 0]
+
+    @staticmethod
+    def _pack_of(w):
+        """(bf16 packed weights, fp32 packed gradient) of an arena-resident channels-last parameter, or None."""
+        pk = getattr(w, "_adm_pack", None)
+        if pk is None:
+            return None
+        if w._version != pk[2]:  # modified through torch (load_state_dict, ...) since the shadow was written
+            ops.cast_bf16_into(pk[3], pk[0])
+            w._adm_pack = pk = (pk[0], pk[1], w._version, pk[3])
+        return pk
 
     # ------------------------------------------------------------------------------------------ weight caches
     def invalidate(self):
@@ -61,17 +96,31 @@ class UNetEngine:
         self._cache[key] = (ver, val)
         return val
 
+    def signature(self):
+        """Changes whenever any parameter may have changed (optimizer epoch or a torch-side in-place write)."""
+        return self._epoch, sum(p._version for p in self.net.parameters())
+
     def _dev(self):
         return self.net.map_layer0.weight.device
 
     def conv_w(self, conv, c1=None, c2=0, perm=None):
         w = conv.weight
+        pk = self._pack_of(w) if perm is None else None
+        if pk is not None:
+            return pk[0]
         return self._cached(("cw", id(conv)), [w],
                             lambda old: ops.pack_conv_weight(w.detach(), c1, c2, row_perm=perm, out=old))
 
+    # Every builder below re-derives INTO the buffer of the previous value when there is one, so that device pointers
+    # stay stable: a CUDA graph captured over a forward pass (sampler) stays valid across weight updates.
     def lin_w(self, lin):
         w = lin.weight
-        return self._cached(("lw", id(lin)), [w], lambda old: ops.cast_bf16(w.detach()))
+
+        def build(old):
+            if old is None:
+                return ops.cast_bf16(w.detach())
+            return ops.cast_bf16_into(w.detach().contiguous(), old)
+        return self._cached(("lw", id(lin)), [w], build)
 
     def aug_w(self):
         w = self.net.map_augment.weight  # [mc, augment_dim] -> zero padded to 16 columns
@@ -79,10 +128,17 @@ class UNetEngine:
         def build(old):
             wp = torch.zeros(w.shape[0], 16, device=w.device, dtype=F32)
             wp[:, :w.shape[1]] = w.detach()
-            return ops.cast_bf16(wp)
+            return ops.cast_bf16(wp) if old is None else ops.cast_bf16_into(wp, old)
         return self._cached(("aug",), [w], build)
 
     def affine_all(self):
+        if self.affine_pack is not None:
+            ap = self.affine_pack
+            ver = tuple(m.affine.weight._version for _, m, _ in self.block_list)
+            if ver != ap[5]:  # written through torch since the shadow was derived (load_state_dict, ...)
+                ops.cast_bf16_into(ap[4], ap[0])
+                self.affine_pack = ap = ap[:5] + (ver,)
+            return ap[0], ap[1]
         ps = [m.affine.weight for _, m, _ in self.block_list] + [m.affine.bias for _, m, _ in self.block_list]
 
         def build(old):
@@ -92,7 +148,8 @@ class UNetEngine:
                 o = m.affine.out_features
                 ops._lib.check(ops._lib.load().adm_cast_f32_bf16(m.affine.weight.data_ptr(), wall[off:off + o].data_ptr(),
                                                                  m.affine.weight.numel(), ops._stream()), "cast")
-            ball = torch.cat([m.affine.bias.detach() for _, m, _ in self.block_list])
+            biases = [m.affine.bias.detach() for _, m, _ in self.block_list]
+            ball = torch.cat(biases) if old is None else torch.cat(biases, out=old[1])
             return wall, ball
         return self._cached(("affine_all",), ps, build)
 
@@ -124,19 +181,31 @@ class UNetEngine:
             p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
         return p.grad
 
-    def _conv_param_grads(self, conv, dy, x1, x2=None, perm=None, dy_cols=None):
-        """dW (tcgen05 wgrad, packed) -> reference layout; db via column sums."""
+    def _conv_param_grads(self, conv, dy, x1, x2=None, perm=None, dy_cols=None, bias_done=False):
+        """dW (tcgen05 wgrad, packed) -> reference layout; db via column sums (unless the producer of dy already
+        accumulated them: bias_done)."""
+        if bias_done:
+            bias = None
+        else:
+            bias = conv.bias
+        self._conv_weight_grad(conv, dy, x1, x2, perm)
+        if bias is not None:
+            self._bias_grad(bias, dy if dy_cols is None else dy_cols, perm)
+
+    def _conv_weight_grad(self, conv, dy, x1, x2=None, perm=None):
         k = conv.weight.shape[-1]
         c1 = x1.shape[-1]
         c2 = x2.shape[-1] if x2 is not None else 0
         cin_ref = conv.weight.shape[1]
+        pk = self._pack_of(conv.weight) if perm is None else None
+        if pk is not None and conv.weight.grad is not None and conv.weight.grad.data_ptr() == pk[1].data_ptr():
+            ops.conv_wgrad(dy, x1, x2=x2, ntaps=k * k, out=pk[1])  # straight into the (channels-last) gradient arena
+            return
         dwp = ops.conv_wgrad(dy, x1, x2=x2, ntaps=k * k)
         if x2 is None and c1 != cin_ref:  # zero-padded network input (3 -> 8 channels)
             c1 = cin_ref
         ops.unpack_conv_wgrad(dwp, c1, c2, k, out=self._grad(conv.weight), accumulate=True,
                               row_perm=perm[0] if perm is not None else None)
-        if conv.bias is not None:
-            self._bias_grad(conv.bias, dy if dy_cols is None else dy_cols, perm)
 
     def _bias_grad(self, bias, dy, perm=None):
         g = self._grad(bias)
@@ -178,7 +247,9 @@ class UNetEngine:
             perm = self.qkv_perm(cout, blk.num_heads)
             c.sums2, c.a2 = ops.gn_forward(c.h1, None, blk.norm2.weight, blk.norm2.bias, _groups(cout), blk.norm2.eps,
                                            act=False)
-            bq = self._cached(("qkvb", id(blk)), [blk.qkv.bias], lambda old: blk.qkv.bias.detach()[perm[1]].contiguous())
+            bq = self._cached(("qkvb", id(blk)), [blk.qkv.bias],
+                              lambda old: blk.qkv.bias.detach()[perm[1]].contiguous() if old is None
+                              else torch.index_select(blk.qkv.bias.detach(), 0, perm[1], out=old))
             c.qkv = ops.conv_fprop(c.a2, self.conv_w(blk.qkv, perm=perm[0]), bias=bq)
             c.att, c.p = ops.attention_fwd(c.qkv, blk.num_heads)
             out = ops.conv_fprop(c.att, self.conv_w(blk.proj), bias=blk.proj.bias, residual=c.h1)
@@ -186,42 +257,62 @@ class UNetEngine:
             save.append(c)
         return out
 
-    def block_bwd(self, c, dout, dparams):
-        """dout: gradient at the block output.  Returns (dx1, dx2)."""
+    def bias_sinks(self, blk):
+        """Bias gradients that equal the column sums of the gradient at a block's OUTPUT (they can be accumulated by
+        whichever kernel produces that gradient): proj.bias with attention, else conv1.bias (+ the 1x1 skip's bias)."""
+        if blk.num_heads:
+            return [self._grad(blk.proj.bias)]
+        sinks = [self._grad(blk.conv1.bias)]
+        if blk.skip is not None and blk.skip.weight is not None and blk.skip.bias is not None:
+            sinks.append(self._grad(blk.skip.bias))
+        return sinks
+
+    def block_bwd(self, c, dout, dparams, dout_bias_done=False, input_sinks=None):
+        """dout: gradient at the block output.  Returns (dx1, dx2).
+        dout_bias_done: the producer of `dout` already added its column sums to bias_sinks(blk).
+        input_sinks: bias_sinks of the block that produced x1 — this block's last kernel accumulates colsum(dx1) there."""
         blk = c.blk
         cin1 = c.x1.shape[-1]
         cin2 = c.x2.shape[-1] if c.x2 is not None else 0
         cin, cout = cin1 + cin2, blk.out_channels
+        has_skip_conv = blk.skip is not None and blk.skip.weight is not None
+        h1_sinks = [self._grad(blk.conv1.bias)] + ([self._grad(blk.skip.bias)] if has_skip_conv else [])
         if blk.num_heads:
             perm = self.qkv_perm(cout, blk.num_heads)
-            self._conv_param_grads(blk.proj, dout, c.att)
+            self._conv_param_grads(blk.proj, dout, c.att, bias_done=dout_bias_done)
             datt = ops.conv_dgrad(dout, self.conv_w(blk.proj))
             dqkv = ops.attention_bwd(datt, c.qkv, c.p, blk.num_heads)
             self._conv_param_grads(blk.qkv, dqkv, c.a2, perm=perm)
             da2 = ops.conv_dgrad(dqkv, self.conv_w(blk.qkv, perm=perm[0]))
             dh1, _ = ops.gn_bwd(da2, c.h1, None, c.sums2, blk.norm2.weight, blk.norm2.bias, _groups(cout),
                                 act=False, dgamma=self._grad(blk.norm2.weight),
-                                dbeta=self._grad(blk.norm2.bias), add=dout, add_mode=0)
+                                dbeta=self._grad(blk.norm2.bias), add=dout, add_mode=0,
+                                dbias1=h1_sinks[0], dbias1b=h1_sinks[1] if len(h1_sinks) > 1 else None)
+            h1_bias_done = True
         else:
             dh1 = dout
+            h1_bias_done = dout_bias_done
         # h1 = conv1(a1) + b1 + skip(x)
-        self._conv_param_grads(blk.conv1, dh1, c.a1)
+        self._conv_param_grads(blk.conv1, dh1, c.a1, bias_done=h1_bias_done)
         da1 = ops.conv_dgrad(dh1, self.conv_w(blk.conv1))
         dh0, _ = ops.gn_bwd(da1, c.h0, None, c.sums1, blk.norm1.weight, blk.norm1.bias, _groups(cout),
                             params=c.params, act=True, drop_p=c.drop_p, seed=c.seed,
-                            dgamma=self._grad(blk.norm1.weight), dbeta=self._grad(blk.norm1.bias), dparams=dparams)
+                            dgamma=self._grad(blk.norm1.weight), dbeta=self._grad(blk.norm1.bias), dparams=dparams,
+                            dbias1=self._grad(blk.conv0.bias))
         # h0 = conv0(a0) + b0
-        self._conv_param_grads(blk.conv0, dh0, c.a0)
+        self._conv_param_grads(blk.conv0, dh0, c.a0, bias_done=True)
         da0 = ops.conv_dgrad(dh0, self.conv_w(blk.conv0))
-        if blk.skip is not None and blk.skip.weight is not None:
-            self._conv_param_grads(blk.skip, dh1, c.x1, c.x2)
+        if has_skip_conv:
+            self._conv_param_grads(blk.skip, dh1, c.x1, c.x2, bias_done=h1_bias_done)
             add = ops.conv_dgrad(dh1, self.conv_w(blk.skip, cin1, cin2))
             add_mode = 0
         else:
             add, add_mode = dh1, c.mode
+        s0 = input_sinks[0] if input_sinks else None
+        s1 = input_sinks[1] if input_sinks and len(input_sinks) > 1 else None
         return ops.gn_bwd(da0, c.x1, c.x2, c.sums0, blk.norm0.weight, blk.norm0.bias, _groups(cin),
                           act=True, resample=c.mode, dgamma=self._grad(blk.norm0.weight),
-                          dbeta=self._grad(blk.norm0.bias), add=add, add_mode=add_mode)
+                          dbeta=self._grad(blk.norm0.bias), add=add, add_mode=add_mode, dbias1=s0, dbias1b=s1)
 
     # ------------------------------------------------------------------------------------------ embedding MLP
     def embed_fwd(self, c_noise, aug, save):
@@ -260,12 +351,16 @@ class UNetEngine:
         net = self.net
         dpb = ops.cast_bf16(dparams_all)
         wall, _ = self.affine_all()
-        dwall = ops.gemm_tn(dpb, e.embb)  # [sum 2*Cout, emb]
-        for _, m, off in self.block_list:
-            o = m.affine.out_features
-            ops.unpack_conv_wgrad(dwall[off:off + o], net.emb_channels, 0, 1, out=self._grad(m.affine.weight),
-                                  accumulate=True)
-            ops.col_sums(dpb[:, off:off + o], self._grad(m.affine.bias))
+        if self.affine_pack is not None:  # all affine weights / biases are contiguous in the gradient arena
+            ops.gemm_tn(dpb, e.embb, out=self.affine_pack[2], accumulate=True)
+            ops.col_sums(dpb, self.affine_pack[3])
+        else:
+            dwall = ops.gemm_tn(dpb, e.embb)  # [sum 2*Cout, emb]
+            for _, m, off in self.block_list:
+                o = m.affine.out_features
+                ops.unpack_conv_wgrad(dwall[off:off + o], net.emb_channels, 0, 1, out=self._grad(m.affine.weight),
+                                      accumulate=True)
+                ops.col_sums(dpb[:, off:off + o], self._grad(m.affine.bias))
         demb = ops.gemm_nn(dpb, wall)
         _, de1b = ops.silu_bwd(e.e1, demb, want_f32=False)
         self._linear_grads(net.map_layer1, de1b, e.s0b)
@@ -280,9 +375,7 @@ class UNetEngine:
     def decouple_fwd(self, seq, x, save):
         conv, sa = seq[0], seq[1]
         d = NS(seq=seq, x=x)
-        d.wkey = ("dcw", id(conv))
-        wpk = self._cached(d.wkey, [conv.weight], lambda old: ops.pack_conv_weight(conv.weight.detach(), out=old))
-        d.h = ops.conv_fprop(x, wpk, bias=conv.bias)
+        d.h = ops.conv_fprop(x, self.conv_w(conv), bias=conv.bias)
         d.w_map = sa.map.weight.detach().reshape(-1)
         d.scal = torch.cat([sa.map.bias.detach(), sa.q_conv.weight.detach().reshape(-1), sa.q_conv.bias.detach(),
                             sa.k_conv.weight.detach().reshape(-1), sa.k_conv.bias.detach()])
@@ -304,11 +397,8 @@ class UNetEngine:
         self._grad(sa.q_conv.bias).add_(dscal[2:3])
         self._grad(sa.k_conv.weight).add_(dscal[3:4].reshape(1, 1, 1, 1))
         self._grad(sa.k_conv.bias).add_(dscal[4:5])
-        dwp = ops.conv_wgrad(dh, d.x, ntaps=9)
-        ops.unpack_conv_wgrad(dwp, c, 0, 3, out=self._grad(conv.weight), accumulate=True)
-        ops.col_sums(dh, self._grad(conv.bias))
-        wpk = self._cache[d.wkey][1]
-        return ops.conv_dgrad(dh, wpk, residual=dy)
+        self._conv_param_grads(conv, dh, d.x)
+        return ops.conv_dgrad(dh, self.conv_w(conv), residual=dy)
 
     # ------------------------------------------------------------------------------------------ whole network
     def _run_fwd(self, xin, c_noise, aug, training, tape):
@@ -399,15 +489,22 @@ class UNetEngine:
             dfv = df[..., :c_img]
             self._conv_param_grads(o.conv, dfv, o.a, dy_cols=df)
             da = ops.conv_dgrad(dfv, self.conv_w(o.conv))
+            # each kernel that produces the gradient at a block's output also accumulates its column sums into that
+            # block's bias gradients (bias_sinks), so the decoder chain needs no separate col_sums passes
+            sinks = self.bias_sinks(items[pos - 1].blk)
             dh, _ = ops.gn_bwd(da, o.x, None, o.sums, o.norm.weight, o.norm.bias, _groups(o.x.shape[-1]),
-                               act=True, dgamma=self._grad(o.norm.weight), dbeta=self._grad(o.norm.bias))
+                               act=True, dgamma=self._grad(o.norm.weight), dbeta=self._grad(o.norm.bias),
+                               dbias1=sinks[0], dbias1b=sinks[1] if len(sinks) > 1 else None)
             self._notify(o.conv, o.norm)
             si = 0  # forward pops skips from the end, so walking the decoder backwards meets skips[0], skips[1], ...
             while not hasattr(items[pos - 1], "seq"):
                 pos -= 1
                 c = items[pos]
                 off = boff[id(c.blk)]
-                dx1, dx2 = self.block_bwd(c, dh, tape.dparams_all[:, off:off + c.blk.affine.out_features])
+                prev = items[pos - 1]
+                sinks = self.bias_sinks(prev.blk) if hasattr(prev, "blk") else None
+                dx1, dx2 = self.block_bwd(c, dh, tape.dparams_all[:, off:off + c.blk.affine.out_features],
+                                          dout_bias_done=True, input_sinks=sinks)
                 self._notify(c.blk)
                 if c.x2 is not None:
                     dskips[si] = dx2 if dskips[si] is None else ops.add_bf16(dskips[si], dx2)

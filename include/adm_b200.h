@@ -154,9 +154,10 @@ int adm_gn_bwd(const void* dy, long long ldy, const void* x1, int c1, long long 
                const float* beta, const float* params, long long ld_params, int act, float drop_p,
                unsigned long long seed, int resample, float* work, float* bcoef, float* dgamma, float* dbeta,
                float* dparams, long long ld_dparams, const void* add, long long ldadd, int add_mode, void* dx1,
-               long long ldx1, void* dx2, long long ldx2, float* dbias1, void* stream);
-/*   dbias1 (optional, fp32 [c1]): += column sums of dx1 — the bias gradient of the conv that produced x1
- *   (unet/uncond_unet.py:111-112 backward), so no separate pass over dx1 is needed.
+               long long ldx1, void* dx2, long long ldx2, float* dbias1, float* dbias1b, void* stream);
+/*   dbias1, dbias1b (optional, fp32 [c1]): += column sums of dx1 — the bias gradient of the conv(s) that produced x1
+ *   (conv1 and the 1x1 skip of a UNetBlock share it; unet/uncond_unet.py:111-112 backward), so no separate pass
+ *   over dx1 is needed.
  * adm_gn_forward = gn_stats + gn_apply in one call.  When the batch fills the SMs it runs ONE kernel with a
  * thread-block cluster per sample (statistics exchanged through distributed shared memory, apply pass re-reading the
  * sample from L2); adm_gn_bwd does the same for the backward pair.  out == NULL computes the coefficient table only. */
@@ -196,9 +197,11 @@ int adm_sq_norm(const float* g, long long numel, float* out, void* stream);
 /* g_eff = g * grad_scale * min(1, max_norm / (sqrt(*sqnorm) * grad_scale + 1e-6)); torch.optim.AdamW update. */
 int adm_adamw(float* p, const float* g, float* m, float* v, long long numel, float lr, float beta1, float beta2,
               float eps, float weight_decay, int step, float grad_scale, float max_norm, const float* sqnorm,
-              const float* hyper_dev, void* stream);
+              const float* hyper_dev, void* p_bf16, void* stream);
 /*   hyper_dev (optional, device fp32[3] = {lr, 1-beta1^step, sqrt(1-beta2^step)}) overrides lr/step so that a captured
- *   CUDA graph of the step can be replayed with fresh values.                                                 */
+ *   CUDA graph of the step can be replayed with fresh values.  p_bf16 (optional, bf16 [numel]): a bf16 shadow of the
+ *   updated parameters written in the same pass — the tensor-core operands of the next step, so no separate
+ *   weight re-pack is needed for parameters whose arena layout already is the packed [Cout][tap][Cin] order.     */
 
 #ifdef __cplusplus
 }

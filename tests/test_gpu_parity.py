@@ -161,3 +161,49 @@ def test_fused_optimizer_step_matches_torch_adamw():
     for n, p in net.named_parameters():
         assert torch.allclose(p.detach(), ps[n].detach(), rtol=1e-5, atol=1e-7), n
     assert float(step.arena.grads.abs().max()) == 0.0  # gradients are cleared for the next step
+
+
+def test_arena_fast_path_matches_plain_backward():
+    """TrainStep stores conv weights channels-last with a bf16 shadow and lets wgrad / the grouped affine GEMM write
+    straight into the gradient arena; the gradients must equal those of the plain (re-pack / un-pack) path, and after
+    an optimizer step the shadow must equal the bf16 rounding of the fp32 masters."""
+    from tests.golden.make_golden import TINY, inputs
+    from adm_b200.ddm.ddm_const import DDPM
+    from adm_b200.train import TrainStep
+    cfg = dict(image_size=[16, 16], sampling_timesteps=3, eps=1e-4, weighting_loss=True)
+    x, t, noise, aug = (a.cuda() for a in inputs(TINY, 16, 7))
+    net_a = CU_build(TINY)
+    dpm_a = DDPM(model=net_a, cfg=cfg, **cfg).cuda()
+    loss_a, _ = dpm_a.p_losses(x, t, noise=noise, augment_labels=aug)
+    loss_a.backward()
+    ga = {n: p.grad.clone() for n, p in net_a.named_parameters()}
+    net_b = CU_build(TINY)
+    dpm_b = DDPM(model=net_b, cfg=cfg, **cfg).cuda()
+    step = TrainStep(dpm_b, lr=1e-3)
+    packed = [n for n, p in net_b.named_parameters() if getattr(p, "_adm_pack", None) is not None]
+    assert len(packed) > 10 and step.engine.affine_pack is not None
+    assert not net_b.state_dict()[packed[0]].is_contiguous()  # channels-last storage behind the reference shape
+    loss_b = step.micro_step(x, t, noise, augment_labels=aug)
+    assert abs(loss_a.item() - loss_b.item()) / abs(loss_a.item()) < 1e-5
+    for n, p in net_b.named_parameters():
+        a, b = ga[n].flatten().double(), p.grad.flatten().double()
+        if a.norm().item() < 1e-6:  # mathematically zero gradients (softmax shift invariance of k_conv.bias): noise
+            assert b.norm().item() < 1e-6, n
+            continue
+        cos = torch.dot(a, b) / (a.norm() * b.norm() + 1e-30)
+        assert cos.item() > 0.9999 and abs(a.norm().item() / (b.norm().item() + 1e-30) - 1) < 1e-2, n
+    step.optimizer_step()
+    torch.cuda.synchronize()
+    assert torch.equal(step.arena.shadow, step.arena.flat.bfloat16())
+    # state_dict round trip through the reference layout
+    sd = {k: v.clone() for k, v in net_b.state_dict().items()}
+    net_c = CU_build(TINY, seed=3)
+    net_c.load_state_dict(sd)
+    for k, v in net_c.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    # out-of-band writes are picked up: load into the arena-resident model, shadow follows via the version check
+    net_b.load_state_dict(CU_build(TINY, seed=3).state_dict())
+    with torch.no_grad():
+        l1, _ = dpm_b.p_losses(x, t, noise=noise, augment_labels=aug)
+        l2, _ = DDPM(model=CU_build(TINY, seed=3), cfg=cfg, **cfg).cuda().p_losses(x, t, noise=noise, augment_labels=aug)
+    assert abs(l1.item() - l2.item()) / abs(l2.item()) < 1e-4

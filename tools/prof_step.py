@@ -1,0 +1,52 @@
+"""Kernel timeline of graph-replayed training steps (or sampler forwards) through torch.profiler / CUPTI: per kernel
+name count, total and average duration, plus GPU busy time against the wall time of the replay (idle = launch gaps).
+Unlike ncu's launch list this is in-context (warm L2, back-to-back).  Usage: python tools/prof_step.py [train|sample] [B]"""
+import collections
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+import bench
+from adm_b200.train import TrainStep
+
+mode = sys.argv[1] if len(sys.argv) > 1 else "train"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+dev = torch.device("cuda", 0)
+dpm = bench.build_model(dev)
+dpm.train()
+step = TrainStep(dpm)
+x = 2 * torch.rand(B, 3, 32, 32, device=dev) - 1
+REPS = 3
+if mode == "train":
+    step.capture(x)
+    for _ in range(3):
+        step.replay(x)
+    run = lambda: step.replay(x)
+else:
+    dpm.eval()
+    dpm.sampling_timesteps = 2
+    dpm.sample(batch_size=B)
+    run = lambda: dpm.sample(batch_size=B)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    e0.record()
+    for _ in range(REPS):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+wall = e0.elapsed_time(e1) / REPS
+tot = collections.defaultdict(lambda: [0, 0.0])
+for ev in prof.events():
+    if ev.device_type == torch.autograd.DeviceType.CUDA:
+        name = ev.name.split("(")[0]
+        tot[name][0] += 1
+        tot[name][1] += ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total
+busy = sum(v[1] for v in tot.values()) / 1000.0 / REPS
+print(f"{mode} B={B}: wall {wall:.2f} ms per run (under the profiler), kernels busy {busy:.2f} ms, "
+      f"{sum(v[0] for v in tot.values()) // REPS} kernels per run")
+for name, (n, us) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:40]:
+    print(f"{us / 1000 / REPS:8.3f} ms {100 * us / 1000 / REPS / wall:5.1f}%  n={n // REPS:5d}  avg={us / n:8.1f} us  {name[:100]}")
