@@ -72,6 +72,11 @@ SIGNATURES = {
     "adm_sq_norm": (c_i, [c_p, c_ll, c_p, c_p]),
     "adm_adamw": (c_i, [c_p, c_p, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_p, c_p, c_p, c_p]),
     "adm_set_seed_counter": (c_i, [c_p]),
+    "adm_ws_pack": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p]),
+    "adm_ws_pack_bwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
+    "adm_linattn_workspace": (c_i, [c_i, c_i, c_i, C.POINTER(c_ll)]),
+    "adm_linattn_fwd": (c_i, [c_p, c_ll, c_i, c_i, c_i, c_i, c_f, c_p, c_ll, c_p, c_p, c_p, c_p]),
+    "adm_linattn_bwd": (c_i, [c_p, c_ll, c_i, c_i, c_i, c_i, c_f, c_p, c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_p]),
 }
 
 

@@ -1,0 +1,442 @@
+// Kernels specific to the conditional two-decoder UNet (reference unet/cond_unet.py):
+//   K11 ws_pack / ws_pack_bwd : weight standardisation of WeightStandardizedConv2d (:345-358) fused with the bf16
+//                               [Cout][tap][Cin] re-pack the GEMM engine consumes, and its backward fused with the
+//                               un-pack of the packed weight gradient.
+//   K12 linattn_*             : LinearAttention (:503-531) without materialising the two softmaxes:
+//         pass A  (reads k, v) per-(b, head) online softmax over pixels + context accumulation  -> partials
+//         combine              partials -> ctx[d][e] = sum_n softmax_n(k)[d,n] v[e,n] / N, and (max, Z) per k channel
+//         pass C  (reads q)    out[e,n] = sum_d ctx[d][e] * softmax_d(q)[d,n] * scale
+//       backward: pass B1 (reads q, dout) -> dq and dctx partials; combine; pass B2 (reads k, v) -> dk, dv.
+// Channel order of qkv is (which, head, d) exactly as `to_qkv(x).chunk(3, dim=1)` + 'b (h c) x y' produces, head dim 32.
+#include "adm_internal.h"
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace adm {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float block_sum(float v, float* red) {  // red: >= 32 floats of smem
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    if (w == 0) {
+        t = warp_sum(t);
+        if (l == 0) red[0] = t;
+    }
+    __syncthreads();
+    return red[0];
+}
+
+// ------------------------------------------------------------------------------------------------ K11 forward
+// One block per output channel.  w fp32 [cout][cin][k][k]; wpk bf16 [cout][taps][kpad] (channels >= cin zero);
+// stats fp32 [cout][2] = (mean, rstd) with var = mean((w - mean)^2) (unbiased=False) and rstd = rsqrt(var + eps).
+__global__ void __launch_bounds__(256) ws_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk,
+                                                      float* __restrict__ stats, int cin, int taps, int kpad,
+                                                      float eps) {
+    __shared__ float red[32];
+    const int o = blockIdx.x;
+    const int K = cin * taps;
+    const float* wr = w + 1LL * o * K;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) s += wr[i];
+    const float mean = block_sum(s, red) / K;
+    float q = 0.f;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        const float d = wr[i] - mean;
+        q += d * d;
+    }
+    const float var = block_sum(q, red) / K;
+    const float rstd = rsqrtf(var + eps);
+    if (threadIdx.x == 0) {
+        stats[2 * o] = mean;
+        stats[2 * o + 1] = rstd;
+    }
+    __nv_bfloat16* out = wpk + 1LL * o * taps * kpad;
+    for (int i = threadIdx.x; i < taps * kpad; i += blockDim.x) {
+        const int t = i / kpad, c = i - t * kpad;
+        out[i] = __float2bfloat16(c < cin ? (wr[c * taps + t] - mean) * rstd : 0.f);
+    }
+}
+
+// Backward: g = d(loss)/d(w_hat) packed fp32 [cout][taps][kpad];  dw[o][c][t] (+)= rstd * (g - mean(g) - w_hat * mean(g * w_hat)).
+__global__ void __launch_bounds__(256) ws_pack_bwd_kernel(const float* __restrict__ g, const float* __restrict__ w,
+                                                          const float* __restrict__ stats, float* __restrict__ dw,
+                                                          int cin, int taps, int kpad, int accumulate) {
+    __shared__ float red[32];
+    const int o = blockIdx.x;
+    const int K = cin * taps;
+    const float* wr = w + 1LL * o * K;
+    const float* gr = g + 1LL * o * taps * kpad;
+    const float mean = stats[2 * o], rstd = stats[2 * o + 1];
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        const int c = i / taps, t = i - c * taps;
+        const float gi = gr[t * kpad + c];
+        s1 += gi;
+        s2 += gi * (wr[i] - mean) * rstd;
+    }
+    const float m1 = block_sum(s1, red) / K;
+    const float m2 = block_sum(s2, red) / K;
+    float* dr = dw + 1LL * o * K;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        const int c = i / taps, t = i - c * taps;
+        const float wh = (wr[i] - mean) * rstd;
+        const float v = rstd * (gr[t * kpad + c] - m1 - wh * m2);
+        dr[i] = accumulate ? dr[i] + v : v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K12 LinearAttention
+constexpr int LA_D = 32;          // head dim (reference default dim_head = 32)
+constexpr int LA_WARPS = 8;       // warps per block in the streaming passes
+
+__device__ __forceinline__ float ldbf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// Pass A.  grid (chunks, B*heads), 256 threads.  Lane = k channel d; each warp strides over the chunk's pixels keeping an
+// online softmax (m, Z) for its channel and the un-normalised context row acc[e] = sum_n exp(k[d,n] - m) v[e,n].
+// part: [B*heads][chunks][32][34] = (acc[0..31], m, Z).
+__global__ void __launch_bounds__(LA_WARPS * 32) linattn_ctx_partial_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                                            long long ld, int N, int heads,
+                                                                            float* __restrict__ part) {
+    __shared__ float vsm[LA_WARPS][LA_D];
+    __shared__ float comb[LA_WARPS][LA_D][LA_D + 2];
+    const int bh = blockIdx.y, b = bh / heads, h = bh % heads;
+    const int hidden = heads * LA_D;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = (N + gridDim.x - 1) / gridDim.x;
+    const int n0 = blockIdx.x * per, n1 = min(N, n0 + per);
+    const __nv_bfloat16* kb = qkv + 1LL * b * N * ld + hidden + h * LA_D + lane;
+    const __nv_bfloat16* vb = qkv + 1LL * b * N * ld + 2 * hidden + h * LA_D + lane;
+    float m = -INFINITY, Z = 0.f, acc[LA_D];
+#pragma unroll
+    for (int e = 0; e < LA_D; ++e) acc[e] = 0.f;
+    for (int n = n0 + warp; n < n1; n += LA_WARPS) {
+        const float kd = ldbf(kb + 1LL * n * ld);
+        vsm[warp][lane] = ldbf(vb + 1LL * n * ld);
+        __syncwarp();
+        if (kd > m) {  // rescale the running sums (rare after the first few pixels)
+            const float f = __expf(m - kd);
+            Z *= f;
+#pragma unroll
+            for (int e = 0; e < LA_D; ++e) acc[e] *= f;
+            m = kd;
+        }
+        const float p = __expf(kd - m);
+        Z += p;
+#pragma unroll
+        for (int e = 0; e < LA_D; e += 4) {
+            const float4 v4 = *reinterpret_cast<const float4*>(&vsm[warp][e]);
+            acc[e] = fmaf(p, v4.x, acc[e]);
+            acc[e + 1] = fmaf(p, v4.y, acc[e + 1]);
+            acc[e + 2] = fmaf(p, v4.z, acc[e + 2]);
+            acc[e + 3] = fmaf(p, v4.w, acc[e + 3]);
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int e = 0; e < LA_D; ++e) comb[warp][lane][e] = acc[e];
+    comb[warp][lane][LA_D] = m;
+    comb[warp][lane][LA_D + 1] = Z;
+    __syncthreads();
+    if (warp == 0) {
+        float M = -INFINITY;
+        for (int w = 0; w < LA_WARPS; ++w) M = fmaxf(M, comb[w][lane][LA_D]);
+        float Zt = 0.f, out[LA_D];
+#pragma unroll
+        for (int e = 0; e < LA_D; ++e) out[e] = 0.f;
+        for (int w = 0; w < LA_WARPS; ++w) {
+            const float mw = comb[w][lane][LA_D];
+            const float f = mw == -INFINITY ? 0.f : __expf(mw - M);
+            Zt += f * comb[w][lane][LA_D + 1];
+#pragma unroll
+            for (int e = 0; e < LA_D; ++e) out[e] = fmaf(f, comb[w][lane][e], out[e]);
+        }
+        float* dst = part + ((1LL * bh * gridDim.x + blockIdx.x) * LA_D + lane) * (LA_D + 2);
+#pragma unroll
+        for (int e = 0; e < LA_D; ++e) dst[e] = out[e];
+        dst[LA_D] = M;
+        dst[LA_D + 1] = Zt;
+    }
+}
+
+// Combine.  grid (B*heads), 32 threads (lane = d).  ctx [B*heads][32][32] (d-major), kstat [B*heads][32][2] = (max, Z).
+__global__ void linattn_ctx_combine_kernel(const float* __restrict__ part, int chunks, int N, float* __restrict__ ctx,
+                                           float* __restrict__ kstat) {
+    const int bh = blockIdx.x, lane = threadIdx.x;
+    float M = -INFINITY;
+    for (int c = 0; c < chunks; ++c) M = fmaxf(M, part[((1LL * bh * chunks + c) * LA_D + lane) * (LA_D + 2) + LA_D]);
+    float Z = 0.f, out[LA_D];
+#pragma unroll
+    for (int e = 0; e < LA_D; ++e) out[e] = 0.f;
+    for (int c = 0; c < chunks; ++c) {
+        const float* src = part + ((1LL * bh * chunks + c) * LA_D + lane) * (LA_D + 2);
+        const float mw = src[LA_D];
+        const float f = mw == -INFINITY ? 0.f : __expf(mw - M);
+        Z += f * src[LA_D + 1];
+#pragma unroll
+        for (int e = 0; e < LA_D; ++e) out[e] = fmaf(f, src[e], out[e]);
+    }
+    const float inv = 1.f / (Z * static_cast<float>(N));
+#pragma unroll
+    for (int e = 0; e < LA_D; ++e) ctx[(1LL * bh * LA_D + lane) * LA_D + e] = out[e] * inv;
+    kstat[(1LL * bh * LA_D + lane) * 2] = M;
+    kstat[(1LL * bh * LA_D + lane) * 2 + 1] = Z;
+}
+
+// Pass C.  grid (pixel blocks, B), blockDim = heads*32: warp = head, lane = e (and = d while computing softmax_d(q)).
+__global__ void linattn_apply_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int N, int heads,
+                                     const float* __restrict__ ctx, float scale, __nv_bfloat16* __restrict__ out,
+                                     long long ldo, int pix_per_block) {
+    extern __shared__ float qsm[];  // [heads][32]
+    const int b = blockIdx.y, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float col[LA_D];  // ctx[d][e = lane]
+    const float* cb = ctx + (1LL * (b * heads + h) * LA_D) * LA_D;
+#pragma unroll
+    for (int d = 0; d < LA_D; ++d) col[d] = cb[d * LA_D + lane];
+    const int n0 = blockIdx.x * pix_per_block, n1 = min(N, n0 + pix_per_block);
+    const __nv_bfloat16* qb = qkv + 1LL * b * N * ld + h * LA_D + lane;
+    __nv_bfloat16* ob = out + 1LL * b * N * ldo + h * LA_D + lane;
+    float* qs = qsm + h * LA_D;
+    for (int n = n0; n < n1; ++n) {
+        const float q = ldbf(qb + 1LL * n * ld);
+        const float mx = warp_max(q);
+        const float p = __expf(q - mx);
+        const float s = warp_sum(p);
+        qs[lane] = p * (scale / s);
+        __syncwarp();
+        float o = 0.f;
+#pragma unroll
+        for (int d = 0; d < LA_D; d += 4) {
+            const float4 q4 = *reinterpret_cast<const float4*>(&qs[d]);
+            o = fmaf(col[d], q4.x, o);
+            o = fmaf(col[d + 1], q4.y, o);
+            o = fmaf(col[d + 2], q4.z, o);
+            o = fmaf(col[d + 3], q4.w, o);
+        }
+        ob[1LL * n * ldo] = __float2bfloat16(o);
+        __syncwarp();
+    }
+}
+
+// Backward pass B1.  grid (chunks, B), blockDim = heads*32: warp = head, lane = d.  Reads q and dout; writes dq and the
+// partial dctx[d][e] = sum_n softmax_d(q)[d,n]*scale * dout[e,n] of this chunk: dpart [B*heads][chunks][32][32].
+__global__ void linattn_bwd_q_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int N, int heads,
+                                     const float* __restrict__ ctx, float scale, const __nv_bfloat16* __restrict__ dout,
+                                     long long ldd, __nv_bfloat16* __restrict__ dqkv, long long ldg,
+                                     float* __restrict__ dpart) {
+    extern __shared__ float dsm[];  // [heads][32] staged dout
+    const int b = blockIdx.y, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float row[LA_D], acc[LA_D];  // ctx[d = lane][e], dctx partial row
+    const float* cb = ctx + (1LL * (b * heads + h) * LA_D + lane) * LA_D;
+#pragma unroll
+    for (int e = 0; e < LA_D; ++e) { row[e] = cb[e]; acc[e] = 0.f; }
+    const int per = (N + gridDim.x - 1) / gridDim.x;
+    const int n0 = blockIdx.x * per, n1 = min(N, n0 + per);
+    const __nv_bfloat16* qb = qkv + 1LL * b * N * ld + h * LA_D + lane;
+    const __nv_bfloat16* db = dout + 1LL * b * N * ldd + h * LA_D + lane;
+    __nv_bfloat16* gq = dqkv + 1LL * b * N * ldg + h * LA_D + lane;
+    float* ds = dsm + h * LA_D;
+    for (int n = n0; n < n1; ++n) {
+        const float q = ldbf(qb + 1LL * n * ld);
+        ds[lane] = ldbf(db + 1LL * n * ldd);
+        const float mx = warp_max(q);
+        const float p = __expf(q - mx);
+        const float s = p / warp_sum(p);  // softmax_d(q)[d]
+        __syncwarp();
+        float dqh = 0.f;  // d(loss)/d(q_hat[d]) = sum_e ctx[d][e] dout[e]
+        const float qh = s * scale;
+#pragma unroll
+        for (int e = 0; e < LA_D; e += 4) {
+            const float4 d4 = *reinterpret_cast<const float4*>(&ds[e]);
+            dqh = fmaf(row[e], d4.x, dqh);
+            dqh = fmaf(row[e + 1], d4.y, dqh);
+            dqh = fmaf(row[e + 2], d4.z, dqh);
+            dqh = fmaf(row[e + 3], d4.w, dqh);
+            acc[e] = fmaf(qh, d4.x, acc[e]);
+            acc[e + 1] = fmaf(qh, d4.y, acc[e + 1]);
+            acc[e + 2] = fmaf(qh, d4.z, acc[e + 2]);
+            acc[e + 3] = fmaf(qh, d4.w, acc[e + 3]);
+        }
+        const float dsv = scale * dqh;  // gradient w.r.t. the softmax output s
+        const float dot = warp_sum(dsv * s);
+        gq[1LL * n * ldg] = __float2bfloat16(s * (dsv - dot));
+        __syncwarp();
+    }
+    float* dst = dpart + ((1LL * (b * heads + h) * gridDim.x + blockIdx.x) * LA_D + lane) * LA_D;
+#pragma unroll
+    for (int e = 0; e < LA_D; ++e) dst[e] = acc[e];
+}
+
+// Combine for backward.  grid (B*heads), 32 threads (lane = d): dctx [B*heads][32][32]; r[d] = sum_e dctx[d][e] ctx[d][e].
+__global__ void linattn_dctx_combine_kernel(const float* __restrict__ dpart, int chunks, const float* __restrict__ ctx,
+                                            float* __restrict__ dctx, float* __restrict__ r) {
+    const int bh = blockIdx.x, lane = threadIdx.x;
+    float out[LA_D];
+#pragma unroll
+    for (int e = 0; e < LA_D; ++e) out[e] = 0.f;
+    for (int c = 0; c < chunks; ++c) {
+        const float* src = dpart + ((1LL * bh * chunks + c) * LA_D + lane) * LA_D;
+#pragma unroll
+        for (int e = 0; e < LA_D; ++e) out[e] += src[e];
+    }
+    float rr = 0.f;
+#pragma unroll
+    for (int e = 0; e < LA_D; ++e) {
+        dctx[(1LL * bh * LA_D + lane) * LA_D + e] = out[e];
+        rr = fmaf(out[e], ctx[(1LL * bh * LA_D + lane) * LA_D + e], rr);
+    }
+    r[1LL * bh * LA_D + lane] = rr;
+}
+
+// Backward pass B2.  grid (pixel blocks, B), blockDim = heads*32: warp = head, lane = d for dk and = e for dv.
+//   k_hat[d] = exp(k[d] - max_d) / Z_d;  dv[e] = (1/N) sum_d k_hat[d] dctx[d][e];
+//   dk[d] = k_hat[d] * ((1/N) sum_e dctx[d][e] v[e] - r[d]).
+__global__ void linattn_bwd_kv_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int N, int heads,
+                                      const float* __restrict__ kstat, const float* __restrict__ dctx,
+                                      const float* __restrict__ r, __nv_bfloat16* __restrict__ dqkv, long long ldg,
+                                      int pix_per_block) {
+    extern __shared__ float sm2[];  // [heads][2][32]: k_hat and v staged per warp
+    const int b = blockIdx.y, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int hidden = heads * LA_D;
+    const int bh = b * heads + h;
+    float row[LA_D], col[LA_D];  // dctx[lane][e], dctx[d][lane]
+#pragma unroll
+    for (int i = 0; i < LA_D; ++i) {
+        row[i] = dctx[(1LL * bh * LA_D + lane) * LA_D + i];
+        col[i] = dctx[(1LL * bh * LA_D + i) * LA_D + lane];
+    }
+    const float mx = kstat[(1LL * bh * LA_D + lane) * 2], invZ = 1.f / kstat[(1LL * bh * LA_D + lane) * 2 + 1];
+    const float rd = r[1LL * bh * LA_D + lane];
+    const float invN = 1.f / static_cast<float>(N);
+    const int n0 = blockIdx.x * pix_per_block, n1 = min(N, n0 + pix_per_block);
+    const __nv_bfloat16* kb = qkv + 1LL * b * N * ld + hidden + h * LA_D + lane;
+    const __nv_bfloat16* vb = qkv + 1LL * b * N * ld + 2 * hidden + h * LA_D + lane;
+    __nv_bfloat16* gk = dqkv + 1LL * b * N * ldg + hidden + h * LA_D + lane;
+    __nv_bfloat16* gv = dqkv + 1LL * b * N * ldg + 2 * hidden + h * LA_D + lane;
+    float* ks = sm2 + h * 2 * LA_D;
+    float* vs = ks + LA_D;
+    for (int n = n0; n < n1; ++n) {
+        const float kh = __expf(ldbf(kb + 1LL * n * ld) - mx) * invZ;
+        ks[lane] = kh;
+        vs[lane] = ldbf(vb + 1LL * n * ld);
+        __syncwarp();
+        float dv = 0.f, t = 0.f;
+#pragma unroll
+        for (int i = 0; i < LA_D; i += 4) {
+            const float4 k4 = *reinterpret_cast<const float4*>(&ks[i]);
+            const float4 v4 = *reinterpret_cast<const float4*>(&vs[i]);
+            dv = fmaf(k4.x, col[i], dv);
+            dv = fmaf(k4.y, col[i + 1], dv);
+            dv = fmaf(k4.z, col[i + 2], dv);
+            dv = fmaf(k4.w, col[i + 3], dv);
+            t = fmaf(row[i], v4.x, t);
+            t = fmaf(row[i + 1], v4.y, t);
+            t = fmaf(row[i + 2], v4.z, t);
+            t = fmaf(row[i + 3], v4.w, t);
+        }
+        gv[1LL * n * ldg] = __float2bfloat16(dv * invN);
+        gk[1LL * n * ldg] = __float2bfloat16(kh * (t * invN - rd));
+        __syncwarp();
+    }
+}
+
+}  // namespace adm
+
+using namespace adm;
+typedef __nv_bfloat16 bf16;
+
+extern "C" {
+
+int adm_ws_pack(const float* w, void* wpk, float* stats, int cout, int cin, int ksize, float eps, void* stream) {
+    if (cout <= 0 || cin <= 0 || ksize <= 0) { set_error("ws_pack: bad shape"); return ADM_ERR_SHAPE; }
+    const int kpad = (cin + 63) / 64 * 64;
+    ws_pack_kernel<<<cout, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, static_cast<bf16*>(wpk), stats, cin,
+                                                                       ksize * ksize, kpad, eps);
+    ADM_CHECK_LAUNCH("ws_pack");
+    return 0;
+}
+
+int adm_ws_pack_bwd(const float* dw_packed, const float* w, const float* stats, float* dw, int cout, int cin, int ksize,
+                    int accumulate, void* stream) {
+    if (cout <= 0 || cin <= 0 || ksize <= 0) { set_error("ws_pack_bwd: bad shape"); return ADM_ERR_SHAPE; }
+    const int kpad = (cin + 63) / 64 * 64;
+    ws_pack_bwd_kernel<<<cout, 256, 0, static_cast<cudaStream_t>(stream)>>>(dw_packed, w, stats, dw, cin, ksize * ksize,
+                                                                           kpad, accumulate);
+    ADM_CHECK_LAUNCH("ws_pack_bwd");
+    return 0;
+}
+
+static int la_chunks(int n_pix, int batch_heads) {
+    long long want = (4LL * num_sms() + batch_heads - 1) / batch_heads;
+    long long max_chunks = (n_pix + 8 * LA_WARPS - 1) / (8 * LA_WARPS);
+    if (want > max_chunks) want = max_chunks;
+    if (want > 64) want = 64;
+    if (want < 1) want = 1;
+    return static_cast<int>(want);
+}
+
+int adm_linattn_workspace(int batch, int heads, int n_pix, long long* floats) {
+    const int chunks = la_chunks(n_pix, batch * heads);
+    *floats = 1LL * batch * heads * chunks * LA_D * (LA_D + 2);
+    return chunks;
+}
+
+int adm_linattn_fwd(const void* qkv, long long ld, int batch, int n_pix, int heads, int dim_head, float scale, void* out,
+                    long long ldo, float* ctx, float* kstat, float* work, void* stream) {
+    if (dim_head != LA_D) { set_error("linattn: dim_head must be 32 (got %d)", dim_head); return ADM_ERR_SHAPE; }
+    if (heads < 1 || heads > 32 || batch <= 0 || n_pix <= 0) { set_error("linattn: bad shape"); return ADM_ERR_SHAPE; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int chunks = la_chunks(n_pix, batch * heads);
+    linattn_ctx_partial_kernel<<<dim3(chunks, batch * heads), LA_WARPS * 32, 0, s>>>(static_cast<const bf16*>(qkv), ld,
+                                                                                     n_pix, heads, work);
+    ADM_CHECK_LAUNCH("linattn_ctx_partial");
+    linattn_ctx_combine_kernel<<<batch * heads, 32, 0, s>>>(work, chunks, n_pix, ctx, kstat);
+    ADM_CHECK_LAUNCH("linattn_ctx_combine");
+    if (out != nullptr) {
+        int blocks = (8 * num_sms() + batch - 1) / batch;
+        int ppb = (n_pix + blocks - 1) / blocks;
+        if (ppb < 4) ppb = 4;
+        blocks = (n_pix + ppb - 1) / ppb;
+        linattn_apply_kernel<<<dim3(blocks, batch), heads * 32, heads * LA_D * sizeof(float), s>>>(
+            static_cast<const bf16*>(qkv), ld, n_pix, heads, ctx, scale, static_cast<bf16*>(out), ldo, ppb);
+        ADM_CHECK_LAUNCH("linattn_apply");
+    }
+    return 0;
+}
+
+int adm_linattn_bwd(const void* qkv, long long ld, int batch, int n_pix, int heads, int dim_head, float scale,
+                    const void* dout, long long ldd, const float* ctx, const float* kstat, float* dctx, float* r,
+                    float* work, void* dqkv, long long ldg, void* stream) {
+    if (dim_head != LA_D) { set_error("linattn: dim_head must be 32 (got %d)", dim_head); return ADM_ERR_SHAPE; }
+    if (heads < 1 || heads > 32 || batch <= 0 || n_pix <= 0) { set_error("linattn: bad shape"); return ADM_ERR_SHAPE; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int chunks = la_chunks(n_pix, batch * heads);
+    linattn_bwd_q_kernel<<<dim3(chunks, batch), heads * 32, heads * LA_D * sizeof(float), s>>>(
+        static_cast<const bf16*>(qkv), ld, n_pix, heads, ctx, scale, static_cast<const bf16*>(dout), ldd,
+        static_cast<bf16*>(dqkv), ldg, work);
+    ADM_CHECK_LAUNCH("linattn_bwd_q");
+    linattn_dctx_combine_kernel<<<batch * heads, 32, 0, s>>>(work, chunks, ctx, dctx, r);
+    ADM_CHECK_LAUNCH("linattn_dctx_combine");
+    int blocks = (8 * num_sms() + batch - 1) / batch;
+    int ppb = (n_pix + blocks - 1) / blocks;
+    if (ppb < 4) ppb = 4;
+    blocks = (n_pix + ppb - 1) / ppb;
+    linattn_bwd_kv_kernel<<<dim3(blocks, batch), heads * 32, heads * 2 * LA_D * sizeof(float), s>>>(
+        static_cast<const bf16*>(qkv), ld, n_pix, heads, kstat, dctx, r, static_cast<bf16*>(dqkv), ldg, ppb);
+    ADM_CHECK_LAUNCH("linattn_bwd_kv");
+    return 0;
+}
+
+}  // extern "C"

@@ -69,8 +69,15 @@ __global__ void __launch_bounds__(256) ddm_loss_kernel(const float* __restrict__
         w2 = q / (1.f - tb + eps);
     }
     const float inv_b = grad_scale / static_cast<float>(batch);
-    const float l1c = use_l1 ? 1.f / static_cast<float>(chw) : 0.f;
-    const float half = use_l1 ? 0.5f : 1.f;
+    // use_l1 flags: 1 = + w * mean|d| (image space, ddm_const.py:345-348), 2 = + w * sum|d| (latent,
+    // ddm_const_2.py:561-564), both then / 2;  4 = + rec_w * sum|x_rec - x0| with rec_w = -log(t)/2 and
+    // x_rec - x0 = -(t*d1 + sqrt(t)*d2) (ddm_const_2.py:566-568 with the sqrt(t) schedule of ddm_const.py:290-293).
+    const float l1c = (use_l1 & 1) ? 1.f / static_cast<float>(chw) : ((use_l1 & 2) ? 1.f : 0.f);
+    const float half = (use_l1 & 3) ? 0.5f : 1.f;
+    const bool vlb = (use_l1 & 4) != 0;
+    const float rec_w = vlb ? -0.5f * logf(tb) : 0.f;
+    const float sq_t = sqrtf(tb);
+    float svlb = 0.f;
     const float* cpb = cp + b * chw;
     const float* epb = ep + b * chw;
     const float* xb = x0 + b * chw;
@@ -108,6 +115,13 @@ __global__ void __launch_bounds__(256) ddm_loss_kernel(const float* __restrict__
                 const float s1 = (d1 > 0.f) - (d1 < 0.f), s2 = (d2 > 0.f) - (d2 < 0.f);
                 g1[j] = inv_b * half * w1 * (2.f * d1 + l1c * s1);
                 g2[j] = inv_b * half * w2 * (2.f * d2 + l1c * s2);
+                if (vlb) {
+                    const float u = tb * d1 + sq_t * d2;
+                    const float su = (u > 0.f) - (u < 0.f);
+                    svlb += fabsf(u);
+                    g1[j] += inv_b * rec_w * su * tb;
+                    g2[j] += inv_b * rec_w * su * sq_t;
+                }
             }
         }
         if (dcp != nullptr) {
@@ -120,15 +134,20 @@ __global__ void __launch_bounds__(256) ddm_loss_kernel(const float* __restrict__
             }
         }
     }
-    float part = half * (w1 * (sse1 + l1c * sae1) + w2 * (sse2 + l1c * sae2));
+    float pv = rec_w * svlb;
+    float part = half * (w1 * (sse1 + l1c * sae1) + w2 * (sse2 + l1c * sae2)) + pv;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    __shared__ float warp_sums[8];
-    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = part;
+    for (int o = 16; o > 0; o >>= 1) {
+        part += __shfl_xor_sync(0xffffffffu, part, o);
+        pv += __shfl_xor_sync(0xffffffffu, pv, o);
+    }
+    __shared__ float warp_sums[8], warp_sums_v[8];
+    if ((threadIdx.x & 31) == 0) { warp_sums[threadIdx.x >> 5] = part; warp_sums_v[threadIdx.x >> 5] = pv; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        float s = 0.f;
-        for (int i = 0; i < (blockDim.x >> 5); ++i) s += warp_sums[i];
+        float s = 0.f, sv = 0.f;
+        for (int i = 0; i < (blockDim.x >> 5); ++i) { s += warp_sums[i]; sv += warp_sums_v[i]; }
+        if (vlb) atomicAdd(loss + batch + b, sv);
         atomicAdd(loss + b, s);
     }
 }
@@ -308,7 +327,7 @@ int adm_ddm_loss(const float* c_pred, const float* eps_pred, const float* x0, co
     if (batch <= 0 || chw <= 0 || batch > 65535) { set_error("ddm_loss: bad batch %lld", batch); return ADM_ERR_SHAPE; }
     if ((d_c_pred == nullptr) != (d_eps_pred == nullptr)) { set_error("ddm_loss: pass both gradients or neither"); return ADM_ERR_SHAPE; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    cudaMemsetAsync(loss_per_sample, 0, sizeof(float) * batch, s);
+    cudaMemsetAsync(loss_per_sample, 0, sizeof(float) * batch * ((use_l1 & 4) ? 2 : 1), s);
     const long long items = (chw & 3) == 0 ? chw / 4 : chw;
     long long bx = (items + 255) / 256;
     const long long cap = (8LL * num_sms() + batch - 1) / batch;

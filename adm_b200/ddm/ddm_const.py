@@ -31,12 +31,14 @@ class _DDMLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, c_pred, eps_pred, x0, noise, t, eps, weighting, use_l1):
+        """use_l1: bool (image-space mean |.| term) or the kernel's flag word (see adm_ddm_loss)."""
         need = c_pred.requires_grad or eps_pred.requires_grad
-        lps, dc, de = ops.ddm_loss(c_pred.detach(), eps_pred.detach(), x0, noise, t, eps, weighting, use_l1,
-                                   need_grad=need)
+        lps, dc, de = ops.ddm_loss(c_pred.detach().float(), eps_pred.detach().float(), x0, noise, t, eps, weighting,
+                                   use_l1, need_grad=need)
         ctx.dc, ctx.de = dc, de
         ctx.mark_non_differentiable(lps)
-        return lps.sum() / x0.shape[0], lps
+        b = x0.shape[0]
+        return lps[:b].sum() / b, lps
 
     @staticmethod
     def backward(ctx, g_loss, _g_lps):
@@ -274,3 +276,145 @@ class DDPM(nn.Module):
         if unnormalize:
             img = unnormalize_to_zero_to_one(img)
         return img
+
+
+class LatentDiffusion(DDPM):
+    """Mirror of the reference's ``LatentDiffusion``: plumbing of /root/reference/ddm/ddm_const_2.py:393-436 (ctor),
+    :473-524 (scale factor, get_input, training_step), :527-588 (loss with the L1-sum and reconstruction terms),
+    :606-630 (sample); math of the sqrt(t) schedule (ddm_const.py:286,292,336-338) and the clamp-free latent sampler
+    (ddm_const.py:868-888).  The frozen first stage is any module with ``encode(x)`` (a tensor, or a posterior with
+    ``.sample()``), ``decode(z)`` and ``down_ratio`` — the reference's ``AutoencoderKL`` fits as is.
+    K1 / K2 / K3 are the same fused kernels as in image space; K2 runs with its latent flag word (L1 sum + -log(t)/2
+    reconstruction term), K3 without the clamp."""
+
+    def __init__(self, auto_encoder, scale_factor=1.0, scale_by_std=True, scale_by_softsign=False, input_keys=["image"],
+                 sample_type="naive", default_scale=False, *args, **kwargs):
+        self.scale_by_std = scale_by_std
+        self.scale_by_softsign = scale_by_softsign
+        self.default_scale = default_scale
+        ckpt_path = kwargs.pop("ckpt_path", None)
+        ignore_keys = kwargs.pop("ignore_keys", [])
+        only_model = kwargs.pop("only_model", False)
+        super().__init__(*args, **kwargs)
+        if not scale_by_std:
+            self.scale_factor = scale_factor
+        else:
+            self.register_buffer("scale_factor", torch.tensor(scale_factor))
+        if self.scale_by_softsign:
+            self.scale_by_std = False
+        assert (self.scale_by_std and self.scale_by_softsign) is False
+        self.init_first_stage(auto_encoder)
+        self.input_keys = input_keys
+        self.clip_denoised = False
+        assert sample_type in ["naive", "ddim", "dpm"]
+        if self.cfg.get("use_disloss", False):
+            raise NotImplementedError("adm_b200: use_disloss (decoder distillation term) is outside the hot path")
+        if ckpt_path is not None:
+            self.init_from_ckpt(ckpt_path, ignore_keys, only_model)
+
+    def init_first_stage(self, first_stage_model):
+        self.first_stage_model = first_stage_model.eval()
+        for p in self.first_stage_model.parameters():
+            p.requires_grad = False
+
+    def get_first_stage_encoding(self, encoder_posterior):
+        if isinstance(encoder_posterior, torch.Tensor):
+            return encoder_posterior.detach()
+        if hasattr(encoder_posterior, "sample"):
+            return encoder_posterior.sample().detach()
+        raise NotImplementedError(f"encoder_posterior of type '{type(encoder_posterior)}' not yet implemented")
+
+    @torch.no_grad()
+    def on_train_batch_start(self, batch):
+        """ddm_const_2.py:473-491: std-rescaling from the first batch unless default_scale."""
+        if self.scale_by_std and not self.scale_by_softsign and not self.default_scale:
+            assert self.scale_factor == 1., "rather not use custom rescaling and std-rescaling simultaneously"
+            x, *_ = batch.values()
+            z = self.get_first_stage_encoding(self.first_stage_model.encode(x))
+            del self.scale_factor
+            self.register_buffer("scale_factor", 1. / z.flatten().std())
+
+    @torch.no_grad()
+    def get_input(self, batch, return_first_stage_outputs=False, return_original_cond=False):
+        assert "image" in self.input_keys
+        x = batch["image"]
+        cond = batch["cond"] if "cond" in batch else None
+        z = self.get_first_stage_encoding(self.first_stage_model.encode(x))
+        out = [z, cond, x]
+        if return_first_stage_outputs:
+            out.extend([x, self.first_stage_model.decode(z)])
+        if return_original_cond:
+            out.append(cond)
+        return out
+
+    def training_step(self, batch, *args, **kwargs):
+        z, c, x, *_ = self.get_input(batch)
+        if self.scale_by_softsign:
+            z = torch.nn.functional.softsign(z)
+        elif self.scale_by_std:
+            z = self.scale_factor * z
+        return self(z, c) if c is not None else self(z)
+
+    def p_losses(self, x_start, t, *args, noise=None, **kwargs):
+        if noise is None:
+            if self.start_dist == "normal":
+                noise = torch.randn_like(x_start)
+            elif self.start_dist == "uniform":
+                noise = 2 * torch.rand_like(x_start) - 1.
+            else:
+                raise NotImplementedError(f"{self.start_dist} is not supported !")
+        x_start = x_start.contiguous().float()
+        noise = noise.contiguous().float()
+        x_noisy = ops.qsample(x_start, noise, t)
+        args = tuple(a for a in args if a is not None)
+        c_pred, noise_pred = self.model(x_noisy, t, *args, **kwargs)[:2]
+        flags = (2 if self.use_l1 else 0) | 4  # L1 as a sum over CHW (ddm_const_2.py:561-564) + reconstruction term
+        loss, lps = _DDMLossFn.apply(c_pred, noise_pred, x_start, noise, t, self._eps, bool(self.weighting_loss), flags)
+        b = x_start.shape[0]
+        n = float(x_start.numel())
+        with torch.no_grad():
+            vlb = lps[b:].sum()
+            loss_dict = {"train/loss_simple": (lps[:b].sum() - vlb) / n, "train/loss_vlb": vlb / n,
+                         "train/loss": loss.detach() / n}
+        return loss, loss_dict
+
+    @torch.no_grad()
+    def sample(self, batch_size=16, up_scale=1, cond=None, mask=None, denoise=True, x_T=None):
+        image_size, channels = self.image_size, self.channels
+        if cond is not None:
+            batch_size = cond.shape[0]
+        down_ratio = self.first_stage_model.down_ratio
+        shape = (batch_size, channels, image_size[0] // down_ratio, image_size[1] // down_ratio)
+        self.sample_type = self.cfg.get("sample_type", "deterministic")
+        if self.sample_type == "stochastic":
+            z = self.sample_fn_s(shape, unnormalize=False, cond=cond, x_T=x_T)
+        else:
+            z = self.sample_fn_latent(shape, cond=cond, x_T=x_T)
+        if self.scale_by_std:
+            z = 1. / self.scale_factor * z.detach()
+        elif self.scale_by_softsign:
+            z = (z / (1 - z.abs())).detach()
+        x_rec = self.first_stage_model.decode(z.to(torch.float32))
+        x_rec = torch.clamp(unnormalize_to_zero_to_one(x_rec), min=0., max=1.)
+        if mask is not None:
+            x_rec = mask * unnormalize_to_zero_to_one(cond) + (1 - mask) * x_rec
+        return x_rec
+
+    @torch.no_grad()
+    def sample_fn_latent(self, shape, cond=None, x_T=None):
+        """ddm_const.py:868-888: x' = x + (t'-t) * (C + eps / (sqrt(t) + sqrt(t'))) == x0 + C t' + sqrt(t') eps with
+        x0 = x - C t - sqrt(t) eps and no clamp — K3 with do_clip = 0."""
+        device = self.eps.device
+        ts = self.t_steps()
+        if x_T is None:
+            x_T = torch.randn(shape, device=device, dtype=torch.float64)
+        x = (x_T.to(device=device, dtype=torch.float64) * ts[0]).contiguous()
+        t_dev = torch.tensor(ts, device=device, dtype=torch.float64)
+        was_training = self.model.training
+        self.model.eval()
+        for i, (t_cur, t_next) in enumerate(zip(ts[:-1], ts[1:])):
+            pred = self.model(x, t_dev[i], cond) if cond is not None else self.model(x, t_dev[i])
+            c, noise = pred[:2]
+            x = ops.sampler_step(x, c.float(), noise.float(), t_cur, t_next, 1.0, False, False, 1.0)
+        self.model.train(was_training)
+        return x

@@ -56,11 +56,12 @@ def ddm_loss(c_pred, eps_pred, x0, noise, t, eps, weighting, use_l1=False, grad_
     _need_cuda(c_pred, eps_pred, x0, noise, t)
     c_pred, eps_pred, x0, noise = (a.contiguous() for a in (c_pred, eps_pred, x0, noise))
     b = x0.shape[0]
-    loss = torch.empty(b, device=x0.device, dtype=F32)
+    flags = int(use_l1) if not isinstance(use_l1, bool) else int(use_l1)  # bool -> 1 (mean |.|); ints are flag words
+    loss = torch.empty(b * (2 if flags & 4 else 1), device=x0.device, dtype=F32)
     dc = torch.empty_like(c_pred) if need_grad else None
     de = torch.empty_like(eps_pred) if need_grad else None
     check(_lib.load().adm_ddm_loss(_ptr(c_pred), _ptr(eps_pred), _ptr(x0), _ptr(noise), _ptr(t.contiguous().float()),
-                                   float(eps), int(bool(weighting)), int(bool(use_l1)), float(grad_scale), _ptr(loss),
+                                   float(eps), int(bool(weighting)), flags, float(grad_scale), _ptr(loss),
                                    _ptr(dc), _ptr(de), b, x0.numel() // b, _stream()), "ddm_loss")
     return loss, dc, de
 
@@ -440,16 +441,18 @@ def _gemm(desc_kw, a_op, b_op, what):
     check(_lib.load().adm_gemm_batched(d, _stream()), what)
 
 
-def attention_fwd(qkv, heads):
-    """qkv: [N, H, W, 3C] bf16 laid out as (q | k | v), each [heads, d].  Returns (a [N,H,W,C], p [N*heads,HW,HW])."""
+def attention_fwd(qkv, heads, scale=None):
+    """qkv: [N, H, W, 3C] bf16 laid out as (q | k | v), each [heads, d].  Returns (a [N,H,W,C], p [N*heads,HW,HW]).
+    scale defaults to 1/sqrt(d) (d = C / heads as stored, which may include zero padding of the head dim)."""
     n, h, w, c3 = qkv.shape
     c, hw = c3 // 3, h * w
     d = c // heads
+    scale = 1.0 / d ** 0.5 if scale is None else float(scale)
     assert qkv.is_contiguous()
     s = torch.empty(n * heads, hw, hw, device=qkv.device, dtype=F32)
     qk_dims, qk_str = (c3, hw, n), (c3, c3 * hw)
     _gemm(dict(m=hw, n=hw, k=d, batches=n * heads, bdiv=heads, splits=1, c=s.data_ptr(), out_mode=1, ldc=hw,
-               c_bhi=heads * hw * hw, c_blo=hw * hw, c_col_lo=0, alpha=1.0 / d ** 0.5),
+               c_bhi=heads * hw * hw, c_blo=hw * hw, c_col_lo=0, alpha=scale),
           _operand(qkv, 0, qk_dims, qk_str, c0=0, c0_lo=d, bhi=1),
           _operand(qkv, 0, qk_dims, qk_str, c0=c, c0_lo=d, bhi=1), "attn QK^T")
     p = softmax_fwd(s)
@@ -461,11 +464,12 @@ def attention_fwd(qkv, heads):
     return a, p
 
 
-def attention_bwd(da, qkv, p, heads):
+def attention_bwd(da, qkv, p, heads, scale=None):
     """Returns dqkv [N,H,W,3C] bf16."""
     n, h, w, c3 = qkv.shape
     c, hw = c3 // 3, h * w
     d = c // heads
+    scale = 1.0 / d ** 0.5 if scale is None else float(scale)
     assert da.is_contiguous() and qkv.is_contiguous()
     dqkv = torch.empty_like(qkv)
     qk_dims, qk_str = (c3, hw, n), (c3, c3 * hw)
@@ -484,7 +488,7 @@ def attention_bwd(da, qkv, p, heads):
                c_bhi=heads * hw * hw, c_blo=hw * hw, c_col_lo=0, alpha=1.0),
           _operand(da, 0, a_dims, a_str, c0=0, c0_lo=d, bhi=1),
           _operand(qkv, 0, qk_dims, qk_str, c0=2 * c, c0_lo=d, bhi=1), "attn dP")
-    ds = softmax_bwd(p, dp, 1.0 / d ** 0.5)
+    ds = softmax_bwd(p, dp, scale)
     # dQ[q, d] = sum_k dS[q, k] K[k, d]
     _gemm(dict(m=hw, n=d, k=hw, batches=nb, bdiv=heads, splits=1, c=dqkv.data_ptr(), out_mode=0, ldc=c3,
                c_bhi=hw * c3, c_blo=0, c_col_lo=d, alpha=1.0),
@@ -534,3 +538,63 @@ def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
 def set_seed_counter(t):
     """t: CUDA int64 tensor with one element (or None)."""
     check(_lib.load().adm_set_seed_counter(_ptr(t)), "set_seed_counter")
+
+
+# ------------------------------------------------------------------------------------------------ conditional UNet ops
+def ws_pack(w, eps=1e-5):
+    """K11: weight standardisation + bf16 re-pack.  w fp32 [cout, cin, k, k] -> (wpk bf16 [cout, k*k, pad64(cin)], stats)."""
+    _need_cuda(w)
+    cout, cin, k, _ = w.shape
+    w = w.contiguous()
+    wpk = torch.empty(cout, k * k, pad64(cin), device=w.device, dtype=BF16)
+    stats = torch.empty(cout, 2, device=w.device, dtype=F32)
+    check(_lib.load().adm_ws_pack(_ptr(w), _ptr(wpk), _ptr(stats), cout, cin, k, float(eps), _stream()), "ws_pack")
+    return wpk, stats
+
+
+def ws_pack_bwd(dw_packed, w, stats, out=None, accumulate=False):
+    """dw (reference layout) from the packed gradient w.r.t. the standardised weights."""
+    cout, cin, k, _ = w.shape
+    if out is None:
+        out = torch.empty_like(w, memory_format=torch.contiguous_format)
+        accumulate = False
+    check(_lib.load().adm_ws_pack_bwd(_ptr(dw_packed), _ptr(w.contiguous()), _ptr(stats), _ptr(out), cout, cin, k,
+                                      int(accumulate), _stream()), "ws_pack_bwd")
+    return out
+
+
+def _linattn_work(b, heads, n, device):
+    import ctypes
+    fl = ctypes.c_longlong(0)
+    _lib.load().adm_linattn_workspace(b, heads, n, ctypes.byref(fl))
+    return torch.empty(fl.value, device=device, dtype=F32)
+
+
+def linattn_fwd(qkv, heads, scale):
+    """K12.  qkv [B, H, W, 3*heads*32] bf16 (q | k | v).  Returns (out [B, H, W, heads*32], ctx, kstat)."""
+    _need_cuda(qkv)
+    b, h, w, c3 = qkv.shape
+    hidden = c3 // 3
+    assert hidden == heads * 32 and qkv.dtype == BF16 and qkv.stride(3) == 1
+    n = h * w
+    out = torch.empty(b, h, w, hidden, device=qkv.device, dtype=BF16)
+    ctx = torch.empty(b * heads, 32, 32, device=qkv.device, dtype=F32)
+    kstat = torch.empty(b * heads, 32, 2, device=qkv.device, dtype=F32)
+    work = _linattn_work(b, heads, n, qkv.device)
+    check(_lib.load().adm_linattn_fwd(_ptr(qkv), qkv.stride(2), b, n, heads, 32, float(scale), _ptr(out), out.stride(2),
+                                      _ptr(ctx), _ptr(kstat), _ptr(work), _stream()), "linattn_fwd")
+    return out, ctx, kstat
+
+
+def linattn_bwd(dout, qkv, ctx, kstat, heads, scale):
+    b, h, w, c3 = qkv.shape
+    n = h * w
+    assert dout.dtype == BF16 and dout.stride(3) == 1
+    dqkv = torch.empty_like(qkv)
+    dctx = torch.empty_like(ctx)
+    r = torch.empty(b * heads, 32, device=qkv.device, dtype=F32)
+    work = _linattn_work(b, heads, n, qkv.device)
+    check(_lib.load().adm_linattn_bwd(_ptr(qkv), qkv.stride(2), b, n, heads, 32, float(scale), _ptr(dout),
+                                      dout.stride(2), _ptr(ctx), _ptr(kstat), _ptr(dctx), _ptr(r), _ptr(work),
+                                      _ptr(dqkv), dqkv.stride(2), _stream()), "linattn_bwd")
+    return dqkv

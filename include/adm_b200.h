@@ -40,7 +40,10 @@ int adm_qsample(const float* x0, const float* noise, const float* t, float* x_t,
  *     (MSE_Loss reduction='sum' over CHW): loss_b = w1_b*SSE(C_pred, -x0) + w2_b*SSE(eps_pred, noise)
  *     [+ use_l1: w*mean|.| terms and /2, ddm_const.py:345-348],  w1 = (t^2-t+1)/t, w2 = (t^2-t+1)/(1-t+eps) when
  *     weighting != 0 else 1.  Writes per-sample loss [B] (caller sums / B) and, if non-null, the gradients of
- *     (sum_b loss_b)/B * grad_scale w.r.t. C_pred and eps_pred.                                           */
+ *     (sum_b loss_b)/B * grad_scale w.r.t. C_pred and eps_pred.
+ *     use_l1 is a flag word: 1 = + w*mean|.| then /2 (image space, ddm_const.py:345-348); 2 = + w*sum|.| then /2
+ *     (latent, ddm_const_2.py:561-564); 4 = + the latent reconstruction term -log(t)/2 * sum|x_rec - x0|
+ *     (ddm_const_2.py:566-568), in which case loss_per_sample has 2*B entries: [total | that term].          */
 int adm_ddm_loss(const float* c_pred, const float* eps_pred, const float* x0, const float* noise, const float* t,
                  float eps, int weighting, int use_l1, float grad_scale, float* loss_per_sample, float* d_c_pred,
                  float* d_eps_pred, long long batch, long long chw, void* stream);
@@ -190,6 +193,26 @@ int adm_spatial_att_fwd(const void* h, long long ldh, const void* res, long long
 int adm_spatial_att_bwd(const void* dy, long long ldy, const void* h, long long ldh, const float* w_map,
                         const float* scalars, const float* att_save, const float* o_save, int n, int hw, int c,
                         void* dh, long long lddh, float* dw_map, float* dscalars, void* stream);
+
+/* ---------------------------------------------------------------- conditional UNet (unet/cond_unet.py)
+ * K11  WeightStandardizedConv2d (:345-358): w_hat = (w - mean_o) * rsqrt(var_o + eps) per output channel (var unbiased =
+ *      False), written straight in the GEMM engine's packed order bf16 [cout][k*k][pad64(cin)]; stats [cout][2] =
+ *      (mean, rstd) are kept for the backward, which folds the un-pack of the packed weight gradient:
+ *      dw = rstd * (g - mean(g) - w_hat * mean(g * w_hat)), g = d loss / d w_hat.                              */
+int adm_ws_pack(const float* w, void* wpk, float* stats, int cout, int cin, int ksize, float eps, void* stream);
+int adm_ws_pack_bwd(const float* dw_packed, const float* w, const float* stats, float* dw, int cout, int cin, int ksize,
+                    int accumulate, void* stream);
+/* K12  LinearAttention (:503-531) on qkv [batch][n_pix][ld] bf16 with channel order (q | k | v) x head x 32:
+ *      q = softmax_d(q) * scale, k = softmax_n(k), v = v / n_pix, ctx[d][e] = sum_n k v, out[e][n] = sum_d ctx q.
+ *      Neither softmax is materialised.  ctx fp32 [batch*heads][32][32] and kstat fp32 [batch*heads][32][2] are saved
+ *      for the backward; work: fp32 scratch of adm_linattn_workspace() floats; dctx / r: scratch [batch*heads][32][32]
+ *      and [batch*heads][32].  out [batch][n_pix][ldo] holds heads*32 channels; dqkv has the layout of qkv.       */
+int adm_linattn_workspace(int batch, int heads, int n_pix, long long* floats);
+int adm_linattn_fwd(const void* qkv, long long ld, int batch, int n_pix, int heads, int dim_head, float scale, void* out,
+                    long long ldo, float* ctx, float* kstat, float* work, void* stream);
+int adm_linattn_bwd(const void* qkv, long long ld, int batch, int n_pix, int heads, int dim_head, float scale,
+                    const void* dout, long long ldd, const float* ctx, const float* kstat, float* dctx, float* r,
+                    float* work, void* dqkv, long long ldg, void* stream);
 
 /* ---------------------------------------------------------------- optimizer over the flat parameter arena
  * train_uncond_dpm.py:292 (clip_grad_norm_ 1.0) + :179-180,296 (AdamW).  out += sum g^2.                      */

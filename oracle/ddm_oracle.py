@@ -374,3 +374,41 @@ def sample_fn_s(model_fn: Callable, x_T, z_list, n_steps, sigma_min=1e-2, sigma_
     if unnormalize:
         img = (img + 1) * 0.5
     return img
+
+
+# ----------------------------------------------------------------------------------------------- latent variant
+def p_losses_latent(model_fn: Callable, x_start, t, noise, eps=1e-4, weighting=True, use_l1=True, **model_kwargs):
+    """LatentDiffusion.p_losses: structure of ddm_const_2.py:527-588 (L1 as a SUM over CHW :561-564, reconstruction term
+    -log(t)/2 * sum|x_rec - x0| :566-568, use_disloss off) with the sqrt(t) schedule's formulas: q_sample
+    ddm_const.py:284-287, x_rec = pred_x0_from_xt ddm_const.py:290-293, weights ddm_const.py:336-338."""
+    b = x_start.shape[0]
+    x_noisy = q_sample(x_start, noise, t)
+    c_pred, noise_pred = model_fn(x_noisy, t, **model_kwargs)[:2]
+    tt = t.reshape(b, 1, 1, 1)
+    x_rec = x_noisy - c_pred * tt - torch.sqrt(tt) * noise_pred
+    c = -x_start
+    if weighting:
+        w1 = (t ** 2 - t + 1) / t
+        w2 = (t ** 2 - t + 1) / (1 - t + eps)
+    else:
+        w1 = w2 = torch.ones_like(t)
+    ls = w1 * ((c_pred - c) ** 2).sum([1, 2, 3]) + w2 * ((noise_pred - noise) ** 2).sum([1, 2, 3])
+    if use_l1:
+        ls = ls + w1 * (c_pred - c).abs().sum([1, 2, 3]) + w2 * (noise_pred - noise).abs().sum([1, 2, 3])
+        ls = ls / 2
+    vlb = (x_rec - x_start).abs().sum([1, 2, 3]) * (-torch.log(t) / 2)
+    loss = ls.sum() / b + vlb.sum() / b
+    n = float(x_start.numel())
+    return loss, {"train/loss_simple": ls.detach().sum() / n, "train/loss_vlb": vlb.detach().sum() / n,
+                  "train/loss": loss.detach() / n}
+
+
+def sample_fn_latent(model_fn: Callable, x_T, n_steps, sigma_min=1e-2, sigma_max=1.0):
+    """ddm_const.py:868-888 (fp64 state, no clamp)."""
+    ts = t_steps_deterministic(n_steps, sigma_min, sigma_max).to(x_T.device)
+    x = x_T.to(torch.float64) * ts[0]
+    for t_cur, t_next in zip(ts[:-1], ts[1:]):
+        c, noise = model_fn(x, t_cur)[:2]
+        c, noise = c.to(torch.float64), noise.to(torch.float64)
+        x = x + (t_next - t_cur) * (c + noise / (t_cur.sqrt() + t_next.sqrt()))
+    return x

@@ -207,3 +207,19 @@ def test_arena_fast_path_matches_plain_backward():
         l1, _ = dpm_b.p_losses(x, t, noise=noise, augment_labels=aug)
         l2, _ = DDPM(model=CU_build(TINY, seed=3), cfg=cfg, **cfg).cuda().p_losses(x, t, noise=noise, augment_labels=aug)
     assert abs(l1.item() - l2.item()) / abs(l2.item()) < 1e-4
+
+
+# ---------------------------------------------------------------- conditional UNet / LatentDiffusion
+from tests.gpu_checks import check_cond as CC  # noqa: E402
+
+
+@pytest.mark.parametrize("case", ["ws_pack", "linear_attention", "attention_padded_heads", "resnet_block"])
+def test_cond_unet_kernels(case):
+    """K11 weight-standardise+pack, K12 fused LinearAttention, padded-head Attention, ResnetBlock fwd/bwd vs torch."""
+    assert CC.CASES[case]()
+
+
+def test_cond_unet_and_latent_diffusion_vs_reference_golden():
+    """Whole cond Unet (outputs, latent DDM loss, per-parameter gradients, 3-step latent sampler) against vectors recorded
+    from the unmodified reference unet.cond_unet.Unet (tests/golden/make_golden_cond.py)."""
+    assert CC.CASES["cond_unet_golden"]()

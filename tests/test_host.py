@@ -106,3 +106,52 @@ def test_lr_schedule():
     assert lr_lambda(0, 800000, 1e-4, 5e-6) == pytest.approx(1 / 5000)
     assert lr_lambda(4999, 800000, 1e-4, 5e-6) == pytest.approx(1.0)
     assert lr_lambda(800000, 800000, 1e-4, 5e-6) == pytest.approx(0.05)
+
+
+def test_cond_unet_state_dict_layout_matches_reference(golden_dir):
+    """1158 keys; every non-Swin key and shape equals the layout recorded from the reference (the Swin part was checked
+    by the strict load_state_dict into the reference module when the golden file was generated)."""
+    import json
+    import os
+    from tests.golden.make_golden_cond import CFG
+    from adm_b200.unet.cond_unet import Unet
+    g = json.load(open(os.path.join(golden_dir, "cond_unet_small.json")))
+    sd = Unet(**CFG).state_dict()
+    assert len(sd) == g["n_keys"] == 1158
+    ours = {k: list(v.shape) for k, v in sd.items() if not k.startswith("init_conv_mask.")}
+    assert ours == g["keys"]
+    assert sum(k.startswith("init_conv_mask.") for k in sd) == g["n_swin_keys"]
+
+
+def test_latent_diffusion_constructor_and_errors():
+    import pytest
+    import torch
+    from adm_b200.ddm.ddm_const import LatentDiffusion
+
+    class AE(torch.nn.Module):
+        down_ratio = 4
+
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.ones(1))
+
+        def encode(self, x):
+            return x[..., ::4, ::4]
+
+        def decode(self, z):
+            return z.repeat_interleave(4, -1).repeat_interleave(4, -2)
+
+    class Net(torch.nn.Module):
+        channels, self_condition = 3, None
+
+    cfg = dict(image_size=[64, 64], sampling_timesteps=5, eps=1e-4, sigma_min=0.01, sigma_max=1, weighting_loss=True,
+               use_l1=True, scale_factor=0.195, scale_by_std=True, default_scale=True)
+    ldm = LatentDiffusion(auto_encoder=AE(), model=Net(), cfg=cfg, **cfg)
+    assert float(ldm.scale_factor) == pytest.approx(0.195) and not any(p.requires_grad for p in ldm.first_stage_model.parameters())
+    assert ldm.t_steps()[0] == 1 and ldm.t_steps()[-1] == 0.0 and len(ldm.t_steps()) == 6
+    z, c, x = ldm.get_input({"image": torch.zeros(2, 3, 64, 64), "cond": torch.ones(2, 3, 16, 16)})
+    assert z.shape == (2, 3, 16, 16) and c.shape == (2, 3, 16, 16)
+    with pytest.raises(RuntimeError):  # no CPU fallback
+        ldm.training_step({"image": torch.zeros(2, 3, 64, 64)})
+    with pytest.raises(NotImplementedError):
+        LatentDiffusion(auto_encoder=AE(), model=Net(), cfg=dict(cfg, use_disloss=True), **cfg)
