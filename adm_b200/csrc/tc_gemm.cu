@@ -5,6 +5,7 @@
 #include <cudaTypedefs.h>
 #include <limits.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace adm {
@@ -109,12 +110,80 @@ static int launch(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap
     return 0;
 }
 
+// CTA-pair conv launch: cluster (2,1,1), an even grid of at most num_sms CTAs.
+static int launch_pair(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const GemmParams& p,
+                       cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             GEMM_SMEM_TOTAL);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return ADM_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    const long long pair_tiles = 1LL * ((p.m_tiles + 1) / 2) * p.n_tiles;
+    const int max_pairs = num_sms() / 2;
+    const int pairs = static_cast<int>(pair_tiles < max_pairs ? pair_tiles : max_pairs);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = GEMM_SMEM_TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_conv_pair_kernel, a, a2, b, p);
+    if (e != cudaSuccess) {
+        set_error("tc_conv_pair launch: %s", cudaGetErrorString(e));
+        return ADM_ERR_CUDA;
+    }
+    count_launch();
+    return 0;
+}
+
+// ADM_GEMM_PAIR=1 enables the cta_group::2 conv path.  It is OFF by default: measured on B200 it is ~6 % slower than the
+// single-CTA kernel on the CIFAR shapes (tools/bench_gemm_variants.py: 960 vs 1022 TF/s at 384->384 @16x16) although it
+// moves 30 % fewer bytes — these convs are not bound by L2 / shared-memory operand traffic.
+static bool pair_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ADM_GEMM_PAIR");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 // Largest multiple of 16 that is <= cap and divides ceil16(n); falls back to the smallest cover.
 static int pick_bn(int n, int cap, int multiple) {
     const int n16 = (n + multiple - 1) / multiple * multiple;
     for (int bn = cap / multiple * multiple; bn >= multiple; bn -= multiple)
         if (n16 % bn == 0) return bn;
     return multiple;
+}
+
+// N tile for the conv kernels from a small cost model (clocks): waves x (k_iters x mma + epilogue), with the MMA time of
+// a 128 x bn x 64 step proportional to the operand rows it reads from shared memory (128 + bn; measured ~0.43 us for
+// bn = 192, tools/bench_floor.py) and ~500 clocks of epilogue per 64 columns.  It only departs from "largest divisor"
+// when there are too few pixel tiles to fill the SMs (4x4 / 8x8 levels), where narrower tiles cut the critical path.
+static int pick_bn_cost(int n, int multiple, int m_tiles, int k_total) {
+    const int n_pad = (n + multiple - 1) / multiple * multiple;
+    const int sms = num_sms();
+    long long best = -1;
+    int best_bn = multiple;
+    for (int bn = 256 / multiple * multiple; bn >= multiple; bn -= multiple) {
+        if (n_pad % bn) continue;
+        const long long tiles = 1LL * m_tiles * (n_pad / bn);
+        const long long waves = (tiles + sms - 1) / sms;
+        const long long cost = waves * (1LL * k_total * 8 * (128 + bn) / 3 + 8LL * bn + 500);
+        if (best < 0 || cost < best) { best = cost; best_bn = bn; }
+    }
+    return best_bn;
 }
 
 // Pixel box (bw, bh, bni) covering `pixels` output pixels of an H x W image batch.
@@ -174,12 +243,12 @@ int adm_conv_fprop(const void* x1, int c1, long long ld1, const void* x2, int c2
     p.H = h; p.W = w;
     p.tiles_w = w / p.bw; p.tiles_h = h / p.bh;
     p.m_tiles = p.tiles_w * p.tiles_h * ((n + p.bni - 1) / p.bni);
-    p.bn = pick_bn(nout, 256, 16);
-    p.n_tiles = (nout + p.bn - 1) / p.bn;
     p.ntaps = ntaps;
     p.cchunks1 = pad64(c1) / 64;
     p.cchunks = p.cchunks1 + (x2 ? pad64(c2) / 64 : 0);
     p.k_total = p.k_iters = ntaps * p.cchunks;
+    p.bn = pick_bn_cost(nout, 16, p.m_tiles, p.k_total);
+    p.n_tiles = (nout + p.bn - 1) / p.bn;
     p.M = n * h * w; p.N = nout;
     p.C = out; p.ldc = ldc; p.bias = bias; p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = ldr;
     p.alpha = alpha; p.out_mode = out_mode;
@@ -189,8 +258,12 @@ int adm_conv_fprop(const void* x1, int c1, long long ld1, const void* x2, int c2
     const long long kpad = 1LL * ntaps * p.cchunks * 64;
     const long long bd[2] = {kpad, nout};
     const long long bs[1] = {kpad};
-    const int bb[2] = {64, p.bn};
+    // CTA pairs: 256-pixel tiles, each CTA loading half of the weight rows (box BN/2) — when there are at least two
+    // pixel tiles and the output mode is a plain store.
+    const bool pair = pair_enabled() && p.m_tiles >= 2 && p.bn % 16 == 0 && out_mode != OUT_F32_ATOMIC;
+    const int bb[2] = {64, pair ? p.bn / 2 : p.bn};
     if (int e = encode_map(&mb, wpk, 2, bd, bs, bb)) return e;
+    if (pair) return launch_pair(ma, ma2, mb, p, static_cast<cudaStream_t>(stream));
     return launch<GEMM_CONV>(ma, ma2, mb, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -206,11 +279,11 @@ int adm_conv_dgrad(const void* dy, int cout, long long ld_dy, int n, int h, int 
     p.H = h; p.W = w;
     p.tiles_w = w / p.bw; p.tiles_h = h / p.bh;
     p.m_tiles = p.tiles_w * p.tiles_h * ((n + p.bni - 1) / p.bni);
-    p.bn = pick_bn(kpad, 256, 64);
-    p.n_tiles = kpad / p.bn;
     p.ntaps = ntaps;
     p.cchunks1 = p.cchunks = pad64(cout) / 64;
     p.k_total = p.k_iters = ntaps * p.cchunks;
+    p.bn = pick_bn_cost(kpad, 64, p.m_tiles, p.k_total);
+    p.n_tiles = kpad / p.bn;
     p.b_mn = 1;
     p.M = n * h * w; p.N = n_valid;
     p.C = dx; p.ldc = ldc; p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = ldr;

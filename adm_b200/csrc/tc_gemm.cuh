@@ -58,6 +58,117 @@ __device__ __forceinline__ void decode_pix(const GemmParams& p, int idx, int& n0
     w0 = (r % p.tiles_w) * p.bw;
 }
 
+// Epilogue of one accumulator tile for one thread (= one output row): TMEM -> registers in groups of up to 64 columns
+// (four 32x32b.x16 loads in flight behind ONE wait, with the residual row segment prefetched behind the same wait),
+// then alpha * acc + bias + residual -> bf16 / fp32 / fp32 atomics.  c_off / r_off: element offsets of this row in the
+// output and the residual (before the column); col_shift: extra output column offset (batched GEMMs).
+__device__ __forceinline__ void epilogue_row(const GemmParams& p, uint32_t taddr, int col_base, int col_shift,
+                                             long long c_off, long long r_off, bool row_ok) {
+    for (int c0 = 0; c0 < p.bn; c0 += 64) {
+        if (col_base + c0 >= p.N) break;  // warp-uniform
+        uint32_t v[4][16];
+        uint4 rr[4][2];
+        const int nsub = min(4, (p.bn - c0) >> 4);
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+            if (s < nsub) tmem_ld_x16(taddr + c0 + 16 * s, v[s]);
+        // residual prefetch (aligned full chunks only; the ragged path re-reads below)
+        const bool res_vec = p.residual != nullptr && row_ok &&
+                             ((reinterpret_cast<uintptr_t>(p.residual + r_off + col_base + c0) & 15) == 0);
+        if (res_vec) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int col = col_base + c0 + 16 * s;
+                if (s < nsub && col + 16 <= p.N) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + r_off + col);
+                    rr[s][0] = rp[0];
+                    rr[s][1] = rp[1];
+                }
+            }
+        }
+        tmem_ld_wait();
+        if (!row_ok) continue;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            if (s >= nsub) break;
+            const int col = col_base + c0 + 16 * s;
+            if (col >= p.N) break;
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[s][j]) * p.alpha;
+            const bool full = (col + 16 <= p.N);
+            if (p.bias != nullptr) {
+                if (full && ((reinterpret_cast<uintptr_t>(p.bias + col) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
+                        f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (full || col + j < p.N) f[j] += __ldg(p.bias + col + j);
+                }
+            }
+            if (p.residual != nullptr) {
+                if (res_vec && full) {
+                    const uint32_t w[8] = {rr[s][0].x, rr[s][0].y, rr[s][0].z, rr[s][0].w,
+                                           rr[s][1].x, rr[s][1].y, rr[s][1].z, rr[s][1].w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        f[2 * j] += __uint_as_float(w[j] << 16);
+                        f[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+                    }
+                } else {
+                    const __nv_bfloat16* rp = p.residual + r_off + col;
+                    for (int j = 0; j < 16; ++j)
+                        if (col + j < p.N) f[j] += __bfloat162float(rp[j]);
+                }
+            }
+            const long long off = c_off + col_shift + col;
+            if (p.out_mode == OUT_BF16) {
+                __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + off;
+                if (full && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+                    uint32_t w[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                        w[j] = *reinterpret_cast<const uint32_t*>(&b2);
+                    }
+                    *reinterpret_cast<uint4*>(cp) = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(cp + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+                } else {
+                    for (int j = 0; j < 16; ++j)
+                        if (col + j < p.N) cp[j] = __float2bfloat16(f[j]);
+                }
+            } else if (p.out_mode == OUT_F32) {
+                float* cp = reinterpret_cast<float*>(p.C) + off;
+                if (full && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<float4*>(cp + 4 * j) =
+                            make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                } else {
+                    for (int j = 0; j < 16; ++j)
+                        if (col + j < p.N) cp[j] = f[j];
+                }
+            } else {
+                float* cp = reinterpret_cast<float*>(p.C) + off;
+                if (full && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        atomicAdd(reinterpret_cast<float4*>(cp + 4 * j),
+                                  make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
+                } else {
+                    for (int j = 0; j < 16; ++j)
+                        if (col + j < p.N) atomicAdd(cp + j, f[j]);
+                }
+            }
+        }
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
@@ -247,81 +358,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&tfull_bar[acc], acc_phase, 4);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(quad * 32) << 16);
-            for (int c = 0; c < p.bn; c += 16) {
-                uint32_t v[16];
-                __syncwarp();
-                tmem_ld_x16(taddr + c, v);
-                tmem_ld_wait();
-                const int col = col_base + c;
-                if (col >= p.N) break;  // warp-uniform
-                if (row_ok) {
-                float f[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-                const bool full = (col + 16 <= p.N);
-                if (p.bias != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (full || col + j < p.N) f[j] += __ldg(p.bias + col + j);
-                }
-                const long long off = c_base + col_shift + col;
-                if (p.residual != nullptr) {
-                    const __nv_bfloat16* rp = p.residual + row_off * p.ldr + col;
-                    if (full && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
-                        const uint4 r0 = *reinterpret_cast<const uint4*>(rp);
-                        const uint4 r1 = *reinterpret_cast<const uint4*>(rp + 8);
-                        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
-                            f[2 * j] += __bfloat162float(b2.x);
-                            f[2 * j + 1] += __bfloat162float(b2.y);
-                        }
-                    } else {
-                        for (int j = 0; j < 16; ++j)
-                            if (col + j < p.N) f[j] += __bfloat162float(rp[j]);
-                    }
-                }
-                if (p.out_mode == OUT_BF16) {
-                    __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + off;
-                    if (full && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
-                        uint32_t w[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                            w[j] = *reinterpret_cast<const uint32_t*>(&b2);
-                        }
-                        *reinterpret_cast<uint4*>(cp) = make_uint4(w[0], w[1], w[2], w[3]);
-                        *reinterpret_cast<uint4*>(cp + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-                    } else {
-                        for (int j = 0; j < 16; ++j)
-                            if (col + j < p.N) cp[j] = __float2bfloat16(f[j]);
-                    }
-                } else if (p.out_mode == OUT_F32) {
-                    float* cp = reinterpret_cast<float*>(p.C) + off;
-                    if (full && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<float4*>(cp + 4 * j) =
-                                make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                    } else {
-                        for (int j = 0; j < 16; ++j)
-                            if (col + j < p.N) cp[j] = f[j];
-                    }
-                } else {
-                    float* cp = reinterpret_cast<float*>(p.C) + off;
-                    if (full && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            atomicAdd(reinterpret_cast<float4*>(cp + 4 * j),
-                                      make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
-                    } else {
-                        for (int j = 0; j < 16; ++j)
-                            if (col + j < p.N) atomicAdd(cp + j, f[j]);
-                    }
-                }
-                }  // row_ok
-            }
+            epilogue_row(p, taddr, col_base, col_shift, c_base, row_off * p.ldr, row_ok);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -334,6 +371,155 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ CTA-pair conv kernel
+// Implicit-GEMM conv (K-major packed weights) with cta_group::2: a cluster of two CTAs computes a 256-pixel x BN tile.
+// Each CTA TMA-loads its own 128-pixel A box and HALF of the weight rows (BN/2 x 64), so per MMA k-step an SM pulls
+// 16 KB + BN*64 B through the L2 fabric instead of 16 KB + BN*128 B — the single-CTA kernel is bound by exactly that
+// traffic (profiles/r01_conv_ncu_full.txt).  Roles per CTA are those of tc_gemm_kernel; differences:
+//   * full barriers live in the leader (rank 0) and collect the TMA bytes of both CTAs;
+//   * the leader's MMA thread issues tcgen05.mma.cta_group::2 (M = 256) and its commits arrive, multicast, on the
+//     empty / tmem-full barriers of both CTAs;
+//   * both epilogues (4 warps each) release the accumulator on the leader's tmem-empty barrier (count 8).
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int half_bn = p.bn >> 1;
+    const int stage_bytes = GEMM_A_STAGE + half_bn * 128;
+    int num_stages = GEMM_SMEM_RING / stage_bytes;
+    if (num_stages > GEMM_MAX_STAGES) num_stages = GEMM_MAX_STAGES;
+
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + GEMM_SMEM_RING);
+    uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
+    uint64_t* tfull_bar = empty_bar + GEMM_MAX_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int rank = static_cast<int>(cluster_ctarank());
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmA2);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < num_stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 8);
+        }
+        fence_barrier_init();
+        fence_proxy_async_smem();
+    }
+    if (warp == 1) tmem_alloc_pair(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA credit
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int m_pairs = (p.m_tiles + 1) >> 1;
+    const int num_tiles = m_pairs * p.n_tiles;
+    const int first = blockIdx.x >> 1, stride = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // =========================================================== TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = first; tile < num_tiles; tile += stride) {
+                const int nt = tile % p.n_tiles;
+                const int mt = 2 * (tile / p.n_tiles) + rank;
+                int n0, h0, w0;
+                decode_pix(p, mt, n0, h0, w0);  // mt == m_tiles (odd tail): n0 is out of range -> zero-filled boxes
+                for (int ki = 0; ki < p.k_total; ++ki) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+                    uint8_t* sa = smem + stage * stage_bytes;
+                    uint8_t* sb = sa + GEMM_A_STAGE;
+                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);
+                    const int tap = ki / p.cchunks, kc = ki % p.cchunks;
+                    int dh = 0, dw = 0;
+                    if (p.ntaps == 9) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+                    if (kc < p.cchunks1)
+                        tma_load_4d_pair(sa, &tmA, &full_bar[stage], kc * 64, w0 + dw, h0 + dh, n0);
+                    else
+                        tma_load_4d_pair(sa, &tmA2, &full_bar[stage], (kc - p.cchunks1) * 64, w0 + dw, h0 + dh, n0);
+                    tma_load_2d_pair(sb, &tmB, &full_bar[stage], ki * 64, nt * p.bn + rank * half_bn);
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================================================== UMMA issuer (leader only)
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = make_idesc_bf16(2 * GEMM_BLOCK_M, p.bn, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = first; tile < num_tiles; tile += stride) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * 256;
+                for (int ki = 0; ki < p.k_total; ++ki) {
+                    mbar_wait(&full_bar[stage], phase, 3);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+                    const uint32_t sb = sa + GEMM_A_STAGE;
+#pragma unroll
+                    for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+                        const uint64_t da = make_smem_desc(sa + k * 32u, 16u, 1024);
+                        const uint64_t db = make_smem_desc(sb + k * 32u, 16u, 1024);
+                        umma_bf16_pair(tmem_d, da, db, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit_pair(&empty_bar[stage]);
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_pair(&tfull_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // =========================================================== epilogue (4 warps per CTA, own 128 rows)
+        const int quad = warp & 3;
+        const int m = quad * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = first; tile < num_tiles; tile += stride) {
+            const int nt = tile % p.n_tiles;
+            const int mt = 2 * (tile / p.n_tiles) + rank;
+            int n0, h0, w0;
+            decode_pix(p, mt, n0, h0, w0);
+            const int wi = m % p.bw, hi = (m / p.bw) % p.bh, ni = m / (p.bw * p.bh);
+            const long long pix = (static_cast<long long>(n0 + ni) * p.H + (h0 + hi)) * p.W + (w0 + wi);
+            const bool row_ok = mt < p.m_tiles && pix < p.M;
+            const long long c_base = pix * p.ldc;
+            const int col_base = nt * p.bn;
+
+            mbar_wait(&tfull_bar[acc], acc_phase, 4);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(quad * 32) << 16);
+            epilogue_row(p, taddr, col_base, 0, c_base, pix * p.ldr, row_ok);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // neither CTA may free TMEM / exit while the pair's MMAs or remote arrives are in flight
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
     }
 }
 
