@@ -166,7 +166,12 @@ class TrainStep:
         dev = self.arena.flat.device
         self.sqnorm = torch.zeros(1, device=dev, dtype=torch.float32)
         self.hyper = torch.zeros(3, device=dev, dtype=torch.float32)
-        self.hyper_host = torch.zeros(3, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(3)
+        # per-step scalars travel through a small ring of pinned buffers: the H2D copy is asynchronous, and the host may
+        # run several (graph-replayed) steps ahead of the device, so a single buffer would be overwritten too early
+        self._hyper_ring = [torch.zeros(3, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(3)
+                            for _ in range(4)]
+        self._hyper_events = [None] * 4
+        self._ring_i = 0
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.pg = process_group
         # gradient buckets in completion order
@@ -174,6 +179,8 @@ class TrainStep:
         per = max(1, bucket_mb * (1 << 20) // 4)
         self.buckets = [(s, min(n, s + per)) for s in range(0, n, per)]
         self.comm_stream = torch.cuda.Stream(device=dev) if (self.world > 1 and dev.type == "cuda") else None
+        self._seg_capture = None
+        self.segments = None
         self._param_end = {}
         for p, o in zip(self.arena.params, self.arena.offsets):
             self._param_end[id(p)] = o + p.numel()
@@ -212,7 +219,7 @@ class TrainStep:
     # overlaps the transfer over NVLink with the rest of the backward pass.  1/world is folded into the AdamW kernel.
     def _arm(self):
         self._done_upto, self._next_bucket = 0, 0
-        self.engine.grad_hook = self._on_grads if self.world > 1 else None
+        self.engine.grad_hook = self._on_grads if (self.world > 1 or self._seg_capture is not None) else None
 
     def _on_grads(self, params):
         for p in params:
@@ -223,6 +230,12 @@ class TrainStep:
 
     def _flush(self, upto):
         if self._next_bucket >= len(self.buckets) or self.buckets[self._next_bucket][1] > upto:
+            return
+        if self._seg_capture is not None:  # segmented graph capture: cut the graph here, reduce between replays
+            first = self._next_bucket
+            while self._next_bucket < len(self.buckets) and self.buckets[self._next_bucket][1] <= upto:
+                self._next_bucket += 1
+            self._cut_segment((first, self._next_bucket))
             return
         if self.comm_stream is None:  # host tensors (gloo tests): reduce synchronously
             while self._next_bucket < len(self.buckets) and self.buckets[self._next_bucket][1] <= upto:
@@ -249,17 +262,26 @@ class TrainStep:
         self.engine.grad_hook = None
 
     # ------------------------------------------------------------------------------------------ the step
-    def _fill_hyper_host(self):
+    def _push_hyper(self):
+        """lr, 1 - beta1^step, sqrt(1 - beta2^step) of the CURRENT step_count -> device (stream-ordered, eager)."""
+        i = self._ring_i
+        self._ring_i = (i + 1) % len(self._hyper_ring)
+        if self._hyper_events[i] is not None:
+            self._hyper_events[i].synchronize()  # the copy that last used this slot has been consumed
+        buf = self._hyper_ring[i]
         step = self.step_count
-        lr = self.lr * (self.lr_schedule(step - 1) if self.lr_schedule is not None else 1.0)
-        self.hyper_host[0] = lr
-        self.hyper_host[1] = 1.0 - self.betas[0] ** step
-        self.hyper_host[2] = math.sqrt(1.0 - self.betas[1] ** step)
+        buf[0] = self.lr * (self.lr_schedule(step - 1) if self.lr_schedule is not None else 1.0)
+        buf[1] = 1.0 - self.betas[0] ** step
+        buf[2] = math.sqrt(1.0 - self.betas[1] ** step)
+        self.hyper.copy_(buf, non_blocking=True)
+        if self.hyper.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._hyper_events[i] = ev
 
     def optimizer_step(self):
         self.step_count += 1
-        self._fill_hyper_host()
-        self.hyper.copy_(self.hyper_host, non_blocking=True)
+        self._push_hyper()
         if self.seed_counter is not None:
             self.seed_counter.add_(1)
         self.device_update()
@@ -278,13 +300,10 @@ class TrainStep:
                 self.optimizer_step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.step_count += 1
-        self._fill_hyper_host()
         g = torch.cuda.CUDAGraph()
         from . import _lib
         l0 = _lib.load().adm_launch_count()
         with torch.cuda.graph(g):
-            self.hyper.copy_(self.hyper_host, non_blocking=True)
             self.seed_counter.add_(1)
             self.static_loss = self.micro_step(self.static_x)
             self.device_update()
@@ -297,8 +316,87 @@ class TrainStep:
         if x is not None:
             self.static_x.copy_(x, non_blocking=True)
         self.step_count += 1
-        self._fill_hyper_host()
+        self._push_hyper()
+        if self.segments is not None:
+            return self._replay_segments()
         self.graph.replay()
+        return self.static_loss
+
+    # ------------------------------------------------------------------------------------------ segmented graphs (DP)
+    # With several ranks the step cannot be ONE graph (capturing the NCCL collectives hung on this stack), and eager
+    # launching makes the host the bottleneck (~1200 launches per step).  So the step is captured as a CHAIN of graphs,
+    # cut at every point where a gradient bucket becomes complete; between two replays the bucket's all-reduce is
+    # launched eagerly on the communication stream, which keeps the overlap of the transfer with the rest of backward.
+    def _cut_segment(self, bucket_range):
+        cap = self._seg_capture
+        cap["graph"].capture_end()
+        cap["segments"].append((cap["graph"], bucket_range))
+        g = torch.cuda.CUDAGraph()
+        g.capture_begin(pool=cap["pool"])
+        cap["graph"] = g
+
+    def capture_dp(self, x_example, warmup=2, t=None, noise=None):
+        """t / noise: optional STATIC tensors baked into the graphs (tests); by default they are drawn inside."""
+        assert self.grad_accum == 1, "graph capture covers the single-micro-batch step"
+        self.static_x = x_example.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.micro_step(self.static_x, t, noise)
+                self.optimizer_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.pg)
+        from . import _lib
+        l0 = _lib.load().adm_launch_count()
+        pool = torch.cuda.graph_pool_handle()
+        self._cap_stream = torch.cuda.Stream()
+        self._cap_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._cap_stream):
+            g = torch.cuda.CUDAGraph()
+            g.capture_begin(pool=pool)
+            self._seg_capture = dict(graph=g, segments=[], pool=pool)
+            try:
+                self.seed_counter.add_(1)
+                self.static_loss = self.micro_step(self.static_x, t, noise)
+                self._flush(self.arena.numel)  # whatever is left of the gradient arena
+                self.engine.grad_hook = None
+                a = self.arena
+                gscale = 1.0 / (self.world * self.grad_accum)
+                self.sqnorm.zero_()
+                ops.sq_norm(a.grads, self.sqnorm)
+                ops.adamw(a.flat, a.grads, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                          max(1, self.step_count), grad_scale=gscale, max_norm=self.max_grad_norm, sqnorm=self.sqnorm,
+                          hyper_dev=self.hyper, p_bf16=a.shadow)
+                a.zero_grad()
+                self.engine.invalidate()
+                self._seg_capture["graph"].capture_end()
+                self.segments = self._seg_capture["segments"] + [(self._seg_capture["graph"], None)]
+            finally:
+                self._seg_capture = None
+        torch.cuda.current_stream().wait_stream(self._cap_stream)
+        self.launches_per_step = _lib.load().adm_launch_count() - l0
+        return self.segments
+
+    def _replay_segments(self):
+        cur = torch.cuda.current_stream()
+        for g, rng in self.segments:
+            if rng is None:  # the optimizer segment: every bucket must have been reduced
+                if self.comm_stream is not None:
+                    cur.wait_stream(self.comm_stream)
+                g.replay()
+                break
+            g.replay()
+            if self.world > 1:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                self.comm_stream.wait_event(ev)
+                with torch.cuda.stream(self.comm_stream):
+                    for b in range(rng[0], rng[1]):
+                        s, e = self.buckets[b]
+                        dist.all_reduce(self.arena.grads[s:e], op=dist.ReduceOp.SUM, group=self.pg)
         return self.static_loss
 
     def device_update(self):
@@ -322,12 +420,38 @@ class TrainStep:
             self._arm()
         else:
             self.engine.grad_hook = None
+        if set(kw) <= {"augment_labels"}:
+            return self._direct_step(x, t, noise, kw.get("augment_labels"))
         if t is None:
             loss, _ = self.dpm(x, **kw)
         else:
             loss, _ = self.dpm.p_losses(x, t, noise=noise, **kw)
         loss.backward()
         return loss.detach()
+
+    def _direct_step(self, x, t, noise, aug):
+        """DDPM.forward + p_losses + backward (ddm_const.py:274-364) driven straight through the engine on the calling
+        thread — K1 q_sample, UNet forward with tape, K2 loss + gradients, hand-written backward — without building an
+        autograd graph (same arithmetic as ``dpm(x)`` followed by ``loss.backward()``)."""
+        dpm = self.dpm
+        if not x.is_cuda:
+            raise RuntimeError("adm_b200.TrainStep runs on CUDA (sm_100a) only; there is no CPU fallback")
+        with torch.no_grad():
+            if dpm.scale_input != 1:
+                x = x * dpm.scale_input
+            if t is None:
+                t = torch.rand(x.shape[0], device=x.device) * (1. - dpm._eps) + dpm._eps
+            if noise is None:
+                noise = torch.randn_like(x) if dpm.start_dist == "normal" else 2 * torch.rand_like(x) - 1.
+            if aug is None and dpm.use_augment and dpm.augment is not None:
+                x, aug = dpm.augment(x)
+            x = x.contiguous().float()
+            noise = noise.contiguous().float()
+            x_noisy = ops.qsample(x, noise, t)
+            d1, d2, tape = self.engine.forward(x_noisy, t, aug, training=self.net.training, need_grad=True)
+            lps, dc, de = ops.ddm_loss(d1, d2, x, noise, t, dpm._eps, bool(dpm.weighting_loss), bool(dpm.use_l1))
+            self.engine.backward(tape, dc, de)
+            return lps.sum() / x.shape[0]
 
     def __call__(self, batches):
         """batches: list of `grad_accum` image tensors (this rank's shard).  Returns the mean loss tensor."""

@@ -184,14 +184,16 @@ def run_ours(args):
     x_dev = 2 * torch.rand(B, 3, 32, 32, device=device, generator=gen) - 1
     x_host = (2 * torch.rand(B, 3, 32, 32) - 1).pin_memory()
 
-    # multi-rank: NCCL collectives on the side stream are launched eagerly (graph capture of them is not validated)
-    use_graph = (not args.no_graph) and (world == 1 or args.graph_dp)
+    # one rank: the whole step is ONE CUDA graph.  Several ranks: a chain of graphs cut at the gradient-bucket boundaries,
+    # with the NCCL all-reduces launched eagerly between replays (capturing NCCL into the graph hung on this stack).
+    use_graph = not args.no_graph
     if use_graph:
         try:
-            step.capture(x_dev)
+            step.capture(x_dev) if world == 1 else step.capture_dp(x_dev)
         except Exception as e:  # keep measuring eagerly, and say so in the JSON line
             print(f"[bench] CUDA graph capture failed ({e!r}); running eagerly", file=sys.stderr, flush=True)
             use_graph = False
+            step.segments = step.graph = None
 
     def one_step(x):
         if use_graph:
@@ -275,7 +277,9 @@ def run_ours(args):
                    "global_batch": B * world, "batch_per_gpu": B, "parallelism": f"dp{world}", "grad_accum": 1,
                    "augment": "off (AugmentPipe is host-side data glue, SURVEY 8f-4)",
                    "l2": "activation working set >> 126 MB L2 (no flush needed)", "timing": "cuda events, max over ranks",
-                   "launch": "one CUDA graph per step" if use_graph else "eager launches"},
+                   "launch": ("one CUDA graph per step" if world == 1 else
+                              f"{len(step.segments)} chained CUDA graphs per step, NCCL all-reduce between them")
+                   if use_graph else "eager launches"},
         "e2e": {"value": B * world / (ms_e2e / 1000), "unit": "img/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "last_loss": loss_host},
         "gpu_launches": int(launches),
@@ -304,7 +308,6 @@ def main():
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--graph-dp", action="store_true", help="also capture the multi-rank step (NCCL inside the graph)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

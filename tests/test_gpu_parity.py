@@ -223,3 +223,40 @@ def test_cond_unet_and_latent_diffusion_vs_reference_golden():
     """Whole cond Unet (outputs, latent DDM loss, per-parameter gradients, 3-step latent sampler) against vectors recorded
     from the unmodified reference unet.cond_unet.Unet (tests/golden/make_golden_cond.py)."""
     assert CC.CASES["cond_unet_golden"]()
+
+
+def test_segmented_graph_step_matches_eager_step():
+    """The multi-rank launch structure (a chain of CUDA graphs cut at the gradient-bucket boundaries, all-reduces
+    launched between replays) on one GPU: three replayed steps must produce the parameters of three eager steps
+    (same x, t, noise; dropout is 0 in this config, so only the fp32 atomics' summation order differs)."""
+    from tests.golden.make_golden import TINY, inputs
+    from adm_b200.ddm.ddm_const import DDPM
+    from adm_b200.train import TrainStep
+    cfg = dict(image_size=[16, 16], sampling_timesteps=3, eps=1e-4, weighting_loss=True)
+    x, t, noise, _ = (a.cuda() for a in inputs(TINY, 16, 8))
+
+    def run(mode):
+        net = CU_build(TINY)
+        net.train()
+        dpm = DDPM(model=net, cfg=cfg, **cfg).cuda()
+        step = TrainStep(dpm, lr=1e-3, bucket_mb=2)
+        start = step.arena.flat.clone()
+        if mode == "segments":
+            segs = step.capture_dp(x, warmup=1, t=t, noise=noise)  # one eager warm-up step, then capture
+            assert len(segs) >= 4  # several bucket cuts + the optimizer graph
+            for _ in range(3):
+                loss = step.replay(x)
+        else:
+            for _ in range(4):
+                loss = step.micro_step(x, t, noise)
+                step.optimizer_step()
+        assert step.step_count == 4
+        torch.cuda.synchronize()
+        return start, step.arena.flat.clone(), float(loss)
+
+    s0, p_eager, l_eager = run("eager")
+    _, p_seg, l_seg = run("segments")
+    assert abs(l_seg - l_eager) / l_eager < 1e-3
+    upd_e, upd_s = p_eager - s0, p_seg - s0
+    cos = torch.dot(upd_e, upd_s) / (upd_e.norm() * upd_s.norm())
+    assert cos.item() > 0.999 and abs(upd_s.norm().item() / upd_e.norm().item() - 1) < 1e-2
