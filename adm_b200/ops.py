@@ -441,14 +441,23 @@ def _gemm(desc_kw, a_op, b_op, what):
     check(_lib.load().adm_gemm_batched(d, _stream()), what)
 
 
-def attention_fwd(qkv, heads, scale=None):
+def attention_fwd(qkv, heads, scale=None, need_p=True, fused=None):
     """qkv: [N, H, W, 3C] bf16 laid out as (q | k | v), each [heads, d].  Returns (a [N,H,W,C], p [N*heads,HW,HW]).
-    scale defaults to 1/sqrt(d) (d = C / heads as stored, which may include zero padding of the head dim)."""
+    scale defaults to 1/sqrt(d) (d = C / heads as stored, which may include zero padding of the head dim).
+    With d == 64 and HW in {16, 64, 256} the whole op is ONE fused kernel (K9); p is None unless need_p."""
     n, h, w, c3 = qkv.shape
     c, hw = c3 // 3, h * w
     d = c // heads
     scale = 1.0 / d ** 0.5 if scale is None else float(scale)
     assert qkv.is_contiguous()
+    if fused is None:
+        fused = d == 64 and hw in (16, 64, 256)
+    if fused:
+        a = torch.empty(n, h, w, c, device=qkv.device, dtype=BF16)
+        p = torch.empty(n * heads, hw, hw, device=qkv.device, dtype=BF16) if need_p else None
+        check(_lib.load().adm_attn_fwd_fused(_ptr(qkv), n, hw, heads, scale, _ptr(a), _ptr(p), _stream()),
+              "attn_fwd_fused")
+        return a, p
     s = torch.empty(n * heads, hw, hw, device=qkv.device, dtype=F32)
     qk_dims, qk_str = (c3, hw, n), (c3, c3 * hw)
     _gemm(dict(m=hw, n=hw, k=d, batches=n * heads, bdiv=heads, splits=1, c=s.data_ptr(), out_mode=1, ldc=hw,

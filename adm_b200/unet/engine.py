@@ -251,7 +251,7 @@ class UNetEngine:
                               lambda old: blk.qkv.bias.detach()[perm[1]].contiguous() if old is None
                               else torch.index_select(blk.qkv.bias.detach(), 0, perm[1], out=old))
             c.qkv = ops.conv_fprop(c.a2, self.conv_w(blk.qkv, perm=perm[0]), bias=bq)
-            c.att, c.p = ops.attention_fwd(c.qkv, blk.num_heads)
+            c.att, c.p = ops.attention_fwd(c.qkv, blk.num_heads, need_p=save is not None)
             out = ops.conv_fprop(c.att, self.conv_w(blk.proj), bias=blk.proj.bias, residual=c.h1)
         if save is not None:
             save.append(c)

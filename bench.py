@@ -27,6 +27,11 @@ MODEL_CFG = dict(image_size=[32, 32], sampling_timesteps=10, loss_type="l2", sta
 TRAIN_GFLOP_PER_IMG = 213.9   # 3 x 71.30 forward GFLOP
 FWD_GFLOP_PER_IMG = 71.30
 METRIC = "train_img_per_s"
+WORKLOAD = ("CIFAR-10 32x32 DDM-const training step, EDMPrecond/DhariwalUNet 216.1M params "
+            "(configs/cifar10/ddm_uncond_const_uncond_unet.yaml), fwd+bwd+clip+AdamW, dropout 0.1")
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel from `ncu --set full`
+# (profiles/r01_conv_ncu_full.txt): the 25 MB input is read once, weights 2.6 MB, the output stays in L2.
+CONV_DRAM_TRAFFIC_BYTES = 27.9e6
 
 
 def peaks():
@@ -114,8 +119,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "img/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "CIFAR-10 32x32 DDM-const training step (EDMPrecond/DhariwalUNet 216.1M), "
-                                   f"CPU sample batch {b}", "global_batch": b},
+            "config": {"workload": WORKLOAD, "global_batch": args.batch * args.gpus, "batch_per_gpu": args.batch,
+                       "parallelism": f"dp{args.gpus}", "grad_accum": 1,
+                       "reference_sample": f"each step is a bounded sample of that workload: batch {b} on "
+                                           f"{base['cores']} host cores (rank 0 only)"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -272,9 +279,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": "CIFAR-10 32x32 DDM-const training step, EDMPrecond/DhariwalUNet 216.1M params "
-                               "(configs/cifar10/ddm_uncond_const_uncond_unet.yaml), fwd+bwd+clip+AdamW, dropout 0.1",
-                   "global_batch": B * world, "batch_per_gpu": B, "parallelism": f"dp{world}", "grad_accum": 1,
+        "config": {"workload": WORKLOAD, "global_batch": B * world, "batch_per_gpu": B, "parallelism": f"dp{world}", "grad_accum": 1,
                    "augment": "off (AugmentPipe is host-side data glue, SURVEY 8f-4)",
                    "l2": "activation working set >> 126 MB L2 (no flush needed)", "timing": "cuda events, max over ranks",
                    "launch": ("one CUDA graph per step" if world == 1 else
@@ -285,7 +290,8 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"bound": "tensor", "achieved": conv_tf, "peak": pk["tf_burst"], "unit": "TFLOP/s",
-                     "frac": conv_tf / pk["tf_burst"], "traffic": None,
+                     "frac": conv_tf / pk["tf_burst"], "traffic": CONV_DRAM_TRAFFIC_BYTES,
+                     "algorithmic_flops_per_launch": 2.0 * 128 * 16 * 16 * 384 * 384 * 9,
                      "kernel": "tc_gemm_kernel<CONV> conv3x3 384->384 @16x16 x128 (dominant shape), timed alone",
                      "ms_per_launch": conv_ms, "peak_source": pk["src"],
                      "step_tflops_per_gpu": step_tf, "step_frac_of_sustained_peak": step_tf / pk["tf_sust"]},

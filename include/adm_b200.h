@@ -185,6 +185,12 @@ int adm_silu_bwd(const float* x, const float* dy, float* dx, void* dx_bf16, long
  * backward: dS = scale * P * (dP - sum_j dP_j P_j).                                                           */
 int adm_softmax_fwd(const float* s, void* p, long long rows, int len, void* stream);
 int adm_softmax_bwd(const void* p, const float* dp, void* ds, float scale, long long rows, int len, void* stream);
+/* K9 forward, fused: one CTA per (sample, head) keeps S = Q K^T in TMEM, runs the softmax in registers, writes P as the
+ * swizzled A operand of the second tcgen05 MMA and stores O = P V — S and P never touch HBM (p_out == NULL) or only the
+ * normalised bf16 P does (training; the backward kernels consume it).  qkv [batch][n_pix][3*heads*64] bf16 laid out
+ * (q | k | v) x head x 64; n_pix in {16, 64, 256}; out [batch][n_pix][heads*64]; p_out [batch*heads][n_pix][n_pix].  */
+int adm_attn_fwd_fused(const void* qkv, int batch, int n_pix, int heads, float scale, void* out, void* p_out,
+                       void* stream);
 /* SpatialAtt + residual of the decouple branches (unet/uncond_unet.py:27-37, :566-567):
  * out = softsign(softmax(q k^T) att) * h + res with att = h . w_map + b; scalars = {b_map, wq, bq, wk, bk}.   */
 int adm_spatial_att_fwd(const void* h, long long ldh, const void* res, long long ldr, const float* w_map,

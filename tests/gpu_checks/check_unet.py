@@ -183,11 +183,16 @@ def attention():
     from adm_b200 import ops
     torch.manual_seed(2)
     ok = True
-    for (n, hw_side, c) in [(4, 16, 384), (8, 8, 128), (16, 4, 384)]:
+    for (n, hw_side, c) in [(4, 16, 384), (8, 8, 128), (16, 4, 384), (128, 16, 384)]:
         heads = c // 64
         hw = hw_side * hw_side
         qkv = (torch.randn(n, hw_side, hw_side, 3 * c, device="cuda") * 0.8).bfloat16()
-        a, p = ops.attention_fwd(qkv, heads)
+        a, p = ops.attention_fwd(qkv, heads)  # K9 fused kernel (d = 64, HW in {16, 64, 256})
+        a_u, p_u = ops.attention_fwd(qkv, heads, fused=False)  # batched GEMMs + softmax kernel
+        ok &= _report(f"attn fused vs unfused a n{n} hw{hw}", a, a_u, 6e-3)
+        ok &= _report(f"attn fused vs unfused P n{n} hw{hw}", p, p_u, 6e-3)
+        a_np, p_none = ops.attention_fwd(qkv, heads, need_p=False)
+        ok &= p_none is None and bool(torch.equal(a_np, a))
         qr = qkv.float().requires_grad_(True)
         q, k, v = (qr[..., i * c:(i + 1) * c].reshape(n, hw, heads, 64).permute(0, 2, 1, 3) for i in range(3))
         w = (q @ k.transpose(-1, -2) / np.sqrt(64)).softmax(-1)
