@@ -7,6 +7,10 @@
 //                the K-major swizzled A-operand layout in shared memory (and to HBM when the backward needs it);
 //   tcgen05    : O = P V    (V consumed MN-major), accumulating over the S columns it replaces;
 //   epilogue   : TMEM -> bf16 -> [B, N, C] with this head's 64 channels.
+// The same kernel in backward mode (MODE 1) fuses three of the five backward products: dP = dO V^T in TMEM, per row
+// dS = scale * P o (dP - sum_j dP_j P_j) with P read back as bf16, dS written as the swizzled A operand (and to HBM for
+// the dK product), and dQ = dS K as the second MMA — dP never exists in HBM.  dV = P^T dO and dK = dS^T Q stay batched
+// GEMMs of the shared engine.
 // Neither S nor P round-trips through HBM in inference; in training only the normalised P is stored (bf16) because the
 // backward kernels consume it.  N (pixels) in {16, 64, 256}; head dim 64 (32 runs zero-padded, see cond_unet.Attention).
 #include "adm_internal.h"
@@ -33,13 +37,17 @@ struct AttnParams {
     int n_pix;       // queries = keys
     int heads, c;    // C = heads * 64
     float scale;     // softmax(scale * q.k)
-    __nv_bfloat16* out;  // [B, n_pix, C]
-    __nv_bfloat16* p_out;  // [B*heads, n_pix, n_pix] or null
+    __nv_bfloat16* out;    // fwd: O [B, n_pix, ld_out] head slice h*64; bwd: dQ into dqkv (ld_out = 3C)
+    long long ld_out;
+    __nv_bfloat16* p_out;  // fwd: normalised P [B*heads, n_pix, n_pix] or null; bwd: dS (same shape)
+    const __nv_bfloat16* p_in;  // bwd: the saved P
+    int a_col, b1_col, b2_col;  // channel offsets (before + h*64) of the three operands in their tensors
 };
 
+template <int MODE>  // 0: forward (Q, K, V -> P, O);  1: backward (dO, V, K, P -> dS, dQ)
 __global__ void __launch_bounds__(AF_THREADS, 1)
-attn_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                      const __grid_constant__ AttnParams p) {
+attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                  const __grid_constant__ AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + AF_SMEM_BAR);
@@ -70,9 +78,9 @@ attn_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     if (threadIdx.x == 0) {
         // ---- loads: Q (q_rows x 64), K, V (N x 64) of this (sample, head)
         mbar_expect_tx(bar_load, (q_rows + 2 * N) * 128);
-        tma_load_3d(smem + AF_SMEM_Q, &tmQ, bar_load, h * 64, 0, b);
-        tma_load_3d(smem + AF_SMEM_K, &tmKV, bar_load, p.c + h * 64, 0, b);
-        tma_load_3d(smem + AF_SMEM_V, &tmKV, bar_load, 2 * p.c + h * 64, 0, b);
+        tma_load_3d(smem + AF_SMEM_Q, &tmQ, bar_load, p.a_col + h * 64, 0, b);
+        tma_load_3d(smem + AF_SMEM_K, &tmKV, bar_load, p.b1_col + h * 64, 0, b);
+        tma_load_3d(smem + AF_SMEM_V, &tmKV, bar_load, p.b2_col + h * 64, 0, b);
         mbar_wait(bar_load, 0, 11);
         tc_fence_after();
         // ---- S[mt] = Q[mt] K^T  (K-major x K-major, 4 k-steps of 16)
@@ -100,6 +108,7 @@ attn_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         mbar_wait(&bar_s[mt], 0, 12);
         tc_fence_after();
         const uint32_t taddr = tmem_base + mt * 256 + (static_cast<uint32_t>(quad * 32) << 16);
+        if (MODE == 0) {
         float mx = -INFINITY;
         for (int c0 = 0; c0 < N; c0 += 64) {
             uint32_t v[4][16];
@@ -165,6 +174,74 @@ attn_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                     }
                 }
         }
+        } else {
+        // dS = scale * P o (dP - dot), dot = sum_j dP_j P_j; P of this row comes back from HBM as bf16
+        const __nv_bfloat16* pr = p.p_in + (1LL * bh * N + (row_ok ? q : 0)) * N;
+        float dot = 0.f;
+        for (int c0 = 0; c0 < N; c0 += 64) {
+            uint32_t v[4][16];
+            uint4 pv[4][2];
+            const int nsub = min(4, (N - c0) >> 4);
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                if (s < nsub) {
+                    tmem_ld_x16(taddr + c0 + 16 * s, v[s]);
+                    pv[s][0] = *reinterpret_cast<const uint4*>(pr + c0 + 16 * s);
+                    pv[s][1] = *reinterpret_cast<const uint4*>(pr + c0 + 16 * s + 8);
+                }
+            tmem_ld_wait();
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                if (s < nsub) {
+                    const uint32_t w[8] = {pv[s][0].x, pv[s][0].y, pv[s][0].z, pv[s][0].w,
+                                           pv[s][1].x, pv[s][1].y, pv[s][1].z, pv[s][1].w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        dot = fmaf(__uint_as_float(v[s][2 * j]), __uint_as_float(w[j] << 16), dot);
+                        dot = fmaf(__uint_as_float(v[s][2 * j + 1]), __uint_as_float(w[j] & 0xFFFF0000u), dot);
+                    }
+                }
+        }
+        uint8_t* sp = smem + AF_SMEM_P + mt * 4 * AF_TILE;
+        __nv_bfloat16* pg = row_ok ? p.p_out + (1LL * bh * N + q) * N : nullptr;
+        for (int c0 = 0; c0 < N; c0 += 64) {
+            uint32_t v[4][16];
+            uint4 pv[4][2];
+            const int nsub = min(4, (N - c0) >> 4);
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                if (s < nsub) {
+                    tmem_ld_x16(taddr + c0 + 16 * s, v[s]);
+                    pv[s][0] = *reinterpret_cast<const uint4*>(pr + c0 + 16 * s);
+                    pv[s][1] = *reinterpret_cast<const uint4*>(pr + c0 + 16 * s + 8);
+                }
+            tmem_ld_wait();
+            uint8_t* chunk = sp + (c0 >> 6) * AF_TILE + row * 128;
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                if (s < nsub) {
+                    const uint32_t pw[8] = {pv[s][0].x, pv[s][0].y, pv[s][0].z, pv[s][0].w,
+                                            pv[s][1].x, pv[s][1].y, pv[s][1].z, pv[s][1].w};
+                    uint32_t w[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float d0 = p.scale * __uint_as_float(pw[j] << 16) * (__uint_as_float(v[s][2 * j]) - dot);
+                        const float d1 =
+                            p.scale * __uint_as_float(pw[j] & 0xFFFF0000u) * (__uint_as_float(v[s][2 * j + 1]) - dot);
+                        const __nv_bfloat162 b2 = __floats2bfloat162_rn(d0, d1);
+                        w[j] = *reinterpret_cast<const uint32_t*>(&b2);
+                    }
+                    *reinterpret_cast<uint4*>(chunk + (((2 * s) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(chunk + (((2 * s + 1) ^ (row & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+                    if (pg != nullptr) {
+                        *reinterpret_cast<uint4*>(pg + c0 + 16 * s) = make_uint4(w[0], w[1], w[2], w[3]);
+                        *reinterpret_cast<uint4*>(pg + c0 + 16 * s + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+                    }
+                }
+        }
+        }
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
     }
     tc_fence_before();
@@ -197,7 +274,7 @@ attn_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         for (int s = 0; s < 4; ++s) tmem_ld_x16(taddr + 16 * s, v[s]);
         tmem_ld_wait();
         if (row_ok) {
-            __nv_bfloat16* op = p.out + (1LL * b * N + q) * p.c + h * 64;
+            __nv_bfloat16* op = p.out + (1LL * b * N + q) * p.ld_out + h * 64;
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 uint32_t w[8];
@@ -252,31 +329,62 @@ static int af_map(CUtensorMap* m, const void* ptr, long long c3, int n_pix, int 
     return 0;
 }
 
+template <int MODE>
+static int af_launch(const CUtensorMap& ma, const CUtensorMap& mb, const AttnParams& p, int blocks, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(attn_fused_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM_TOTAL);
+        attr_set = true;
+    }
+    attn_fused_kernel<MODE><<<blocks, AF_THREADS, AF_SMEM_TOTAL, st>>>(ma, mb, p);
+    ADM_CHECK_LAUNCH("attn_fused");
+    return 0;
+}
+
+static int af_check(const char* what, int batch, int n_pix, int heads, const void* a, const void* b, const void* c) {
+    if (n_pix != 16 && n_pix != 64 && n_pix != 256) {
+        set_error("%s: n_pix must be 16, 64 or 256 (got %d)", what, n_pix);
+        return ADM_ERR_SHAPE;
+    }
+    if (batch <= 0 || heads <= 0 || ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+                                       reinterpret_cast<uintptr_t>(c)) & 15)) {
+        set_error("%s: bad arguments", what);
+        return ADM_ERR_SHAPE;
+    }
+    return 0;
+}
+
 extern "C" int adm_attn_fwd_fused(const void* qkv, int batch, int n_pix, int heads, float scale, void* out, void* p_out,
                                   void* stream) {
-    if (n_pix != 16 && n_pix != 64 && n_pix != 256) {
-        set_error("attn_fwd_fused: n_pix must be 16, 64 or 256 (got %d)", n_pix);
-        return ADM_ERR_SHAPE;
-    }
-    if (batch <= 0 || heads <= 0 || (reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
-        (reinterpret_cast<uintptr_t>(p_out) & 15)) {
-        set_error("attn_fwd_fused: bad arguments");
-        return ADM_ERR_SHAPE;
-    }
+    if (int e = af_check("attn_fwd_fused", batch, n_pix, heads, qkv, out, p_out)) return e;
     const int c = heads * 64;
     CUtensorMap mq, mkv;
     if (int e = af_map(&mq, qkv, 3LL * c, n_pix, batch, n_pix > 128 ? 256 : 128)) return e;
     if (int e = af_map(&mkv, qkv, 3LL * c, n_pix, batch, n_pix)) return e;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(attn_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM_TOTAL);
-        attr_set = true;
-    }
     AttnParams p;
     p.n_pix = n_pix; p.heads = heads; p.c = c; p.scale = scale;
-    p.out = static_cast<__nv_bfloat16*>(out);
-    p.p_out = static_cast<__nv_bfloat16*>(p_out);
-    attn_fwd_fused_kernel<<<batch * heads, AF_THREADS, AF_SMEM_TOTAL, static_cast<cudaStream_t>(stream)>>>(mq, mkv, p);
-    ADM_CHECK_LAUNCH("attn_fwd_fused");
-    return 0;
+    p.out = static_cast<__nv_bfloat16*>(out); p.ld_out = c;
+    p.p_out = static_cast<__nv_bfloat16*>(p_out); p.p_in = nullptr;
+    p.a_col = 0; p.b1_col = c; p.b2_col = 2 * c;
+    return af_launch<0>(mq, mkv, p, batch * heads, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int adm_attn_bwd_fused(const void* da, const void* qkv, const void* p_saved, int batch, int n_pix, int heads,
+                                  float scale, void* ds_out, void* dqkv, void* stream) {
+    if (int e = af_check("attn_bwd_fused", batch, n_pix, heads, da, qkv, dqkv)) return e;
+    if (p_saved == nullptr || ds_out == nullptr || ((reinterpret_cast<uintptr_t>(p_saved) |
+                                                       reinterpret_cast<uintptr_t>(ds_out)) & 15)) {
+        set_error("attn_bwd_fused: P and dS buffers are required (16 B aligned)");
+        return ADM_ERR_SHAPE;
+    }
+    const int c = heads * 64;
+    CUtensorMap mdo, mkv;
+    if (int e = af_map(&mdo, da, c, n_pix, batch, n_pix > 128 ? 256 : 128)) return e;
+    if (int e = af_map(&mkv, qkv, 3LL * c, n_pix, batch, n_pix)) return e;
+    AttnParams p;
+    p.n_pix = n_pix; p.heads = heads; p.c = c; p.scale = scale;
+    p.out = static_cast<__nv_bfloat16*>(dqkv); p.ld_out = 3LL * c;  // dQ occupies channels [0, C) of dqkv
+    p.p_out = static_cast<__nv_bfloat16*>(ds_out); p.p_in = static_cast<const __nv_bfloat16*>(p_saved);
+    p.a_col = 0; p.b1_col = 2 * c; p.b2_col = c;                    // A = dO, B1 = V, B2 = K
+    return af_launch<1>(mdo, mkv, p, batch * heads, static_cast<cudaStream_t>(stream));
 }

@@ -473,8 +473,9 @@ def attention_fwd(qkv, heads, scale=None, need_p=True, fused=None):
     return a, p
 
 
-def attention_bwd(da, qkv, p, heads, scale=None):
-    """Returns dqkv [N,H,W,3C] bf16."""
+def attention_bwd(da, qkv, p, heads, scale=None, fused=None):
+    """Returns dqkv [N,H,W,3C] bf16.  With d == 64 and HW in {16, 64, 256}: dP, dS and dQ come from ONE fused kernel
+    (dP stays in TMEM); dV and dK are two batched GEMMs."""
     n, h, w, c3 = qkv.shape
     c, hw = c3 // 3, h * w
     d = c // heads
@@ -486,6 +487,21 @@ def attention_bwd(da, qkv, p, heads, scale=None):
     p_dims, p_str = (hw, hw, n * heads), (hw, hw * hw)
     nb = n * heads
     esz = 2
+    if fused is None:
+        fused = d == 64 and hw in (16, 64, 256)
+    if fused:
+        ds = torch.empty_like(p)
+        check(_lib.load().adm_attn_bwd_fused(_ptr(da), _ptr(qkv), _ptr(p), n, hw, heads, scale, _ptr(ds), _ptr(dqkv),
+                                             _stream()), "attn_bwd_fused")
+        _gemm(dict(m=hw, n=d, k=hw, batches=nb, bdiv=heads, splits=1, c=dqkv.data_ptr() + 2 * c * esz, out_mode=0,
+                   ldc=c3, c_bhi=hw * c3, c_blo=0, c_col_lo=d, alpha=1.0),
+              _operand(p, 1, p_dims, p_str, bhi=heads, blo=1),
+              _operand(da, 1, a_dims, a_str, c0=0, c0_lo=d, bhi=1), "attn dV")
+        _gemm(dict(m=hw, n=d, k=hw, batches=nb, bdiv=heads, splits=1, c=dqkv.data_ptr() + c * esz, out_mode=0, ldc=c3,
+                   c_bhi=hw * c3, c_blo=0, c_col_lo=d, alpha=1.0),
+              _operand(ds, 1, p_dims, p_str, bhi=heads, blo=1),
+              _operand(qkv, 1, qk_dims, qk_str, c0=0, c0_lo=d, bhi=1), "attn dK")
+        return dqkv
     # dV[k, d] = sum_q P[q, k] dA[q, d]
     _gemm(dict(m=hw, n=d, k=hw, batches=nb, bdiv=heads, splits=1, c=dqkv.data_ptr() + 2 * c * esz, out_mode=0,
                ldc=c3, c_bhi=hw * c3, c_blo=0, c_col_lo=d, alpha=1.0),

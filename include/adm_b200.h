@@ -191,6 +191,11 @@ int adm_softmax_bwd(const void* p, const float* dp, void* ds, float scale, long 
  * (q | k | v) x head x 64; n_pix in {16, 64, 256}; out [batch][n_pix][heads*64]; p_out [batch*heads][n_pix][n_pix].  */
 int adm_attn_fwd_fused(const void* qkv, int batch, int n_pix, int heads, float scale, void* out, void* p_out,
                        void* stream);
+/* K9 backward, fused part: dP = dO V^T (TMEM) -> dS = scale * P o (dP - rowsum(dP o P)) -> dQ = dS K in ONE kernel per
+ * (sample, head); dS (bf16, the shape of P) is also written out for the dK product.  da [batch][n_pix][heads*64];
+ * dQ is written into channels [0, C) of dqkv [batch][n_pix][3C].  dV = P^T dO and dK = dS^T Q use adm_gemm_batched. */
+int adm_attn_bwd_fused(const void* da, const void* qkv, const void* p_saved, int batch, int n_pix, int heads,
+                       float scale, void* ds_out, void* dqkv, void* stream);
 /* SpatialAtt + residual of the decouple branches (unet/uncond_unet.py:27-37, :566-567):
  * out = softsign(softmax(q k^T) att) * h + res with att = h . w_map + b; scalars = {b_map, wq, bq, wk, bk}.   */
 int adm_spatial_att_fwd(const void* h, long long ldh, const void* res, long long ldr, const float* w_map,

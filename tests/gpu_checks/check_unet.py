@@ -202,6 +202,8 @@ def attention():
         ar.backward(da.float())
         dqkv = ops.attention_bwd(da, qkv, p, heads)
         ok &= _report(f"attn bwd n{n} hw{hw} c{c}", dqkv, qr.grad, 2e-2)
+        dqkv_u = ops.attention_bwd(da, qkv, p, heads, fused=False)
+        ok &= _report(f"attn bwd fused vs unfused n{n} hw{hw}", dqkv, dqkv_u, 8e-3)
     return ok
 
 
