@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(256) ws_pack_bwd_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------------ K12 LinearAttention
 constexpr int LA_D = 32;          // head dim (reference default dim_head = 32)
 constexpr int LA_WARPS = 8;       // warps per block in the streaming passes
+constexpr int LA_U = 4;           // pixels per warp iteration in the per-pixel passes
 
 __device__ __forceinline__ float ldbf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
@@ -208,24 +209,37 @@ __global__ void linattn_apply_kernel(const __nv_bfloat16* __restrict__ qkv, long
     const int n0 = blockIdx.x * pix_per_block, n1 = min(N, n0 + pix_per_block);
     const __nv_bfloat16* qb = qkv + 1LL * b * N * ld + h * LA_D + lane;
     __nv_bfloat16* ob = out + 1LL * b * N * ldo + h * LA_D + lane;
-    float* qs = qsm + h * LA_D;
-    for (int n = n0; n < n1; ++n) {
-        const float q = ldbf(qb + 1LL * n * ld);
-        const float mx = warp_max(q);
-        const float p = __expf(q - mx);
-        const float s = warp_sum(p);
-        qs[lane] = p * (scale / s);
+    float* qs = qsm + h * LA_U * LA_D;  // [LA_U][32] per warp
+    for (int n = n0; n < n1; n += LA_U) {  // LA_U pixels per iteration: independent shuffle / FMA chains in flight
+        float q[LA_U], mx[LA_U], pe[LA_U], sm_[LA_U];
+#pragma unroll
+        for (int u = 0; u < LA_U; ++u) q[u] = n + u < n1 ? ldbf(qb + 1LL * (n + u) * ld) : 0.f;
+#pragma unroll
+        for (int u = 0; u < LA_U; ++u) mx[u] = warp_max(q[u]);
+#pragma unroll
+        for (int u = 0; u < LA_U; ++u) pe[u] = __expf(q[u] - mx[u]);
+#pragma unroll
+        for (int u = 0; u < LA_U; ++u) sm_[u] = warp_sum(pe[u]);
+#pragma unroll
+        for (int u = 0; u < LA_U; ++u) qs[u * LA_D + lane] = pe[u] * (scale / sm_[u]);
         __syncwarp();
-        float o = 0.f;
+        float o[LA_U];
+#pragma unroll
+        for (int u = 0; u < LA_U; ++u) o[u] = 0.f;
 #pragma unroll
         for (int d = 0; d < LA_D; d += 4) {
-            const float4 q4 = *reinterpret_cast<const float4*>(&qs[d]);
-            o = fmaf(col[d], q4.x, o);
-            o = fmaf(col[d + 1], q4.y, o);
-            o = fmaf(col[d + 2], q4.z, o);
-            o = fmaf(col[d + 3], q4.w, o);
+#pragma unroll
+            for (int u = 0; u < LA_U; ++u) {
+                const float4 q4 = *reinterpret_cast<const float4*>(&qs[u * LA_D + d]);
+                o[u] = fmaf(col[d], q4.x, o[u]);
+                o[u] = fmaf(col[d + 1], q4.y, o[u]);
+                o[u] = fmaf(col[d + 2], q4.z, o[u]);
+                o[u] = fmaf(col[d + 3], q4.w, o[u]);
+            }
         }
-        ob[1LL * n * ldo] = __float2bfloat16(o);
+#pragma unroll
+        for (int u = 0; u < LA_U; ++u)
+            if (n + u < n1) ob[1LL * (n + u) * ldo] = __float2bfloat16(o[u]);
         __syncwarp();
     }
 }
@@ -247,31 +261,47 @@ __global__ void linattn_bwd_q_kernel(const __nv_bfloat16* __restrict__ qkv, long
     const __nv_bfloat16* qb = qkv + 1LL * b * N * ld + h * LA_D + lane;
     const __nv_bfloat16* db = dout + 1LL * b * N * ldd + h * LA_D + lane;
     __nv_bfloat16* gq = dqkv + 1LL * b * N * ldg + h * LA_D + lane;
-    float* ds = dsm + h * LA_D;
-    for (int n = n0; n < n1; ++n) {
-        const float q = ldbf(qb + 1LL * n * ld);
-        ds[lane] = ldbf(db + 1LL * n * ldd);
-        const float mx = warp_max(q);
-        const float p = __expf(q - mx);
-        const float s = p / warp_sum(p);  // softmax_d(q)[d]
+    float* ds = dsm + h * LA_U * LA_D;  // [LA_U][32] staged dout rows per warp
+    for (int n = n0; n < n1; n += LA_U) {
+        float q[LA_U], mx[LA_U], pe[LA_U], sv[LA_U];
+#pragma unroll
+        for (int u = 0; u < LA_U; ++u) {
+            const bool ok = n + u < n1;
+            q[u] = ok ? ldbf(qb + 1LL * (n + u) * ld) : 0.f;
+            ds[u * LA_D + lane] = ok ? ldbf(db + 1LL * (n + u) * ldd) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < LA_U; ++u) mx[u] = warp_max(q[u]);
+#pragma unroll
+        for (int u = 0; u < LA_U; ++u) pe[u] = __expf(q[u] - mx[u]);
+#pragma unroll
+        for (int u = 0; u < LA_U; ++u) sv[u] = pe[u] / warp_sum(pe[u]);  // softmax_d(q)[d]
         __syncwarp();
-        float dqh = 0.f;  // d(loss)/d(q_hat[d]) = sum_e ctx[d][e] dout[e]
-        const float qh = s * scale;
+        float dqh[LA_U];  // d(loss)/d(q_hat[d]) = sum_e ctx[d][e] dout[e]
+#pragma unroll
+        for (int u = 0; u < LA_U; ++u) dqh[u] = 0.f;
 #pragma unroll
         for (int e = 0; e < LA_D; e += 4) {
-            const float4 d4 = *reinterpret_cast<const float4*>(&ds[e]);
-            dqh = fmaf(row[e], d4.x, dqh);
-            dqh = fmaf(row[e + 1], d4.y, dqh);
-            dqh = fmaf(row[e + 2], d4.z, dqh);
-            dqh = fmaf(row[e + 3], d4.w, dqh);
-            acc[e] = fmaf(qh, d4.x, acc[e]);
-            acc[e + 1] = fmaf(qh, d4.y, acc[e + 1]);
-            acc[e + 2] = fmaf(qh, d4.z, acc[e + 2]);
-            acc[e + 3] = fmaf(qh, d4.w, acc[e + 3]);
+#pragma unroll
+            for (int u = 0; u < LA_U; ++u) {
+                const float4 d4 = *reinterpret_cast<const float4*>(&ds[u * LA_D + e]);
+                const float qh = sv[u] * scale;
+                dqh[u] = fmaf(row[e], d4.x, dqh[u]);
+                dqh[u] = fmaf(row[e + 1], d4.y, dqh[u]);
+                dqh[u] = fmaf(row[e + 2], d4.z, dqh[u]);
+                dqh[u] = fmaf(row[e + 3], d4.w, dqh[u]);
+                acc[e] = fmaf(qh, d4.x, acc[e]);
+                acc[e + 1] = fmaf(qh, d4.y, acc[e + 1]);
+                acc[e + 2] = fmaf(qh, d4.z, acc[e + 2]);
+                acc[e + 3] = fmaf(qh, d4.w, acc[e + 3]);
+            }
         }
-        const float dsv = scale * dqh;  // gradient w.r.t. the softmax output s
-        const float dot = warp_sum(dsv * s);
-        gq[1LL * n * ldg] = __float2bfloat16(s * (dsv - dot));
+        float dot[LA_U];
+#pragma unroll
+        for (int u = 0; u < LA_U; ++u) dot[u] = warp_sum(scale * dqh[u] * sv[u]);
+#pragma unroll
+        for (int u = 0; u < LA_U; ++u)
+            if (n + u < n1) gq[1LL * (n + u) * ldg] = __float2bfloat16(sv[u] * (scale * dqh[u] - dot[u]));
         __syncwarp();
     }
     float* dst = dpart + ((1LL * (b * heads + h) * gridDim.x + blockIdx.x) * LA_D + lane) * LA_D;
@@ -325,29 +355,43 @@ __global__ void linattn_bwd_kv_kernel(const __nv_bfloat16* __restrict__ qkv, lon
     const __nv_bfloat16* vb = qkv + 1LL * b * N * ld + 2 * hidden + h * LA_D + lane;
     __nv_bfloat16* gk = dqkv + 1LL * b * N * ldg + hidden + h * LA_D + lane;
     __nv_bfloat16* gv = dqkv + 1LL * b * N * ldg + 2 * hidden + h * LA_D + lane;
-    float* ks = sm2 + h * 2 * LA_D;
-    float* vs = ks + LA_D;
-    for (int n = n0; n < n1; ++n) {
-        const float kh = __expf(ldbf(kb + 1LL * n * ld) - mx) * invZ;
-        ks[lane] = kh;
-        vs[lane] = ldbf(vb + 1LL * n * ld);
+    float* ks = sm2 + h * 2 * LA_U * LA_D;  // [LA_U][32] k_hat rows, then [LA_U][32] v rows, per warp
+    float* vs = ks + LA_U * LA_D;
+    for (int n = n0; n < n1; n += LA_U) {
+        float kh[LA_U];
+#pragma unroll
+        for (int u = 0; u < LA_U; ++u) {
+            const bool ok = n + u < n1;
+            kh[u] = ok ? __expf(ldbf(kb + 1LL * (n + u) * ld) - mx) * invZ : 0.f;
+            ks[u * LA_D + lane] = kh[u];
+            vs[u * LA_D + lane] = ok ? ldbf(vb + 1LL * (n + u) * ld) : 0.f;
+        }
         __syncwarp();
-        float dv = 0.f, t = 0.f;
+        float dv[LA_U], t[LA_U];
+#pragma unroll
+        for (int u = 0; u < LA_U; ++u) dv[u] = t[u] = 0.f;
 #pragma unroll
         for (int i = 0; i < LA_D; i += 4) {
-            const float4 k4 = *reinterpret_cast<const float4*>(&ks[i]);
-            const float4 v4 = *reinterpret_cast<const float4*>(&vs[i]);
-            dv = fmaf(k4.x, col[i], dv);
-            dv = fmaf(k4.y, col[i + 1], dv);
-            dv = fmaf(k4.z, col[i + 2], dv);
-            dv = fmaf(k4.w, col[i + 3], dv);
-            t = fmaf(row[i], v4.x, t);
-            t = fmaf(row[i + 1], v4.y, t);
-            t = fmaf(row[i + 2], v4.z, t);
-            t = fmaf(row[i + 3], v4.w, t);
+#pragma unroll
+            for (int u = 0; u < LA_U; ++u) {
+                const float4 k4 = *reinterpret_cast<const float4*>(&ks[u * LA_D + i]);
+                const float4 v4 = *reinterpret_cast<const float4*>(&vs[u * LA_D + i]);
+                dv[u] = fmaf(k4.x, col[i], dv[u]);
+                dv[u] = fmaf(k4.y, col[i + 1], dv[u]);
+                dv[u] = fmaf(k4.z, col[i + 2], dv[u]);
+                dv[u] = fmaf(k4.w, col[i + 3], dv[u]);
+                t[u] = fmaf(row[i], v4.x, t[u]);
+                t[u] = fmaf(row[i + 1], v4.y, t[u]);
+                t[u] = fmaf(row[i + 2], v4.z, t[u]);
+                t[u] = fmaf(row[i + 3], v4.w, t[u]);
+            }
         }
-        gv[1LL * n * ldg] = __float2bfloat16(dv * invN);
-        gk[1LL * n * ldg] = __float2bfloat16(kh * (t * invN - rd));
+#pragma unroll
+        for (int u = 0; u < LA_U; ++u)
+            if (n + u < n1) {
+                gv[1LL * (n + u) * ldg] = __float2bfloat16(dv[u] * invN);
+                gk[1LL * (n + u) * ldg] = __float2bfloat16(kh[u] * (t[u] * invN - rd));
+            }
         __syncwarp();
     }
 }
@@ -409,7 +453,7 @@ int adm_linattn_fwd(const void* qkv, long long ld, int batch, int n_pix, int hea
         int ppb = (n_pix + blocks - 1) / blocks;
         if (ppb < 4) ppb = 4;
         blocks = (n_pix + ppb - 1) / ppb;
-        linattn_apply_kernel<<<dim3(blocks, batch), heads * 32, heads * LA_D * sizeof(float), s>>>(
+        linattn_apply_kernel<<<dim3(blocks, batch), heads * 32, heads * LA_U * LA_D * sizeof(float), s>>>(
             static_cast<const bf16*>(qkv), ld, n_pix, heads, ctx, scale, static_cast<bf16*>(out), ldo, ppb);
         ADM_CHECK_LAUNCH("linattn_apply");
     }
@@ -423,7 +467,7 @@ int adm_linattn_bwd(const void* qkv, long long ld, int batch, int n_pix, int hea
     if (heads < 1 || heads > 32 || batch <= 0 || n_pix <= 0) { set_error("linattn: bad shape"); return ADM_ERR_SHAPE; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int chunks = la_chunks(n_pix, batch * heads);
-    linattn_bwd_q_kernel<<<dim3(chunks, batch), heads * 32, heads * LA_D * sizeof(float), s>>>(
+    linattn_bwd_q_kernel<<<dim3(chunks, batch), heads * 32, heads * LA_U * LA_D * sizeof(float), s>>>(
         static_cast<const bf16*>(qkv), ld, n_pix, heads, ctx, scale, static_cast<const bf16*>(dout), ldd,
         static_cast<bf16*>(dqkv), ldg, work);
     ADM_CHECK_LAUNCH("linattn_bwd_q");
@@ -433,7 +477,7 @@ int adm_linattn_bwd(const void* qkv, long long ld, int batch, int n_pix, int hea
     int ppb = (n_pix + blocks - 1) / blocks;
     if (ppb < 4) ppb = 4;
     blocks = (n_pix + ppb - 1) / ppb;
-    linattn_bwd_kv_kernel<<<dim3(blocks, batch), heads * 32, heads * 2 * LA_D * sizeof(float), s>>>(
+    linattn_bwd_kv_kernel<<<dim3(blocks, batch), heads * 32, heads * 2 * LA_U * LA_D * sizeof(float), s>>>(
         static_cast<const bf16*>(qkv), ld, n_pix, heads, kstat, dctx, r, static_cast<bf16*>(dqkv), ldg, ppb);
     ADM_CHECK_LAUNCH("linattn_bwd_kv");
     return 0;
