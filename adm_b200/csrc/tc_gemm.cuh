@@ -14,7 +14,7 @@ constexpr int GEMM_BLOCK_K = 64;
 constexpr int GEMM_THREADS = 192;
 constexpr int GEMM_A_STAGE = GEMM_BLOCK_M * 128;  // 16 KB
 constexpr int GEMM_SMEM_RING = 200 * 1024;        // operand ring budget
-constexpr int GEMM_SMEM_AUX = 1024;               // barriers + tmem ptr
+constexpr int GEMM_SMEM_AUX = 4096;               // barriers + tmem ptr (first 1 KB) + per-tile bias slices (2 x 1 KB)
 constexpr int GEMM_SMEM_TOTAL = GEMM_SMEM_RING + GEMM_SMEM_AUX + 1024;  // + alignment slack
 constexpr int GEMM_MAX_STAGES = 8;
 
@@ -58,12 +58,25 @@ __device__ __forceinline__ void decode_pix(const GemmParams& p, int idx, int& n0
     w0 = (r % p.tiles_w) * p.bw;
 }
 
+// The four epilogue warps stage the tile's bias slice (bn <= 256 floats, zero beyond N) in shared memory BEFORE waiting
+// for the accumulator: per-chunk __ldg of the bias missed L1 behind the streaming stores and cost ~30 us on the
+// epilogue-bound 1x1 convs.  `m` = epilogue thread index 0..127; named barrier 1 covers exactly those 128 threads.
+__device__ __forceinline__ void stage_bias(const GemmParams& p, float* sbias, int col_base, int m) {
+    if (p.bias == nullptr) return;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int c = m + 128 * i;
+        if (c < p.bn) sbias[c] = (col_base + c < p.N) ? __ldg(p.bias + col_base + c) : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
 // Epilogue of one accumulator tile for one thread (= one output row): TMEM -> registers in groups of up to 64 columns
 // (four 32x32b.x16 loads in flight behind ONE wait, with the residual row segment prefetched behind the same wait),
 // then alpha * acc + bias + residual -> bf16 / fp32 / fp32 atomics.  c_off / r_off: element offsets of this row in the
 // output and the residual (before the column); col_shift: extra output column offset (batched GEMMs).
 __device__ __forceinline__ void epilogue_row(const GemmParams& p, uint32_t taddr, int col_base, int col_shift,
-                                             long long c_off, long long r_off, bool row_ok) {
+                                             long long c_off, long long r_off, bool row_ok, const float* sbias) {
     for (int c0 = 0; c0 < p.bn; c0 += 64) {
         if (col_base + c0 >= p.N) break;  // warp-uniform
         uint32_t v[4][16];
@@ -98,17 +111,11 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, uint32_t taddr
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[s][j]) * p.alpha;
             const bool full = (col + 16 <= p.N);
-            if (p.bias != nullptr) {
-                if (full && ((reinterpret_cast<uintptr_t>(p.bias + col) & 15) == 0)) {
+            if (p.bias != nullptr) {  // this tile's bias slice was staged in shared memory (zero beyond N)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
-                        f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (full || col + j < p.N) f[j] += __ldg(p.bias + col + j);
+                for (int j = 0; j < 4; ++j) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + 16 * s + 4 * j);
+                    f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
                 }
             }
             if (p.residual != nullptr) {
@@ -136,8 +143,16 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, uint32_t taddr
                         const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
                         w[j] = *reinterpret_cast<const uint32_t*>(&b2);
                     }
-                    *reinterpret_cast<uint4*>(cp) = make_uint4(w[0], w[1], w[2], w[3]);
-                    *reinterpret_cast<uint4*>(cp + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+                    if ((reinterpret_cast<uintptr_t>(cp) & 31) == 0) {
+                        // one 256-bit store = one full 32 B sector per thread (sm_100 st.global.v8): rows of a tile are
+                        // scattered over 128 different lines, so two 16 B halves would each be a partial-sector write
+                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(cp), "r"(w[0]),
+                                     "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                                     : "memory");
+                    } else {
+                        *reinterpret_cast<uint4*>(cp) = make_uint4(w[0], w[1], w[2], w[3]);
+                        *reinterpret_cast<uint4*>(cp + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+                    }
                 } else {
                     for (int j = 0; j < 16; ++j)
                         if (col + j < p.N) cp[j] = __float2bfloat16(f[j]);
@@ -355,10 +370,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int col_base = nt * p.bn;           // column inside [0, N)
             const int col_shift = b_lo * p.c_col_lo;  // extra offset in the output row
 
+            float* sbias = reinterpret_cast<float*>(smem + GEMM_SMEM_RING + 1024) + acc * 256;
+            stage_bias(p, sbias, col_base, m);
             mbar_wait(&tfull_bar[acc], acc_phase, 4);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(quad * 32) << 16);
-            epilogue_row(p, taddr, col_base, col_shift, c_base, row_off * p.ldr, row_ok);
+            epilogue_row(p, taddr, col_base, col_shift, c_base, row_off * p.ldr, row_ok, sbias);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -503,10 +520,12 @@ tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const long long c_base = pix * p.ldc;
             const int col_base = nt * p.bn;
 
+            float* sbias = reinterpret_cast<float*>(smem + GEMM_SMEM_RING + 1024) + acc * 256;
+            stage_bias(p, sbias, col_base, m);
             mbar_wait(&tfull_bar[acc], acc_phase, 4);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(quad * 32) << 16);
-            epilogue_row(p, taddr, col_base, 0, c_base, pix * p.ldr, row_ok);
+            epilogue_row(p, taddr, col_base, 0, c_base, pix * p.ldr, row_ok, sbias);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
