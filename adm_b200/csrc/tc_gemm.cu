@@ -100,7 +100,11 @@ static int launch(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap
         return ADM_ERR_SHAPE;
     }
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    tc_gemm_kernel<MODE><<<grid, GEMM_THREADS, GEMM_SMEM_TOTAL, stream>>>(a, a2, b, p);
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("ADM_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+    GemmParams pd = p;
+    pd.debug = dbg;
+    tc_gemm_kernel<MODE><<<grid, GEMM_THREADS, GEMM_SMEM_TOTAL, stream>>>(a, a2, b, pd);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("tc_gemm launch: %s", cudaGetErrorString(e));
@@ -173,6 +177,10 @@ static int pick_bn(int n, int cap, int multiple) {
 // when there are too few pixel tiles to fill the SMs (4x4 / 8x8 levels), where narrower tiles cut the critical path.
 static int pick_bn_cost(int n, int multiple, int m_tiles, int k_total) {
     const int n_pad = (n + multiple - 1) / multiple * multiple;
+    if (const char* e = getenv("ADM_BN")) {  // experiments: force the N tile when it is legal for this problem
+        const int bn = atoi(e);
+        if (bn >= multiple && bn <= 256 && bn % multiple == 0 && n_pad % bn == 0) return bn;
+    }
     const int sms = num_sms();
     long long best = -1;
     int best_bn = multiple;

@@ -6,6 +6,9 @@
 // Tile = 128 (M) x BN (N, runtime, multiple of 16, <= 256) x 64 (K per stage, bf16 = one 128 B swizzle row).
 #pragma once
 #include "ptx.cuh"
+#ifdef ADM_GEMM_TIMING
+#include <stdio.h>
+#endif
 
 namespace adm {
 
@@ -48,6 +51,7 @@ struct GemmParams {
     long long ldr;
     float alpha;
     int out_mode;
+    int debug;  // experiments only (ADM_GEMM_DEBUG): bit 0 = skip the MMAs, bit 1 = skip the TMA loads
 };
 
 __device__ __forceinline__ void decode_pix(const GemmParams& p, int idx, int& n0, int& h0, int& w0) {
@@ -247,6 +251,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&empty_bar[stage], phase ^ 1, 1);
                     uint8_t* sa = smem + stage * stage_bytes;
                     uint8_t* sb = sa + GEMM_A_STAGE;
+                    if (p.debug & 2) {
+                        mbar_arrive(&full_bar[stage]);
+                        if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_expect_tx(&full_bar[stage], stage_bytes);
                     if (MODE == GEMM_CONV) {
                         const int tap = ki / p.cchunks, kc = ki % p.cchunks;
@@ -320,20 +329,41 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * 256;
+#ifdef ADM_GEMM_TIMING
+                long long t_wait = 0, t_issue = 0, t_commit = 0;
+#endif
                 for (int ki = k_begin; ki < k_end; ++ki) {
+#ifdef ADM_GEMM_TIMING
+                    const long long c0 = clock64();
+#endif
                     mbar_wait(&full_bar[stage], phase, 3);
                     tc_fence_after();
+#ifdef ADM_GEMM_TIMING
+                    const long long c1 = clock64();
+#endif
                     const uint32_t sa = smem_u32(smem + stage * stage_bytes);
                     const uint32_t sb = sa + GEMM_A_STAGE;
 #pragma unroll
                     for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
                         const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
                         const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-                        umma_bf16(tmem_d, da, db, idesc, (ki > k_begin || k > 0) ? 1u : 0u);
+                        if (!(p.debug & 1)) umma_bf16(tmem_d, da, db, idesc, (ki > k_begin || k > 0) ? 1u : 0u);
                     }
+#ifdef ADM_GEMM_TIMING
+                    const long long c2 = clock64();
+#endif
                     umma_commit(&empty_bar[stage]);
+#ifdef ADM_GEMM_TIMING
+                    const long long c3 = clock64();
+                    t_wait += c1 - c0; t_issue += c2 - c1; t_commit += c3 - c2;
+#endif
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
+#ifdef ADM_GEMM_TIMING
+                if (blockIdx.x == 0 && tile == blockIdx.x)
+                    printf("[mma thread] k-iters %d: wait %lld issue %lld commit %lld clocks per k-iter\n", k_end - k_begin,
+                           t_wait / (k_end - k_begin), t_issue / (k_end - k_begin), t_commit / (k_end - k_begin));
+#endif
                 umma_commit(&tfull_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
@@ -485,9 +515,18 @@ tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * 256;
+#ifdef ADM_GEMM_TIMING
+                long long t_wait = 0, t_issue = 0, t_commit = 0;
+#endif
                 for (int ki = 0; ki < p.k_total; ++ki) {
+#ifdef ADM_GEMM_TIMING
+                    const long long c0 = clock64();
+#endif
                     mbar_wait(&full_bar[stage], phase, 3);
                     tc_fence_after();
+#ifdef ADM_GEMM_TIMING
+                    const long long c1 = clock64();
+#endif
                     const uint32_t sa = smem_u32(smem + stage * stage_bytes);
                     const uint32_t sb = sa + GEMM_A_STAGE;
 #pragma unroll
@@ -496,9 +535,21 @@ tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const uint64_t db = make_smem_desc(sb + k * 32u, 16u, 1024);
                         umma_bf16_pair(tmem_d, da, db, idesc, (ki > 0 || k > 0) ? 1u : 0u);
                     }
+#ifdef ADM_GEMM_TIMING
+                    const long long c2 = clock64();
+#endif
                     umma_commit_pair(&empty_bar[stage]);
+#ifdef ADM_GEMM_TIMING
+                    const long long c3 = clock64();
+                    t_wait += c1 - c0; t_issue += c2 - c1; t_commit += c3 - c2;
+#endif
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
+#ifdef ADM_GEMM_TIMING
+                if (blockIdx.x == 0 && tile == first)
+                    printf("[pair mma thread] k-iters %d stages %d: wait %lld issue %lld commit %lld clocks per k-iter\n",
+                           p.k_total, num_stages, t_wait / p.k_total, t_issue / p.k_total, t_commit / p.k_total);
+#endif
                 umma_commit_pair(&tfull_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
