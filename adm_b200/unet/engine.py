@@ -220,6 +220,51 @@ class UNetEngine:
             else:
                 g.add_(tmp[:g.numel()])
 
+    def _dgrad(self, dy, conv, wpk, c1=None, c2=0, residual=None):
+        """Data gradient of `conv` in its INPUT channel count (the packed weights pad every source to 64 channels:
+        channel counts like 96 / 288 of the CelebAHQ-latent config come back padded and are cut here; a concat input
+        whose first part is not a multiple of 64 is re-joined)."""
+        cin = conv.weight.shape[1]
+        c1 = cin if c1 is None else c1
+        if c2 and c1 % 64:
+            full = ops.conv_dgrad(dy, wpk, residual=residual)
+            p1 = pad64(c1)
+            return torch.cat([full[..., :c1], full[..., p1:p1 + c2]], dim=-1)
+        return ops.conv_dgrad(dy, wpk, n_valid=c1 + c2, residual=residual)
+
+    # Attention heads whose width is not a multiple of 64 (d = 72 when C = 288 in the CelebAHQ-latent config; the head
+    # width is out_channels // 64 heads, uncond_unet.py:173): every head is zero-padded to dpad = pad64(d) INSIDE the
+    # projection weights — q.k and p.v are unchanged, the activations need no re-layout, and the tensor-core GEMMs keep
+    # their 64-wide K slabs.  Padded fp32 weights are derived with torch index ops (cached per parameter version).
+    def _head_rows(self, c, heads):
+        d = c // heads
+        which, hh, dd = torch.meshgrid(torch.arange(3), torch.arange(heads), torch.arange(d), indexing="ij")
+        return (hh * 3 * d + dd * 3 + which).to(self._dev())  # [3, heads, d] -> reference row of the qkv projection
+
+    def qkv_padded(self, blk):
+        c, heads = blk.out_channels, blk.num_heads
+        d, dpad = c // heads, pad64(c // heads)
+
+        def build(old):
+            rows = self._head_rows(c, heads)
+            w = torch.zeros(3, heads, dpad, c, device=self._dev(), dtype=F32)
+            w[:, :, :d] = blk.qkv.weight.detach().reshape(3 * c, c)[rows]
+            b = torch.zeros(3, heads, dpad, device=self._dev(), dtype=F32)
+            b[:, :, :d] = blk.qkv.bias.detach()[rows]
+            wpk = ops.pack_conv_weight(w.reshape(3 * heads * dpad, c, 1, 1), out=old[0] if old is not None else None)
+            return wpk, b.reshape(-1).contiguous(), rows
+        return self._cached(("qkvpad", id(blk)), [blk.qkv.weight, blk.qkv.bias], build)
+
+    def proj_padded(self, blk):
+        c, heads = blk.out_channels, blk.num_heads
+        d, dpad = c // heads, pad64(c // heads)
+
+        def build(old):
+            w = torch.zeros(c, heads, dpad, device=self._dev(), dtype=F32)
+            w[:, :, :d] = blk.proj.weight.detach().reshape(c, heads, d)
+            return ops.pack_conv_weight(w.reshape(c, heads * dpad, 1, 1), out=old)
+        return self._cached(("projpad", id(blk)), [blk.proj.weight], build)
+
     # ------------------------------------------------------------------------------------------ UNetBlock
     def block_fwd(self, blk, x1, x2, params, training, seed, save):
         c = NS(blk=blk, x1=x1, x2=x2, params=params, seed=seed)
@@ -244,15 +289,22 @@ class UNetEngine:
         c.h1 = ops.conv_fprop(c.a1, self.conv_w(blk.conv1), bias=blk.conv1.bias, residual=res)
         out = c.h1
         if blk.num_heads:
-            perm = self.qkv_perm(cout, blk.num_heads)
             c.sums2, c.a2 = ops.gn_forward(c.h1, None, blk.norm2.weight, blk.norm2.bias, _groups(cout), blk.norm2.eps,
                                            act=False)
-            bq = self._cached(("qkvb", id(blk)), [blk.qkv.bias],
-                              lambda old: blk.qkv.bias.detach()[perm[1]].contiguous() if old is None
-                              else torch.index_select(blk.qkv.bias.detach(), 0, perm[1], out=old))
-            c.qkv = ops.conv_fprop(c.a2, self.conv_w(blk.qkv, perm=perm[0]), bias=bq)
-            c.att, c.p = ops.attention_fwd(c.qkv, blk.num_heads, need_p=save is not None)
-            out = ops.conv_fprop(c.att, self.conv_w(blk.proj), bias=blk.proj.bias, residual=c.h1)
+            if (cout // blk.num_heads) % 64:  # head width 72 / 96: zero-padded heads
+                wq, bq, _ = self.qkv_padded(blk)
+                c.qkv = ops.conv_fprop(c.a2, wq, bias=bq)
+                c.att, c.p = ops.attention_fwd(c.qkv, blk.num_heads, scale=(cout // blk.num_heads) ** -0.5,
+                                               need_p=save is not None)
+                out = ops.conv_fprop(c.att, self.proj_padded(blk), bias=blk.proj.bias, residual=c.h1)
+            else:
+                perm = self.qkv_perm(cout, blk.num_heads)
+                bq = self._cached(("qkvb", id(blk)), [blk.qkv.bias],
+                                  lambda old: blk.qkv.bias.detach()[perm[1]].contiguous() if old is None
+                                  else torch.index_select(blk.qkv.bias.detach(), 0, perm[1], out=old))
+                c.qkv = ops.conv_fprop(c.a2, self.conv_w(blk.qkv, perm=perm[0]), bias=bq)
+                c.att, c.p = ops.attention_fwd(c.qkv, blk.num_heads, need_p=save is not None)
+                out = ops.conv_fprop(c.att, self.conv_w(blk.proj), bias=blk.proj.bias, residual=c.h1)
         if save is not None:
             save.append(c)
         return out
@@ -277,13 +329,34 @@ class UNetEngine:
         cin, cout = cin1 + cin2, blk.out_channels
         has_skip_conv = blk.skip is not None and blk.skip.weight is not None
         h1_sinks = [self._grad(blk.conv1.bias)] + ([self._grad(blk.skip.bias)] if has_skip_conv else [])
-        if blk.num_heads:
+        if blk.num_heads and (cout // blk.num_heads) % 64:
+            heads, d = blk.num_heads, cout // blk.num_heads
+            dpad = pad64(d)
+            wq, _, rows = self.qkv_padded(blk)
+            wp = self.proj_padded(blk)
+            # proj: weight gradient comes back in the padded column layout (head, dpad)
+            dwp = ops.conv_wgrad(dout, c.att, ntaps=1)  # [cout, 1, heads*dpad]
+            self._grad(blk.proj.weight).add_(
+                dwp[:, 0, :heads * dpad].reshape(cout, heads, dpad)[:, :, :d].reshape(blk.proj.weight.shape))
+            if not dout_bias_done:
+                self._bias_grad(blk.proj.bias, dout)
+            datt = ops.conv_dgrad(dout, wp)
+            dqkv = ops.attention_bwd(datt, c.qkv, c.p, heads, scale=d ** -0.5)
+            dwq = ops.conv_wgrad(dqkv, c.a2, ntaps=1)  # [3*heads*dpad, 1, pad64(cout)]
+            gq = dwq[:, 0, :cout].reshape(3, heads, dpad, cout)[:, :, :d]
+            self._grad(blk.qkv.weight).view(3 * cout, cout).index_add_(0, rows.reshape(-1), gq.reshape(-1, cout))
+            bsum = torch.zeros(3 * heads * dpad, device=dqkv.device, dtype=F32)
+            ops.col_sums(dqkv, bsum)
+            self._grad(blk.qkv.bias).index_add_(0, rows.reshape(-1), bsum.reshape(3, heads, dpad)[:, :, :d].reshape(-1))
+            da2 = ops.conv_dgrad(dqkv, wq, n_valid=cout)
+        elif blk.num_heads:
             perm = self.qkv_perm(cout, blk.num_heads)
             self._conv_param_grads(blk.proj, dout, c.att, bias_done=dout_bias_done)
-            datt = ops.conv_dgrad(dout, self.conv_w(blk.proj))
+            datt = self._dgrad(dout, blk.proj, self.conv_w(blk.proj))
             dqkv = ops.attention_bwd(datt, c.qkv, c.p, blk.num_heads)
             self._conv_param_grads(blk.qkv, dqkv, c.a2, perm=perm)
-            da2 = ops.conv_dgrad(dqkv, self.conv_w(blk.qkv, perm=perm[0]))
+            da2 = self._dgrad(dqkv, blk.qkv, self.conv_w(blk.qkv, perm=perm[0]))
+        if blk.num_heads:
             dh1, _ = ops.gn_bwd(da2, c.h1, None, c.sums2, blk.norm2.weight, blk.norm2.bias, _groups(cout),
                                 act=False, dgamma=self._grad(blk.norm2.weight),
                                 dbeta=self._grad(blk.norm2.bias), add=dout, add_mode=0,
@@ -294,17 +367,17 @@ class UNetEngine:
             h1_bias_done = dout_bias_done
         # h1 = conv1(a1) + b1 + skip(x)
         self._conv_param_grads(blk.conv1, dh1, c.a1, bias_done=h1_bias_done)
-        da1 = ops.conv_dgrad(dh1, self.conv_w(blk.conv1))
+        da1 = self._dgrad(dh1, blk.conv1, self.conv_w(blk.conv1))
         dh0, _ = ops.gn_bwd(da1, c.h0, None, c.sums1, blk.norm1.weight, blk.norm1.bias, _groups(cout),
                             params=c.params, act=True, drop_p=c.drop_p, seed=c.seed,
                             dgamma=self._grad(blk.norm1.weight), dbeta=self._grad(blk.norm1.bias), dparams=dparams,
                             dbias1=self._grad(blk.conv0.bias))
         # h0 = conv0(a0) + b0
         self._conv_param_grads(blk.conv0, dh0, c.a0, bias_done=True)
-        da0 = ops.conv_dgrad(dh0, self.conv_w(blk.conv0))
+        da0 = self._dgrad(dh0, blk.conv0, self.conv_w(blk.conv0))
         if has_skip_conv:
             self._conv_param_grads(blk.skip, dh1, c.x1, c.x2, bias_done=h1_bias_done)
-            add = ops.conv_dgrad(dh1, self.conv_w(blk.skip, cin1, cin2))
+            add = self._dgrad(dh1, blk.skip, self.conv_w(blk.skip, cin1, cin2), cin1, cin2)
             add_mode = 0
         else:
             add, add_mode = dh1, c.mode
@@ -398,7 +471,7 @@ class UNetEngine:
         self._grad(sa.k_conv.weight).add_(dscal[3:4].reshape(1, 1, 1, 1))
         self._grad(sa.k_conv.bias).add_(dscal[4:5])
         self._conv_param_grads(conv, dh, d.x)
-        return ops.conv_dgrad(dh, self.conv_w(conv), residual=dy)
+        return self._dgrad(dh, conv, self.conv_w(conv), residual=dy)
 
     # ------------------------------------------------------------------------------------------ whole network
     def _run_fwd(self, xin, c_noise, aug, training, tape):
@@ -488,7 +561,7 @@ class UNetEngine:
             o = items[pos]
             dfv = df[..., :c_img]
             self._conv_param_grads(o.conv, dfv, o.a, dy_cols=df)
-            da = ops.conv_dgrad(dfv, self.conv_w(o.conv))
+            da = self._dgrad(dfv, o.conv, self.conv_w(o.conv))
             # each kernel that produces the gradient at a block's output also accumulates its column sums into that
             # block's bias gradients (bias_sinks), so the decoder chain needs no separate col_sums passes
             sinks = self.bias_sinks(items[pos - 1].blk)

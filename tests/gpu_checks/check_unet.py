@@ -324,6 +324,18 @@ def unet_tiny():
     return ok and psnr >= 40
 
 
+# CelebAHQ-latent family (configs/celebahq/celeb_uncond_ddm_const_uncond_unet_ldm.yaml: model_channels 96, mult 1-2-3-4,
+# attention where C = 192 and 288 -> 3 heads of 64 and 4 heads of 72), reduced to three levels at 32x32 for the CPU oracle
+CELEB_SMALL = dict(img_resolution=32, img_channels=3, model_channels=96, channel_mult=[1, 2, 3], channel_mult_emb=4,
+                   num_blocks=1, attn_resolutions=[16, 8], dropout=0.0, augment_dim=9, label_dim=0)
+
+
+@case
+def unet_celeb_small():
+    ok, _, _ = _unet_case(dict(CELEB_SMALL), 4, 1, 0.999)
+    return ok
+
+
 @case
 def unet_cifar():
     from tests.golden.make_golden import CIFAR
