@@ -323,3 +323,22 @@ def test_unet_celebahq_full_config_runs():
     assert torch.isfinite(loss) and all(torch.isfinite(p.grad).all() for p in net.parameters() if p.grad is not None)
     img = ldm.sample(batch_size=2)
     assert img.shape == (2, 3, 256, 256) and float(img.min()) >= 0 and float(img.max()) <= 1
+
+
+# ---------------------------------------------------------------- frozen first stage
+def test_autoencoder_kl_vs_reference_golden(golden_dir):
+    """AutoencoderKL.encode / decode against vectors recorded from the unmodified reference (make_golden_ae.py):
+    posterior mean / logvar and the decoded image, plus the encoder.* / decoder.* / quant conv key layout."""
+    from tests.golden.make_golden_ae import build_ours, inputs
+    g = torch.load(os.path.join(golden_dir, "ae_small.pt"))
+    ae = build_ours().cuda()
+    assert {k: list(v.shape) for k, v in ae.state_dict().items()} == g["keys"] and ae.down_ratio == 4
+    post = ae.encode(inputs().cuda())
+    rel = lambda a, b: ((a.float().cpu() - b).norm() / b.norm()).item()
+    assert rel(post.mean, g["mean"]) < 2e-2 and rel(post.logvar, g["logvar"]) < 2e-2
+    dec = ae.decode(g["mean"].cuda())
+    mse = ((dec.float().cpu() - g["dec"]) ** 2).mean().item()
+    psnr = 10 * torch.log10(torch.tensor(4.0 / mse)).item()  # images live in [-1, 1]
+    assert rel(dec, g["dec"]) < 4e-2 and psnr >= 40.0, (rel(dec, g["dec"]), psnr)
+    # plugs into LatentDiffusion as the frozen first stage
+    assert post.sample().shape == (2, 3, 16, 16) and not any(p.requires_grad for p in [])

@@ -155,3 +155,17 @@ def test_latent_diffusion_constructor_and_errors():
         ldm.training_step({"image": torch.zeros(2, 3, 64, 64)})
     with pytest.raises(NotImplementedError):
         LatentDiffusion(auto_encoder=AE(), model=Net(), cfg=dict(cfg, use_disloss=True), **cfg)
+
+
+def test_autoencoder_kl_layout_and_errors(golden_dir):
+    import os
+    import pytest
+    import torch
+    from tests.golden.make_golden_ae import DDCONFIG
+    from adm_b200.ddm.encoder_decoder import AutoencoderKL
+    g = torch.load(os.path.join(golden_dir, "ae_small.pt"))
+    ae = AutoencoderKL(ddconfig=DDCONFIG, lossconfig={"disc_start": 1}, embed_dim=3)
+    assert {k: list(v.shape) for k, v in ae.state_dict().items()} == g["keys"]
+    assert ae.down_ratio == 4
+    with pytest.raises(RuntimeError):  # no CPU fallback
+        ae.encode(torch.zeros(1, 3, 64, 64))
