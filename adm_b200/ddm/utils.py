@@ -10,6 +10,9 @@ ALIASES = {
     "ddm.loss": "adm_b200.ddm.loss",
     "ddm.utils": "adm_b200.ddm.utils",
     "unet.uncond_unet": "adm_b200.unet.uncond_unet",
+    "unet.cond_unet": "adm_b200.unet.cond_unet",
+    "ddm.encoder_decoder": "adm_b200.ddm.encoder_decoder",
+    "ddm.ema": "adm_b200.ddm.ema",
 }
 
 

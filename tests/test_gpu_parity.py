@@ -342,3 +342,42 @@ def test_autoencoder_kl_vs_reference_golden(golden_dir):
     assert rel(dec, g["dec"]) < 4e-2 and psnr >= 40.0, (rel(dec, g["dec"]), psnr)
     # plugs into LatentDiffusion as the frozen first stage
     assert post.sample().shape == (2, 3, 16, 16) and not any(p.requires_grad for p in [])
+
+
+# ---------------------------------------------------------------- Trainer / Sampler shells + EMA
+def test_trainer_checkpoint_resume_and_ema_sampling(tmp_path):
+    from tests.golden.make_golden import TINY
+    from adm_b200.ddm.ddm_const import DDPM
+    from adm_b200.trainer import Sampler, Trainer
+    cfg = dict(image_size=[16, 16], sampling_timesteps=3, eps=1e-4, weighting_loss=True)
+    tcfg = {"trainer": {"warmup_iter": 4, "min_lr": 1e-6, "ema_update_after_step": 2, "ema_update_every": 2}}
+
+    def loader():
+        g = torch.Generator().manual_seed(0)
+        while True:
+            yield {"image": 2 * torch.rand(8, 3, 16, 16, generator=g) - 1}
+
+    def make(resume=0):
+        dpm = DDPM(model=CU_build(TINY), cfg=cfg, **cfg).cuda()
+        return Trainer(dpm, loader(), train_batch_size=8, gradient_accumulate_every=2, train_lr=1e-3,
+                       train_num_steps=6, save_and_sample_every=3, num_samples=4, results_folder=str(tmp_path),
+                       log_freq=100, resume_milestone=resume, cfg=tcfg)
+
+    tr = make()
+    tr.train()
+    assert tr.step == 6 and torch.isfinite(tr.last_loss) and (tmp_path / "model-2.pt").exists()
+    ck = torch.load(tmp_path / "model-2.pt", map_location="cpu", weights_only=False)
+    assert set(ck) == {"step", "model", "opt", "lr_scheduler", "ema", "scaler"} and ck["step"] == 6
+    assert any(k.startswith("ema_model.model.") for k in ck["ema"]) and "model.model.map_layer0.weight" in ck["model"]
+    # resume: parameters, step and optimizer moments come back
+    tr2 = make(resume=2)
+    assert tr2.step == 6 and tr2.step_fn.step_count == tr.step_fn.step_count
+    for (n, a), (_, b) in zip(tr.model.named_parameters(), tr2.model.named_parameters()):
+        assert torch.equal(a, b), n
+    assert torch.equal(tr.step_fn.m, tr2.step_fn.m)
+    # the EMA copy differs from the online weights and samples through its own engine caches
+    d = sum(float((a - b).abs().sum()) for a, b in zip(tr.ema.ema_model.parameters(), tr.model.parameters()))
+    assert d > 0
+    img = Sampler(DDPM(model=CU_build(TINY), cfg=cfg, **cfg).cuda(), batch_size=4, sample_num=6,
+                  ckpt_path=str(tmp_path / "model-2.pt"), use_ema=True).sample()
+    assert img.shape == (6, 3, 16, 16) and float(img.min()) >= 0 and float(img.max()) <= 1
