@@ -84,10 +84,26 @@ class DDPM(nn.Module):
         self.use_augment = g("use_augment", False)
         self.augment = None
         if self.use_augment:
-            from .augment import AugmentPipe
-            self.augment = AugmentPipe(p=0.15, xflip=1e8, yflip=1, scale=1, rotate_frac=1, aniso=1, translate_frac=1)
+            # AugmentPipe (ddm/augment.py:115-328, EDM's augmentation) is host-side data glue (SURVEY section 8 row a-4 /
+            # f-4): it is taken from the host project when that is importable, with the reference's arguments
+            # (ddm_const.py:179-180); `model.augment` can also be assigned any callable x -> (x_aug, labels [B, 9]).
+            self.augment = self._host_augment_pipe()
         if ckpt_path is not None:
             self.init_from_ckpt(ckpt_path, ignore_keys, only_model)
+
+    @staticmethod
+    def _host_augment_pipe():
+        import importlib
+        for name in ("ddm.augment", "ADM.ddm.augment"):
+            try:
+                mod = importlib.import_module(name)
+            except Exception:
+                continue
+            return mod.AugmentPipe(p=0.15, xflip=1e8, yflip=1, scale=1, rotate_frac=1, aniso=1, translate_frac=1)
+        raise NotImplementedError(
+            "use_augment=True needs the host project's AugmentPipe (ddm/augment.py of zacz08/ADM) on sys.path; "
+            "adm_b200 replaces the training-step / sampler hot path, not the data augmentation. "
+            "Set use_augment: False, or assign `model.augment` yourself.")
 
     # -------------------------------------------------------------------------------------------- checkpoints
     def init_from_ckpt(self, path, ignore_keys=list(), only_model=False, use_ema=False):

@@ -223,3 +223,22 @@ def test_yaml_config_builds_the_reference_surface():
                            ("ddm.encoder_decoder.AutoencoderKL", "adm_b200.ddm.encoder_decoder"),
                            ("ddm.ema.EMA", "adm_b200.ddm.ema"), ("unet.uncond_unet.EDMPrecond", "adm_b200.unet.uncond_unet")]:
         assert get_obj_by_name(ref_name).__module__ == ours
+
+
+def test_use_augment_needs_the_host_projects_pipe():
+    """use_augment: True (the reference CIFAR YAML) resolves the host project's ddm.augment.AugmentPipe; without it the
+    module says so instead of silently training without augmentation."""
+    import sys
+    import pytest
+    import torch
+    from adm_b200.ddm.ddm_const import DDPM
+
+    class Net(torch.nn.Module):
+        channels, self_condition = 3, None
+
+    cfg = dict(image_size=[32, 32], use_augment=True)
+    if "ddm.augment" not in sys.modules and not any(p.rstrip("/").endswith("reference") for p in sys.path):
+        with pytest.raises(NotImplementedError):
+            DDPM(model=Net(), cfg=cfg, **cfg)
+    d = DDPM(model=Net(), cfg=dict(image_size=[32, 32]), image_size=[32, 32])
+    assert d.augment is None and d.use_augment is False
