@@ -151,6 +151,46 @@ static int launch_pair(const CUtensorMap& a, const CUtensorMap& a2, const CUtens
     return 0;
 }
 
+// Halo conv launch (tc_conv_halo_kernel): plain persistent grid.
+static int launch_halo(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const GemmParams& p,
+                       cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             GEMM_SMEM_TOTAL);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return ADM_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    const long long tiles = 1LL * p.m_tiles * p.n_tiles;
+    if (tiles <= 0 || tiles > INT_MAX) {
+        set_error("conv: bad tile count %lld", tiles);
+        return ADM_ERR_SHAPE;
+    }
+    const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+    tc_conv_halo_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_TOTAL, stream>>>(a, a2, b, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("tc_conv_halo launch: %s", cudaGetErrorString(e));
+        return ADM_ERR_CUDA;
+    }
+    count_launch();
+    return 0;
+}
+
+// The halo kernel serves 3x3 convs whose images tile into 8 x 16 pixel boxes (the 32x32 and 16x16 levels).
+// ADM_CONV_HALO=0 falls back to the per-tap loads (experiments / A-B timing).
+static bool halo_ok(int ntaps, int h, int w) {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ADM_CONV_HALO");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1 && ntaps == 9 && w % 8 == 0 && h % 16 == 0;
+}
+
 // ADM_GEMM_PAIR=1 enables the cta_group::2 conv path.  It is OFF by default: measured on B200 it is ~6 % slower than the
 // single-CTA kernel on the CIFAR shapes (tools/bench_gemm_variants.py: 960 vs 1022 TF/s at 384->384 @16x16) although it
 // moves 30 % fewer bytes — these convs are not bound by L2 / shared-memory operand traffic.
@@ -247,7 +287,9 @@ int adm_conv_fprop(const void* x1, int c1, long long ld1, const void* x2, int c2
     if (c1 <= 0 || c1 % 8 || (x2 && (c2 <= 0 || c2 % 8))) { set_error("conv_fprop: channels must be multiples of 8"); return ADM_ERR_SHAPE; }
     GemmParams p;
     init_params(&p);
-    if (pick_box(n, h, w, 128, &p.bw, &p.bh, &p.bni)) { set_error("conv_fprop: unsupported H x W = %d x %d", h, w); return ADM_ERR_SHAPE; }
+    const bool halo = halo_ok(ntaps, h, w);
+    if (halo) { p.bw = 8; p.bh = 16; p.bni = 1; }
+    else if (pick_box(n, h, w, 128, &p.bw, &p.bh, &p.bni)) { set_error("conv_fprop: unsupported H x W = %d x %d", h, w); return ADM_ERR_SHAPE; }
     p.H = h; p.W = w;
     p.tiles_w = w / p.bw; p.tiles_h = h / p.bh;
     p.m_tiles = p.tiles_w * p.tiles_h * ((n + p.bni - 1) / p.bni);
@@ -261,17 +303,19 @@ int adm_conv_fprop(const void* x1, int c1, long long ld1, const void* x2, int c2
     p.C = out; p.ldc = ldc; p.bias = bias; p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = ldr;
     p.alpha = alpha; p.out_mode = out_mode;
     CUtensorMap ma, ma2, mb;
-    if (int e = nhwc_map(&ma, x1, c1, ld1, n, h, w, p.bw, p.bh, p.bni)) return e;
-    if (x2) { if (int e = nhwc_map(&ma2, x2, c2, ld2, n, h, w, p.bw, p.bh, p.bni)) return e; } else ma2 = ma;
+    const int abw = halo ? HALO_W : p.bw, abh = halo ? HALO_H : p.bh;  // A box: the tile, or the tile + its 3x3 halo
+    if (int e = nhwc_map(&ma, x1, c1, ld1, n, h, w, abw, abh, p.bni)) return e;
+    if (x2) { if (int e = nhwc_map(&ma2, x2, c2, ld2, n, h, w, abw, abh, p.bni)) return e; } else ma2 = ma;
     const long long kpad = 1LL * ntaps * p.cchunks * 64;
     const long long bd[2] = {kpad, nout};
     const long long bs[1] = {kpad};
     // CTA pairs: 256-pixel tiles, each CTA loading half of the weight rows (box BN/2) — when there are at least two
     // pixel tiles and the output mode is a plain store.
-    const bool pair = pair_enabled() && p.m_tiles >= 2 && p.bn % 16 == 0 && out_mode != OUT_F32_ATOMIC;
+    const bool pair = !halo && pair_enabled() && p.m_tiles >= 2 && p.bn % 16 == 0 && out_mode != OUT_F32_ATOMIC;
     const int bb[2] = {64, pair ? p.bn / 2 : p.bn};
     if (int e = encode_map(&mb, wpk, 2, bd, bs, bb)) return e;
     if (pair) return launch_pair(ma, ma2, mb, p, static_cast<cudaStream_t>(stream));
+    if (halo) return launch_halo(ma, ma2, mb, p, static_cast<cudaStream_t>(stream));
     return launch<GEMM_CONV>(ma, ma2, mb, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -283,7 +327,9 @@ int adm_conv_dgrad(const void* dy, int cout, long long ld_dy, int n, int h, int 
     if (kpad % 64) { set_error("conv_dgrad: kpad must be a multiple of 64"); return ADM_ERR_SHAPE; }
     GemmParams p;
     init_params(&p);
-    if (pick_box(n, h, w, 128, &p.bw, &p.bh, &p.bni)) { set_error("conv_dgrad: unsupported H x W = %d x %d", h, w); return ADM_ERR_SHAPE; }
+    const bool halo = halo_ok(ntaps, h, w);
+    if (halo) { p.bw = 8; p.bh = 16; p.bni = 1; }
+    else if (pick_box(n, h, w, 128, &p.bw, &p.bh, &p.bni)) { set_error("conv_dgrad: unsupported H x W = %d x %d", h, w); return ADM_ERR_SHAPE; }
     p.H = h; p.W = w;
     p.tiles_w = w / p.bw; p.tiles_h = h / p.bh;
     p.m_tiles = p.tiles_w * p.tiles_h * ((n + p.bni - 1) / p.bni);
@@ -297,11 +343,12 @@ int adm_conv_dgrad(const void* dy, int cout, long long ld_dy, int n, int h, int 
     p.C = dx; p.ldc = ldc; p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = ldr;
     p.alpha = alpha; p.out_mode = OUT_BF16;
     CUtensorMap ma, mb;
-    if (int e = nhwc_map(&ma, dy, cout, ld_dy, n, h, w, p.bw, p.bh, p.bni)) return e;
+    if (int e = nhwc_map(&ma, dy, cout, ld_dy, n, h, w, halo ? HALO_W : p.bw, halo ? HALO_H : p.bh, p.bni)) return e;
     const long long bd[3] = {kpad, ntaps, cout};
     const long long bs[2] = {kpad, 1LL * kpad * ntaps};
     const int bb[3] = {64, 1, 64};
     if (int e = encode_map(&mb, wpk, 3, bd, bs, bb)) return e;
+    if (halo) return launch_halo(ma, ma, mb, p, static_cast<cudaStream_t>(stream));
     return launch<GEMM_CONV>(ma, ma, mb, p, static_cast<cudaStream_t>(stream));
 }
 

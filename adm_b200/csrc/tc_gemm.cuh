@@ -51,7 +51,7 @@ struct GemmParams {
     long long ldr;
     float alpha;
     int out_mode;
-    int debug;  // experiments only (ADM_GEMM_DEBUG): bit 0 = skip the MMAs, bit 1 = skip the TMA loads
+    int debug;  // experiments only (ADM_GEMM_DEBUG): 1 = skip the MMAs, 2 = skip the TMA loads, 4 / 8 = load only B / only A
 };
 
 __device__ __forceinline__ void decode_pix(const GemmParams& p, int idx, int& n0, int& h0, int& w0) {
@@ -188,6 +188,55 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, uint32_t taddr
     }
 }
 
+// The epilogue warps' persistent loop (4 warps, one TMEM lane quadrant each): per tile, stage the bias slice, wait for
+// the accumulator, drain it through epilogue_row, release it.  Shared by tc_gemm_kernel and tc_conv_halo_kernel.
+template <int MODE>
+__device__ __forceinline__ void epilogue_warps(const GemmParams& p, uint8_t* smem, uint32_t tmem_base,
+                                               uint64_t* tfull_bar, uint64_t* tempty_bar, int warp, int lane,
+                                               int num_tiles) {
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;  // row inside the tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        int r = tile / p.n_tiles;
+        const int mt = r % p.m_tiles;
+        r /= p.m_tiles;
+        const int bt = r / p.splits;
+        const int b_hi = bt / p.bdiv, b_lo = bt % p.bdiv;
+
+        long long row_off;  // element offset of this thread's output row (before column)
+        bool row_ok;
+        if (MODE == GEMM_CONV) {
+            int n0, h0, w0;
+            decode_pix(p, mt, n0, h0, w0);
+            const int wi = m % p.bw, hi = (m / p.bw) % p.bh, ni = m / (p.bw * p.bh);
+            const long long pix = (static_cast<long long>(n0 + ni) * p.H + (h0 + hi)) * p.W + (w0 + wi);
+            row_ok = pix < p.M;
+            row_off = pix;
+        } else {
+            const int row = mt * 128 + m;
+            row_ok = row < p.M;
+            row_off = row;
+        }
+        const long long c_base = b_hi * p.c_bhi + b_lo * p.c_blo + row_off * p.ldc;
+        const int col_base = nt * p.bn;           // column inside [0, N)
+        const int col_shift = b_lo * p.c_col_lo;  // extra offset in the output row
+
+        float* sbias = reinterpret_cast<float*>(smem + GEMM_SMEM_RING + 1024) + acc * 256;
+        stage_bias(p, sbias, col_base, m);
+        mbar_wait(&tfull_bar[acc], acc_phase, 4);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(quad * 32) << 16);
+        epilogue_row(p, taddr, col_base, col_shift, c_base, row_off * p.ldr, row_ok, sbias);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
@@ -253,6 +302,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint8_t* sb = sa + GEMM_A_STAGE;
                     if (p.debug & 2) {
                         mbar_arrive(&full_bar[stage]);
+                        if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
+                    if (MODE == GEMM_CONV && (p.debug & 12)) {  // experiments: load only B (4) or only A (8)
+                        const int tap = ki / p.cchunks, kc = ki % p.cchunks;
+                        if ((p.debug & 4) && ki - k_begin >= num_stages) {  // (first ring pass loads A too)
+                            mbar_expect_tx(&full_bar[stage], p.bn * 128);
+                            tma_load_2d(sb, &tmB, &full_bar[stage], ki * 64, nt * p.bn);
+                        } else if (p.debug & 4) {
+                            mbar_expect_tx(&full_bar[stage], stage_bytes);
+                            tma_load_4d(sa, &tmA, &full_bar[stage], kc * 64, w0 + tap % 3 - 1, h0 + tap / 3 - 1, n0);
+                            tma_load_2d(sb, &tmB, &full_bar[stage], ki * 64, nt * p.bn);
+                        } else {
+                            mbar_expect_tx(&full_bar[stage], GEMM_A_STAGE);
+                            tma_load_4d(sa, &tmA, &full_bar[stage], kc * 64, w0 + tap % 3 - 1, h0 + tap / 3 - 1, n0);
+                        }
                         if (++stage == num_stages) { stage = 0; phase ^= 1; }
                         continue;
                     }
@@ -370,47 +435,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // =========================================================== epilogue (4 warps, one TMEM lane quadrant each)
-        const int quad = warp & 3;
-        const int m = quad * 32 + lane;  // row inside the tile
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int nt = tile % p.n_tiles;
-            int r = tile / p.n_tiles;
-            const int mt = r % p.m_tiles;
-            r /= p.m_tiles;
-            const int bt = r / p.splits;
-            const int b_hi = bt / p.bdiv, b_lo = bt % p.bdiv;
-
-            long long row_off;  // element offset of this thread's output row (before column)
-            bool row_ok;
-            if (MODE == GEMM_CONV) {
-                int n0, h0, w0;
-                decode_pix(p, mt, n0, h0, w0);
-                const int wi = m % p.bw, hi = (m / p.bw) % p.bh, ni = m / (p.bw * p.bh);
-                const long long pix = (static_cast<long long>(n0 + ni) * p.H + (h0 + hi)) * p.W + (w0 + wi);
-                row_ok = pix < p.M;
-                row_off = pix;
-            } else {
-                const int row = mt * 128 + m;
-                row_ok = row < p.M;
-                row_off = row;
-            }
-            const long long c_base = b_hi * p.c_bhi + b_lo * p.c_blo + row_off * p.ldc;
-            const int col_base = nt * p.bn;           // column inside [0, N)
-            const int col_shift = b_lo * p.c_col_lo;  // extra offset in the output row
-
-            float* sbias = reinterpret_cast<float*>(smem + GEMM_SMEM_RING + 1024) + acc * 256;
-            stage_bias(p, sbias, col_base, m);
-            mbar_wait(&tfull_bar[acc], acc_phase, 4);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(quad * 32) << 16);
-            epilogue_row(p, taddr, col_base, col_shift, c_base, row_off * p.ldr, row_ok, sbias);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        }
+        epilogue_warps<MODE>(p, smem, tmem_base, tfull_bar, tempty_bar, warp, lane, num_tiles);
     }
 
     tc_fence_before();
@@ -590,6 +615,163 @@ tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ halo conv kernel
+// 3x3 implicit-GEMM conv whose pixel operand is loaded ONCE per 64-channel chunk instead of once per tap.  The pixel
+// tile is 8 (w) x 16 (h); its 10 x 18 halo (zero-filled outside the image by TMA) lands in shared memory as 180 rows of
+// 128 B.  A tap (dy, dx) is then just a shifted window of that halo: the UMMA A descriptor starts at row dy*10 + dx and
+// walks its sixteen 8-row groups (= pixel rows of the tile) SBO = 10 rows apart.  The 128B-swizzle XOR is a function of
+// the absolute shared-memory address on both the TMA and the UMMA side, so an unaligned start and a group stride that
+// is not a multiple of 1024 B read back exactly what TMA wrote (tools/exp/umma_row_offset.cu, measured on B200).
+// Per k-iteration (one tap x 64 channels) the SM ingests bn*128 B of weights + 23 KB / 9 of pixels instead of
+// bn*128 B + 16 KB: -34 % for bn = 192.  K order is chunk-major (chunk, tap) — the weight TMA coordinates follow.
+// Roles, accumulators and the epilogue are those of tc_gemm_kernel; two rings replace the single one:
+//   halo ring  : HALO_BUFS buffers, filled one chunk step AHEAD (across tiles), released by a commit after the 9th tap
+//   weight ring: as many bn*128 B stages as fit beside it
+constexpr int HALO_W = 10, HALO_H = 18;
+constexpr int HALO_TX_BYTES = HALO_W * HALO_H * 128;  // 23040
+constexpr int HALO_BYTES = 23 * 1024;                 // buffer pitch, 1024-aligned
+constexpr int HALO_BUFS = 3;
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_bytes = p.bn * 128;
+    int nb = (GEMM_SMEM_RING - HALO_BUFS * HALO_BYTES) / b_bytes;
+    if (nb > GEMM_MAX_STAGES) nb = GEMM_MAX_STAGES;
+    uint8_t* b_ring = smem + HALO_BUFS * HALO_BYTES;
+
+    uint64_t* bfull = reinterpret_cast<uint64_t*>(smem + GEMM_SMEM_RING);
+    uint64_t* bempty = bfull + GEMM_MAX_STAGES;
+    uint64_t* tfull_bar = bempty + GEMM_MAX_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint64_t* hfull = tempty_bar + 2;
+    uint64_t* hempty = hfull + HALO_BUFS;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(hempty + HALO_BUFS);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmA2);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < nb; ++i) {
+            mbar_init(&bfull[i], 1);
+            mbar_init(&bempty[i], 1);
+        }
+        for (int i = 0; i < HALO_BUFS; ++i) {
+            mbar_init(&hfull[i], 1);
+            mbar_init(&hempty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 4);
+        }
+        fence_barrier_init();
+        fence_proxy_async_smem();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int num_tiles = p.m_tiles * p.n_tiles;
+
+    if (warp == 0) {
+        // =========================================================== TMA producer
+        if (lane == 0) {
+            int hs = 0, bs = 0;
+            uint32_t hphase = 0, bphase = 0;
+            auto load_halo = [&](int tile, int kc) {
+                int n0, h0, w0;
+                decode_pix(p, (tile / p.n_tiles) % p.m_tiles, n0, h0, w0);
+                mbar_wait(&hempty[hs], hphase ^ 1, 5);
+                mbar_expect_tx(&hfull[hs], HALO_TX_BYTES);
+                uint8_t* dst = smem + hs * HALO_BYTES;
+                if (kc < p.cchunks1)
+                    tma_load_4d(dst, &tmA, &hfull[hs], kc * 64, w0 - 1, h0 - 1, n0);
+                else
+                    tma_load_4d(dst, &tmA2, &hfull[hs], (kc - p.cchunks1) * 64, w0 - 1, h0 - 1, n0);
+                if (++hs == HALO_BUFS) { hs = 0; hphase ^= 1; }
+            };
+            if (static_cast<int>(blockIdx.x) < num_tiles) load_halo(blockIdx.x, 0);
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles;
+                for (int kc = 0; kc < p.cchunks; ++kc) {
+                    // the NEXT chunk step's halo goes out before this step's nine weight tiles
+                    if (kc + 1 < p.cchunks)
+                        load_halo(tile, kc + 1);
+                    else if (tile + static_cast<int>(gridDim.x) < num_tiles)
+                        load_halo(tile + gridDim.x, 0);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&bempty[bs], bphase ^ 1, 1);
+                        uint8_t* sb = b_ring + bs * b_bytes;
+                        mbar_expect_tx(&bfull[bs], b_bytes);
+                        if (!p.b_mn) {
+                            tma_load_2d(sb, &tmB, &bfull[bs], (tap * p.cchunks + kc) * 64, nt * p.bn);
+                        } else {
+                            for (int c = 0; c * 64 < p.bn; ++c)
+                                tma_load_3d(sb + c * 8192, &tmB, &bfull[bs], nt * p.bn + c * 64, 8 - tap, kc * 64);
+                        }
+                        if (++bs == nb) { bs = 0; bphase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================================================== UMMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, p.bn, 0, p.b_mn);
+            const uint32_t b_lbo = p.b_mn ? 8192u : 16u;
+            const uint32_t b_kstep = p.b_mn ? 2048u : 32u;
+            int hs = 0, bs = 0;
+            uint32_t hphase = 0, bphase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * 256;
+                for (int kc = 0; kc < p.cchunks; ++kc) {
+                    mbar_wait(&hfull[hs], hphase, 6);
+                    tc_fence_after();
+                    const uint32_t halo = smem_u32(smem + hs * HALO_BYTES);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&bfull[bs], bphase, 3);
+                        tc_fence_after();
+                        const uint32_t sa = halo + ((tap / 3) * HALO_W + tap % 3) * 128;
+                        const uint32_t sb = smem_u32(b_ring + bs * b_bytes);
+#pragma unroll
+                        for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+                            const uint64_t da = make_smem_desc(sa + k * 32, 16, HALO_W * 128);
+                            const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
+                            umma_bf16(tmem_d, da, db, idesc, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit(&bempty[bs]);
+                        if (++bs == nb) { bs = 0; bphase ^= 1; }
+                    }
+                    umma_commit(&hempty[hs]);
+                    if (++hs == HALO_BUFS) { hs = 0; hphase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        epilogue_warps<GEMM_CONV>(p, smem, tmem_base, tfull_bar, tempty_bar, warp, lane, num_tiles);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
     }
 }
 

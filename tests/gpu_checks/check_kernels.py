@@ -96,7 +96,7 @@ def conv_fprop_3x3():
     torch.manual_seed(2)
     ok = True
     for (n, hw, cin, cout) in [(2, 16, 64, 192), (1, 32, 128, 96), (8, 8, 192, 384), (16, 4, 64, 192), (3, 16, 64, 48),
-                               (2, 32, 8, 192)]:
+                               (2, 32, 8, 192), (3, 32, 192, 256), (5, 16, 384, 384)]:
         x = _bf(torch.randn(n, hw, hw, cin, device="cuda"))
         w = _bf(torch.randn(cout, cin, 3, 3, device="cuda") / (3 * cin ** 0.5)).float()
         bias = torch.randn(cout, device="cuda")
@@ -146,7 +146,7 @@ def conv_dgrad_wgrad():
     torch.manual_seed(4)
     ok = True
     for (n, hw, cin, cout, k) in [(2, 16, 64, 128, 3), (8, 8, 192, 384, 3), (16, 4, 128, 64, 3), (2, 32, 64, 192, 1),
-                                  (4, 16, 128, 3, 3)]:
+                                  (4, 16, 128, 3, 3), (3, 32, 192, 192, 3), (5, 16, 384, 256, 3)]:
         x = _bf(torch.randn(n, hw, hw, cin, device="cuda"))
         w = _bf(torch.randn(cout, cin, k, k, device="cuda") / (k * cin ** 0.5)).float()
         ldy = (cout + 7) // 8 * 8
