@@ -180,6 +180,65 @@ static int launch_halo(const CUtensorMap& a, const CUtensorMap& a2, const CUtens
     return 0;
 }
 
+static int launch_wgrad_rows(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& b2, const GemmParams& p,
+                             cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_wgrad_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             GEMM_SMEM_TOTAL);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return ADM_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    const long long tiles = 1LL * p.splits * p.m_tiles * p.n_tiles;
+    if (tiles <= 0 || tiles > INT_MAX) {
+        set_error("wgrad: bad tile count %lld", tiles);
+        return ADM_ERR_SHAPE;
+    }
+    const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+    tc_wgrad_rows_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_TOTAL, stream>>>(a, b, b2, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("tc_wgrad_rows launch: %s", cudaGetErrorString(e));
+        return ADM_ERR_CUDA;
+    }
+    count_launch();
+    return 0;
+}
+
+// ADM_WGRAD_ROWS=0 falls back to the per-tap wgrad tiles (experiments / A-B timing).
+static bool wgrad_rows_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ADM_WGRAD_ROWS");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+// split K (pixels) for the wgrad kernels: the split that minimises waves x (k-iterations per tile + epilogue cost) on
+// the persistent grid — fewer, fuller waves beat "more tiles" (wave quantisation), fewer splits mean fewer atomics.
+static void pick_wgrad_split(GemmParams* p, int base_tiles, int epi) {
+    const int sms = num_sms();
+    long long best_cost = -1;
+    int best_s = 1;
+    for (int s = 1; s <= p->k_total && s <= 64; ++s) {
+        const int k_per = (p->k_total + s - 1) / s;
+        const int s_eff = (p->k_total + k_per - 1) / k_per;
+        const long long waves = (1LL * base_tiles * s_eff + sms - 1) / sms;
+        const long long cost = waves * (k_per + epi);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = s_eff; }
+    }
+    if (const char* e = getenv("ADM_WGRAD_SPLITS")) {  // experiments: force the split count
+        const int s = atoi(e);
+        if (s >= 1 && s <= p->k_total) best_s = s;
+    }
+    p->k_iters = (p->k_total + best_s - 1) / best_s;
+    p->splits = (p->k_total + p->k_iters - 1) / p->k_iters;
+}
+
 // The halo kernel serves 3x3 convs whose images tile into 8 x 16 pixel boxes (the 32x32 and 16x16 levels).
 // ADM_CONV_HALO=0 falls back to the per-tap loads (experiments / A-B timing).
 static bool halo_ok(int ntaps, int h, int w) {
@@ -366,6 +425,24 @@ int adm_conv_wgrad(const void* dy, int cout, long long ld_dy, const void* x1, in
     p.k_total = p.tiles_w * p.tiles_h * ((n + p.bni - 1) / p.bni);
     const int kpad = pad64(c1) + (x2 ? pad64(c2) : 0);
     p.M = cout; p.N = kpad;
+    if (ntaps == 9 && wgrad_rows_enabled() && p.bni == 1 && (p.bw == 8 || p.bw % 16 == 0)) {
+        // tap-row kernel: M chunks = (dy, 64-channel dY chunk), N = the three dx taps of one 64-channel X chunk
+        p.co_chunks = pad64(cout) / 64;
+        p.m_tiles = (3 * p.co_chunks + 1) / 2;
+        p.n_tiles = kpad / 64;
+        p.cchunks1 = pad64(c1) / 64;
+        p.bn = 192;
+        p.ntaps = 9;
+        p.a_mn = 1; p.b_mn = 1;
+        p.c_col_lo = kpad;
+        pick_wgrad_split(&p, p.m_tiles * p.n_tiles, 8);
+        p.C = dw; p.ldc = 9LL * kpad; p.out_mode = OUT_F32_ATOMIC;
+        CUtensorMap ma, mb, mb2;
+        if (int e = nhwc_map(&ma, dy, cout, ld_dy, n, h, w, p.bw, p.bh, 1)) return e;
+        if (int e = nhwc_map(&mb, x1, c1, ld1, n, h, w, p.bw + 2, p.bh, 1)) return e;
+        if (x2) { if (int e = nhwc_map(&mb2, x2, c2, ld2, n, h, w, p.bw + 2, p.bh, 1)) return e; } else mb2 = mb;
+        return launch_wgrad_rows(ma, mb, mb2, p, static_cast<cudaStream_t>(stream));
+    }
     p.m_tiles = (cout + 127) / 128;
     p.bn = x2 ? pick_bn(pad64(c1), 256, 64) : pick_bn(kpad, 256, 64);
     if (x2 && pad64(c2) % p.bn) p.bn = 64;
@@ -374,24 +451,7 @@ int adm_conv_wgrad(const void* dy, int cout, long long ld_dy, const void* x1, in
     p.ntaps = ntaps;
     p.batches = ntaps; p.bdiv = ntaps; p.c_col_lo = kpad;
     p.a_mn = 1; p.b_mn = 1;
-    // split K (pixels): pick the split that minimises waves x (k-iterations per tile + epilogue cost) for the
-    // persistent grid — fewer, fuller waves beat "more tiles" (wave quantisation), and fewer splits mean fewer atomics.
-    const int base_tiles = ntaps * p.m_tiles * p.n_tiles;
-    {
-        const int sms = num_sms();
-        const int epi = 6;  // epilogue cost of one tile in k-iteration units (fp32 vector atomics)
-        long long best_cost = -1;
-        int best_s = 1;
-        for (int s = 1; s <= p.k_total && s <= 64; ++s) {
-            const int k_per = (p.k_total + s - 1) / s;
-            const int s_eff = (p.k_total + k_per - 1) / k_per;
-            const long long waves = (1LL * base_tiles * s_eff + sms - 1) / sms;
-            const long long cost = waves * (k_per + epi);
-            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = s_eff; }
-        }
-        p.k_iters = (p.k_total + best_s - 1) / best_s;
-        p.splits = (p.k_total + p.k_iters - 1) / p.k_iters;
-    }
+    pick_wgrad_split(&p, ntaps * p.m_tiles * p.n_tiles, 6);  // epilogue ~ 6 k-iterations (fp32 vector atomics)
     p.C = dw; p.ldc = 1LL * ntaps * kpad; p.out_mode = OUT_F32_ATOMIC;
     (void)pixels;
     CUtensorMap ma, mb, mb2;

@@ -38,6 +38,7 @@ struct GemmParams {
     int cchunks;   // 64-channel chunks per tap (both A sources)
     int cchunks1;  // chunks taken from A source 1; the rest come from A source 2 (fused channel concat)
     int n_split;   // wgrad: output columns (per tap) served by X source 1; the rest by X source 2
+    int co_chunks; // tap-row wgrad: 64-channel chunks of dY (M chunks = 3 dy x co_chunks)
     // ---- plain / batched coordinates: bt -> (b_hi = bt / bdiv, b_lo = bt % bdiv)
     int bdiv;
     int a_c0, a_c0_lo, a_c1, a_c1_lo, a_bhi, a_blo;
@@ -51,7 +52,7 @@ struct GemmParams {
     long long ldr;
     float alpha;
     int out_mode;
-    int debug;  // experiments only (ADM_GEMM_DEBUG): 1 = skip the MMAs, 2 = skip the TMA loads, 4 / 8 = load only B / only A
+    int debug;  // experiments only (ADM_GEMM_DEBUG): bit 0 = skip the MMAs, bit 1 = skip the TMA loads
 };
 
 __device__ __forceinline__ void decode_pix(const GemmParams& p, int idx, int& n0, int& h0, int& w0) {
@@ -61,6 +62,21 @@ __device__ __forceinline__ void decode_pix(const GemmParams& p, int idx, int& n0
     h0 = (r / p.tiles_w) * p.bh;
     w0 = (r % p.tiles_w) * p.bw;
 }
+
+// Pixel-box coordinates of consecutive k-iterations without per-iteration divisions (the producer is ONE thread: a few
+// runtime integer divisions per k-iteration are a measurable share of its budget).
+struct PixWalker {
+    int n0, h0, w0;
+    __device__ __forceinline__ PixWalker(const GemmParams& p, int idx) { decode_pix(p, idx, n0, h0, w0); }
+    __device__ __forceinline__ void advance(const GemmParams& p) {
+        w0 += p.bw;
+        if (w0 >= p.W) {
+            w0 = 0;
+            h0 += p.bh;
+            if (h0 >= p.H) { h0 = 0; n0 += p.bni; }
+        }
+    }
+};
 
 // The four epilogue warps stage the tile's bias slice (bn <= 256 floats, zero beyond N) in shared memory BEFORE waiting
 // for the accumulator: per-chunk __ldg of the bias missed L1 behind the streaming stores and cost ~30 us on the
@@ -80,12 +96,13 @@ __device__ __forceinline__ void stage_bias(const GemmParams& p, float* sbias, in
 // then alpha * acc + bias + residual -> bf16 / fp32 / fp32 atomics.  c_off / r_off: element offsets of this row in the
 // output and the residual (before the column); col_shift: extra output column offset (batched GEMMs).
 __device__ __forceinline__ void epilogue_row(const GemmParams& p, uint32_t taddr, int col_base, int col_shift,
-                                             long long c_off, long long r_off, bool row_ok, const float* sbias) {
-    for (int c0 = 0; c0 < p.bn; c0 += 64) {
+                                             long long c_off, long long r_off, bool row_ok, const float* sbias,
+                                             int ncols) {
+    for (int c0 = 0; c0 < ncols; c0 += 64) {
         if (col_base + c0 >= p.N) break;  // warp-uniform
         uint32_t v[4][16];
         uint4 rr[4][2];
-        const int nsub = min(4, (p.bn - c0) >> 4);
+        const int nsub = min(4, (ncols - c0) >> 4);
         __syncwarp();
 #pragma unroll
         for (int s = 0; s < 4; ++s)
@@ -229,7 +246,7 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, uint8_t* sme
         mbar_wait(&tfull_bar[acc], acc_phase, 4);
         tc_fence_after();
         const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(quad * 32) << 16);
-        epilogue_row(p, taddr, col_base, col_shift, c_base, row_off * p.ldr, row_ok, sbias);
+        epilogue_row(p, taddr, col_base, col_shift, c_base, row_off * p.ldr, row_ok, sbias, p.bn);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -296,6 +313,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 int n0 = 0, h0 = 0, w0 = 0;
                 if (MODE == GEMM_CONV) decode_pix(p, mt, n0, h0, w0);
                 const int b_hi = bt / p.bdiv, b_lo = bt % p.bdiv;
+                int tap = 0, kc = 0;  // conv: ki = tap * cchunks + kc, walked without divisions
+                if (MODE == GEMM_CONV) { tap = k_begin / p.cchunks; kc = k_begin % p.cchunks; }
+                PixWalker px(p, MODE == GEMM_WGRAD ? k_begin : 0);
                 for (int ki = k_begin; ki < k_end; ++ki) {
                     mbar_wait(&empty_bar[stage], phase ^ 1, 1);
                     uint8_t* sa = smem + stage * stage_bytes;
@@ -305,25 +325,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (++stage == num_stages) { stage = 0; phase ^= 1; }
                         continue;
                     }
-                    if (MODE == GEMM_CONV && (p.debug & 12)) {  // experiments: load only B (4) or only A (8)
-                        const int tap = ki / p.cchunks, kc = ki % p.cchunks;
-                        if ((p.debug & 4) && ki - k_begin >= num_stages) {  // (first ring pass loads A too)
-                            mbar_expect_tx(&full_bar[stage], p.bn * 128);
-                            tma_load_2d(sb, &tmB, &full_bar[stage], ki * 64, nt * p.bn);
-                        } else if (p.debug & 4) {
-                            mbar_expect_tx(&full_bar[stage], stage_bytes);
-                            tma_load_4d(sa, &tmA, &full_bar[stage], kc * 64, w0 + tap % 3 - 1, h0 + tap / 3 - 1, n0);
-                            tma_load_2d(sb, &tmB, &full_bar[stage], ki * 64, nt * p.bn);
-                        } else {
-                            mbar_expect_tx(&full_bar[stage], GEMM_A_STAGE);
-                            tma_load_4d(sa, &tmA, &full_bar[stage], kc * 64, w0 + tap % 3 - 1, h0 + tap / 3 - 1, n0);
-                        }
-                        if (++stage == num_stages) { stage = 0; phase ^= 1; }
-                        continue;
-                    }
                     mbar_expect_tx(&full_bar[stage], stage_bytes);
                     if (MODE == GEMM_CONV) {
-                        const int tap = ki / p.cchunks, kc = ki % p.cchunks;
                         int dh = 0, dw = 0;
                         if (p.ntaps == 9) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
                         if (kc < p.cchunks1)
@@ -340,9 +343,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 tma_load_3d(sb + c * 8192, &tmB, &full_bar[stage], nt * p.bn + c * 64,
                                             p.ntaps - 1 - tap, kc * 64);
                         }
+                        if (++kc == p.cchunks) { kc = 0; ++tap; }
                     } else if (MODE == GEMM_WGRAD) {
                         // K runs over pixel blocks of 64; bt = tap.  A = dY (MN-major), B = shifted X (MN-major).
-                        decode_pix(p, ki, n0, h0, w0);
+                        n0 = px.n0; h0 = px.h0; w0 = px.w0;
+                        px.advance(p);
                         int dh = 0, dw = 0;
                         if (p.ntaps == 9) { dh = bt / 3 - 1; dw = bt % 3 - 1; }
                         tma_load_4d(sa, &tmA, &full_bar[stage], mt * 128, w0, h0, n0);
@@ -382,7 +387,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, p.bn, p.a_mn, p.b_mn);
             const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
-            const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
+            // descriptor constants and k-step strides (in 16 B units) are hoisted: this thread's instruction stream is
+            // the critical path of the main loop
+            const uint32_t a_kstep = (p.a_mn ? 2048u : 32u) >> 4, b_kstep = (p.b_mn ? 2048u : 32u) >> 4;
+            const uint64_t da0 = make_smem_desc(0, a_lbo, 1024), db0 = make_smem_desc(0, b_lbo, 1024);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -406,14 +414,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #ifdef ADM_GEMM_TIMING
                     const long long c1 = clock64();
 #endif
-                    const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-                    const uint32_t sb = sa + GEMM_A_STAGE;
+                    const uint32_t sa16 = smem_u32(smem + stage * stage_bytes) >> 4;
+                    const uint64_t da = da0 + sa16, db = db0 + (sa16 + (GEMM_A_STAGE >> 4));
 #pragma unroll
-                    for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
-                        const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
-                        const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-                        if (!(p.debug & 1)) umma_bf16(tmem_d, da, db, idesc, (ki > k_begin || k > 0) ? 1u : 0u);
-                    }
+                    for (int k = 0; k < GEMM_BLOCK_K / 16; ++k)
+                        if (!(p.debug & 1))
+                            umma_bf16(tmem_d, da + k * a_kstep, db + k * b_kstep, idesc, (ki > k_begin || k > 0) ? 1u : 0u);
 #ifdef ADM_GEMM_TIMING
                     const long long c2 = clock64();
 #endif
@@ -601,7 +607,7 @@ tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_wait(&tfull_bar[acc], acc_phase, 4);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(quad * 32) << 16);
-            epilogue_row(p, taddr, col_base, 0, c_base, pix * p.ldr, row_ok, sbias);
+            epilogue_row(p, taddr, col_base, 0, c_base, pix * p.ldr, row_ok, sbias, p.bn);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
@@ -729,7 +735,8 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, p.bn, 0, p.b_mn);
             const uint32_t b_lbo = p.b_mn ? 8192u : 16u;
-            const uint32_t b_kstep = p.b_mn ? 2048u : 32u;
+            const uint32_t b_kstep = (p.b_mn ? 2048u : 32u) >> 4;
+            const uint64_t da0 = make_smem_desc(0, 16, HALO_W * 128), db0 = make_smem_desc(0, b_lbo, 1024);
             int hs = 0, bs = 0;
             uint32_t hphase = 0, bphase = 0;
             int acc = 0;
@@ -741,18 +748,16 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int kc = 0; kc < p.cchunks; ++kc) {
                     mbar_wait(&hfull[hs], hphase, 6);
                     tc_fence_after();
-                    const uint32_t halo = smem_u32(smem + hs * HALO_BYTES);
+                    const uint64_t da_halo = da0 + (smem_u32(smem + hs * HALO_BYTES) >> 4);
+#pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         mbar_wait(&bfull[bs], bphase, 3);
                         tc_fence_after();
-                        const uint32_t sa = halo + ((tap / 3) * HALO_W + tap % 3) * 128;
-                        const uint32_t sb = smem_u32(b_ring + bs * b_bytes);
+                        const uint64_t da = da_halo + ((tap / 3) * HALO_W + tap % 3) * 8;  // (128 B rows) >> 4
+                        const uint64_t db = db0 + (smem_u32(b_ring + bs * b_bytes) >> 4);
 #pragma unroll
-                        for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
-                            const uint64_t da = make_smem_desc(sa + k * 32, 16, HALO_W * 128);
-                            const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-                            umma_bf16(tmem_d, da, db, idesc, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
-                        }
+                        for (int k = 0; k < GEMM_BLOCK_K / 16; ++k)
+                            umma_bf16(tmem_d, da + 2 * k, db + k * b_kstep, idesc, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
                         umma_commit(&bempty[bs]);
                         if (++bs == nb) { bs = 0; bphase ^= 1; }
                     }
@@ -765,6 +770,170 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else {
         epilogue_warps<GEMM_CONV>(p, smem, tmem_base, tfull_bar, tempty_bar, warp, lane, num_tiles);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ tap-row wgrad kernel
+// 3x3 weight gradient  dW[co][dy][dx][ci] = sum_q dY[q - (dy-1, 0)][co] * X[q + (0, dx-1)][ci]  with the vertical shift
+// on the dY side and the horizontal shift on the X side, so that
+//   * N = 192 = the THREE dx taps of one 64-channel X chunk, read as three windows of ONE w-halo tile (bw+2 pixels per
+//     row): the MN-major B descriptor's chunk stride (LBO) is a single 128 B row — one MMA covers three taps;
+//   * M = 128 = two (dy, 64-channel dY chunk) pairs, each an ordinary 64-pixel box loaded with its own vertical offset
+//     (zero outside the image): Cout = 192 gives 9 M chunks = 4.5 tiles instead of 9 x 2 half-empty ones.
+// Per k-iteration (64 pixels) an SM ingests 16 KB + ~9 KB for 128 x 192 x 64 MACs, against 16 KB + 24 KB per tap before.
+// K = pixels (split across CTAs, fp32 atomics into the gradient arena), roles as in tc_gemm_kernel.
+// K = pixels (split across CTAs, fp32 atomics into the gradient arena), roles as in tc_gemm_kernel.
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+tc_wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int halo_w = p.bw + 2;
+    const int b_tx = p.bh * halo_w * 128;
+    const int stage_bytes = GEMM_A_STAGE + ((b_tx + 1023) & ~1023);
+    int num_stages = GEMM_SMEM_RING / stage_bytes;
+    if (num_stages > GEMM_MAX_STAGES) num_stages = GEMM_MAX_STAGES;
+
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + GEMM_SMEM_RING);
+    uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
+    uint64_t* tfull_bar = empty_bar + GEMM_MAX_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmB2);
+        for (int i = 0; i < num_stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 4);
+        }
+        fence_barrier_init();
+        fence_proxy_async_smem();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    // tile = (sp * m_tiles + mt) * n_tiles + nt : CTAs running together share a pixel range (split) — its dY / X boxes
+    // stay L2-resident.  (A stream-K division of the (tile, k) space balanced the SMs but was 10 % slower: neighbouring
+    // CTAs then stream different pixel ranges and the operand re-reads miss L2.)
+    const int num_tiles = p.splits * p.m_tiles * p.n_tiles;
+    const int m_chunks = 3 * p.co_chunks;
+
+    if (warp == 0) {
+        // =========================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles;
+                const int mt = (tile / p.n_tiles) % p.m_tiles;
+                const int sp = tile / (p.n_tiles * p.m_tiles);
+                const int k_begin = sp * p.k_iters;
+                const int k_end = min(p.k_total, k_begin + p.k_iters);
+                const int mc0 = 2 * mt, mc1 = min(2 * mt + 1, m_chunks - 1);  // an odd tail repeats a chunk (masked)
+                const int dy0 = mc0 / p.co_chunks, cc0 = mc0 % p.co_chunks;
+                const int dy1 = mc1 / p.co_chunks, cc1 = mc1 % p.co_chunks;
+                const bool src2 = nt >= p.cchunks1;
+                const CUtensorMap* mb = src2 ? &tmB2 : &tmB;
+                const int nc = (src2 ? nt - p.cchunks1 : nt) * 64;
+                PixWalker px(p, k_begin);
+                for (int ki = k_begin; ki < k_end; ++ki) {
+                    const int n0 = px.n0, h0 = px.h0, w0 = px.w0;
+                    px.advance(p);
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+                    uint8_t* sa = smem + stage * stage_bytes;
+                    mbar_expect_tx(&full_bar[stage], GEMM_A_STAGE + b_tx);
+                    tma_load_4d(sa, &tmA, &full_bar[stage], cc0 * 64, w0, h0 + 1 - dy0, n0);
+                    tma_load_4d(sa + 8192, &tmA, &full_bar[stage], cc1 * 64, w0, h0 + 1 - dy1, n0);
+                    tma_load_4d(sa + GEMM_A_STAGE, mb, &full_bar[stage], nc, w0 - 1, h0, n0);
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================================================== UMMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, 192, 1, 1);
+            // a 16-pixel k-step is two 8-pixel runs of the halo tile: adjacent (one image row, bw >= 16) or one halo
+            // row apart (bw == 8: two image rows)
+            const uint32_t b_sbo = p.bw >= 16 ? 1024u : static_cast<uint32_t>(halo_w) * 128u;
+            // everything that does not depend on the stage is hoisted: this one thread's issue loop is the critical
+            // path (two runtime integer divisions per k-step cost 25 % of the kernel when they sat inside it)
+            const uint64_t da0 = make_smem_desc(0, 8192, 1024), db0 = make_smem_desc(0, 128, b_sbo);
+            uint32_t a_off[GEMM_BLOCK_K / 16], b_off[GEMM_BLOCK_K / 16];
+#pragma unroll
+            for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+                const int px = k * 16;  // halo row of this k-step's first pixel at dx = 0
+                a_off[k] = (k * 2048) >> 4;
+                b_off[k] = (GEMM_A_STAGE + ((px / p.bw) * halo_w + px % p.bw) * 128) >> 4;
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int sp = tile / (p.n_tiles * p.m_tiles);
+                const int k_begin = sp * p.k_iters;
+                const int k_end = min(p.k_total, k_begin + p.k_iters);
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * 256;
+                for (int ki = k_begin; ki < k_end; ++ki) {
+                    mbar_wait(&full_bar[stage], phase, 3);
+                    tc_fence_after();
+                    const uint32_t sa16 = smem_u32(smem + stage * stage_bytes) >> 4;
+#pragma unroll
+                    for (int k = 0; k < GEMM_BLOCK_K / 16; ++k)
+                        umma_bf16(tmem_d, da0 + (sa16 + a_off[k]), db0 + (sa16 + b_off[k]), idesc,
+                                  (ki > k_begin || k > 0) ? 1u : 0u);
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // =========================================================== epilogue: rows = (dy, co), three 64-column taps
+        const int quad = warp & 3;
+        const int m = quad * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles;
+            const int mt = (tile / p.n_tiles) % p.m_tiles;
+            const int mc = 2 * mt + (m >> 6);
+            const int dy = mc / p.co_chunks, co = (mc % p.co_chunks) * 64 + (m & 63);
+            const bool row_ok = mc < m_chunks && co < p.M;
+            const long long c_base = static_cast<long long>(co) * p.ldc;
+            mbar_wait(&tfull_bar[acc], acc_phase, 4);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(quad * 32) << 16);
+            for (int dx = 0; dx < 3; ++dx)
+                epilogue_row(p, taddr + dx * 64, nt * 64, (dy * 3 + dx) * p.c_col_lo, c_base, 0, row_ok, nullptr, 64);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
     }
 
     tc_fence_before();
