@@ -132,7 +132,7 @@ static int launch_pair(const CUtensorMap& a, const CUtensorMap& a2, const CUtens
     const int pairs = static_cast<int>(pair_tiles < max_pairs ? pair_tiles : max_pairs);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(PAIR_THREADS);
     cfg.dynamicSmemBytes = GEMM_SMEM_TOTAL;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];

@@ -2,7 +2,9 @@
 // batched attention products.  One persistent warp-specialised kernel:
 //   warp 0      : TMA producer (one lane)        global -> 128B-swizzled smem ring
 //   warp 1      : TMEM allocator + UMMA issuer   tcgen05.mma, fp32 accumulators in TMEM (2 x 256 columns)
-//   warps 2..5  : epilogue                       tcgen05.ld -> +bias, +residual, *alpha -> bf16 / fp32 / fp32 atomics
+//   warps 2..   : epilogue                       tcgen05.ld -> +bias, +residual, *alpha -> bf16 / fp32 / fp32 atomics
+//                 (warp w drains TMEM lane quadrant w % 4; with GEMM_EPI_WARPS = 8 the two warps of a quadrant split
+//                 the tile's columns)
 // Tile = 128 (M) x BN (N, runtime, multiple of 16, <= 256) x 64 (K per stage, bf16 = one 128 B swizzle row).
 #pragma once
 #include "ptx.cuh"
@@ -14,7 +16,13 @@ namespace adm {
 
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;
-constexpr int GEMM_THREADS = 192;
+// Epilogue warps: 4 (one per TMEM lane quadrant) or 8 (two per quadrant, each draining half of the tile's columns).
+// Measured on B200 (tools/gemm_accounting.py): 8 warps change nothing on the short-K 1x1 convs — they wait for operand
+// bytes, not for the epilogue — and cost ~8 % on the small 8x8 / 4x4 tiles, so 4 it is.
+constexpr int GEMM_EPI_WARPS = 4;
+constexpr int EPI_HALVES = GEMM_EPI_WARPS / 4;
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
+constexpr int PAIR_THREADS = 192;                        // the (experimental) CTA-pair kernel keeps 4 epilogue warps
 constexpr int GEMM_A_STAGE = GEMM_BLOCK_M * 128;  // 16 KB
 constexpr int GEMM_SMEM_RING = 200 * 1024;        // operand ring budget
 constexpr int GEMM_SMEM_AUX = 4096;               // barriers + tmem ptr (first 1 KB) + per-tile bias slices (2 x 1 KB)
@@ -78,10 +86,17 @@ struct PixWalker {
     }
 };
 
-// The four epilogue warps stage the tile's bias slice (bn <= 256 floats, zero beyond N) in shared memory BEFORE waiting
-// for the accumulator: per-chunk __ldg of the bias missed L1 behind the streaming stores and cost ~30 us on the
-// epilogue-bound 1x1 convs.  `m` = epilogue thread index 0..127; named barrier 1 covers exactly those 128 threads.
-__device__ __forceinline__ void stage_bias(const GemmParams& p, float* sbias, int col_base, int m) {
+// The epilogue warps stage the tile's bias slice (bn <= 256 floats, zero beyond N) in shared memory BEFORE waiting for the
+// accumulator: per-chunk __ldg of the bias missed L1 behind the streaming stores and cost ~30 us on the epilogue-bound
+// 1x1 convs.  `t` = epilogue thread index; named barrier 1 covers exactly the epilogue threads.
+__device__ __forceinline__ void stage_bias(const GemmParams& p, float* sbias, int col_base, int t) {
+    if (p.bias == nullptr) return;
+    for (int c = t; c < p.bn; c += 32 * GEMM_EPI_WARPS)
+        sbias[c] = (col_base + c < p.N) ? __ldg(p.bias + col_base + c) : 0.f;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * GEMM_EPI_WARPS) : "memory");
+}
+// pair kernel: 128 epilogue threads, two columns each
+__device__ __forceinline__ void stage_bias_128(const GemmParams& p, float* sbias, int col_base, int m) {
     if (p.bias == nullptr) return;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -94,11 +109,12 @@ __device__ __forceinline__ void stage_bias(const GemmParams& p, float* sbias, in
 // Epilogue of one accumulator tile for one thread (= one output row): TMEM -> registers in groups of up to 64 columns
 // (four 32x32b.x16 loads in flight behind ONE wait, with the residual row segment prefetched behind the same wait),
 // then alpha * acc + bias + residual -> bf16 / fp32 / fp32 atomics.  c_off / r_off: element offsets of this row in the
-// output and the residual (before the column); col_shift: extra output column offset (batched GEMMs).
+// output and the residual (before the column); col_shift: extra output column offset (batched GEMMs); the tile columns
+// drained are [c_begin, ncols) (multiples of 16).
 __device__ __forceinline__ void epilogue_row(const GemmParams& p, uint32_t taddr, int col_base, int col_shift,
                                              long long c_off, long long r_off, bool row_ok, const float* sbias,
-                                             int ncols) {
-    for (int c0 = 0; c0 < ncols; c0 += 64) {
+                                             int c_begin, int ncols) {
+    for (int c0 = c_begin; c0 < ncols; c0 += 64) {
         if (col_base + c0 >= p.N) break;  // warp-uniform
         uint32_t v[4][16];
         uint4 rr[4][2];
@@ -212,7 +228,10 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, uint8_t* sme
                                                uint64_t* tfull_bar, uint64_t* tempty_bar, int warp, int lane,
                                                int num_tiles) {
     const int quad = warp & 3;
-    const int m = quad * 32 + lane;  // row inside the tile
+    const int half = (warp - 2) >> 2;   // which half of the tile's columns this warp drains
+    const int m = quad * 32 + lane;     // row inside the tile
+    const int c_split = EPI_HALVES == 2 ? (((p.bn >> 1) + 15) & ~15) : p.bn;
+    const int c_begin = half ? c_split : 0, c_end = half ? p.bn : c_split;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -242,11 +261,11 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, uint8_t* sme
         const int col_shift = b_lo * p.c_col_lo;  // extra offset in the output row
 
         float* sbias = reinterpret_cast<float*>(smem + GEMM_SMEM_RING + 1024) + acc * 256;
-        stage_bias(p, sbias, col_base, m);
+        stage_bias(p, sbias, col_base, (warp - 2) * 32 + lane);
         mbar_wait(&tfull_bar[acc], acc_phase, 4);
         tc_fence_after();
         const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(quad * 32) << 16);
-        epilogue_row(p, taddr, col_base, col_shift, c_base, row_off * p.ldr, row_ok, sbias, p.bn);
+        epilogue_row(p, taddr, col_base, col_shift, c_base, row_off * p.ldr, row_ok, sbias, c_begin, c_end);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -283,7 +302,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);
+            mbar_init(&tempty_bar[i], GEMM_EPI_WARPS);
         }
         fence_barrier_init();
         fence_proxy_async_smem();
@@ -461,7 +480,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //   * the leader's MMA thread issues tcgen05.mma.cta_group::2 (M = 256) and its commits arrive, multicast, on the
 //     empty / tmem-full barriers of both CTAs;
 //   * both epilogues (4 warps each) release the accumulator on the leader's tmem-empty barrier (count 8).
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
 tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -603,11 +622,11 @@ tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int col_base = nt * p.bn;
 
             float* sbias = reinterpret_cast<float*>(smem + GEMM_SMEM_RING + 1024) + acc * 256;
-            stage_bias(p, sbias, col_base, m);
+            stage_bias_128(p, sbias, col_base, m);
             mbar_wait(&tfull_bar[acc], acc_phase, 4);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(quad * 32) << 16);
-            epilogue_row(p, taddr, col_base, 0, c_base, pix * p.ldr, row_ok, sbias, p.bn);
+            epilogue_row(p, taddr, col_base, 0, c_base, pix * p.ldr, row_ok, sbias, 0, p.bn);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
@@ -676,7 +695,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);
+            mbar_init(&tempty_bar[i], GEMM_EPI_WARPS);
         }
         fence_barrier_init();
         fence_proxy_async_smem();
@@ -820,7 +839,7 @@ tc_wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);
+            mbar_init(&tempty_bar[i], GEMM_EPI_WARPS);
         }
         fence_barrier_init();
         fence_proxy_async_smem();
@@ -914,6 +933,7 @@ tc_wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     } else {
         // =========================================================== epilogue: rows = (dy, co), three 64-column taps
         const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int m = quad * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -927,8 +947,13 @@ tc_wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mbar_wait(&tfull_bar[acc], acc_phase, 4);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(quad * 32) << 16);
-            for (int dx = 0; dx < 3; ++dx)
-                epilogue_row(p, taddr + dx * 64, nt * 64, (dy * 3 + dx) * p.c_col_lo, c_base, 0, row_ok, nullptr, 64);
+            // 3 taps x 64 columns (with two warps per quadrant: 96 columns each, taps {0, 1 lower half} / {1 upper, 2})
+#pragma unroll 1
+            for (int i = 0; i < (EPI_HALVES == 2 ? 2 : 3); ++i) {
+                const int dx = half + i;
+                const int cb = (half == 1 && i == 0) ? 32 : 0, ce = (EPI_HALVES == 2 && half == 0 && i == 1) ? 32 : 64;
+                epilogue_row(p, taddr + dx * 64, nt * 64, (dy * 3 + dx) * p.c_col_lo, c_base, 0, row_ok, nullptr, cb, ce);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);

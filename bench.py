@@ -30,8 +30,8 @@ METRIC = "train_img_per_s"
 WORKLOAD = ("CIFAR-10 32x32 DDM-const training step, EDMPrecond/DhariwalUNet 216.1M params "
             "(configs/cifar10/ddm_uncond_const_uncond_unet.yaml), fwd+bwd+clip+AdamW, dropout 0.1")
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel from `ncu --set full`
-# (profiles/r01_conv_ncu_full.txt): the 25 MB input is read once, weights 2.6 MB, the output stays in L2.
-CONV_DRAM_TRAFFIC_BYTES = 27.9e6
+# (profiles/r02_conv_ncu_full.txt): the 25 MB input is read once, weights 2.6 MB, the output stays in L2.
+CONV_DRAM_TRAFFIC_BYTES = 28.1e6
 
 
 def peaks():
@@ -297,7 +297,7 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": conv_tf, "peak": pk["tf_burst"], "unit": "TFLOP/s",
                      "frac": conv_tf / pk["tf_burst"], "traffic": CONV_DRAM_TRAFFIC_BYTES,
                      "algorithmic_flops_per_launch": 2.0 * 128 * 16 * 16 * 384 * 384 * 9,
-                     "kernel": "tc_gemm_kernel<CONV> conv3x3 384->384 @16x16 x128 (dominant shape), timed alone",
+                     "kernel": "tc_conv_halo_kernel conv3x3 384->384 @16x16 x128 (dominant shape), timed alone",
                      "ms_per_launch": conv_ms, "peak_source": pk["src"],
                      "step_tflops_per_gpu": step_tf, "step_frac_of_sustained_peak": step_tf / pk["tf_sust"]},
         "sample": {"metric": "sample10_img_per_s", "value": B * world / (ms_sample / 1000), "unit": "img/s",
