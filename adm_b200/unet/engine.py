@@ -16,6 +16,7 @@ role of autograd's AccumulateGrad for its own parameters.
 from __future__ import annotations
 
 import itertools
+import os
 from types import SimpleNamespace as NS
 
 import torch
@@ -50,6 +51,13 @@ class UNetEngine:
         # fp32 master slice of wall, parameter versions)
         # when every block's affine weight / bias are laid out back to back in the parameter arena
         self.affine_pack = None
+        # Weight / bias gradients of the convs run on a side stream, concurrently with the data-gradient chain: a wgrad
+        # only feeds the optimizer, and every GEMM is a persistent kernel whose last partial wave leaves SMs idle (and
+        # the 4x4 / 8x8 levels never fill 148 SMs) — the other stream's CTAs take those SMs.  Joined at every _notify.
+        # ADM_WGRAD_STREAM=0 keeps everything on one stream.
+        self._side = None
+        self._side_on = os.environ.get("ADM_WGRAD_STREAM", "1") != "0"
+        self._side_pending = []
 
     # ------------------------------------------------------------------------------------------ arena fast paths
     def packable_params(self):
@@ -164,7 +172,22 @@ class UNetEngine:
         return self._perm[key]
 
     # ------------------------------------------------------------------------------------------ gradient helpers
+    def _fork_side(self, *keep):
+        """Side stream ordered after everything issued so far on the current stream; `keep` (tensors the side work
+        reads) stay referenced until the join, so the allocator cannot hand their memory to a later main-stream op."""
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        self._side.wait_stream(torch.cuda.current_stream())
+        self._side_pending.append(keep)
+        return self._side
+
+    def _join_side(self):
+        if self._side_pending:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_pending.clear()
+
     def _notify(self, *modules, skip_affine=True):
+        self._join_side()
         if self.grad_hook is None:
             return
         ps = []
@@ -188,6 +211,12 @@ class UNetEngine:
             bias = None
         else:
             bias = conv.bias
+        if self._side_on and dy.is_cuda:
+            with torch.cuda.stream(self._fork_side(dy, x1, x2, dy_cols)):
+                self._conv_weight_grad(conv, dy, x1, x2, perm)
+                if bias is not None:
+                    self._bias_grad(bias, dy if dy_cols is None else dy_cols, perm)
+            return
         self._conv_weight_grad(conv, dy, x1, x2, perm)
         if bias is not None:
             self._bias_grad(bias, dy if dy_cols is None else dy_cols, perm)
