@@ -1144,6 +1144,9 @@ static int gn_cluster_size(int n) {
     const int want = (num_sms() * 6 + 9) / 10;
     int k = 1;
     while (k < 8 && n * k < want) k *= 2;
+    static int mult = -1;  // experiments: ADM_GN_KMULT=2|4 splits every sample over that many more CTAs
+    if (mult < 0) { const char* e = getenv("ADM_GN_KMULT"); mult = e ? atoi(e) : 1; if (mult < 1) mult = 1; }
+    if (n * k >= want) for (int m = mult; m > 1 && k < 8; m >>= 1) k *= 2;
     return (n * k >= want || forced == 2) ? k : 0;
 }
 

@@ -15,6 +15,7 @@ role of autograd's AccumulateGrad for its own parameters.
 """
 from __future__ import annotations
 
+import contextlib
 import itertools
 import os
 from types import SimpleNamespace as NS
@@ -532,20 +533,36 @@ class UNetEngine:
             idx += 1
             skips.append(x)
         outs = []
-        for dec, dname, norm, oconv in ((net.dec, "decouple1", net.out_norm, net.out_conv),
-                                        (net.dec2, "decouple2", net.out_norm2, net.out_conv2)):
-            h = self.decouple_fwd(getattr(net, dname), x, save)
-            sk = list(skips)
-            for name, m in dec.items():
-                x2 = sk.pop() if h.shape[-1] != m.in_channels else None
-                h = run_block(m, h, x2, idx)
-                idx += 1
-            o = NS(x=h, norm=norm, conv=oconv)
-            o.sums, o.a = ops.gn_forward(h, None, norm.weight, norm.bias, _groups(h.shape[-1]), norm.eps, act=True)
-            f = ops.conv_fprop(o.a, self.conv_w(oconv), bias=oconv.bias, out_dtype=F32, keep_pad=True)
-            if save is not None:
-                save.append(o)
-            outs.append(f)  # [N,H,W,4] fp32, channels >= img_channels are zero
+        # The two decoders only share their inputs (bottleneck, skips, embedding): the second one is enqueued on the
+        # side stream, forked HERE (before decoder 1 is enqueued), so their kernels interleave on the SMs — most of
+        # them leave a partial last wave, the 4x4 / 8x8 levels never fill the GPU.  Host order (and the tape) unchanged.
+        fork = None
+        if self._side_on and x.is_cuda:
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            fork = torch.cuda.Event()
+            fork.record(torch.cuda.current_stream())
+        for di, (dec, dname, norm, oconv) in enumerate(((net.dec, "decouple1", net.out_norm, net.out_conv),
+                                                       (net.dec2, "decouple2", net.out_norm2, net.out_conv2))):
+            ctx = contextlib.nullcontext()
+            if di == 1 and fork is not None:
+                self._side.wait_event(fork)
+                self._side_pending.append((x, skips, params_all))
+                ctx = torch.cuda.stream(self._side)
+            with ctx:
+                h = self.decouple_fwd(getattr(net, dname), x, save)
+                sk = list(skips)
+                for name, m in dec.items():
+                    x2 = sk.pop() if h.shape[-1] != m.in_channels else None
+                    h = run_block(m, h, x2, idx)
+                    idx += 1
+                o = NS(x=h, norm=norm, conv=oconv)
+                o.sums, o.a = ops.gn_forward(h, None, norm.weight, norm.bias, _groups(h.shape[-1]), norm.eps, act=True)
+                f = ops.conv_fprop(o.a, self.conv_w(oconv), bias=oconv.bias, out_dtype=F32, keep_pad=True)
+                if save is not None:
+                    save.append(o)
+                outs.append(f)  # [N,H,W,4] fp32, channels >= img_channels are zero
+        self._join_side()
         if tape is not None:
             tape.n_skips = len(skips)
         return outs[0], outs[1]
