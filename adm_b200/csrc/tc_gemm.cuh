@@ -1,5 +1,7 @@
 // tcgen05 / TMEM / TMA GEMM engine shared by conv3x3 (implicit GEMM fprop + dgrad), conv1x1, wgrad, Linear and the
-// batched attention products.  One persistent warp-specialised kernel:
+// batched attention products.  Persistent warp-specialised kernels — tc_gemm_kernel<PLAIN|CONV|WGRAD> (general),
+// tc_conv_halo_kernel (3x3 fprop/dgrad with halo re-use of the pixel operand), tc_wgrad_rows_kernel (3x3 wgrad, three
+// taps per MMA), tc_conv_pair_kernel (cta_group::2 experiment) — with the same roles:
 //   warp 0      : TMA producer (one lane)        global -> 128B-swizzled smem ring
 //   warp 1      : TMEM allocator + UMMA issuer   tcgen05.mma, fp32 accumulators in TMEM (2 x 256 columns)
 //   warps 2..   : epilogue                       tcgen05.ld -> +bias, +residual, *alpha -> bf16 / fp32 / fp32 atomics
