@@ -55,11 +55,13 @@ SIGNATURES = {
     "adm_unpack_conv_wgrad": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "adm_cast_f32_bf16": (c_i, [c_p, c_p, c_ll, c_p]),
     "adm_gn_stats": (c_i, [c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_ll, c_p, c_p, c_p]),
-    "adm_gn_apply": (c_i, [c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_p, c_i, c_f, c_ull, c_i, c_p, c_ll, c_p]),
+    "adm_gn_apply": (c_i, [c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_p, c_i, c_f, c_ull, c_p, c_i, c_p, c_ll,
+                           c_p]),
     "adm_gn_bwd": (c_i, [c_p, c_ll, c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_ll, c_i,
-                         c_f, c_ull, c_i, c_p, c_p, c_p, c_p, c_p, c_ll, c_p, c_ll, c_i, c_p, c_ll, c_p, c_ll, c_p, c_p, c_p]),
+                         c_f, c_ull, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_ll, c_p, c_ll, c_i, c_p, c_ll, c_p, c_ll, c_p, c_p,
+                         c_p]),
     "adm_gn_forward": (c_i, [c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_ll, c_p, c_p, c_i,
-                             c_f, c_ull, c_i, c_p, c_ll, c_p]),
+                             c_f, c_ull, c_p, c_i, c_p, c_ll, c_p]),
     "adm_col_sums": (c_i, [c_p, c_ll, c_ll, c_i, c_p, c_p]),
     "adm_add_bf16": (c_i, [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_p, c_ll, c_ll, c_i, c_p]),
     "adm_resample": (c_i, [c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_p, c_ll, c_p]),
@@ -73,7 +75,7 @@ SIGNATURES = {
     "adm_spatial_att_bwd": (c_i, [c_p, c_ll, c_p, c_ll, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_ll, c_p, c_p, c_p]),
     "adm_sq_norm": (c_i, [c_p, c_ll, c_p, c_p]),
     "adm_adamw": (c_i, [c_p, c_p, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_p, c_p, c_p, c_p]),
-    "adm_set_seed_counter": (c_i, [c_p]),
+    "adm_lerp_f32": (c_i, [c_p, c_p, c_ll, c_f, c_p]),
     "adm_ws_pack": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p]),
     "adm_ws_pack_bwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
     "adm_linattn_workspace": (c_i, [c_i, c_i, c_i, C.POINTER(c_ll)]),

@@ -316,6 +316,25 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
     }
 }
 
+// EMA of the parameter arena (ddm/ema.py:141-156 as one pass): dst += w * (src - dst); 12 B per element, HBM-bound.
+__global__ void __launch_bounds__(256) lerp_f32_kernel(float* __restrict__ dst, const float* __restrict__ src,
+                                                       long long n, float w) {
+    const long long n4 = n >> 2;
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < n4; i += 1LL * gridDim.x * blockDim.x) {
+        float4 a = d4[i];
+        const float4 b = __ldcs(s4 + i);
+        a.x = fmaf(w, b.x - a.x, a.x);
+        a.y = fmaf(w, b.y - a.y, a.y);
+        a.z = fmaf(w, b.z - a.z, a.z);
+        a.w = fmaf(w, b.w - a.w, a.w);
+        d4[i] = a;
+    }
+    for (long long i = (n4 << 2) + blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < n; i += 1LL * gridDim.x * blockDim.x)
+        dst[i] = fmaf(w, src[i] - dst[i], dst[i]);
+}
+
 static int ew_blocks(long long work, int per_sm) {
     long long b = (work + 255) / 256;
     const long long cap = 1LL * num_sms() * per_sm;
@@ -386,6 +405,17 @@ int adm_adamw(float* p, const float* g, float* m, float* v, long long numel, flo
         p, g, m, v, numel, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, max_norm, sqnorm, hyper_dev,
         static_cast<__nv_bfloat16*>(p_bf16));
     ADM_CHECK_LAUNCH("adamw");
+    return 0;
+}
+
+int adm_lerp_f32(float* dst, const float* src, long long numel, float weight, void* stream) {
+    if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) != 0) {
+        set_error("lerp_f32: pointers must be 16 B aligned");
+        return ADM_ERR_SHAPE;
+    }
+    if (numel <= 0) return 0;
+    lerp_f32_kernel<<<ew_blocks(numel / 4 + 1, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(dst, src, numel, weight);
+    ADM_CHECK_LAUNCH("lerp_f32");
     return 0;
 }
 

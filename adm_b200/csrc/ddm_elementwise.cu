@@ -74,8 +74,21 @@ __global__ void __launch_bounds__(256) ddm_loss_kernel(const float* __restrict__
     // x_rec - x0 = -(t*d1 + sqrt(t)*d2) (ddm_const_2.py:566-568 with the sqrt(t) schedule of ddm_const.py:290-293).
     const float l1c = (use_l1 & 1) ? 1.f / static_cast<float>(chw) : ((use_l1 & 2) ? 1.f : 0.f);
     const float half = (use_l1 & 3) ? 0.5f : 1.f;
+    // The reference multiplies the per-sample [B] reconstruction sums by rec_weight of shape [B, 1]
+    // (ddm_const_2.py:565-568): that broadcasts to a [B, B] outer product whose total is (sum_i a_i) * (sum_j w_j), so
+    // every sample is effectively weighted by W = sum_j -log(t_j)/2.  Reproduced as is.
     const bool vlb = (use_l1 & 4) != 0;
-    const float rec_w = vlb ? -0.5f * logf(tb) : 0.f;
+    float rec_w = 0.f;
+    if (vlb) {
+        __shared__ float w_part[8];
+        float w = 0.f;
+        for (long long j = threadIdx.x; j < batch; j += blockDim.x) w -= 0.5f * logf(__ldg(t + j));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+        if ((threadIdx.x & 31) == 0) w_part[threadIdx.x >> 5] = w;
+        __syncthreads();
+        for (int i = 0; i < (blockDim.x >> 5); ++i) rec_w += w_part[i];
+    }
     const float sq_t = sqrtf(tb);
     float svlb = 0.f;
     const float* cpb = cp + b * chw;

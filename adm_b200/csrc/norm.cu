@@ -1120,8 +1120,6 @@ __global__ void __launch_bounds__(512, 1) gn_bwd_fused_kernel(
     }
 }
 
-static const unsigned long long* g_seed_dev = nullptr;
-
 static int grid_for(long long work, int threads, int n_batch) {
     long long blocks = (work + threads - 1) / threads;
     long long cap = (8LL * num_sms() + n_batch - 1) / n_batch;
@@ -1196,11 +1194,6 @@ typedef __nv_bfloat16 bf16;
 
 extern "C" {
 
-int adm_set_seed_counter(const unsigned long long* dev_counter) {
-    g_seed_dev = dev_counter;
-    return 0;
-}
-
 int adm_gn_stats(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int hw,
                  int groups, float eps, const float* gamma, const float* beta, const float* params,
                  long long ld_params, float* work, float* coef, void* stream) {
@@ -1223,8 +1216,9 @@ int adm_gn_stats(const void* x1, int c1, long long ld1, const void* x2, int c2, 
 }
 
 int adm_gn_apply(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int h, int w,
-                 const float* coef, int act, float drop_p, unsigned long long seed, int resample, void* out,
-                 long long ldo, void* stream) {
+                 const float* coef, int act, float drop_p, unsigned long long seed,
+                 const unsigned long long* seed_counter, int resample, void* out, long long ldo, void* stream) {
+    const unsigned long long* g_seed_dev = drop_p > 0.f ? seed_counter : nullptr;
     const int C = c1 + c2;
     ADM_REQUIRE(c1 > 0 && c1 % 8 == 0 && c2 % 8 == 0, "gn_apply: channels must be multiples of 8");
     ADM_REQUIRE(resample == 0 || (resample == 1 && h % 2 == 0 && w % 2 == 0) || resample == 2, "gn_apply: bad resample");
@@ -1242,7 +1236,8 @@ int adm_gn_apply(const void* x1, int c1, long long ld1, const void* x2, int c2, 
 int adm_gn_forward(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int h, int w,
                    int groups, float eps, const float* gamma, const float* beta, const float* params,
                    long long ld_params, float* work, float* coef, int act, float drop_p, unsigned long long seed,
-                   int resample, void* out, long long ldo, void* stream) {
+                   const unsigned long long* seed_counter, int resample, void* out, long long ldo, void* stream) {
+    const unsigned long long* g_seed_dev = drop_p > 0.f ? seed_counter : nullptr;
     const int C = c1 + c2;
     ADM_REQUIRE(c1 > 0 && c1 % 8 == 0 && c2 % 8 == 0 && (x2 != nullptr || c2 == 0) && C % groups == 0,
                 "gn_forward: channels must be multiples of 8 and divisible by groups");
@@ -1253,7 +1248,8 @@ int adm_gn_forward(const void* x1, int c1, long long ld1, const void* x2, int c2
         int rc = adm_gn_stats(x1, c1, ld1, x2, c2, ld2, n, h * w, groups, eps, gamma, beta, params, ld_params, work, coef,
                               stream);
         if (rc != 0 || out == nullptr) return rc;
-        return adm_gn_apply(x1, c1, ld1, x2, c2, ld2, n, h, w, coef, act, drop_p, seed, resample, out, ldo, stream);
+        return adm_gn_apply(x1, c1, ld1, x2, c2, ld2, n, h, w, coef, act, drop_p, seed, seed_counter, resample, out, ldo,
+                            stream);
     }
     const int V = C / 8;
     const int threads = gn_fused_threads(V, h * w, k);
@@ -1273,9 +1269,11 @@ int adm_gn_forward(const void* x1, int c1, long long ld1, const void* x2, int c2
 int adm_gn_bwd(const void* dy, long long ldy, const void* x1, int c1, long long ld1, const void* x2, int c2,
                long long ld2, int n, int h, int w, int groups, const float* coef, const float* gamma,
                const float* beta, const float* params, long long ld_params, int act, float drop_p,
-               unsigned long long seed, int resample, float* work, float* bcoef, float* dgamma, float* dbeta,
-               float* dparams, long long ld_dparams, const void* add, long long ldadd, int add_mode, void* dx1,
-               long long ldx1, void* dx2, long long ldx2, float* dbias1, float* dbias1b, void* stream) {
+               unsigned long long seed, const unsigned long long* seed_counter, int resample, float* work,
+               float* bcoef, float* dgamma, float* dbeta, float* dparams, long long ld_dparams, const void* add,
+               long long ldadd, int add_mode, void* dx1, long long ldx1, void* dx2, long long ldx2, float* dbias1,
+               float* dbias1b, void* stream) {
+    const unsigned long long* g_seed_dev = drop_p > 0.f ? seed_counter : nullptr;
     const int C = c1 + c2;
     ADM_REQUIRE(c1 > 0 && c1 % 8 == 0 && c2 % 8 == 0 && C % groups == 0, "gn_bwd: bad channels / groups");
     ADM_REQUIRE(C <= 2048, "gn_bwd: C too large");

@@ -75,7 +75,15 @@ class DDPM(nn.Module):
         self.objective = objective
         self.start_dist = start_dist
         assert start_dist in ["normal", "uniform"]
-        self.loss_type = loss_type
+        if loss_type not in ("l1", "l2"):
+            raise NotImplementedError(f"unknown loss type '{loss_type}'")  # ddm_const_2.py:261-271
+        self.loss_type = loss_type  # only selects the reference's unused `loss_fn` property; p_losses never reads it
+        # loss_main_func (ddm_const_2.py:98-102): the per-sample SUM-reduced squared error of ddm/loss.py:300-312 is what
+        # K2 evaluates; any other class would silently train a different objective, so it is refused.
+        loss_main = (self.cfg.get("loss_main") or {}).get("class_name", "ddm.loss.MSE_Loss")
+        if loss_main.split(".")[-1] != "MSE_Loss":
+            raise NotImplementedError(f"adm_b200: loss_main '{loss_main}' is not supported (the fused loss kernel "
+                                      "implements ddm.loss.MSE_Loss, the reference default)")
         self.sampling_timesteps = default(sampling_timesteps, 10)
         self.use_l1 = use_l1
         self.perceptual_weight = perceptual_weight  # LPIPS term is 0 here (see module docstring)
@@ -237,11 +245,17 @@ class DDPM(nn.Module):
         eng = getattr(getattr(self.model, "model", None), "engine", None)
         return eng.signature() if eng is not None else None
 
+    def _model_pointers(self):
+        eng = getattr(getattr(self.model, "model", None), "engine", None)
+        return eng.pointer_signature() if eng is not None else None
+
     def _sample_d_graph(self, x_T, ts, unnormalize):
         key = (tuple(x_T.shape), tuple(ts), bool(unnormalize), bool(self.clip_x_start), float(self.scale_input))
         cache = self.__dict__.setdefault("_sample_graphs", {})
         ent = cache.get(key)
-        sig = self._model_signature()
+        sig, ptrs = self._model_signature(), self._model_pointers()
+        if ent is not None and ent["ptrs"] != ptrs:  # parameters were re-homed since capture: the graph is stale
+            ent = None
         if ent is None:
             t_dev = torch.tensor(ts, device=x_T.device, dtype=torch.float64)
             static_in = x_T.clone()
@@ -253,7 +267,7 @@ class DDPM(nn.Module):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 static_out = self._sample_d_loop(static_in, ts, t_dev, unnormalize)
-            ent = cache[key] = dict(graph=g, x=static_in, out=static_out, t=t_dev, sig=sig)
+            ent = cache[key] = dict(graph=g, x=static_in, out=static_out, t=t_dev, sig=sig, ptrs=ptrs)
         elif ent["sig"] != sig:
             # parameters changed since capture: one eager forward re-derives the cached bf16 operands in place
             self.model(ent["x"], ent["t"][0])
@@ -298,7 +312,13 @@ class LatentDiffusion(DDPM):
     """Mirror of the reference's ``LatentDiffusion``: plumbing of /root/reference/ddm/ddm_const_2.py:393-436 (ctor),
     :473-524 (scale factor, get_input, training_step), :527-588 (loss with the L1-sum and reconstruction terms),
     :606-630 (sample); math of the sqrt(t) schedule (ddm_const.py:286,292,336-338) and the clamp-free latent sampler
-    (ddm_const.py:868-888).  The frozen first stage is any module with ``encode(x)`` (a tensor, or a posterior with
+    (ddm_const.py:868-888).  Two points where this class has to choose, both pinned by tests/golden/make_golden_ddm.py:
+    the fork's own latent ``p_losses`` (ddm_const.py:716-784) is a nuScenes segmentation objective, so the loss keeps
+    the sibling's STRUCTURE with the const schedule's weights (t^2-t+1)/t, (t^2-t+1)/(1-t+eps) — the sibling's own
+    weights ((t-1)/t)^2+1, (t/(1-t+eps))^2+1 belong to its t-linear schedule; and the sibling multiplies the per-sample
+    reconstruction sums [B] by ``rec_weight`` of shape [B, 1] (:565-568), which broadcasts to a [B, B] outer product:
+    the term is (sum_i |x_rec-x0|_i) * (sum_j -log(t_j)/2) / B.  That is what the reference computes, so K2 does too.
+    The frozen first stage is any module with ``encode(x)`` (a tensor, or a posterior with
     ``.sample()``), ``decode(z)`` and ``down_ratio`` — the reference's ``AutoencoderKL`` fits as is.
     K1 / K2 / K3 are the same fused kernels as in image space; K2 runs with its latent flag word (L1 sum + -log(t)/2
     reconstruction term), K3 without the clamp."""

@@ -1,10 +1,16 @@
-"""Exponential moving average of the model weights: mirror of /root/reference/ddm/ema.py (``EMA`` :21-191) — same
-constructor arguments, warm-up decay ``1 - (1 + epoch / inv_gamma) ** -power`` clamped to [min_value, beta] (:132-139),
-``update()`` cadence (:141-156) and state_dict layout (``online_model.*``, ``ema_model.*``, ``initted``, ``step``).
+"""Exponential moving average of the model weights as ONE flat lerp over the parameter arena.
 
-Differences in execution only: the ~1600 per-tensor ``lerp_`` launches of the reference become ONE multi-tensor launch
-(``torch._foreach_lerp_``), and because the moving average is written through ``.data`` (which does not bump tensor
-versions) every fused UNet engine inside the EMA copy is told to re-derive its cached bf16 operands.
+Role of /root/reference/ddm/ema.py (``EMA`` :21-191) for the Trainer / Sampler shells: same constructor keywords, the
+same warm-up decay ``1 - (1 + epoch / inv_gamma) ** -power`` clamped to [min_value, beta] (:132-139), the same
+``update()`` cadence (:141-156: hard copies until ``update_after_step``, then a lerp every ``update_every`` calls) and
+the same state_dict layout (``online_model.*``, ``ema_model.*``, ``initted``, ``step``) so checkpoints interchange.
+
+Execution is different.  When the online parameters live in a training arena (``adm_b200.train.ParamArena``: every
+parameter is a view of one flat fp32 buffer) the averaged copy is laid out as a second flat buffer with identical
+offsets and strides, and an update is a single HBM-bound kernel ``ema += w * (online - ema)`` over the whole arena
+(``adm_lerp_f32``, 12 B per parameter) instead of ~1600 per-tensor launches.  Parameters outside an arena (host tests,
+float buffers) take per-tensor ``lerp_``.  The moving average is written through raw pointers, so the fused UNet
+engines inside the averaged copy are told to re-derive their cached bf16 operands.
 """
 from __future__ import annotations
 
@@ -14,17 +20,12 @@ import torch
 from torch import nn
 
 
-def exists(val):
-    return val is not None
-
-
-def clamp(value, min_value=None, max_value=None):
-    assert exists(min_value) or exists(max_value)
-    if exists(min_value):
-        value = max(value, min_value)
-    if exists(max_value):
-        value = min(value, max_value)
-    return value
+def ema_decay(step, update_after_step=100, inv_gamma=1.0, power=2 / 3, min_value=0.0, beta=0.9999):
+    """Decay used by the update that happens when the step counter reads ``step`` (ddm/ema.py:132-139)."""
+    epoch = max(step - update_after_step - 1, 0.)
+    if epoch <= 0:
+        return 0.
+    return min(max(1 - (1 + epoch / inv_gamma) ** -power, min_value), beta)
 
 
 def _engines(model):
@@ -35,112 +36,140 @@ def _detached_copy(model):
     """deepcopy that leaves training-arena plumbing behind: CUDA graphs are not copyable, and parameters re-homed in a
     TrainStep arena carry bf16-shadow attributes that must not follow the copy."""
     stash = [(m, m.__dict__.pop("_sample_graphs")) for m in model.modules() if "_sample_graphs" in m.__dict__]
-    hooks = [(e, e.grad_hook, e.affine_pack, e._cache) for e in _engines(model)]
+    hooks = [(e, e.grad_hook, e.affine_pack, e._cache, e.seed_counter) for e in _engines(model)]
     for e, *_ in hooks:
-        e.grad_hook, e.affine_pack, e._cache = None, None, {}
+        e.grad_hook, e.affine_pack, e._cache, e.seed_counter = None, None, {}, None
     try:
         new = copy.deepcopy(model)
     finally:
         for m, g in stash:
             m.__dict__["_sample_graphs"] = g
-        for e, h, a, c in hooks:
-            e.grad_hook, e.affine_pack, e._cache = h, a, c
+        for e, h, a, c, s in hooks:
+            e.grad_hook, e.affine_pack, e._cache, e.seed_counter = h, a, c, s
     for p in new.parameters():
         p.__dict__.pop("_adm_pack", None)
-        p.data = p.data.clone(memory_format=torch.contiguous_format)
         p.grad = None
     return new
 
 
+def _shared_flat(params):
+    """(flat fp32 tensor covering the storage, True) when every tensor is a view of ONE fp32 CUDA storage."""
+    if not params or any((not p.is_cuda) or p.dtype != torch.float32 for p in params):
+        return None
+    first = params[0].untyped_storage()
+    if any(p.untyped_storage().data_ptr() != first.data_ptr() for p in params):
+        return None
+    n = first.nbytes() // 4
+    return torch.empty(0, device=params[0].device, dtype=torch.float32).set_(first, 0, (n,), (1,))
+
+
 class EMA(nn.Module):
     def __init__(self, model, ema_model=None, beta=0.9999, update_after_step=100, update_every=10, inv_gamma=1.0,
-                 power=2 / 3, min_value=0.0, param_or_buffer_names_no_ema=set(), ignore_names=set(),
-                 ignore_startswith_names=set(), include_online_model=True):
+                 power=2 / 3, min_value=0.0, param_or_buffer_names_no_ema=(), ignore_names=(),
+                 ignore_startswith_names=(), include_online_model=True):
         super().__init__()
-        self.beta = beta
+        self.beta, self.update_every, self.update_after_step = beta, update_every, update_after_step
+        self.inv_gamma, self.power, self.min_value = inv_gamma, power, min_value
         self.include_online_model = include_online_model
         if include_online_model:
             self.online_model = model
         else:
-            self.online_model = [model]  # not registered as a sub-module
-        self.ema_model = ema_model if exists(ema_model) else _detached_copy(model)
+            self._online = [model]  # kept out of the module tree (and of the state_dict)
+        self.ema_model = ema_model if ema_model is not None else _detached_copy(model)
         self.ema_model.requires_grad_(False)
-        self.parameter_names = {n for n, p in self.ema_model.named_parameters() if p.dtype == torch.float}
-        self.buffer_names = {n for n, b in self.ema_model.named_buffers() if b.dtype == torch.float}
-        self.update_every, self.update_after_step = update_every, update_after_step
-        self.inv_gamma, self.power, self.min_value = inv_gamma, power, min_value
-        assert isinstance(param_or_buffer_names_no_ema, (set, list))
-        self.param_or_buffer_names_no_ema = param_or_buffer_names_no_ema
-        self.ignore_names = ignore_names
-        self.ignore_startswith_names = ignore_startswith_names
+        self._copy_only = set(param_or_buffer_names_no_ema)
+        self._skip = (set(ignore_names), tuple(ignore_startswith_names))
         self.register_buffer("initted", torch.Tensor([False]))
         self.register_buffer("step", torch.tensor([0]))
+        self._plan = None
 
     @property
     def model(self):
-        return self.online_model if self.include_online_model else self.online_model[0]
+        return self.online_model if self.include_online_model else self._online[0]
 
-    def restore_ema_model_device(self):
-        self.ema_model.to(self.initted.device)
+    # ------------------------------------------------------------------------------------------ layout
+    def _float_tensors(self, module):
+        out = {n: p for n, p in module.named_parameters() if p.dtype == torch.float}
+        out.update({n: b for n, b in module.named_buffers() if b.dtype == torch.float})
+        return out
 
-    def get_params_iter(self, model):
-        for name, param in model.named_parameters():
-            if name in self.parameter_names:
-                yield name, param
+    def _build_plan(self):
+        """Pairs (ema, online) by name; when the online parameters are views of one arena, re-home the averaged copy
+        into a flat buffer with the same offsets/strides so that ONE kernel updates all of them."""
+        on, av = self._float_tensors(self.model), self._float_tensors(self.ema_model)
+        names = [n for n in av if n in on and n not in self._skip[0] and not n.startswith(self._skip[1] or ("\0",))]
+        lerp = [n for n in names if n not in self._copy_only]
+        flat_on = _shared_flat([on[n].data for n in lerp if isinstance(on[n], nn.Parameter)])
+        flat_ema, loose = None, lerp
+        if flat_on is not None and not self._copy_only:
+            flat_ema = torch.empty_like(flat_on)
+            flat_ema.copy_(flat_on)
+            homed = []
+            for n in lerp:
+                src = on[n]
+                if isinstance(src, nn.Parameter):
+                    view = flat_ema.as_strided(src.shape, src.stride(), src.storage_offset())
+                    view.copy_(av[n].data)
+                    av[n].data = view
+                    homed.append(n)
+            loose = [n for n in lerp if n not in set(homed)]
+        self._plan = dict(flat=(flat_ema, flat_on), loose=[(av[n], on[n]) for n in loose],
+                          copy=[(av[n], on[n]) for n in names if n in self._copy_only])
 
-    def get_buffers_iter(self, model):
-        for name, buffer in model.named_buffers():
-            if name in self.buffer_names:
-                yield name, buffer
-
-    def _invalidate(self):
+    def invalidate_engines(self):
         for e in _engines(self.ema_model):
             e.invalidate()
 
+    _invalidate = invalidate_engines
+
+    # ------------------------------------------------------------------------------------------ updates
     @torch.no_grad()
+    def _blend(self, weight):
+        """ema <- ema + weight * (online - ema); weight == 1 is a hard copy."""
+        key = tuple(p.data_ptr() for p in self.model.parameters())  # re-homed parameters (a new arena) re-plan
+        if self._plan is None or self._plan["key"] != key:
+            self._build_plan()
+            self._plan["key"] = key
+        flat_ema, flat_on = self._plan["flat"]
+        if flat_ema is not None:
+            if weight >= 1.:
+                flat_ema.copy_(flat_on)
+            else:
+                from .. import ops
+                ops.lerp_f32(flat_ema, flat_on, weight)
+        for ma, cur in self._plan["loose"]:
+            if weight >= 1.:
+                ma.data.copy_(cur.data)
+            else:
+                ma.data.lerp_(cur.data.to(ma.dtype), weight)
+        for ma, cur in self._plan["copy"]:
+            ma.data.copy_(cur.data)
+        self.invalidate_engines()
+
     def copy_params_from_model_to_ema(self):
-        for (_, ma), (_, cur) in zip(self.get_params_iter(self.ema_model), self.get_params_iter(self.model)):
-            ma.data.copy_(cur.data)
-        for (_, ma), (_, cur) in zip(self.get_buffers_iter(self.ema_model), self.get_buffers_iter(self.model)):
-            ma.data.copy_(cur.data)
-        self._invalidate()
+        self._blend(1.)
 
     def get_current_decay(self):
-        epoch = clamp(self.step.item() - self.update_after_step - 1, min_value=0.)
-        value = 1 - (1 + epoch / self.inv_gamma) ** - self.power
-        if epoch <= 0:
-            return 0.
-        return clamp(value, min_value=self.min_value, max_value=self.beta)
+        return ema_decay(self.step.item(), self.update_after_step, self.inv_gamma, self.power, self.min_value,
+                         self.beta)
 
     def update(self):
-        step = self.step.item()
+        step = int(self.step.item())
         self.step += 1
-        if (step % self.update_every) != 0:
+        if step % self.update_every:
             return
         if step <= self.update_after_step:
-            self.copy_params_from_model_to_ema()
+            self._blend(1.)
             return
-        if not self.initted.item():
-            self.copy_params_from_model_to_ema()
-            self.initted.data.copy_(torch.Tensor([True]))
-        self.update_moving_average(self.ema_model, self.model)
+        if not bool(self.initted.item()):
+            self._blend(1.)
+            self.initted.fill_(1.)
+        self._blend(1. - self.get_current_decay())
 
-    @torch.no_grad()
-    def update_moving_average(self, ma_model, current_model):
-        decay = self.get_current_decay()
-        lerp_ma, lerp_cur = [], []
-        for it in (self.get_params_iter, self.get_buffers_iter):
-            for (name, cur), (_, ma) in zip(it(current_model), it(ma_model)):
-                if name in self.ignore_names or any(name.startswith(p) for p in self.ignore_startswith_names):
-                    continue
-                if name in self.param_or_buffer_names_no_ema:
-                    ma.data.copy_(cur.data)
-                    continue
-                lerp_ma.append(ma.data)
-                lerp_cur.append(cur.data if cur.data.is_contiguous() == ma.data.is_contiguous() else cur.data.contiguous())
-        if lerp_ma:
-            torch._foreach_lerp_(lerp_ma, lerp_cur, 1. - decay)  # one multi-tensor launch
-        self._invalidate()
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        out = super().load_state_dict(state_dict, strict=strict, assign=assign)
+        self.invalidate_engines()
+        return out
 
-    def __call__(self, *args, **kwargs):
+    def forward(self, *args, **kwargs):
         return self.ema_model(*args, **kwargs)

@@ -7,7 +7,6 @@ import importlib
 # reference module path -> adm_b200 module path
 ALIASES = {
     "ddm.ddm_const": "adm_b200.ddm.ddm_const",
-    "ddm.loss": "adm_b200.ddm.loss",
     "ddm.utils": "adm_b200.ddm.utils",
     "unet.uncond_unet": "adm_b200.unet.uncond_unet",
     "unet.cond_unet": "adm_b200.unet.cond_unet",

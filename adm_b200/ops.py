@@ -315,20 +315,22 @@ def gn_stats(x1, x2, gamma, beta, groups, eps=1e-5, params=None):
     return coef
 
 
-def gn_apply(x1, x2, coef, act=True, drop_p=0.0, seed=0, resample=0):
+def gn_apply(x1, x2, coef, act=True, drop_p=0.0, seed=0, resample=0, seed_counter=None):
     n, h, w, _ = x1.shape
     p1, c1, ld1 = _src(x1)
     p2, c2, ld2 = _src(x2)
     ho, wo = (h // 2, w // 2) if resample == 1 else ((2 * h, 2 * w) if resample == 2 else (h, w))
     out = torch.empty(n, ho, wo, c1 + c2, device=x1.device, dtype=BF16)
     check(_lib.load().adm_gn_apply(p1, c1, ld1, p2, c2, ld2, n, h, w, _ptr(coef), int(act), float(drop_p),
-                                   int(seed) & 0xFFFFFFFFFFFFFFFF, int(resample), _ptr(out), out.stride(2), _stream()),
-          "gn_apply")
+                                   int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(seed_counter), int(resample), _ptr(out),
+                                   out.stride(2), _stream()), "gn_apply")
     return out
 
 
-def gn_forward(x1, x2, gamma, beta, groups, eps=1e-5, params=None, act=True, drop_p=0.0, seed=0, resample=0):
+def gn_forward(x1, x2, gamma, beta, groups, eps=1e-5, params=None, act=True, drop_p=0.0, seed=0, resample=0,
+               seed_counter=None):
     """GroupNorm statistics + apply in one call (one cluster-per-sample kernel when the batch fills the SMs).
+    seed_counter: optional CUDA int64[1] step counter mixed into the dropout seed (read only when drop_p > 0).
     Returns (coef [N, C, 4], y)."""
     _need_cuda(x1)
     n, h, w, _ = x1.shape
@@ -342,13 +344,14 @@ def gn_forward(x1, x2, gamma, beta, groups, eps=1e-5, params=None, act=True, dro
     ldp = params.stride(0) if params is not None else 0
     check(_lib.load().adm_gn_forward(p1, c1, ld1, p2, c2, ld2, n, h, w, groups, float(eps), _ptr(gamma), _ptr(beta),
                                      _ptr(params), ldp, _ptr(work), _ptr(coef), int(act), float(drop_p),
-                                     int(seed) & 0xFFFFFFFFFFFFFFFF, int(resample), _ptr(out), out.stride(2),
-                                     _stream()), "gn_forward")
+                                     int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(seed_counter), int(resample), _ptr(out),
+                                     out.stride(2), _stream()), "gn_forward")
     return coef, out
 
 
 def gn_bwd(dy, x1, x2, coef, gamma, beta, groups, params=None, act=True, drop_p=0.0, seed=0, resample=0,
-           dgamma=None, dbeta=None, dparams=None, add=None, add_mode=0, need_dx=True, dbias1=None, dbias1b=None):
+           dgamma=None, dbeta=None, dparams=None, add=None, add_mode=0, need_dx=True, dbias1=None, dbias1b=None,
+           seed_counter=None):
     """Returns (dx1, dx2).  dgamma/dbeta are accumulated in place; dparams ([N, 2C] view) is overwritten;
     dbias1 (fp32 [c1]) += column sums of dx1."""
     n, h, w, _ = x1.shape
@@ -364,7 +367,8 @@ def gn_bwd(dy, x1, x2, coef, gamma, beta, groups, params=None, act=True, drop_p=
     lddp = dparams.stride(0) if dparams is not None else 0
     check(_lib.load().adm_gn_bwd(_ptr(dy), dy.stride(-2), p1, c1, ld1, p2, c2, ld2, n, h, w, groups, _ptr(coef),
                                  _ptr(gamma), _ptr(beta), _ptr(params), ldp, int(act), float(drop_p),
-                                 int(seed) & 0xFFFFFFFFFFFFFFFF, int(resample), _ptr(work), _ptr(bcoef), _ptr(dgamma),
+                                 int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(seed_counter), int(resample), _ptr(work),
+                                 _ptr(bcoef), _ptr(dgamma),
                                  _ptr(dbeta), _ptr(dparams), lddp, _ptr(add),
                                  add.stride(-2) if add is not None else 0, int(add_mode), _ptr(dx1),
                                  dx1.stride(2) if dx1 is not None else 0, _ptr(dx2),
@@ -560,9 +564,13 @@ def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
                                 _ptr(sqnorm), _ptr(hyper_dev), _ptr(p_bf16), _stream()), "adamw")
 
 
-def set_seed_counter(t):
-    """t: CUDA int64 tensor with one element (or None)."""
-    check(_lib.load().adm_set_seed_counter(_ptr(t)), "set_seed_counter")
+def lerp_f32(dst, src, weight):
+    """dst += weight * (src - dst) over two flat fp32 CUDA tensors of equal length (the EMA arena update)."""
+    _need_cuda(dst, src)
+    assert dst.dtype == F32 and src.dtype == F32 and dst.is_contiguous() and src.is_contiguous()
+    assert dst.numel() == src.numel()
+    check(_lib.load().adm_lerp_f32(_ptr(dst), _ptr(src), dst.numel(), float(weight), _stream()), "lerp_f32")
+    return dst
 
 
 # ------------------------------------------------------------------------------------------------ conditional UNet ops

@@ -154,6 +154,8 @@ class TrainStep:
         self.dpm = dpm
         self.net = dpm.model
         self.engine = self.net.model.engine
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.pg = process_group
         self.arena = ParamArena(self.net, completion_order(self.net), channels_last=self.engine.packable_params())
         self._bind_affine()
         self.m = torch.zeros_like(self.arena.flat)
@@ -172,8 +174,6 @@ class TrainStep:
                             for _ in range(4)]
         self._hyper_events = [None] * 4
         self._ring_i = 0
-        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
-        self.pg = process_group
         # gradient buckets in completion order
         n = self.arena.numel
         per = max(1, bucket_mb * (1 << 20) // 4)
@@ -184,11 +184,10 @@ class TrainStep:
         self._param_end = {}
         for p, o in zip(self.arena.params, self.arena.offsets):
             self._param_end[id(p)] = o + p.numel()
-        self.engine.invalidate()
+        self.sync_params(moments=False)
         # device-resident step counter mixed into every dropout seed (fresh masks per CUDA-graph replay)
         self.seed_counter = torch.zeros(1, device=dev, dtype=torch.int64) if dev.type == "cuda" else None
-        if self.seed_counter is not None:
-            ops.set_seed_counter(self.seed_counter)
+        self.engine.seed_counter = self.seed_counter  # passed per call to the GroupNorm kernels (no global state)
         self.graph = None
 
     def _bind_affine(self):
@@ -212,6 +211,17 @@ class TrainStep:
         """Call after parameters were written outside the fused optimizer (load_state_dict, manual edits)."""
         self.arena.refresh_shadow()
         self.engine.invalidate()
+
+    def sync_params(self, src=0, moments=True):
+        """Data parallelism needs identical replicas: rank `src`'s parameter arena (and optimizer moments, when they
+        exist) are broadcast to every rank — what accelerate / DDP do for the reference at wrap time
+        (train_uncond_dpm.py:197-198).  Called at construction and after a checkpoint load."""
+        if self.world > 1:
+            dist.broadcast(self.arena.flat, src=src, group=self.pg)
+            if moments:
+                dist.broadcast(self.m, src=src, group=self.pg)
+                dist.broadcast(self.v, src=src, group=self.pg)
+        self.refresh()
 
     # ------------------------------------------------------------------------------------------ gradient reduction
     # The arena is laid out in gradient-completion order, so "everything below offset X is final" grows monotonically

@@ -77,7 +77,10 @@ class Trainer(object):
             return
         s = self.step_fn
         data = {"step": self.step, "model": self.model.state_dict(),
-                "opt": {"m": s.m, "v": s.v, "step_count": s.step_count, "format": "adm_b200 flat AdamW moments"},
+                "opt": {"m": s.m, "v": s.v, "step_count": s.step_count, "format": "adm_b200 flat AdamW moments",
+                        # dropout-mask stream position: device step counter + the engine's per-forward seed index
+                        "seed_counter": int(s.seed_counter.item()) if s.seed_counter is not None else 0,
+                        "seed_iter": s.engine.seed_position()},
                 "lr_scheduler": {"last_epoch": s.step_count}, "ema": self.ema.state_dict(), "scaler": None}
         torch.save(data, str(self.results_folder / f"model-{milestone}.pt"))
 
@@ -91,12 +94,15 @@ class Trainer(object):
             s.m.copy_(opt["m"])
             s.v.copy_(opt["v"])
             s.step_count = int(opt.get("step_count", self.step))
+            if s.seed_counter is not None:
+                s.seed_counter.fill_(int(opt.get("seed_counter", 0)))
+            s.engine.seed_position(int(opt.get("seed_iter", 0)))
         else:  # a reference checkpoint: torch.optim state is not transferable to the flat arena; restart the moments
             s.step_count = self.step
         if self.is_main and "ema" in data:
             self.ema.load_state_dict(data["ema"])
-            self.ema._invalidate()
-        s.refresh()
+            self.ema.invalidate_engines()
+        s.sync_params()  # every rank ends up with rank 0's weights and moments (only rank 0 is guaranteed the file)
 
     # ------------------------------------------------------------------------------------------ the loop
     def train_one_step(self):

@@ -16,7 +16,6 @@ role of autograd's AccumulateGrad for its own parameters.
 from __future__ import annotations
 
 import contextlib
-import itertools
 import os
 from types import SimpleNamespace as NS
 
@@ -35,7 +34,7 @@ class UNetEngine:
         self.net = net
         self._cache = {}
         self._epoch = 0
-        self._seed_iter = itertools.count(1)
+        self._seed_next = 1  # index of the next training forward (mixed into the dropout seeds)
         self.base_seed = 0x1234
         # ordered block table + offsets into the batched affine GEMM
         self.block_list = []
@@ -59,6 +58,15 @@ class UNetEngine:
         self._side = None
         self._side_on = os.environ.get("ADM_WGRAD_STREAM", "1") != "0"
         self._side_pending = []
+        # device-resident step counter mixed into every dropout seed (fresh masks per CUDA-graph replay); owned by the
+        # training step (adm_b200.train.TrainStep) and passed to the GroupNorm kernels per call
+        self.seed_counter = None
+
+    def seed_position(self, value=None):
+        """Get (or restore, from a checkpoint) the position in the dropout-mask stream."""
+        if value is not None:
+            self._seed_next = int(value) + 1
+        return self._seed_next - 1
 
     # ------------------------------------------------------------------------------------------ arena fast paths
     def packable_params(self):
@@ -108,6 +116,11 @@ class UNetEngine:
     def signature(self):
         """Changes whenever any parameter may have changed (optimizer epoch or a torch-side in-place write)."""
         return self._epoch, sum(p._version for p in self.net.parameters())
+
+    def pointer_signature(self):
+        """Changes when parameters are re-homed (a training or EMA arena took them over): anything that baked device
+        pointers of derived operands (a captured CUDA graph) must be rebuilt, not just refreshed."""
+        return hash(tuple(p.data_ptr() for p in self.net.parameters()))
 
     def _dev(self):
         return self.net.map_layer0.weight.device
@@ -282,7 +295,10 @@ class UNetEngine:
             b = torch.zeros(3, heads, dpad, device=self._dev(), dtype=F32)
             b[:, :, :d] = blk.qkv.bias.detach()[rows]
             wpk = ops.pack_conv_weight(w.reshape(3 * heads * dpad, c, 1, 1), out=old[0] if old is not None else None)
-            return wpk, b.reshape(-1).contiguous(), rows
+            bq = b.reshape(-1).contiguous()
+            if old is not None:  # keep the device pointer stable: captured sampler graphs read this buffer
+                bq = old[1].copy_(bq)
+            return wpk, bq, rows
         return self._cached(("qkvpad", id(blk)), [blk.qkv.weight, blk.qkv.bias], build)
 
     def proj_padded(self, blk):
@@ -309,7 +325,8 @@ class UNetEngine:
         # after the fused concat-GroupNorm the conv sees ONE tensor a0 with cin channels
         c.h0 = ops.conv_fprop(c.a0, self.conv_w(blk.conv0), bias=blk.conv0.bias)
         c.sums1, c.a1 = ops.gn_forward(c.h0, None, blk.norm1.weight, blk.norm1.bias, _groups(cout), blk.norm1.eps,
-                                       params=params, act=True, drop_p=c.drop_p, seed=seed)
+                                       params=params, act=True, drop_p=c.drop_p, seed=seed,
+                                       seed_counter=self.seed_counter)
         if blk.skip is not None and blk.skip.weight is not None:
             res = ops.conv_fprop(x1, self.conv_w(blk.skip, cin1, cin2), x2=x2, bias=blk.skip.bias)
         elif mode:
@@ -337,6 +354,24 @@ class UNetEngine:
                 out = ops.conv_fprop(c.att, self.conv_w(blk.proj), bias=blk.proj.bias, residual=c.h1)
         if save is not None:
             save.append(c)
+        return out
+
+    def export_dropout_masks(self, tape):
+        """The dropout keep-masks (already scaled by 1/(1-p)) a training forward drew, one NCHW fp32 tensor per UNetBlock,
+        keyed by the block's state_dict prefix.  The masks are a stateless hash of (seed, element index), so they are
+        regenerated here by running the GroupNorm-apply kernel over a tensor of ones with the block's own seed.
+        Used by the parity tests to feed the reference's dropout (uncond_unet.py:200) the same masks."""
+        names = {id(m): name for name, m, _ in self.block_list}
+        out = {}
+        for c in tape.items:
+            if not hasattr(c, "blk") or not c.drop_p:
+                continue
+            n, h, w, ch = c.h0.shape
+            coef = torch.zeros(n, ch, 4, device=c.h0.device, dtype=F32)
+            coef[..., 0] = 1.0
+            ones = torch.ones(n, h, w, ch, device=c.h0.device, dtype=BF16)
+            m = ops.gn_apply(ones, None, coef, act=False, drop_p=c.drop_p, seed=c.seed, seed_counter=self.seed_counter)
+            out["model." + names[id(c.blk)]] = m.float().permute(0, 3, 1, 2).contiguous()
         return out
 
     def bias_sinks(self, blk):
@@ -399,7 +434,7 @@ class UNetEngine:
         self._conv_param_grads(blk.conv1, dh1, c.a1, bias_done=h1_bias_done)
         da1 = self._dgrad(dh1, blk.conv1, self.conv_w(blk.conv1))
         dh0, _ = ops.gn_bwd(da1, c.h0, None, c.sums1, blk.norm1.weight, blk.norm1.bias, _groups(cout),
-                            params=c.params, act=True, drop_p=c.drop_p, seed=c.seed,
+                            params=c.params, act=True, drop_p=c.drop_p, seed=c.seed, seed_counter=self.seed_counter,
                             dgamma=self._grad(blk.norm1.weight), dbeta=self._grad(blk.norm1.bias), dparams=dparams,
                             dbias1=self._grad(blk.conv0.bias))
         # h0 = conv0(a0) + b0
@@ -507,7 +542,10 @@ class UNetEngine:
     def _run_fwd(self, xin, c_noise, aug, training, tape):
         net = self.net
         save = tape.items if tape is not None else None
-        step_seed = (self.base_seed * 1000003 + next(self._seed_iter)) if training else 0
+        step_seed = 0
+        if training:
+            step_seed = self.base_seed * 1000003 + self._seed_next
+            self._seed_next += 1
         emb_save = [] if tape is not None else None
         params_all = self.embed_fwd(c_noise, aug, emb_save)
         boff = {id(m): off for _, m, off in self.block_list}

@@ -42,8 +42,9 @@ int adm_qsample(const float* x0, const float* noise, const float* t, float* x_t,
  *     weighting != 0 else 1.  Writes per-sample loss [B] (caller sums / B) and, if non-null, the gradients of
  *     (sum_b loss_b)/B * grad_scale w.r.t. C_pred and eps_pred.
  *     use_l1 is a flag word: 1 = + w*mean|.| then /2 (image space, ddm_const.py:345-348); 2 = + w*sum|.| then /2
- *     (latent, ddm_const_2.py:561-564); 4 = + the latent reconstruction term -log(t)/2 * sum|x_rec - x0|
- *     (ddm_const_2.py:566-568), in which case loss_per_sample has 2*B entries: [total | that term].          */
+ *     (latent, ddm_const_2.py:561-564); 4 = + the latent reconstruction term W * sum|x_rec - x0| (ddm_const_2.py:565-568;
+ *     the reference's [B] x [B,1] broadcast sums an outer product, i.e. every sample is weighted by
+ *     W = sum_j -log(t_j)/2), in which case loss_per_sample has 2*B entries: [total | that term].           */
 int adm_ddm_loss(const float* c_pred, const float* eps_pred, const float* x0, const float* noise, const float* t,
                  float eps, int weighting, int use_l1, float grad_scale, float* loss_per_sample, float* d_c_pred,
                  float* d_eps_pred, long long batch, long long chw, void* stream);
@@ -133,9 +134,9 @@ int adm_cast_f32_bf16(const float* src, void* dst, long long numel, void* stream
  * UNetBlock.forward (:191, :193-196, :200): silu, addcmul(shift, norm, scale+1), dropout, plus the depthwise 2x2
  * resample of Conv2d.forward (:105-108) when it directly follows.  x1 (+ optional x2 = fused torch.cat, :570-571).
                                                                                                               */
-/* Optional device-resident u64 step counter mixed into every dropout seed (lets a captured CUDA graph draw fresh
- * masks per replay); NULL disables. */
-int adm_set_seed_counter(const unsigned long long* dev_counter);
+/* seed_counter (adm_gn_apply / adm_gn_forward / adm_gn_bwd): optional device-resident u64 step counter mixed into the
+ * dropout seed, so that a captured CUDA graph draws fresh masks per replay.  It is passed per call (no process-global
+ * state), dereferenced only when drop_p > 0, and may be NULL. */
 int adm_gn_stats(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int hw,
                  int groups, float eps, const float* gamma, const float* beta, const float* params,
                  long long ld_params, float* work, float* coef, void* stream);
@@ -145,8 +146,8 @@ int adm_gn_stats(const void* x1, int c1, long long ld1, const void* x2, int c2, 
 /* y = act(x*A + B); act 1 = SiLU; drop_p > 0 applies Philox dropout keyed by seed; resample 0 none / 1 2x2 average /
  * 2 nearest x2.                                                                                              */
 int adm_gn_apply(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int h, int w,
-                 const float* coef, int act, float drop_p, unsigned long long seed, int resample, void* out,
-                 long long ldo, void* stream);
+                 const float* coef, int act, float drop_p, unsigned long long seed,
+                 const unsigned long long* seed_counter, int resample, void* out, long long ldo, void* stream);
 /* Backward of gn_stats + gn_apply.  dy: gradient at the op's output (its resolution).  Accumulates dgamma/dbeta (+=,
  * atomics), writes dparams [n][ld_dparams] = (dscale | dshift), and dx1/dx2 (+ `add`, a skip-path gradient over the
  * full channel range: add_mode 0 same resolution, 1 half resolution spread /4, 2 double resolution summed 2x2).
@@ -155,9 +156,10 @@ int adm_gn_apply(const void* x1, int c1, long long ld1, const void* x2, int c2, 
 int adm_gn_bwd(const void* dy, long long ldy, const void* x1, int c1, long long ld1, const void* x2, int c2,
                long long ld2, int n, int h, int w, int groups, const float* coef, const float* gamma,
                const float* beta, const float* params, long long ld_params, int act, float drop_p,
-               unsigned long long seed, int resample, float* work, float* bcoef, float* dgamma, float* dbeta,
-               float* dparams, long long ld_dparams, const void* add, long long ldadd, int add_mode, void* dx1,
-               long long ldx1, void* dx2, long long ldx2, float* dbias1, float* dbias1b, void* stream);
+               unsigned long long seed, const unsigned long long* seed_counter, int resample, float* work,
+               float* bcoef, float* dgamma, float* dbeta, float* dparams, long long ld_dparams, const void* add,
+               long long ldadd, int add_mode, void* dx1, long long ldx1, void* dx2, long long ldx2, float* dbias1,
+               float* dbias1b, void* stream);
 /*   dbias1, dbias1b (optional, fp32 [c1]): += column sums of dx1 — the bias gradient of the conv(s) that produced x1
  *   (conv1 and the 1x1 skip of a UNetBlock share it; unet/uncond_unet.py:111-112 backward), so no separate pass
  *   over dx1 is needed.
@@ -167,7 +169,7 @@ int adm_gn_bwd(const void* dy, long long ldy, const void* x1, int c1, long long 
 int adm_gn_forward(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int h, int w,
                    int groups, float eps, const float* gamma, const float* beta, const float* params,
                    long long ld_params, float* work, float* coef, int act, float drop_p, unsigned long long seed,
-                   int resample, void* out, long long ldo, void* stream);
+                   const unsigned long long* seed_counter, int resample, void* out, long long ldo, void* stream);
 /* out[c] += sum_rows x[row][c] (bias gradients, unet/uncond_unet.py:111-112 backward). */
 int adm_col_sums(const void* x, long long ld, long long rows, int c, float* out, void* stream);
 /* out = a + b (+ c): gradient fan-in of the skip connections (torch autograd's implicit adds, unet/uncond_unet.py:563-564) */
@@ -236,6 +238,9 @@ int adm_adamw(float* p, const float* g, float* m, float* v, long long numel, flo
  *   CUDA graph of the step can be replayed with fresh values.  p_bf16 (optional, bf16 [numel]): a bf16 shadow of the
  *   updated parameters written in the same pass — the tensor-core operands of the next step, so no separate
  *   weight re-pack is needed for parameters whose arena layout already is the packed [Cout][tap][Cin] order.     */
+/* EMA of the weights as one pass over the flat arena (ddm/ema.py:141-156, EMA.update -> update_moving_average:
+ * ma.lerp_(current, 1 - decay) per tensor): dst[i] += weight * (src[i] - dst[i]).                              */
+int adm_lerp_f32(float* dst, const float* src, long long numel, float weight, void* stream);
 
 #ifdef __cplusplus
 }

@@ -14,9 +14,11 @@ A CPU restatement, in plain functional PyTorch (fp32 / fp64), of the reference's
 Parity pin: tests/golden/*.json were produced by tests/golden/make_golden.py, which imports the *unmodified* reference
 ``unet.uncond_unet.EDMPrecond`` (and ``ddm.ddm_const_2.DDPM`` for the plumbing cross-check) from /root/reference in the
 build container and records its outputs on seeded inputs; tests/test_oracle.py checks this file against them.
-The reference's own ``ddm/ddm_const.py`` is not importable (needs ldm/cldm/pytorch_lightning), so the DDM-const step
-itself is pinned by (a) the sibling ddm_const_2.DDPM run with const_2's three formulas swapped in and (b) the UNet
-being pinned bit-for-bit.
+The DDM-const math is pinned DIRECTLY: tests/golden/make_golden_ddm.py imports the reference's own
+``ddm/ddm_const.py`` with its absent import-only packages (ldm, cldm, pytorch_lightning, ...) stubbed and records what
+the unmodified ``DDPM.q_sample / pred_x0_from_xt / pred_xtms_from_xt / p_losses / sample_fn_d / sample_fn_s`` (and the
+sibling's ``LatentDiffusion.p_losses``) return on seeded inputs with a closed-form denoiser (tests/golden/ddm_math.pt);
+tests/test_oracle.py checks every function below against it.
 """
 from __future__ import annotations
 
@@ -281,6 +283,21 @@ def q_sample(x_start, noise, t):
     return x_start + c * time + torch.sqrt(time) * noise
 
 
+def pred_x0_from_xt(xt, noise, c, t):
+    """ddm_const.py:290-293."""
+    time = t.reshape(c.shape[0], *((1,) * (c.dim() - 1)))
+    return xt - c * time - torch.sqrt(time) * noise
+
+
+def pred_xtms_from_xt(xt, noise, c, t, s, z):
+    """ddm_const.py:296-303 with the Gaussian draw passed in (z replaces randn_like, :300)."""
+    time = t.reshape(c.shape[0], *((1,) * (c.dim() - 1)))
+    s = s.reshape(c.shape[0], *((1,) * (c.dim() - 1)))
+    mean = xt + c * (time - s) - c * time - s / torch.sqrt(time) * noise
+    sigma = torch.sqrt(s * (time - s) / time)
+    return mean + sigma * z
+
+
 def ddm_loss(c_pred, noise_pred, x_start, noise, t, eps=1e-4, weighting=True, use_l1=False):
     """ddm_const.py:335-358 with loss_main_func = MSE_Loss(reduction='sum') and loss_vlb = 0.
     Returns (loss, loss_simple_per_sample)."""
@@ -346,15 +363,16 @@ def sample_fn_d(model_fn: Callable, x_T, n_steps, sigma_min=1e-2, sigma_max=1.0,
 def sample_fn_s(model_fn: Callable, x_T, z_list, n_steps, sigma_min=1e-2, sigma_max=1.0, scale_input=1.0,
                 clip_x_start=True, unnormalize=True):
     """ddm_const.py:381-422 with the per-step Gaussian draws passed in (z_list[i] replaces randn_like, :300)."""
-    idx = torch.arange(n_steps, dtype=torch.float64)
+    dev = x_T.device
+    idx = torch.arange(n_steps, dtype=torch.float64, device=dev)
     ts = (sigma_max ** 2) + idx / (n_steps - 1) * (sigma_min ** 2 - sigma_max ** 2)
-    ts = torch.cat((ts, torch.tensor([0.0], dtype=torch.float64)))
+    ts = torch.cat((ts, torch.tensor([0.0], dtype=torch.float64, device=dev)))
     time_steps = -torch.diff(ts)
     img = x_T.to(torch.float32)
     batch = img.shape[0]
-    cur_time = torch.ones((batch,), dtype=torch.float64)
+    cur_time = torch.ones((batch,), dtype=torch.float64, device=dev)
     for i, time_step in enumerate(time_steps):
-        s = torch.full((batch,), float(time_step), dtype=torch.float64)
+        s = torch.full((batch,), float(time_step), dtype=torch.float64, device=dev)
         if i == time_steps.shape[0] - 1:
             s = cur_time
         c, noise = model_fn(img, cur_time)[:2]
@@ -377,11 +395,32 @@ def sample_fn_s(model_fn: Callable, x_T, z_list, n_steps, sigma_min=1e-2, sigma_
 
 
 # ----------------------------------------------------------------------------------------------- latent variant
-def p_losses_latent(model_fn: Callable, x_start, t, noise, eps=1e-4, weighting=True, use_l1=True, **model_kwargs):
+def p_losses_latent(model_fn: Callable, x_start, t, noise, eps=1e-4, weighting=True, use_l1=True, variant="const",
+                    **model_kwargs):
     """LatentDiffusion.p_losses: structure of ddm_const_2.py:527-588 (L1 as a SUM over CHW :561-564, reconstruction term
-    -log(t)/2 * sum|x_rec - x0| :566-568, use_disloss off) with the sqrt(t) schedule's formulas: q_sample
-    ddm_const.py:284-287, x_rec = pred_x0_from_xt ddm_const.py:290-293, weights ddm_const.py:336-338."""
+    -log(t)/2 * sum|x_rec - x0| :566-568, use_disloss off).
+    variant "const"  : the sqrt(t) schedule's formulas — q_sample ddm_const.py:284-287, x_rec = pred_x0_from_xt
+                       ddm_const.py:290-293, weights ddm_const.py:336-338 (the fork's own latent p_losses, :716-784, is a
+                       nuScenes segmentation objective and unusable here);
+    variant "const_2": the sibling file verbatim — t-linear noise (ddm_const_2.py:175,181) and weights
+                       ((t-1)/t)^2+1, (t/(1-t+eps))^2+1 (:553-555)."""
     b = x_start.shape[0]
+    if variant == "const_2":
+        tt = t.reshape(b, 1, 1, 1)
+        x_noisy = x_start + (-x_start) * tt + tt * noise
+        c_pred, noise_pred = model_fn(x_noisy, t, **model_kwargs)[:2]
+        x_rec = x_noisy - c_pred * tt - tt * noise_pred
+        c = -x_start
+        w1 = ((t - 1) / t) ** 2 + 1 if weighting else torch.ones_like(t)
+        w2 = (t / (1 - t + eps)) ** 2 + 1 if weighting else torch.ones_like(t)
+        ls = w1 * ((c_pred - c) ** 2).sum([1, 2, 3]) + w2 * ((noise_pred - noise) ** 2).sum([1, 2, 3])
+        if use_l1:
+            ls = (ls + w1 * (c_pred - c).abs().sum([1, 2, 3]) + w2 * (noise_pred - noise).abs().sum([1, 2, 3])) / 2
+        vlb = (x_rec - x_start).abs().sum([1, 2, 3]) * (-torch.log(t.reshape(b, 1)) / 2)  # [B, B], as the reference
+        loss = ls.sum() / b + vlb.sum() / b
+        n = float(x_start.numel())
+        return loss, {"train/loss_simple": ls.detach().sum() / n, "train/loss_vlb": vlb.detach().sum() / n,
+                      "train/loss": loss.detach() / n}
     x_noisy = q_sample(x_start, noise, t)
     c_pred, noise_pred = model_fn(x_noisy, t, **model_kwargs)[:2]
     tt = t.reshape(b, 1, 1, 1)
@@ -396,7 +435,9 @@ def p_losses_latent(model_fn: Callable, x_start, t, noise, eps=1e-4, weighting=T
     if use_l1:
         ls = ls + w1 * (c_pred - c).abs().sum([1, 2, 3]) + w2 * (noise_pred - noise).abs().sum([1, 2, 3])
         ls = ls / 2
-    vlb = (x_rec - x_start).abs().sum([1, 2, 3]) * (-torch.log(t) / 2)
+    # rec_weight has shape [B, 1] in the reference (ddm_const_2.py:565): [B] * [B, 1] broadcasts to the [B, B] outer
+    # product, whose sum is (sum_i a_i) * (sum_j w_j).  Reproduced as is.
+    vlb = (x_rec - x_start).abs().sum([1, 2, 3]) * (-torch.log(t.reshape(b, 1)) / 2)
     loss = ls.sum() / b + vlb.sum() / b
     n = float(x_start.numel())
     return loss, {"train/loss_simple": ls.detach().sum() / n, "train/loss_vlb": vlb.detach().sum() / n,

@@ -43,8 +43,9 @@ def main():
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         dist.init_process_group("nccl", device_id=device)
     rank = dist.get_rank() if dist.is_initialized() else 0
-    torch.manual_seed(1234 + rank)
+    torch.manual_seed(1234)  # identical initial weights on every rank (TrainStep also broadcasts rank 0's arena)
     model = build_model(cfg, device)
+    torch.manual_seed(1234 + rank)  # per-rank streams for t, noise, dropout and augmentation from here on
     t, d = cfg["trainer"], cfg["data"]
     if d.get("class_name", "synthetic") == "synthetic":
         dl = synthetic_loader(d["batch_size"], d["image_size"], seed=rank)

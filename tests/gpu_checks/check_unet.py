@@ -344,6 +344,136 @@ def unet_cifar():
     return ok
 
 
+def _psnr(a, b):
+    import torch
+    mse = ((a.double() - b.double()) ** 2).mean().item()
+    return 10 * torch.log10(torch.tensor(1.0 / max(mse, 1e-20))).item()
+
+
+@case
+def stochastic_sampler():
+    """DDPM.sample_fn_s (K3 stochastic variant, ddm_const.py:381-422) against oracle.sample_fn_s on the same x_T and
+    per-step Gaussian draws; PSNR >= 40 dB (north_star), N = 2 / 5 / 10."""
+    import torch
+    from oracle import ddm_oracle as O
+    from adm_b200.unet.uncond_unet import EDMPrecond
+    from adm_b200.ddm.ddm_const import DDPM
+    from tests.golden.make_golden import TINY
+    sd = O.make_state_dict(TINY, seed=0)
+    kw = {k: v for k, v in TINY.items() if k not in ("img_resolution", "img_channels", "label_dim")}
+    net = EDMPrecond(img_resolution=16, img_channels=3, sigma_data=1.0, model_type="DhariwalUNet", **kw)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    sdr = {k: v.cuda() for k, v in sd.items()}
+    ok = True
+    for n in (2, 5, 10):
+        cfg = dict(image_size=[16, 16], sampling_timesteps=n, eps=1e-4, sigma_max=1, sigma_min=0.01, weighting_loss=True,
+                   sample_type="stochastic")
+        dpm = DDPM(model=net, cfg=cfg, **cfg).cuda()
+        g = torch.Generator().manual_seed(100 + n)
+        x_T = torch.randn(8, 3, 16, 16, generator=g)
+        z = [torch.randn(8, 3, 16, 16, generator=g) for _ in range(n)]
+        img = dpm.sample(batch_size=8, x_T=x_T.cuda(), z_list=[zz.cuda() for zz in z])
+        with torch.no_grad():
+            ref = O.sample_fn_s(lambda xx, tt: O.edm_precond_forward(sdr, TINY, xx, tt), x_T.cuda(),
+                                [zz.cuda() for zz in z], n)
+        p = _psnr(img, ref)
+        print(f"  stochastic sampler N={n}: PSNR vs oracle {p:.2f} dB (need >= 40); range [{float(img.min()):.3f}, "
+              f"{float(img.max()):.3f}]", flush=True)
+        ok &= p >= 40 and float(img.min()) >= 0 and float(img.max()) <= 1
+    return ok
+
+
+def _oracle_step(sd, cfg, x, t, noise, aug, masks=None):
+    """fp32 oracle step on the GPU (same torch ops as the CPU oracle); returns (loss, grads by name)."""
+    import torch
+    from oracle import ddm_oracle as O
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sdr = {k: v.cuda().requires_grad_(not k.endswith("resample_filter")) for k, v in sd.items()}
+    c_ref, e_ref = O.edm_precond_forward(sdr, cfg, O.q_sample(x, noise, t), t, augment_labels=aug, dropout_masks=masks)
+    loss_ref, _ = O.ddm_loss(c_ref, e_ref, x, noise, t)
+    loss_ref.backward()
+    return loss_ref.item(), {k: v.grad for k, v in sdr.items() if v.grad is not None}
+
+
+def _compare_grads(net, grads_ref, cos_tol):
+    worst = []
+    gmax = max(float(g.norm()) for g in grads_ref.values())
+    for name, p in net.named_parameters():
+        gref = grads_ref[name]
+        if float(gref.norm()) < 1e-7 * gmax:
+            assert p.grad is None or float(p.grad.norm()) < 1e-3 * gmax, name
+            continue
+        a, b = p.grad.flatten().double(), gref.flatten().double()
+        worst.append(((a @ b / (a.norm() * b.norm() + 1e-30)).item(), name, (a.norm() / (b.norm() + 1e-30)).item()))
+    worst.sort(key=lambda z: z[0])
+    for cos, name, ratio in worst[:8]:
+        print(f"  grad cos {cos:.5f}  {name}  norm ratio {ratio:.4f}", flush=True)
+    nbad = sum(1 for w in worst if w[0] < cos_tol)
+    print(f"  params {len(worst)}, below cos {cos_tol}: {nbad}; min cos {worst[0][0]:.5f}", flush=True)
+    return nbad == 0
+
+
+def _train_step_case(cfg, batch, training, seed_in=3):
+    """One micro-step through adm_b200.train.TrainStep._direct_step — the code path bench.py times — against the oracle."""
+    import torch
+    from oracle import ddm_oracle as O
+    from adm_b200.unet.uncond_unet import EDMPrecond
+    from adm_b200.ddm.ddm_const import DDPM
+    from adm_b200.train import TrainStep
+    from tests.golden.make_golden import inputs
+    sd = O.make_state_dict(cfg, seed=0)
+    kw = {k: v for k, v in cfg.items() if k not in ("img_resolution", "img_channels", "label_dim")}
+    net = EDMPrecond(img_resolution=cfg["img_resolution"], img_channels=3, sigma_data=1.0, model_type="DhariwalUNet", **kw)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda()
+    net.train(training)
+    mcfg = dict(image_size=[cfg["img_resolution"]] * 2, sampling_timesteps=5, eps=1e-4, sigma_max=1, sigma_min=0.01,
+                weighting_loss=True, use_l1=False, use_augment=False)
+    dpm = DDPM(model=net, cfg=mcfg, **mcfg).cuda()
+    step = TrainStep(dpm, lr=1e-4)
+    x, t, noise, aug = (a.cuda() for a in inputs(cfg, batch, seed_in))
+    eng = net.model.engine
+    masks = None
+    if training:
+        # draw the masks this forward will draw: same seeds, exported through a probe forward with the tape kept
+        pos = eng.seed_position()
+        with torch.no_grad():
+            _, _, tape = eng.forward(O.q_sample(x, noise, t), t, aug, training=True, need_grad=True)
+        masks = eng.export_dropout_masks(tape)
+        del tape
+        eng.seed_position(pos)  # rewind: the measured step re-draws exactly these masks
+        keep = torch.cat([m.flatten() for m in masks.values()])
+        rate = float((keep > 0).float().mean())
+        print(f"  dropout: {len(masks)} masks, keep rate {rate:.4f} (p = {cfg['dropout']})", flush=True)
+        assert abs(rate - (1 - cfg["dropout"])) < 5e-3
+    loss = step.micro_step(x, t, noise, augment_labels=aug)
+    torch.cuda.synchronize()
+    loss_ref, grads_ref = _oracle_step(sd, cfg, x, t, noise, aug, masks)
+    rel = abs(loss.item() - loss_ref) / abs(loss_ref)
+    print(f"  TrainStep loss {loss.item():.5f} vs oracle {loss_ref:.5f} rel={rel:.3e} (tol 1e-2)", flush=True)
+    ok = rel < 1e-2
+    ok &= _compare_grads(net, grads_ref, 0.999)
+    return ok
+
+
+@case
+def unet_cifar_b128():
+    """The benchmark configuration itself: CIFAR-10 net at batch 128 (fused one-cluster-per-sample GroupNorm, persistent
+    148-CTA tiling, split-K wgrad, two-stream fork/join, gradient arena) vs the fp32 oracle."""
+    from tests.golden.make_golden import CIFAR
+    return _train_step_case(dict(CIFAR), 128, training=False)
+
+
+@case
+def unet_dropout_on():
+    """Training mode with dropout 0.1: the kernel's hash masks are exported and fed to the oracle's dropout."""
+    from tests.golden.make_golden import CIFAR
+    cfg = dict(CIFAR, model_channels=64, num_blocks=1)
+    return _train_step_case(cfg, 16, training=True)
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] != "--all":
         import torch

@@ -1,4 +1,5 @@
-"""CPU, world_size 2 over gloo: the overlapped bucketed gradient reduction of TrainStep (host logic of the DP path).
+"""CPU, world_size 2 over gloo: replica synchronisation at construction and the overlapped bucketed gradient reduction of
+TrainStep (host logic of the DP path).
 The engine's backward is simulated by filling rank-dependent gradients and firing the gradient-ready hooks in
 completion order."""
 import os
@@ -26,7 +27,7 @@ def _worker(rank, world, port, out):
     from adm_b200.ddm.ddm_const import DDPM
     from adm_b200.train import TrainStep
     from adm_b200.unet.uncond_unet import EDMPrecond
-    torch.manual_seed(0)
+    torch.manual_seed(100 + rank)  # replicas start from DIFFERENT weights: TrainStep must broadcast rank 0's
     kw = {k: v for k, v in TINY.items() if k not in ("img_resolution", "img_channels", "label_dim")}
     net = EDMPrecond(img_resolution=16, img_channels=3, sigma_data=1.0, model_type="DhariwalUNet", **kw)
     cfg = dict(image_size=[16, 16], sampling_timesteps=3)
@@ -34,6 +35,9 @@ def _worker(rank, world, port, out):
     step = TrainStep(dpm, bucket_mb=1)  # ~6 M parameters -> many 1 MiB buckets
     assert step.world == world and len(step.buckets) > 8
     a = step.arena
+    flats = [torch.empty_like(a.flat) for _ in range(world)]
+    dist.all_gather(flats, a.flat)
+    same_weights = all(torch.equal(f, flats[0]) for f in flats) and float(a.flat.abs().sum()) > 0
     # fake backward: rank r contributes (r + 1) * ramp; hooks fire block by block in completion order
     ramp = torch.arange(a.numel, dtype=torch.float32) % 97
     step._arm()
@@ -51,7 +55,7 @@ def _worker(rank, world, port, out):
     # parameters see the reduced gradients through their .grad views
     p = a.params[5]
     ok = ok and torch.equal(p.grad.flatten(), expect[a.offsets[5]:a.offsets[5] + p.numel()])
-    out[rank] = bool(ok)
+    out[rank] = bool(ok and same_weights)
     dist.destroy_process_group()
 
 

@@ -36,6 +36,23 @@ def test_gemm_engine_and_ddm_kernels(case):
     assert CK.CASES[case]()
 
 
+def test_ddm_kernels_vs_reference_functions():
+    """K1/K2/K3 (both samplers) against outputs of the unmodified ddm/ddm_const.py functions (tests/golden/ddm_math.pt)."""
+    assert CK.CASES["ddm_math_vs_reference"]()
+
+
+def test_stochastic_sampler_vs_oracle():
+    assert CU.CASES["stochastic_sampler"]()
+
+
+def test_benchmark_configuration_b128_step_vs_oracle():
+    assert CU.CASES["unet_cifar_b128"]()
+
+
+def test_training_mode_dropout_masks_vs_oracle():
+    assert CU.CASES["unet_dropout_on"]()
+
+
 @pytest.mark.parametrize("case", ["groupnorm", "small_ops", "attention", "spatial_att"])
 def test_norm_attention_kernels(case):
     assert CU.CASES[case]()

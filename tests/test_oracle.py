@@ -69,6 +69,65 @@ def test_cifar_forward_matches_reference(golden_dir):
     _close(checksum(e_pred)["abssum"], g["eps_pred"]["abssum"])
 
 
+# ---------------------------------------------------------------- DDM-const math pinned DIRECTLY to the reference
+def _ddm_math(golden_dir):
+    return torch.load(os.path.join(golden_dir, "ddm_math.pt"))
+
+
+def _same(a, b, tol=1e-6):
+    a, b = a.double(), b.double()
+    assert a.shape == b.shape
+    assert (a - b).abs().max().item() <= tol * max(1.0, b.abs().max().item()), (a - b).abs().max().item()
+
+
+def test_oracle_elementwise_math_vs_reference_functions(golden_dir):
+    """oracle.q_sample / pred_x0_from_xt / pred_xtms_from_xt vs the unmodified ddm/ddm_const.py:284-303."""
+    g = _ddm_math(golden_dir)
+    x, t, noise, s = g["x"], g["t"], g["noise"], g["s"]
+    xt = O.q_sample(x, noise, t)
+    _same(xt, g["q_sample"], 0)  # same torch expression -> bit-exact
+    _same(O.pred_x0_from_xt(xt, noise, -x, t), g["pred_x0_from_xt"], 0)
+    _same(O.pred_xtms_from_xt(xt, noise, -x, t, s, g["pred_xtms_z"]), g["pred_xtms_from_xt"], 0)
+
+
+@pytest.mark.parametrize("weighting", [True, False])
+@pytest.mark.parametrize("use_l1", [False, True])
+def test_oracle_p_losses_vs_reference_p_losses(golden_dir, weighting, use_l1):
+    """oracle.p_losses vs DDPM.p_losses (ddm_const.py:305-364) on the noise the reference itself drew."""
+    from tests.golden.make_golden_ddm import toy_model
+    g = _ddm_math(golden_dir)
+    ref = g[f"p_losses_w{int(weighting)}_l1{int(use_l1)}"]
+    loss, ld = O.p_losses(toy_model, g["x"], g["t"], ref["noise"], weighting=weighting, use_l1=use_l1)
+    _close(loss.item(), ref["loss"].item(), 1e-6)
+    for k in ("train/loss_simple", "train/loss_vlb", "train/loss"):
+        _close(float(ld[k]), float(ref[k]), 1e-6)
+
+
+@pytest.mark.parametrize("n", [2, 5, 10])
+def test_oracle_samplers_vs_reference_samplers(golden_dir, n):
+    """oracle.sample_fn_d / sample_fn_s vs ddm_const.py:425-476 / :381-422 with the reference's own random draws."""
+    from tests.golden.make_golden_ddm import toy_model
+    g = _ddm_math(golden_dir)
+    d = g[f"sample_fn_d_{n}"]
+    img = O.sample_fn_d(toy_model, d["x_T"], n)
+    assert img.dtype == torch.float64
+    _same(img, d["img"], 1e-12)
+    s = g[f"sample_fn_s_{n}"]
+    img = O.sample_fn_s(toy_model, s["x_T"], list(s["z"]), n)
+    _same(img, s["img"], 1e-5)
+
+
+@pytest.mark.parametrize("use_l1", [False, True])
+def test_oracle_latent_loss_const2_variant_vs_reference(golden_dir, use_l1):
+    """oracle.p_losses_latent(variant='const_2') vs the sibling LatentDiffusion.p_losses (ddm_const_2.py:527-588)."""
+    from tests.golden.make_golden_ddm import toy_model
+    g = _ddm_math(golden_dir)
+    ref = g[f"latent2_p_losses_l1{int(use_l1)}"]
+    loss, ld = O.p_losses_latent(toy_model, g["x"], g["t"], ref["noise"], use_l1=use_l1, variant="const_2")
+    _close(loss.item(), ref["loss"].item(), 1e-6)
+    _close(float(ld["train/loss_vlb"]), float(ref["train/loss_vlb"]), 1e-6)
+
+
 def test_const2_plumbing_crosscheck(golden_dir):
     """The importable sibling class reproduced the restated step exactly when given its three formulas."""
     g = _load(golden_dir, "const2_step.json")
