@@ -68,7 +68,7 @@ SIGNATURES = {
     "adm_silu": (c_i, [c_p, c_p, c_p, c_ll, c_p]),
     "adm_silu_bwd": (c_i, [c_p, c_p, c_p, c_p, c_ll, c_p]),
     "adm_attn_fwd_fused": (c_i, [c_p, c_i, c_i, c_i, c_f, c_p, c_p, c_p]),
-    "adm_attn_bwd_fused": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p, c_p, c_p]),
+    "adm_attn_bwd_fused": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p, c_p]),
     "adm_softmax_fwd": (c_i, [c_p, c_p, c_ll, c_i, c_p]),
     "adm_softmax_bwd": (c_i, [c_p, c_p, c_p, c_f, c_ll, c_i, c_p]),
     "adm_spatial_att_fwd": (c_i, [c_p, c_ll, c_p, c_ll, c_p, c_p, c_i, c_i, c_i, c_p, c_ll, c_p, c_p, c_p]),

@@ -129,15 +129,15 @@ class _AttentionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, heads, scale):
         qkv = _nhwc(qkv)
-        a, p = ops.attention_fwd(qkv, heads, scale)
-        ctx.save_for_backward(qkv, p)
+        a, aux = ops.attention_fwd(qkv, heads, scale)  # aux: log-sum-exp (fused kernel) or probabilities (unfused)
+        ctx.save_for_backward(qkv, aux, a)
         ctx.heads, ctx.scale = heads, scale
         return a
 
     @staticmethod
     def backward(ctx, da):
-        qkv, p = ctx.saved_tensors
-        return ops.attention_bwd(_nhwc(da), qkv, p, ctx.heads, ctx.scale), None, None
+        qkv, aux, a = ctx.saved_tensors
+        return ops.attention_bwd(_nhwc(da), qkv, aux, ctx.heads, ctx.scale, a=a), None, None
 
 
 def attention(qkv, heads, scale):

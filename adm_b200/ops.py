@@ -445,23 +445,30 @@ def _gemm(desc_kw, a_op, b_op, what):
     check(_lib.load().adm_gemm_batched(d, _stream()), what)
 
 
+def attention_fused_ok(d, hw):
+    """Shapes served by the fused K9 kernels (everything else runs as batched GEMMs + a softmax kernel)."""
+    return d == 64 and hw in (16, 64, 256)
+
+
 def attention_fwd(qkv, heads, scale=None, need_p=True, fused=None):
-    """qkv: [N, H, W, 3C] bf16 laid out as (q | k | v), each [heads, d].  Returns (a [N,H,W,C], p [N*heads,HW,HW]).
-    scale defaults to 1/sqrt(d) (d = C / heads as stored, which may include zero padding of the head dim).
-    With d == 64 and HW in {16, 64, 256} the whole op is ONE fused kernel (K9); p is None unless need_p."""
+    """qkv: [N, H, W, 3C] bf16 laid out as (q | k | v), each [heads, d].  Returns (a [N,H,W,C], aux) where aux is what
+    attention_bwd needs besides qkv and a: the per-row log-sum-exp [N, heads, HW] fp32 for the fused kernel (d == 64, HW in
+    {16, 64, 256}: ONE kernel, probabilities only ever in TMEM), or the normalised probabilities [N*heads, HW, HW] bf16
+    for the unfused path.  aux is None when need_p is False.
+    scale defaults to 1/sqrt(d) (d = C / heads as stored, which may include zero padding of the head dim)."""
     n, h, w, c3 = qkv.shape
     c, hw = c3 // 3, h * w
     d = c // heads
     scale = 1.0 / d ** 0.5 if scale is None else float(scale)
     assert qkv.is_contiguous()
     if fused is None:
-        fused = d == 64 and hw in (16, 64, 256)
+        fused = attention_fused_ok(d, hw)
     if fused:
         a = torch.empty(n, h, w, c, device=qkv.device, dtype=BF16)
-        p = torch.empty(n * heads, hw, hw, device=qkv.device, dtype=BF16) if need_p else None
-        check(_lib.load().adm_attn_fwd_fused(_ptr(qkv), n, hw, heads, scale, _ptr(a), _ptr(p), _stream()),
+        lse = torch.empty(n, heads, hw, device=qkv.device, dtype=F32) if need_p else None
+        check(_lib.load().adm_attn_fwd_fused(_ptr(qkv), n, hw, heads, scale, _ptr(a), _ptr(lse), _stream()),
               "attn_fwd_fused")
-        return a, p
+        return a, lse
     s = torch.empty(n * heads, hw, hw, device=qkv.device, dtype=F32)
     qk_dims, qk_str = (c3, hw, n), (c3, c3 * hw)
     _gemm(dict(m=hw, n=hw, k=d, batches=n * heads, bdiv=heads, splits=1, c=s.data_ptr(), out_mode=1, ldc=hw,
@@ -477,35 +484,29 @@ def attention_fwd(qkv, heads, scale=None, need_p=True, fused=None):
     return a, p
 
 
-def attention_bwd(da, qkv, p, heads, scale=None, fused=None):
-    """Returns dqkv [N,H,W,3C] bf16.  With d == 64 and HW in {16, 64, 256}: dP, dS and dQ come from ONE fused kernel
-    (dP stays in TMEM); dV and dK are two batched GEMMs."""
+def attention_bwd(da, qkv, aux, heads, scale=None, fused=None, a=None):
+    """Returns dqkv [N,H,W,3C] bf16.  Fused (aux = log-sum-exp, `a` = the forward output): ONE kernel recomputes the
+    probabilities and produces dQ, dK, dV.  Unfused (aux = the saved probabilities): five batched GEMMs + softmax_bwd."""
     n, h, w, c3 = qkv.shape
     c, hw = c3 // 3, h * w
     d = c // heads
     scale = 1.0 / d ** 0.5 if scale is None else float(scale)
     assert da.is_contiguous() and qkv.is_contiguous()
     dqkv = torch.empty_like(qkv)
+    if fused is None:
+        fused = attention_fused_ok(d, hw)
+    if fused:
+        assert a is not None and a.is_contiguous() and aux is not None and aux.dtype == F32, \
+            "fused attention backward needs the forward output and its log-sum-exp"
+        check(_lib.load().adm_attn_bwd_fused(_ptr(da), _ptr(qkv), _ptr(a), _ptr(aux), n, hw, heads, scale, _ptr(dqkv),
+                                             _stream()), "attn_bwd_fused")
+        return dqkv
+    p = aux
     qk_dims, qk_str = (c3, hw, n), (c3, c3 * hw)
     a_dims, a_str = (c, hw, n), (c, c * hw)
     p_dims, p_str = (hw, hw, n * heads), (hw, hw * hw)
     nb = n * heads
     esz = 2
-    if fused is None:
-        fused = d == 64 and hw in (16, 64, 256)
-    if fused:
-        ds = torch.empty_like(p)
-        check(_lib.load().adm_attn_bwd_fused(_ptr(da), _ptr(qkv), _ptr(p), n, hw, heads, scale, _ptr(ds), _ptr(dqkv),
-                                             _stream()), "attn_bwd_fused")
-        _gemm(dict(m=hw, n=d, k=hw, batches=nb, bdiv=heads, splits=1, c=dqkv.data_ptr() + 2 * c * esz, out_mode=0,
-                   ldc=c3, c_bhi=hw * c3, c_blo=0, c_col_lo=d, alpha=1.0),
-              _operand(p, 1, p_dims, p_str, bhi=heads, blo=1),
-              _operand(da, 1, a_dims, a_str, c0=0, c0_lo=d, bhi=1), "attn dV")
-        _gemm(dict(m=hw, n=d, k=hw, batches=nb, bdiv=heads, splits=1, c=dqkv.data_ptr() + c * esz, out_mode=0, ldc=c3,
-                   c_bhi=hw * c3, c_blo=0, c_col_lo=d, alpha=1.0),
-              _operand(ds, 1, p_dims, p_str, bhi=heads, blo=1),
-              _operand(qkv, 1, qk_dims, qk_str, c0=0, c0_lo=d, bhi=1), "attn dK")
-        return dqkv
     # dV[k, d] = sum_q P[q, k] dA[q, d]
     _gemm(dict(m=hw, n=d, k=hw, batches=nb, bdiv=heads, splits=1, c=dqkv.data_ptr() + 2 * c * esz, out_mode=0,
                ldc=c3, c_bhi=hw * c3, c_blo=0, c_col_lo=d, alpha=1.0),

@@ -406,7 +406,7 @@ class UNetEngine:
             if not dout_bias_done:
                 self._bias_grad(blk.proj.bias, dout)
             datt = ops.conv_dgrad(dout, wp)
-            dqkv = ops.attention_bwd(datt, c.qkv, c.p, heads, scale=d ** -0.5)
+            dqkv = ops.attention_bwd(datt, c.qkv, c.p, heads, scale=d ** -0.5, a=c.att)
             dwq = ops.conv_wgrad(dqkv, c.a2, ntaps=1)  # [3*heads*dpad, 1, pad64(cout)]
             gq = dwq[:, 0, :cout].reshape(3, heads, dpad, cout)[:, :, :d]
             self._grad(blk.qkv.weight).view(3 * cout, cout).index_add_(0, rows.reshape(-1), gq.reshape(-1, cout))
@@ -418,7 +418,7 @@ class UNetEngine:
             perm = self.qkv_perm(cout, blk.num_heads)
             self._conv_param_grads(blk.proj, dout, c.att, bias_done=dout_bias_done)
             datt = self._dgrad(dout, blk.proj, self.conv_w(blk.proj))
-            dqkv = ops.attention_bwd(datt, c.qkv, c.p, blk.num_heads)
+            dqkv = ops.attention_bwd(datt, c.qkv, c.p, blk.num_heads, a=c.att)
             self._conv_param_grads(blk.qkv, dqkv, c.a2, perm=perm)
             da2 = self._dgrad(dqkv, blk.qkv, self.conv_w(blk.qkv, perm=perm[0]))
         if blk.num_heads:

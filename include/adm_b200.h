@@ -187,17 +187,20 @@ int adm_silu_bwd(const float* x, const float* dy, float* dx, void* dx_bf16, long
  * backward: dS = scale * P * (dP - sum_j dP_j P_j).                                                           */
 int adm_softmax_fwd(const float* s, void* p, long long rows, int len, void* stream);
 int adm_softmax_bwd(const void* p, const float* dp, void* ds, float scale, long long rows, int len, void* stream);
-/* K9 forward, fused: one CTA per (sample, head) keeps S = Q K^T in TMEM, runs the softmax in registers, writes P as the
- * swizzled A operand of the second tcgen05 MMA and stores O = P V — S and P never touch HBM (p_out == NULL) or only the
- * normalised bf16 P does (training; the backward kernels consume it).  qkv [batch][n_pix][3*heads*64] bf16 laid out
- * (q | k | v) x head x 64; n_pix in {16, 64, 256}; out [batch][n_pix][heads*64]; p_out [batch*heads][n_pix][n_pix].  */
-int adm_attn_fwd_fused(const void* qkv, int batch, int n_pix, int heads, float scale, void* out, void* p_out,
+/* K9 forward, fused (unet/uncond_unet.py:204-208; cond_unet.Attention, unet/cond_unet.py:533-555 with zero-padded heads):
+ * persistent CTAs walk (sample, head) units; S = Q K^T lives in TMEM, the softmax runs in registers, P is written back
+ * to TMEM as bf16 and consumed from there as the A operand of O = P V.  Neither S nor P ever reaches shared memory or
+ * HBM.  qkv [batch][n_pix][3*heads*64] bf16 laid out (q | k | v) x head x 64; n_pix in {16, 64, 256} (small images are
+ * packed 2 / 8 samples per 128-row tile); out [batch][n_pix][heads*64] bf16; lse (optional) [batch][heads][n_pix] fp32 =
+ * log2-domain log-sum-exp of every query row, the only thing the backward needs besides qkv and out.           */
+int adm_attn_fwd_fused(const void* qkv, int batch, int n_pix, int heads, float scale, void* out, float* lse,
                        void* stream);
-/* K9 backward, fused part: dP = dO V^T (TMEM) -> dS = scale * P o (dP - rowsum(dP o P)) -> dQ = dS K in ONE kernel per
- * (sample, head); dS (bf16, the shape of P) is also written out for the dK product.  da [batch][n_pix][heads*64];
- * dQ is written into channels [0, C) of dqkv [batch][n_pix][3C].  dV = P^T dO and dK = dS^T Q use adm_gemm_batched. */
-int adm_attn_bwd_fused(const void* da, const void* qkv, const void* p_saved, int batch, int n_pix, int heads,
-                       float scale, void* ds_out, void* dqkv, void* stream);
+/* K9 backward, ONE kernel: recomputes P from qkv and lse (nothing N x N is read from HBM), and produces dQ, dK and dV:
+ * S^T = K Q^T and dP^T = V dO^T in TMEM, dS^T = scale P^T (dP^T - rowsum(dO o O)), dV += P^T dO and dK += dS^T Q with
+ * the A operand read from TMEM, dQ += dS K through a shared-memory tile.  da [batch][n_pix][heads*64] bf16 (gradient
+ * of out), out_fwd = the forward output, dqkv [batch][n_pix][3*heads*64] bf16 (dq | dk | dv).                 */
+int adm_attn_bwd_fused(const void* da, const void* qkv, const void* out_fwd, const float* lse, int batch, int n_pix,
+                       int heads, float scale, void* dqkv, void* stream);
 /* SpatialAtt + residual of the decouple branches (unet/uncond_unet.py:27-37, :566-567):
  * out = softsign(softmax(q k^T) att) * h + res with att = h . w_map + b; scalars = {b_map, wq, bq, wk, bk}.   */
 int adm_spatial_att_fwd(const void* h, long long ldh, const void* res, long long ldr, const float* w_map,
