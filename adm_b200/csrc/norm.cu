@@ -94,6 +94,24 @@ __device__ __forceinline__ float silu_grad_precise(float v) {
     return s * (1.f + v * (1.f - s));
 }
 
+__device__ __forceinline__ Vec8 unpack8(const uint4 u) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    Vec8 r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        r.v[2 * i] = __uint_as_float(w[i] << 16);
+        r.v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+    return r;
+}
+// tanh-form SiLU on a pre-halved pre-activation h = v/2:  silu(v) = h*tanh(h) + h,
+// silu'(v) = 0.5 * (1 + T + h * (1 - T^2)), T = tanh(h).
+__device__ __forceinline__ float tanh_fast(float h) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return t;
+}
+
 static inline int threads_for(int nvec) {  // a multiple of nvec (threads keep a fixed channel vector), <= 256
     if (nvec >= 256) return 256;
     return nvec * (256 / nvec);
@@ -118,6 +136,57 @@ __device__ __forceinline__ void gn_finish_coef(const float* __restrict__ sums, c
             s += t.x;
             q += t.y;
         }
+        const float mean = s * inv_cnt;
+        const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        const float ga = gamma[c], be = beta[c];
+        float a = rstd * ga, b = be - mean * rstd * ga;
+        if (params != nullptr) {
+            const float sc = 1.f + params[n * ldp + c], sh = params[n * ldp + C + c];
+            a *= sc;
+            b = b * sc + sh;
+        }
+        coef[1LL * n * C + c] = make_float4(a, b, mean, rstd);
+    }
+}
+
+// Coefficient table from producer-emitted partial statistics (conv epilogue): one CTA per sample.
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ st1, int slots1, int c1,
+                                                          const float* __restrict__ st2, int slots2, int c2, int hw,
+                                                          int G, float eps, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta,
+                                                          const float* __restrict__ params, long long ldp,
+                                                          float4* __restrict__ coef) {
+    extern __shared__ float fsum[];  // [C][2]
+    const int n = blockIdx.x, C = c1 + c2;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const bool first = c < c1;
+        const int cc = first ? c : c - c1, cs = first ? c1 : c2, slots = first ? slots1 : slots2;
+        const float2* src = reinterpret_cast<const float2*>(first ? st1 : st2) + (1LL * n * slots) * cs + cc;
+        float s = 0.f, q = 0.f;
+        int k = 0;
+        for (; k + 8 <= slots; k += 8) {  // eight independent loads in flight, summed in a fixed order (deterministic)
+            float2 t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = __ldcg(src + 1LL * (k + u) * cs);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { s += t[u].x; q += t[u].y; }
+        }
+        for (; k < slots; ++k) {
+            const float2 t = __ldcg(src + 1LL * k * cs);
+            s += t.x;
+            q += t.y;
+        }
+        fsum[2 * c] = s;
+        fsum[2 * c + 1] = q;
+    }
+    __syncthreads();
+    const int cpg = C / G;
+    const float inv_cnt = 1.f / (static_cast<float>(cpg) * static_cast<float>(hw));
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g0 = (c / cpg) * cpg;
+        float s = 0.f, q = 0.f;
+        for (int j = 0; j < cpg; ++j) { s += fsum[2 * (g0 + j)]; q += fsum[2 * (g0 + j) + 1]; }
         const float mean = s * inv_cnt;
         const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
         const float rstd = rsqrtf(var + eps);
@@ -243,36 +312,46 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const __nv_bfloat16* _
     const int Wo = 2 * W;
     __nv_bfloat16* ob = out + 1LL * n * (resample == 2 ? 4 * hw : hw) * ldo + v * 8;
     const unsigned long long vec0 = 1ULL * n * hw * V + v;
-    int p = blockIdx.x * tpv + lane;
-    for (; p < hw; p += 2 * step) {  // two pixels per iteration: both loads issued before the math
-        const bool has2 = p + step < hw;
-        const Vec8 xa = load8(base + p * ld);
-        Vec8 xb = xa;
-        if (has2) xb = load8(base + (p + step) * ld);
+    if (act) {  // silu(v) = h*tanh(h) + h with h = v/2: halve the coefficients once
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (u == 1 && !has2) break;
-            const int pp = p + u * step;
-            const Vec8& xv = u == 0 ? xa : xb;
-            float ds[8];
-            if (drop_p > 0.f) dropout_scales(seed, vec0 + 1ULL * pp * V, drop_p, ds);
-            Vec8 o;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float y = xv.v[j] * a[j] + b[j];
-                if (act) y = silu_f(y);
-                if (drop_p > 0.f) y *= ds[j];
-                o.v[j] = y;
-            }
-            if (resample == 0) {
-                store8(ob + pp * ldo, o);
-            } else {
-                const int h = pp / W, w = pp - h * W;
-#pragma unroll
-                for (int d = 0; d < 4; ++d) store8(ob + (1LL * (2 * h + (d >> 1)) * Wo + 2 * w + (d & 1)) * ldo, o);
-            }
-        }
+        for (int j = 0; j < 8; ++j) { a[j] *= 0.5f; b[j] *= 0.5f; }
     }
+    auto emit = [&](int pp, const uint4 raw) {
+        const Vec8 xv = unpack8(raw);
+        float ds[8];
+        if (drop_p > 0.f) dropout_scales(seed, vec0 + 1ULL * pp * V, drop_p, ds);
+        Vec8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float y = fmaf(xv.v[j], a[j], b[j]);
+            if (act) y = fmaf(y, tanh_fast(y), y);
+            if (drop_p > 0.f) y *= ds[j];
+            o.v[j] = y;
+        }
+        if (resample == 0) {
+            store8(ob + pp * ldo, o);
+        } else {
+            const int h = pp / W, w = pp - h * W;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) store8(ob + (1LL * (2 * h + (d >> 1)) * Wo + 2 * w + (d & 1)) * ldo, o);
+        }
+    };
+    // a pure stream: eight 16 B loads in flight per thread, then the math and the stores
+    int p = blockIdx.x * tpv + lane;
+    for (; p + 7 * step < hw; p += 8 * step) {
+        uint4 raw[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) raw[u] = __ldcs(reinterpret_cast<const uint4*>(base + (p + u * step) * ld));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) emit(p + u * step, raw[u]);
+    }
+    for (; p + 1 * step < hw; p += 2 * step) {
+        const uint4 r0 = __ldcs(reinterpret_cast<const uint4*>(base + p * ld));
+        const uint4 r1 = __ldcs(reinterpret_cast<const uint4*>(base + (p + step) * ld));
+        emit(p, r0);
+        emit(p + step, r1);
+    }
+    if (p < hw) emit(p, __ldcs(reinterpret_cast<const uint4*>(base + p * ld)));
 }
 
 // dv (gradient at the pre-activation v = x*A+B) for input pixel p (h, w), channel vector v.
@@ -636,29 +715,11 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ Vec8 unpack8(const uint4 u) {
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-    Vec8 r;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        r.v[2 * i] = __uint_as_float(w[i] << 16);
-        r.v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
-    }
-    return r;
-}
 // Dropout keep-scales from ONE mixed 32-bit word per vector: four odd multipliers spread it into eight 16-bit uniforms.
 __device__ __forceinline__ void dropout_scales_fast(unsigned long long seed, unsigned long long vec_index, float p,
                                                     float (&s)[8]) {
     dropout_scales(seed, vec_index, p, s);
 }
-// tanh-form SiLU on a pre-halved pre-activation h = v/2:  silu(v) = h*tanh(h) + h,
-// silu'(v) = 0.5 * (1 + T + h * (1 - T^2)), T = tanh(h).
-__device__ __forceinline__ float tanh_fast(float h) {
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-    return t;
-}
-
 __global__ void __launch_bounds__(512, 1) gn_fwd_fused_kernel(
     const __nv_bfloat16* __restrict__ x1, int c1, long long ld1, const __nv_bfloat16* __restrict__ x2, int c2,
     long long ld2, int H, int W, int G, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -1215,6 +1276,20 @@ int adm_gn_stats(const void* x1, int c1, long long ld1, const void* x2, int c2, 
     return 0;
 }
 
+int adm_gn_finalize(const float* st1, int slots1, int c1, const float* st2, int slots2, int c2, int n, int hw,
+                    int groups, float eps, const float* gamma, const float* beta, const float* params,
+                    long long ld_params, float* coef, void* stream) {
+    const int C = c1 + c2;
+    ADM_REQUIRE(st1 != nullptr && c1 > 0 && (st2 != nullptr || c2 == 0) && C % groups == 0 && slots1 > 0,
+                "gn_finalize: bad arguments");
+    ADM_REQUIRE(C <= 4096, "gn_finalize: C too large");
+    gn_finalize_kernel<<<n, 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        st1, slots1, c1, st2, slots2, c2, hw, groups, eps, gamma, beta, params, ld_params,
+        reinterpret_cast<float4*>(coef));
+    ADM_CHECK_LAUNCH("gn_finalize");
+    return 0;
+}
+
 int adm_gn_apply(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int h, int w,
                  const float* coef, int act, float drop_p, unsigned long long seed,
                  const unsigned long long* seed_counter, int resample, void* out, long long ldo, void* stream) {
@@ -1225,7 +1300,13 @@ int adm_gn_apply(const void* x1, int c1, long long ld1, const void* x2, int c2, 
     ADM_REQUIRE(C <= 2048, "gn_apply: C too large");
     const int threads = threads_for(C / 8);
     const int tpv = threads / (C / 8);
-    dim3 grid(grid_for(resample == 1 ? (h / 2) * (w / 2) : h * w, tpv * 2, n), n);
+    // ~3 CTAs per SM in total, each thread streaming >= 8 pixels of its channel vector when the image has that many
+    const int pixels = resample == 1 ? (h / 2) * (w / 2) : h * w;
+    int bps = (3 * num_sms() + n - 1) / n;
+    const int maxb = (pixels + tpv * 8 - 1) / (tpv * 8);
+    if (bps > maxb) bps = maxb;
+    if (bps < 1) bps = 1;
+    dim3 grid(bps, n);
     gn_apply_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const bf16*>(x1), c1, ld1, static_cast<const bf16*>(x2), c2, ld2, h, w,
         reinterpret_cast<const float4*>(coef), act, drop_p, seed, resample, static_cast<bf16*>(out), ldo, g_seed_dev);

@@ -338,9 +338,22 @@ using namespace adm;
 
 extern "C" {
 
+int adm_conv_stats_slots(int h, int w) {
+    const int s = (h * w) / 32;
+    return s < 1 ? 1 : s;
+}
+
 int adm_conv_fprop(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int h, int w,
                    const void* wpk, int nout, int ntaps, void* out, int out_mode, long long ldc, const float* bias,
                    const void* residual, long long ldr, float alpha, void* stream) {
+    return adm_conv_fprop_stats(x1, c1, ld1, x2, c2, ld2, n, h, w, wpk, nout, ntaps, out, out_mode, ldc, bias, residual,
+                                ldr, alpha, nullptr, stream);
+}
+
+int adm_conv_fprop_stats(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int h,
+                         int w, const void* wpk, int nout, int ntaps, void* out, int out_mode, long long ldc,
+                         const float* bias, const void* residual, long long ldr, float alpha, float* stats,
+                         void* stream) {
     if (int e = init_driver()) return e;
     if (ntaps != 1 && ntaps != 9) { set_error("conv_fprop: ntaps must be 1 or 9"); return ADM_ERR_SHAPE; }
     if (c1 <= 0 || c1 % 8 || (x2 && (c2 <= 0 || c2 % 8))) { set_error("conv_fprop: channels must be multiples of 8"); return ADM_ERR_SHAPE; }
@@ -361,6 +374,17 @@ int adm_conv_fprop(const void* x1, int c1, long long ld1, const void* x2, int c2
     p.M = n * h * w; p.N = nout;
     p.C = out; p.ldc = ldc; p.bias = bias; p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = ldr;
     p.alpha = alpha; p.out_mode = out_mode;
+    if (stats != nullptr) {
+        // the epilogue's per-warp column sums assume 32 consecutive tile rows stay inside one image (or split it in two
+        // 16-pixel halves): images of 16, 64 or a multiple of 128 pixels
+        const int hw = h * w;
+        if (!(hw == 16 || hw == 64 || hw % 128 == 0) || out_mode != OUT_BF16) {
+            set_error("conv_fprop: GroupNorm statistics need H*W in {16, 64, k*128} and a bf16 output (got %d x %d)", h, w);
+            return ADM_ERR_SHAPE;
+        }
+        p.stats = stats;
+        p.stats_slots = adm_conv_stats_slots(h, w);
+    }
     CUtensorMap ma, ma2, mb;
     const int abw = halo ? HALO_W : p.bw, abh = halo ? HALO_H : p.bh;  // A box: the tile, or the tile + its 3x3 halo
     if (int e = nhwc_map(&ma, x1, c1, ld1, n, h, w, abw, abh, p.bni)) return e;
@@ -370,7 +394,8 @@ int adm_conv_fprop(const void* x1, int c1, long long ld1, const void* x2, int c2
     const long long bs[1] = {kpad};
     // CTA pairs: 256-pixel tiles, each CTA loading half of the weight rows (box BN/2) — when there are at least two
     // pixel tiles and the output mode is a plain store.
-    const bool pair = !halo && pair_enabled() && p.m_tiles >= 2 && p.bn % 16 == 0 && out_mode != OUT_F32_ATOMIC;
+    const bool pair = !halo && pair_enabled() && p.m_tiles >= 2 && p.bn % 16 == 0 && out_mode != OUT_F32_ATOMIC &&
+                      stats == nullptr;
     const int bb[2] = {64, pair ? p.bn / 2 : p.bn};
     if (int e = encode_map(&mb, wpk, 2, bd, bs, bb)) return e;
     if (pair) return launch_pair(ma, ma2, mb, p, static_cast<cudaStream_t>(stream));

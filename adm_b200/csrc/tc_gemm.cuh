@@ -63,6 +63,12 @@ struct GemmParams {
     float alpha;
     int out_mode;
     int debug;  // experiments only (ADM_GEMM_DEBUG): bit 0 = skip the MMAs, bit 1 = skip the TMA loads
+    // ---- GroupNorm statistics of the OUTPUT, emitted by the conv epilogue: per (sample, slot, channel)
+    // partial {sum, sum of squares} over the pixels one epilogue warp (or half-warp, 4x4 images) holds, plain stores into
+    // stats[n][slot][N][2] — no atomics, no zeroing, deterministic.  The next norm derives its group statistics from these
+    // instead of re-reading the activation (adm_gn_finalize).  nullptr = off.
+    float* stats;
+    int stats_slots;  // slots per sample: (H*W) / 32, at least 1
 };
 
 __device__ __forceinline__ void decode_pix(const GemmParams& p, int idx, int& n0, int& h0, int& w0) {
@@ -108,14 +114,35 @@ __device__ __forceinline__ void stage_bias_128(const GemmParams& p, float* sbias
     asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
+// Column sums of 16 values per lane over the lanes of a warp in 15 (+1) shuffles: at each halving step a lane keeps the
+// half of its values selected by one lane bit and receives the partner's copy of that half.  Afterwards lane l holds in
+// v[0] the total of column (l & 15) over the 16 lanes sharing its bit 4 — or, with whole_warp, over all 32 lanes.
+__device__ __forceinline__ void warp_colsum16(float (&v)[16], int lane, bool whole_warp) {
+#pragma unroll
+    for (int step = 0; step < 4; ++step) {
+        const int off = 8 >> step;
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < (8 >> step); ++i) {
+            const float send = hi ? v[i] : v[i + off];
+            const float keep = hi ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    if (whole_warp) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
 // Epilogue of one accumulator tile for one thread (= one output row): TMEM -> registers in groups of up to 64 columns
 // (four 32x32b.x16 loads in flight behind ONE wait, with the residual row segment prefetched behind the same wait),
 // then alpha * acc + bias + residual -> bf16 / fp32 / fp32 atomics.  c_off / r_off: element offsets of this row in the
 // output and the residual (before the column); col_shift: extra output column offset (batched GEMMs); the tile columns
 // drained are [c_begin, ncols) (multiples of 16).
+// stat_row: this lane's base into the statistics table (sample and slot resolved, column 0), or nullptr; the column sums
+// are taken over the bf16-ROUNDED outputs (what the next norm will read); rows that do not exist contribute zeros.
 __device__ __forceinline__ void epilogue_row(const GemmParams& p, uint32_t taddr, int col_base, int col_shift,
                                              long long c_off, long long r_off, bool row_ok, const float* sbias,
-                                             int c_begin, int ncols) {
+                                             int c_begin, int ncols, float* stat_row = nullptr, bool stat_whole = true,
+                                             int lane = 0) {
     for (int c0 = c_begin; c0 < ncols; c0 += 64) {
         if (col_base + c0 >= p.N) break;  // warp-uniform
         uint32_t v[4][16];
@@ -140,7 +167,7 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, uint32_t taddr
             }
         }
         tmem_ld_wait();
-        if (!row_ok) continue;
+        if (!row_ok && stat_row == nullptr) continue;
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
             if (s >= nsub) break;
@@ -166,13 +193,27 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, uint32_t taddr
                         f[2 * j] += __uint_as_float(w[j] << 16);
                         f[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
                     }
-                } else {
+                } else if (row_ok) {
                     const __nv_bfloat16* rp = p.residual + r_off + col;
                     for (int j = 0; j < 16; ++j)
                         if (col + j < p.N) f[j] += __bfloat162float(rp[j]);
                 }
             }
             const long long off = c_off + col_shift + col;
+            if (stat_row != nullptr) {  // every lane of the warp takes part (rows that do not exist contribute zeros)
+                float s1[16], s2[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float r = (row_ok && col + j < p.N) ? __bfloat162float(__float2bfloat16(f[j])) : 0.f;
+                    s1[j] = r;
+                    s2[j] = r * r;
+                }
+                warp_colsum16(s1, lane, stat_whole);
+                warp_colsum16(s2, lane, stat_whole);
+                if ((stat_whole ? lane < 16 : true) && col + (lane & 15) < p.N)
+                    *reinterpret_cast<float2*>(stat_row + 2 * (col + (lane & 15))) = make_float2(s1[0], s2[0]);
+                if (!row_ok) continue;
+            }
             if (p.out_mode == OUT_BF16) {
                 __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + off;
                 if (full && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
@@ -246,6 +287,8 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, uint8_t* sme
 
         long long row_off;  // element offset of this thread's output row (before column)
         bool row_ok;
+        float* stat_row = nullptr;
+        bool stat_whole = true;
         if (MODE == GEMM_CONV) {
             int n0, h0, w0;
             decode_pix(p, mt, n0, h0, w0);
@@ -253,6 +296,22 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, uint8_t* sme
             const long long pix = (static_cast<long long>(n0 + ni) * p.H + (h0 + hi)) * p.W + (w0 + wi);
             row_ok = pix < p.M;
             row_off = pix;
+            if (p.stats != nullptr) {
+                // slot of this warp's 32 rows inside its sample: tiles of one image are (tile in image) * 4 + quadrant;
+                // images smaller than a tile (8x8: 2 warps each, 4x4: half a warp each) count their own warps
+                const int rows_per_img = p.bw * p.bh;  // rows of one image inside this tile
+                int slot;
+                if (p.bni == 1) {
+                    slot = (mt % (p.tiles_w * p.tiles_h)) * 4 + quad;
+                } else {
+                    slot = (m % rows_per_img) >> 5;
+                    stat_whole = rows_per_img >= 32;
+                }
+                // samples beyond the batch (ragged last tile of packed small images) write into one scratch sample row
+                const long long nsmp = p.M / (p.H * p.W);
+                const long long smp = (n0 + ni) < nsmp ? (n0 + ni) : nsmp;
+                stat_row = p.stats + (smp * p.stats_slots + slot) * 2LL * p.N;
+            }
         } else {
             const int row = mt * 128 + m;
             row_ok = row < p.M;
@@ -267,7 +326,8 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, uint8_t* sme
         mbar_wait(&tfull_bar[acc], acc_phase, 4);
         tc_fence_after();
         const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(quad * 32) << 16);
-        epilogue_row(p, taddr, col_base, col_shift, c_base, row_off * p.ldr, row_ok, sbias, c_begin, c_end);
+        epilogue_row(p, taddr, col_base, col_shift, c_base, row_off * p.ldr, row_ok, sbias, c_begin, c_end, stat_row,
+                     stat_whole, lane);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);

@@ -57,6 +57,12 @@ class UNetEngine:
         # ADM_WGRAD_STREAM=0 keeps everything on one stream.
         self._side = None
         self._side_on = os.environ.get("ADM_WGRAD_STREAM", "1") != "0"
+        # ADM_GN_STATS=1: GroupNorm statistics come from the epilogue of the conv that produced the tensor
+        # (adm_conv_fprop_stats + adm_gn_finalize) instead of the norm re-reading its input.  Exact and tested, but OFF by
+        # default: measured on B200 (profiles/r03_gn_stats_epilogue_microbench.txt) the cross-lane column reduction makes
+        # the epilogue-bound convs 13-120 % slower while the norm's own statistics pass costs only ~3 us of its 24 us
+        # (its apply pass is instruction-issue bound) — the step is 1.4 ms slower with it.
+        self._gn_stats = os.environ.get("ADM_GN_STATS", "0") == "1"
         self._side_pending = []
         # device-resident step counter mixed into every dropout seed (fresh masks per CUDA-graph replay); owned by the
         # training step (adm_b200.train.TrainStep) and passed to the GroupNorm kernels per call
@@ -312,7 +318,21 @@ class UNetEngine:
         return self._cached(("projpad", id(blk)), [blk.proj.weight], build)
 
     # ------------------------------------------------------------------------------------------ UNetBlock
-    def block_fwd(self, blk, x1, x2, params, training, seed, save):
+    def _gn(self, x1, st1, x2, st2, norm, groups, **kw):
+        """GroupNorm (+ activation ...) of the fused concat (x1 | x2): from the producers' epilogue statistics when both
+        sources carry them (one finalize + one streaming pass), else statistics + apply in the cluster kernel."""
+        if st1 is not None and (x2 is None or st2 is not None):
+            return ops.gn_forward_stats(x1, st1, x2, st2, norm.weight, norm.bias, groups, norm.eps, **kw)
+        return ops.gn_forward(x1, x2, norm.weight, norm.bias, groups, norm.eps, **kw)
+
+    def _conv_stats(self, x, *args, **kw):
+        """conv_fprop that also returns the GroupNorm statistics of its output when the image size allows it."""
+        if self._gn_stats and ops.stats_ok(x.shape[1], x.shape[2]):
+            return ops.conv_fprop(x, *args, stats=True, **kw)
+        return ops.conv_fprop(x, *args, **kw), None
+
+    def block_fwd(self, blk, x1, x2, params, training, seed, save, st1=None, st2=None):
+        """Returns (block output, its epilogue statistics or None)."""
         c = NS(blk=blk, x1=x1, x2=x2, params=params, seed=seed)
         cin1 = x1.shape[-1]
         cin2 = x2.shape[-1] if x2 is not None else 0
@@ -320,30 +340,27 @@ class UNetEngine:
         mode = 1 if blk.down else (2 if blk.up else 0)
         c.mode = mode
         c.drop_p = float(blk.dropout) if training else 0.0
-        c.sums0, c.a0 = ops.gn_forward(x1, x2, blk.norm0.weight, blk.norm0.bias, _groups(cin), blk.norm0.eps, act=True,
-                                       resample=mode)
+        c.sums0, c.a0 = self._gn(x1, st1, x2, st2, blk.norm0, _groups(cin), act=True, resample=mode)
         # after the fused concat-GroupNorm the conv sees ONE tensor a0 with cin channels
-        c.h0 = ops.conv_fprop(c.a0, self.conv_w(blk.conv0), bias=blk.conv0.bias)
-        c.sums1, c.a1 = ops.gn_forward(c.h0, None, blk.norm1.weight, blk.norm1.bias, _groups(cout), blk.norm1.eps,
-                                       params=params, act=True, drop_p=c.drop_p, seed=seed,
-                                       seed_counter=self.seed_counter)
+        c.h0, st_h0 = self._conv_stats(c.a0, self.conv_w(blk.conv0), bias=blk.conv0.bias)
+        c.sums1, c.a1 = self._gn(c.h0, st_h0, None, None, blk.norm1, _groups(cout), params=params, act=True,
+                                 drop_p=c.drop_p, seed=seed, seed_counter=self.seed_counter)
         if blk.skip is not None and blk.skip.weight is not None:
             res = ops.conv_fprop(x1, self.conv_w(blk.skip, cin1, cin2), x2=x2, bias=blk.skip.bias)
         elif mode:
             res = ops.resample(x1, mode)
         else:
             res = x1
-        c.h1 = ops.conv_fprop(c.a1, self.conv_w(blk.conv1), bias=blk.conv1.bias, residual=res)
+        c.h1, st_out = self._conv_stats(c.a1, self.conv_w(blk.conv1), bias=blk.conv1.bias, residual=res)
         out = c.h1
         if blk.num_heads:
-            c.sums2, c.a2 = ops.gn_forward(c.h1, None, blk.norm2.weight, blk.norm2.bias, _groups(cout), blk.norm2.eps,
-                                           act=False)
+            c.sums2, c.a2 = self._gn(c.h1, st_out, None, None, blk.norm2, _groups(cout), act=False)
             if (cout // blk.num_heads) % 64:  # head width 72 / 96: zero-padded heads
                 wq, bq, _ = self.qkv_padded(blk)
                 c.qkv = ops.conv_fprop(c.a2, wq, bias=bq)
                 c.att, c.p = ops.attention_fwd(c.qkv, blk.num_heads, scale=(cout // blk.num_heads) ** -0.5,
                                                need_p=save is not None)
-                out = ops.conv_fprop(c.att, self.proj_padded(blk), bias=blk.proj.bias, residual=c.h1)
+                out, st_out = self._conv_stats(c.att, self.proj_padded(blk), bias=blk.proj.bias, residual=c.h1)
             else:
                 perm = self.qkv_perm(cout, blk.num_heads)
                 bq = self._cached(("qkvb", id(blk)), [blk.qkv.bias],
@@ -351,10 +368,10 @@ class UNetEngine:
                                   else torch.index_select(blk.qkv.bias.detach(), 0, perm[1], out=old))
                 c.qkv = ops.conv_fprop(c.a2, self.conv_w(blk.qkv, perm=perm[0]), bias=bq)
                 c.att, c.p = ops.attention_fwd(c.qkv, blk.num_heads, need_p=save is not None)
-                out = ops.conv_fprop(c.att, self.conv_w(blk.proj), bias=blk.proj.bias, residual=c.h1)
+                out, st_out = self._conv_stats(c.att, self.conv_w(blk.proj), bias=blk.proj.bias, residual=c.h1)
         if save is not None:
             save.append(c)
-        return out
+        return out, st_out
 
     def export_dropout_masks(self, tape):
         """The dropout keep-masks (already scaled by 1/(1-p)) a training forward drew, one NCHW fp32 tensor per UNetBlock,
@@ -553,23 +570,23 @@ class UNetEngine:
             tape.emb = emb_save[0]
             tape.dparams_all = torch.zeros_like(params_all)
 
-        def run_block(m, x1, x2, idx):
+        def run_block(m, x1, x2, idx, st1=None, st2=None):
             off = boff[id(m)]
             return self.block_fwd(m, x1, x2, params_all[:, off:off + m.affine.out_features], training,
-                                  step_seed * 4099 + idx, save)
+                                  step_seed * 4099 + idx, save, st1, st2)
 
-        x = xin
-        skips = []
+        x, st = xin, None
+        skips = []  # (tensor, epilogue statistics) of every encoder entry
         idx = 0
         for name, m in net.enc.items():
             if hasattr(m, "affine"):
-                x = run_block(m, x, None, idx)
+                x, st = run_block(m, x, None, idx, st)
             else:
-                x = ops.conv_fprop(x, self.conv_w(m, c1=m.in_channels), bias=m.bias)
+                x, st = self._conv_stats(x, self.conv_w(m, c1=m.in_channels), bias=m.bias)
                 if tape is not None:
                     tape.first = NS(conv=m, x=xin)
             idx += 1
-            skips.append(x)
+            skips.append((x, st))
         outs = []
         # The two decoders only share their inputs (bottleneck, skips, embedding): the second one is enqueued on the
         # side stream, forked HERE (before decoder 1 is enqueued), so their kernels interleave on the SMs — most of
@@ -588,14 +605,14 @@ class UNetEngine:
                 self._side_pending.append((x, skips, params_all))
                 ctx = torch.cuda.stream(self._side)
             with ctx:
-                h = self.decouple_fwd(getattr(net, dname), x, save)
+                h, hst = self.decouple_fwd(getattr(net, dname), x, save), None
                 sk = list(skips)
                 for name, m in dec.items():
-                    x2 = sk.pop() if h.shape[-1] != m.in_channels else None
-                    h = run_block(m, h, x2, idx)
+                    x2, st2 = sk.pop() if h.shape[-1] != m.in_channels else (None, None)
+                    h, hst = run_block(m, h, x2, idx, hst, st2)
                     idx += 1
                 o = NS(x=h, norm=norm, conv=oconv)
-                o.sums, o.a = ops.gn_forward(h, None, norm.weight, norm.bias, _groups(h.shape[-1]), norm.eps, act=True)
+                o.sums, o.a = self._gn(h, hst, None, None, norm, _groups(h.shape[-1]), act=True)
                 f = ops.conv_fprop(o.a, self.conv_w(oconv), bias=oconv.bias, out_dtype=F32, keep_pad=True)
                 if save is not None:
                     save.append(o)

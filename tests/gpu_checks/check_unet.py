@@ -120,6 +120,58 @@ def groupnorm():
 
 
 @case
+def gn_stats_epilogue():
+    """GroupNorm statistics emitted by the conv epilogue (adm_conv_fprop_stats) + adm_gn_finalize + the streaming apply,
+    against F.group_norm on the conv output and against the statistics-kernel path; every tile geometry: 32x32 / 16x16
+    (halo tiles, 8 / 2 per image), 8x8 (two images per tile), 4x4 (eight per tile, half-warp segments, ragged batch),
+    1x1 convs with a residual, a fused channel concat of two producers."""
+    import torch
+    import torch.nn.functional as F
+    from adm_b200 import ops
+    torch.manual_seed(11)
+    ok = True
+    for (n, hw, cin, cout, k, with_res) in [(4, 32, 64, 192, 3, False), (6, 16, 128, 384, 3, True), (5, 8, 64, 192, 3, False),
+                                            (13, 4, 128, 384, 3, True), (16, 16, 192, 96, 1, True), (3, 8, 128, 72, 1, False),
+                                            (130, 4, 64, 64, 3, False)]:
+        x = (torch.randn(n, hw, hw, cin, device="cuda")).bfloat16()
+        wt = (torch.randn(cout, cin, k, k, device="cuda") / (k * cin ** 0.5))
+        bias = 0.1 * torch.randn(cout, device="cuda")
+        res = torch.randn(n, hw, hw, cout, device="cuda").bfloat16() if with_res else None
+        wpk = ops.pack_conv_weight(wt)
+        y0 = ops.conv_fprop(x, wpk, bias=bias, residual=res)
+        y, st = ops.conv_fprop(x, wpk, bias=bias, residual=res, stats=True)
+        ok &= bool(torch.equal(y, y0)) and tuple(st.shape) == (n + 1, max(1, hw * hw // 32), cout, 2)
+        ref = y.float()
+        tot = st[:n].sum(1)  # [n, cout, 2]
+        ok &= _report(f"epilogue sum   n{n} {hw}x{hw} {cin}->{cout} k{k}", tot[..., 0], ref.sum((1, 2)), 2e-5)
+        ok &= _report(f"epilogue sumsq n{n} {hw}x{hw} {cin}->{cout} k{k}", tot[..., 1], (ref * ref).sum((1, 2)), 2e-5)
+        g = min(32, cout // 4)
+        gamma = 1 + 0.1 * torch.randn(cout, device="cuda")
+        beta = 0.1 * torch.randn(cout, device="cuda")
+        params = 0.3 * torch.randn(n, 2 * cout, device="cuda")
+        coef_s, ys = ops.gn_forward_stats(y, st, None, None, gamma, beta, g, 1e-5, params=params, act=True)
+        coef_k, yk = ops.gn_forward(y, None, gamma, beta, g, 1e-5, params=params, act=True)
+        ok &= _report("  coef from epilogue stats vs stats kernel", coef_s, coef_k, 1e-4)
+        ok &= _report("  y from epilogue stats vs stats kernel", ys, yk, 4e-3)
+        v = F.group_norm(ref.permute(0, 3, 1, 2), g, gamma, beta, 1e-5)
+        v = F.silu(v * (1 + params[:, :cout, None, None]) + params[:, cout:, None, None])
+        ok &= _report("  y vs F.group_norm", ys, v.permute(0, 2, 3, 1), 6e-3)
+    # fused concat of two producers with different channel counts (group 21 of cat(384, 192) straddles the sources)
+    n, hw = 4, 16
+    xa = torch.randn(n, hw, hw, 64, device="cuda").bfloat16()
+    wa = ops.pack_conv_weight(torch.randn(384, 64, 3, 3, device="cuda") / 24)
+    wb = ops.pack_conv_weight(torch.randn(192, 64, 1, 1, device="cuda") / 8)
+    ya, sa = ops.conv_fprop(xa, wa, stats=True)
+    yb, sb = ops.conv_fprop(xa, wb, stats=True)
+    gamma = 1 + 0.1 * torch.randn(576, device="cuda")
+    beta = 0.1 * torch.randn(576, device="cuda")
+    coef_s, ys = ops.gn_forward_stats(ya, sa, yb, sb, gamma, beta, 32, 1e-5, act=True)
+    v = F.silu(F.group_norm(torch.cat([ya, yb], -1).float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-5))
+    ok &= _report("concat (384 | 192) from two producers vs F.group_norm", ys, v.permute(0, 2, 3, 1), 6e-3)
+    return ok
+
+
+@case
 def small_ops():
     import torch
     import torch.nn.functional as F
