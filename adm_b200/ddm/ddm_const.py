@@ -92,26 +92,11 @@ class DDPM(nn.Module):
         self.use_augment = g("use_augment", False)
         self.augment = None
         if self.use_augment:
-            # AugmentPipe (ddm/augment.py:115-328, EDM's augmentation) is host-side data glue (SURVEY section 8 row a-4 /
-            # f-4): it is taken from the host project when that is importable, with the reference's arguments
-            # (ddm_const.py:179-180); `model.augment` can also be assigned any callable x -> (x_aug, labels [B, 9]).
-            self.augment = self._host_augment_pipe()
+            # ddm_const.py:179-180.  Host-side data glue: torch ops, before the fused step.
+            from .augment import AugmentPipe
+            self.augment = AugmentPipe(p=0.15, xflip=1e8, yflip=1, scale=1, rotate_frac=1, aniso=1, translate_frac=1)
         if ckpt_path is not None:
             self.init_from_ckpt(ckpt_path, ignore_keys, only_model)
-
-    @staticmethod
-    def _host_augment_pipe():
-        import importlib
-        for name in ("ddm.augment", "ADM.ddm.augment"):
-            try:
-                mod = importlib.import_module(name)
-            except Exception:
-                continue
-            return mod.AugmentPipe(p=0.15, xflip=1e8, yflip=1, scale=1, rotate_frac=1, aniso=1, translate_frac=1)
-        raise NotImplementedError(
-            "use_augment=True needs the host project's AugmentPipe (ddm/augment.py of zacz08/ADM) on sys.path; "
-            "adm_b200 replaces the training-step / sampler hot path, not the data augmentation. "
-            "Set use_augment: False, or assign `model.augment` yourself.")
 
     # -------------------------------------------------------------------------------------------- checkpoints
     def init_from_ckpt(self, path, ignore_keys=list(), only_model=False, use_ema=False):
@@ -149,6 +134,10 @@ class DDPM(nn.Module):
             x = x * self.scale_input
         t = torch.rand(x.shape[0], device=x.device) * (1. - self._eps) + self._eps
         return self.p_losses(x, t, *args, **kwargs)
+
+    def _loss_flags(self):
+        """K2 flag word of this module's objective (image space: bool use_l1 -> the mean-|.| term of ddm_const.py:345-348)."""
+        return bool(self.use_l1)
 
     def q_sample(self, x_start, noise, t, C=None):
         """K1.  C is implied (-x_start, ddm_const.py:319) and only accepted for signature compatibility."""
@@ -383,6 +372,10 @@ class LatentDiffusion(DDPM):
             out.append(cond)
         return out
 
+    def _loss_flags(self):
+        """L1 as a sum over CHW (ddm_const_2.py:561-564) + the reconstruction term (:565-568)."""
+        return (2 if self.use_l1 else 0) | 4
+
     def training_step(self, batch, *args, **kwargs):
         z, c, x, *_ = self.get_input(batch)
         if self.scale_by_softsign:
@@ -404,8 +397,8 @@ class LatentDiffusion(DDPM):
         x_noisy = ops.qsample(x_start, noise, t)
         args = tuple(a for a in args if a is not None)
         c_pred, noise_pred = self.model(x_noisy, t, *args, **kwargs)[:2]
-        flags = (2 if self.use_l1 else 0) | 4  # L1 as a sum over CHW (ddm_const_2.py:561-564) + reconstruction term
-        loss, lps = _DDMLossFn.apply(c_pred, noise_pred, x_start, noise, t, self._eps, bool(self.weighting_loss), flags)
+        loss, lps = _DDMLossFn.apply(c_pred, noise_pred, x_start, noise, t, self._eps, bool(self.weighting_loss),
+                                     self._loss_flags())
         b = x_start.shape[0]
         n = float(x_start.numel())
         with torch.no_grad():

@@ -302,11 +302,12 @@ class TrainStep:
         shape into a CUDA graph.  Per-step scalars (lr, bias corrections, dropout seed counter) live in device memory."""
         assert self.grad_accum == 1, "graph capture covers the single-micro-batch step"
         self.static_x = x_example.clone()
+        kw = self._static_augment(x_example)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self.micro_step(self.static_x)
+                self.micro_step(self.static_x, **kw)
                 self.optimizer_step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
@@ -315,16 +316,32 @@ class TrainStep:
         l0 = _lib.load().adm_launch_count()
         with torch.cuda.graph(g):
             self.seed_counter.add_(1)
-            self.static_loss = self.micro_step(self.static_x)
+            self.static_loss = self.micro_step(self.static_x, **kw)
             self.device_update()
         self.launches_per_step = _lib.load().adm_launch_count() - l0  # kernels of ours inside one replay
         self.graph = g
         return g
 
+    def _static_augment(self, x_example):
+        """With use_augment the augmentation (data glue with a data-dependent padding, ddm/augment.py:236-250) runs
+        eagerly BEFORE each replay; the graph reads the augmented batch and its labels from static tensors."""
+        self.static_aug = None
+        if self.dpm.use_augment and self.dpm.augment is not None:
+            _, lab = self.dpm.augment(x_example)
+            self.static_aug = torch.zeros_like(lab)
+            return {"augment_labels": self.static_aug}
+        return {}
+
     def replay(self, x=None):
-        """One optimizer step through the captured graph; `x` (device or pinned host) is copied into the static input."""
+        """One optimizer step through the captured graph; `x` (device or pinned host) is copied into the static input
+        (after the augmentation pipe when the model has one)."""
         if x is not None:
-            self.static_x.copy_(x, non_blocking=True)
+            if getattr(self, "static_aug", None) is not None:
+                xa, lab = self.dpm.augment(x.to(self.static_x.device, non_blocking=True))
+                self.static_x.copy_(xa)
+                self.static_aug.copy_(lab)
+            else:
+                self.static_x.copy_(x, non_blocking=True)
         self.step_count += 1
         self._push_hyper()
         if self.segments is not None:
@@ -349,11 +366,12 @@ class TrainStep:
         """t / noise: optional STATIC tensors baked into the graphs (tests); by default they are drawn inside."""
         assert self.grad_accum == 1, "graph capture covers the single-micro-batch step"
         self.static_x = x_example.clone()
+        kw = self._static_augment(x_example)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self.micro_step(self.static_x, t, noise)
+                self.micro_step(self.static_x, t, noise, **kw)
                 self.optimizer_step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
@@ -370,7 +388,7 @@ class TrainStep:
             self._seg_capture = dict(graph=g, segments=[], pool=pool)
             try:
                 self.seed_counter.add_(1)
-                self.static_loss = self.micro_step(self.static_x, t, noise)
+                self.static_loss = self.micro_step(self.static_x, t, noise, **kw)
                 self._flush(self.arena.numel)  # whatever is left of the gradient arena
                 self.engine.grad_hook = None
                 a = self.arena
@@ -459,9 +477,9 @@ class TrainStep:
             noise = noise.contiguous().float()
             x_noisy = ops.qsample(x, noise, t)
             d1, d2, tape = self.engine.forward(x_noisy, t, aug, training=self.net.training, need_grad=True)
-            lps, dc, de = ops.ddm_loss(d1, d2, x, noise, t, dpm._eps, bool(dpm.weighting_loss), bool(dpm.use_l1))
+            lps, dc, de = ops.ddm_loss(d1, d2, x, noise, t, dpm._eps, bool(dpm.weighting_loss), dpm._loss_flags())
             self.engine.backward(tape, dc, de)
-            return lps.sum() / x.shape[0]
+            return lps[:x.shape[0]].sum() / x.shape[0]
 
     def __call__(self, batches):
         """batches: list of `grad_accum` image tensors (this rank's shard).  Returns the mean loss tensor."""

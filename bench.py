@@ -3,6 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port) on host cores
+    python bench.py --config celebahq|div2k                  # BASELINE configs 4 / 5 (one GPU, reported lines)
 
 Workload (BASELINE.json configs[1]): configs/cifar10/ddm_uncond_const_uncond_unet.yaml UNet (216.1 M parameters),
 batch 128 per GPU, bf16 compute with fp32 master weights, one micro-batch forward + backward + clip + AdamW per step,
@@ -23,12 +24,22 @@ CIFAR_UNET = dict(img_resolution=32, img_channels=3, sigma_data=1.0, model_type=
                   channel_mult=[1, 2, 2, 2], channel_mult_emb=4, num_blocks=3, attn_resolutions=[16, 8], dropout=0.1,
                   label_dropout=0, augment_dim=9)
 MODEL_CFG = dict(image_size=[32, 32], sampling_timesteps=10, loss_type="l2", start_dist="normal", perceptual_weight=1.0,
-                 eps=1e-4, sigma_max=1, sigma_min=0.01, weighting_loss=True, use_l1=False, use_augment=False)
+                 eps=1e-4, sigma_max=1, sigma_min=0.01, weighting_loss=True, use_l1=False, use_augment=True)
 TRAIN_GFLOP_PER_IMG = 213.9   # 3 x 71.30 forward GFLOP
 FWD_GFLOP_PER_IMG = 71.30
 METRIC = "train_img_per_s"
 WORKLOAD = ("CIFAR-10 32x32 DDM-const training step, EDMPrecond/DhariwalUNet 216.1M params "
-            "(configs/cifar10/ddm_uncond_const_uncond_unet.yaml), fwd+bwd+clip+AdamW, dropout 0.1")
+            "(configs/cifar10/ddm_uncond_const_uncond_unet.yaml), AugmentPipe + fwd+bwd+clip+AdamW, dropout 0.1")
+# the other BASELINE configs (reported through --config; the headline stays the CIFAR-10 one)
+LATENT_CONFIGS = {
+    "celebahq": dict(yaml="configs/celebahq/celeb_uncond_ddm_const_uncond_unet_ldm.yaml", batch=48, gflop_train=297.4,
+                     gflop_ae=345.4, workload="CelebAHQ-256 latent DDM-const training step: frozen AutoencoderKL encode "
+                     "(random init) + EDMPrecond/DhariwalUNet 121.1M on 64x64 latents, fwd+bwd+clip+AdamW"),
+    "div2k": dict(yaml="configs/super-resolution/div2k_cond_ddm_const_ldm.yaml", batch=8, gflop_train=1153.9,
+                  gflop_ae=1794.0, workload="DIV2K 512x512 conditional SR latent DDM-const training step: frozen "
+                  "AutoencoderKL encode + cond_unet.Unet 224.8M (Swin-B condition encoder) on 128x128 latents, "
+                  "fwd+bwd+AdamW"),
+}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel from `ncu --set full`
 # (profiles/r02_conv_ncu_full.txt): the 25 MB input is read once, weights 2.6 MB, the output stays in L2.
 CONV_DRAM_TRAFFIC_BYTES = 28.1e6
@@ -170,6 +181,158 @@ def conv_roofline(device, iters=30):
     return flops / (ms * 1e-3) / 1e12, ms
 
 
+def sampler_sweep(dpm, B, device, steps_list=(1, 10, 50)):
+    """BASELINE config 3: sampling_timesteps 1 / 10 / 50 at 128 images per GPU (batch 1024 sharded over 8), no comm."""
+    import torch
+    out = {}
+    keep = dpm.sampling_timesteps
+    for n in steps_list:
+        dpm.sampling_timesteps = n
+        dpm.sample(batch_size=B)  # capture / warm
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 2 if n <= 10 else 1
+        s0.record()
+        for _ in range(reps):
+            dpm.sample(batch_size=B)
+        s1.record()
+        torch.cuda.synchronize()
+        out[n] = s0.elapsed_time(s1) / reps
+    dpm.sampling_timesteps = keep
+    return out
+
+
+def torch_gpu_eager(device, B, steps=3):
+    """Reported, not a target (the thing a user would otherwise run on this GPU): the SAME step as plain
+    torch ops (the oracle's functional UNet = the reference's op sequence) under bf16 autocast with torch's fused AdamW."""
+    import torch
+    from oracle import ddm_oracle as O
+    cfg = O.unet_config(**{k: v for k, v in CIFAR_UNET.items() if k in ("img_resolution", "img_channels", "model_channels",
+                           "channel_mult", "channel_mult_emb", "num_blocks", "attn_resolutions", "dropout", "augment_dim")})
+    sd = {k: v.to(device).requires_grad_(not k.endswith("resample_filter")) for k, v in O.make_state_dict(cfg, 0).items()}
+    params = [v for v in sd.values() if v.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-4, fused=True)
+    x = 2 * torch.rand(B, 3, 32, 32, device=device) - 1
+
+    def one():
+        t = torch.rand(B, device=device) * (1 - 1e-4) + 1e-4
+        noise = torch.randn_like(x)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss, _ = O.p_losses(lambda xx, tt: O.edm_precond_forward(sd, cfg, xx, tt), x, t, noise)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+
+    one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del sd, params, opt
+    torch.cuda.empty_cache()
+    return {"value": B / (ms / 1000), "unit": "img/s", "ms_per_step": ms,
+            "what": "same step as stock torch ops (cuDNN / cuBLAS) under bf16 autocast + fused AdamW, eager, no dropout"}
+
+
+def build_from_yaml(path, device):
+    """Builds the model the way the reference scripts do (train_uncond_ldm.py:40-57): unet, first stage, diffusion module
+    through construct_class_by_name from the reference-schema YAML."""
+    import yaml
+    from adm_b200.ddm.utils import construct_class_by_name
+    cfg = yaml.safe_load(open(os.path.join(ROOT, path)))
+    model_cfg = dict(cfg["model"])
+    unet = construct_class_by_name(**dict(model_cfg.pop("unet")))
+    kw = {}
+    if "first_stage" in model_cfg:
+        kw["auto_encoder"] = construct_class_by_name(**dict(model_cfg.pop("first_stage")))
+    cls = model_cfg.pop("class_name")
+    return construct_class_by_name(class_name=cls, model=unet, cfg=model_cfg, **kw, **model_cfg).to(device), cfg
+
+
+def run_latent(args):
+    """BASELINE configs 4 / 5 on ONE GPU: AE encode (no grad) -> DDM-const step on latents.  Reported lines, not the headline."""
+    import torch
+    from adm_b200 import _lib
+    spec = LATENT_CONFIGS[args.config]
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(device)
+    torch.manual_seed(0)
+    ldm, cfg = build_from_yaml(spec["yaml"], device)
+    B = args.batch if args.batch != 128 else spec["batch"]
+    size = cfg["model"]["image_size"]
+    x = 2 * torch.rand(B, 3, *size, device=device) - 1
+    batch = {"image": x}
+    down = ldm.first_stage_model.down_ratio
+    if args.config == "div2k":
+        batch["cond"] = 2 * torch.rand(B, 3, size[0] // down, size[1] // down, device=device) - 1
+    lib = _lib.load()
+    ldm.train()
+    if args.config == "celebahq":
+        from adm_b200.train import TrainStep
+        step = TrainStep(ldm, lr=5e-5, weight_decay=1e-4, max_grad_norm=1.0)
+
+        def one():
+            with torch.no_grad():
+                z, *_ = ldm.get_input(batch)
+                z = ldm.scale_factor * z
+            loss = step.micro_step(z)
+            step.optimizer_step()
+            return loss
+    else:
+        params = [p for p in ldm.model.parameters() if p.requires_grad]
+        opt = torch.optim.AdamW(params, lr=5e-5, weight_decay=1e-4, fused=True)
+
+        def one():
+            opt.zero_grad(set_to_none=True)
+            loss, _ = ldm.training_step(batch)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+            return loss.detach()
+    for _ in range(max(2, args.warmup)):
+        loss = one()
+    torch.cuda.synchronize()
+    l0 = lib.adm_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (lib.adm_launch_count() - l0) // args.steps
+    ldm.eval()
+    with torch.no_grad():
+        kw = {"cond": batch["cond"]} if "cond" in batch else {"batch_size": B}
+        ldm.sample(**kw)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        ldm.sample(**kw)
+        s1.record()
+        torch.cuda.synchronize()
+    ms_s = s0.elapsed_time(s1)
+    pk = peaks()
+    tf = (spec["gflop_train"] + spec["gflop_ae"]) * B / ms
+    line = {"metric": METRIC, "value": B / (ms / 1000), "unit": "img/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": spec["workload"], "yaml": spec["yaml"], "global_batch": B, "batch_per_gpu": B,
+                       "parallelism": "dp1", "launch": "eager launches", "timing": "cuda events"},
+            "gpu_launches": int(launches), "last_loss": float(loss),
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": tf / pk["tf_sust"],
+                         "traffic": None, "kernel": "whole step: (UNet train + frozen AE encode) algorithmic GFLOP per image x "
+                         "batch / step time, against the sustained bf16 figure", "peak_source": pk["src"]},
+            "sample": {"metric": "sample10_img_per_s", "value": B / (ms_s / 1000), "unit": "img/s", "ms_per_batch": ms_s,
+                       "steps": 10, "batch_per_gpu": B, "includes": "10 UNet steps + AE decode"}}
+    print(json.dumps(line), flush=True)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -193,6 +356,7 @@ def run_ours(args):
 
     # one rank: the whole step is ONE CUDA graph.  Several ranks: a chain of graphs cut at the gradient-bucket boundaries,
     # with the NCCL all-reduces launched eagerly between replays (capturing NCCL into the graph hung on this stack).
+    # The augmentation pipe (use_augment: True, as the reference YAML) runs eagerly before every replay.
     use_graph = not args.no_graph
     if use_graph:
         try:
@@ -205,7 +369,7 @@ def run_ours(args):
     def one_step(x):
         if use_graph:
             return step.replay(x)
-        loss = step.micro_step(x)
+        loss = step.micro_step(x.to(device, non_blocking=True))
         step.optimizer_step()
         return loss
 
@@ -243,8 +407,7 @@ def run_ours(args):
     e2.record()
     loss_host = 0.0
     for _ in range(args.steps):
-        xb = x_host if use_graph else x_host.to(device, non_blocking=True)  # graph path copies H2D into its static input
-        loss = one_step(xb)
+        loss = one_step(x_host)  # H2D copy of the pinned batch (into the graph's static input), then the step
         loss_host = float(loss.item())
     e3.record()
     barrier()
@@ -253,22 +416,14 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
-    # ---- 10-step sampler throughput (batch sharded, no communication)
+    # ---- sampler throughput (batch sharded, no communication): N = 1 / 10 / 50 steps
     dpm.eval()
-    for _ in range(1):
-        dpm.sample(batch_size=B)
-    barrier()
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record()
-    reps = 2
-    for _ in range(reps):
-        img = dpm.sample(batch_size=B)
-    s1.record()
-    barrier()
-    ts = torch.tensor([s0.elapsed_time(s1) / reps], device=device, dtype=torch.float64)
+    sweep = sampler_sweep(dpm, B, device)
+    ts = torch.tensor([sweep[n] for n in sorted(sweep)], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
-    ms_sample = ts.item()
+    sweep = dict(zip(sorted(sweep), ts.tolist()))
+    ms_sample = sweep[10]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -280,15 +435,26 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu_baseline:
         cpu, _, _ = cpu_reference(2, 1, budget_s=30.0)
+    eager = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            del step
+            torch.cuda.empty_cache()
+            eager = torch_gpu_eager(device, B)
+        except Exception as e:
+            eager = {"unavailable": repr(e)[:200]}
     line = {
         "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
+        "step_frac_of_sustained_peak": step_tf / pk["tf_sust"],
         "config": {"workload": WORKLOAD, "global_batch": B * world, "batch_per_gpu": B, "parallelism": f"dp{world}", "grad_accum": 1,
-                   "augment": "off (AugmentPipe is host-side data glue, SURVEY 8f-4)",
+                   "augment": "on: AugmentPipe(p=0.15, flips + anti-aliased affine warp) as torch ops before every step "
+                              "(use_augment: True, as the reference YAML), inside the timed region",
                    "l2": "activation working set >> 126 MB L2 (no flush needed)", "timing": "cuda events, max over ranks",
-                   "launch": ("one CUDA graph per step" if world == 1 else
-                              f"{len(step.segments)} chained CUDA graphs per step, NCCL all-reduce between them")
+                   "launch": ("AugmentPipe eager + one CUDA graph per step" if world == 1 else
+                              f"AugmentPipe eager + {len(step.segments) if use_graph else 0} chained CUDA graphs per step, "
+                              "NCCL all-reduce between them")
                    if use_graph else "eager launches"},
         "e2e": {"value": B * world / (ms_e2e / 1000), "unit": "img/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "last_loss": loss_host},
@@ -296,6 +462,8 @@ def run_ours(args):
         "clocks": clk,
         "roofline": {"bound": "tensor", "achieved": conv_tf, "peak": pk["tf_burst"], "unit": "TFLOP/s",
                      "frac": conv_tf / pk["tf_burst"], "traffic": CONV_DRAM_TRAFFIC_BYTES,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
+                                       "(profiles/r02_conv_ncu_full.txt); not re-measured by this run",
                      "algorithmic_flops_per_launch": 2.0 * 128 * 16 * 16 * 384 * 384 * 9,
                      "kernel": "tc_conv_halo_kernel conv3x3 384->384 @16x16 x128 (dominant shape), timed alone",
                      "ms_per_launch": conv_ms, "peak_source": pk["src"],
@@ -303,7 +471,10 @@ def run_ours(args):
         "sample": {"metric": "sample10_img_per_s", "value": B * world / (ms_sample / 1000), "unit": "img/s",
                    "ms_per_batch": ms_sample, "steps": 10, "batch_per_gpu": B,
                    "tflops_per_gpu": FWD_GFLOP_PER_IMG * 10 * B / ms_sample},
+        "sample_sweep": {str(n): {"img_per_s": B * world / (sweep[n] / 1000), "ms_per_batch": sweep[n],
+                                  "tflops_per_gpu": FWD_GFLOP_PER_IMG * n * B / sweep[n]} for n in sorted(sweep)},
         "cpu_baseline": cpu,
+        "torch_gpu_eager": eager,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -319,10 +490,14 @@ def main():
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--config", default="cifar", choices=["cifar"] + sorted(LATENT_CONFIGS),
+                    help="cifar = the headline (BASELINE configs 2 and 3); celebahq / div2k = configs 4 / 5, one GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "cifar":
+        run_latent(args)
     else:
         run_ours(args)
 

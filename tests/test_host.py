@@ -171,6 +171,25 @@ def test_autoencoder_kl_layout_and_errors(golden_dir):
         ae.encode(torch.zeros(1, 3, 64, 64))
 
 
+def test_augment_pipe_reproduces_the_reference(golden_dir):
+    """adm_b200.ddm.augment.AugmentPipe vs the batch recorded from the unmodified reference AugmentPipe
+    (tests/golden/make_golden_augment.py; ddm/augment.py:115-328 with the arguments of ddm_const.py:179-180) under the
+    same global seed: labels exact, images to float32 round-off; p = 1 makes every transform fire on every sample."""
+    import torch
+    from adm_b200.ddm.augment import AugmentPipe
+    from tests.golden.make_golden_augment import KW, KW_HOT, SEEDS, inputs
+    g = torch.load(os.path.join(golden_dir, "augment.pt"))
+    for name, kw in (("cfg", KW), ("hot", KW_HOT)):
+        for seed in SEEDS:
+            torch.manual_seed(seed)
+            y, lab = AugmentPipe(**kw)(inputs(seed))
+            ref = g[f"{name}_{seed}"]
+            assert lab.shape == (16, 9) and torch.equal(lab, ref["labels"])
+            assert (y - ref["images"]).abs().max().item() < 1e-4
+    with pytest.raises(NotImplementedError):
+        AugmentPipe(brightness=1)
+
+
 def test_ema_schedule_and_state_dict_match_reference_semantics():
     """ddm/ema.py:132-156: copy until update_after_step, then lerp with decay 1 - (1 + epoch)^-power clamped to beta,
     every update_every calls; state_dict keys online_model.* / ema_model.* / initted / step."""
@@ -225,20 +244,18 @@ def test_yaml_config_builds_the_reference_surface():
         assert get_obj_by_name(ref_name).__module__ == ours
 
 
-def test_use_augment_needs_the_host_projects_pipe():
-    """use_augment: True (the reference CIFAR YAML) resolves the host project's ddm.augment.AugmentPipe; without it the
-    module says so instead of silently training without augmentation."""
-    import sys
-    import pytest
+def test_use_augment_builds_the_in_tree_pipe():
+    """use_augment: True (the reference CIFAR YAML, line 17) builds adm_b200.ddm.augment.AugmentPipe with the reference's
+    arguments (ddm_const.py:179-180); without the flag there is no pipe."""
     import torch
+    from adm_b200.ddm.augment import AugmentPipe
     from adm_b200.ddm.ddm_const import DDPM
 
     class Net(torch.nn.Module):
         channels, self_condition = 3, None
 
     cfg = dict(image_size=[32, 32], use_augment=True)
-    if "ddm.augment" not in sys.modules and not any(p.rstrip("/").endswith("reference") for p in sys.path):
-        with pytest.raises(NotImplementedError):
-            DDPM(model=Net(), cfg=cfg, **cfg)
+    d = DDPM(model=Net(), cfg=cfg, **cfg)
+    assert isinstance(d.augment, AugmentPipe) and d.augment.p == 0.15 and d.augment.xflip == 1e8
     d = DDPM(model=Net(), cfg=dict(image_size=[32, 32]), image_size=[32, 32])
     assert d.augment is None and d.use_augment is False
