@@ -332,16 +332,37 @@ class TrainStep:
             return {"augment_labels": self.static_aug}
         return {}
 
+    def prefetch(self, x):
+        """Stage the NEXT batch (device or pinned host tensor) for the following replay().  With an augmentation pipe this
+        runs the pipe on a side stream, i.e. concurrently with the step that is executing — its ~40 small kernels fill
+        the gaps of the step instead of sitting in front of it."""
+        if getattr(self, "static_aug", None) is None:
+            self._pending = (x, None, None)
+            return
+        if getattr(self, "_aug_stream", None) is None:
+            self._aug_stream = torch.cuda.Stream()
+        with torch.cuda.stream(self._aug_stream):
+            xa, lab = self.dpm.augment(x.to(self.static_x.device, non_blocking=True))
+            ev = torch.cuda.Event()
+            ev.record()
+        self._pending = (xa, lab, ev)
+
     def replay(self, x=None):
-        """One optimizer step through the captured graph; `x` (device or pinned host) is copied into the static input
-        (after the augmentation pipe when the model has one)."""
+        """One optimizer step through the captured graph on the batch staged by prefetch() (or on `x`, staged now)."""
         if x is not None:
-            if getattr(self, "static_aug", None) is not None:
-                xa, lab = self.dpm.augment(x.to(self.static_x.device, non_blocking=True))
+            self.prefetch(x)
+        pend, self._pending = getattr(self, "_pending", None), None
+        if pend is not None:
+            xa, lab, ev = pend
+            if ev is None:
+                self.static_x.copy_(xa, non_blocking=True)
+            else:
+                cur = torch.cuda.current_stream()
+                cur.wait_event(ev)
                 self.static_x.copy_(xa)
                 self.static_aug.copy_(lab)
-            else:
-                self.static_x.copy_(x, non_blocking=True)
+                xa.record_stream(cur)
+                lab.record_stream(cur)
         self.step_count += 1
         self._push_hyper()
         if self.segments is not None:

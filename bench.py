@@ -367,11 +367,18 @@ def run_ours(args):
             step.segments = step.graph = None
 
     def one_step(x):
+        """One optimizer step on the batch staged by the previous call, then stage `x` for the next one (the augmentation
+        pipe runs on a side stream under the step; every step still augments, copies and consumes a fresh batch)."""
         if use_graph:
-            return step.replay(x)
+            loss = step.replay()
+            step.prefetch(x)
+            return loss
         loss = step.micro_step(x.to(device, non_blocking=True))
         step.optimizer_step()
         return loss
+
+    if use_graph:
+        step.prefetch(x_dev)
 
     def barrier():
         if world > 1:
