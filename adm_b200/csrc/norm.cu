@@ -921,7 +921,7 @@ __global__ void __launch_bounds__(512, 1) gn_bwd_fused_kernel(
     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dparams, long long ld_dparams,
     const __nv_bfloat16* __restrict__ add, long long ldadd, int add_mode, __nv_bfloat16* __restrict__ dx1,
     long long ldx1, __nv_bfloat16* __restrict__ dx2, long long ldx2, float* __restrict__ dbias1,
-    float* __restrict__ dbias1b, const unsigned long long* __restrict__ seed_dev) {
+    float* __restrict__ dbias1b, const unsigned long long* __restrict__ seed_dev, int dy_scratch) {
     cg::cluster_group cluster = cg::this_cluster();
     const int K = static_cast<int>(cluster.num_blocks()), r = static_cast<int>(cluster.block_rank());
     if (seed_dev != nullptr) seed += *seed_dev * 0x9E3779B97F4A7C15ull;
@@ -945,6 +945,10 @@ __global__ void __launch_bounds__(512, 1) gn_bwd_fused_kernel(
     const int step = K * tpv;
     const int p0 = r * tpv + lane;
     const bool piped = resample == 0 && (add == nullptr || add_mode == 0);  // the common, fully pipelined shape
+    // dy_scratch: the caller does not need dy afterwards.  Pass 1 then overwrites it with dv (the gradient at the
+    // pre-activation, bf16) and pass 2 reads that back instead of re-deriving it: the SiLU derivative and the dropout hash
+    // are evaluated once per element instead of twice (this kernel is instruction-issue bound, not DRAM bound).
+    const bool reuse_dv = dy_scratch != 0 && piped && dx1 != nullptr && (act != 0 || drop_p > 0.f);
     float a[8], b[8];      // pre-activation coefficients (as stored)
     float ah[8], bh[8];    // halved when act (tanh-form SiLU); used by the pipelined path
     if (active) {
@@ -992,6 +996,12 @@ __global__ void __launch_bounds__(512, 1) gn_bwd_fused_kernel(
                 for (int j = 0; j < 8; ++j) {
                     s1[j] += dv[j];
                     sx[j] = fmaf(dv[j], xv.v[j], sx[j]);
+                }
+                if (reuse_dv) {
+                    Vec8 t;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) t.v[j] = dv[j];
+                    store8(const_cast<__nv_bfloat16*>(dyb) + p * ldy, t);
                 }
             }
             cp_async_wait<0>();
@@ -1113,7 +1123,12 @@ __global__ void __launch_bounds__(512, 1) gn_bwd_fused_kernel(
                 pf += step;
                 if (++st == GNF_STAGES) st = 0;
                 float dv[8];
-                dv_from(g, xv, ah, bh, act, drop_p, seed, vec0 + 1ULL * p * V, dv);
+                if (reuse_dv) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dv[j] = g.v[j];  // pass 1 left dv in dy's place
+                } else {
+                    dv_from(g, xv, ah, bh, act, drop_p, seed, vec0 + 1ULL * p * V, dv);
+                }
                 Vec8 o;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o.v[j] = fmaf(dv[j], k1[j], fmaf(xv.v[j], k2[j], k3[j]));
@@ -1353,7 +1368,7 @@ int adm_gn_bwd(const void* dy, long long ldy, const void* x1, int c1, long long 
                unsigned long long seed, const unsigned long long* seed_counter, int resample, float* work,
                float* bcoef, float* dgamma, float* dbeta, float* dparams, long long ld_dparams, const void* add,
                long long ldadd, int add_mode, void* dx1, long long ldx1, void* dx2, long long ldx2, float* dbias1,
-               float* dbias1b, void* stream) {
+               float* dbias1b, int dy_scratch, void* stream) {
     const unsigned long long* g_seed_dev = drop_p > 0.f ? seed_counter : nullptr;
     const int C = c1 + c2;
     ADM_REQUIRE(c1 > 0 && c1 % 8 == 0 && c2 % 8 == 0 && C % groups == 0, "gn_bwd: bad channels / groups");
@@ -1372,7 +1387,7 @@ int adm_gn_bwd(const void* dy, long long ldy, const void* x1, int c1, long long 
             gn_bwd_fused_kernel, n * kc, threads, smem, kc, s, dyp, ldy, x1p, c1, ld1, x2p, c2, ld2, h, w, groups,
             reinterpret_cast<const float4*>(coef), gamma, beta, params, ld_params, act, drop_p, seed, resample, dgamma,
             dbeta, dparams, ld_dparams, static_cast<const bf16*>(add), ldadd, add_mode, static_cast<bf16*>(dx1), ldx1,
-            static_cast<bf16*>(dx2), ldx2, dbias1, dbias1b, g_seed_dev);
+            static_cast<bf16*>(dx2), ldx2, dbias1, dbias1b, g_seed_dev, dy_scratch);
         if (e != cudaSuccess) {
             set_error("gn_bwd (fused) launch: %s", cudaGetErrorString(e));
             return ADM_ERR_CUDA;

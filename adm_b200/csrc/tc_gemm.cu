@@ -151,12 +151,13 @@ static int launch_pair(const CUtensorMap& a, const CUtensorMap& a2, const CUtens
     return 0;
 }
 
-// Halo conv launch (tc_conv_halo_kernel): plain persistent grid.
-static int launch_halo(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const GemmParams& p,
-                       cudaStream_t stream) {
+// Halo conv launch (tc_conv_halo_kernel): plain persistent grid.  PRO = with the GroupNorm + SiLU prologue warps.
+template <bool PRO>
+static int launch_halo_t(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const GemmParams& p,
+                         cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_halo_kernel<PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              GEMM_SMEM_TOTAL);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -170,7 +171,7 @@ static int launch_halo(const CUtensorMap& a, const CUtensorMap& a2, const CUtens
         return ADM_ERR_SHAPE;
     }
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    tc_conv_halo_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_TOTAL, stream>>>(a, a2, b, p);
+    tc_conv_halo_kernel<PRO><<<grid, PRO ? GEMM_PRO_THREADS : GEMM_THREADS, GEMM_SMEM_TOTAL, stream>>>(a, a2, b, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("tc_conv_halo launch: %s", cudaGetErrorString(e));
@@ -178,6 +179,11 @@ static int launch_halo(const CUtensorMap& a, const CUtensorMap& a2, const CUtens
     }
     count_launch();
     return 0;
+}
+
+static int launch_halo(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const GemmParams& p,
+                       cudaStream_t stream) {
+    return p.pro_coef != nullptr ? launch_halo_t<true>(a, a2, b, p, stream) : launch_halo_t<false>(a, a2, b, p, stream);
 }
 
 static int launch_wgrad_rows(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& b2, const GemmParams& p,
@@ -336,6 +342,20 @@ static int nhwc_map(CUtensorMap* m, const void* ptr, int c, long long ld, int n,
 
 using namespace adm;
 
+struct ProArgs {  // GroupNorm prologue of adm_conv_fprop_gn
+    const float* coef;
+    int act;
+    float drop_p;
+    unsigned long long seed;
+    const unsigned long long* seed_dev;
+    void* a_out;
+    long long ld_a;
+};
+static int conv_fprop_impl(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int h,
+                           int w, const void* wpk, int nout, int ntaps, void* out, int out_mode, long long ldc,
+                           const float* bias, const void* residual, long long ldr, float alpha, float* stats,
+                           const ProArgs* pro, void* stream);
+
 extern "C" {
 
 int adm_conv_stats_slots(int h, int w) {
@@ -354,6 +374,35 @@ int adm_conv_fprop_stats(const void* x1, int c1, long long ld1, const void* x2, 
                          int w, const void* wpk, int nout, int ntaps, void* out, int out_mode, long long ldc,
                          const float* bias, const void* residual, long long ldr, float alpha, float* stats,
                          void* stream) {
+    return conv_fprop_impl(x1, c1, ld1, x2, c2, ld2, n, h, w, wpk, nout, ntaps, out, out_mode, ldc, bias, residual, ldr,
+                           alpha, stats, nullptr, stream);
+}
+
+int adm_conv_gn_ok(int h, int w) { return halo_ok(9, h, w) ? 1 : 0; }
+
+int adm_conv_fprop_gn(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int h, int w,
+                      const void* wpk, int nout, void* out, long long ldc, const float* bias, const void* residual,
+                      long long ldr, const float* coef, int act, float drop_p, unsigned long long seed,
+                      const unsigned long long* seed_counter, void* a_out, long long ld_a, void* stream) {
+    if (coef == nullptr || !halo_ok(9, h, w)) {
+        set_error("conv_fprop_gn: needs a coefficient table and an image that tiles into 8 x 16 pixel boxes (got %d x %d)", h, w);
+        return ADM_ERR_SHAPE;
+    }
+    if (c1 + c2 > 1024) { set_error("conv_fprop_gn: more than 1024 input channels"); return ADM_ERR_SHAPE; }
+    ProArgs pro;
+    pro.coef = coef; pro.act = act; pro.drop_p = drop_p; pro.seed = seed;
+    pro.seed_dev = drop_p > 0.f ? seed_counter : nullptr;
+    pro.a_out = a_out; pro.ld_a = ld_a;
+    return conv_fprop_impl(x1, c1, ld1, x2, c2, ld2, n, h, w, wpk, nout, 9, out, OUT_BF16, ldc, bias, residual, ldr, 1.f,
+                           nullptr, &pro, stream);
+}
+
+}  // extern "C"
+
+static int conv_fprop_impl(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int h,
+                           int w, const void* wpk, int nout, int ntaps, void* out, int out_mode, long long ldc,
+                           const float* bias, const void* residual, long long ldr, float alpha, float* stats,
+                           const ProArgs* pro, void* stream) {
     if (int e = init_driver()) return e;
     if (ntaps != 1 && ntaps != 9) { set_error("conv_fprop: ntaps must be 1 or 9"); return ADM_ERR_SHAPE; }
     if (c1 <= 0 || c1 % 8 || (x2 && (c2 <= 0 || c2 % 8))) { set_error("conv_fprop: channels must be multiples of 8"); return ADM_ERR_SHAPE; }
@@ -385,6 +434,14 @@ int adm_conv_fprop_stats(const void* x1, int c1, long long ld1, const void* x2, 
         p.stats = stats;
         p.stats_slots = adm_conv_stats_slots(h, w);
     }
+    if (pro != nullptr) {
+        p.pro_coef = reinterpret_cast<const float4*>(pro->coef);
+        p.pro_act = pro->act; p.pro_c1 = c1; p.pro_c2 = x2 ? c2 : 0;
+        p.pro_drop_p = pro->drop_p; p.pro_seed = pro->seed; p.pro_seed_dev = pro->seed_dev;
+        p.pro_out = static_cast<__nv_bfloat16*>(pro->a_out); p.pro_ldo = pro->ld_a;
+        p.pro_x1 = static_cast<const __nv_bfloat16*>(x1); p.pro_ld1 = ld1;
+        p.pro_x2 = static_cast<const __nv_bfloat16*>(x2); p.pro_ld2 = ld2;
+    }
     CUtensorMap ma, ma2, mb;
     const int abw = halo ? HALO_W : p.bw, abh = halo ? HALO_H : p.bh;  // A box: the tile, or the tile + its 3x3 halo
     if (int e = nhwc_map(&ma, x1, c1, ld1, n, h, w, abw, abh, p.bni)) return e;
@@ -395,13 +452,15 @@ int adm_conv_fprop_stats(const void* x1, int c1, long long ld1, const void* x2, 
     // CTA pairs: 256-pixel tiles, each CTA loading half of the weight rows (box BN/2) — when there are at least two
     // pixel tiles and the output mode is a plain store.
     const bool pair = !halo && pair_enabled() && p.m_tiles >= 2 && p.bn % 16 == 0 && out_mode != OUT_F32_ATOMIC &&
-                      stats == nullptr;
+                      stats == nullptr && pro == nullptr;
     const int bb[2] = {64, pair ? p.bn / 2 : p.bn};
     if (int e = encode_map(&mb, wpk, 2, bd, bs, bb)) return e;
     if (pair) return launch_pair(ma, ma2, mb, p, static_cast<cudaStream_t>(stream));
     if (halo) return launch_halo(ma, ma2, mb, p, static_cast<cudaStream_t>(stream));
     return launch<GEMM_CONV>(ma, ma2, mb, p, static_cast<cudaStream_t>(stream));
 }
+
+extern "C" {
 
 int adm_conv_dgrad(const void* dy, int cout, long long ld_dy, int n, int h, int w, const void* wpk, int kpad,
                    int ntaps, void* dx, int n_valid, long long ldc, const void* residual, long long ldr, float alpha,

@@ -27,7 +27,13 @@ constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;   // TMA warp + MMA warp 
 constexpr int PAIR_THREADS = 192;                        // the (experimental) CTA-pair kernel keeps 4 epilogue warps
 constexpr int GEMM_A_STAGE = GEMM_BLOCK_M * 128;  // 16 KB
 constexpr int GEMM_SMEM_RING = 200 * 1024;        // operand ring budget
-constexpr int GEMM_SMEM_AUX = 4096;               // barriers + tmem ptr (first 1 KB) + per-tile bias slices (2 x 1 KB)
+constexpr int GEMM_SMEM_AUX = 4096 + 8192;        // barriers + tmem ptr (first 1 KB) + per-tile bias slices (2 x 1 KB) +
+                                                  // 1 KB spare + the prologue's per-tile (A, B) table (1024 channels x 8 B)
+// halo conv with the GroupNorm prologue: + 4 transform warps.  (8 warps halve the transform time but cap the kernel at 128
+// registers per thread, which spills in the epilogue; measured in the step they are equal within noise — see
+// profiles/r03_conv_gn_prologue.txt for all the variants that were timed.)
+constexpr int GEMM_PRO_WARPS = 4;
+constexpr int GEMM_PRO_THREADS = GEMM_THREADS + 32 * GEMM_PRO_WARPS;
 constexpr int GEMM_SMEM_TOTAL = GEMM_SMEM_RING + GEMM_SMEM_AUX + 1024;  // + alignment slack
 constexpr int GEMM_MAX_STAGES = 8;
 
@@ -69,7 +75,54 @@ struct GemmParams {
     // instead of re-reading the activation (adm_gn_finalize).  nullptr = off.
     float* stats;
     int stats_slots;  // slots per sample: (H*W) / 32, at least 1
+    // ---- GroupNorm(+ adaptive scale/shift) + SiLU (+ dropout) PROLOGUE of the halo conv kernel (north_star: "implicit-GEMM
+    // conv3x3 ... with a GroupNorm+SiLU prologue"): the conv reads the RAW tensor; four transform warps apply
+    // y = dropout(silu(x * A[n,c] + B[n,c])) to each halo tile in shared memory, once per 64-channel chunk (not once per
+    // tap), between the TMA load and the MMAs.  pro_coef = the norm's coefficient table [n][C]{A, B, mean, rstd}.
+    const float4* pro_coef;
+    int pro_act, pro_c1, pro_c2;          // SiLU on/off; valid channels of A source 1 / 2 (C = c1 + c2)
+    float pro_drop_p;
+    unsigned long long pro_seed;
+    const unsigned long long* pro_seed_dev;
+    __nv_bfloat16* pro_out;               // optional: the activated tensor [N,H,W,C] (the wgrad operand), written once
+    long long pro_ldo;
+    const __nv_bfloat16* pro_x1;          // the raw A sources (the prologue warps read them with plain vector loads)
+    const __nv_bfloat16* pro_x2;
+    long long pro_ld1, pro_ld2;
 };
+
+// sm_100a SFU tanh; silu(v) = h * tanh(h) + h with h = v / 2
+__device__ __forceinline__ float gemm_tanh_fast(float h) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return t;
+}
+// The dropout keep-scales of csrc/norm.cu (same hash, same indexing: backward regenerates these masks there).
+__device__ __forceinline__ uint32_t gemm_mix32(uint32_t h) {
+    h ^= h >> 16;
+    h *= 0x85EBCA6Bu;
+    h ^= h >> 13;
+    h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
+}
+__device__ __forceinline__ void gemm_dropout_scales(unsigned long long seed, unsigned long long vec_index, float p,
+                                                    float (&s)[8]) {
+    const unsigned long long z = (vec_index + seed) * 0x9E3779B97F4A7C15ull;
+    const uint32_t base =
+        gemm_mix32(static_cast<uint32_t>(z) ^ static_cast<uint32_t>(z >> 32) ^ static_cast<uint32_t>(seed >> 20));
+    const float keep = __frcp_rn(1.f - p);
+    const uint32_t thr = static_cast<uint32_t>(p * 65536.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t w = (base + static_cast<uint32_t>(i) * 0x9E3779B9u) * 0x85EBCA6Bu;
+        w ^= w >> 15;
+        w *= 0xC2B2AE35u;
+        w ^= w >> 16;
+        s[2 * i] = ((w & 0xFFFFu) >= thr) ? keep : 0.f;
+        s[2 * i + 1] = ((w >> 16) >= thr) ? keep : 0.f;
+    }
+}
 
 __device__ __forceinline__ void decode_pix(const GemmParams& p, int idx, int& n0, int& h0, int& w0) {
     const int per = p.tiles_w * p.tiles_h;
@@ -722,7 +775,8 @@ constexpr int HALO_TX_BYTES = HALO_W * HALO_H * 128;  // 23040
 constexpr int HALO_BYTES = 23 * 1024;                 // buffer pitch, 1024-aligned
 constexpr int HALO_BUFS = 3;
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <bool PRO>
+__global__ void __launch_bounds__(PRO ? GEMM_PRO_THREADS : GEMM_THREADS, 1)
 tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -736,9 +790,10 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* bempty = bfull + GEMM_MAX_STAGES;
     uint64_t* tfull_bar = bempty + GEMM_MAX_STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint64_t* hfull = tempty_bar + 2;
+    uint64_t* hfull = tempty_bar + 2;                    // halo buffer ready for the MMAs
     uint64_t* hempty = hfull + HALO_BUFS;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(hempty + HALO_BUFS);
+    uint64_t* hraw = PRO ? hempty + HALO_BUFS : hfull;   // halo buffer landed (PRO: still to be transformed)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(hempty + 2 * HALO_BUFS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -752,8 +807,9 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_init(&bempty[i], 1);
         }
         for (int i = 0; i < HALO_BUFS; ++i) {
-            mbar_init(&hfull[i], 1);
+            mbar_init(&hfull[i], PRO ? GEMM_PRO_WARPS : 1);
             mbar_init(&hempty[i], 1);
+            if (PRO) mbar_init(&hraw[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
@@ -779,23 +835,29 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 int n0, h0, w0;
                 decode_pix(p, (tile / p.n_tiles) % p.m_tiles, n0, h0, w0);
                 mbar_wait(&hempty[hs], hphase ^ 1, 5);
-                mbar_expect_tx(&hfull[hs], HALO_TX_BYTES);
+                mbar_expect_tx(&hraw[hs], HALO_TX_BYTES);
                 uint8_t* dst = smem + hs * HALO_BYTES;
                 if (kc < p.cchunks1)
-                    tma_load_4d(dst, &tmA, &hfull[hs], kc * 64, w0 - 1, h0 - 1, n0);
+                    tma_load_4d(dst, &tmA, &hraw[hs], kc * 64, w0 - 1, h0 - 1, n0);
                 else
-                    tma_load_4d(dst, &tmA2, &hfull[hs], (kc - p.cchunks1) * 64, w0 - 1, h0 - 1, n0);
+                    tma_load_4d(dst, &tmA2, &hraw[hs], (kc - p.cchunks1) * 64, w0 - 1, h0 - 1, n0);
                 if (++hs == HALO_BUFS) { hs = 0; hphase ^= 1; }
             };
-            if (static_cast<int>(blockIdx.x) < num_tiles) load_halo(blockIdx.x, 0);
+            // Halo loads run AHEAD of the weight tiles by `ahead` chunk steps (a cursor over (tile, chunk) that only this
+            // thread advances): 1 step hides the TMA latency (and, with the GroupNorm prologue, the transform) under the nine
+            // MMAs of the current chunk; three buffers: loading / transforming, multiplying, draining.
+            int cur_tile = blockIdx.x, cur_kc = 0;
+            auto next_halo = [&]() {
+                if (cur_tile >= num_tiles) return;
+                load_halo(cur_tile, cur_kc);
+                if (++cur_kc == p.cchunks) { cur_kc = 0; cur_tile += gridDim.x; }
+            };
+            const int ahead = 1;  // (2 makes this thread wait for the buffer still being multiplied before it issues weights)
+            for (int i = 0; i < ahead; ++i) next_halo();
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_tiles;
                 for (int kc = 0; kc < p.cchunks; ++kc) {
-                    // the NEXT chunk step's halo goes out before this step's nine weight tiles
-                    if (kc + 1 < p.cchunks)
-                        load_halo(tile, kc + 1);
-                    else if (tile + static_cast<int>(gridDim.x) < num_tiles)
-                        load_halo(tile + gridDim.x, 0);
+                    next_halo();  // the halo `ahead` steps from now goes out before this step's nine weight tiles
                     for (int tap = 0; tap < 9; ++tap) {
                         mbar_wait(&bempty[bs], bphase ^ 1, 1);
                         uint8_t* sb = b_ring + bs * b_bytes;
@@ -849,8 +911,97 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else {
+    } else if (warp < 2 + GEMM_EPI_WARPS) {
         epilogue_warps<GEMM_CONV>(p, smem, tmem_base, tfull_bar, tempty_bar, warp, lane, num_tiles);
+    } else if (PRO) {
+        // =========================================================== GroupNorm + SiLU (+ dropout) prologue warps
+        // Thread tt owns the 16-byte unit u = tt & 7 (8 channels) of the rows r = tt >> 3, + PT / 8, ... of each 180-row halo
+        // tile.  A row is one halo pixel; rows outside the image were zero-filled by TMA and must stay zero (the conv pads
+        // the ACTIVATED tensor), channels beyond the valid count get A = B = 0 (silu(0) = 0).
+        constexpr int PT = 32 * GEMM_PRO_WARPS;
+        const int tt = threadIdx.x - GEMM_THREADS;
+        const int u = tt & 7, r0 = tt >> 3;
+        float2* sco = reinterpret_cast<float2*>(smem + GEMM_SMEM_RING + 4096);  // [cchunks * 64] (A, B) of this tile's sample
+        const int C = p.pro_c1 + p.pro_c2, V = C >> 3;
+        unsigned long long seed = p.pro_seed;
+        if (p.pro_seed_dev != nullptr) seed += *p.pro_seed_dev * 0x9E3779B97F4A7C15ull;
+        int hs = 0;
+        uint32_t hphase = 0;
+        int last_n = -1;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int n0, h0, w0;
+            decode_pix(p, (tile / p.n_tiles) % p.m_tiles, n0, h0, w0);
+            const bool writer = p.pro_out != nullptr && (tile % p.n_tiles) == 0;
+            if (n0 != last_n) {  // (uniform over these warps) stage this sample's coefficients, padded per 64-channel chunk
+                asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");
+                for (int i = tt; i < p.cchunks * 64; i += PT) {
+                    const int kc = i >> 6, cc = i & 63;
+                    const bool first = kc < p.cchunks1;
+                    const int ch = first ? kc * 64 + cc : (kc - p.cchunks1) * 64 + cc;
+                    const bool ok = ch < (first ? p.pro_c1 : p.pro_c2);
+                    float2 ab = make_float2(0.f, 0.f);
+                    if (ok) {
+                        const float4 t = __ldg(p.pro_coef + 1LL * n0 * C + (first ? ch : p.pro_c1 + ch));
+                        ab = p.pro_act ? make_float2(0.5f * t.x, 0.5f * t.y) : make_float2(t.x, t.y);
+                    }
+                    sco[i] = ab;
+                }
+                asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");
+                last_n = n0;
+            }
+            for (int kc = 0; kc < p.cchunks; ++kc) {
+                mbar_wait(&hraw[hs], hphase, 7);
+                uint8_t* buf = smem + hs * HALO_BYTES;
+                float a[8], b[8];
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    const float4 t = *reinterpret_cast<const float4*>(sco + kc * 64 + u * 8 + j);
+                    a[j] = t.x; b[j] = t.y; a[j + 1] = t.z; b[j + 1] = t.w;
+                }
+                const bool first = kc < p.cchunks1;
+                const int cbase = first ? kc * 64 + u * 8 : p.pro_c1 + (kc - p.cchunks1) * 64 + u * 8;  // channel in the concat
+                const bool ch_ok = (first ? kc * 64 + u * 8 : (kc - p.cchunks1) * 64 + u * 8) < (first ? p.pro_c1 : p.pro_c2);
+#pragma unroll 1
+                for (int r = r0; r < HALO_W * HALO_H; r += PT / 8) {
+                    const int hy = r / HALO_W, hx = r - hy * HALO_W;
+                    const int y = h0 - 1 + hy, x = w0 - 1 + hx;
+                    if (y < 0 || y >= p.H || x < 0 || x >= p.W) continue;
+                    uint4* cell = reinterpret_cast<uint4*>(buf + r * 128 + ((u ^ (r & 7)) << 4));
+                    const uint4 raw = *cell;
+                    const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        v[2 * j] = __uint_as_float(w4[j] << 16);
+                        v[2 * j + 1] = __uint_as_float(w4[j] & 0xFFFF0000u);
+                    }
+                    const long long pix = (static_cast<long long>(n0) * p.H + y) * p.W + x;
+                    float ds[8];
+                    if (p.pro_drop_p > 0.f)
+                        gemm_dropout_scales(seed, static_cast<unsigned long long>(pix) * V + (cbase >> 3), p.pro_drop_p, ds);
+                    uint32_t o[4];
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        float y0 = fmaf(v[j], a[j], b[j]), y1 = fmaf(v[j + 1], a[j + 1], b[j + 1]);
+                        if (p.pro_act) {
+                            y0 = fmaf(y0, gemm_tanh_fast(y0), y0);
+                            y1 = fmaf(y1, gemm_tanh_fast(y1), y1);
+                        }
+                        if (p.pro_drop_p > 0.f) { y0 *= ds[j]; y1 *= ds[j + 1]; }
+                        const __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
+                        o[j >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+                    }
+                    const uint4 res = make_uint4(o[0], o[1], o[2], o[3]);
+                    *cell = res;
+                    if (writer && ch_ok && hy >= 1 && hy <= HALO_H - 2 && hx >= 1 && hx <= HALO_W - 2)
+                        *reinterpret_cast<uint4*>(p.pro_out + pix * p.pro_ldo + cbase) = res;
+                }
+                fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hfull[hs]);
+                if (++hs == HALO_BUFS) { hs = 0; hphase ^= 1; }
+            }
+        }
     }
 
     tc_fence_before();

@@ -206,6 +206,41 @@ def conv_fprop(x1, wpk, x2=None, bias=None, residual=None, alpha=1.0, out_dtype=
     return (res, st) if stats else res
 
 
+def conv_gn_ok(h, w):
+    """Image sizes the conv with the fused GroupNorm prologue serves (8 x 16 pixel halo tiles)."""
+    return bool(_lib.load().adm_conv_gn_ok(int(h), int(w)))
+
+
+def conv_fprop_gn(x1, wpk, coef, x2=None, bias=None, residual=None, act=True, drop_p=0.0, seed=0, seed_counter=None,
+                  want_act=True):
+    """conv3x3(dropout(silu(x * A + B))) with the GroupNorm prologue fused into the conv: reads the RAW x1 (| x2) and the
+    norm's coefficient table coef [N, C, 4].  Returns (out, a) with a = the activated tensor [N, H, W, C] (what the
+    weight-gradient kernel needs; None when want_act is False, e.g. in inference)."""
+    _need_cuda(x1, wpk, coef)
+    p1, c1, ld1, n, h, w = _nhwc(x1)
+    p2, c2, ld2 = None, 0, 0
+    if x2 is not None:
+        p2, c2, ld2, n2, h2, w2 = _nhwc(x2)
+        assert (n2, h2, w2) == (n, h, w)
+    nout, ntaps, kpad = wpk.shape
+    assert ntaps == 9 and kpad == pad64(c1) + (pad64(c2) if x2 is not None else 0), (wpk.shape, c1, c2)
+    assert coef.dtype == F32 and tuple(coef.shape) == (n, c1 + c2, 4) and coef.is_contiguous()
+    ldc = (nout + 7) // 8 * 8
+    out = torch.empty(n, h, w, ldc, device=x1.device, dtype=BF16)
+    if ldc != nout:
+        out.zero_()
+    a = torch.empty(n, h, w, c1 + c2, device=x1.device, dtype=BF16) if want_act else None
+    ldr = 0
+    if residual is not None:
+        assert residual.dtype == BF16 and residual.stride(3) == 1
+        ldr = residual.stride(2)
+    check(_lib.load().adm_conv_fprop_gn(p1, c1, ld1, p2, c2, ld2, n, h, w, _ptr(wpk), nout, _ptr(out), ldc, _ptr(bias),
+                                        _ptr(residual), ldr, _ptr(coef), int(act), float(drop_p),
+                                        int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(seed_counter), _ptr(a),
+                                        a.stride(2) if a is not None else 0, _stream()), "conv_fprop_gn")
+    return (out[..., :nout] if ldc != nout else out), a
+
+
 def conv_dgrad(dy, wpk, n_valid=None, residual=None, alpha=1.0, out=None):
     """dx = conv^T(dy) using the fprop-packed weights.  Returns NHWC bf16 [N,H,W,n_valid]."""
     _need_cuda(dy, wpk)
@@ -340,10 +375,11 @@ def gn_apply(x1, x2, coef, act=True, drop_p=0.0, seed=0, resample=0, seed_counte
 
 
 def gn_forward(x1, x2, gamma, beta, groups, eps=1e-5, params=None, act=True, drop_p=0.0, seed=0, resample=0,
-               seed_counter=None):
+               seed_counter=None, apply=True):
     """GroupNorm statistics + apply in one call (one cluster-per-sample kernel when the batch fills the SMs).
     seed_counter: optional CUDA int64[1] step counter mixed into the dropout seed (read only when drop_p > 0).
-    Returns (coef [N, C, 4], y)."""
+    apply=False: statistics only (the coefficient table for a conv with the GroupNorm prologue, conv_fprop_gn).
+    Returns (coef [N, C, 4], y or None)."""
     _need_cuda(x1)
     n, h, w, _ = x1.shape
     p1, c1, ld1 = _src(x1)
@@ -352,12 +388,12 @@ def gn_forward(x1, x2, gamma, beta, groups, eps=1e-5, params=None, act=True, dro
     work = torch.empty(2 * n * c + n, device=x1.device, dtype=F32)
     coef = torch.empty(n, c, 4, device=x1.device, dtype=F32)
     ho, wo = (h // 2, w // 2) if resample == 1 else ((2 * h, 2 * w) if resample == 2 else (h, w))
-    out = torch.empty(n, ho, wo, c, device=x1.device, dtype=BF16)
+    out = torch.empty(n, ho, wo, c, device=x1.device, dtype=BF16) if apply else None
     ldp = params.stride(0) if params is not None else 0
     check(_lib.load().adm_gn_forward(p1, c1, ld1, p2, c2, ld2, n, h, w, groups, float(eps), _ptr(gamma), _ptr(beta),
                                      _ptr(params), ldp, _ptr(work), _ptr(coef), int(act), float(drop_p),
                                      int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(seed_counter), int(resample), _ptr(out),
-                                     out.stride(2), _stream()), "gn_forward")
+                                     out.stride(2) if apply else c, _stream()), "gn_forward")
     return coef, out
 
 
@@ -382,9 +418,9 @@ def gn_forward_stats(x1, st1, x2, st2, gamma, beta, groups, eps=1e-5, params=Non
 
 def gn_bwd(dy, x1, x2, coef, gamma, beta, groups, params=None, act=True, drop_p=0.0, seed=0, resample=0,
            dgamma=None, dbeta=None, dparams=None, add=None, add_mode=0, need_dx=True, dbias1=None, dbias1b=None,
-           seed_counter=None):
+           seed_counter=None, dy_scratch=False):
     """Returns (dx1, dx2).  dgamma/dbeta are accumulated in place; dparams ([N, 2C] view) is overwritten;
-    dbias1 (fp32 [c1]) += column sums of dx1."""
+    dbias1 (fp32 [c1]) += column sums of dx1.  dy_scratch=True lets the kernel overwrite dy (saves recomputation)."""
     n, h, w, _ = x1.shape
     p1, c1, ld1 = _src(x1)
     p2, c2, ld2 = _src(x2)
@@ -403,8 +439,8 @@ def gn_bwd(dy, x1, x2, coef, gamma, beta, groups, params=None, act=True, drop_p=
                                  _ptr(dbeta), _ptr(dparams), lddp, _ptr(add),
                                  add.stride(-2) if add is not None else 0, int(add_mode), _ptr(dx1),
                                  dx1.stride(2) if dx1 is not None else 0, _ptr(dx2),
-                                 dx2.stride(2) if dx2 is not None else 0, _ptr(dbias1), _ptr(dbias1b), _stream()),
-          "gn_bwd")
+                                 dx2.stride(2) if dx2 is not None else 0, _ptr(dbias1), _ptr(dbias1b), int(dy_scratch),
+                                 _stream()), "gn_bwd")
     return dx1, dx2
 
 

@@ -63,6 +63,16 @@ class UNetEngine:
         # the epilogue-bound convs 13-120 % slower while the norm's own statistics pass costs only ~3 us of its 24 us
         # (its apply pass is instruction-issue bound) — the step is 1.4 ms slower with it.
         self._gn_stats = os.environ.get("ADM_GN_STATS", "0") == "1"
+        # the data gradients fed to the GroupNorm backward kernels are consumed only there: let the kernel use them as
+        # scratch (it stores the pre-activation gradient in place between its passes).  ADM_GN_DVREUSE=0 for A/B timing.
+        self._dy_scratch = os.environ.get("ADM_GN_DVREUSE", "1") != "0"
+        # GroupNorm + SiLU (+ dropout) as a PROLOGUE of the 3x3 conv that consumes it (adm_conv_fprop_gn) wherever the image
+        # tiles into halo boxes and no resample sits between norm and conv: the norm kernel then only computes statistics.
+        # Bit-identical to the two-kernel path and tested, but OFF by default: measured on B200 it is break-even at best
+        # (profiles/r03_conv_gn_prologue.txt — the transform of a halo chunk is not fully hidden under its nine MMAs, and in
+        # training it also hashes the dropout masks and writes out the tensor the weight gradients need).
+        # ADM_CONV_GN=1: in inference (sampler) only, 2: also in training.
+        self._conv_gn = int(os.environ.get("ADM_CONV_GN", "0"))
         self._side_pending = []
         # device-resident step counter mixed into every dropout seed (fresh masks per CUDA-graph replay); owned by the
         # training step (adm_b200.train.TrainStep) and passed to the GroupNorm kernels per call
@@ -340,18 +350,43 @@ class UNetEngine:
         mode = 1 if blk.down else (2 if blk.up else 0)
         c.mode = mode
         c.drop_p = float(blk.dropout) if training else 0.0
-        c.sums0, c.a0 = self._gn(x1, st1, x2, st2, blk.norm0, _groups(cin), act=True, resample=mode)
-        # after the fused concat-GroupNorm the conv sees ONE tensor a0 with cin channels
-        c.h0, st_h0 = self._conv_stats(c.a0, self.conv_w(blk.conv0), bias=blk.conv0.bias)
-        c.sums1, c.a1 = self._gn(c.h0, st_h0, None, None, blk.norm1, _groups(cout), params=params, act=True,
-                                 drop_p=c.drop_p, seed=seed, seed_counter=self.seed_counter)
+        n_, hh, ww, _ = x1.shape
+        want_act = save is not None  # the activated tensors are only needed by the weight gradients
+        use_pro = self._conv_gn == 2 or (self._conv_gn == 1 and not want_act)
+        fuse0 = use_pro and mode == 0 and ops.conv_gn_ok(hh, ww) and not (cin1 % 8 or cin2 % 8) \
+            and (x2 is None or cin1 % 64 == 0)
+        if fuse0:  # conv0(silu(norm0(x))) in one kernel: statistics here, normalisation in the conv's prologue
+            c.sums0, _ = ops.gn_forward(x1, x2, blk.norm0.weight, blk.norm0.bias, _groups(cin), blk.norm0.eps, act=True,
+                                        apply=False)
+            # (cin1 % 64 == 0: the packed weights of the concatenated input and of the two sources are the same buffer)
+            c.h0, c.a0 = ops.conv_fprop_gn(x1, self.conv_w(blk.conv0), c.sums0, x2=x2, bias=blk.conv0.bias, act=True,
+                                           want_act=want_act)
+            st_h0 = None
+        else:
+            c.sums0, c.a0 = self._gn(x1, st1, x2, st2, blk.norm0, _groups(cin), act=True, resample=mode)
+            # after the fused concat-GroupNorm the conv sees ONE tensor a0 with cin channels
+            c.h0, st_h0 = self._conv_stats(c.a0, self.conv_w(blk.conv0), bias=blk.conv0.bias)
+        ho, wo = c.h0.shape[1], c.h0.shape[2]
+        fuse1 = use_pro and ops.conv_gn_ok(ho, wo) and cout % 8 == 0
+        if fuse1:
+            c.sums1, c.a1 = ops.gn_forward(c.h0, None, blk.norm1.weight, blk.norm1.bias, _groups(cout), blk.norm1.eps,
+                                           params=params, act=True, apply=False)
+        else:
+            c.sums1, c.a1 = self._gn(c.h0, st_h0, None, None, blk.norm1, _groups(cout), params=params, act=True,
+                                     drop_p=c.drop_p, seed=seed, seed_counter=self.seed_counter)
         if blk.skip is not None and blk.skip.weight is not None:
             res = ops.conv_fprop(x1, self.conv_w(blk.skip, cin1, cin2), x2=x2, bias=blk.skip.bias)
         elif mode:
             res = ops.resample(x1, mode)
         else:
             res = x1
-        c.h1, st_out = self._conv_stats(c.a1, self.conv_w(blk.conv1), bias=blk.conv1.bias, residual=res)
+        if fuse1:  # conv1(dropout(silu(norm1(h0) * (1 + scale) + shift))) + residual in one kernel
+            c.h1, c.a1 = ops.conv_fprop_gn(c.h0, self.conv_w(blk.conv1), c.sums1, bias=blk.conv1.bias, residual=res,
+                                           act=True, drop_p=c.drop_p, seed=seed, seed_counter=self.seed_counter,
+                                           want_act=want_act)
+            st_out = None
+        else:
+            c.h1, st_out = self._conv_stats(c.a1, self.conv_w(blk.conv1), bias=blk.conv1.bias, residual=res)
         out = c.h1
         if blk.num_heads:
             c.sums2, c.a2 = self._gn(c.h1, st_out, None, None, blk.norm2, _groups(cout), act=False)
@@ -453,7 +488,7 @@ class UNetEngine:
         dh0, _ = ops.gn_bwd(da1, c.h0, None, c.sums1, blk.norm1.weight, blk.norm1.bias, _groups(cout),
                             params=c.params, act=True, drop_p=c.drop_p, seed=c.seed, seed_counter=self.seed_counter,
                             dgamma=self._grad(blk.norm1.weight), dbeta=self._grad(blk.norm1.bias), dparams=dparams,
-                            dbias1=self._grad(blk.conv0.bias))
+                            dbias1=self._grad(blk.conv0.bias), dy_scratch=self._dy_scratch)
         # h0 = conv0(a0) + b0
         self._conv_param_grads(blk.conv0, dh0, c.a0, bias_done=True)
         da0 = self._dgrad(dh0, blk.conv0, self.conv_w(blk.conv0))
@@ -467,7 +502,8 @@ class UNetEngine:
         s1 = input_sinks[1] if input_sinks and len(input_sinks) > 1 else None
         return ops.gn_bwd(da0, c.x1, c.x2, c.sums0, blk.norm0.weight, blk.norm0.bias, _groups(cin),
                           act=True, resample=c.mode, dgamma=self._grad(blk.norm0.weight),
-                          dbeta=self._grad(blk.norm0.bias), add=add, add_mode=add_mode, dbias1=s0, dbias1b=s1)
+                          dbeta=self._grad(blk.norm0.bias), add=add, add_mode=add_mode, dbias1=s0, dbias1b=s1,
+                          dy_scratch=self._dy_scratch)
 
     # ------------------------------------------------------------------------------------------ embedding MLP
     def embed_fwd(self, c_noise, aug, save):
@@ -668,7 +704,8 @@ class UNetEngine:
             sinks = self.bias_sinks(items[pos - 1].blk)
             dh, _ = ops.gn_bwd(da, o.x, None, o.sums, o.norm.weight, o.norm.bias, _groups(o.x.shape[-1]),
                                act=True, dgamma=self._grad(o.norm.weight), dbeta=self._grad(o.norm.bias),
-                               dbias1=sinks[0], dbias1b=sinks[1] if len(sinks) > 1 else None)
+                               dbias1=sinks[0], dbias1b=sinks[1] if len(sinks) > 1 else None,
+                               dy_scratch=self._dy_scratch)
             self._notify(o.conv, o.norm)
             si = 0  # forward pops skips from the end, so walking the decoder backwards meets skips[0], skips[1], ...
             while not hasattr(items[pos - 1], "seq"):

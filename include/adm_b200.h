@@ -92,6 +92,19 @@ int adm_conv_fprop_stats(const void* x1, int c1, long long ld1, const void* x2, 
                          const float* bias, const void* residual, long long ldr, float alpha, float* stats,
                          void* stream);
 int adm_conv_stats_slots(int h, int w);
+/* conv3x3 with the GroupNorm(+ adaptive scale/shift) + SiLU (+ dropout) PROLOGUE fused in (north_star; UNetBlock.forward,
+ * unet/uncond_unet.py:191 `conv0(silu(norm0(x)))` and :196-200 `conv1(dropout(silu(addcmul(shift, norm1(x), scale+1))))`):
+ * the conv reads the RAW tensor x1 (| x2); four extra warps apply y = dropout(silu(x*A[n,c] + B[n,c])) to every halo
+ * tile in shared memory, once per 64-channel chunk, between the TMA load and the tcgen05 MMAs, so the normalised tensor
+ * is never read back from HBM.  coef = the norm's table [n][c1+c2]{A, B, mean, rstd} (adm_gn_stats / adm_gn_forward with
+ * out == NULL); seed / seed_counter / drop_p as adm_gn_apply (the backward regenerates the same masks); a_out (optional,
+ * bf16 [n][h][w][ld_a]) receives the activated tensor once — the operand adm_conv_wgrad needs in training.
+ * Images must tile into 8 x 16 pixel boxes (adm_conv_gn_ok).  Output bf16.                                     */
+int adm_conv_fprop_gn(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int h, int w,
+                      const void* wpk, int nout, void* out, long long ldc, const float* bias, const void* residual,
+                      long long ldr, const float* coef, int act, float drop_p, unsigned long long seed,
+                      const unsigned long long* seed_counter, void* a_out, long long ld_a, void* stream);
+int adm_conv_gn_ok(int h, int w);
 /* data gradient: dx[pix][0:n_valid] = alpha * conv^T(dy) + residual, reading the SAME packed weights through a
  * (Cin, tap, Cout) view with reversed taps; kpad = padded input channels of the forward conv.              */
 int adm_conv_dgrad(const void* dy, int cout, long long ld_dy, int n, int h, int w, const void* wpk, int kpad,
@@ -175,7 +188,9 @@ int adm_gn_bwd(const void* dy, long long ldy, const void* x1, int c1, long long 
                unsigned long long seed, const unsigned long long* seed_counter, int resample, float* work,
                float* bcoef, float* dgamma, float* dbeta, float* dparams, long long ld_dparams, const void* add,
                long long ldadd, int add_mode, void* dx1, long long ldx1, void* dx2, long long ldx2, float* dbias1,
-               float* dbias1b, void* stream);
+               float* dbias1b, int dy_scratch, void* stream);
+/*   dy_scratch != 0: the caller is done with dy — the kernel may overwrite it (it keeps the gradient at the
+ *   pre-activation there between its two passes instead of recomputing SiLU' and the dropout mask).          */
 /*   dbias1, dbias1b (optional, fp32 [c1]): += column sums of dx1 — the bias gradient of the conv(s) that produced x1
  *   (conv1 and the 1x1 skip of a UNetBlock share it; unet/uncond_unet.py:111-112 backward), so no separate pass
  *   over dx1 is needed.

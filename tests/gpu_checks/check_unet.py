@@ -111,6 +111,28 @@ def groupnorm():
         ok &= _report("dropout bwd mask", dx_a, dx_b, 2e-2)
     # the two-kernel entry points stay available (and agree with the fused call)
     x = torch.randn(16, 8, 8, 192, device="cuda").bfloat16()
+    # dy_scratch: the kernel keeps the pre-activation gradient in dy's place between its passes (bf16) instead of
+    # recomputing SiLU' and the dropout mask — same dx up to one extra bf16 rounding, and dy really is overwritten
+    for (n, hw, c) in [(16, 16, 384), (128, 8, 192)]:
+        x = (torch.randn(n, hw, hw, c, device="cuda") * 1.5 + 0.3).bfloat16()
+        dy = torch.randn(n, hw, hw, c, device="cuda").bfloat16()
+        add = torch.randn(n, hw, hw, c, device="cuda").bfloat16()
+        gamma = 1 + 0.1 * torch.randn(c, device="cuda")
+        beta = 0.1 * torch.randn(c, device="cuda")
+        params = 0.3 * torch.randn(n, 2 * c, device="cuda")
+        coef, _ = ops.gn_forward(x, None, gamma, beta, 32, params=params, act=True, drop_p=0.1, seed=5)
+        outs = []
+        for scratch in (False, True):
+            dyc = dy.clone()
+            dg, db = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+            dp = torch.zeros(n, 2 * c, device="cuda")
+            dx, _ = ops.gn_bwd(dyc, x, None, coef, gamma, beta, 32, params=params, act=True, drop_p=0.1, seed=5, dgamma=dg,
+                               dbeta=db, dparams=dp, add=add, add_mode=0, dy_scratch=scratch)
+            outs.append((dx, dg, db, dp, dyc))
+        ok &= _report(f"gn_bwd dy_scratch dx n{n}", outs[1][0], outs[0][0], 6e-3)
+        ok &= _report(f"gn_bwd dy_scratch dgamma n{n}", outs[1][1], outs[0][1], 1e-5)
+        ok &= _report(f"gn_bwd dy_scratch dparams n{n}", outs[1][3], outs[0][3], 1e-5)
+        ok &= bool(torch.equal(outs[0][4], dy)) and not bool(torch.equal(outs[1][4], dy))
     sums_f, y_f = ops.gn_forward(x, None, gamma, beta, 32, act=True)
     sums_s = ops.gn_stats(x, None, gamma, beta, 32)
     y_s = ops.gn_apply(x, None, sums_s, act=True)
@@ -168,6 +190,57 @@ def gn_stats_epilogue():
     coef_s, ys = ops.gn_forward_stats(ya, sa, yb, sb, gamma, beta, 32, 1e-5, act=True)
     v = F.silu(F.group_norm(torch.cat([ya, yb], -1).float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-5))
     ok &= _report("concat (384 | 192) from two producers vs F.group_norm", ys, v.permute(0, 2, 3, 1), 6e-3)
+    return ok
+
+
+@case
+def conv_gn_prologue():
+    """adm_conv_fprop_gn (GroupNorm + adaptive scale/shift + SiLU + dropout applied to the halo tiles in shared memory inside
+    the conv) against the two-kernel path gn_apply -> conv_fprop: the activated tensor it writes out and the conv result
+    must be BIT-identical (same formula, same rounding, same MMA order); plus fp32 torch as the outer reference."""
+    import torch
+    import torch.nn.functional as F
+    from adm_b200 import ops
+    torch.manual_seed(12)
+    ok = True
+    for (n, h, w, c1, c2, cout, drop, with_res, act) in [(4, 16, 16, 128, 0, 192, 0.0, False, True),
+                                                         (3, 32, 32, 64, 0, 64, 0.1, True, True),
+                                                         (5, 16, 16, 128, 64, 384, 0.0, False, True),
+                                                         (2, 32, 16, 192, 192, 96, 0.1, True, True),
+                                                         (6, 16, 8, 96, 0, 192, 0.0, False, True),
+                                                         (130, 16, 16, 64, 0, 64, 0.1, False, False)]:
+        c = c1 + c2
+        x1 = (torch.randn(n, h, w, c1, device="cuda") * 1.3 + 0.2).bfloat16()
+        x2 = (torch.randn(n, h, w, c2, device="cuda") * 0.8 - 0.1).bfloat16() if c2 else None
+        wt = torch.randn(cout, c, 3, 3, device="cuda") / (3 * c ** 0.5)
+        bias = 0.1 * torch.randn(cout, device="cuda")
+        res = torch.randn(n, h, w, cout, device="cuda").bfloat16() if with_res else None
+        gamma = 1 + 0.1 * torch.randn(c, device="cuda")
+        beta = 0.1 * torch.randn(c, device="cuda")
+        params = 0.3 * torch.randn(n, 2 * c, device="cuda")
+        g = min(32, c // 4)
+        wpk = ops.pack_conv_weight(wt, c1, c2) if c2 else ops.pack_conv_weight(wt)
+        coef, _ = ops.gn_forward(x1, x2, gamma, beta, g, 1e-5, params=params, act=act, apply=False)
+        a_ref = ops.gn_apply(x1, x2, coef, act=act, drop_p=drop, seed=99)
+        wpk1 = ops.pack_conv_weight(wt)  # single concatenated source
+        y_ref = ops.conv_fprop(a_ref, wpk1, bias=bias, residual=res)
+        y, a = ops.conv_fprop_gn(x1, wpk, coef, x2=x2, bias=bias, residual=res, act=act, drop_p=drop, seed=99)
+        tag = f"n{n} {h}x{w} {c1}+{c2}->{cout} drop{drop} act{int(act)}"
+        eq_a, eq_y = bool(torch.equal(a, a_ref)), bool(torch.equal(y, y_ref))
+        print(f"  {tag}: activated tensor bit-equal {eq_a}, conv output bit-equal {eq_y}", flush=True)
+        ok &= eq_a and eq_y
+        y2, none = ops.conv_fprop_gn(x1, wpk, coef, x2=x2, bias=bias, residual=res, act=act, drop_p=drop, seed=99,
+                                     want_act=False)
+        ok &= none is None and bool(torch.equal(y2, y))
+        if drop == 0.0:
+            xc = torch.cat([x1, x2], -1) if c2 else x1
+            v = F.group_norm(xc.float().permute(0, 3, 1, 2), g, gamma, beta, 1e-5)
+            v = v * (1 + params[:, :c, None, None]) + params[:, c:, None, None]
+            v = F.silu(v) if act else v
+            yr = F.conv2d(v, wt, bias, padding=1)
+            if res is not None:
+                yr = yr + res.float().permute(0, 3, 1, 2)
+            ok &= _report(f"  {tag} vs fp32 torch", y, yr.permute(0, 2, 3, 1), 1.5e-2)
     return ok
 
 

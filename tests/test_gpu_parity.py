@@ -53,7 +53,7 @@ def test_training_mode_dropout_masks_vs_oracle():
     assert CU.CASES["unet_dropout_on"]()
 
 
-@pytest.mark.parametrize("case", ["groupnorm", "gn_stats_epilogue", "small_ops", "attention", "spatial_att"])
+@pytest.mark.parametrize("case", ["groupnorm", "gn_stats_epilogue", "conv_gn_prologue", "small_ops", "attention", "spatial_att"])
 def test_norm_attention_kernels(case):
     assert CU.CASES[case]()
 
