@@ -67,6 +67,7 @@ struct AttnParams {
 // ------------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ AttnParams p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + AT_RING);
@@ -98,6 +99,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
 
     if (warp == 0) {
         // =========================================================== TMA producer
@@ -274,6 +276,7 @@ constexpr int BW_DK = 256, BW_DV = 320, BW_DQ = 384;
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ AttnParams p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + AT_RING);
@@ -312,6 +315,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
 
     if (warp == 0) {
         // =========================================================== TMA producer
@@ -621,7 +625,7 @@ extern "C" int adm_attn_fwd_fused(const void* qkv, int batch, int n_pix, int hea
         attr_set = true;
     }
     const int grid = p.units < num_sms() ? p.units : num_sms();
-    attn_fwd_kernel<<<grid, AT_THREADS, AT_SMEM_TOTAL, static_cast<cudaStream_t>(stream)>>>(mq, p);
+    launch_k(attn_fwd_kernel, dim3(grid), dim3(AT_THREADS), AT_SMEM_TOTAL, static_cast<cudaStream_t>(stream), 0, mq, p);
     ADM_CHECK_LAUNCH("attn_fwd_fused");
     return 0;
 }
@@ -648,7 +652,7 @@ extern "C" int adm_attn_bwd_fused(const void* da, const void* qkv, const void* o
         attr_set = true;
     }
     const int grid = p.units < num_sms() ? p.units : num_sms();
-    attn_bwd_kernel<<<grid, AT_THREADS, AT_SMEM_TOTAL, static_cast<cudaStream_t>(stream)>>>(mq, mdo, p);
+    launch_k(attn_bwd_kernel, dim3(grid), dim3(AT_THREADS), AT_SMEM_TOTAL, static_cast<cudaStream_t>(stream), 0, mq, mdo, p);
     ADM_CHECK_LAUNCH("attn_bwd_fused");
     return 0;
 }

@@ -590,6 +590,8 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(const __nv_bfloat1
 // out[c] += sum over rows of x[row][c]; x bf16 [rows][ld].  grid (chunks).
 __global__ void __launch_bounds__(256) col_sums_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
                                                        long long rows, int C_total, float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];  // [blockDim][8]
     const int col0 = blockIdx.y * 2048;
     const int C = min(2048, C_total - col0);
@@ -624,6 +626,8 @@ __global__ void __launch_bounds__(256) add_bf16_kernel(const __nv_bfloat16* __re
                                                        const __nv_bfloat16* __restrict__ c, long long ldc,
                                                        __nv_bfloat16* __restrict__ out, long long ldo, long long rows,
                                                        int C) {
+    pdl_trigger();
+    pdl_wait();
     const int V = C >> 3;
     const long long total = rows * V;
     for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
@@ -726,6 +730,8 @@ __global__ void __launch_bounds__(512, 1) gn_fwd_fused_kernel(
     const float* __restrict__ params, long long ldp, float4* __restrict__ coef, int act, float drop_p,
     unsigned long long seed, int resample, __nv_bfloat16* __restrict__ out, long long ldo,
     const unsigned long long* __restrict__ seed_dev) {
+    pdl_trigger();
+    pdl_wait();
     cg::cluster_group cluster = cg::this_cluster();
     const int K = static_cast<int>(cluster.num_blocks()), r = static_cast<int>(cluster.block_rank());
     if (seed_dev != nullptr) seed += *seed_dev * 0x9E3779B97F4A7C15ull;
@@ -922,6 +928,8 @@ __global__ void __launch_bounds__(512, 1) gn_bwd_fused_kernel(
     const __nv_bfloat16* __restrict__ add, long long ldadd, int add_mode, __nv_bfloat16* __restrict__ dx1,
     long long ldx1, __nv_bfloat16* __restrict__ dx2, long long ldx2, float* __restrict__ dbias1,
     float* __restrict__ dbias1b, const unsigned long long* __restrict__ seed_dev, int dy_scratch) {
+    pdl_trigger();
+    pdl_wait();
     cg::cluster_group cluster = cg::this_cluster();
     const int K = static_cast<int>(cluster.num_blocks()), r = static_cast<int>(cluster.block_rank());
     if (seed_dev != nullptr) seed += *seed_dev * 0x9E3779B97F4A7C15ull;
@@ -1245,13 +1253,19 @@ static cudaError_t launch_cluster(void (*kern)(KArgs...), int grid, int block, s
     cfg.blockDim = dim3(block);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = k;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    int na = 1;
+    if (pdl_enabled()) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
@@ -1434,8 +1448,8 @@ int adm_col_sums(const void* x, long long ld, long long rows, int c, float* out,
     ADM_REQUIRE(chunks == 1 || last % 8 == 0, "col_sums: bad width");
     const int tpv = threads / ((chunks > 1 ? 2048 : last) / 8);
     dim3 grid(grid_for(rows, tpv > 0 ? tpv : 1, chunks), chunks);
-    col_sums_kernel<<<grid, threads, threads * 8 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const bf16*>(x), ld, rows, c, out);
+    launch_k(col_sums_kernel, grid, dim3(threads), threads * 8 * sizeof(float), static_cast<cudaStream_t>(stream), 0,
+             static_cast<const bf16*>(x), ld, rows, c, out);
     ADM_CHECK_LAUNCH("col_sums");
     return 0;
 }
@@ -1443,9 +1457,9 @@ int adm_col_sums(const void* x, long long ld, long long rows, int c, float* out,
 int adm_add_bf16(const void* a, long long lda, const void* b, long long ldb, const void* c, long long ldc, void* out,
                  long long ldo, long long rows, int ch, void* stream) {
     ADM_REQUIRE(ch > 0 && ch % 8 == 0, "add_bf16: channels must be a multiple of 8");
-    add_bf16_kernel<<<grid_for(rows * (ch / 8), 256, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const bf16*>(a), lda, static_cast<const bf16*>(b), ldb, static_cast<const bf16*>(c), ldc,
-        static_cast<bf16*>(out), ldo, rows, ch);
+    launch_k(add_bf16_kernel, dim3(grid_for(rows * (ch / 8), 256, 1)), dim3(256), 0, static_cast<cudaStream_t>(stream), 0,
+             static_cast<const bf16*>(a), lda, static_cast<const bf16*>(b), ldb, static_cast<const bf16*>(c), ldc,
+             static_cast<bf16*>(out), ldo, rows, ch);
     ADM_CHECK_LAUNCH("add_bf16");
     return 0;
 }

@@ -10,6 +10,7 @@
 // Tile = 128 (M) x BN (N, runtime, multiple of 16, <= 256) x 64 (K per stage, bf16 = one 128 B swizzle row).
 #pragma once
 #include "ptx.cuh"
+#include "adm_internal.h"
 #ifdef ADM_GEMM_TIMING
 #include <stdio.h>
 #endif
@@ -392,6 +393,7 @@ template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stage_bytes = GEMM_A_STAGE + p.bn * 128;
@@ -427,6 +429,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();  // everything above touched only this kernel's own state; the predecessor's results are visible from here on
 
     const int num_tiles = p.batches * p.splits * p.m_tiles * p.n_tiles;
 
@@ -779,6 +782,7 @@ template <bool PRO>
 __global__ void __launch_bounds__(PRO ? GEMM_PRO_THREADS : GEMM_THREADS, 1)
 tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_bytes = p.bn * 128;
@@ -823,6 +827,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();  // everything above touched only this kernel's own state; the predecessor's results are visible from here on
 
     const int num_tiles = p.m_tiles * p.n_tiles;
 
@@ -1025,6 +1030,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 tc_wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ GemmParams p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int halo_w = p.bw + 2;
@@ -1062,6 +1068,7 @@ tc_wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();  // everything above touched only this kernel's own state; the predecessor's results are visible from here on
 
     // tile = (sp * m_tiles + mt) * n_tiles + nt : CTAs running together share a pixel range (split) — its dY / X boxes
     // stay L2-resident.  (A stream-K division of the (tile, k) space balanced the SMs but was 10 % slower: neighbouring
