@@ -198,6 +198,64 @@ static int launch_halo(const CUtensorMap& a, const CUtensorMap& a2, const CUtens
     return p.pro_coef != nullptr ? launch_halo_t<true>(a, a2, b, p, stream) : launch_halo_t<false>(a, a2, b, p, stream);
 }
 
+// Cluster split-K conv launch (tc_conv_splitk_kernel): one tile per CTA, clusters of p.ksplit CTAs along K.
+static int launch_splitk(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const GemmParams& p,
+                         cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             GEMM_SMEM_TOTAL);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return ADM_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    const int grid = p.m_tiles * p.n_tiles * p.ksplit;
+    cudaError_t e = launch_k(tc_conv_splitk_kernel, dim3(grid), dim3(GEMM_THREADS), GEMM_SMEM_TOTAL, stream, p.ksplit, a, a2, b, p);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("tc_conv_splitk launch: %s", cudaGetErrorString(e));
+        return ADM_ERR_CUDA;
+    }
+    count_launch();
+    return 0;
+}
+
+// Under-filled convs (few pixel tiles, long K): pick (N tile, K split) minimising the critical path
+// ceil(k_total / ks) x (128 + bn) operand rows + reduction, subject to tiles x ks <= SMs.  Returns ks (1 = plain kernel).
+// ADM_CONV_SPLITK=0 disables (A/B timing).
+static int pick_splitk(int n, int multiple, int m_tiles, int k_total, int* bn_out) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("ADM_CONV_SPLITK"); on = (e != nullptr && e[0] == '0') ? 0 : 1; }
+    if (!on) return 1;
+    const int n_pad = (n + multiple - 1) / multiple * multiple;
+    if (const char* f = getenv("ADM_SPLITK_FORCE")) {  // tests: "bn,ks" forces a tile width and split (read per call)
+        int fb = 0, fk = 0;
+        if (sscanf(f, "%d,%d", &fb, &fk) == 2 && fb >= multiple && fb % multiple == 0 && n_pad % fb == 0 && fk >= 1 && fk <= 8 &&
+            m_tiles * (n_pad / fb) * fk <= num_sms() && (fk - 1) * ((k_total + fk - 1) / fk) < k_total) {
+            if (fk > 1) *bn_out = fb;
+            return fk;
+        }
+    }
+    const int sms = num_sms();
+    long long best = -1;
+    int best_bn = 0, best_ks = 1;
+    for (int bn = 256 / multiple * multiple; bn >= multiple; bn -= multiple) {
+        if (n_pad % bn) continue;
+        const int tiles = m_tiles * (n_pad / bn);
+        for (int ks = 1; ks <= 4; ++ks) {
+            if (tiles * ks > sms || ks * 6 > k_total) continue;
+            const int k_per = (k_total + ks - 1) / ks;
+            if ((ks - 1) * k_per >= k_total) continue;  // an empty last split
+            const long long cost = 1LL * k_per * 8 * (128 + bn) / 3 + 8LL * bn + 500 + (ks > 1 ? 1500 + 12LL * bn * (ks - 1) : 0);
+            if (best < 0 || cost < best) { best = cost; best_bn = bn; best_ks = ks; }
+        }
+    }
+    if (best_ks > 1) *bn_out = best_bn;
+    return best_ks;
+}
+
 static int launch_wgrad_rows(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& b2, const GemmParams& p,
                              cudaStream_t stream) {
     static bool attr_set = false;
@@ -431,6 +489,12 @@ static int conv_fprop_impl(const void* x1, int c1, long long ld1, const void* x2
     p.cchunks = p.cchunks1 + (x2 ? pad64(c2) / 64 : 0);
     p.k_total = p.k_iters = ntaps * p.cchunks;
     p.bn = pick_bn_cost(nout, 16, p.m_tiles, p.k_total);
+    p.ksplit = 1;
+    if (!halo && stats == nullptr && pro == nullptr && out_mode != OUT_F32_ATOMIC) {
+        int bn_s = p.bn;
+        const int ks = pick_splitk(nout, 16, p.m_tiles, p.k_total, &bn_s);
+        if (ks > 1) { p.ksplit = ks; p.bn = bn_s; p.k_iters = (p.k_total + ks - 1) / ks; }
+    }
     p.n_tiles = (nout + p.bn - 1) / p.bn;
     p.M = n * h * w; p.N = nout;
     p.C = out; p.ldc = ldc; p.bias = bias; p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = ldr;
@@ -463,12 +527,13 @@ static int conv_fprop_impl(const void* x1, int c1, long long ld1, const void* x2
     const long long bs[1] = {kpad};
     // CTA pairs: 256-pixel tiles, each CTA loading half of the weight rows (box BN/2) — when there are at least two
     // pixel tiles and the output mode is a plain store.
-    const bool pair = !halo && pair_enabled() && p.m_tiles >= 2 && p.bn % 16 == 0 && out_mode != OUT_F32_ATOMIC &&
+    const bool pair = !halo && p.ksplit == 1 && pair_enabled() && p.m_tiles >= 2 && p.bn % 16 == 0 && out_mode != OUT_F32_ATOMIC &&
                       stats == nullptr && pro == nullptr;
     const int bb[2] = {64, pair ? p.bn / 2 : p.bn};
     if (int e = encode_map(&mb, wpk, 2, bd, bs, bb)) return e;
     if (pair) return launch_pair(ma, ma2, mb, p, static_cast<cudaStream_t>(stream));
     if (halo) return launch_halo(ma, ma2, mb, p, static_cast<cudaStream_t>(stream));
+    if (p.ksplit > 1) return launch_splitk(ma, ma2, mb, p, static_cast<cudaStream_t>(stream));
     return launch<GEMM_CONV>(ma, ma2, mb, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -492,6 +557,12 @@ int adm_conv_dgrad(const void* dy, int cout, long long ld_dy, int n, int h, int 
     p.cchunks1 = p.cchunks = pad64(cout) / 64;
     p.k_total = p.k_iters = ntaps * p.cchunks;
     p.bn = pick_bn_cost(kpad, 64, p.m_tiles, p.k_total);
+    p.ksplit = 1;
+    if (!halo) {
+        int bn_s = p.bn;
+        const int ks = pick_splitk(kpad, 64, p.m_tiles, p.k_total, &bn_s);
+        if (ks > 1) { p.ksplit = ks; p.bn = bn_s; p.k_iters = (p.k_total + ks - 1) / ks; }
+    }
     p.n_tiles = kpad / p.bn;
     p.b_mn = 1;
     p.M = n * h * w; p.N = n_valid;
@@ -504,6 +575,7 @@ int adm_conv_dgrad(const void* dy, int cout, long long ld_dy, int n, int h, int 
     const int bb[3] = {64, 1, 64};
     if (int e = encode_map(&mb, wpk, 3, bd, bs, bb)) return e;
     if (halo) return launch_halo(ma, ma, mb, p, static_cast<cudaStream_t>(stream));
+    if (p.ksplit > 1) return launch_splitk(ma, ma, mb, p, static_cast<cudaStream_t>(stream));
     return launch<GEMM_CONV>(ma, ma, mb, p, static_cast<cudaStream_t>(stream));
 }
 

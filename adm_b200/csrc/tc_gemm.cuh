@@ -46,6 +46,7 @@ struct GemmParams {
     int m_tiles, n_tiles, batches, splits;
     int k_iters;  // K iterations (of 64) per split
     int k_total;  // total K iterations (last split may be shorter)
+    int ksplit;   // tc_conv_splitk_kernel: CTAs of a cluster that split the K range of one tile (reduced through DSMEM)
     int bn;       // N tile
     int a_mn, b_mn;
     int M, N;  // valid rows (per batch) / cols
@@ -551,7 +552,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #ifdef ADM_GEMM_TIMING
                     const long long c1 = clock64();
 #endif
-                    const uint32_t sa16 = smem_u32(smem + stage * stage_bytes) >> 4;
+                    const uint32_t sa16 = (smem_u32(smem + stage * stage_bytes) & 0x3FFFFu) >> 4;
                     const uint64_t da = da0 + sa16, db = db0 + (sa16 + (GEMM_A_STAGE >> 4));
 #pragma unroll
                     for (int k = 0; k < GEMM_BLOCK_K / 16; ++k)
@@ -586,6 +587,207 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ cluster split-K conv
+// Implicit-GEMM conv (fprop / dgrad, 3x3 or 1x1) for problems with too few 128 x bn output tiles to fill the GPU (the 4x4
+// level: 2048 pixels x 384 channels = 48 tiles of 128 x 128, each with a K loop of 54-108 iterations).  A thread-block
+// cluster of ksplit CTAs shares ONE output tile: CTA r multiplies K iterations [r * k_iters, (r + 1) * k_iters) into its own
+// TMEM accumulator; the non-leaders then park their fp32 partial tiles in their (now idle) operand ring, signal the leader's
+// mbarrier across the cluster, and the leader adds them through distributed shared memory (ld.shared::cluster) into its
+// accumulator before the ordinary epilogue.  One tile per CTA (grid = tiles x ksplit); roles as in tc_gemm_kernel.
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t caddr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(caddr));
+    return v;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t caddr) {  // release at cluster scope
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int code) {  // acquire at cluster scope
+    const long long t0 = clock64();
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (!ok && clock64() - t0 > 8000000000LL) {
+            g_device_error = code;
+            __threadfence_system();
+            asm volatile("trap;");
+        }
+    }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+tc_conv_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                      const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
+    pdl_trigger();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_bytes = GEMM_A_STAGE + p.bn * 128;
+    int num_stages = GEMM_SMEM_RING / stage_bytes;
+    if (num_stages > GEMM_MAX_STAGES) num_stages = GEMM_MAX_STAGES;
+
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + GEMM_SMEM_RING);
+    uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
+    uint64_t* tfull_bar = empty_bar + GEMM_MAX_STAGES;
+    uint64_t* peers_bar = tfull_bar + 1;  // leader: the non-leaders' partial tiles are parked
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(peers_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int rank = static_cast<int>(cluster_ctarank());
+    const int tile = blockIdx.x / p.ksplit;
+    const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+    const int k_begin = rank * p.k_iters;
+    const int k_end = min(p.k_total, k_begin + p.k_iters);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmA2);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < num_stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(tfull_bar, 1);
+        mbar_init(peers_bar, (p.ksplit - 1) * GEMM_EPI_WARPS);
+        fence_barrier_init();
+        fence_proxy_async_smem();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 256);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the leader's peers_bar is initialised before any remote arrive
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
+
+    int n0, h0, w0;
+    decode_pix(p, mt, n0, h0, w0);
+    if (warp == 0) {
+        // =========================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int tap = k_begin / p.cchunks, kc = k_begin % p.cchunks;
+            for (int ki = k_begin; ki < k_end; ++ki) {
+                mbar_wait(&empty_bar[stage], phase ^ 1, 41);
+                uint8_t* sa = smem + stage * stage_bytes;
+                uint8_t* sb = sa + GEMM_A_STAGE;
+                mbar_expect_tx(&full_bar[stage], stage_bytes);
+                int dh = 0, dw = 0;
+                if (p.ntaps == 9) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+                if (kc < p.cchunks1)
+                    tma_load_4d(sa, &tmA, &full_bar[stage], kc * 64, w0 + dw, h0 + dh, n0);
+                else
+                    tma_load_4d(sa, &tmA2, &full_bar[stage], (kc - p.cchunks1) * 64, w0 + dw, h0 + dh, n0);
+                if (!p.b_mn) {
+                    tma_load_2d(sb, &tmB, &full_bar[stage], ki * 64, nt * p.bn);
+                } else {
+                    for (int c = 0; c * 64 < p.bn; ++c)
+                        tma_load_3d(sb + c * 8192, &tmB, &full_bar[stage], nt * p.bn + c * 64, p.ntaps - 1 - tap, kc * 64);
+                }
+                if (++kc == p.cchunks) { kc = 0; ++tap; }
+                if (++stage == num_stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================================================== UMMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, p.bn, 0, p.b_mn);
+            const uint32_t b_lbo = p.b_mn ? 8192u : 16u;
+            const uint32_t b_kstep = (p.b_mn ? 2048u : 32u) >> 4;
+            const uint64_t da0 = make_smem_desc(0, 16u, 1024), db0 = make_smem_desc(0, b_lbo, 1024);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int ki = k_begin; ki < k_end; ++ki) {
+                mbar_wait(&full_bar[stage], phase, 43);
+                tc_fence_after();
+                // In a non-leader CTA of a cluster the shared-window address carries bits above the 14-bit descriptor field:
+                // unmasked they spill into the leading-byte-offset field (which only MN-major multi-chunk B reads).
+                const uint32_t sa16 = (smem_u32(smem + stage * stage_bytes) & 0x3FFFFu) >> 4;
+                const uint64_t da = da0 + sa16, db = db0 + (sa16 + (GEMM_A_STAGE >> 4));
+#pragma unroll
+                for (int k = 0; k < GEMM_BLOCK_K / 16; ++k)
+                    umma_bf16(tmem_base, da + 2 * k, db + k * b_kstep, idesc, (ki > k_begin || k > 0) ? 1u : 0u);
+                umma_commit(&empty_bar[stage]);
+                if (++stage == num_stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tfull_bar);
+        }
+    } else {
+        // =========================================================== epilogue (4 warps, one TMEM lane quadrant each)
+        const int quad = warp & 3;
+        const int m = quad * 32 + lane;
+        const int wi = m % p.bw, hi = (m / p.bw) % p.bh, ni = m / (p.bw * p.bh);
+        const long long pix = (static_cast<long long>(n0 + ni) * p.H + (h0 + hi)) * p.W + (w0 + wi);
+        const bool row_ok = pix < p.M;
+        const int col_base = nt * p.bn;
+        float* sbias = reinterpret_cast<float*>(smem + GEMM_SMEM_RING + 1024);
+        if (rank == 0) stage_bias(p, sbias, col_base, (warp - 2) * 32 + lane);
+        mbar_wait(tfull_bar, 0, 44);  // this CTA's K range is in its accumulator; its operand ring is idle from here on
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+        float4* park = reinterpret_cast<float4*>(smem);  // [bn / 4][128 rows] float4: lanes write consecutive 16 B
+        if (rank != 0) {
+            for (int c0 = 0; c0 < p.bn; c0 += 16) {
+                uint32_t v[16];
+                __syncwarp();
+                tmem_ld_x16(taddr + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    park[((c0 >> 2) + j) * 128 + m] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(peers_bar), 0));
+        } else {
+            if (p.ksplit > 1) {
+                mbar_wait_cluster(peers_bar, 0, 45);
+                for (int c0 = 0; c0 < p.bn; c0 += 16) {
+                    uint32_t v[16];
+                    __syncwarp();
+                    tmem_ld_x16(taddr + c0, v);
+                    tmem_ld_wait();
+                    for (int r = 1; r < p.ksplit; ++r) {
+                        const uint32_t peer = mapa_shared(smem_u32(park), static_cast<uint32_t>(r));
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 t = ld_dsmem_f4(peer + (((c0 >> 2) + j) * 128 + m) * 16);
+                            v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + t.x);
+                            v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + t.y);
+                            v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + t.z);
+                            v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + t.w);
+                        }
+                    }
+                    __syncwarp();
+                    tmem_st_x16(taddr + c0, v);  // the total goes back into the accumulator: the epilogue below is unchanged
+                }
+                tmem_st_wait();
+            }
+            epilogue_row(p, taddr, col_base, 0, pix * p.ldc, pix * p.ldr, row_ok, sbias, 0, p.bn);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // no CTA exits (or frees TMEM) while the leader may still read its shared memory
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
     }
 }
 

@@ -162,7 +162,9 @@ def gn_stats_epilogue():
         wpk = ops.pack_conv_weight(wt)
         y0 = ops.conv_fprop(x, wpk, bias=bias, residual=res)
         y, st = ops.conv_fprop(x, wpk, bias=bias, residual=res, stats=True)
-        ok &= bool(torch.equal(y, y0)) and tuple(st.shape) == (n + 1, max(1, hw * hw // 32), cout, 2)
+        # y0 may come from the cluster split-K kernel (another fp32 summation order): equal up to the bf16 rounding
+        ok &= _report(f"stats-epilogue output vs plain n{n} {hw}x{hw} {cin}->{cout} k{k}", y, y0, 4e-3)
+        ok &= tuple(st.shape) == (n + 1, max(1, hw * hw // 32), cout, 2)
         ref = y.float()
         tot = st[:n].sum(1)  # [n, cout, 2]
         ok &= _report(f"epilogue sum   n{n} {hw}x{hw} {cin}->{cout} k{k}", tot[..., 0], ref.sum((1, 2)), 2e-5)
@@ -190,6 +192,45 @@ def gn_stats_epilogue():
     coef_s, ys = ops.gn_forward_stats(ya, sa, yb, sb, gamma, beta, 32, 1e-5, act=True)
     v = F.silu(F.group_norm(torch.cat([ya, yb], -1).float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-5))
     ok &= _report("concat (384 | 192) from two producers vs F.group_norm", ys, v.permute(0, 2, 3, 1), 6e-3)
+    return ok
+
+
+@case
+def conv_splitk():
+    """Cluster split-K conv (tc_conv_splitk_kernel): fprop and dgrad at the under-filled 4x4 / 8x8 levels, with the split
+    the cost model picks and with forced (tile width, split) pairs, against fp32 torch convolutions of the same bf16 data."""
+    import os
+    import torch
+    import torch.nn.functional as F
+    from adm_b200 import ops
+    torch.manual_seed(0)
+    ok = True
+    old = os.environ.pop("ADM_SPLITK_FORCE", None)
+    try:
+        for (n, hw, cin, cout, k) in [(128, 4, 384, 384, 3), (16, 4, 128, 128, 3), (16, 4, 384, 192, 3), (24, 8, 192, 384, 3),
+                                      (128, 4, 384, 384, 1), (5, 4, 104, 72, 3)]:
+            wt = (torch.randn(cout, cin, k, k, device="cuda") / (k * cin ** 0.5)).bfloat16().float()
+            bias = 0.1 * torch.randn(cout, device="cuda")
+            wpk = ops.pack_conv_weight(wt)
+            x = torch.randn(n, hw, hw, cin, device="cuda").bfloat16()
+            res = torch.randn(n, hw, hw, cout, device="cuda").bfloat16()
+            dy = torch.randn(n, hw, hw, cout, device="cuda").bfloat16()
+            y_ref = (F.conv2d(x.float().permute(0, 3, 1, 2), wt, bias, padding=k // 2).permute(0, 2, 3, 1) + res.float())
+            dx_ref = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), wt, padding=k // 2).permute(0, 2, 3, 1)
+            for force in (None, "64,2", "128,2", "128,3", "192,2", "192,4", "64,4", "16,2", "48,3"):
+                if force is None:
+                    os.environ.pop("ADM_SPLITK_FORCE", None)
+                else:
+                    os.environ["ADM_SPLITK_FORCE"] = force  # ignored (plain kernel) where the pair does not fit the problem
+                y = ops.conv_fprop(x, wpk, bias=bias, residual=res)
+                dx = ops.conv_dgrad(dy, wpk, n_valid=cin)
+                tag = f"n{n} {hw}x{hw} {cin}->{cout} k{k} force={force}"
+                ok &= _report(f"split-K fprop {tag}", y, y_ref, 4e-3)
+                ok &= _report(f"split-K dgrad {tag}", dx, dx_ref, 4e-3)
+    finally:
+        os.environ.pop("ADM_SPLITK_FORCE", None)
+        if old is not None:
+            os.environ["ADM_SPLITK_FORCE"] = old
     return ok
 
 
@@ -226,9 +267,11 @@ def conv_gn_prologue():
         y_ref = ops.conv_fprop(a_ref, wpk1, bias=bias, residual=res)
         y, a = ops.conv_fprop_gn(x1, wpk, coef, x2=x2, bias=bias, residual=res, act=act, drop_p=drop, seed=99)
         tag = f"n{n} {h}x{w} {c1}+{c2}->{cout} drop{drop} act{int(act)}"
-        eq_a, eq_y = bool(torch.equal(a, a_ref)), bool(torch.equal(y, y_ref))
-        print(f"  {tag}: activated tensor bit-equal {eq_a}, conv output bit-equal {eq_y}", flush=True)
-        ok &= eq_a and eq_y
+        eq_a = bool(torch.equal(a, a_ref))
+        print(f"  {tag}: activated tensor bit-equal {eq_a}", flush=True)
+        ok &= eq_a
+        # y_ref may come from the cluster split-K kernel (another fp32 summation order): equal up to the bf16 rounding
+        ok &= _report(f"conv output vs unfused {tag}", y, y_ref, 4e-3)
         y2, none = ops.conv_fprop_gn(x1, wpk, coef, x2=x2, bias=bias, residual=res, act=act, drop_p=drop, seed=99,
                                      want_act=False)
         ok &= none is None and bool(torch.equal(y2, y))
@@ -537,7 +580,11 @@ def _compare_grads(net, grads_ref, cos_tol):
     for name, p in net.named_parameters():
         gref = grads_ref[name]
         if float(gref.norm()) < 1e-7 * gmax:
-            assert p.grad is None or float(p.grad.norm()) < 1e-3 * gmax, name
+            # analytically zero (SpatialAtt.k_conv.bias: the softmax is shift invariant): ours is the rounding noise of a sum
+            # of cancelling bf16 terms — it only has to stay far below the real gradients
+            ratio = 0.0 if p.grad is None else float(p.grad.norm()) / gmax
+            print(f"  analytically zero gradient {name}: |ours| / max|grad| = {ratio:.2e} (need < 1e-2)", flush=True)
+            assert ratio < 1e-2, name
             continue
         a, b = p.grad.flatten().double(), gref.flatten().double()
         worst.append(((a @ b / (a.norm() * b.norm() + 1e-30)).item(), name, (a.norm() / (b.norm() + 1e-30)).item()))

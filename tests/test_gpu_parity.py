@@ -53,7 +53,7 @@ def test_training_mode_dropout_masks_vs_oracle():
     assert CU.CASES["unet_dropout_on"]()
 
 
-@pytest.mark.parametrize("case", ["groupnorm", "gn_stats_epilogue", "conv_gn_prologue", "small_ops", "attention", "spatial_att"])
+@pytest.mark.parametrize("case", ["groupnorm", "gn_stats_epilogue", "conv_splitk", "conv_gn_prologue", "small_ops", "attention", "spatial_att"])
 def test_norm_attention_kernels(case):
     assert CU.CASES[case]()
 
@@ -112,7 +112,9 @@ def test_gradient_is_linear_over_the_batch():
     g_b, l_b = grads(slice(16, 32))
     g_mean = 0.5 * (g_a + g_b)
     cos = torch.dot(g_all, g_mean) / (g_all.norm() * g_mean.norm())
-    assert abs(l_all - 0.5 * (l_a + l_b)) / l_all < 1e-4
+    # bf16 compute: the batch of 32 and its halves run different tilings (tile width, K split), i.e. different fp32
+    # summation orders before each bf16 rounding; 1e-3 is a tenth of the north-star loss tolerance for bf16 (1e-2)
+    assert abs(l_all - 0.5 * (l_a + l_b)) / l_all < 1e-3
     assert cos.item() > 0.9995 and abs(g_all.norm().item() / g_mean.norm().item() - 1) < 2e-2
 
 
