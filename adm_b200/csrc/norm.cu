@@ -19,6 +19,8 @@
 #include <string.h>
 #include <cooperative_groups.h>
 
+#include "vecmath.cuh"
+
 namespace cg = cooperative_groups;
 
 namespace adm {
@@ -46,34 +48,6 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const Vec8& r) {
         w[i] = *reinterpret_cast<const uint32_t*>(&b);
     }
     *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-// Counter-based dropout mask: a 64-bit mix of (seed, vector index) is expanded to four 32-bit words (murmur-style
-// finalisers), each giving two 16-bit uniforms.  Stateless, so backward regenerates exactly the forward mask.
-__device__ __forceinline__ uint32_t mix32(uint32_t h) {
-    h ^= h >> 16;
-    h *= 0x85EBCA6Bu;
-    h ^= h >> 13;
-    h *= 0xC2B2AE35u;
-    h ^= h >> 16;
-    return h;
-}
-// keep-mask scale for the 8 channels of vector `vec_index`: 0 or 1/(1-p).
-__device__ __forceinline__ void dropout_scales(unsigned long long seed, unsigned long long vec_index, float p,
-                                               float (&s)[8]) {
-    const unsigned long long z = (vec_index + seed) * 0x9E3779B97F4A7C15ull;
-    const uint32_t base = mix32(static_cast<uint32_t>(z) ^ static_cast<uint32_t>(z >> 32) ^ static_cast<uint32_t>(seed >> 20));
-    const float keep = __frcp_rn(1.f - p);
-    const uint32_t thr = static_cast<uint32_t>(p * 65536.f);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        uint32_t w = (base + static_cast<uint32_t>(i) * 0x9E3779B9u) * 0x85EBCA6Bu;
-        w ^= w >> 15;
-        w *= 0xC2B2AE35u;
-        w ^= w >> 16;
-        s[2 * i] = ((w & 0xFFFFu) >= thr) ? keep : 0.f;
-        s[2 * i + 1] = ((w >> 16) >= thr) ? keep : 0.f;
-    }
 }
 
 // sigmoid via the hardware tanh (1 MUFU op, no division): s = 0.5 * tanh(0.5 v) + 0.5; |err| ~ 2^-12, far below bf16.
@@ -270,6 +244,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const __nv_bfloat16* _
                                                        __nv_bfloat16* __restrict__ out, long long ldo,
                                                        const unsigned long long* __restrict__ seed_dev) {
     if (seed_dev != nullptr) seed += *seed_dev * 0x9E3779B97F4A7C15ull;
+    const DropCtx dc = drop_ctx(seed, drop_p);
     const int C = c1 + c2, V = C >> 3, V1 = c1 >> 3;
     const int n = blockIdx.y, hw = H * W;
     const int tpv = blockDim.x / V;
@@ -319,7 +294,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const __nv_bfloat16* _
     auto emit = [&](int pp, const uint4 raw) {
         const Vec8 xv = unpack8(raw);
         float ds[8];
-        if (drop_p > 0.f) dropout_scales(seed, vec0 + 1ULL * pp * V, drop_p, ds);
+        if (drop_p > 0.f) dropout_scales(dc, static_cast<uint32_t>(vec0 + 1ULL * pp * V), ds);
         Vec8 o;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -356,7 +331,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const __nv_bfloat16* _
 
 // dv (gradient at the pre-activation v = x*A+B) for input pixel p (h, w), channel vector v.
 __device__ __forceinline__ void grad_preact(const __nv_bfloat16* __restrict__ dyb, long long ldy, int H, int W, int p,
-                                            int resample, int act, float drop_p, unsigned long long seed,
+                                            int resample, int act, float drop_p, const DropCtx& dc,
                                             unsigned long long vec_index, const Vec8& xv, const float* a,
                                             const float* b, float (&dv)[8]) {
     Vec8 g;
@@ -377,7 +352,7 @@ __device__ __forceinline__ void grad_preact(const __nv_bfloat16* __restrict__ dy
         }
     }
     float ds[8];
-    if (drop_p > 0.f) dropout_scales(seed, vec_index, drop_p, ds);
+    if (drop_p > 0.f) dropout_scales(dc, static_cast<uint32_t>(vec_index), ds);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         float d = g.v[j];
@@ -407,6 +382,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(const __nv_bfloat
                                                             long long ld_dparams,
                                                             const unsigned long long* __restrict__ seed_dev) {
     if (seed_dev != nullptr) seed += *seed_dev * 0x9E3779B97F4A7C15ull;
+    const DropCtx dc = drop_ctx(seed, drop_p);
     extern __shared__ float sm[];
     __shared__ int s_last;
     const int C = c1 + c2, V = C >> 3, V1 = c1 >> 3;
@@ -434,8 +410,8 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(const __nv_bfloat
         for (; p + step < hw; p += 2 * step) {  // two pixels in flight
             const Vec8 xa = load8(base + p * ld), xb = load8(base + (p + step) * ld);
             float da[8], db[8];
-            grad_preact(dyb, ldy, H, W, p, resample, act, drop_p, seed, vec0 + 1ULL * p * V, xa, a, b, da);
-            grad_preact(dyb, ldy, H, W, p + step, resample, act, drop_p, seed, vec0 + 1ULL * (p + step) * V, xb, a, b, db);
+            grad_preact(dyb, ldy, H, W, p, resample, act, drop_p, dc, vec0 + 1ULL * p * V, xa, a, b, da);
+            grad_preact(dyb, ldy, H, W, p + step, resample, act, drop_p, dc, vec0 + 1ULL * (p + step) * V, xb, a, b, db);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 s1[j] += da[j] + db[j];
@@ -445,7 +421,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(const __nv_bfloat
         for (; p < hw; p += step) {
             const Vec8 xv = load8(base + p * ld);
             float dv[8];
-            grad_preact(dyb, ldy, H, W, p, resample, act, drop_p, seed, vec0 + 1ULL * p * V, xv, a, b, dv);
+            grad_preact(dyb, ldy, H, W, p, resample, act, drop_p, dc, vec0 + 1ULL * p * V, xv, a, b, dv);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 s1[j] += dv[j];
@@ -527,6 +503,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(const __nv_bfloat1
                                                            __nv_bfloat16* __restrict__ dx2, long long ldx2,
                                                            const unsigned long long* __restrict__ seed_dev) {
     if (seed_dev != nullptr) seed += *seed_dev * 0x9E3779B97F4A7C15ull;
+    const DropCtx dc = drop_ctx(seed, drop_p);
     const int C = c1 + c2, V = C >> 3, V1 = c1 >> 3;
     const int n = blockIdx.y, hw = H * W;
     const int tpv = blockDim.x / V;
@@ -574,7 +551,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(const __nv_bfloat1
             }
         }
         float dv[8];
-        grad_preact(dyb, ldy, H, W, p, resample, act, drop_p, seed, vec0 + 1ULL * p * V, xv, a, b, dv);
+        grad_preact(dyb, ldy, H, W, p, resample, act, drop_p, dc, vec0 + 1ULL * p * V, xv, a, b, dv);
         Vec8 o;
 #pragma unroll
         for (int j = 0; j < 8; ++j) o.v[j] = dv[j] * k1[j] + xv.v[j] * k2[j] + k3[j];
@@ -719,11 +696,6 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-// Dropout keep-scales from ONE mixed 32-bit word per vector: four odd multipliers spread it into eight 16-bit uniforms.
-__device__ __forceinline__ void dropout_scales_fast(unsigned long long seed, unsigned long long vec_index, float p,
-                                                    float (&s)[8]) {
-    dropout_scales(seed, vec_index, p, s);
-}
 __global__ void __launch_bounds__(512, 1) gn_fwd_fused_kernel(
     const __nv_bfloat16* __restrict__ x1, int c1, long long ld1, const __nv_bfloat16* __restrict__ x2, int c2,
     long long ld2, int H, int W, int G, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -735,6 +707,7 @@ __global__ void __launch_bounds__(512, 1) gn_fwd_fused_kernel(
     cg::cluster_group cluster = cg::this_cluster();
     const int K = static_cast<int>(cluster.num_blocks()), r = static_cast<int>(cluster.block_rank());
     if (seed_dev != nullptr) seed += *seed_dev * 0x9E3779B97F4A7C15ull;
+    const DropCtx dc = drop_ctx(seed, drop_p);
     const int C = c1 + c2, V = C >> 3, V1 = c1 >> 3;
     const int n = blockIdx.x / K, hw = H * W;
     const int tpv = blockDim.x / V;
@@ -750,32 +723,48 @@ __global__ void __launch_bounds__(512, 1) gn_fwd_fused_kernel(
     const long long ld = v < V1 ? ld1 : ld2;
     const int step = K * tpv;
     const int p0 = r * tpv + lane;
-    // ---- pass 1: per-channel sums over this CTA's pixels (eight 16 B loads in flight per thread)
+    // ---- pass 1: per-channel sums over this CTA's pixels (eight 16 B loads in flight per thread; packed fp32 math)
     {
-        float s[8], q[8];
+        f32x2 s[4], q[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+        for (int i = 0; i < 4; ++i) s[i] = q[i] = 0ull;
         if (active) {
+            const long long stride = step * ld;
+            const __nv_bfloat16* px = base + p0 * ld;
             int p = p0;
             for (; p + 7 * step < hw; p += 8 * step) {
                 uint4 raw[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) raw[u] = *reinterpret_cast<const uint4*>(base + (p + u * step) * ld);
+                for (int u = 0; u < 8; ++u) raw[u] = *reinterpret_cast<const uint4*>(px + u * stride);
+                px += 8 * stride;
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const Vec8 t = unpack8(raw[u]);
+                    const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) { s[i] += t.v[i]; q[i] = fmaf(t.v[i], t.v[i], q[i]); }
+                    for (int i = 0; i < 4; ++i) {
+                        const f32x2 t = bf2_to_f2(w[i]);
+                        s[i] = fadd2(s[i], t);
+                        q[i] = ffma2(t, t, q[i]);
+                    }
                 }
             }
             for (; p < hw; p += step) {
-                const Vec8 t = load8(base + p * ld);
+                const uint4 raw = *reinterpret_cast<const uint4*>(px);
+                px += stride;
+                const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { s[i] += t.v[i]; q[i] = fmaf(t.v[i], t.v[i], q[i]); }
+                for (int i = 0; i < 4; ++i) {
+                    const f32x2 t = bf2_to_f2(w[i]);
+                    s[i] = fadd2(s[i], t);
+                    q[i] = ffma2(t, t, q[i]);
+                }
             }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { red[threadIdx.x * 16 + i] = s[i]; red[threadIdx.x * 16 + 8 + i] = q[i]; }
+        for (int i = 0; i < 4; ++i) {
+            unpack2(s[i], red[threadIdx.x * 16 + 2 * i], red[threadIdx.x * 16 + 2 * i + 1]);
+            unpack2(q[i], red[threadIdx.x * 16 + 8 + 2 * i], red[threadIdx.x * 16 + 8 + 2 * i + 1]);
+        }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -856,61 +845,83 @@ __global__ void __launch_bounds__(512, 1) gn_fwd_fused_kernel(
 #pragma unroll
         for (int j = 0; j < 8; ++j) { a[j] *= 0.5f; b[j] *= 0.5f; }
     }
+    f32x2 a2[4], b2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { a2[j] = pack2(a[2 * j], a[2 * j + 1]); b2[j] = pack2(b[2 * j], b[2 * j + 1]); }
     const int Wo = 2 * W;
     __nv_bfloat16* ob = out + 1LL * n * (resample == 2 ? 4 * hw : hw) * ldo + v * 8;
-    const unsigned long long vec0 = 1ULL * n * hw * V + v;
+    const uint32_t vec0 = static_cast<uint32_t>(1ULL * n * hw * V + v);
     uint4* ring = reinterpret_cast<uint4*>(red);  // [STAGES][blockDim]; `red` is dead (all threads passed the barriers)
+    const long long stride = step * ld;
+    const __nv_bfloat16* pfp = base + p0 * ld;  // prefetch cursor
     int pf = p0;
 #pragma unroll
     for (int st = 0; st < GNF_STAGES; ++st) {
-        if (pf < hw) cp_async16(ring + st * blockDim.x + threadIdx.x, base + pf * ld);
+        if (pf < hw) cp_async16(ring + st * blockDim.x + threadIdx.x, pfp);
         cp_async_commit();
         pf += step;
+        pfp += stride;
     }
     int st = 0;
+    const long long ostride = 1LL * step * ldo;
+    __nv_bfloat16* op = ob + p0 * ldo;
+    uint32_t vec = vec0 + static_cast<uint32_t>(p0) * V;
+    const uint32_t vstep = static_cast<uint32_t>(step) * V;
     for (int p = p0; p < hw; p += step) {
         cp_async_wait<GNF_STAGES - 1>();
         uint4* slot = ring + st * blockDim.x + threadIdx.x;
-        const Vec8 xv = unpack8(*slot);
-        if (pf < hw) cp_async16(slot, base + pf * ld);
+        const uint4 raw = *slot;
+        if (pf < hw) cp_async16(slot, pfp);
         cp_async_commit();
         pf += step;
+        pfp += stride;
         if (++st == GNF_STAGES) st = 0;
-        float ds[8];
-        if (drop_p > 0.f) dropout_scales_fast(seed, vec0 + 1ULL * p * V, drop_p, ds);
-        Vec8 o;
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+        f32x2 y[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float y = fmaf(xv.v[j], a[j], b[j]);
-            if (act) y = fmaf(y, tanh_fast(y), y);
-            if (drop_p > 0.f) y *= ds[j];
-            o.v[j] = y;
+        for (int j = 0; j < 4; ++j) {
+            y[j] = ffma2(bf2_to_f2(w[j]), a2[j], b2[j]);
+            if (act) y[j] = ffma2(y[j], tanh2_fast(y[j]), y[j]);
         }
-        if (resample == 0) {
-            store8(ob + p * ldo, o);
-        } else {
-            const int h = p / W, w = p - h * W;
+        if (drop_p > 0.f) {
+            f32x2 ds[4];
+            dropout_scales2(dc, vec, ds);
 #pragma unroll
-            for (int d = 0; d < 4; ++d) store8(ob + (1LL * (2 * h + (d >> 1)) * Wo + 2 * w + (d & 1)) * ldo, o);
+            for (int j = 0; j < 4; ++j) y[j] = fmul2(y[j], ds[j]);
+        }
+        vec += vstep;
+        const uint4 o = make_uint4(f2_to_bf2(y[0]), f2_to_bf2(y[1]), f2_to_bf2(y[2]), f2_to_bf2(y[3]));
+        if (resample == 0) {
+            *reinterpret_cast<uint4*>(op) = o;
+            op += ostride;
+        } else {
+            const int h = p / W, w_ = p - h * W;
+#pragma unroll
+            for (int d = 0; d < 4; ++d)
+                *reinterpret_cast<uint4*>(ob + (1LL * (2 * h + (d >> 1)) * Wo + 2 * w_ + (d & 1)) * ldo) = o;
         }
     }
 }
 
-// dv (gradient at the pre-activation) from an already loaded upstream-gradient vector g; a/b are pre-halved when act.
-__device__ __forceinline__ void dv_from(const Vec8& g, const Vec8& xv, const float* a, const float* b, int act,
-                                        float drop_p, unsigned long long seed, unsigned long long vec_index,
-                                        float (&dv)[8]) {
-    float ds[8];
-    if (drop_p > 0.f) dropout_scales_fast(seed, vec_index, drop_p, ds);
+// dv (gradient at the pre-activation) of one 8-channel vector in packed fp32: g = upstream gradient, x = GroupNorm input,
+// ah/bh = coefficient pairs, pre-halved when act (h = v/2).  silu'(v) = s * (1 + h * Q) with T = tanh(h), s = (1 + T)/2
+// (the sigmoid) and Q = 1 - T = 2 (1 - s).
+__device__ __forceinline__ void dv_from2(const f32x2 (&g)[4], const f32x2 (&x)[4], const f32x2 (&ah)[4],
+                                         const f32x2 (&bh)[4], int act, float drop_p, const DropCtx& dc, uint32_t vec,
+                                         f32x2 (&dv)[4]) {
+    f32x2 ds[4];
+    if (drop_p > 0.f) dropout_scales2(dc, vec, ds);
+    const f32x2 half = splat2(0.5f), one = splat2(1.f), neg1 = splat2(-1.f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        float d = g.v[j];
-        if (drop_p > 0.f) d *= ds[j];
+    for (int j = 0; j < 4; ++j) {
+        f32x2 d = g[j];
+        if (drop_p > 0.f) d = fmul2(d, ds[j]);
         if (act) {
-            const float h = fmaf(xv.v[j], a[j], b[j]);
-            const float T = tanh_fast(h);
-            const float w = fmaf(h, fmaf(-T, T, 1.f), T);
-            d *= fmaf(w, 0.5f, 0.5f);
+            const f32x2 h = ffma2(x[j], ah[j], bh[j]);
+            const f32x2 T = tanh2_fast(h);
+            const f32x2 sg = ffma2(T, half, half);
+            const f32x2 Q = ffma2(T, neg1, one);
+            d = fmul2(d, fmul2(sg, ffma2(h, Q, one)));
         }
         dv[j] = d;
     }
@@ -933,6 +944,7 @@ __global__ void __launch_bounds__(512, 1) gn_bwd_fused_kernel(
     cg::cluster_group cluster = cg::this_cluster();
     const int K = static_cast<int>(cluster.num_blocks()), r = static_cast<int>(cluster.block_rank());
     if (seed_dev != nullptr) seed += *seed_dev * 0x9E3779B97F4A7C15ull;
+    const DropCtx dc = drop_ctx(seed, drop_p);
     const int C = c1 + c2, V = C >> 3, V1 = c1 >> 3;
     const int n = blockIdx.x / K, hw = H * W;
     const int tpv = blockDim.x / V;
@@ -949,7 +961,7 @@ __global__ void __launch_bounds__(512, 1) gn_bwd_fused_kernel(
     const long long ld = first ? ld1 : ld2;
     const int out_hw = resample == 1 ? hw / 4 : (resample == 2 ? hw * 4 : hw);
     const __nv_bfloat16* dyb = dy + 1LL * n * out_hw * ldy + v * 8;
-    const unsigned long long vec0 = 1ULL * n * hw * V + v;
+    const uint32_t vec0 = static_cast<uint32_t>(1ULL * n * hw * V + v);
     const int step = K * tpv;
     const int p0 = r * tpv + lane;
     const bool piped = resample == 0 && (add == nullptr || add_mode == 0);  // the common, fully pipelined shape
@@ -969,47 +981,66 @@ __global__ void __launch_bounds__(512, 1) gn_bwd_fused_kernel(
             bh[j] = act ? 0.5f * t.y : t.y;
         }
     }
+    f32x2 ah2[4], bh2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { ah2[j] = pack2(ah[2 * j], ah[2 * j + 1]); bh2[j] = pack2(bh[2 * j], bh[2 * j + 1]); }
     // ---- pass 1
     {
         float s1[8], sx[8];
+        f32x2 s1p[4], sxp[4];  // the pipelined path accumulates in packed fp32
 #pragma unroll
         for (int j = 0; j < 8; ++j) s1[j] = sx[j] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s1p[j] = sxp[j] = 0ull;
         if (active && piped) {
+            const long long xstride = step * ld, gstride = step * ldy;
+            const __nv_bfloat16* xpf = base + p0 * ld;
+            const __nv_bfloat16* gpf = dyb + p0 * ldy;
+            __nv_bfloat16* gst = const_cast<__nv_bfloat16*>(dyb) + p0 * ldy;  // dv goes where dy was (reuse_dv)
+            uint32_t vec = vec0 + static_cast<uint32_t>(p0) * V;
+            const uint32_t vstep = static_cast<uint32_t>(step) * V;
             int pf = p0;
 #pragma unroll
             for (int st = 0; st < GNF_STAGES; ++st) {
                 if (pf < hw) {
-                    cp_async16(ring + (st * 3 + 0) * blockDim.x + threadIdx.x, base + pf * ld);
-                    cp_async16(ring + (st * 3 + 1) * blockDim.x + threadIdx.x, dyb + pf * ldy);
+                    cp_async16(ring + (st * 3 + 0) * blockDim.x + threadIdx.x, xpf);
+                    cp_async16(ring + (st * 3 + 1) * blockDim.x + threadIdx.x, gpf);
                 }
                 cp_async_commit();
                 pf += step;
+                xpf += xstride;
+                gpf += gstride;
             }
             int st = 0;
             for (int p = p0; p < hw; p += step) {
                 cp_async_wait<GNF_STAGES - 1>();
                 uint4* sx_ = ring + (st * 3 + 0) * blockDim.x + threadIdx.x;
                 uint4* sd_ = ring + (st * 3 + 1) * blockDim.x + threadIdx.x;
-                const Vec8 xv = unpack8(*sx_), g = unpack8(*sd_);
+                const uint4 xr = *sx_, gr = *sd_;
                 if (pf < hw) {
-                    cp_async16(sx_, base + pf * ld);
-                    cp_async16(sd_, dyb + pf * ldy);
+                    cp_async16(sx_, xpf);
+                    cp_async16(sd_, gpf);
                 }
                 cp_async_commit();
                 pf += step;
+                xpf += xstride;
+                gpf += gstride;
                 if (++st == GNF_STAGES) st = 0;
-                float dv[8];
-                dv_from(g, xv, ah, bh, act, drop_p, seed, vec0 + 1ULL * p * V, dv);
+                const uint32_t xw[4] = {xr.x, xr.y, xr.z, xr.w}, gw[4] = {gr.x, gr.y, gr.z, gr.w};
+                f32x2 x2[4], g2[4], dv[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    s1[j] += dv[j];
-                    sx[j] = fmaf(dv[j], xv.v[j], sx[j]);
+                for (int j = 0; j < 4; ++j) { x2[j] = bf2_to_f2(xw[j]); g2[j] = bf2_to_f2(gw[j]); }
+                dv_from2(g2, x2, ah2, bh2, act, drop_p, dc, vec, dv);
+                vec += vstep;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    s1p[j] = fadd2(s1p[j], dv[j]);
+                    sxp[j] = ffma2(dv[j], x2[j], sxp[j]);
                 }
                 if (reuse_dv) {
-                    Vec8 t;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) t.v[j] = dv[j];
-                    store8(const_cast<__nv_bfloat16*>(dyb) + p * ldy, t);
+                    *reinterpret_cast<uint4*>(gst) =
+                        make_uint4(f2_to_bf2(dv[0]), f2_to_bf2(dv[1]), f2_to_bf2(dv[2]), f2_to_bf2(dv[3]));
+                    gst += gstride;
                 }
             }
             cp_async_wait<0>();
@@ -1017,13 +1048,23 @@ __global__ void __launch_bounds__(512, 1) gn_bwd_fused_kernel(
             for (int p = p0; p < hw; p += step) {
                 const Vec8 xv = load8(base + p * ld);
                 float dv[8];
-                grad_preact(dyb, ldy, H, W, p, resample, act, drop_p, seed, vec0 + 1ULL * p * V, xv, a, b, dv);
+                grad_preact(dyb, ldy, H, W, p, resample, act, drop_p, dc, vec0 + 1ULL * p * V, xv, a, b, dv);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     s1[j] += dv[j];
                     sx[j] += dv[j] * xv.v[j];
                 }
             }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float lo, hi;
+            unpack2(s1p[j], lo, hi);
+            s1[2 * j] += lo;
+            s1[2 * j + 1] += hi;
+            unpack2(sxp[j], lo, hi);
+            sx[2 * j] += lo;
+            sx[2 * j + 1] += hi;
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) { red[threadIdx.x * 16 + j] = s1[j]; red[threadIdx.x * 16 + 8 + j] = sx[j]; }
@@ -1102,16 +1143,35 @@ __global__ void __launch_bounds__(512, 1) gn_bwd_fused_kernel(
         const __nv_bfloat16* addb = add != nullptr ? add + 1LL * n * add_hw * ldadd + v * 8 : nullptr;
         const bool want_bs = dbias1 != nullptr && first;
         if (piped) {
+            f32x2 k1p[4], k2p[4], k3p[4], bsp[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                k1p[j] = pack2(k1[2 * j], k1[2 * j + 1]);
+                k2p[j] = pack2(k2[2 * j], k2[2 * j + 1]);
+                k3p[j] = pack2(k3[2 * j], k3[2 * j + 1]);
+                bsp[j] = 0ull;
+            }
+            const long long xstride = step * ld, gstride = step * ldy, ostride = step * ldo;
+            const long long astride = addb != nullptr ? step * ldadd : 0;
+            const __nv_bfloat16* xpf = base + p0 * ld;
+            const __nv_bfloat16* gpf = dyb + p0 * ldy;
+            const __nv_bfloat16* apf = addb != nullptr ? addb + p0 * ldadd : nullptr;
+            __nv_bfloat16* op = ob + p0 * ldo;
+            uint32_t vec = vec0 + static_cast<uint32_t>(p0) * V;
+            const uint32_t vstep = static_cast<uint32_t>(step) * V;
             int pf = p0;
 #pragma unroll
             for (int st = 0; st < GNF_STAGES; ++st) {
                 if (pf < hw) {
-                    cp_async16(ring + (st * 3 + 0) * blockDim.x + threadIdx.x, base + pf * ld);
-                    cp_async16(ring + (st * 3 + 1) * blockDim.x + threadIdx.x, dyb + pf * ldy);
-                    if (addb != nullptr) cp_async16(ring + (st * 3 + 2) * blockDim.x + threadIdx.x, addb + pf * ldadd);
+                    cp_async16(ring + (st * 3 + 0) * blockDim.x + threadIdx.x, xpf);
+                    cp_async16(ring + (st * 3 + 1) * blockDim.x + threadIdx.x, gpf);
+                    if (addb != nullptr) cp_async16(ring + (st * 3 + 2) * blockDim.x + threadIdx.x, apf);
                 }
                 cp_async_commit();
                 pf += step;
+                xpf += xstride;
+                gpf += gstride;
+                apf += astride;
             }
             int st = 0;
             for (int p = p0; p < hw; p += step) {
@@ -1119,37 +1179,43 @@ __global__ void __launch_bounds__(512, 1) gn_bwd_fused_kernel(
                 uint4* sx_ = ring + (st * 3 + 0) * blockDim.x + threadIdx.x;
                 uint4* sd_ = ring + (st * 3 + 1) * blockDim.x + threadIdx.x;
                 uint4* sa_ = ring + (st * 3 + 2) * blockDim.x + threadIdx.x;
-                const Vec8 xv = unpack8(*sx_), g = unpack8(*sd_);
-                Vec8 addv;
-                if (addb != nullptr) addv = unpack8(*sa_);
+                const uint4 xr = *sx_, gr = *sd_;
+                uint4 ar = make_uint4(0u, 0u, 0u, 0u);
+                if (addb != nullptr) ar = *sa_;
                 if (pf < hw) {
-                    cp_async16(sx_, base + pf * ld);
-                    cp_async16(sd_, dyb + pf * ldy);
-                    if (addb != nullptr) cp_async16(sa_, addb + pf * ldadd);
+                    cp_async16(sx_, xpf);
+                    cp_async16(sd_, gpf);
+                    if (addb != nullptr) cp_async16(sa_, apf);
                 }
                 cp_async_commit();
                 pf += step;
+                xpf += xstride;
+                gpf += gstride;
+                apf += astride;
                 if (++st == GNF_STAGES) st = 0;
-                float dv[8];
+                const uint32_t xw[4] = {xr.x, xr.y, xr.z, xr.w}, gw[4] = {gr.x, gr.y, gr.z, gr.w};
+                const uint32_t aw[4] = {ar.x, ar.y, ar.z, ar.w};
+                f32x2 x2[4], g2[4], dv[4], o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { x2[j] = bf2_to_f2(xw[j]); g2[j] = bf2_to_f2(gw[j]); }
                 if (reuse_dv) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) dv[j] = g.v[j];  // pass 1 left dv in dy's place
+                    for (int j = 0; j < 4; ++j) dv[j] = g2[j];  // pass 1 left dv in dy's place
                 } else {
-                    dv_from(g, xv, ah, bh, act, drop_p, seed, vec0 + 1ULL * p * V, dv);
+                    dv_from2(g2, x2, ah2, bh2, act, drop_p, dc, vec, dv);
                 }
-                Vec8 o;
+                vec += vstep;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o.v[j] = fmaf(dv[j], k1[j], fmaf(xv.v[j], k2[j], k3[j]));
-                if (addb != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) o.v[j] += addv.v[j];
+                for (int j = 0; j < 4; ++j) {
+                    o[j] = ffma2(dv[j], k1p[j], ffma2(x2[j], k2p[j], k3p[j]));
+                    if (addb != nullptr) o[j] = fadd2(o[j], bf2_to_f2(aw[j]));
+                    if (want_bs) bsp[j] = fadd2(bsp[j], o[j]);
                 }
-                if (want_bs) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) bs[j] += o.v[j];
-                }
-                store8(ob + p * ldo, o);
+                *reinterpret_cast<uint4*>(op) = make_uint4(f2_to_bf2(o[0]), f2_to_bf2(o[1]), f2_to_bf2(o[2]), f2_to_bf2(o[3]));
+                op += ostride;
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) unpack2(bsp[j], bs[2 * j], bs[2 * j + 1]);
         } else {
             for (int p = p0; p < hw; p += step) {
                 const Vec8 xv = load8(base + p * ld);
@@ -1174,7 +1240,7 @@ __global__ void __launch_bounds__(512, 1) gn_bwd_fused_kernel(
                     }
                 }
                 float dv[8];
-                grad_preact(dyb, ldy, H, W, p, resample, act, drop_p, seed, vec0 + 1ULL * p * V, xv, a, b, dv);
+                grad_preact(dyb, ldy, H, W, p, resample, act, drop_p, dc, vec0 + 1ULL * p * V, xv, a, b, dv);
                 Vec8 o;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o.v[j] = dv[j] * k1[j] + xv.v[j] * k2[j] + k3[j];

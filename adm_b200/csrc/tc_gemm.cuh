@@ -11,6 +11,7 @@
 #pragma once
 #include "ptx.cuh"
 #include "adm_internal.h"
+#include "vecmath.cuh"
 #ifdef ADM_GEMM_TIMING
 #include <stdio.h>
 #endif
@@ -99,32 +100,8 @@ __device__ __forceinline__ float gemm_tanh_fast(float h) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
     return t;
 }
-// The dropout keep-scales of csrc/norm.cu (same hash, same indexing: backward regenerates these masks there).
-__device__ __forceinline__ uint32_t gemm_mix32(uint32_t h) {
-    h ^= h >> 16;
-    h *= 0x85EBCA6Bu;
-    h ^= h >> 13;
-    h *= 0xC2B2AE35u;
-    h ^= h >> 16;
-    return h;
-}
-__device__ __forceinline__ void gemm_dropout_scales(unsigned long long seed, unsigned long long vec_index, float p,
-                                                    float (&s)[8]) {
-    const unsigned long long z = (vec_index + seed) * 0x9E3779B97F4A7C15ull;
-    const uint32_t base =
-        gemm_mix32(static_cast<uint32_t>(z) ^ static_cast<uint32_t>(z >> 32) ^ static_cast<uint32_t>(seed >> 20));
-    const float keep = __frcp_rn(1.f - p);
-    const uint32_t thr = static_cast<uint32_t>(p * 65536.f);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        uint32_t w = (base + static_cast<uint32_t>(i) * 0x9E3779B9u) * 0x85EBCA6Bu;
-        w ^= w >> 15;
-        w *= 0xC2B2AE35u;
-        w ^= w >> 16;
-        s[2 * i] = ((w & 0xFFFFu) >= thr) ? keep : 0.f;
-        s[2 * i + 1] = ((w >> 16) >= thr) ? keep : 0.f;
-    }
-}
+// The dropout keep-scales are those of csrc/norm.cu (vecmath.cuh: same hash, same indexing — backward regenerates the
+// masks there).
 
 __device__ __forceinline__ void decode_pix(const GemmParams& p, int idx, int& n0, int& h0, int& w0) {
     const int per = p.tiles_w * p.tiles_h;
@@ -1132,6 +1109,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int C = p.pro_c1 + p.pro_c2, V = C >> 3;
         unsigned long long seed = p.pro_seed;
         if (p.pro_seed_dev != nullptr) seed += *p.pro_seed_dev * 0x9E3779B97F4A7C15ull;
+        const DropCtx dc = drop_ctx(seed, p.pro_drop_p);
         int hs = 0;
         uint32_t hphase = 0;
         int last_n = -1;
@@ -1185,7 +1163,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const long long pix = (static_cast<long long>(n0) * p.H + y) * p.W + x;
                     float ds[8];
                     if (p.pro_drop_p > 0.f)
-                        gemm_dropout_scales(seed, static_cast<unsigned long long>(pix) * V + (cbase >> 3), p.pro_drop_p, ds);
+                        dropout_scales(dc, static_cast<uint32_t>(static_cast<unsigned long long>(pix) * V + (cbase >> 3)), ds);
                     uint32_t o[4];
 #pragma unroll
                     for (int j = 0; j < 8; j += 2) {

@@ -137,7 +137,10 @@ def test_step_is_repeatable_and_dropout_changes_it():
         l3, _ = dpm.p_losses(x, t, noise=noise)
         l4, _ = dpm.p_losses(x, t, noise=noise)
     rel = lambda a, b: abs(a.item() - b.item()) / abs(b.item())
-    assert rel(l3, l1) > 5e-3 and rel(l3, l4) > 5e-3  # dropout active, fresh masks per call
+    assert rel(l3, l1) > 5e-3  # dropout active
+    # fresh masks per call: two draws differ by far more than the run-to-run noise of identical inputs (the loss averages
+    # over ~10^5 independent mask elements, so the difference between two draws is itself small)
+    assert rel(l3, l4) > max(20 * rel(l2, l1), 1e-4)
 
 
 def test_sampler_full_size_properties():
