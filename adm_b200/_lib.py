@@ -76,6 +76,9 @@ SIGNATURES = {
     "adm_silu_bwd": (c_i, [c_p, c_p, c_p, c_p, c_ll, c_p]),
     "adm_attn_fwd_fused": (c_i, [c_p, c_i, c_i, c_i, c_f, c_p, c_p, c_p]),
     "adm_attn_bwd_fused": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p, c_p]),
+    "adm_attn_long_workspace": (c_ll, [c_i, c_i, c_i, c_i]),
+    "adm_attn_fwd_long": (c_i, [c_p, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_ll, c_p]),
+    "adm_attn_bwd_long": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p, c_p, c_ll, c_p]),
     "adm_softmax_fwd": (c_i, [c_p, c_p, c_ll, c_i, c_p]),
     "adm_softmax_bwd": (c_i, [c_p, c_p, c_p, c_f, c_ll, c_i, c_p]),
     "adm_spatial_att_fwd": (c_i, [c_p, c_ll, c_p, c_ll, c_p, c_p, c_i, c_i, c_i, c_p, c_ll, c_p, c_p, c_p]),

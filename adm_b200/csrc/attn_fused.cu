@@ -20,6 +20,14 @@
 // Small images are PACKED: 128 tile rows hold 2 samples of 64 pixels or 8 samples of 16 pixels (one TMA box over
 // (channel, pixel, sample)); the off-diagonal blocks of S are masked to zero probability.
 // Shapes: pixels N in {16, 64, 256}, head dim 64 (32 / 72 run zero-padded by the caller).
+// Longer sequences (N = nblk * 256, e.g. the 32 x 32 level of the CelebAHQ-latent UNet, configs/celebahq/...ldm.yaml:55) run
+// BLOCKED on the same kernels: a work unit is (sample, head, query block, key block) of 256 x 256.  Forward units emit a
+// block-normalised partial O and a partial log-sum-exp per key block, merged by attn_combine_kernel; backward units use
+// the merged log-sum-exp (so P is already the global probability) and emit partial dQ (per key block) and dK / dV (per
+// query block) into nblk dqkv-shaped buffers that attn_reduce_kernel sums.  No N x N tensor exists in either direction.
+#include <algorithm>
+#include <climits>
+
 #include "adm_internal.h"
 #include "ptx.cuh"
 
@@ -62,7 +70,26 @@ struct AttnParams {
     __nv_bfloat16* out;        // fwd: O [B, N, C];  bwd: dqkv [B, N, 3C]
     float* lse;                // [B, heads, N]  (log2 domain: c1 * max + log2(sum))
     const __nv_bfloat16* o_in; // bwd: the forward output O
+    int nblk;                  // 1, or the number of 256-pixel blocks of a long sequence (blocked units, see above)
+    long long out_stride;      // blocked: elements between consecutive partial buffers of `out`
+    long long lse_stride;      // blocked forward: elements between consecutive partial log-sum-exp buffers
 };
+
+// work unit -> (first sample, head, query block, key block)
+__device__ __forceinline__ void attn_unit(const AttnParams& p, int u, int& b0, int& h, int& qb, int& kb) {
+    if (p.nblk == 1) {
+        b0 = (u / p.heads) * p.pack;
+        h = u % p.heads;
+        qb = kb = 0;
+    } else {
+        kb = u % p.nblk;
+        u /= p.nblk;
+        qb = u % p.nblk;
+        u /= p.nblk;
+        h = u % p.heads;
+        b0 = u / p.heads;
+    }
+}
 
 // ------------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(AT_THREADS, 1)
@@ -105,15 +132,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         // =========================================================== TMA producer
         if (lane == 0) {
             for (int ul = 0; ul < n_local; ++ul) {
-                const int u = blockIdx.x + ul * gridDim.x;
-                const int b0 = (u / p.heads) * p.pack, h = u % p.heads;
+                int b0, h, qb, kb;
+                attn_unit(p, blockIdx.x + ul * gridDim.x, b0, h, qb, kb);
                 const int st = ul % p.stages;
                 mbar_wait(&empty[st], ((ul / p.stages) & 1) ^ 1, 21);
                 mbar_expect_tx(&full[st], stage_bytes);
                 uint8_t* sq = smem + st * stage_bytes;
-                tma_load_3d(sq, &tmQKV, &full[st], h * 64, 0, b0);
-                tma_load_3d(sq + q_bytes, &tmQKV, &full[st], p.c + h * 64, 0, b0);
-                tma_load_3d(sq + q_bytes + kv_bytes, &tmQKV, &full[st], 2 * p.c + h * 64, 0, b0);
+                tma_load_3d(sq, &tmQKV, &full[st], h * 64, qb * 256, b0);
+                tma_load_3d(sq + q_bytes, &tmQKV, &full[st], p.c + h * 64, kb * 256, b0);
+                tma_load_3d(sq + q_bytes + kv_bytes, &tmQKV, &full[st], 2 * p.c + h * 64, kb * 256, b0);
             }
         }
     } else if (warp == 1) {
@@ -162,14 +189,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const int row = quad * 32 + lane;      // row inside the 128-row tile
         const uint32_t taddr = tmem_base + g * 256 + (static_cast<uint32_t>(quad * 32) << 16);
         const int N = p.n_pix;
-        const int wn = N < 32 ? 32 : N;        // key window this warp reads (warp-uniform), a multiple of 32
+        const int wn = N < 32 ? 32 : (N > 256 ? 256 : N);  // key window this warp reads (warp-uniform), a multiple of 32
         const int wbeg = p.ncols == 256 ? 0 : (row / wn) * wn;
         const int my_blk = row / N;            // packed: the sample (inside the tile) this row belongs to
         int it = 0;
         for (int ul = (p.tiles == 2 ? 0 : g); ul < n_local; ul += (p.tiles == 2 ? 1 : 2), ++it) {
             const int tl = p.tiles == 2 ? g : 0;
-            const int u = blockIdx.x + ul * gridDim.x;
-            const int b0 = (u / p.heads) * p.pack, h = u % p.heads;
+            int b0, h, qb, kb;
+            attn_unit(p, blockIdx.x + ul * gridDim.x, b0, h, qb, kb);
             mbar_wait(&s_full[g], it & 1, 25);
             tc_fence_after();
             // ---- pass 1: row maximum over this row's own keys
@@ -230,12 +257,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             if (lane == 0) mbar_arrive(&p_full[g]);
             // ---- epilogue: O / sum -> bf16, log-sum-exp
             const int smp = b0 + (p.ncols == 256 ? 0 : my_blk);
-            const int pix = p.ncols == 256 ? tl * 128 + row : row - my_blk * N;
+            const int pix = p.ncols == 256 ? qb * 256 + tl * 128 + row : row - my_blk * N;
             const bool row_ok = smp < p.batch;
             const float inv = 1.f / sum;
             mbar_wait(&o_full[g], it & 1, 26);
             tc_fence_after();
-            __nv_bfloat16* op = p.out + (1LL * smp * N + pix) * p.c + h * 64;
+            __nv_bfloat16* op = p.out + kb * p.out_stride + (1LL * smp * N + pix) * p.c + h * 64;
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 32) {
                 uint32_t v[32];
@@ -253,7 +280,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     }
                 }
             }
-            if (row_ok && p.lse != nullptr) p.lse[(1LL * smp * p.heads + h) * N + pix] = mc + log2f(sum);
+            if (row_ok && p.lse != nullptr) p.lse[kb * p.lse_stride + (1LL * smp * p.heads + h) * N + pix] = mc + log2f(sum);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&o_done[g]);
@@ -321,16 +348,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         // =========================================================== TMA producer
         if (lane == 0) {
             for (int ul = 0; ul < n_local; ++ul) {
-                const int u = blockIdx.x + ul * gridDim.x;
-                const int b0 = (u / p.heads) * p.pack, h = u % p.heads;
+                int b0, h, qb, kb;
+                attn_unit(p, blockIdx.x + ul * gridDim.x, b0, h, qb, kb);
                 const int st = ul % p.stages;
                 mbar_wait(&empty[st], ((ul / p.stages) & 1) ^ 1, 31);
                 mbar_expect_tx(&full[st], stage_bytes);
                 uint8_t* s0 = smem + st * stage_bytes;
-                tma_load_3d(s0, &tmQKV, &full[st], h * 64, 0, b0);                        // Q
-                tma_load_3d(s0 + t_bytes, &tmQKV, &full[st], p.c + h * 64, 0, b0);         // K
-                tma_load_3d(s0 + 2 * t_bytes, &tmQKV, &full[st], 2 * p.c + h * 64, 0, b0); // V
-                tma_load_3d(s0 + 3 * t_bytes, &tmDO, &full[st], h * 64, 0, b0);            // dO
+                tma_load_3d(s0, &tmQKV, &full[st], h * 64, qb * 256, b0);                        // Q
+                tma_load_3d(s0 + t_bytes, &tmQKV, &full[st], p.c + h * 64, kb * 256, b0);         // K
+                tma_load_3d(s0 + 2 * t_bytes, &tmQKV, &full[st], 2 * p.c + h * 64, kb * 256, b0); // V
+                tma_load_3d(s0 + 3 * t_bytes, &tmDO, &full[st], h * 64, qb * 256, b0);            // dO
             }
         }
     } else if (warp == 1) {
@@ -406,14 +433,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             // copies selected by the unit's parity are enough
             float* sL = sLD + (ul & 1) * 512;
             float* sD = sL + 256;
-            const int u = blockIdx.x + ul * gridDim.x;
-            const int b0 = (u / p.heads) * p.pack, h = u % p.heads;
+            int b0, h, qb, kb;
+            attn_unit(p, blockIdx.x + ul * gridDim.x, b0, h, qb, kb);
             const int st = ul % p.stages;
             const uint8_t* sdo = smem + st * stage_bytes + 3 * t_bytes;
             mbar_wait(&full[st], (ul / p.stages) & 1, 35);
             // ---- prologue: D_q = sum_d dO_qd O_qd and L_q for every query of the unit
             if (tq < nq) {
-                const int smp = b0 + (packed ? tq / N : 0), pix = packed ? tq % N : tq;
+                const int smp = b0 + (packed ? tq / N : 0), pix = packed ? tq % N : qb * 256 + tq;
                 float d = 0.f, l = 0.f;
                 if (smp < p.batch) {
                     const uint4* orow = reinterpret_cast<const uint4*>(p.o_in + (1LL * smp * N + pix) * p.c + h * 64);
@@ -497,8 +524,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     mbar_wait(acc_full, jj & 1, 38);
                     tc_fence_after();
                     const int krow = j * 128 + row;
-                    const int smp = b0 + (packed ? krow / N : 0), pix = packed ? krow % N : krow;
-                    __nv_bfloat16* gp = p.out + (1LL * smp * N + pix) * 3 * p.c + (g == 0 ? p.c : 2 * p.c) + h * 64;
+                    const int smp = b0 + (packed ? krow / N : 0), pix = packed ? krow % N : kb * 256 + krow;
+                    // blocked: partial dK / dV of this query block go to buffer qb, partial dQ of this key block to buffer kb
+                    __nv_bfloat16* gp =
+                        p.out + qb * p.out_stride + (1LL * smp * N + pix) * 3 * p.c + (g == 0 ? p.c : 2 * p.c) + h * 64;
                     const uint32_t src = trow + (g == 0 ? BW_DK : BW_DV);
 #pragma unroll
                     for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -519,8 +548,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     }
                     if (j == nkt - 1 && g < p.tiles) {  // dQ tile g: rows = queries g*128 + row
                         const int qrow = g * 128 + row;
-                        const int qs = b0 + (packed ? qrow / N : 0), qp = packed ? qrow % N : qrow;
-                        __nv_bfloat16* qg = p.out + (1LL * qs * N + qp) * 3 * p.c + h * 64;
+                        const int qs = b0 + (packed ? qrow / N : 0), qp = packed ? qrow % N : qb * 256 + qrow;
+                        __nv_bfloat16* qg = p.out + kb * p.out_stride + (1LL * qs * N + qp) * 3 * p.c + h * 64;
 #pragma unroll
                         for (int c0 = 0; c0 < 64; c0 += 32) {
                             uint32_t v[32];
@@ -552,6 +581,66 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ blocked sequences
+// Forward merge of the per-key-block partials: L = log2 sum_kb 2^L_kb, O = sum_kb 2^(L_kb - L) O_kb.
+// One thread per (row, head, 8 channels); po [nblk][B, N, C] bf16, pl [nblk][B, heads, N] fp32.
+__global__ void __launch_bounds__(256) attn_combine_kernel(const __nv_bfloat16* __restrict__ po, const float* __restrict__ pl,
+                                                           int nblk, long long rows, int n_pix, int heads,
+                                                           __nv_bfloat16* __restrict__ out, float* __restrict__ lse) {
+    const long long total = rows * heads * 8;
+    const long long ostride = rows * heads * 64, lstride = rows * heads;
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+        const int v = static_cast<int>(i & 7);
+        const long long rh = i >> 3;  // row * heads + head
+        const long long row = rh / heads;
+        const int h = static_cast<int>(rh - row * heads);
+        const long long li = ((row / n_pix) * heads + h) * n_pix + row % n_pix;
+        float m = -INFINITY;
+        for (int k = 0; k < nblk; ++k) m = fmaxf(m, pl[k * lstride + li]);
+        float tot = 0.f;
+        for (int k = 0; k < nblk; ++k) tot += ex2(pl[k * lstride + li] - m);
+        const float inv = 1.f / tot;
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        const long long off = rh * 64 + v * 8;
+        for (int k = 0; k < nblk; ++k) {
+            const float w = ex2(pl[k * lstride + li] - m) * inv;
+            const uint4 raw = *reinterpret_cast<const uint4*>(po + k * ostride + off);
+            const uint32_t ww[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                acc[2 * e] = fmaf(w, __uint_as_float(ww[e] << 16), acc[2 * e]);
+                acc[2 * e + 1] = fmaf(w, __uint_as_float(ww[e] & 0xFFFF0000u), acc[2 * e + 1]);
+            }
+        }
+        *reinterpret_cast<uint4*>(out + off) = make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]),
+                                                          pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+        if (v == 0 && lse != nullptr) lse[li] = m + log2f(tot);
+    }
+}
+
+// Backward merge: dqkv = sum over the nblk partial buffers (fp32 accumulation, one rounding).
+__global__ void __launch_bounds__(256) attn_reduce_kernel(const __nv_bfloat16* __restrict__ part, int nblk, long long nvec,
+                                                          __nv_bfloat16* __restrict__ out) {
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < nvec; i += 1LL * gridDim.x * blockDim.x) {
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        for (int k = 0; k < nblk; ++k) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(part + (k * nvec + i) * 8);
+            const uint32_t ww[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                acc[2 * e] += __uint_as_float(ww[e] << 16);
+                acc[2 * e + 1] += __uint_as_float(ww[e] & 0xFFFF0000u);
+            }
+        }
+        *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]),
+                                                            pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
     }
 }
 
@@ -602,6 +691,7 @@ static int af_setup(const char* what, AttnParams* p, int batch, int n_pix, int h
     p->tiles = n_pix == 256 ? 2 : 1;
     p->ncols = n_pix == 256 ? 256 : 128;
     p->units = ((batch + p->pack - 1) / p->pack) * heads;
+    p->nblk = 1; p->out_stride = 0; p->lse_stride = 0;
     p->scale = scale;
     p->c1 = scale * 1.4426950408889634f;
     return 0;
@@ -654,5 +744,96 @@ extern "C" int adm_attn_bwd_fused(const void* da, const void* qkv, const void* o
     const int grid = p.units < num_sms() ? p.units : num_sms();
     launch_k(attn_bwd_kernel, dim3(grid), dim3(AT_THREADS), AT_SMEM_TOTAL, static_cast<cudaStream_t>(stream), 0, mq, mdo, p);
     ADM_CHECK_LAUNCH("attn_bwd_fused");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ long sequences (blocked)
+static int af_setup_long(const char* what, AttnParams* p, int batch, int n_pix, int heads, float scale) {
+    if (n_pix < 512 || n_pix > 4096 || n_pix % 256 != 0 || batch <= 0 || heads <= 0) {
+        set_error("%s: n_pix must be a multiple of 256 in [512, 4096] (got %d)", what, n_pix);
+        return ADM_ERR_SHAPE;
+    }
+    p->n_pix = n_pix; p->heads = heads; p->batch = batch; p->c = heads * 64;
+    p->pack = 1; p->tiles = 2; p->ncols = 256;
+    p->nblk = n_pix / 256;
+    const long long units = 1LL * batch * heads * p->nblk * p->nblk;
+    if (units > INT_MAX) {
+        set_error("%s: too many work units", what);
+        return ADM_ERR_SHAPE;
+    }
+    p->units = static_cast<int>(units);
+    p->scale = scale;
+    p->c1 = scale * 1.4426950408889634f;
+    return 0;
+}
+
+// Bytes of scratch the blocked kernels need: forward = nblk partial outputs [B, N, C] bf16 + nblk partial log-sum-exps
+// [B, heads, N] fp32; backward = nblk partial dqkv [B, N, 3C] bf16.
+extern "C" long long adm_attn_long_workspace(int batch, int n_pix, int heads, int backward) {
+    if (n_pix < 512 || n_pix % 256 != 0 || batch <= 0 || heads <= 0) return 0;
+    const long long nblk = n_pix / 256, rows = 1LL * batch * n_pix, c = 64LL * heads;
+    return backward ? nblk * rows * 3 * c * 2 : nblk * (rows * c * 2 + rows * heads * 4);
+}
+
+extern "C" int adm_attn_fwd_long(const void* qkv, int batch, int n_pix, int heads, float scale, void* out, float* lse,
+                                 void* work, long long work_bytes, void* stream) {
+    AttnParams p;
+    if (int e = af_setup_long("attn_fwd_long", &p, batch, n_pix, heads, scale)) return e;
+    if (work == nullptr || work_bytes < adm_attn_long_workspace(batch, n_pix, heads, 0) ||
+        ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(work)) & 15) != 0) {
+        set_error("attn_fwd_long: workspace too small or pointers not 16 B aligned");
+        return ADM_ERR_SHAPE;
+    }
+    const long long rows = 1LL * batch * n_pix;
+    p.stages = 2;
+    p.out = static_cast<__nv_bfloat16*>(work);
+    p.out_stride = rows * p.c;
+    p.lse = reinterpret_cast<float*>(static_cast<__nv_bfloat16*>(work) + p.nblk * p.out_stride);
+    p.lse_stride = rows * heads;
+    p.o_in = nullptr;
+    CUtensorMap mq;
+    if (int e = af_map(&mq, qkv, 3LL * p.c, n_pix, batch, 256, 1)) return e;
+    cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_TOTAL);
+    const int grid = p.units < num_sms() ? p.units : num_sms();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    launch_k(attn_fwd_kernel, dim3(grid), dim3(AT_THREADS), AT_SMEM_TOTAL, st, 0, mq, p);
+    ADM_CHECK_LAUNCH("attn_fwd_long");
+    const long long total = rows * heads * 8;
+    const int cgrid = static_cast<int>(std::min<long long>((total + 255) / 256, 8LL * num_sms()));
+    attn_combine_kernel<<<cgrid, 256, 0, st>>>(p.out, p.lse, p.nblk, rows, n_pix, heads, static_cast<__nv_bfloat16*>(out), lse);
+    ADM_CHECK_LAUNCH("attn_combine");
+    return 0;
+}
+
+extern "C" int adm_attn_bwd_long(const void* da, const void* qkv, const void* out_fwd, const float* lse, int batch,
+                                 int n_pix, int heads, float scale, void* dqkv, void* work, long long work_bytes,
+                                 void* stream) {
+    AttnParams p;
+    if (int e = af_setup_long("attn_bwd_long", &p, batch, n_pix, heads, scale)) return e;
+    if (out_fwd == nullptr || lse == nullptr || work == nullptr ||
+        work_bytes < adm_attn_long_workspace(batch, n_pix, heads, 1) ||
+        ((reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out_fwd) |
+          reinterpret_cast<uintptr_t>(dqkv) | reinterpret_cast<uintptr_t>(work)) & 15) != 0) {
+        set_error("attn_bwd_long: forward output, log-sum-exp and workspace are required; pointers must be 16 B aligned");
+        return ADM_ERR_SHAPE;
+    }
+    const long long rows = 1LL * batch * n_pix;
+    p.stages = 1;
+    p.out = static_cast<__nv_bfloat16*>(work);
+    p.out_stride = rows * 3 * p.c;
+    p.lse = const_cast<float*>(lse);
+    p.o_in = static_cast<const __nv_bfloat16*>(out_fwd);
+    CUtensorMap mq, mdo;
+    if (int e = af_map(&mq, qkv, 3LL * p.c, n_pix, batch, 256, 1)) return e;
+    if (int e = af_map(&mdo, da, p.c, n_pix, batch, 256, 1)) return e;
+    cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_TOTAL);
+    const int grid = p.units < num_sms() ? p.units : num_sms();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    launch_k(attn_bwd_kernel, dim3(grid), dim3(AT_THREADS), AT_SMEM_TOTAL, st, 0, mq, mdo, p);
+    ADM_CHECK_LAUNCH("attn_bwd_long");
+    const long long nvec = p.out_stride / 8;
+    const int rgrid = static_cast<int>(std::min<long long>((nvec + 255) / 256, 8LL * num_sms()));
+    attn_reduce_kernel<<<rgrid, 256, 0, st>>>(p.out, p.nblk, nvec, static_cast<__nv_bfloat16*>(dqkv));
+    ADM_CHECK_LAUNCH("attn_reduce");
     return 0;
 }

@@ -513,8 +513,14 @@ def _gemm(desc_kw, a_op, b_op, what):
 
 
 def attention_fused_ok(d, hw):
-    """Shapes served by the fused K9 kernels (everything else runs as batched GEMMs + a softmax kernel)."""
-    return d == 64 and hw in (16, 64, 256)
+    """Shapes served by the fused K9 kernels (everything else runs as batched GEMMs + a softmax kernel): one unit per
+    (sample, head) up to 256 pixels, 256 x 256 blocks with a log-sum-exp merge for 512..4096 pixels."""
+    return d == 64 and (hw in (16, 64, 256) or (hw % 256 == 0 and 512 <= hw <= 4096))
+
+
+def _attn_workspace(n, hw, heads, backward, device):
+    nbytes = _lib.load().adm_attn_long_workspace(n, hw, heads, int(backward))
+    return torch.empty(nbytes, device=device, dtype=torch.uint8), nbytes
 
 
 def attention_fwd(qkv, heads, scale=None, need_p=True, fused=None):
@@ -533,6 +539,11 @@ def attention_fwd(qkv, heads, scale=None, need_p=True, fused=None):
     if fused:
         a = torch.empty(n, h, w, c, device=qkv.device, dtype=BF16)
         lse = torch.empty(n, heads, hw, device=qkv.device, dtype=F32) if need_p else None
+        if hw > 256:
+            work, nbytes = _attn_workspace(n, hw, heads, False, qkv.device)
+            check(_lib.load().adm_attn_fwd_long(_ptr(qkv), n, hw, heads, scale, _ptr(a), _ptr(lse), _ptr(work), nbytes,
+                                                _stream()), "attn_fwd_long")
+            return a, lse
         check(_lib.load().adm_attn_fwd_fused(_ptr(qkv), n, hw, heads, scale, _ptr(a), _ptr(lse), _stream()),
               "attn_fwd_fused")
         return a, lse
@@ -565,6 +576,11 @@ def attention_bwd(da, qkv, aux, heads, scale=None, fused=None, a=None):
     if fused:
         assert a is not None and a.is_contiguous() and aux is not None and aux.dtype == F32, \
             "fused attention backward needs the forward output and its log-sum-exp"
+        if hw > 256:
+            work, nbytes = _attn_workspace(n, hw, heads, True, qkv.device)
+            check(_lib.load().adm_attn_bwd_long(_ptr(da), _ptr(qkv), _ptr(a), _ptr(aux), n, hw, heads, scale, _ptr(dqkv),
+                                                _ptr(work), nbytes, _stream()), "attn_bwd_long")
+            return dqkv
         check(_lib.load().adm_attn_bwd_fused(_ptr(da), _ptr(qkv), _ptr(a), _ptr(aux), n, hw, heads, scale, _ptr(dqkv),
                                              _stream()), "attn_bwd_fused")
         return dqkv

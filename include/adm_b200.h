@@ -232,6 +232,16 @@ int adm_attn_fwd_fused(const void* qkv, int batch, int n_pix, int heads, float s
  * of out), out_fwd = the forward output, dqkv [batch][n_pix][3*heads*64] bf16 (dq | dk | dv).                 */
 int adm_attn_bwd_fused(const void* da, const void* qkv, const void* out_fwd, const float* lse, int batch, int n_pix,
                        int heads, float scale, void* dqkv, void* stream);
+/* The same attention for long sequences, n_pix = nblk * 256 in [512, 4096] (the 32 x 32 level of the CelebAHQ-latent UNet,
+ * /root/reference/configs/celebahq/celeb_uncond_ddm_const_uncond_unet_ldm.yaml:55: attn_resolutions [32, 16]): the fused
+ * kernels run over (sample, head, query block, key block) units of 256 x 256 and two small merge kernels combine the
+ * per-block partials (log-sum-exp weighted sum forward, plain sum backward) — no n_pix x n_pix tensor exists.
+ * `work` is caller-owned scratch of at least adm_attn_long_workspace(batch, n_pix, heads, backward) bytes.          */
+long long adm_attn_long_workspace(int batch, int n_pix, int heads, int backward);
+int adm_attn_fwd_long(const void* qkv, int batch, int n_pix, int heads, float scale, void* out, float* lse, void* work,
+                      long long work_bytes, void* stream);
+int adm_attn_bwd_long(const void* da, const void* qkv, const void* out_fwd, const float* lse, int batch, int n_pix,
+                      int heads, float scale, void* dqkv, void* work, long long work_bytes, void* stream);
 /* SpatialAtt + residual of the decouple branches (unet/uncond_unet.py:27-37, :566-567):
  * out = softsign(softmax(q k^T) att) * h + res with att = h . w_map + b; scalars = {b_map, wq, bq, wk, bk}.   */
 int adm_spatial_att_fwd(const void* h, long long ldh, const void* res, long long ldr, const float* w_map,

@@ -135,12 +135,20 @@ def test_step_is_repeatable_and_dropout_changes_it():
     net.train()
     with torch.no_grad():
         l3, _ = dpm.p_losses(x, t, noise=noise)
-        l4, _ = dpm.p_losses(x, t, noise=noise)
+        c3, e3 = net(x, t)
+        c4, e4 = net(x, t)
+    net.eval()
+    with torch.no_grad():
+        c1, e1 = net(x, t)
+        c2, e2 = net(x, t)
     rel = lambda a, b: abs(a.item() - b.item()) / abs(b.item())
+    dist = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()
     assert rel(l3, l1) > 5e-3  # dropout active
-    # fresh masks per call: two draws differ by far more than the run-to-run noise of identical inputs (the loss averages
-    # over ~10^5 independent mask elements, so the difference between two draws is itself small)
-    assert rel(l3, l4) > max(20 * rel(l2, l1), 1e-4)
+    # fresh masks per call: two training-mode forwards differ element-wise by far more than two evaluation-mode forwards
+    # (a scalar loss averages ~10^5 independent mask elements and hides the difference)
+    noise = max(dist(c1, c2), dist(e1, e2))  # small batches: fp32 atomics reorder the GroupNorm sums, bf16 roundings flip
+    assert noise < 2e-2
+    assert min(dist(c3, c4), dist(e3, e4)) > max(10 * noise, 5e-2)
 
 
 def test_sampler_full_size_properties():

@@ -14,7 +14,15 @@ from adm_b200.train import TrainStep
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "train"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 128
-dev = torch.device("cuda", 0)
+# under torchrun (WORLD_SIZE > 1) this profiles the data-parallel step: the graph chain plus the NCCL all-reduces between
+# its segments; every rank profiles itself, rank 0 prints
+world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
 dpm = bench.build_model(dev)
 dpm.train()
 step = TrainStep(dpm)
@@ -46,7 +54,15 @@ for ev in prof.events():
         tot[name][0] += 1
         tot[name][1] += ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total
 busy = sum(v[1] for v in tot.values()) / 1000.0 / REPS
-print(f"{mode} B={B}: wall {wall:.2f} ms per run (under the profiler), kernels busy {busy:.2f} ms, "
+if rank != 0:
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    sys.exit(0)
+print(f"{mode} B={B} ranks={world}: wall {wall:.2f} ms per run (under the profiler), kernels busy {busy:.2f} ms, "
       f"{sum(v[0] for v in tot.values()) // REPS} kernels per run")
 for name, (n, us) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:40]:
     print(f"{us / 1000 / REPS:8.3f} ms {100 * us / 1000 / REPS / wall:5.1f}%  n={n // REPS:5d}  avg={us / n:8.1f} us  {name[:100]}")
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
