@@ -61,6 +61,7 @@ SIGNATURES = {
     "adm_pack_conv_weight": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     "adm_unpack_conv_wgrad": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "adm_cast_f32_bf16": (c_i, [c_p, c_p, c_ll, c_p]),
+    "adm_transpose_weight_tiles": (c_i, [c_p, c_p, c_p, c_i, c_p]),
     "adm_gn_stats": (c_i, [c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_ll, c_p, c_p, c_p]),
     "adm_gn_apply": (c_i, [c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_p, c_i, c_f, c_ull, c_p, c_i, c_p, c_ll,
                            c_p]),

@@ -293,6 +293,41 @@ __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __re
         o[i] = __float2bfloat16(v);
     }
 }
+// ------------------------------------------------------------------------------------------------ dgrad weight shadow
+// Batched 64 x 64 tile transpose of packed bf16 conv weights: [cout][tap][cin] -> [cin][ntaps-1-tap][cout], i.e. the
+// K-major operand of the DATA-gradient GEMM (dX = dY * W^T with the 3x3 taps mirrored), so that dgrad runs through
+// the fprop kernels.  One CTA per tile; `tiles` holds {src offset, dst offset, src row stride, dst row stride} in
+// elements for every tile of every conv (built once by the host), so ONE launch re-derives the shadow of a whole arena.
+__global__ void __launch_bounds__(256) transpose_tiles_kernel(const uint16_t* __restrict__ src,
+                                                              uint16_t* __restrict__ dst,
+                                                              const longlong4* __restrict__ tiles) {
+    __shared__ uint32_t t32[64 * 33];  // 64 rows of 66 bf16 (odd word pitch: the column gather below is 2-way at worst)
+    const longlong4 d = tiles[blockIdx.x];
+    const uint16_t* s = src + d.x;
+    uint16_t* o = dst + d.y;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int i = threadIdx.x + it * 256;
+        const int r = i >> 3, c = i & 7;
+        const uint4 v = *reinterpret_cast<const uint4*>(s + r * d.z + c * 8);
+        uint32_t* row = t32 + r * 33 + c * 4;
+        row[0] = v.x; row[1] = v.y; row[2] = v.z; row[3] = v.w;
+    }
+    __syncthreads();
+    const uint16_t* t16 = reinterpret_cast<const uint16_t*>(t32);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int i = threadIdx.x + it * 256;
+        const int r = i >> 3, c = i & 7;  // output row r (a source column), output chunk c (source rows 8c .. 8c+7)
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t lo = t16[(c * 8 + 2 * j) * 66 + r], hi = t16[(c * 8 + 2 * j + 1) * 66 + r];
+            w[j] = lo | (hi << 16);
+        }
+        *reinterpret_cast<uint4*>(o + r * d.w + c * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
 __global__ void __launch_bounds__(256) unpack_conv_wgrad_kernel(const float* __restrict__ g, float* __restrict__ o,
                                                                 int cout, int c1, int c2, int kk, int p1, int kpad,
                                                                 int accumulate, const int* __restrict__ row_perm) {
@@ -426,6 +461,18 @@ int adm_unpack_conv_wgrad(const float* dw_packed, float* dw, int cout, int c1, i
                                static_cast<cudaStream_t>(stream)>>>(dw_packed, dw, cout, c1, c2, ksize * ksize, p1,
                                                                     kpad, accumulate, row_perm);
     ADM_CHECK_LAUNCH("unpack_conv_wgrad");
+    return 0;
+}
+
+int adm_transpose_weight_tiles(const void* src, void* dst, const long long* tiles, int num_tiles, void* stream) {
+    if (num_tiles <= 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) {
+        set_error("transpose_weight_tiles: buffers must be 16 B aligned");
+        return ADM_ERR_SHAPE;
+    }
+    transpose_tiles_kernel<<<num_tiles, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), reinterpret_cast<const longlong4*>(tiles));
+    ADM_CHECK_LAUNCH("transpose_weight_tiles");
     return 0;
 }
 

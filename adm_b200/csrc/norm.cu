@@ -748,15 +748,20 @@ __global__ void __launch_bounds__(512, 1) gn_fwd_fused_kernel(
                     }
                 }
             }
-            for (; p < hw; p += step) {
-                const uint4 raw = *reinterpret_cast<const uint4*>(px);
-                px += stride;
-                const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+            if (p < hw) {  // remainder (< 8 pixels; the WHOLE sample at 8x8 / 4x4): predicated, still all loads in flight
+                uint4 raw[7];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const f32x2 t = bf2_to_f2(w[i]);
-                    s[i] = fadd2(s[i], t);
-                    q[i] = ffma2(t, t, q[i]);
+                for (int u = 0; u < 7; ++u)
+                    raw[u] = p + u * step < hw ? *reinterpret_cast<const uint4*>(px + u * stride) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int u = 0; u < 7; ++u) {
+                    const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const f32x2 t = bf2_to_f2(w[i]);
+                        s[i] = fadd2(s[i], t);
+                        q[i] = ffma2(t, t, q[i]);
+                    }
                 }
             }
         }

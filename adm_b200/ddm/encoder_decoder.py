@@ -9,9 +9,12 @@ training-only ``loss.*`` sub-module (LPIPS + PatchGAN, needs a VGG download) is 
 
 It is used frozen and without gradients (ddm_const_2.py:438-442, 494-503), so only the forward exists here: activations
 are NHWC bf16, every GroupNorm(32, eps 1e-6)+swish is the fused GroupNorm kernel, every 3x3 / 1x1 stride-1 conv is the
-tcgen05 implicit GEMM, nearest x2 is the resample kernel.  Left to library calls: the two stride-2 3x3 convs of the
-encoder (cuDNN on the channels-last view), the single-head mid attention over H*W <= 16384 tokens with d = 512
-(``scaled_dot_product_attention``) and the 1x1 (quant) convs on 3-6 channels.
+tcgen05 implicit GEMM, nearest x2 is the resample kernel.  The stride-2 3x3 convs of the encoder (:78-97: pad right /
+bottom by one, stride 2, no other padding) run through the same implicit-GEMM kernel: such a conv equals the pad-1
+stride-1 conv sampled at the odd pixels, o[i, j] = full[2i + 1, 2j + 1].  The single-head mid attention (:168-220,
+d = 512, H*W up to 4096 tokens) is q.k^T -> softmax kernel -> p.v on the tcgen05 batched GEMMs with the three 1x1
+projections fused into one conv; beyond 4096 tokens the N x N score matrix is not worth materialising and
+``scaled_dot_product_attention`` takes over.  Only the 1x1 (quant) convs on 3-6 channels stay ATen.
 """
 from __future__ import annotations
 
@@ -78,9 +81,14 @@ class Downsample(nn.Module):
     def forward(self, x):
         if not self.with_conv:
             return ops.resample(x, 1)  # 2x2 average
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            y = self.conv(F.pad(_nchw(x), (0, 1, 0, 1), mode="constant", value=0))
-        return _nhwc(y)
+        if x.shape[1] % 2 or x.shape[2] % 2:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = self.conv(F.pad(_nchw(x), (0, 1, 0, 1), mode="constant", value=0))
+            return _nhwc(y)
+        # pad (0, 1, 0, 1) + stride 2 + no padding reads rows 2i .. 2i+2: the window of the pad-1 stride-1 conv centred on
+        # the odd pixel (2i+1, 2j+1); its zero row / column beyond the image is the reference's explicit padding
+        full = AF.conv2d(x, self.conv.weight, self.conv.bias)
+        return full[:, 1::2, 1::2, :].contiguous()
 
 
 class ResnetBlock(nn.Module):
@@ -124,9 +132,16 @@ class AttnBlock(nn.Module):
     def forward(self, x):
         b, h, w, c = x.shape
         hn = self.norm(x, act=False)
-        q, k, v = (f(hn).reshape(b, 1, h * w, c) for f in (self.q, self.k, self.v))
-        a = F.scaled_dot_product_attention(q, k, v, scale=int(c) ** (-0.5))  # softmax(q k^T / sqrt(c)) v
-        return x + self.proj_out(a.reshape(b, h, w, c))
+        if h * w > 4096 or c % 64:
+            q, k, v = (f(hn).reshape(b, 1, h * w, c) for f in (self.q, self.k, self.v))
+            a = F.scaled_dot_product_attention(q, k, v, scale=int(c) ** (-0.5))  # softmax(q k^T / sqrt(c)) v
+            return x + self.proj_out(a.reshape(b, h, w, c))
+        # one conv for the three projections, output laid out (q | k | v) as the attention kernels read it
+        wqkv = torch.cat([self.q.weight, self.k.weight, self.v.weight], dim=0)
+        bqkv = torch.cat([self.q.bias, self.k.bias, self.v.bias], dim=0)
+        qkv = AF.conv2d(hn, wqkv, bqkv)
+        a, _ = ops.attention_fwd(qkv.contiguous(), 1, scale=int(c) ** (-0.5), need_p=False, fused=False)
+        return x + self.proj_out(a)
 
 
 def make_attn(in_channels, attn_type="vanilla"):

@@ -166,6 +166,27 @@ def cast_bf16_into(src, dst):
     return dst
 
 
+def weight_transpose_tiles(offset, cout, ntaps, cin):
+    """Tile table (host int64 [tiles, 4]) of adm_transpose_weight_tiles for ONE conv whose packed bf16 weights
+    [cout][ntaps][cin] start `offset` elements into the source buffer; the transposed, tap-mirrored copy
+    [cin][ntaps][cout] goes to the same offset of the destination buffer.  cout, cin multiples of 64."""
+    assert cout % 64 == 0 and cin % 64 == 0
+    cot, t, cit = torch.meshgrid(torch.arange(cout // 64), torch.arange(ntaps), torch.arange(cin // 64), indexing="ij")
+    src = offset + (cot * 64 * ntaps + t) * cin + cit * 64
+    dst = offset + (cit * 64 * ntaps + (ntaps - 1 - t)) * cout + cot * 64
+    return torch.stack([src, dst, torch.full_like(src, ntaps * cin), torch.full_like(src, ntaps * cout)],
+                       dim=-1).reshape(-1, 4).to(torch.int64)
+
+
+def transpose_weight_tiles(src, dst, tiles):
+    """dst <- per-conv transposed / tap-mirrored copy of the packed bf16 weights in src (see weight_transpose_tiles)."""
+    _need_cuda(src, dst, tiles)
+    assert src.dtype == BF16 and dst.dtype == BF16 and tiles.dtype == torch.int64 and tiles.is_contiguous()
+    check(_lib.load().adm_transpose_weight_tiles(_ptr(src), _ptr(dst), _ptr(tiles), tiles.shape[0], _stream()),
+          "transpose_weight_tiles")
+    return dst
+
+
 def stats_ok(h, w):
     """Image sizes for which the conv epilogue can emit GroupNorm statistics (see adm_conv_fprop_stats)."""
     return h * w in (16, 64) or (h * w) % 128 == 0

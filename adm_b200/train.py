@@ -71,7 +71,10 @@ class ParamArena:
         order of the GEMM engine.  They keep their logical (reference) shape as a permuted view, so state_dict /
         load_state_dict are unaffected, and on CUDA they get a bf16 shadow (written by the fused AdamW kernel) plus a
         packed view of their gradient: ``p._adm_pack = (bf16 [Cout, k*k, Cin], fp32 grad [Cout, k*k, Cin], version,
-        fp32 flat slice)``."""
+        fp32 flat slice, bf16 [Cin, k*k, Cout] or None)``.  The last entry is the DGRAD shadow: the same weights
+        transposed with the taps mirrored (Cout a multiple of 64), re-derived from the bf16 shadow by ONE batched tile
+        transpose per optimizer step, so the data gradient of a conv runs through the fprop kernels on a K-major
+        operand instead of the slower MN-major view of the fprop-packed weights (ADM_DGRAD_SHADOW=0 disables)."""
         params = order if order is not None else list(module.parameters())
         dev = params[0].device
         cl = {id(p) for p in channels_last}
@@ -85,6 +88,10 @@ class ParamArena:
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
         self.grads = torch.zeros(total, device=dev, dtype=torch.float32)
         self.shadow = torch.zeros(total, device=dev, dtype=torch.bfloat16) if (cl and dev.type == "cuda") else None
+        want_t = self.shadow is not None and os.environ.get("ADM_DGRAD_SHADOW", "1") != "0"
+        self.shadow_t = torch.zeros(total, device=dev, dtype=torch.bfloat16) if want_t else None
+        self.t_tiles = None
+        tiles = []
         self._grad_views = []
         for p, o in zip(params, offs):
             n = p.numel()
@@ -100,18 +107,30 @@ class ParamArena:
             p.grad = gview
             self._grad_views.append(gview)
             if id(p) in cl and self.shadow is not None:
+                wt = None
+                if self.shadow_t is not None and co % 64 == 0 and ci % 64 == 0 and o % 8 == 0:
+                    wt = self.shadow_t[o:o + n].view(ci, kh * kw, co)
+                    tiles.append(ops.weight_transpose_tiles(o, co, kh * kw, ci))
                 p._adm_pack = (self.shadow[o:o + n].view(co, kh * kw, ci), self.grads[o:o + n].view(co, kh * kw, ci),
-                               p._version, self.flat[o:o + n])
+                               p._version, self.flat[o:o + n], wt)
+        if tiles:
+            self.t_tiles = torch.cat(tiles).to(dev)
         self.refresh_shadow()
 
     def refresh_shadow(self):
         """Re-derive the bf16 shadow from the fp32 masters (after construction or an out-of-band parameter write)."""
         if self.shadow is not None:
             ops.cast_bf16_into(self.flat, self.shadow)
+            self.refresh_dgrad_shadow()
             for p in self.params:
                 pk = getattr(p, "_adm_pack", None)
                 if pk is not None:
-                    p._adm_pack = (pk[0], pk[1], p._version, pk[3])
+                    p._adm_pack = (pk[0], pk[1], p._version, pk[3], pk[4])
+
+    def refresh_dgrad_shadow(self):
+        """shadow_t <- transposed / tap-mirrored bf16 shadow of every conv that has one (one kernel launch)."""
+        if self.t_tiles is not None:
+            ops.transpose_weight_tiles(self.shadow, self.shadow_t, self.t_tiles)
 
     def slice_of(self, params):
         """(offset, numel) of a run of parameters that sit back to back in the arena, else None."""
@@ -419,6 +438,7 @@ class TrainStep:
                 ops.adamw(a.flat, a.grads, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
                           max(1, self.step_count), grad_scale=gscale, max_norm=self.max_grad_norm, sqnorm=self.sqnorm,
                           hyper_dev=self.hyper, p_bf16=a.shadow)
+                a.refresh_dgrad_shadow()
                 a.zero_grad()
                 self.engine.invalidate()
                 self._seg_capture["graph"].capture_end()
@@ -458,6 +478,7 @@ class TrainStep:
         ops.adamw(a.flat, a.grads, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
                   max(1, self.step_count), grad_scale=gscale, max_norm=self.max_grad_norm, sqnorm=self.sqnorm,
                   hyper_dev=self.hyper, p_bf16=a.shadow)
+        a.refresh_dgrad_shadow()
         a.zero_grad()
         self.engine.invalidate()
 

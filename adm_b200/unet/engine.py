@@ -112,7 +112,11 @@ class UNetEngine:
             return None
         if w._version != pk[2]:  # modified through torch (load_state_dict, ...) since the shadow was written
             ops.cast_bf16_into(pk[3], pk[0])
-            w._adm_pack = pk = (pk[0], pk[1], w._version, pk[3])
+            if pk[4] is not None:  # and its transposed twin for the data gradient
+                co, kk, ci = pk[0].shape
+                tiles = ops.weight_transpose_tiles(0, co, kk, ci).to(pk[0].device)
+                ops.transpose_weight_tiles(pk[0], pk[4], tiles)
+            w._adm_pack = pk = (pk[0], pk[1], w._version, pk[3], pk[4])
         return pk
 
     # ------------------------------------------------------------------------------------------ weight caches
@@ -285,6 +289,10 @@ class UNetEngine:
         whose first part is not a multiple of 64 is re-joined)."""
         cin = conv.weight.shape[1]
         c1 = cin if c1 is None else c1
+        pk = self._pack_of(conv.weight)
+        if pk is not None and pk[4] is not None and pk[0].data_ptr() == wpk.data_ptr():
+            # arena-resident conv: dX = fprop(dY, W^T with mirrored taps) on the K-major dgrad shadow
+            return ops.conv_fprop(dy, pk[4], residual=residual)
         if c2 and c1 % 64:
             full = ops.conv_dgrad(dy, wpk, residual=residual)
             p1 = pad64(c1)

@@ -152,6 +152,12 @@ int adm_pack_conv_weight(const float* w, void* wpk, int cout, int c1, int c2, in
 int adm_unpack_conv_wgrad(const float* dw_packed, float* dw, int cout, int c1, int c2, int ksize, int accumulate,
                           const int* row_perm, void* stream);
 int adm_cast_f32_bf16(const float* src, void* dst, long long numel, void* stream);
+/* dgrad shadow: batched 64 x 64 tile transpose of packed bf16 weights, [cout][tap][cin] -> [cin][ntaps-1-tap][cout]
+ * (the flipped, transposed kernel of conv2d's data gradient — what autograd derives for F.conv2d,
+ * unet/uncond_unet.py:100,110), so the data gradient runs through adm_conv_fprop.  tiles: device array of
+ * num_tiles x {src offset, dst offset, src row stride, dst row stride} (elements, all multiples of 8); one launch
+ * covers every conv of a parameter arena.                                                                    */
+int adm_transpose_weight_tiles(const void* src, void* dst, const long long* tiles, int num_tiles, void* stream);
 
 /* ---------------------------------------------------------------- GroupNorm family (NHWC bf16, HBM-bound)
  * Replaces torch.nn.functional.group_norm (unet/uncond_unet.py:128) and the elementwise chain around it in

@@ -178,6 +178,51 @@ def conv_dgrad_wgrad():
 
 
 @case
+def conv_dgrad_shadow():
+    """Data gradient through the FPROP kernels on the transposed, tap-mirrored bf16 weight shadow
+    (adm_transpose_weight_tiles, one batched launch for several convs) vs autograd and vs the MN-major dgrad path."""
+    import torch
+    import torch.nn.functional as F
+    from adm_b200 import ops
+    torch.manual_seed(14)
+    ok = True
+    shapes = [(4, 16, 128, 192, 3), (8, 8, 384, 384, 3), (16, 4, 768, 384, 3), (2, 32, 192, 64, 1), (3, 32, 192, 192, 3)]
+    # all convs live in ONE flat buffer, as in the parameter arena
+    offs, total = [], 0
+    for (_, _, cin, cout, k) in shapes:
+        offs.append(total)
+        total += cout * k * k * cin
+    src = torch.zeros(total, device="cuda", dtype=torch.bfloat16)
+    dst = torch.full((total,), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ws = []
+    for o, (_, _, cin, cout, k) in zip(offs, shapes):
+        w = _bf(torch.randn(cout, cin, k, k, device="cuda") / (k * cin ** 0.5)).float()
+        ws.append(w)
+        ops.pack_conv_weight(w, out=src[o:o + w.numel()].view(cout, k * k, cin))
+    tiles = torch.cat([ops.weight_transpose_tiles(o, cout, k * k, cin) for o, (_, _, cin, cout, k) in zip(offs, shapes)])
+    ops.transpose_weight_tiles(src, dst, tiles.cuda())
+    torch.cuda.synchronize()
+    ok &= bool(torch.isfinite(dst.float()).all())
+    for o, w, (n, hw, cin, cout, k) in zip(offs, ws, shapes):
+        wpk = src[o:o + w.numel()].view(cout, k * k, cin)
+        wt = dst[o:o + w.numel()].view(cin, k * k, cout)
+        ref_t = wpk.flip(1).permute(2, 1, 0)
+        exact = torch.equal(wt, ref_t)
+        print(f"  transpose {cin}->{cout} k{k}: {'bit-exact' if exact else 'MISMATCH'}", flush=True)
+        ok &= exact
+        dy = _bf(torch.randn(n, hw, hw, cout, device="cuda"))
+        res = _bf(torch.randn(n, hw, hw, cin, device="cuda"))
+        xr = torch.zeros(n, cin, hw, hw, device="cuda", requires_grad=True)
+        F.conv2d(xr, w, padding=k // 2).backward(dy.float().permute(0, 3, 1, 2))
+        dx = ops.conv_fprop(dy, wt, residual=res)
+        dx_old = ops.conv_dgrad(dy, wpk, n_valid=cin, residual=res)
+        torch.cuda.synchronize()
+        ok &= _report(f"dgrad(shadow) n{n} {hw} {cin}<-{cout} k{k}", dx.float() - res.float(), xr.grad.permute(0, 2, 3, 1), 1e-2)
+        ok &= _report(f"  vs MN-major dgrad", dx, dx_old, 2e-3)
+    return ok
+
+
+@case
 def elementwise():
     import torch
     from adm_b200 import ops

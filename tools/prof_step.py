@@ -63,6 +63,25 @@ print(f"{mode} B={B} ranks={world}: wall {wall:.2f} ms per run (under the profil
       f"{sum(v[0] for v in tot.values()) // REPS} kernels per run")
 for name, (n, us) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:40]:
     print(f"{us / 1000 / REPS:8.3f} ms {100 * us / 1000 / REPS / wall:5.1f}%  n={n // REPS:5d}  avg={us / n:8.1f} us  {name[:100]}")
+# ADM_PROF_TIMELINE=path: every kernel of the LAST profiled run in start order — start (us from the first kernel), duration,
+# gap to the end of the previous kernel on the same stream, stream, name — to see where a latency-bound chain waits
+tl = os.environ.get("ADM_PROF_TIMELINE")
+if tl:
+    evs = []
+    for ev in prof.events():
+        if ev.device_type == torch.autograd.DeviceType.CUDA:
+            dur = ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total
+            evs.append((ev.time_range.start, dur, getattr(ev, "device_resource_id", -1), ev.name.split("(")[0]))
+    evs.sort()
+    evs = evs[len(evs) - len(evs) // REPS:]
+    t0 = evs[0][0]
+    last_end = {}
+    with open(tl, "w") as f:
+        for st, dur, stream, name in evs:
+            gap = st - last_end.get(stream, st)
+            last_end[stream] = st + dur
+            short = name.replace("void ", "").replace("adm::", "")[:60]
+            f.write(f"{st - t0:10.1f} {dur:8.1f} gap {gap:7.1f} s{stream} {short}\n")
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
