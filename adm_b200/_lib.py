@@ -62,6 +62,9 @@ SIGNATURES = {
     "adm_unpack_conv_wgrad": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "adm_cast_f32_bf16": (c_i, [c_p, c_p, c_ll, c_p]),
     "adm_transpose_weight_tiles": (c_i, [c_p, c_p, c_p, c_i, c_p]),
+    "adm_gather_rows": (c_i, [c_p, c_p, c_p, c_ll, c_i, c_p]),
+    "adm_conv_wgrad_mapped": (c_i, [c_p, c_i, c_ll, c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "adm_col_sums_mapped": (c_i, [c_p, c_ll, c_ll, c_i, c_p, c_p, c_p]),
     "adm_gn_stats": (c_i, [c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_ll, c_p, c_p, c_p]),
     "adm_gn_apply": (c_i, [c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_p, c_i, c_f, c_ull, c_p, c_i, c_p, c_ll,
                            c_p]),

@@ -293,6 +293,22 @@ __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __re
         o[i] = __float2bfloat16(v);
     }
 }
+// Batched row gather: row i of the table copies `row_bytes` bytes from src + table[i].x to dst + table[i].y (byte offsets).
+// Re-derives, in ONE launch per optimizer step, every operand that is a row permutation of arena-resident parameters:
+// the qkv projections stored as (q | k | v) x head x d instead of the reference's interleaved (head, d, {q,k,v}) rows.
+template <typename T>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                          const longlong2* __restrict__ table, long long n_rows,
+                                                          int units) {  // units of sizeof(T) per row
+    const long long total = n_rows * units;
+    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+        const long long r = i / units;
+        const int u = static_cast<int>(i - r * units);
+        const longlong2 t = table[r];
+        reinterpret_cast<T*>(dst + t.y)[u] = reinterpret_cast<const T*>(src + t.x)[u];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ dgrad weight shadow
 // Batched 64 x 64 tile transpose of packed bf16 conv weights: [cout][tap][cin] -> [cin][ntaps-1-tap][cout], i.e. the
 // K-major operand of the DATA-gradient GEMM (dX = dY * W^T with the 3x3 taps mirrored), so that dgrad runs through
@@ -461,6 +477,23 @@ int adm_unpack_conv_wgrad(const float* dw_packed, float* dw, int cout, int c1, i
                                static_cast<cudaStream_t>(stream)>>>(dw_packed, dw, cout, c1, c2, ksize * ksize, p1,
                                                                     kpad, accumulate, row_perm);
     ADM_CHECK_LAUNCH("unpack_conv_wgrad");
+    return 0;
+}
+
+int adm_gather_rows(const void* src, void* dst, const long long* table, long long n_rows, int row_bytes,
+                    void* stream) {
+    if (n_rows <= 0) return 0;
+    if (row_bytes <= 0 || row_bytes % 4) { set_error("gather_rows: row_bytes must be a positive multiple of 4"); return ADM_ERR_SHAPE; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint8_t* sp = static_cast<const uint8_t*>(src);
+    uint8_t* dp = static_cast<uint8_t*>(dst);
+    const longlong2* tb = reinterpret_cast<const longlong2*>(table);
+    // 16 B units need 16 B aligned offsets: the caller guarantees that whenever row_bytes is a multiple of 16
+    if (row_bytes % 16 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0)
+        gather_rows_kernel<uint4><<<ew_grid(n_rows * (row_bytes / 16), 256, 8), 256, 0, s>>>(sp, dp, tb, n_rows, row_bytes / 16);
+    else
+        gather_rows_kernel<uint32_t><<<ew_grid(n_rows * (row_bytes / 4), 256, 8), 256, 0, s>>>(sp, dp, tb, n_rows, row_bytes / 4);
+    ADM_CHECK_LAUNCH("gather_rows");
     return 0;
 }
 

@@ -581,7 +581,14 @@ int adm_conv_dgrad(const void* dy, int cout, long long ld_dy, int n, int h, int 
 
 int adm_conv_wgrad(const void* dy, int cout, long long ld_dy, const void* x1, int c1, long long ld1, const void* x2,
                    int c2, long long ld2, int n, int h, int w, int ntaps, float* dw, void* stream) {
+    return adm_conv_wgrad_mapped(dy, cout, ld_dy, x1, c1, ld1, x2, c2, ld2, n, h, w, ntaps, nullptr, dw, stream);
+}
+
+int adm_conv_wgrad_mapped(const void* dy, int cout, long long ld_dy, const void* x1, int c1, long long ld1,
+                          const void* x2, int c2, long long ld2, int n, int h, int w, int ntaps, const int* row_map,
+                          float* dw, void* stream) {
     if (int e = init_driver()) return e;
+    if (row_map != nullptr && ntaps != 1) { set_error("conv_wgrad: a row map is supported for 1x1 convs only"); return ADM_ERR_SHAPE; }
     if (ntaps != 1 && ntaps != 9) { set_error("conv_wgrad: ntaps must be 1 or 9"); return ADM_ERR_SHAPE; }
     GemmParams p;
     init_params(&p);
@@ -621,6 +628,7 @@ int adm_conv_wgrad(const void* dy, int cout, long long ld_dy, const void* x1, in
     p.a_mn = 1; p.b_mn = 1;
     pick_wgrad_split(&p, ntaps * p.m_tiles * p.n_tiles, 6);  // epilogue ~ 6 k-iterations (fp32 vector atomics)
     p.C = dw; p.ldc = 1LL * ntaps * kpad; p.out_mode = OUT_F32_ATOMIC;
+    p.row_map = row_map;
     (void)pixels;
     CUtensorMap ma, mb, mb2;
     if (int e = nhwc_map(&ma, dy, cout, ld_dy, n, h, w, p.bw, p.bh, p.bni)) return e;

@@ -71,6 +71,7 @@ struct GemmParams {
     long long ldr;
     float alpha;
     int out_mode;
+    const int* row_map;  // plain / wgrad tiles: GEMM row r is stored at output row row_map[r] (nullptr = identity)
     int debug;  // experiments only (ADM_GEMM_DEBUG): bit 0 = skip the MMAs, bit 1 = skip the TMA loads
     // ---- GroupNorm statistics of the OUTPUT, emitted by the conv epilogue: per (sample, slot, channel)
     // partial {sum, sum of squares} over the pixels one epilogue warp (or half-warp, 4x4 images) holds, plain stores into
@@ -347,7 +348,7 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, uint8_t* sme
         } else {
             const int row = mt * 128 + m;
             row_ok = row < p.M;
-            row_off = row;
+            row_off = (p.row_map != nullptr && row_ok) ? __ldg(p.row_map + row) : row;
         }
         const long long c_base = b_hi * p.c_bhi + b_lo * p.c_blo + row_off * p.ldc;
         const int col_base = nt * p.bn;           // column inside [0, N)

@@ -48,6 +48,7 @@ def _detached_copy(model):
             e.grad_hook, e.affine_pack, e._cache, e.seed_counter = h, a, c, s
     for p in new.parameters():
         p.__dict__.pop("_adm_pack", None)
+        p.__dict__.pop("_adm_qkv", None)
         p.grad = None
     return new
 

@@ -277,8 +277,9 @@ def conv_dgrad(dy, wpk, n_valid=None, residual=None, alpha=1.0, out=None):
     return out[..., :n_valid] if out.shape[-1] != n_valid else out
 
 
-def conv_wgrad(dy, x1, x2=None, ntaps=9, out=None):
-    """Packed weight gradient fp32 [cout, taps, kpad] (accumulated into `out` when given)."""
+def conv_wgrad(dy, x1, x2=None, ntaps=9, out=None, row_map=None):
+    """Packed weight gradient fp32 [cout, taps, kpad] (accumulated into `out` when given).
+    row_map (1x1 convs; device int32 [cout]): the gradient of executed output channel r goes to row row_map[r] of `out`."""
     _need_cuda(dy, x1)
     pd, cout, ldd, n, h, w = _nhwc(dy)
     p1, c1, ld1, n1, h1, w1 = _nhwc(x1)
@@ -289,6 +290,11 @@ def conv_wgrad(dy, x1, x2=None, ntaps=9, out=None):
     kpad = pad64(c1) + (pad64(c2) if x2 is not None else 0)
     if out is None:
         out = torch.zeros(cout, ntaps, kpad, device=dy.device, dtype=F32)
+    if row_map is not None:
+        assert row_map.dtype == torch.int32 and row_map.numel() == cout and row_map.is_cuda
+        check(_lib.load().adm_conv_wgrad_mapped(pd, cout, ldd, p1, c1, ld1, p2, c2, ld2, n, h, w, ntaps, _ptr(row_map),
+                                                _ptr(out), _stream()), "conv_wgrad_mapped")
+        return out
     check(_lib.load().adm_conv_wgrad(pd, cout, ldd, p1, c1, ld1, p2, c2, ld2, n, h, w, ntaps, _ptr(out), _stream()),
           "conv_wgrad")
     return out
@@ -465,12 +471,27 @@ def gn_bwd(dy, x1, x2, coef, gamma, beta, groups, params=None, act=True, drop_p=
     return dx1, dx2
 
 
-def col_sums(x, out):
-    """out[c] += sum over rows of x[..., c]; x bf16 with contiguous last dim and uniform row stride."""
+def col_sums(x, out, out_map=None):
+    """out[c] += sum over rows of x[..., c]; x bf16 with contiguous last dim and uniform row stride.
+    out_map (device int32 [c]): column c is accumulated into out[out_map[c]] instead."""
     c = x.shape[-1]
     rows = x.numel() // c
+    if out_map is not None:
+        assert out_map.dtype == torch.int32 and out_map.numel() == c and out_map.is_cuda
+        check(_lib.load().adm_col_sums_mapped(_ptr(x), x.stride(-2), rows, c, _ptr(out), _ptr(out_map), _stream()),
+              "col_sums_mapped")
+        return out
     check(_lib.load().adm_col_sums(_ptr(x), x.stride(-2), rows, c, _ptr(out), _stream()), "col_sums")
     return out
+
+
+def gather_rows(src, dst, table, row_bytes):
+    """For every row i of table (device int64 [rows, 2], BYTE offsets): dst[table[i,1] : +row_bytes] = src[table[i,0] : ...]."""
+    _need_cuda(src, dst, table)
+    assert table.dtype == torch.int64 and table.is_contiguous() and table.shape[1] == 2
+    check(_lib.load().adm_gather_rows(_ptr(src), _ptr(dst), _ptr(table), table.shape[0], int(row_bytes), _stream()),
+          "gather_rows")
+    return dst
 
 
 def resample(x, mode):

@@ -177,6 +177,7 @@ class TrainStep:
         self.pg = process_group
         self.arena = ParamArena(self.net, completion_order(self.net), channels_last=self.engine.packable_params())
         self._bind_affine()
+        self._bind_qkv()
         self.m = torch.zeros_like(self.arena.flat)
         self.v = torch.zeros_like(self.arena.flat)
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
@@ -226,9 +227,53 @@ class TrainStep:
                            a.grads[ws[0]:ws[0] + ws[1]].view(t, emb), a.grads[bs[0]:bs[0] + t],
                            a.flat[ws[0]:ws[0] + ws[1]], tuple(m.weight._version for m in mods))
 
+    def _bind_qkv(self):
+        """The qkv projections run in (q | k | v) x head x d row order (the reference interleaves (head, d, {q,k,v}),
+        unet/uncond_unet.py:205).  Instead of re-packing 24 weights and biases every step, keep ONE bf16 buffer with all of
+        them in executed order plus a byte-offset table, and re-derive it from the arena's bf16 shadow (weights) and fp32
+        masters (biases) with two batched row-gather launches per optimizer step (ADM_QKV_GATHER=0 disables)."""
+        a, eng = self.arena, self.engine
+        self._qkv = None
+        if a.shadow is None or os.environ.get("ADM_QKV_GATHER", "1") == "0":
+            return
+        off = {id(p): o for p, o in zip(a.params, a.offsets)}
+        blocks = [m for _, m, _ in eng.block_list
+                  if m.num_heads and m.out_channels % 64 == 0 and (m.out_channels // m.num_heads) % 64 == 0
+                  and id(m.qkv.weight) in off and id(m.qkv.bias) in off]
+        if not blocks or len({m.out_channels for m in blocks}) != 1:
+            return
+        c = blocks[0].out_channels
+        dev = a.flat.device
+        wbuf = torch.empty(len(blocks) * 3 * c * c, device=dev, dtype=torch.bfloat16)
+        bbuf = torch.empty(len(blocks) * 3 * c, device=dev, dtype=torch.float32)
+        wt, bt = [], []
+        for i, m in enumerate(blocks):
+            perm = eng.qkv_perm(c, m.num_heads)[1].cpu()  # executed row r holds reference row perm[r]
+            r = torch.arange(3 * c)
+            wt.append(torch.stack([(off[id(m.qkv.weight)] + perm * c) * 2, (i * 3 * c * c + r * c) * 2], dim=1))
+            bt.append(torch.stack([(off[id(m.qkv.bias)] + perm) * 4, (i * 3 * c + r) * 4], dim=1))
+            w, b = m.qkv.weight, m.qkv.bias
+            w._adm_qkv = (wbuf[i * 3 * c * c:(i + 1) * 3 * c * c].view(3 * c, 1, c), bbuf[i * 3 * c:(i + 1) * 3 * c],
+                          (w._version, b._version))
+        self._qkv = (wbuf, bbuf, torch.cat(wt).to(torch.int64).contiguous().to(dev),
+                     torch.cat(bt).to(torch.int64).contiguous().to(dev), c, blocks)
+
+    def refresh_derived(self):
+        """Operands derived from the arena once per optimizer step: the transposed dgrad shadow and the qkv packs."""
+        a = self.arena
+        a.refresh_dgrad_shadow()
+        if self._qkv is not None:
+            wbuf, bbuf, wtab, btab, c, blocks = self._qkv
+            ops.gather_rows(a.shadow, wbuf, wtab, 2 * c)
+            ops.gather_rows(a.flat, bbuf, btab, 4)
+            for m in blocks:
+                w, b = m.qkv.weight, m.qkv.bias
+                w._adm_qkv = (w._adm_qkv[0], w._adm_qkv[1], (w._version, b._version))
+
     def refresh(self):
         """Call after parameters were written outside the fused optimizer (load_state_dict, manual edits)."""
         self.arena.refresh_shadow()
+        self.refresh_derived()
         self.engine.invalidate()
 
     def sync_params(self, src=0, moments=True):
@@ -438,7 +483,7 @@ class TrainStep:
                 ops.adamw(a.flat, a.grads, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
                           max(1, self.step_count), grad_scale=gscale, max_norm=self.max_grad_norm, sqnorm=self.sqnorm,
                           hyper_dev=self.hyper, p_bf16=a.shadow)
-                a.refresh_dgrad_shadow()
+                self.refresh_derived()
                 a.zero_grad()
                 self.engine.invalidate()
                 self._seg_capture["graph"].capture_end()
@@ -478,7 +523,7 @@ class TrainStep:
         ops.adamw(a.flat, a.grads, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
                   max(1, self.step_count), grad_scale=gscale, max_norm=self.max_grad_norm, sqnorm=self.sqnorm,
                   hyper_dev=self.hyper, p_bf16=a.shadow)
-        a.refresh_dgrad_shadow()
+        self.refresh_derived()
         a.zero_grad()
         self.engine.invalidate()
 

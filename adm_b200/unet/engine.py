@@ -119,6 +119,21 @@ class UNetEngine:
             w._adm_pack = pk = (pk[0], pk[1], w._version, pk[3], pk[4])
         return pk
 
+    @staticmethod
+    def _qkv_pack_of(blk, perm):
+        """(bf16 [3C, 1, C] weights, fp32 [3C] bias) of an attention block in the executed (q | k | v) x head x d row order
+        when a parameter arena keeps them (``qkv.weight._adm_qkv``, re-derived by ONE batched row gather per optimizer step,
+        adm_b200.train.ParamArena), else None."""
+        qp = getattr(blk.qkv.weight, "_adm_qkv", None)
+        if qp is None:
+            return None
+        w, b = blk.qkv.weight, blk.qkv.bias
+        if (w._version, b._version) != qp[2]:  # written through torch since the last gather (load_state_dict, ...)
+            ops.pack_conv_weight(w.detach().contiguous(), row_perm=perm[0], out=qp[0])
+            torch.index_select(b.detach(), 0, perm[1], out=qp[1])
+            w._adm_qkv = qp = (qp[0], qp[1], (w._version, b._version))
+        return qp[0], qp[1]
+
     # ------------------------------------------------------------------------------------------ weight caches
     def invalidate(self):
         """Call after parameters were updated through raw pointers (the fused optimizer)."""
@@ -264,6 +279,11 @@ class UNetEngine:
         if pk is not None and conv.weight.grad is not None and conv.weight.grad.data_ptr() == pk[1].data_ptr():
             ops.conv_wgrad(dy, x1, x2=x2, ntaps=k * k, out=pk[1])  # straight into the (channels-last) gradient arena
             return
+        g = self._grad(conv.weight)
+        if perm is not None and k == 1 and x2 is None and c1 == cin_ref and c1 % 64 == 0 and g.is_contiguous():
+            # row-permuted 1x1 conv (qkv): the wgrad epilogue scatters its rows into the reference-ordered gradient
+            ops.conv_wgrad(dy, x1, ntaps=1, out=g.view(g.shape[0], 1, c1), row_map=perm[0])
+            return
         dwp = ops.conv_wgrad(dy, x1, x2=x2, ntaps=k * k)
         if x2 is None and c1 != cin_ref:  # zero-padded network input (3 -> 8 channels)
             c1 = cin_ref
@@ -275,6 +295,8 @@ class UNetEngine:
         c = dy.shape[-1]
         if perm is None and c == g.numel():
             ops.col_sums(dy, g)
+        elif perm is not None and c == g.numel() and g.is_contiguous():
+            ops.col_sums(dy, g, out_map=perm[0])
         else:
             tmp = torch.zeros(c, device=dy.device, dtype=F32)
             ops.col_sums(dy, tmp)
@@ -406,10 +428,15 @@ class UNetEngine:
                 out, st_out = self._conv_stats(c.att, self.proj_padded(blk), bias=blk.proj.bias, residual=c.h1)
             else:
                 perm = self.qkv_perm(cout, blk.num_heads)
-                bq = self._cached(("qkvb", id(blk)), [blk.qkv.bias],
-                                  lambda old: blk.qkv.bias.detach()[perm[1]].contiguous() if old is None
-                                  else torch.index_select(blk.qkv.bias.detach(), 0, perm[1], out=old))
-                c.qkv = ops.conv_fprop(c.a2, self.conv_w(blk.qkv, perm=perm[0]), bias=bq)
+                qp = self._qkv_pack_of(blk, perm)
+                if qp is not None:  # arena: (q | k | v)-ordered weights / bias re-derived by one batched gather per step
+                    wq, bq = qp
+                else:
+                    bq = self._cached(("qkvb", id(blk)), [blk.qkv.bias],
+                                      lambda old: blk.qkv.bias.detach()[perm[1]].contiguous() if old is None
+                                      else torch.index_select(blk.qkv.bias.detach(), 0, perm[1], out=old))
+                    wq = self.conv_w(blk.qkv, perm=perm[0])
+                c.qkv = ops.conv_fprop(c.a2, wq, bias=bq)
                 c.att, c.p = ops.attention_fwd(c.qkv, blk.num_heads, need_p=save is not None)
                 out, st_out = self._conv_stats(c.att, self.conv_w(blk.proj), bias=blk.proj.bias, residual=c.h1)
         if save is not None:
@@ -480,7 +507,8 @@ class UNetEngine:
             datt = self._dgrad(dout, blk.proj, self.conv_w(blk.proj))
             dqkv = ops.attention_bwd(datt, c.qkv, c.p, blk.num_heads, a=c.att)
             self._conv_param_grads(blk.qkv, dqkv, c.a2, perm=perm)
-            da2 = self._dgrad(dqkv, blk.qkv, self.conv_w(blk.qkv, perm=perm[0]))
+            qp = self._qkv_pack_of(blk, perm)
+            da2 = self._dgrad(dqkv, blk.qkv, qp[0] if qp is not None else self.conv_w(blk.qkv, perm=perm[0]))
         if blk.num_heads:
             dh1, _ = ops.gn_bwd(da2, c.h1, None, c.sums2, blk.norm2.weight, blk.norm2.bias, _groups(cout),
                                 act=False, dgamma=self._grad(blk.norm2.weight),

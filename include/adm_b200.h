@@ -113,6 +113,12 @@ int adm_conv_dgrad(const void* dy, int cout, long long ld_dy, int n, int h, int 
 /* weight gradient, accumulated (atomic fp32) into dw [cout][ntaps][kpad] (packed layout, zero it first). */
 int adm_conv_wgrad(const void* dy, int cout, long long ld_dy, const void* x1, int c1, long long ld1, const void* x2,
                    int c2, long long ld2, int n, int h, int w, int ntaps, float* dw, void* stream);
+/* same, 1x1 convs only, with an output row map: the gradient of GEMM row r (output channel r of the conv as it is
+ * executed) is accumulated into dw row row_map[r] — lets the qkv projection, executed in (q | k | v) x head x d row order,
+ * write its weight gradient straight into the reference-ordered gradient (unet/uncond_unet.py:205).           */
+int adm_conv_wgrad_mapped(const void* dy, int cout, long long ld_dy, const void* x1, int c1, long long ld1,
+                          const void* x2, int c2, long long ld2, int n, int h, int w, int ntaps, const int* row_map,
+                          float* dw, void* stream);
 
 /* Generic batched GEMM C[b] = alpha * A[b] * B[b]^T (+bias, +residual) on 3-D bf16 tensor views.  Used for Linear
  * (unet/uncond_unet.py:62-66), and the attention products (:207-208).  An operand is K-major (dim0 = K) or MN-major
@@ -158,6 +164,11 @@ int adm_cast_f32_bf16(const float* src, void* dst, long long numel, void* stream
  * num_tiles x {src offset, dst offset, src row stride, dst row stride} (elements, all multiples of 8); one launch
  * covers every conv of a parameter arena.                                                                    */
 int adm_transpose_weight_tiles(const void* src, void* dst, const long long* tiles, int num_tiles, void* stream);
+/* batched row gather: for i < n_rows copy row_bytes bytes from src + table[2i] to dst + table[2i+1] (byte offsets,
+ * multiples of 4; of 16 when row_bytes is).  One launch per optimizer step re-derives every operand that is a row
+ * permutation of arena-resident parameters (the qkv projections in (q | k | v) x head x d row order).        */
+int adm_gather_rows(const void* src, void* dst, const long long* table, long long n_rows, int row_bytes,
+                    void* stream);
 
 /* ---------------------------------------------------------------- GroupNorm family (NHWC bf16, HBM-bound)
  * Replaces torch.nn.functional.group_norm (unet/uncond_unet.py:128) and the elementwise chain around it in
@@ -209,6 +220,9 @@ int adm_gn_forward(const void* x1, int c1, long long ld1, const void* x2, int c2
                    const unsigned long long* seed_counter, int resample, void* out, long long ldo, void* stream);
 /* out[c] += sum_rows x[row][c] (bias gradients, unet/uncond_unet.py:111-112 backward). */
 int adm_col_sums(const void* x, long long ld, long long rows, int c, float* out, void* stream);
+/* out[out_map[c]] += sum_rows x[row][c] (out_map: device int[c], or NULL = identity) */
+int adm_col_sums_mapped(const void* x, long long ld, long long rows, int c, float* out, const int* out_map,
+                        void* stream);
 /* out = a + b (+ c): gradient fan-in of the skip connections (torch autograd's implicit adds, unet/uncond_unet.py:563-564) */
 int adm_add_bf16(const void* a, long long lda, const void* b, long long ldb, const void* c, long long ldc, void* out,
                  long long ldo, long long rows, int ch, void* stream);

@@ -223,6 +223,61 @@ def conv_dgrad_shadow():
 
 
 @case
+def row_maps():
+    """Row-permuted operands of the qkv projection: batched row gather (weights bf16, biases fp32), wgrad with an output
+    row map and column sums with an output map — each against the torch index op it replaces (bit-exact / 1e-6)."""
+    import torch
+    from adm_b200 import ops
+    torch.manual_seed(21)
+    ok = True
+    c, n, hw = 128, 4, 8
+    perm = torch.randperm(3 * c, device="cuda")
+    perm32 = perm.to(torch.int32)
+    # gather: two "blocks" living at different offsets of one source buffer
+    src = _bf(torch.randn(5 * 3 * c * c, device="cuda"))
+    offs = [3 * c * c, 0]
+    dst = torch.zeros(2 * 3 * c * c, device="cuda", dtype=torch.bfloat16)
+    r = torch.arange(3 * c, device="cuda")
+    table = torch.cat([torch.stack([(o + perm * c) * 2, (i * 3 * c * c + r * c) * 2], dim=1) for i, o in enumerate(offs)])
+    ops.gather_rows(src, dst, table.contiguous(), 2 * c)
+    ref = torch.cat([src[o:o + 3 * c * c].view(3 * c, c)[perm].reshape(-1) for o in offs])
+    ok &= torch.equal(dst, ref)
+    print(f"  gather_rows bf16 rows: {'bit-exact' if torch.equal(dst, ref) else 'MISMATCH'}", flush=True)
+    bsrc = torch.randn(1000, device="cuda")
+    bdst = torch.zeros(3 * c, device="cuda")
+    btab = torch.stack([(17 + perm) * 4, r * 4], dim=1).contiguous()
+    ops.gather_rows(bsrc, bdst, btab, 4)
+    ok &= torch.equal(bdst, bsrc[17 + perm])
+    print(f"  gather_rows fp32 elements: {'bit-exact' if torch.equal(bdst, bsrc[17 + perm]) else 'MISMATCH'}", flush=True)
+    # wgrad of the row-permuted 1x1 conv straight into the reference-ordered gradient
+    x = _bf(torch.randn(n, hw, hw, c, device="cuda"))
+    dy = _bf(torch.randn(n, hw, hw, 3 * c, device="cuda"))  # executed (permuted) channel order
+    g = torch.randn(3 * c, c, 1, 1, device="cuda")
+    want = g.clone()
+    dwp = ops.conv_wgrad(dy, x, ntaps=1)
+    want.view(3 * c, c).index_add_(0, perm, dwp[:, 0, :c])
+    ops.conv_wgrad(dy, x, ntaps=1, out=g.view(3 * c, 1, c), row_map=perm32)
+    torch.cuda.synchronize()
+    ok &= _report("wgrad with row map", g, want, 1e-6)
+    gb = torch.randn(3 * c, device="cuda")
+    wantb = gb.clone()
+    tmp = torch.zeros(3 * c, device="cuda")
+    ops.col_sums(dy, tmp)
+    wantb.index_add_(0, perm, tmp)
+    ops.col_sums(dy, gb, out_map=perm32)
+    torch.cuda.synchronize()
+    ok &= _report("col_sums with output map", gb, wantb, 1e-6)
+    # wide, narrow and ragged tensors through the re-pipelined column-sum kernel
+    for rows, cc in [(128 * 256, 1152), (37, 64), (128 * 1024, 192), (5000, 2056)]:
+        xx = _bf(torch.randn(rows, cc, device="cuda"))
+        out = torch.zeros(cc, device="cuda")
+        ops.col_sums(xx, out)
+        torch.cuda.synchronize()
+        ok &= _report(f"col_sums {rows}x{cc}", out, xx.float().sum(0), 1e-5)
+    return ok
+
+
+@case
 def elementwise():
     import torch
     from adm_b200 import ops
