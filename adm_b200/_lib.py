@@ -92,6 +92,9 @@ SIGNATURES = {
     "adm_lerp_f32": (c_i, [c_p, c_p, c_ll, c_f, c_p]),
     "adm_ws_pack": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p]),
     "adm_ws_pack_bwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
+    "adm_chan_layernorm_ok": (c_i, [c_i]),
+    "adm_chan_layernorm_fwd": (c_i, [c_p, c_ll, c_ll, c_i, c_p, c_f, c_p, c_ll, c_p]),
+    "adm_chan_layernorm_bwd": (c_i, [c_p, c_ll, c_p, c_ll, c_ll, c_i, c_p, c_f, c_p, c_ll, c_p, c_p]),
     "adm_linattn_workspace": (c_i, [c_i, c_i, c_i, C.POINTER(c_ll)]),
     "adm_linattn_fwd": (c_i, [c_p, c_ll, c_i, c_i, c_i, c_i, c_f, c_p, c_ll, c_p, c_p, c_p, c_p]),
     "adm_linattn_bwd": (c_i, [c_p, c_ll, c_i, c_i, c_i, c_i, c_f, c_p, c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_p]),

@@ -52,6 +52,58 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restric
     }
 }
 
+// Rows longer than 1024 (the single-head mid attention of the frozen autoencoder, 4096 tokens): one CTA per row, three
+// passes over the row (maximum, sum of exponentials, normalised write); the 16 KB row stays in L1 / L2 between passes.
+__global__ void __launch_bounds__(256) softmax_fwd_long_kernel(const float* __restrict__ s,
+                                                               __nv_bfloat16* __restrict__ p, long long rows, int L) {
+    __shared__ float red[8];
+    __shared__ float bcast;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+        const float4* sr = reinterpret_cast<const float4*>(s + r * L);
+        const int L4 = L >> 2;  // L is a multiple of 4 (checked by the launcher)
+        float m = -INFINITY;
+        for (int j = threadIdx.x; j < L4; j += 256) {
+            const float4 v = sr[j];
+            m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+        }
+        m = warp_max(m);
+        if (lane == 0) red[warp] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = red[0];
+            for (int i = 1; i < 8; ++i) t = fmaxf(t, red[i]);
+            bcast = t;
+        }
+        __syncthreads();
+        m = bcast;
+        float sum = 0.f;
+        for (int j = threadIdx.x; j < L4; j += 256) {
+            const float4 v = sr[j];
+            sum += __expf(v.x - m) + __expf(v.y - m) + __expf(v.z - m) + __expf(v.w - m);
+        }
+        sum = warp_sum(sum);
+        __syncthreads();  // everyone has read bcast
+        if (lane == 0) red[warp] = sum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int i = 0; i < 8; ++i) t += red[i];
+            bcast = 1.f / t;
+        }
+        __syncthreads();
+        const float inv = bcast;
+        uint2* pr = reinterpret_cast<uint2*>(p + r * L);
+        for (int j = threadIdx.x; j < L4; j += 256) {
+            const float4 v = sr[j];
+            const __nv_bfloat162 a = __floats2bfloat162_rn(__expf(v.x - m) * inv, __expf(v.y - m) * inv);
+            const __nv_bfloat162 b = __floats2bfloat162_rn(__expf(v.z - m) * inv, __expf(v.w - m) * inv);
+            pr[j] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+        }
+        __syncthreads();  // red / bcast are re-used by the next row
+    }
+}
+
 // dS[row] = scale * P * (dP - sum_j dP_j P_j)
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p,
                                                           const float* __restrict__ dp, __nv_bfloat16* __restrict__ ds,
@@ -351,6 +403,14 @@ typedef __nv_bfloat16 bf16;
 extern "C" {
 
 int adm_softmax_fwd(const float* s, void* p, long long rows, int len, void* stream) {
+    if (len > 1024) {
+        if (len % 4 || len > 65536) { set_error("softmax: long rows must be a multiple of 4 and <= 65536 (got %d)", len); return ADM_ERR_SHAPE; }
+        const long long cap = 16LL * num_sms();
+        softmax_fwd_long_kernel<<<static_cast<unsigned>(rows < cap ? rows : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            s, static_cast<bf16*>(p), rows, len);
+        ADM_CHECK_LAUNCH("softmax_fwd_long");
+        return 0;
+    }
     if (len <= 0 || len > 1024) { set_error("softmax: row length %d not in [1, 1024]", len); return ADM_ERR_SHAPE; }
     softmax_fwd_kernel<<<ew_blocks(rows * 32, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         s, static_cast<bf16*>(p), rows, len);

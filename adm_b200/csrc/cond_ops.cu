@@ -396,6 +396,148 @@ __global__ void linattn_bwd_kv_kernel(const __nv_bfloat16* __restrict__ qkv, lon
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ channel LayerNorm
+// cond_unet.py LayerNorm (:360-369): y[p][c] = (x[p][c] - mean_p) * rsqrt(var_p + eps) * g[c], statistics over the C channels
+// of ONE pixel (biased variance), NHWC bf16 in and out.  HBM-bound: 2 B read + 2 B written per element forward; backward
+// reads x and dy, writes dx (6 B) and re-derives mean / rstd from x instead of storing them.
+// A pixel is held by gs = C / (8 * NV) lanes (a power of two <= 32), each with NV 16-byte vectors in registers; a warp works on
+// 32 / gs pixels at a time and reduces with xor-shuffles inside each lane group.
+template <int NV>
+__device__ __forceinline__ void cln_load(const __nv_bfloat16* row, int li, int gs, float (&v)[NV][8]) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(row + (li + k * gs) * 8);
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[k][2 * j] = __uint_as_float(w[j] << 16);
+            v[k][2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+        }
+    }
+}
+__device__ __forceinline__ float cln_group_sum(float a, int gs) {
+    for (int o = gs >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    return a;
+}
+template <int NV>
+__device__ __forceinline__ void cln_stats(const float (&v)[NV][8], int gs, float inv_c, float eps, float& mean,
+                                          float& rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[k][j];
+    mean = cln_group_sum(s, gs) * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[k][j] - mean; q += d * d; }
+    rstd = rsqrtf(cln_group_sum(q, gs) * inv_c + eps);
+}
+__device__ __forceinline__ uint4 cln_pack(const float (&o)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 b2 = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+        w[j] = *reinterpret_cast<const uint32_t*>(&b2);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) chan_ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                          long long rows, int C, const float* __restrict__ g, float eps,
+                                                          __nv_bfloat16* __restrict__ y, long long ldy) {
+    const int gs = (C >> 3) / NV, lane = threadIdx.x & 31;
+    const int sub = lane / gs, li = lane % gs, ppw = 32 / gs;
+    const long long warp0 = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = (1LL * gridDim.x * blockDim.x) >> 5;
+    const float inv_c = 1.f / static_cast<float>(C);
+    float gg[NV][8];
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gg[k][j] = g[(li + k * gs) * 8 + j];
+    for (long long r0 = warp0 * ppw; r0 < rows; r0 += nwarps * ppw) {
+        const long long r = r0 + sub;
+        const bool ok = r < rows;  // lanes of a missing pixel still take part in the shuffles
+        float v[NV][8];
+        cln_load<NV>(x + (ok ? r : rows - 1) * ldx, li, gs, v);
+        float mean, rstd;
+        cln_stats<NV>(v, gs, inv_c, eps, mean, rstd);
+        if (!ok) continue;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (v[k][j] - mean) * rstd * gg[k][j];
+            *reinterpret_cast<uint4*>(y + r * ldy + (li + k * gs) * 8) = cln_pack(o);
+        }
+    }
+}
+
+// dx = rstd * (g dy - mean_c(g dy) - xhat * mean_c(g dy xhat)); dg[c] += sum_p dy * xhat (per-thread partials over the
+// pixels it visits, then one shared-memory reduction per CTA and C atomics).
+template <int NV>
+__global__ void __launch_bounds__(256) chan_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
+                                                          const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                          long long rows, int C, const float* __restrict__ g, float eps,
+                                                          __nv_bfloat16* __restrict__ dx, long long lddx,
+                                                          float* __restrict__ dg) {
+    extern __shared__ float cln_sm[];  // [C] dg partials of this CTA
+    const int gs = (C >> 3) / NV, lane = threadIdx.x & 31;
+    const int sub = lane / gs, li = lane % gs, ppw = 32 / gs;
+    const long long warp0 = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = (1LL * gridDim.x * blockDim.x) >> 5;
+    const float inv_c = 1.f / static_cast<float>(C);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) cln_sm[c] = 0.f;
+    __syncthreads();
+    float gg[NV][8], acc[NV][8];
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { gg[k][j] = g[(li + k * gs) * 8 + j]; acc[k][j] = 0.f; }
+    for (long long r0 = warp0 * ppw; r0 < rows; r0 += nwarps * ppw) {
+        const long long r = r0 + sub;
+        const bool ok = r < rows;
+        const long long rr = ok ? r : rows - 1;
+        float v[NV][8], d[NV][8];
+        cln_load<NV>(x + rr * ldx, li, gs, v);
+        cln_load<NV>(dy + rr * lddy, li, gs, d);
+        float mean, rstd;
+        cln_stats<NV>(v, gs, inv_c, eps, mean, rstd);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[k][j] = (v[k][j] - mean) * rstd;  // xhat
+                if (ok) acc[k][j] += d[k][j] * v[k][j];
+                d[k][j] *= gg[k][j];                // g dy
+                s1 += d[k][j];
+                s2 += d[k][j] * v[k][j];
+            }
+        s1 = cln_group_sum(s1, gs) * inv_c;
+        s2 = cln_group_sum(s2, gs) * inv_c;
+        if (!ok) continue;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = rstd * (d[k][j] - s1 - v[k][j] * s2);
+            *reinterpret_cast<uint4*>(dx + r * lddx + (li + k * gs) * 8) = cln_pack(o);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(cln_sm + (li + k * gs) * 8 + j, acc[k][j]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dg + c, cln_sm[c]);
+}
+
 }  // namespace adm
 
 using namespace adm;
@@ -480,6 +622,58 @@ int adm_linattn_bwd(const void* qkv, long long ld, int batch, int n_pix, int hea
     linattn_bwd_kv_kernel<<<dim3(blocks, batch), heads * 32, heads * 2 * LA_U * LA_D * sizeof(float), s>>>(
         static_cast<const bf16*>(qkv), ld, n_pix, heads, kstat, dctx, r, static_cast<bf16*>(dqkv), ldg, ppb);
     ADM_CHECK_LAUNCH("linattn_bwd_kv");
+    return 0;
+}
+
+// vectors per lane for a channel count: C / 8 vectors spread over gs = C / (8 NV) lanes, gs a power of two <= 32
+static int cln_nv(int c) {
+    if (c <= 0 || c % 8) return 0;
+    const int nvec = c / 8;
+    for (int nv = 1; nv <= 4; nv *= 2) {
+        if (nvec % nv) continue;
+        const int gs = nvec / nv;
+        if (gs <= 32 && (gs & (gs - 1)) == 0) return nv;
+    }
+    return 0;
+}
+
+int adm_chan_layernorm_ok(int c) { return cln_nv(c) != 0; }
+
+int adm_chan_layernorm_fwd(const void* x, long long ldx, long long rows, int c, const float* g, float eps, void* y,
+                           long long ldy, void* stream) {
+    const int nv = cln_nv(c);
+    if (nv == 0 || rows <= 0) { set_error("chan_layernorm: C = %d must be 8 * 2^k * {1,2,4} with 2^k <= 32", c); return ADM_ERR_SHAPE; }
+    if (ldx % 8 || ldy % 8) { set_error("chan_layernorm: pixel strides must be multiples of 8"); return ADM_ERR_SHAPE; }
+    const int ppw = 32 / ((c / 8) / nv);
+    long long blocks = (rows + 8LL * ppw - 1) / (8LL * ppw);
+    if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bf16* xp = static_cast<const bf16*>(x);
+    bf16* yp = static_cast<bf16*>(y);
+    if (nv == 1) chan_ln_fwd_kernel<1><<<static_cast<unsigned>(blocks), 256, 0, s>>>(xp, ldx, rows, c, g, eps, yp, ldy);
+    else if (nv == 2) chan_ln_fwd_kernel<2><<<static_cast<unsigned>(blocks), 256, 0, s>>>(xp, ldx, rows, c, g, eps, yp, ldy);
+    else chan_ln_fwd_kernel<4><<<static_cast<unsigned>(blocks), 256, 0, s>>>(xp, ldx, rows, c, g, eps, yp, ldy);
+    ADM_CHECK_LAUNCH("chan_layernorm_fwd");
+    return 0;
+}
+
+int adm_chan_layernorm_bwd(const void* dy, long long lddy, const void* x, long long ldx, long long rows, int c,
+                           const float* g, float eps, void* dx, long long lddx, float* dg, void* stream) {
+    const int nv = cln_nv(c);
+    if (nv == 0 || rows <= 0) { set_error("chan_layernorm: C = %d must be 8 * 2^k * {1,2,4} with 2^k <= 32", c); return ADM_ERR_SHAPE; }
+    if (ldx % 8 || lddy % 8 || lddx % 8) { set_error("chan_layernorm: pixel strides must be multiples of 8"); return ADM_ERR_SHAPE; }
+    const int ppw = 32 / ((c / 8) / nv);
+    long long blocks = (rows + 8LL * ppw - 1) / (8LL * ppw);
+    if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bf16 *dyp = static_cast<const bf16*>(dy), *xp = static_cast<const bf16*>(x);
+    bf16* dxp = static_cast<bf16*>(dx);
+    const size_t sm = sizeof(float) * c;
+    const unsigned b = static_cast<unsigned>(blocks);
+    if (nv == 1) chan_ln_bwd_kernel<1><<<b, 256, sm, s>>>(dyp, lddy, xp, ldx, rows, c, g, eps, dxp, lddx, dg);
+    else if (nv == 2) chan_ln_bwd_kernel<2><<<b, 256, sm, s>>>(dyp, lddy, xp, ldx, rows, c, g, eps, dxp, lddx, dg);
+    else chan_ln_bwd_kernel<4><<<b, 256, sm, s>>>(dyp, lddy, xp, ldx, rows, c, g, eps, dxp, lddx, dg);
+    ADM_CHECK_LAUNCH("chan_layernorm_bwd");
     return 0;
 }
 

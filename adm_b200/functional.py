@@ -168,3 +168,26 @@ class _SpatialAttFn(torch.autograd.Function):
 
 def spatial_att(h, res, w_map, scalars):
     return _SpatialAttFn.apply(h, res, w_map, scalars)
+
+
+class _ChanLayerNormFn(torch.autograd.Function):
+    """Per-pixel LayerNorm over channels with a gain and no bias (cond_unet.py LayerNorm :360-369): one HBM-bound kernel each
+    way on NHWC bf16; the backward re-derives the statistics from x."""
+
+    @staticmethod
+    def forward(ctx, x, g, eps):
+        x = _nhwc(x)
+        gf = g.detach().reshape(-1).float().contiguous()
+        ctx.save_for_backward(x, gf)
+        ctx.eps, ctx.g_shape = eps, g.shape
+        return ops.chan_layernorm_fwd(x, gf, eps)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gf = ctx.saved_tensors
+        dx, dg = ops.chan_layernorm_bwd(_nhwc(dy), x, gf, ctx.eps)
+        return dx, dg.reshape(ctx.g_shape), None
+
+
+def channel_layer_norm(x, g, eps=1e-5):
+    return _ChanLayerNormFn.apply(x, g, eps)

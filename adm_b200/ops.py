@@ -757,3 +757,33 @@ def linattn_bwd(dout, qkv, ctx, kstat, heads, scale):
                                       dout.stride(2), _ptr(ctx), _ptr(kstat), _ptr(dctx), _ptr(r), _ptr(work),
                                       _ptr(dqkv), dqkv.stride(2), _stream()), "linattn_bwd")
     return dqkv
+
+
+# ------------------------------------------------------------------------------------------------ channel LayerNorm
+def chan_layernorm_ok(c):
+    return bool(_lib.load().adm_chan_layernorm_ok(int(c)))
+
+
+def chan_layernorm_fwd(x, g, eps=1e-5):
+    """Per-pixel LayerNorm over the channels of an NHWC bf16 tensor with gain g [C] fp32 (cond_unet.py:360-369)."""
+    _need_cuda(x, g)
+    assert x.dtype == BF16 and x.stride(-1) == 1 and g.dtype == F32 and g.is_contiguous()
+    c = x.shape[-1]
+    rows = x.numel() // c
+    y = torch.empty(x.shape, device=x.device, dtype=BF16)
+    check(_lib.load().adm_chan_layernorm_fwd(_ptr(x), x.stride(-2), rows, c, _ptr(g), float(eps), _ptr(y), c, _stream()),
+          "chan_layernorm_fwd")
+    return y
+
+
+def chan_layernorm_bwd(dy, x, g, eps=1e-5):
+    """Returns (dx bf16 like x, dg fp32 [C])."""
+    _need_cuda(dy, x, g)
+    assert dy.dtype == BF16 and dy.stride(-1) == 1 and x.stride(-1) == 1
+    c = x.shape[-1]
+    rows = x.numel() // c
+    dx = torch.empty(x.shape, device=x.device, dtype=BF16)
+    dg = torch.zeros(c, device=x.device, dtype=F32)
+    check(_lib.load().adm_chan_layernorm_bwd(_ptr(dy), dy.stride(-2), _ptr(x), x.stride(-2), rows, c, _ptr(g), float(eps),
+                                             _ptr(dx), c, _ptr(dg), _stream()), "chan_layernorm_bwd")
+    return dx, dg

@@ -26,6 +26,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import functional as AF
+from .. import ops
 
 
 def exists(x):
@@ -347,6 +348,8 @@ class LayerNorm(nn.Module):
         self.g = nn.Parameter(torch.ones(1, dim, 1, 1))
 
     def forward(self, x):  # NHWC
+        if x.is_cuda and ops.chan_layernorm_ok(x.shape[-1]):
+            return AF.channel_layer_norm(x, self.g, 1e-5)
         return F.layer_norm(x.float(), (x.shape[-1],), self.g.reshape(-1), None, 1e-5).to(torch.bfloat16)
 
 

@@ -234,8 +234,9 @@ int adm_silu(const float* x, float* y, void* y_bf16, long long numel, void* stre
 int adm_silu_bwd(const float* x, const float* dy, float* dx, void* dx_bf16, long long numel, void* stream);
 
 /* ---------------------------------------------------------------- attention pieces
- * softmax over the key axis of S = Q^T K / sqrt(d) (unet/uncond_unet.py:207); P bf16 [rows][len], len <= 1024.
- * backward: dS = scale * P * (dP - sum_j dP_j P_j).                                                           */
+ * softmax over the key axis of S = Q^T K / sqrt(d) (unet/uncond_unet.py:207); P bf16 [rows][len].  Forward: any len
+ * <= 1024 (one warp per row) or a multiple of 4 up to 65536 (one CTA per row: the autoencoder's single-head mid
+ * attention, ddm/encoder_decoder.py:204-209); backward len <= 1024: dS = scale * P * (dP - sum_j dP_j P_j).                                                       */
 int adm_softmax_fwd(const float* s, void* p, long long rows, int len, void* stream);
 int adm_softmax_bwd(const void* p, const float* dp, void* ds, float scale, long long rows, int len, void* stream);
 /* K9 forward, fused (unet/uncond_unet.py:204-208; cond_unet.Attention, unet/cond_unet.py:533-555 with zero-padded heads):
@@ -270,6 +271,17 @@ int adm_spatial_att_fwd(const void* h, long long ldh, const void* res, long long
 int adm_spatial_att_bwd(const void* dy, long long ldy, const void* h, long long ldh, const float* w_map,
                         const float* scalars, const float* att_save, const float* o_save, int n, int hw, int c,
                         void* dh, long long lddh, float* dw_map, float* dscalars, void* stream);
+
+/* ---------------------------------------------------------------- channel LayerNorm (conditional UNet)
+ * cond_unet.py LayerNorm (:360-369, used by PreNorm / LinearAttention.to_out :371-379, :516-519):
+ * y[p][c] = (x[p][c] - mean_p) * rsqrt(var_p + eps) * g[c] over the C channels of each pixel (biased variance), NHWC bf16.
+ * C = 8 * 2^k * {1, 2, 4} with 2^k <= 32 (adm_chan_layernorm_ok).  backward: dx and dg[c] += sum_p dy * xhat (zero dg first);
+ * mean / rstd are re-derived from x.                                                                         */
+int adm_chan_layernorm_ok(int c);
+int adm_chan_layernorm_fwd(const void* x, long long ldx, long long rows, int c, const float* g, float eps, void* y,
+                           long long ldy, void* stream);
+int adm_chan_layernorm_bwd(const void* dy, long long lddy, const void* x, long long ldx, long long rows, int c,
+                           const float* g, float eps, void* dx, long long lddx, float* dg, void* stream);
 
 /* ---------------------------------------------------------------- conditional UNet (unet/cond_unet.py)
  * K11  WeightStandardizedConv2d (:345-358): w_hat = (w - mean_o) * rsqrt(var_o + eps) per output channel (var unbiased =

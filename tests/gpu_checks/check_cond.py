@@ -66,6 +66,33 @@ def _linattn_ref(qkv, heads, scale):
 
 
 @case
+def channel_layernorm():
+    """Channel LayerNorm kernels (cond_unet.py:360-369) against the reference formula in fp32 autograd."""
+    import torch
+    from adm_b200 import functional as AF
+    torch.manual_seed(3)
+    ok = True
+    for (b, h, w, c) in [(2, 16, 16, 128), (1, 7, 5, 64), (2, 8, 8, 256), (1, 4, 4, 512), (1, 3, 3, 32), (1, 2, 2, 1024)]:
+        x = (torch.randn(b, h, w, c, device="cuda") * 2 + 0.3).bfloat16()
+        g = (torch.rand(1, c, 1, 1, device="cuda") + 0.5).requires_grad_(True)
+        dy = torch.randn(b, h, w, c, device="cuda").bfloat16()
+        xr = x.float().requires_grad_(True)
+        gr = g.detach().clone().requires_grad_(True)
+        var = torch.var(xr, dim=-1, unbiased=False, keepdim=True)
+        mean = torch.mean(xr, dim=-1, keepdim=True)
+        yr = (xr - mean) * (var + 1e-5).rsqrt() * gr.reshape(1, 1, 1, c)
+        yr.backward(dy.float())
+        xo = x.clone().requires_grad_(True)
+        y = AF.channel_layer_norm(xo, g, 1e-5)
+        y.backward(dy)
+        torch.cuda.synchronize()
+        ok &= _report(f"chan LN fwd {b}x{h}x{w}x{c}", y, yr, 5e-3)
+        ok &= _report(f"chan LN dx", xo.grad, xr.grad, 6e-3)
+        ok &= _report(f"chan LN dg", g.grad, gr.grad, 1e-3)
+    return ok
+
+
+@case
 def linear_attention():
     import torch
     from adm_b200 import functional as AF

@@ -315,6 +315,14 @@ def small_ops():
     F.silu(er).backward(g)
     dx, _ = ops.silu_bwd(e, g)
     ok &= _report("silu_bwd", dx, er.grad, 1e-5)
+    sl = torch.randn(3, 40, 4096, device="cuda") * 4  # rows longer than 1024: one CTA per row (autoencoder mid attention)
+    ok &= _report("softmax long rows", ops.softmax_fwd(sl), torch.softmax(sl, -1), 5e-3)
+    # single-head attention with d = 512 over 4096 tokens through the batched GEMMs + long-row softmax
+    qkv = (torch.randn(1, 64, 64, 3 * 512, device="cuda") * 0.5).bfloat16()
+    a, _ = ops.attention_fwd(qkv, 1, scale=512 ** -0.5, need_p=False, fused=False)
+    q, k, v = (t.float().reshape(1, 4096, 512) for t in qkv.split(512, dim=-1))
+    ref = torch.softmax(q @ k.transpose(1, 2) * 512 ** -0.5, -1) @ v
+    ok &= _report("attention d=512 N=4096 (unfused)", a.reshape(1, 4096, 512), ref, 1e-2)
     s = torch.randn(6 * 4, 256, 256, device="cuda") * 3
     p = ops.softmax_fwd(s)
     ok &= _report("softmax", p, s.softmax(-1), 5e-3)

@@ -258,7 +258,8 @@ def test_arena_fast_path_matches_plain_backward():
 from tests.gpu_checks import check_cond as CC  # noqa: E402
 
 
-@pytest.mark.parametrize("case", ["ws_pack", "linear_attention", "attention_padded_heads", "resnet_block"])
+@pytest.mark.parametrize("case", ["ws_pack", "channel_layernorm", "linear_attention", "attention_padded_heads",
+                                  "resnet_block"])
 def test_cond_unet_kernels(case):
     """K11 weight-standardise+pack, K12 fused LinearAttention, padded-head Attention, ResnetBlock fwd/bwd vs torch."""
     assert CC.CASES[case]()

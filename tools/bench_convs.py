@@ -1,4 +1,5 @@
-"""Times every distinct conv shape of the CIFAR UNet (batch 128) in isolation: fprop, dgrad, wgrad -> TFLOP/s."""
+"""Times every distinct conv shape of the CIFAR UNet (batch 128) in isolation: fprop, dgrad (MN-major view of the fprop-packed
+weights), dgrad_T (fprop kernels on the transposed weight shadow: what the training step runs), wgrad -> TFLOP/s."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -38,7 +39,7 @@ def timeit(fn, iters=10):
     return e0.elapsed_time(e1) / (3 * iters)
 
 
-tot = {"fprop": 0.0, "dgrad": 0.0, "wgrad": 0.0}
+tot = {"fprop": 0.0, "dgrad": 0.0, "dgrad_T": 0.0, "wgrad": 0.0}
 for cnt, cin, cout, res, k in SHAPES:
     x = torch.randn(N, res, res, cin, device="cuda").bfloat16()
     dy = torch.randn(N, res, res, cout, device="cuda").bfloat16()
@@ -50,9 +51,13 @@ for cnt, cin, cout, res, k in SHAPES:
     r = {}
     r["fprop"] = timeit(lambda: ops.conv_fprop(x, w, out=out))
     r["dgrad"] = timeit(lambda: ops.conv_dgrad(dy, w, out=dx))
+    # the training step's data gradient: the fprop kernels on the transposed, tap-mirrored weight shadow (dgrad_T)
+    wt = torch.empty(cin, k * k, cout, device="cuda", dtype=torch.bfloat16)
+    ops.transpose_weight_tiles(w, wt, ops.weight_transpose_tiles(0, cout, k * k, cin).cuda())
+    r["dgrad_T"] = timeit(lambda: ops.conv_fprop(dy, wt, out=dx))
     r["wgrad"] = timeit(lambda: ops.conv_wgrad(dy, x, ntaps=k * k, out=dw))
     for kk in tot:
         tot[kk] += cnt * r[kk]
     print(f"{cnt:3d} x [{cin:4d}->{cout:4d} @{res:2d} k{k}] GFLOP {flops/1e9:7.1f} | " +
-          " | ".join(f"{kk} {r[kk]*1000:7.1f} us {flops/r[kk]/1e9:7.1f} TF/s" for kk in ("fprop", "dgrad", "wgrad")), flush=True)
+          " | ".join(f"{kk} {r[kk]*1000:7.1f} us {flops/r[kk]/1e9:7.1f} TF/s" for kk in ("fprop", "dgrad", "dgrad_T", "wgrad")), flush=True)
 print("weighted totals (ms):", {k: round(v, 2) for k, v in tot.items()})
