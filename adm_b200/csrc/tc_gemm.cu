@@ -182,8 +182,12 @@ static int launch_halo_t(const CUtensorMap& a, const CUtensorMap& a2, const CUte
         return ADM_ERR_SHAPE;
     }
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("ADM_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+    GemmParams pd = p;
+    pd.debug = dbg;
     cudaError_t e = launch_k(tc_conv_halo_kernel<PRO>, dim3(grid), dim3(PRO ? GEMM_PRO_THREADS : GEMM_THREADS),
-                             GEMM_SMEM_TOTAL, stream, 0, a, a2, b, p);
+                             GEMM_SMEM_TOTAL, stream, 0, a, a2, b, pd);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("tc_conv_halo launch: %s", cudaGetErrorString(e));

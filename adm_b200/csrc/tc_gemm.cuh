@@ -1046,6 +1046,11 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int tap = 0; tap < 9; ++tap) {
                         mbar_wait(&bempty[bs], bphase ^ 1, 1);
                         uint8_t* sb = b_ring + bs * b_bytes;
+                        if (p.debug & 2) {  // ADM_GEMM_DEBUG=2 (timing experiment, results are garbage): no weight traffic
+                            mbar_arrive(&bfull[bs]);
+                            if (++bs == nb) { bs = 0; bphase ^= 1; }
+                            continue;
+                        }
                         mbar_expect_tx(&bfull[bs], b_bytes);
                         if (!p.b_mn) {
                             tma_load_2d(sb, &tmB, &bfull[bs], (tap * p.cchunks + kc) * 64, nt * p.bn);

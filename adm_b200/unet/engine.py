@@ -326,9 +326,12 @@ class UNetEngine:
     # projection weights — q.k and p.v are unchanged, the activations need no re-layout, and the tensor-core GEMMs keep
     # their 64-wide K slabs.  Padded fp32 weights are derived with torch index ops (cached per parameter version).
     def _head_rows(self, c, heads):
-        d = c // heads
-        which, hh, dd = torch.meshgrid(torch.arange(3), torch.arange(heads), torch.arange(d), indexing="ij")
-        return (hh * 3 * d + dd * 3 + which).to(self._dev())  # [3, heads, d] -> reference row of the qkv projection
+        key = ("rows", c, heads)  # cached: built once per shape (a host -> device copy, not capturable into a CUDA graph)
+        if key not in self._perm:
+            d = c // heads
+            which, hh, dd = torch.meshgrid(torch.arange(3), torch.arange(heads), torch.arange(d), indexing="ij")
+            self._perm[key] = (hh * 3 * d + dd * 3 + which).to(self._dev())  # [3, heads, d] -> reference qkv row
+        return self._perm[key]
 
     def qkv_padded(self, blk):
         c, heads = blk.out_channels, blk.num_heads

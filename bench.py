@@ -272,28 +272,69 @@ def run_latent(args):
         batch["cond"] = 2 * torch.rand(B, 3, size[0] // down, size[1] // down, device=device) - 1
     lib = _lib.load()
     ldm.train()
+    launch = "eager launches"
+    graph_launches = 0  # kernels of ours inside one replay of a captured graph (replays do not pass the host-side counter)
     if args.config == "celebahq":
         from adm_b200.train import TrainStep
         step = TrainStep(ldm, lr=5e-5, weight_decay=1e-4, max_grad_norm=1.0)
 
-        def one():
+        def encode():
             with torch.no_grad():
                 z, *_ = ldm.get_input(batch)
-                z = ldm.scale_factor * z
-            loss = step.micro_step(z)
-            step.optimizer_step()
-            return loss
-    else:
-        params = [p for p in ldm.model.parameters() if p.requires_grad]
-        opt = torch.optim.AdamW(params, lr=5e-5, weight_decay=1e-4, fused=True)
+                return ldm.scale_factor * z
 
         def one():
+            loss = step.micro_step(encode())
+            step.optimizer_step()
+            return loss
+        if not args.no_graph:  # frozen AE encode eagerly, then the DDM step (fwd, bwd, clip, AdamW) as ONE CUDA graph
+            try:
+                step.capture(encode())
+                graph_launches = step.launches_per_step
+                launch = "AE encode eager + one CUDA graph per DDM step"
+
+                def one():  # noqa: F811
+                    return step.replay(encode())
+            except Exception as e:
+                print(f"[bench] CUDA graph capture failed ({e!r}); running eagerly", file=sys.stderr, flush=True)
+                step.graph = None
+    else:
+        params = [p for p in ldm.model.parameters() if p.requires_grad]
+        # the conditional UNet is a module graph under torch autograd: everything runs on a side stream so that autograd's
+        # AccumulateGrad nodes are not bound to the default stream and the whole step can be captured into one CUDA graph
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        torch.cuda.set_stream(side)
+        opt = torch.optim.AdamW(params, lr=5e-5, weight_decay=1e-4, fused=True, capturable=not args.no_graph)
+
+        def eager_step():
             opt.zero_grad(set_to_none=True)
             loss, _ = ldm.training_step(batch)
             loss.backward()
             torch.nn.utils.clip_grad_norm_(params, 1.0)
             opt.step()
             return loss.detach()
+        one = eager_step
+        if not args.no_graph:
+            try:
+                for _ in range(3):
+                    eager_step()
+                torch.cuda.synchronize()
+                opt.zero_grad(set_to_none=True)
+                g = torch.cuda.CUDAGraph()
+                lc = lib.adm_launch_count()
+                with torch.cuda.graph(g, stream=side):
+                    static_loss = eager_step()
+                graph_launches = lib.adm_launch_count() - lc
+                launch = "one CUDA graph per step (AE encode, forward, autograd backward, clip, AdamW)"
+
+                def one():  # noqa: F811
+                    g.replay()
+                    return static_loss
+            except Exception as e:
+                print(f"[bench] CUDA graph capture failed ({e!r}); running eagerly", file=sys.stderr, flush=True)
+                torch.cuda.synchronize()
+                one = eager_step
     for _ in range(max(2, args.warmup)):
         loss = one()
     torch.cuda.synchronize()
@@ -305,7 +346,7 @@ def run_latent(args):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
-    launches = (lib.adm_launch_count() - l0) // args.steps
+    launches = (lib.adm_launch_count() - l0) // args.steps + graph_launches
     ldm.eval()
     with torch.no_grad():
         kw = {"cond": batch["cond"]} if "cond" in batch else {"batch_size": B}
@@ -323,7 +364,7 @@ def run_latent(args):
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": spec["workload"], "yaml": spec["yaml"], "global_batch": B, "batch_per_gpu": B,
-                       "parallelism": "dp1", "launch": "eager launches", "timing": "cuda events"},
+                       "parallelism": "dp1", "launch": launch, "timing": "cuda events"},
             "gpu_launches": int(launches), "last_loss": float(loss),
             "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": tf / pk["tf_sust"],
                          "traffic": None, "kernel": "whole step: (UNet train + frozen AE encode) algorithmic GFLOP per image x "

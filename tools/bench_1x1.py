@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from adm_b200 import ops
-from tools.bench_convs import timeit
+from tools.bench_convs_lib import timeit
 for cin, cout, res in [(384, 1152, 16), (384, 1152, 8), (384, 384, 16), (768, 384, 16), (384, 192, 32)]:
     x = torch.randn(128, res, res, cin, device="cuda").bfloat16()
     w = ops.pack_conv_weight(torch.randn(cout, cin, 1, 1, device="cuda") / 20)

@@ -14,29 +14,7 @@ SHAPES = [  # (count, cin, cout, res, k)
 ]
 
 
-def timeit(fn, iters=10):
-    """GPU time per call with host launch overhead removed: `iters` calls captured in one CUDA graph, replayed 3x."""
-    for _ in range(2):
-        fn()
-    torch.cuda.synchronize()
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.stream(side):
-        fn()
-    torch.cuda.current_stream().wait_stream(side)
-    with torch.cuda.graph(g):
-        for _ in range(iters):
-            fn()
-    g.replay()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(3):
-        g.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / (3 * iters)
+from tools.bench_convs_lib import timeit  # noqa: E402
 
 
 tot = {"fprop": 0.0, "dgrad": 0.0, "dgrad_T": 0.0, "wgrad": 0.0}

@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from adm_b200 import ops
-from tools.bench_convs import timeit
+from tools.bench_convs_lib import timeit
 dev = "cuda"
 def gemm(m, n, k):
     a = torch.randn(m, k, device=dev).bfloat16(); b = torch.randn(n, k, device=dev).bfloat16()

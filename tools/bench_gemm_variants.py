@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from adm_b200 import ops
-from tools.bench_convs import timeit
+from tools.bench_convs_lib import timeit
 
 N = 128
 print("ADM_GEMM_PAIR =", os.environ.get("ADM_GEMM_PAIR", "(default 1)"))

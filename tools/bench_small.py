@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from adm_b200 import ops
-from tools.bench_convs import timeit
+from tools.bench_convs_lib import timeit
 print("ADM_BN =", os.environ.get("ADM_BN"))
 for cin, cout, res in [(384, 384, 4), (768, 384, 4), (384, 384, 8), (768, 384, 8)]:
     x = torch.randn(128, res, res, cin, device="cuda").bfloat16()

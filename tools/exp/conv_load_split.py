@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from adm_b200 import ops
-from tools.bench_convs import timeit
+from tools.bench_convs_lib import timeit
 
 N = 128
 for cin, cout, res in [(384, 384, 16), (192, 192, 32), (768, 384, 16), (256, 256, 16), (128, 128, 32)]:

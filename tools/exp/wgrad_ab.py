@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from adm_b200 import ops
-from tools.bench_convs import timeit
+from tools.bench_convs_lib import timeit
 
 N = 128
 for cin, cout, res in [(192, 192, 32), (384, 192, 32), (384, 384, 16), (768, 384, 16), (384, 384, 8), (576, 192, 32)]:

@@ -7,7 +7,7 @@ import torch
 import bench
 from adm_b200 import ops
 from adm_b200.train import TrainStep
-from tools.bench_convs import timeit
+from tools.bench_convs_lib import timeit
 
 dev = torch.device("cuda", 0)
 dpm = bench.build_model(dev)
