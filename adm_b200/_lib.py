@@ -58,6 +58,8 @@ SIGNATURES = {
     "adm_conv_dgrad": (c_i, [c_p, c_i, c_ll, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_i, c_ll, c_p, c_ll, c_f, c_p]),
     "adm_conv_wgrad": (c_i, [c_p, c_i, c_ll, c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_i, c_p, c_p]),
     "adm_gemm_batched": (c_i, [C.POINTER(GemmDesc), c_p]),
+    "adm_augment_warp_smem": (c_ll, [c_i, c_i, c_i]),
+    "adm_augment_warp": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
     "adm_pack_conv_weight": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     "adm_unpack_conv_wgrad": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "adm_cast_f32_bf16": (c_i, [c_p, c_p, c_ll, c_p]),

@@ -273,6 +273,110 @@ __global__ void __launch_bounds__(256) unet_output_bwd_kernel(const float* __res
     }
 }
 
+// ------------------------------------------------------------------------------------------------ AugmentPipe warp (f-4)
+// One CTA per sample runs the whole geometric augmentation of ddm/augment.py:153-328 as the reference's DDM module
+// configures it (ddm_const.py:179-180): x / y flips, reflect padding by the batch-wide margins, 2x upsampling with the
+// sym6 low-pass, bilinear sampling through the per-sample inverse affine map, sym6 low-pass + 2x decimation, crop.
+// The padded and the upsampled images are never materialised: a tap of the bilinear sampler evaluates the zero-stuffed
+// 12-tap separable filter directly on the flipped 32x32 image held in shared memory (6 x 6 non-zero taps per point,
+// reflect indexing on the fly).  Shared memory: image [C][H][W], sampled grid [C][Gh][Gw], x-decimated [C][Gh][W].
+// theta [N][6] is the matrix handed to affine_grid (all compositions done on the host: a few floats per sample).
+__constant__ float c_sym6[12] = {0.015404109327027373f, 0.0034907120842174702f, -0.11799011114819057f,
+                                 -0.048311742585633f,   0.4910559419267466f,    0.787641141030194f,
+                                 0.3379294217276218f,   -0.07263752278646252f,  -0.021060292512300564f,
+                                 0.04472490177066578f,  0.0017677118642428036f, -0.007800708325034148f};
+
+__device__ __forceinline__ int aug_reflect(int i, int n) {  // one reflection is enough: margins are <= n - 1
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+
+__global__ void __launch_bounds__(256) augment_warp_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                           const float* __restrict__ theta,
+                                                           const int* __restrict__ flips, int C, int H, int W, int mx0,
+                                                           int mx1, int my0, int my1) {
+    extern __shared__ float aug_sm[];
+    const int n = blockIdx.x;
+    const int pad4 = 3;                                   // len(sym6) / 4
+    const int Gh = (H + 2 * pad4) * 2, Gw = (W + 2 * pad4) * 2;
+    const int Hp = H + my0 + my1, Wp = W + mx0 + mx1;     // reflect-padded image
+    const int Hu = 2 * Hp, Wu = 2 * Wp;                   // upsampled image the sampler reads
+    float* img = aug_sm;                                  // [C][H][W], flips applied
+    float* grid = img + C * H * W;                        // [C][Gh][Gw]
+    float* dec = grid + C * Gh * Gw;                      // [C][Gh][W]
+    const int fx = flips[2 * n], fy = flips[2 * n + 1];
+    for (int i = threadIdx.x; i < C * H * W; i += blockDim.x) {
+        const int w = i % W, h = (i / W) % H, c = i / (W * H);
+        img[i] = x[(static_cast<long long>(n) * C + c) * H * W + (fy ? H - 1 - h : h) * W + (fx ? W - 1 - w : w)];
+    }
+    __syncthreads();
+    const float t00 = theta[6 * n], t01 = theta[6 * n + 1], t02 = theta[6 * n + 2];
+    const float t10 = theta[6 * n + 3], t11 = theta[6 * n + 4], t12 = theta[6 * n + 5];
+    // value of the upsampled image at integer (Y, X), all channels: sum over the taps that land on non-zero (even)
+    // positions of the zero-stuffed image; the conv is a cross-correlation with the FLIPPED filter and padding 6
+    auto upsampled = [&](int Y, int X, float* out) {
+        for (int c = 0; c < C; ++c) out[c] = 0.f;
+        if (Y < 0 || Y >= Hu || X < 0 || X >= Wu) return;  // grid_sample padding_mode = zeros
+        for (int a = Y & 1; a < 12; a += 2) {
+            const int iy = (Y + a - 6) >> 1;               // (Y + a - 6) is even
+            if (iy < 0 || iy >= Hp) continue;
+            const int sy = aug_reflect(iy - my0, H);
+            const float ka = c_sym6[11 - a];
+            for (int b = X & 1; b < 12; b += 2) {
+                const int ix = (X + b - 6) >> 1;
+                if (ix < 0 || ix >= Wp) continue;
+                const int sx = aug_reflect(ix - mx0, W);
+                const float k = ka * c_sym6[11 - b];
+                for (int c = 0; c < C; ++c) out[c] += k * img[(c * H + sy) * W + sx];
+            }
+        }
+    };
+    // bilinear sampling (affine_grid + grid_sample, align_corners = False, zeros outside)
+    for (int i = threadIdx.x; i < Gh * Gw; i += blockDim.x) {
+        const int gi = i / Gw, gj = i - gi * Gw;
+        const float bx = (2.f * gj + 1.f) / Gw - 1.f, by = (2.f * gi + 1.f) / Gh - 1.f;
+        const float gx = t00 * bx + t01 * by + t02, gy = t10 * bx + t11 * by + t12;
+        const float px = ((gx + 1.f) * Wu - 1.f) * 0.5f, py = ((gy + 1.f) * Hu - 1.f) * 0.5f;
+        const float fx0 = floorf(px), fy0 = floorf(py);
+        const int x0 = static_cast<int>(fx0), y0 = static_cast<int>(fy0);
+        const float wx1 = px - fx0, wy1 = py - fy0, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f}, v[4];
+        const float wts[4] = {wy0 * wx0, wy0 * wx1, wy1 * wx0, wy1 * wx1};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            upsampled(y0 + (t >> 1), x0 + (t & 1), v);
+            for (int c = 0; c < C; ++c) acc[c] += wts[t] * v[c];
+        }
+        for (int c = 0; c < C; ++c) grid[(c * Gh + gi) * Gw + gj] = acc[c];
+    }
+    __syncthreads();
+    // low-pass + decimate along x (stride 2, padding 5), cropped to the W centre columns
+    for (int i = threadIdx.x; i < C * Gh * W; i += blockDim.x) {
+        const int w = i % W, gi = (i / W) % Gh, c = i / (W * Gh);
+        const float* row = grid + (c * Gh + gi) * Gw;
+        float a = 0.f;
+#pragma unroll
+        for (int b = 0; b < 12; ++b) {
+            const int j = 2 * (w + pad4) + b - 5;
+            if (j >= 0 && j < Gw) a += c_sym6[b] * row[j];
+        }
+        dec[i] = a;
+    }
+    __syncthreads();
+    // ... and along y, cropped to the H centre rows
+    for (int i = threadIdx.x; i < C * H * W; i += blockDim.x) {
+        const int w = i % W, h = (i / W) % H, c = i / (W * H);
+        float a = 0.f;
+#pragma unroll
+        for (int b = 0; b < 12; ++b) {
+            const int j = 2 * (h + pad4) + b - 5;
+            if (j >= 0 && j < Gh) a += c_sym6[b] * dec[(c * Gh + j) * W + w];
+        }
+        y[(static_cast<long long>(n) * C + c) * H * W + h * W + w] = a;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ weight packing
 // w [cout][cin][k][k] fp32 -> bf16 [cout][k*k][kpad]; source 2 channels start at pad64(c1).
 __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __restrict__ w,
@@ -455,6 +559,31 @@ int adm_unet_output_bwd(const float* dd1, const float* dd2, const float* sigma, 
     unet_output_bwd_kernel<<<ew_grid(1LL * n * h * w, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         dd1, dd2, sigma, static_cast<__nv_bfloat16*>(df1), static_cast<__nv_bfloat16*>(df2), n, c, h * w, ld_out);
     ADM_CHECK_LAUNCH("unet_output_bwd");
+    return 0;
+}
+
+long long adm_augment_warp_smem(int c, int h, int w) {
+    const long long gh = (h + 6) * 2, gw = (w + 6) * 2;
+    return 4LL * (1LL * c * h * w + c * gh * gw + c * gh * w);
+}
+
+int adm_augment_warp(const float* x, float* y, const float* theta, const int* flips, int n, int c, int h, int w,
+                     int mx0, int mx1, int my0, int my1, void* stream) {
+    if (n <= 0 || c <= 0 || c > 4 || h < 2 || w < 2) { set_error("augment_warp: bad shape (channels <= 4)"); return ADM_ERR_SHAPE; }
+    if (mx0 < 0 || mx1 < 0 || my0 < 0 || my1 < 0 || mx0 >= w || mx1 >= w || my0 >= h || my1 >= h) {
+        set_error("augment_warp: margins must lie in [0, size - 1]");
+        return ADM_ERR_SHAPE;
+    }
+    const long long smem = adm_augment_warp_smem(c, h, w);
+    if (smem > 200 * 1024) { set_error("augment_warp: image too large for one CTA (%lld B of shared memory)", smem); return ADM_ERR_SHAPE; }
+    static long long attr_set = 0;
+    if (smem > attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(augment_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) { set_error("augment_warp: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ADM_ERR_CUDA; }
+        attr_set = smem;
+    }
+    augment_warp_kernel<<<n, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, y, theta, flips, c, h, w, mx0, mx1, my0, my1);
+    ADM_CHECK_LAUNCH("augment_warp");
     return 0;
 }
 

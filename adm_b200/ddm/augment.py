@@ -7,15 +7,18 @@ composed into a single inverse matrix), returning the augmented batch and the 9 
 ``[xflip, yflip, scale, cos(rot) - 1, sin(rot), aniso * cos(r), aniso * sin(r), tx, ty]`` that enter the UNet through
 ``map_augment`` (unet/uncond_unet.py:548-549).
 
-This is host-side data glue: it runs as ordinary torch ops on whatever device the batch lives
-on, before the fused training step.  It draws from the global torch RNG in the reference's order, so with the same seed it
-reproduces the reference's augmented batch (tests/golden/make_golden_augment.py records one; tests/test_host.py compares).
+The random decisions (a few scalars per sample) are drawn on the host from the global torch RNG in the reference's order, so
+with the same seed it reproduces the reference's augmented batch (tests/golden/make_golden_augment.py records one;
+tests/test_host.py compares).  CUDA batches then run flips + the whole warp as ONE sm_100a kernel (``adm_augment_warp``,
+SURVEY section 8 row f-4: one CTA per sample, nothing but the 32 x 32 image and the sampled grid in shared memory); CPU
+tensors (and ``fused = False``) run the same arithmetic as ordinary torch ops.
 Only what the DDM configs use is implemented; integer rotation / translation and the colour transforms (all disabled in
 ddm_const.py:179-180) raise.
 """
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -61,6 +64,9 @@ class AugmentPipe:
                                                                          float(translate_frac))
         self.scale_std, self.rotate_frac_max, self.aniso_std = float(scale_std), float(rotate_frac_max), float(aniso_std)
         self.aniso_rotate_prob, self.translate_frac_std = float(aniso_rotate_prob), float(translate_frac_std)
+        # CUDA batches run flips + warp as ONE kernel (adm_augment_warp); fused = False keeps the torch-op sequence below
+        # (the same arithmetic, ~40 launches), which is also what runs on CPU tensors
+        self.fused = os.environ.get("ADM_AUG_FUSED", "1") != "0"  # 0: A/B timing of the torch-op sequence
 
     # ------------------------------------------------------------------------------------------ random parameters
     def draw(self, n, h, w, device):
@@ -159,12 +165,60 @@ class AugmentPipe:
         images = F.conv2d(images, k_dn.unsqueeze(3), groups=c, stride=[2, 1], padding=[dn_pad, 0])[:, :, pad4:-pad4, :]
         return images
 
+    # ------------------------------------------------------------------------------------------ the warp, one kernel
+    @staticmethod
+    def warp_plan(g_inv, h, w):
+        """Host side of the warp (a few floats per sample): the batch-wide reflect margins (:245-250) and the 2 x 3 matrix
+        the reference hands to affine_grid (:252-266) — the same compositions as ``warp`` above, on the host tensors."""
+        n = g_inv.shape[0]
+        pad4 = len(SYM6) // 4
+        cx, cy = (w - 1) / 2, (h - 1) / 2
+        corners = torch.tensor([[-cx, -cy, 1], [cx, -cy, 1], [cx, cy, 1], [-cx, cy, 1]], dtype=g_inv.dtype)
+        moved = g_inv @ corners.t()
+        ext = moved[:, :2, :].permute(1, 0, 2).flatten(1)
+        ext = torch.cat([-ext, ext]).max(dim=1).values
+        ext = ext + torch.tensor([pad4 * 2 - cx, pad4 * 2 - cy] * 2, dtype=ext.dtype)
+        ext = ext.clamp(min=0).min(torch.tensor([w - 1, h - 1] * 2, dtype=ext.dtype))
+        mx0, my0, mx1, my1 = (int(v) for v in ext.ceil().to(torch.int32).tolist())
+        like = g_inv[:, 0, 0]
+        g = _shift((mx0 - mx1) / 2, (my0 - my1) / 2, like) @ g_inv
+        g = _scale(2, 2, like) @ g @ _scale(0.5, 0.5, like)
+        g = _shift(-0.5, -0.5, like) @ g @ _shift(0.5, 0.5, like)
+        wu, hu = 2 * (w + mx0 + mx1), 2 * (h + my0 + my1)
+        out_h, out_w = (h + pad4 * 2) * 2, (w + pad4 * 2) * 2
+        g = _scale(2 / wu, 2 / hu, like) @ g @ _scale(out_w / 2, out_h / 2, like)
+        return (mx0, mx1, my0, my1), g[:, :2, :].reshape(n, 6).to(torch.float32).contiguous()
+
+    @staticmethod
+    def fused_ok(images):
+        if not images.is_cuda or images.dtype != torch.float32 or images.shape[1] > 4:
+            return False
+        from .. import _lib
+        n, c, h, w = images.shape
+        return _lib.load().adm_augment_warp_smem(c, h, w) <= 200 * 1024
+
+    def warp_fused(self, images, fx, fy, g_inv):
+        """Flips + the whole anti-aliased warp as ONE sm_100a kernel (adm_augment_warp, one CTA per sample)."""
+        from .. import ops
+        n, c, h, w = images.shape
+        margins, theta = self.warp_plan(g_inv, h, w)
+        flips = torch.zeros(n, 2, dtype=torch.int32)
+        if fx is not None:
+            flips[:, 0] = fx.to(torch.int32)
+        if fy is not None:
+            flips[:, 1] = fy.to(torch.int32)
+        dev = images.device
+        return ops.augment_warp(images.contiguous(), theta.to(dev, non_blocking=True), flips.to(dev, non_blocking=True),
+                                margins)
+
     def __call__(self, images):
         n, c, h, w = images.shape
         # The random decisions are a few scalars per sample: they are drawn on the HOST (also for CUDA batches), so that
         # the batch-wide padding of the warp is known without synchronising with the device.
         fx, fy, g_inv, labels = self.draw(n, h, w, torch.device("cpu"))
         dev = images.device
+        if g_inv is not None and self.fused and self.fused_ok(images):
+            return self.warp_fused(images, fx, fy, g_inv), labels.to(dev, torch.float32, non_blocking=True)
         if fx is not None:
             images = torch.where(fx.to(dev, non_blocking=True).reshape(n, 1, 1, 1), images.flip(3), images)
         if fy is not None:

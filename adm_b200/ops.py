@@ -787,3 +787,17 @@ def chan_layernorm_bwd(dy, x, g, eps=1e-5):
     check(_lib.load().adm_chan_layernorm_bwd(_ptr(dy), dy.stride(-2), _ptr(x), x.stride(-2), rows, c, _ptr(g), float(eps),
                                              _ptr(dx), c, _ptr(dg), _stream()), "chan_layernorm_bwd")
     return dx, dg
+
+
+# ------------------------------------------------------------------------------------------------ AugmentPipe warp
+def augment_warp(x, theta, flips, margins):
+    """x fp32 [N,C,H,W] (CUDA) -> flipped + warped batch (ddm/augment.py:153-328); theta fp32 [N,6], flips int32 [N,2],
+    margins = (mx0, mx1, my0, my1) host ints."""
+    _need_cuda(x, theta, flips)
+    assert x.dtype == F32 and x.is_contiguous() and theta.dtype == F32 and flips.dtype == torch.int32
+    n, c, h, w = x.shape
+    y = torch.empty_like(x)
+    mx0, mx1, my0, my1 = (int(v) for v in margins)
+    check(_lib.load().adm_augment_warp(_ptr(x), _ptr(y), _ptr(theta), _ptr(flips), n, c, h, w, mx0, mx1, my0, my1,
+                                       _stream()), "augment_warp")
+    return y

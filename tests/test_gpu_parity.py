@@ -371,6 +371,34 @@ def test_unet_celebahq_full_config_runs():
     assert img.shape == (2, 3, 256, 256) and float(img.min()) >= 0 and float(img.max()) <= 1
 
 
+# ---------------------------------------------------------------- AugmentPipe as one kernel
+def test_fused_augment_pipe_vs_reference_golden(golden_dir):
+    """adm_augment_warp (flips + reflect pad + sym6 upsample + affine bilinear sample + sym6 decimate + crop in ONE kernel,
+    one CTA per sample) against the batches recorded from the unmodified reference AugmentPipe (make_golden_augment.py:
+    the DDM configuration at p = 0.15 and the same with p = 1 so that every transform fires on every sample), and against
+    the in-tree torch-op sequence on the same draws; labels exact, images to float32 round-off."""
+    from adm_b200 import _lib
+    from adm_b200.ddm.augment import AugmentPipe
+    from tests.golden.make_golden_augment import KW, KW_HOT, SEEDS, inputs
+    g = torch.load(os.path.join(golden_dir, "augment.pt"))
+    for name, kw in (("cfg", KW), ("hot", KW_HOT)):
+        for seed in SEEDS:
+            pipe = AugmentPipe(**kw)
+            x = inputs(seed).cuda()
+            assert pipe.fused and pipe.fused_ok(x)
+            l0 = _lib.load().adm_launch_count()
+            torch.manual_seed(seed)
+            y, lab = pipe(x)
+            assert _lib.load().adm_launch_count() == l0 + 1  # the whole pipe was one kernel of ours
+            ref = g[f"{name}_{seed}"]
+            assert torch.equal(lab.cpu(), ref["labels"])
+            assert (y.cpu() - ref["images"]).abs().max().item() < 1e-4, (name, seed)
+            pipe.fused = False
+            torch.manual_seed(seed)
+            y2, _ = pipe(x)
+            assert (y - y2).abs().max().item() < 1e-4
+
+
 # ---------------------------------------------------------------- frozen first stage (SURVEY section 8 row f-1)
 def test_autoencoder_kl_vs_reference_golden(golden_dir):
     """AutoencoderKL.encode / decode against vectors recorded from the unmodified reference (make_golden_ae.py):
