@@ -274,17 +274,21 @@ __global__ void __launch_bounds__(256) unet_output_bwd_kernel(const float* __res
 }
 
 // ------------------------------------------------------------------------------------------------ AugmentPipe warp (f-4)
-// One CTA per sample runs the whole geometric augmentation of ddm/augment.py:153-328 as the reference's DDM module
-// configures it (ddm_const.py:179-180): x / y flips, reflect padding by the batch-wide margins, 2x upsampling with the
-// sym6 low-pass, bilinear sampling through the per-sample inverse affine map, sym6 low-pass + 2x decimation, crop.
-// The padded and the upsampled images are never materialised: a tap of the bilinear sampler evaluates the zero-stuffed
-// 12-tap separable filter directly on the flipped 32x32 image held in shared memory (6 x 6 non-zero taps per point,
-// reflect indexing on the fly).  Shared memory: image [C][H][W], sampled grid [C][Gh][Gw], x-decimated [C][Gh][W].
+// The whole geometric augmentation of ddm/augment.py:153-328 as the reference's DDM module configures it
+// (ddm_const.py:179-180) in ONE kernel: x / y flips, reflect padding by the batch-wide margins, 2x upsampling with the sym6
+// low-pass, bilinear sampling through the per-sample inverse affine map, sym6 low-pass + 2x decimation, crop.
+// grid (AUG_BANDS, N): a CTA produces a band of output rows of one sample and evaluates only the rows of the sampled grid
+// that band's decimation filter reads.  The padded and the upsampled images are never materialised: the upsampling filter is
+// separable, so a bilinear sample of the upsampled image is sum_iy sum_ix wY[iy] wX[ix] P[iy][ix] over an 8 x 8 window of
+// the (reflect-indexed) flipped source image, where wY / wX fold the two bilinear weights into the zero-stuffed 12-tap
+// filter (6 non-zero taps per upsampled row).  Shared memory: image [C][H][W], grid band [C][rows][Gw], x-decimated band.
 // theta [N][6] is the matrix handed to affine_grid (all compositions done on the host: a few floats per sample).
 __constant__ float c_sym6[12] = {0.015404109327027373f, 0.0034907120842174702f, -0.11799011114819057f,
                                  -0.048311742585633f,   0.4910559419267466f,    0.787641141030194f,
                                  0.3379294217276218f,   -0.07263752278646252f,  -0.021060292512300564f,
                                  0.04472490177066578f,  0.0017677118642428036f, -0.007800708325034148f};
+constexpr int AUG_BANDS = 4;
+constexpr int AUG_PAD4 = 3;  // len(sym6) / 4
 
 __device__ __forceinline__ int aug_reflect(int i, int n) {  // one reflection is enough: margins are <= n - 1
     if (i < 0) i = -i;
@@ -292,19 +296,52 @@ __device__ __forceinline__ int aug_reflect(int i, int n) {  // one reflection is
     return i;
 }
 
+// Combined weights of one axis for a bilinear sample at upsampled coordinate p (p0 = floor(p), weights w0 / w1 on p0 / p0 + 1):
+// wgt[k] multiplies padded-image index base + k (k < 8, base = floor(p0 / 2) - 3); src[k] = its reflect-mapped source index,
+// or -1 when the padded index falls outside the image (zeros).  The upsampling conv is a cross-correlation of the
+// zero-stuffed image with the FLIPPED filter and padding 6: U[P] = sum over a = (P mod 2) + 2h of sym6[11 - a] * pad[(P + a - 6) / 2],
+// which puts tap h of row p0 at k = h + (p0 mod 2) and tap h of row p0 + 1 at k = h + 1.  Every array index below is a
+// compile-time constant (registers, no local memory).
+__device__ __forceinline__ void aug_axis(int p0, float w0, float w1, int size_up, int size_pad, int margin, int size,
+                                         float (&wgt)[8], int (&src)[8]) {
+    constexpr float E[6] = {-0.007800708325034148f, 0.04472490177066578f, -0.07263752278646252f, 0.787641141030194f,
+                            -0.048311742585633f, 0.0034907120842174702f};  // sym6[11 - 2h]
+    constexpr float O[6] = {0.0017677118642428036f, -0.021060292512300564f, 0.3379294217276218f, 0.4910559419267466f,
+                            -0.11799011114819057f, 0.015404109327027373f};  // sym6[10 - 2h]
+    const bool par = (p0 & 1) != 0;
+    if (p0 < 0 || p0 >= size_up) w0 = 0.f;          // grid_sample padding_mode = zeros
+    if (p0 + 1 < 0 || p0 + 1 >= size_up) w1 = 0.f;
+    const int base = (p0 >> 1) - 3;  // arithmetic shift = floor for negative p0
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        // row p0 (parity par): even rows use the even taps E, odd rows the odd taps O; row p0 + 1 the other set
+        const float f0_same = (k <= 5) ? (par ? 0.f : E[k <= 5 ? k : 0]) : 0.f;               // par == 0: tap k
+        const float f0_shift = (k >= 1 && k <= 6) ? (par ? O[(k >= 1 && k <= 6) ? k - 1 : 0] : 0.f) : 0.f;  // par == 1: tap k - 1
+        const float f1 = (k >= 1 && k <= 6) ? (par ? E[(k >= 1 && k <= 6) ? k - 1 : 0] : O[(k >= 1 && k <= 6) ? k - 1 : 0]) : 0.f;
+        wgt[k] = w0 * (f0_same + f0_shift) + w1 * f1;
+        const int i = base + k;
+        src[k] = (i < 0 || i >= size_pad) ? -1 : aug_reflect(i - margin, size);
+    }
+}
+
 __global__ void __launch_bounds__(256) augment_warp_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                            const float* __restrict__ theta,
                                                            const int* __restrict__ flips, int C, int H, int W, int mx0,
                                                            int mx1, int my0, int my1) {
     extern __shared__ float aug_sm[];
-    const int n = blockIdx.x;
-    const int pad4 = 3;                                   // len(sym6) / 4
-    const int Gh = (H + 2 * pad4) * 2, Gw = (W + 2 * pad4) * 2;
+    const int n = blockIdx.y;
+    const int Gh = (H + 2 * AUG_PAD4) * 2, Gw = (W + 2 * AUG_PAD4) * 2;
     const int Hp = H + my0 + my1, Wp = W + mx0 + mx1;     // reflect-padded image
     const int Hu = 2 * Hp, Wu = 2 * Wp;                   // upsampled image the sampler reads
+    const int rows_out = (H + AUG_BANDS - 1) / AUG_BANDS;
+    const int h_lo = blockIdx.x * rows_out, h_hi = min(H, h_lo + rows_out);
+    if (h_lo >= h_hi) return;
+    // grid rows the band's y-decimation reads: 2 (h + pad4) + b - 5, b = 0 .. 11
+    const int g_lo = max(0, 2 * (h_lo + AUG_PAD4) - 5), g_hi = min(Gh, 2 * (h_hi - 1 + AUG_PAD4) + 7);
+    const int R = g_hi - g_lo;
     float* img = aug_sm;                                  // [C][H][W], flips applied
-    float* grid = img + C * H * W;                        // [C][Gh][Gw]
-    float* dec = grid + C * Gh * Gw;                      // [C][Gh][W]
+    float* grid = img + C * H * W;                        // [C][R][Gw]
+    float* dec = grid + C * R * Gw;                       // [C][R][W]
     const int fx = flips[2 * n], fy = flips[2 * n + 1];
     for (int i = threadIdx.x; i < C * H * W; i += blockDim.x) {
         const int w = i % W, h = (i / W) % H, c = i / (W * H);
@@ -313,65 +350,65 @@ __global__ void __launch_bounds__(256) augment_warp_kernel(const float* __restri
     __syncthreads();
     const float t00 = theta[6 * n], t01 = theta[6 * n + 1], t02 = theta[6 * n + 2];
     const float t10 = theta[6 * n + 3], t11 = theta[6 * n + 4], t12 = theta[6 * n + 5];
-    // value of the upsampled image at integer (Y, X), all channels: sum over the taps that land on non-zero (even)
-    // positions of the zero-stuffed image; the conv is a cross-correlation with the FLIPPED filter and padding 6
-    auto upsampled = [&](int Y, int X, float* out) {
-        for (int c = 0; c < C; ++c) out[c] = 0.f;
-        if (Y < 0 || Y >= Hu || X < 0 || X >= Wu) return;  // grid_sample padding_mode = zeros
-        for (int a = Y & 1; a < 12; a += 2) {
-            const int iy = (Y + a - 6) >> 1;               // (Y + a - 6) is even
-            if (iy < 0 || iy >= Hp) continue;
-            const int sy = aug_reflect(iy - my0, H);
-            const float ka = c_sym6[11 - a];
-            for (int b = X & 1; b < 12; b += 2) {
-                const int ix = (X + b - 6) >> 1;
-                if (ix < 0 || ix >= Wp) continue;
-                const int sx = aug_reflect(ix - mx0, W);
-                const float k = ka * c_sym6[11 - b];
-                for (int c = 0; c < C; ++c) out[c] += k * img[(c * H + sy) * W + sx];
-            }
-        }
-    };
-    // bilinear sampling (affine_grid + grid_sample, align_corners = False, zeros outside)
-    for (int i = threadIdx.x; i < Gh * Gw; i += blockDim.x) {
-        const int gi = i / Gw, gj = i - gi * Gw;
+    // bilinear sampling (affine_grid + grid_sample, align_corners = False, zeros outside) of the upsampled image
+    for (int i = threadIdx.x; i < R * Gw; i += blockDim.x) {
+        const int r = i / Gw, gj = i - r * Gw, gi = g_lo + r;
         const float bx = (2.f * gj + 1.f) / Gw - 1.f, by = (2.f * gi + 1.f) / Gh - 1.f;
         const float gx = t00 * bx + t01 * by + t02, gy = t10 * bx + t11 * by + t12;
         const float px = ((gx + 1.f) * Wu - 1.f) * 0.5f, py = ((gy + 1.f) * Hu - 1.f) * 0.5f;
-        const float fx0 = floorf(px), fy0 = floorf(py);
-        const int x0 = static_cast<int>(fx0), y0 = static_cast<int>(fy0);
-        const float wx1 = px - fx0, wy1 = py - fy0, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f}, v[4];
-        const float wts[4] = {wy0 * wx0, wy0 * wx1, wy1 * wx0, wy1 * wx1};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            upsampled(y0 + (t >> 1), x0 + (t & 1), v);
-            for (int c = 0; c < C; ++c) acc[c] += wts[t] * v[c];
+        // far outside: nothing to sample (also keeps the float -> int conversion in range)
+        if (!(px > -2.f && px < Wu + 1.f && py > -2.f && py < Hu + 1.f)) {
+            for (int c = 0; c < C; ++c) grid[(c * R + r) * Gw + gj] = 0.f;
+            continue;
         }
-        for (int c = 0; c < C; ++c) grid[(c * Gh + gi) * Gw + gj] = acc[c];
+        const float fx0 = floorf(px), fy0 = floorf(py);
+        float wX[8], wY[8];
+        int sX[8], sY[8];
+        aug_axis(static_cast<int>(fx0), 1.f - (px - fx0), px - fx0, Wu, Wp, mx0, W, wX, sX);
+        aug_axis(static_cast<int>(fy0), 1.f - (py - fy0), py - fy0, Hu, Hp, my0, H, wY, sY);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ky = 0; ky < 8; ++ky) {
+            if (sY[ky] < 0 || wY[ky] == 0.f) continue;
+            float row[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int kx = 0; kx < 8; ++kx) {
+                if (sX[kx] < 0) continue;
+                const float* pix = img + sY[ky] * W + sX[kx];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < C) row[c] += wX[kx] * pix[c * H * W];
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[c] += wY[ky] * row[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c < C) grid[(c * R + r) * Gw + gj] = acc[c];
     }
     __syncthreads();
     // low-pass + decimate along x (stride 2, padding 5), cropped to the W centre columns
-    for (int i = threadIdx.x; i < C * Gh * W; i += blockDim.x) {
-        const int w = i % W, gi = (i / W) % Gh, c = i / (W * Gh);
-        const float* row = grid + (c * Gh + gi) * Gw;
+    for (int i = threadIdx.x; i < C * R * W; i += blockDim.x) {
+        const int w = i % W, r = (i / W) % R, c = i / (W * R);
+        const float* row = grid + (c * R + r) * Gw;
         float a = 0.f;
 #pragma unroll
         for (int b = 0; b < 12; ++b) {
-            const int j = 2 * (w + pad4) + b - 5;
+            const int j = 2 * (w + AUG_PAD4) + b - 5;
             if (j >= 0 && j < Gw) a += c_sym6[b] * row[j];
         }
         dec[i] = a;
     }
     __syncthreads();
-    // ... and along y, cropped to the H centre rows
-    for (int i = threadIdx.x; i < C * H * W; i += blockDim.x) {
-        const int w = i % W, h = (i / W) % H, c = i / (W * H);
+    // ... and along y, cropped to the H centre rows (this CTA's band)
+    const int rows = h_hi - h_lo;
+    for (int i = threadIdx.x; i < C * rows * W; i += blockDim.x) {
+        const int w = i % W, h = h_lo + (i / W) % rows, c = i / (W * rows);
         float a = 0.f;
 #pragma unroll
         for (int b = 0; b < 12; ++b) {
-            const int j = 2 * (h + pad4) + b - 5;
-            if (j >= 0 && j < Gh) a += c_sym6[b] * dec[(c * Gh + j) * W + w];
+            const int j = 2 * (h + AUG_PAD4) + b - 5;
+            if (j >= 0 && j < Gh) a += c_sym6[b] * dec[(c * R + (j - g_lo)) * W + w];
         }
         y[(static_cast<long long>(n) * C + c) * H * W + h * W + w] = a;
     }
@@ -563,13 +600,15 @@ int adm_unet_output_bwd(const float* dd1, const float* dd2, const float* sigma, 
 }
 
 long long adm_augment_warp_smem(int c, int h, int w) {
-    const long long gh = (h + 6) * 2, gw = (w + 6) * 2;
-    return 4LL * (1LL * c * h * w + c * gh * gw + c * gh * w);
+    // worst-case band: rows_out output rows read 2 rows_out + 10 grid rows
+    const long long rows_out = (h + AUG_BANDS - 1) / AUG_BANDS, gw = (w + 2 * AUG_PAD4) * 2;
+    const long long r = 2 * rows_out + 10;
+    return 4LL * (1LL * c * h * w + c * r * gw + c * r * w);
 }
 
 int adm_augment_warp(const float* x, float* y, const float* theta, const int* flips, int n, int c, int h, int w,
                      int mx0, int mx1, int my0, int my1, void* stream) {
-    if (n <= 0 || c <= 0 || c > 4 || h < 2 || w < 2) { set_error("augment_warp: bad shape (channels <= 4)"); return ADM_ERR_SHAPE; }
+    if (n <= 0 || n > 65535 || c <= 0 || c > 4 || h < 2 || w < 2) { set_error("augment_warp: bad shape (channels <= 4)"); return ADM_ERR_SHAPE; }
     if (mx0 < 0 || mx1 < 0 || my0 < 0 || my1 < 0 || mx0 >= w || mx1 >= w || my0 >= h || my1 >= h) {
         set_error("augment_warp: margins must lie in [0, size - 1]");
         return ADM_ERR_SHAPE;
@@ -582,7 +621,8 @@ int adm_augment_warp(const float* x, float* y, const float* theta, const int* fl
         if (e != cudaSuccess) { set_error("augment_warp: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ADM_ERR_CUDA; }
         attr_set = smem;
     }
-    augment_warp_kernel<<<n, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, y, theta, flips, c, h, w, mx0, mx1, my0, my1);
+    augment_warp_kernel<<<dim3(AUG_BANDS, n), 256, smem, static_cast<cudaStream_t>(stream)>>>(x, y, theta, flips, c, h, w, mx0,
+                                                                                             mx1, my0, my1);
     ADM_CHECK_LAUNCH("augment_warp");
     return 0;
 }

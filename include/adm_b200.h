@@ -151,7 +151,7 @@ int adm_gemm_batched(const adm_gemm_desc* desc, void* stream);
  * ddm/augment.py AugmentPipe.__call__ :153-328 as ddm_const.py:179-180 configures it (flips + one anti-aliased affine
  * warp): x, y fp32 NCHW [n][c][h][w] (c <= 4); flips int [n][2] = (flip x, flip y); theta fp32 [n][6] = the 2 x 3 matrix
  * the reference hands to affine_grid (:265-267, after its margin / upsampling / normalisation compositions); mx0, mx1,
- * my0, my1 = the batch-wide reflect-padding margins (:245-250).  One CTA per sample; padded and upsampled images are
+ * my0, my1 = the batch-wide reflect-padding margins (:245-250).  Four CTAs (row bands) per sample; padded and upsampled images are
  * never materialised.  adm_augment_warp_smem: dynamic shared memory the kernel needs (<= 200 KB).             */
 long long adm_augment_warp_smem(int c, int h, int w);
 int adm_augment_warp(const float* x, float* y, const float* theta, const int* flips, int n, int c, int h, int w,
