@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libadm_b200.so")
+# ADM_B200_LIB: another build of the same library (A/B timing of kernel changes on one box); default = the in-tree build
+LIB_PATH = os.environ.get("ADM_B200_LIB") or os.path.join(_HERE, "libadm_b200.so")
 
 _lib = None
 
