@@ -177,6 +177,7 @@ class TrainStep:
         self.pg = process_group
         self.arena = ParamArena(self.net, completion_order(self.net), channels_last=self.engine.packable_params())
         self._bind_affine()
+        self._grads_clean = True  # the gradient arena is all zeros (fresh, or zeroed by the last optimizer step)
         self._bind_qkv()
         self.m = torch.zeros_like(self.arena.flat)
         self.v = torch.zeros_like(self.arena.flat)
@@ -485,6 +486,7 @@ class TrainStep:
                           hyper_dev=self.hyper, p_bf16=a.shadow)
                 self.refresh_derived()
                 a.zero_grad()
+                self._grads_clean = True
                 self.engine.invalidate()
                 self._seg_capture["graph"].capture_end()
                 self.segments = self._seg_capture["segments"] + [(self._seg_capture["graph"], None)]
@@ -525,6 +527,7 @@ class TrainStep:
                   hyper_dev=self.hyper, p_bf16=a.shadow)
         self.refresh_derived()
         a.zero_grad()
+        self._grads_clean = True
         self.engine.invalidate()
 
     def micro_step(self, x, t=None, noise=None, last=True, **kw):
@@ -535,6 +538,10 @@ class TrainStep:
             self._arm()
         else:
             self.engine.grad_hook = None
+        # first backward into a zeroed arena: the grouped affine weight gradient may be stored instead of accumulated
+        self.engine.affine_grad_overwrite = (self._grads_clean and self.engine.affine_pack is not None
+                                             and os.environ.get("ADM_AFFINE_OVERWRITE", "1") != "0")
+        self._grads_clean = False
         if set(kw) <= {"augment_labels"}:
             return self._direct_step(x, t, noise, kw.get("augment_labels"))
         if t is None:

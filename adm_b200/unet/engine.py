@@ -51,6 +51,7 @@ class UNetEngine:
         # fp32 master slice of wall, parameter versions)
         # when every block's affine weight / bias are laid out back to back in the parameter arena
         self.affine_pack = None
+        self.affine_grad_overwrite = False  # set by TrainStep when grad_accum == 1 (gradients are zero before backward)
         # Weight / bias gradients of the convs run on a side stream, concurrently with the data-gradient chain: a wgrad
         # only feeds the optimizer, and every GEMM is a persistent kernel whose last partial wave leaves SMs idle (and
         # the 4x4 / 8x8 levels never fill 148 SMs) — the other stream's CTAs take those SMs.  Joined at every _notify.
@@ -582,7 +583,9 @@ class UNetEngine:
         dpb = ops.cast_bf16(dparams_all)
         wall, _ = self.affine_all()
         if self.affine_pack is not None:  # all affine weights / biases are contiguous in the gradient arena
-            ops.gemm_tn(dpb, e.embb, out=self.affine_pack[2], accumulate=True)
+            # the [sum 2*Cout, emb] result is 123 MB for K = batch = 128: purely output bound.  When the arena's gradients
+            # are known to be zero here (one micro-batch per optimizer step) a plain store replaces 31 M vector atomics.
+            ops.gemm_tn(dpb, e.embb, out=self.affine_pack[2], accumulate=not self.affine_grad_overwrite)
             ops.col_sums(dpb, self.affine_pack[3])
         else:
             dwall = ops.gemm_tn(dpb, e.embb)  # [sum 2*Cout, emb]
