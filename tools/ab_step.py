@@ -19,7 +19,8 @@ def child(steps, sample):
     dpm = bench.build_model(dev)
     dpm.train()
     step = TrainStep(dpm)
-    x = 2 * torch.rand(128, 3, 32, 32, device=dev) - 1
+    B = int(os.environ.get("ADM_AB_BATCH", "128"))
+    x = 2 * torch.rand(B, 3, 32, 32, device=dev) - 1
     step.capture(x)
     step.prefetch(x)
     for _ in range(5):
@@ -33,7 +34,8 @@ def child(steps, sample):
         step.prefetch(x)
     e1.record()
     torch.cuda.synchronize()
-    out = f"train {e0.elapsed_time(e1) / steps:.3f} ms/step loss {float(loss):.2f}"
+    ms = e0.elapsed_time(e1) / steps
+    out = f"train {ms:.3f} ms/step ({B / ms * 1000:.0f} img/s at batch {B}) loss {float(loss):.2f}"
     if sample:
         dpm.eval()
         dpm.sampling_timesteps = 10
