@@ -2,7 +2,7 @@
 denoiser of DDM).  Same class names, constructor arguments, attributes and ``state_dict`` layout as the reference:
 
     EDMPrecond(img_resolution, img_channels, label_dim=0, use_fp16=False, sigma_min=0, sigma_max=inf, sigma_data=0.5,
-               model_type='DhariwalUNet', precondition=True, **model_kwargs)        uncond_unet.py:588-612
+               model_type='DhariwalUNet' | 'SongUNet', precondition=True, **model_kwargs)        uncond_unet.py:588-612
     forward(x, sigma, class_labels=None, force_fp32=False, **{'augment_labels': ...}) -> (D_x, D_y)   :614-635
 
 The modules below only *own parameters* (fp32, reference names and shapes).  All arithmetic of the network runs in
@@ -232,18 +232,47 @@ class EDMPrecond(nn.Module):
         self.channels = img_channels
         self.label_dim, self.use_fp16 = label_dim, use_fp16
         self.sigma_min, self.sigma_max, self.sigma_data = sigma_min, sigma_max, sigma_data
-        if model_type != "DhariwalUNet":
-            raise NotImplementedError(f"adm_b200 implements model_type='DhariwalUNet' (got {model_type!r})")
-        if not precondition:
-            raise NotImplementedError("adm_b200 implements precondition=True (the configured DDM path)")
+        if model_type not in ("DhariwalUNet", "SongUNet"):
+            raise NotImplementedError(f"adm_b200 implements model_type 'DhariwalUNet' and 'SongUNet' (got {model_type!r})")
         model_kwargs.pop("class_name", None)
+        self.model_type = model_type
+        if model_type == "SongUNet":
+            from .song_unet import SongUNet
+            self.model = SongUNet(img_resolution=img_resolution, in_channels=img_channels, out_channels=img_channels,
+                                  label_dim=label_dim, **model_kwargs)
+            return
+        if not precondition:
+            raise NotImplementedError("adm_b200 implements precondition=True for DhariwalUNet (the configured DDM path)")
         self.model = DhariwalUNet(img_resolution=img_resolution, in_channels=img_channels, out_channels=img_channels,
                                   label_dim=label_dim, **model_kwargs)
 
     def forward(self, x, sigma, class_labels=None, force_fp32=False, *args, **model_kwargs):
         """x: [B, C, H, W] (any float dtype, NCHW), sigma = t: [B] or 0-dim.  Returns (D_x, D_y) fp32 NCHW."""
+        if self.model_type == "SongUNet":
+            return self._forward_module_graph(x, sigma, class_labels, **model_kwargs)
         from .engine import unet_apply
         return unet_apply(self.model.engine, x, sigma, model_kwargs.get("augment_labels"))
+
+    def _forward_module_graph(self, x, sigma, class_labels=None, **model_kwargs):
+        """uncond_unet.py:614-635 around a network that is a torch-autograd module graph (SongUNet): the per-sample
+        preconditioning scalars and the two output mixes are a handful of elementwise ops on 3-channel images."""
+        x = x.to(torch.float32)
+        sigma = sigma.to(torch.float32).reshape(-1, 1, 1, 1)
+        if self.label_dim == 0:
+            class_labels = None
+        elif class_labels is None:
+            class_labels = torch.zeros([1, self.label_dim], device=x.device)
+        else:
+            class_labels = class_labels.to(torch.float32).reshape(-1, self.label_dim)
+        den = sigma ** 2 - sigma + 1
+        c_skip1, c_skip2 = (sigma - 1) / den, sigma.sqrt() / den
+        c_out1, c_out2 = torch.sqrt(sigma / den), (1 - sigma) / den.sqrt()
+        c_in = 1 / torch.sqrt((1 - sigma) ** 2 + sigma)
+        c_noise = sigma.log()
+        f_x, f_y = self.model(c_in * x, c_noise.flatten().expand(x.shape[0]), class_labels=class_labels, **model_kwargs)
+        if not self.precondition:
+            return f_x, f_y
+        return c_skip1 * x + c_out1 * f_x, c_skip2 * x + c_out2 * f_y
 
     def round_sigma(self, sigma):
         return torch.as_tensor(sigma)

@@ -7,6 +7,8 @@ A CPU restatement, in plain functional PyTorch (fp32 / fp64), of the reference's
   :53-66, :72-113, :119-129, :217-230.  Parameters are taken from a flat ``state_dict`` with the reference's key
   grammar (``model.enc.32x32_block0.conv0.weight`` ...), so the restatement shares no module code with either the
   reference or the product.
+* EDMPrecond + SongUNet forward      — /root/reference/unet/uncond_unet.py:253-441 (row f-4), every Conv2d / UNetBlock
+  branch it uses (:91-113, :189-211); pinned by tests/golden/make_golden_song.py (song_unet.pt).
 * DDM-const math                     — /root/reference/ddm/ddm_const.py:274-287 (t, q_sample), :290-303 (x0, x_{t-s}),
   :305-364 (loss; ``loss_main_func`` = MSE_Loss, ddm/loss.py:300-312; LPIPS term = 0 because the reference cannot build
   LPIPS offline), :425-476 (deterministic sampler), :381-422 (stochastic sampler).
@@ -273,6 +275,150 @@ def edm_precond_forward(sd: StateDict, cfg, x, sigma, augment_labels=None, dropo
     c_noise = sigma.log()
     f_x, f_y = dhariwal_forward(sd, cfg, c_in * x, c_noise.flatten(), augment_labels, dropout_masks)
     return c_skip1 * x + c_out1 * f_x, c_skip2 * x + c_out2 * f_y
+
+
+# ----------------------------------------------------------------------------------------------- SongUNet (row f-4)
+def song_config(img_resolution=32, img_channels=3, model_channels=128, channel_mult=(1, 2, 2, 2), channel_mult_emb=4,
+                num_blocks=4, attn_resolutions=(16,), dropout=0.10, augment_dim=0, embedding_type="fourier",
+                channel_mult_noise=2, encoder_type="residual", decoder_type="standard", resample_filter=(1, 3, 3, 1), **_):
+    """Constructor defaults of SongUNet, uncond_unet.py:254-272."""
+    return dict(img_resolution=img_resolution, img_channels=img_channels, model_channels=model_channels,
+                channel_mult=list(channel_mult), channel_mult_emb=channel_mult_emb, num_blocks=num_blocks,
+                attn_resolutions=list(attn_resolutions), dropout=dropout, augment_dim=augment_dim,
+                embedding_type=embedding_type, channel_mult_noise=channel_mult_noise, encoder_type=encoder_type,
+                decoder_type=decoder_type, resample_filter=list(resample_filter))
+
+
+def _song_conv(x, sd, p, filt, up=False, down=False, fused=False):
+    """Conv2d.forward, uncond_unet.py:91-113, every branch (general resample filter, fused resample)."""
+    w = sd.get(p + ".weight")
+    b = sd.get(p + ".bias")
+    f = None
+    if up or down:
+        f1 = torch.as_tensor(filt, dtype=torch.float32)
+        f = (f1.ger(f1) / f1.sum().square()).reshape(1, 1, len(filt), len(filt)).to(x.dtype)
+    w_pad = w.shape[-1] // 2 if w is not None else 0
+    f_pad = (f.shape[-1] - 1) // 2 if f is not None else 0
+    cin = x.shape[1]
+    if fused and up and w is not None:
+        x = F.conv_transpose2d(x, f.mul(4).tile([cin, 1, 1, 1]), groups=cin, stride=2, padding=max(f_pad - w_pad, 0))
+        x = F.conv2d(x, w, padding=max(w_pad - f_pad, 0))
+    elif fused and down and w is not None:
+        x = F.conv2d(x, w, padding=w_pad + f_pad)
+        x = F.conv2d(x, f.tile([w.shape[0], 1, 1, 1]), groups=w.shape[0], stride=2)
+    else:
+        if up:
+            x = F.conv_transpose2d(x, f.mul(4).tile([cin, 1, 1, 1]), groups=cin, stride=2, padding=f_pad)
+        if down:
+            x = F.conv2d(x, f.tile([cin, 1, 1, 1]), groups=cin, stride=2, padding=f_pad)
+        if w is not None:
+            x = F.conv2d(x, w, padding=w_pad)
+    if b is not None:
+        x = x + b.reshape(1, -1, 1, 1)
+    return x
+
+
+def _song_block(x, emb, sd, p, filt, up=False, down=False, dropout_mask=None):
+    """UNetBlock.forward, uncond_unet.py:189-211 as SongUNet configures it (:284-288): adaptive_scale=False, num_heads=1,
+    skip_scale=sqrt(0.5), eps=1e-6, resample_proj=True.  Which sub-modules exist is read off the state_dict."""
+    skip_scale = math.sqrt(0.5)
+    gn = lambda t, q: F.group_norm(t, min(32, t.shape[1] // 4), sd[q + ".weight"], sd[q + ".bias"], 1e-6)
+    orig = x
+    x = _song_conv(F.silu(gn(x, p + ".norm0")), sd, p + ".conv0", filt, up=up, down=down)
+    params = (emb @ sd[p + ".affine.weight"].t() + sd[p + ".affine.bias"]).unsqueeze(2).unsqueeze(3)
+    x = F.silu(gn(x + params, p + ".norm1"))
+    if dropout_mask is not None:
+        x = x * dropout_mask
+    x = _song_conv(x, sd, p + ".conv1", filt)
+    has_skip = (p + ".skip.weight") in sd or up or down
+    x = x + (_song_conv(orig, sd, p + ".skip", filt, up=up, down=down) if has_skip else orig)
+    x = x * skip_scale
+    if (p + ".qkv.weight") in sd:
+        qkv = _song_conv(gn(x, p + ".norm2"), sd, p + ".qkv", filt)
+        q, k, v = qkv.reshape(x.shape[0], x.shape[1], 3, -1).unbind(2)  # num_heads = 1
+        w = torch.einsum("ncq,nck->nqk", q, k / np.sqrt(k.shape[1])).softmax(dim=2)
+        a = torch.einsum("nqk,nck->ncq", w, v)
+        x = (_song_conv(a.reshape(*x.shape), sd, p + ".proj", filt) + x) * skip_scale
+    return x
+
+
+def song_forward(sd: StateDict, cfg, x, noise_labels, augment_labels=None):
+    """SongUNet.forward, uncond_unet.py:359-425 (the fork's two-decoder variant).  Returns (F_x, F_y).  The module order of
+    enc / dec / dec2 is the key order of the state_dict (= construction order of the ModuleDicts)."""
+    filt = cfg["resample_filter"]
+    nc = cfg["model_channels"] * cfg["channel_mult_noise"]
+    if cfg["embedding_type"] == "positional":  # PositionalEmbedding(endpoint=True), :217-230
+        freqs = torch.arange(0, nc // 2, dtype=torch.float32) / (nc // 2 - 1)
+        freqs = (1 / 10000) ** freqs
+        e = noise_labels.ger(freqs.to(noise_labels.dtype))
+    else:  # FourierEmbedding, :236-244
+        e = noise_labels.ger((2 * np.pi * sd["model.map_noise.freqs"]).to(noise_labels.dtype))
+    emb = torch.cat([e.cos(), e.sin()], dim=1)
+    emb = emb.reshape(emb.shape[0], 2, -1).flip(1).reshape(*emb.shape)
+    if cfg["augment_dim"] and augment_labels is not None:
+        emb = emb + augment_labels @ sd["model.map_augment.weight"].t()
+    emb = F.silu(emb @ sd["model.map_layer0.weight"].t() + sd["model.map_layer0.bias"])
+    emb = F.silu(emb @ sd["model.map_layer1.weight"].t() + sd["model.map_layer1.bias"])
+
+    def modules(section):
+        seen = []
+        for k in sd:
+            if k.startswith(f"model.{section}."):
+                name = k.split(".")[2]
+                if name not in seen:
+                    seen.append(name)
+        return seen
+
+    # aux_down / aux_up (kernel 0) own no parameter: only their resample_filter buffer shows up in the state_dict, which
+    # is enough to list them
+    # The fork keeps a second skip list for decoder 2 (:371, :388) that is appended to but NOT updated by the aux branches
+    # (`x = skips[-1] = ...` touches the first list only, :381-384): decoder 2 sees the pre-aux tensors.  Restated as is.
+    skips, skips2, aux = [], [], x
+    for name in modules("enc"):
+        p = "model.enc." + name
+        if "aux_down" in name:
+            aux = _song_conv(aux, sd, p, filt, down=True)
+        elif "aux_skip" in name:
+            x = skips[-1] = x + _song_conv(aux, sd, p, filt)
+        elif "aux_residual" in name:
+            x = skips[-1] = aux = (x + _song_conv(aux, sd, p, filt, down=True, fused=True)) / np.sqrt(2)
+        else:
+            x = _song_conv(x, sd, p, filt) if name.endswith("_conv") else \
+                _song_block(x, emb, sd, p, filt, down=name.endswith("_down"))
+            skips.append(x)
+            skips2.append(x)
+    outs = []
+    for dec, dname, src in (("dec", "decouple1", skips), ("dec2", "decouple2", skips2)):
+        h = F.conv2d(x, sd[f"model.{dname}.0.weight"], sd[f"model.{dname}.0.bias"], padding=1)
+        h = _spatial_att(h, sd, f"model.{dname}.1") + x
+        sk = list(src)
+        aux_o = tmp = None
+        for name in modules(dec):
+            p = f"model.{dec}." + name
+            if "aux_up" in name:
+                aux_o = _song_conv(aux_o, sd, p, filt, up=True)
+            elif "aux_norm" in name:
+                tmp = F.group_norm(h, min(32, h.shape[1] // 4), sd[p + ".weight"], sd[p + ".bias"], 1e-6)
+            elif "aux_conv" in name:
+                tmp = _song_conv(F.silu(tmp), sd, p, filt)
+                aux_o = tmp if aux_o is None else tmp + aux_o
+            else:
+                cin = sd[p + ".norm0.weight"].shape[0]
+                if h.shape[1] != cin:
+                    h = torch.cat([h, sk.pop()], dim=1)
+                h = _song_block(h, emb, sd, p, filt, up=name.endswith("_up"))
+        outs.append(aux_o)
+    return outs[0], outs[1]
+
+
+def song_precond_forward(sd: StateDict, cfg, x, sigma, augment_labels=None):
+    """EDMPrecond.forward (uncond_unet.py:614-635) around SongUNet."""
+    x = x.to(torch.float32)
+    sigma = sigma.to(torch.float32).reshape(-1, 1, 1, 1)
+    q = sigma ** 2 - sigma + 1
+    c_in = 1 / torch.sqrt((1 - sigma) ** 2 + sigma)
+    f_x, f_y = song_forward(sd, cfg, c_in * x, sigma.log().flatten(), augment_labels)
+    return (sigma - 1) / q * x + torch.sqrt(sigma / q) * f_x, sigma.sqrt() / q * x + (1 - sigma) / q.sqrt() * f_y
 
 
 # ----------------------------------------------------------------------------------------------- DDM-const math

@@ -371,6 +371,14 @@ def test_unet_celebahq_full_config_runs():
     assert img.shape == (2, 3, 256, 256) and float(img.min()) >= 0 and float(img.max()) <= 1
 
 
+# ---------------------------------------------------------------- SongUNet
+@pytest.mark.parametrize("case", ["song_unet_ddpmpp", "song_unet_ncsnpp"])
+def test_song_unet_vs_reference_golden(case):
+    """EDMPrecond(model_type='SongUNet') — DDPM++ and NCSN++ flavours — forward and backward against vectors recorded from
+    the unmodified reference (tests/golden/make_golden_song.py)."""
+    assert CU.CASES[case]()
+
+
 # ---------------------------------------------------------------- AugmentPipe as one kernel (SURVEY section 8 row f-4)
 def test_fused_augment_pipe_vs_reference_golden(golden_dir):
     """adm_augment_warp (flips + reflect pad + sym6 upsample + affine bilinear sample + sym6 decimate + crop in ONE kernel,

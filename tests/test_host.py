@@ -259,3 +259,20 @@ def test_use_augment_builds_the_in_tree_pipe():
     assert isinstance(d.augment, AugmentPipe) and d.augment.p == 0.15 and d.augment.xflip == 1e8
     d = DDPM(model=Net(), cfg=dict(image_size=[32, 32]), image_size=[32, 32])
     assert d.augment is None and d.use_augment is False
+
+
+@pytest.mark.parametrize("name", ["ddpmpp", "ncsnpp"])
+def test_song_unet_state_dict_layout_matches_reference(golden_dir, name):
+    """EDMPrecond(model_type='SongUNet') builds the reference's key -> shape map (recorded by make_golden_song.py from the
+    unmodified reference) for the DDPM++ and the NCSN++ flavour, and loads a reference-style state_dict."""
+    import torch
+    from adm_b200.unet.uncond_unet import EDMPrecond
+    from tests.golden.make_golden_song import CONFIGS, state_dict_for
+    g = torch.load(os.path.join(golden_dir, "song_unet.pt"))[name]
+    net = EDMPrecond(**CONFIGS[name])
+    assert {k: list(v.shape) for k, v in net.state_dict().items()} == g["keys"]
+    assert list(net.state_dict().keys()) == list(g["keys"].keys())
+    missing, unexpected = net.load_state_dict(state_dict_for(g["keys"]), strict=False)
+    assert not unexpected and all(k.endswith("resample_filter") for k in missing)
+    with pytest.raises(RuntimeError):  # no CPU fallback
+        net(torch.zeros(1, 3, 16, 16), torch.ones(1))

@@ -141,3 +141,21 @@ def test_t_steps():
     assert abs(ts[-2].item() - 1e-4) < 1e-12  # sigma_min ** 2 (ddm_const.py:429)
     assert abs(ts[1].item() - (1 + (1e-4 - 1) / 9)) < 1e-12
     assert O.t_steps_deterministic(1).tolist() == [1.0, 0.0]  # documented deviation from the reference's NaN
+
+
+@pytest.mark.parametrize("name", ["ddpmpp", "ncsnpp"])
+def test_oracle_song_unet_vs_reference_golden(golden_dir, name):
+    """oracle.song_precond_forward (EDMPrecond + SongUNet, uncond_unet.py:253-441) against D_x / D_y and parameter
+    gradients recorded from the unmodified reference (make_golden_song.py), DDPM++ and NCSN++ flavours, CPU fp32."""
+    from tests.golden.make_golden_song import CONFIGS, inputs, state_dict_for
+    g = torch.load(os.path.join(golden_dir, "song_unet.pt"))[name]
+    cfg = O.song_config(**CONFIGS[name])
+    sd = {k: v.requires_grad_(True) for k, v in state_dict_for(g["keys"]).items()}
+    x, t, aug, g1, g2 = inputs()
+    d_x, d_y = O.song_precond_forward(sd, cfg, x, t, aug if cfg["augment_dim"] else None)
+    assert torch.allclose(d_x, g["d_x"], rtol=1e-4, atol=1e-4) and torch.allclose(d_y, g["d_y"], rtol=1e-4, atol=1e-4)
+    ((d_x * g1).sum() + (d_y * g2).sum()).backward()
+    for k, ref in g["grads"].items():
+        assert torch.allclose(sd[k].grad, ref, rtol=1e-3, atol=1e-4 * float(ref.abs().max()) + 1e-6), k
+    for k, n in g["grad_norms"].items():
+        assert abs(float(sd[k].grad.norm()) - n) <= 1e-3 * n + 1e-6, k
