@@ -205,7 +205,10 @@ class DDPM(nn.Module):
         was_training = self.model.training
         self.model.eval()
         if use_graph is None:
-            use_graph = cond is None and x_T.is_cuda and not torch.cuda.is_current_stream_capturing()
+            # networks without the fused engine (SongUNet: a module graph) have no weight-change signature to key the
+            # captured loop on: they run the loop eagerly
+            use_graph = (cond is None and x_T.is_cuda and not torch.cuda.is_current_stream_capturing()
+                         and self._model_signature() is not None)
         try:
             if use_graph:
                 return self._sample_d_graph(x_T, ts, unnormalize)

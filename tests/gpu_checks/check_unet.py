@@ -589,6 +589,43 @@ def song_unet_ncsnpp():
 
 
 @case
+def song_unet_ddm_step():
+    """DDPM(model=EDMPrecond(model_type='SongUNet')): the DDM-const loss against oracle.p_losses over oracle.song_precond_forward
+    on the same weights / t / noise (1e-2, bf16), backward through torch autograd fills every gradient, 3-step sampler."""
+    import os
+    import torch
+    from oracle import ddm_oracle as O
+    from adm_b200.ddm.ddm_const import DDPM
+    from adm_b200.unet.uncond_unet import EDMPrecond
+    from tests.golden.make_golden_song import CONFIGS, inputs, state_dict_for
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "song_unet.pt"))["ddpmpp"]
+    cfg = CONFIGS["ddpmpp"]
+    sd = state_dict_for(g["keys"])
+    net = EDMPrecond(**cfg)
+    net.load_state_dict(sd, strict=False)
+    mcfg = dict(image_size=[16, 16], sampling_timesteps=3, eps=1e-4, sigma_max=1, sigma_min=0.01, weighting_loss=True)
+    dpm = DDPM(model=net, cfg=mcfg, **mcfg).cuda()
+    x, t, aug, g1, _ = inputs()
+    noise = g1
+    with torch.no_grad():
+        ocfg = O.song_config(**cfg)
+        ref, _ = O.p_losses(lambda xx, tt: O.song_precond_forward(sd, ocfg, xx, tt, aug), x, t, noise)
+    dpm.train()
+    loss, _ = dpm.p_losses(x.cuda(), t.cuda(), noise=noise.cuda(), augment_labels=aug.cuda())
+    rel = abs(loss.item() - ref.item()) / abs(ref.item())
+    print(f"  loss {loss.item():.4f} vs oracle {ref.item():.4f} rel {rel:.2e}", flush=True)
+    ok = rel < 1e-2
+    loss.backward()
+    missing = [k for k, p in net.named_parameters() if p.grad is None or not torch.isfinite(p.grad).all()]
+    print(f"  parameters without a finite gradient: {missing[:5]}", flush=True)
+    ok &= not missing
+    dpm.eval()
+    img = dpm.sample(batch_size=4)
+    ok &= tuple(img.shape) == (4, 3, 16, 16) and float(img.min()) >= 0 and float(img.max()) <= 1
+    return ok
+
+
+@case
 def unet_cifar():
     from tests.golden.make_golden import CIFAR
     cfg = dict(CIFAR)

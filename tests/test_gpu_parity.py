@@ -372,6 +372,10 @@ def test_unet_celebahq_full_config_runs():
 
 
 # ---------------------------------------------------------------- SongUNet
+def test_song_unet_ddm_step_vs_oracle():
+    assert CU.CASES["song_unet_ddm_step"]()
+
+
 @pytest.mark.parametrize("case", ["song_unet_ddpmpp", "song_unet_ncsnpp"])
 def test_song_unet_vs_reference_golden(case):
     """EDMPrecond(model_type='SongUNet') — DDPM++ and NCSN++ flavours — forward and backward against vectors recorded from
