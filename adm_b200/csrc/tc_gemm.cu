@@ -397,9 +397,12 @@ static int pick_box(int n, int h, int w, int pixels, int* bw, int* bh, int* bni)
 
 static inline int pad64(int c) { return (c + 63) / 64 * 64; }
 
+// taps per kernel row of a square odd kernel ('same' padding): 1 -> 1, 9 -> 3, 25 -> 5, 49 -> 7; 0 = unsupported
+static inline int taps_per_row(int ntaps) { return ntaps == 1 ? 1 : ntaps == 9 ? 3 : ntaps == 25 ? 5 : ntaps == 49 ? 7 : 0; }
+
 static void init_params(GemmParams* p) {
     memset(p, 0, sizeof(*p));
-    p->batches = 1; p->splits = 1; p->bdiv = 1; p->ntaps = 1; p->alpha = 1.f;
+    p->batches = 1; p->splits = 1; p->bdiv = 1; p->ntaps = 1; p->kw = 1; p->alpha = 1.f;
     p->tiles_w = 1; p->tiles_h = 1; p->bni = 1; p->bw = 1; p->bh = 1;
     p->n_split = INT_MAX;
 }
@@ -478,7 +481,7 @@ static int conv_fprop_impl(const void* x1, int c1, long long ld1, const void* x2
                            const float* bias, const void* residual, long long ldr, float alpha, float* stats,
                            const ProArgs* pro, void* stream) {
     if (int e = init_driver()) return e;
-    if (ntaps != 1 && ntaps != 9) { set_error("conv_fprop: ntaps must be 1 or 9"); return ADM_ERR_SHAPE; }
+    if (taps_per_row(ntaps) == 0) { set_error("conv_fprop: ntaps must be 1, 9, 25 or 49"); return ADM_ERR_SHAPE; }
     if (c1 <= 0 || c1 % 8 || (x2 && (c2 <= 0 || c2 % 8))) { set_error("conv_fprop: channels must be multiples of 8"); return ADM_ERR_SHAPE; }
     GemmParams p;
     init_params(&p);
@@ -488,7 +491,7 @@ static int conv_fprop_impl(const void* x1, int c1, long long ld1, const void* x2
     p.H = h; p.W = w;
     p.tiles_w = w / p.bw; p.tiles_h = h / p.bh;
     p.m_tiles = p.tiles_w * p.tiles_h * ((n + p.bni - 1) / p.bni);
-    p.ntaps = ntaps;
+    p.ntaps = ntaps; p.kw = taps_per_row(ntaps);
     p.cchunks1 = pad64(c1) / 64;
     p.cchunks = p.cchunks1 + (x2 ? pad64(c2) / 64 : 0);
     p.k_total = p.k_iters = ntaps * p.cchunks;
@@ -547,7 +550,7 @@ int adm_conv_dgrad(const void* dy, int cout, long long ld_dy, int n, int h, int 
                    int ntaps, void* dx, int n_valid, long long ldc, const void* residual, long long ldr, float alpha,
                    void* stream) {
     if (int e = init_driver()) return e;
-    if (ntaps != 1 && ntaps != 9) { set_error("conv_dgrad: ntaps must be 1 or 9"); return ADM_ERR_SHAPE; }
+    if (taps_per_row(ntaps) == 0) { set_error("conv_dgrad: ntaps must be 1, 9, 25 or 49"); return ADM_ERR_SHAPE; }
     if (kpad % 64) { set_error("conv_dgrad: kpad must be a multiple of 64"); return ADM_ERR_SHAPE; }
     GemmParams p;
     init_params(&p);
@@ -557,7 +560,7 @@ int adm_conv_dgrad(const void* dy, int cout, long long ld_dy, int n, int h, int 
     p.H = h; p.W = w;
     p.tiles_w = w / p.bw; p.tiles_h = h / p.bh;
     p.m_tiles = p.tiles_w * p.tiles_h * ((n + p.bni - 1) / p.bni);
-    p.ntaps = ntaps;
+    p.ntaps = ntaps; p.kw = taps_per_row(ntaps);
     p.cchunks1 = p.cchunks = pad64(cout) / 64;
     p.k_total = p.k_iters = ntaps * p.cchunks;
     p.bn = pick_bn_cost(kpad, 64, p.m_tiles, p.k_total);
@@ -593,7 +596,7 @@ int adm_conv_wgrad_mapped(const void* dy, int cout, long long ld_dy, const void*
                           float* dw, void* stream) {
     if (int e = init_driver()) return e;
     if (row_map != nullptr && ntaps != 1) { set_error("conv_wgrad: a row map is supported for 1x1 convs only"); return ADM_ERR_SHAPE; }
-    if (ntaps != 1 && ntaps != 9) { set_error("conv_wgrad: ntaps must be 1 or 9"); return ADM_ERR_SHAPE; }
+    if (taps_per_row(ntaps) == 0) { set_error("conv_wgrad: ntaps must be 1, 9, 25 or 49"); return ADM_ERR_SHAPE; }
     GemmParams p;
     init_params(&p);
     const long long pixels = 1LL * n * h * w;
@@ -611,7 +614,7 @@ int adm_conv_wgrad_mapped(const void* dy, int cout, long long ld_dy, const void*
         p.n_tiles = kpad / 64;
         p.cchunks1 = pad64(c1) / 64;
         p.bn = 192;
-        p.ntaps = 9;
+        p.ntaps = 9; p.kw = 3;
         p.a_mn = 1; p.b_mn = 1;
         p.c_col_lo = kpad;
         pick_wgrad_split(&p, p.m_tiles * p.n_tiles, 8);
@@ -627,7 +630,7 @@ int adm_conv_wgrad_mapped(const void* dy, int cout, long long ld_dy, const void*
     if (x2 && pad64(c2) % p.bn) p.bn = 64;
     p.n_tiles = kpad / p.bn;
     p.n_split = x2 ? pad64(c1) : INT_MAX;
-    p.ntaps = ntaps;
+    p.ntaps = ntaps; p.kw = taps_per_row(ntaps);
     p.batches = ntaps; p.bdiv = ntaps; p.c_col_lo = kpad;
     p.a_mn = 1; p.b_mn = 1;
     pick_wgrad_split(&p, ntaps * p.m_tiles * p.n_tiles, 6);  // epilogue ~ 6 k-iterations (fp32 vector atomics)

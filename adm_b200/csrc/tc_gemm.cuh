@@ -53,7 +53,8 @@ struct GemmParams {
     int M, N;  // valid rows (per batch) / cols
     // ---- conv / wgrad geometry (NHWC tensors; box = bw x bh x bni pixels)
     int H, W, bw, bh, bni, tiles_w, tiles_h;
-    int ntaps;     // 1 or 9
+    int ntaps;     // kw * kw: 1, 9, 25 or 49 (odd square kernels, 'same' padding kw / 2)
+    int kw;        // taps per kernel row (1, 3, 5, 7)
     int cchunks;   // 64-channel chunks per tap (both A sources)
     int cchunks1;  // chunks taken from A source 1; the rest come from A source 2 (fused channel concat)
     int n_split;   // wgrad: output columns (per tap) served by X source 1; the rest by X source 2
@@ -444,7 +445,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_expect_tx(&full_bar[stage], stage_bytes);
                     if (MODE == GEMM_CONV) {
                         int dh = 0, dw = 0;
-                        if (p.ntaps == 9) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+                        if (p.kw == 3) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+                        else if (p.kw > 1) { dh = tap / p.kw - (p.kw >> 1); dw = tap % p.kw - (p.kw >> 1); }
                         if (kc < p.cchunks1)
                             tma_load_4d(sa, &tmA, &full_bar[stage], kc * 64, w0 + dw, h0 + dh, n0);
                         else
@@ -465,7 +467,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         n0 = px.n0; h0 = px.h0; w0 = px.w0;
                         px.advance(p);
                         int dh = 0, dw = 0;
-                        if (p.ntaps == 9) { dh = bt / 3 - 1; dw = bt % 3 - 1; }
+                        if (p.kw == 3) { dh = bt / 3 - 1; dw = bt % 3 - 1; }
+                        else if (p.kw > 1) { dh = bt / p.kw - (p.kw >> 1); dw = bt % p.kw - (p.kw >> 1); }
                         tma_load_4d(sa, &tmA, &full_bar[stage], mt * 128, w0, h0, n0);
                         tma_load_4d(sa + 8192, &tmA, &full_bar[stage], mt * 128 + 64, w0, h0, n0);
                         // fused channel concat on the X side: columns >= n_split come from the second source
@@ -666,7 +669,8 @@ tc_conv_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 uint8_t* sb = sa + GEMM_A_STAGE;
                 mbar_expect_tx(&full_bar[stage], stage_bytes);
                 int dh = 0, dw = 0;
-                if (p.ntaps == 9) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+                if (p.kw == 3) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+                        else if (p.kw > 1) { dh = tap / p.kw - (p.kw >> 1); dw = tap % p.kw - (p.kw >> 1); }
                 if (kc < p.cchunks1)
                     tma_load_4d(sa, &tmA, &full_bar[stage], kc * 64, w0 + dw, h0 + dh, n0);
                 else
@@ -841,7 +845,8 @@ tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);
                     const int tap = ki / p.cchunks, kc = ki % p.cchunks;
                     int dh = 0, dw = 0;
-                    if (p.ntaps == 9) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+                    if (p.kw == 3) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+                        else if (p.kw > 1) { dh = tap / p.kw - (p.kw >> 1); dw = tap % p.kw - (p.kw >> 1); }
                     if (kc < p.cchunks1)
                         tma_load_4d_pair(sa, &tmA, &full_bar[stage], kc * 64, w0 + dw, h0 + dh, n0);
                     else

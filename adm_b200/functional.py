@@ -18,7 +18,8 @@ def _nhwc(x):
 
 
 class _Conv2dFn(torch.autograd.Function):
-    """3x3 (pad 1) / 1x1 convolution as tcgen05 implicit GEMM; ws=True applies weight standardisation (K11) on the fly.
+    """k x k convolution (k = 1, 3, 5, 7; stride 1, padding k // 2) as tcgen05 implicit GEMM; ws=True applies weight
+    standardisation (K11) on the fly.
     Replaces F.conv2d in cond_unet.py: WeightStandardizedConv2d.forward :349-358, nn.Conv2d of Block / res_conv /
     to_qkv / to_out / Upsample / final_conv."""
 
@@ -26,7 +27,7 @@ class _Conv2dFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, ws, ws_eps):
         x = _nhwc(x)
         cout, cin, k, _ = weight.shape
-        assert k in (1, 3) and x.shape[-1] == cin, (weight.shape, x.shape)
+        assert k in (1, 3, 5, 7) and x.shape[-1] == cin, (weight.shape, x.shape)
         w = weight.detach()
         if ws:
             wpk, stats = ops.ws_pack(w, ws_eps)

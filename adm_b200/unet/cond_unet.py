@@ -321,11 +321,48 @@ def _side(x):
 
 
 class _DownConv(nn.Conv2d):
-    """4x4 stride-2 conv (cond_unet.py:342-343): 1.1 % of the FLOPs, left to cuDNN on the channels-last view."""
+    """4x4 stride-2 padding-1 conv (cond_unet.py:342-343) on the implicit-GEMM engine: on the space-to-depth image
+    X'[i, j, (p, q, c)] = x[2i + p, 2j + q, c] it is a 3x3 padding-1 conv — out[i, j] reads rows 2i - 1 .. 2i + 2, i.e.
+    (i - 1, p = 1), (i, p = 0), (i, p = 1), (i + 1, p = 0) — whose weight W'[co, (p, q, c), di, dj] = w[co, c, 2 di + p + 1,
+    2 dj + q + 1] (zero where that index leaves 0 .. 3: 16 of the 36 (tap, sub-pixel) pairs are live, 2.25 x the FLOPs of a
+    conv that is 1.1 % of the network's).  The re-indexing of the weights is differentiable torch indexing."""
+
+    def _s2d_weight(self):
+        w = self.weight  # [co, c, 4, 4]
+        co, c = w.shape[:2]
+        zero = w.new_zeros(co, c)
+        taps = []
+        for di in (-1, 0, 1):
+            for dj in (-1, 0, 1):
+                sub = []
+                for p in (0, 1):
+                    for q in (0, 1):
+                        a, b = 2 * di + p + 1, 2 * dj + q + 1
+                        sub.append(w[:, :, a, b] if 0 <= a <= 3 and 0 <= b <= 3 else zero)
+                taps.append(torch.stack(sub, dim=1))      # [co, 4 (p, q), c]
+        return torch.stack(taps, dim=-1).reshape(co, 4 * c, 3, 3)  # [co, (p, q, c), di, dj]
 
     def forward(self, x):
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=SIDE_DTYPE == torch.bfloat16):
-            return _nhwc(super().forward(_side(_nchw(x))))
+        b, h, w, c = x.shape
+        ok = (self.kernel_size == (4, 4) and self.stride == (2, 2) and self.padding == (1, 1) and h % 2 == 0
+              and w % 2 == 0 and c % 2 == 0 and _conv_tiles(h // 2, w // 2))
+        if not ok:
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=SIDE_DTYPE == torch.bfloat16):
+                return _nhwc(super().forward(_side(_nchw(x))))
+        xs = x.reshape(b, h // 2, 2, w // 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(b, h // 2, w // 2, 4 * c)
+        return AF.conv2d(xs, self._s2d_weight(), self.bias)
+
+
+def _conv_tiles(h, w):
+    """Image sizes the implicit-GEMM kernels tile (128-pixel output boxes, 64-pixel K boxes of the weight gradient)."""
+    def box(pixels):
+        if w >= pixels:
+            return w % pixels == 0
+        if pixels % w:
+            return False
+        rows = pixels // w
+        return h % rows == 0 if h >= rows else rows % h == 0
+    return box(128) and box(64)
 
 
 def Downsample(dim, dim_out=None):
@@ -631,9 +668,17 @@ class Unet(nn.Module):
             up0 = F.interpolate(hm[0].float().contiguous(memory_format=torch.channels_last), size=x.shape[-2:],
                                 mode="bilinear")
             stem_in = torch.cat([x, up0], dim=1)
-            h0 = self.init_conv[0](stem_in.contiguous(memory_format=torch.channels_last))
             hm = [proj(f) for proj, f in zip(self.projects, hm)]
-        xh = self.init_conv[1](_nhwc(h0))
+        # 7x7 stem (cond_unet.py:656, 7 % of the FLOPs): the implicit-GEMM conv with 49 taps; the 131 input channels are
+        # zero-padded to a multiple of 8 on the activation and on the weight
+        stem, sx = self.init_conv[0], _nhwc(stem_in)
+        if _conv_tiles(sx.shape[1], sx.shape[2]) and stem.kernel_size == (7, 7) and stem.padding == (3, 3):
+            pad = (-sx.shape[-1]) % 8
+            h0 = AF.conv2d(F.pad(sx, (0, pad)), F.pad(stem.weight, (0, 0, 0, 0, 0, pad)), stem.bias)
+        else:
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=SIDE_DTYPE == torch.bfloat16):
+                h0 = _nhwc(stem(stem_in.contiguous(memory_format=torch.channels_last)))
+        xh = self.init_conv[1](h0)
         r = xh
         t = self.time_mlp(c_noise)
         skips = []

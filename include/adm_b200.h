@@ -77,7 +77,9 @@ int adm_unet_output_bwd(const float* dd1, const float* dd2, const float* sigma, 
  * conv3x3 / conv1x1 forward as implicit GEMM (replaces F.conv2d at unet/uncond_unet.py:100,110 and nn.Conv2d in
  * decouple1/2 :500-507).  x1 (and optionally x2: fused channel concat, :570-571) NHWC bf16; wpk = packed weights
  * bf16 [nout][ntaps][pad64(c1)+pad64(c2)] (adm_pack_conv_weight); out [n*h*w][ldc] bf16 (out_mode 0) / fp32 (1);
- * epilogue: out = alpha*acc + bias[col] + residual[row][col].                                              */
+ * epilogue: out = alpha*acc + bias[col] + residual[row][col].  ntaps = k*k for a square odd kernel with 'same'
+ * padding k/2: 1, 9, 25 or 49 (the 7x7 stem of the conditional UNet, unet/cond_unet.py:656); the same values are
+ * accepted by adm_conv_dgrad and adm_conv_wgrad.                                                           */
 int adm_conv_fprop(const void* x1, int c1, long long ld1, const void* x2, int c2, long long ld2, int n, int h, int w,
                    const void* wpk, int nout, int ntaps, void* out, int out_mode, long long ldc, const float* bias,
                    const void* residual, long long ldr, float alpha, void* stream);

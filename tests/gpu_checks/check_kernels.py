@@ -278,6 +278,36 @@ def row_maps():
 
 
 @case
+def conv_large_kernels():
+    """5x5 and 7x7 'same' convs (49 taps: the conditional UNet's stem, cond_unet.py:656) through the implicit-GEMM engine:
+    fprop, dgrad, wgrad against F.conv2d autograd, including an input channel count that is padded to 8 (131 -> 136)."""
+    import torch
+    import torch.nn.functional as F
+    from adm_b200 import functional as AF
+    torch.manual_seed(31)
+    ok = True
+    for (n, hw, cin, cout, k) in [(2, 16, 64, 64, 7), (2, 32, 136, 128, 7), (3, 16, 72, 96, 5), (1, 128, 8, 32, 7)]:
+        x = _bf(torch.randn(n, hw, hw, cin, device="cuda"))
+        w = (torch.randn(cout, cin, k, k, device="cuda") / (k * cin ** 0.5)).requires_grad_(True)
+        b = (torch.randn(cout, device="cuda") * 0.1).requires_grad_(True)
+        dy = _bf(torch.randn(n, hw, hw, cout, device="cuda"))
+        xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+        wr = _bf(w.detach()).float().requires_grad_(True)
+        br = b.detach().clone().requires_grad_(True)
+        yr = F.conv2d(xr, wr, br, padding=k // 2)
+        yr.backward(dy.float().permute(0, 3, 1, 2))
+        xo = x.clone().requires_grad_(True)
+        y = AF.conv2d(xo, w, b)
+        y.backward(dy)
+        torch.cuda.synchronize()
+        ok &= _report(f"conv {k}x{k} n{n} {hw} {cin}->{cout} fprop", y, yr.permute(0, 2, 3, 1), 5e-3)
+        ok &= _report(f"  dgrad", xo.grad, xr.grad.permute(0, 2, 3, 1), 5e-3)
+        ok &= _report(f"  wgrad", w.grad, wr.grad, 2e-3)
+        ok &= _report(f"  bias grad", b.grad, br.grad, 2e-3)
+    return ok
+
+
+@case
 def elementwise():
     import torch
     from adm_b200 import ops

@@ -31,7 +31,8 @@ from tests.gpu_checks import check_unet as CU  # noqa: E402
 
 
 @pytest.mark.parametrize("case", ["gemm_nt_basic", "gemm_nn_tn", "conv_fprop_3x3", "conv_fprop_concat_1x1",
-                                  "conv_dgrad_wgrad", "conv_dgrad_shadow", "row_maps", "elementwise"])
+                                  "conv_dgrad_wgrad", "conv_dgrad_shadow", "conv_large_kernels", "row_maps",
+                                  "elementwise"])
 def test_gemm_engine_and_ddm_kernels(case):
     assert CK.CASES[case]()
 
