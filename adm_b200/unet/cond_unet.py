@@ -19,6 +19,7 @@ There is no CPU fallback: the kernels raise on non-CUDA tensors.
 from __future__ import annotations
 
 import math
+import os
 from functools import partial
 
 import torch
@@ -151,7 +152,7 @@ def _pad_to(x, win):
 
 class BasicAttetnionLayer(nn.Module):
     """cond_unet.py:160-252: window-pooled cross attention from the condition map (queries) to the feature map
-    (keys / values).  Stays in PyTorch."""
+    (keys / values)."""
 
     def __init__(self, embed_dim=128, nhead=8, ffn_dim=512, window_size1=[4, 4], window_size2=[1, 1], dropout=0.1):
         super().__init__()
@@ -170,17 +171,25 @@ class BasicAttetnionLayer(nn.Module):
         _init_like_reference(self)
 
     def forward(self, x1, x2):
-        b, c1, _, _ = x1.shape
-        _, c2, h2, w2 = x2.shape
-        cl = torch.channels_last  # torch's NHWC resampling kernels are an order of magnitude faster than its NCHW ones
-        x1, x2 = x1.contiguous(memory_format=cl), x2.contiguous(memory_format=cl)
-        up = F.interpolate(x1, size=(h2, w2), mode="bilinear", align_corners=True)
-        shortcut = self.gn(x2 + self.concat_conv(torch.cat([up, x2], dim=1)))
-        x1p, x2p = _pad_to(x1, self.window_size1), _pad_to(x2, self.window_size2)
-        pooled = self.avgpool_q(x1p)
-        hq, wq = pooled.shape[-2:]
-        q = pooled.permute(0, 2, 3, 1)
-        q = (q + self.pos_enc(q).to(q.dtype)).reshape(b, -1, c2)
+        """x1 (condition features) and x2 (trunk features): NHWC bf16.  The full-resolution work — the two 1x1 convs and
+        the GroupNorm — runs on the sm_100a kernels; the window-pooled cross attention (a few hundred tokens) and the
+        bilinear resizes stay torch ops on channels-last views of the same tensors (no layout copies)."""
+        b, _, _, c1 = x1.shape
+        _, h2, w2, c2 = x2.shape
+        up = _bilinear(x1, (h2, w2))
+        pre = x2.float() + _conv1x1(torch.cat([up, x2], dim=-1), self.concat_conv).float()
+        if os.environ.get("ADM_REL_GN", "torch") == "torch":
+            # fp32 GroupNorm on the channels-last view: the residual stream of the relation layer stays fp32 end to end, as
+            # under the reference's fp32 arithmetic (with the bf16 kernel here one Downsample weight gradient of the golden
+            # check drops from cosine 0.9995 to 0.9983)
+            shortcut = F.group_norm(_nchw(pre), self.gn.num_groups, self.gn.weight, self.gn.bias, self.gn.eps).permute(0, 2, 3, 1)
+        else:
+            shortcut = AF.group_norm_act(pre.to(torch.bfloat16), self.gn.weight, self.gn.bias, self.gn.num_groups,
+                                         self.gn.eps, act=False)
+        x1p, x2p = _pad_to(_nchw(x1), self.window_size1), _pad_to(_nchw(x2), self.window_size2)
+        pooled = self.avgpool_q(x1p).permute(0, 2, 3, 1)            # [b, hq, wq, c] (channels-last view)
+        hq, wq = pooled.shape[1:3]
+        q = (pooled + self.pos_enc(pooled).to(pooled.dtype)).reshape(b, -1, c2)
         k = self.avgpool_k(x2p).permute(0, 2, 3, 1)
         k = (k + self.pos_enc(k).to(k.dtype)).reshape(b, -1, c1)
         nq, nk, hd = q.shape[1], k.shape[1], c1 // self.nhead
@@ -188,11 +197,29 @@ class BasicAttetnionLayer(nn.Module):
         kh = self.k_lin(k).reshape(b, nk, self.nhead, hd).permute(0, 2, 1, 3)
         vh = self.v_lin(k).reshape(b, nk, self.nhead, hd).permute(0, 2, 1, 3)
         attn = self.softmax(qh @ kh.transpose(-2, -1))  # no 1/sqrt(d): as in the reference
-        o = (attn @ vh).transpose(1, 2).reshape(b, nq, c1).transpose(1, 2).reshape(b, c1, hq, wq)
-        pooled = pooled + o
-        pooled = pooled + self.mlp(pooled)
-        pooled = F.interpolate(pooled.contiguous(memory_format=cl), size=(h2, w2), mode="bilinear", align_corners=True)
-        return shortcut + self.out_conv(pooled)
+        o = (attn @ vh).transpose(1, 2).reshape(b, hq, wq, c1)
+        pooled = pooled + o.to(pooled.dtype)
+        m = self.mlp
+        hid = m.drop(m.act(F.linear(pooled, m.fc1.weight.flatten(1), m.fc1.bias)))  # the Mlp's 1x1 convs on [b, hq, wq, c]
+        pooled = pooled + m.drop(F.linear(hid, m.fc2.weight.flatten(1), m.fc2.bias)).to(pooled.dtype)
+        pooled = _bilinear(pooled.to(torch.bfloat16).contiguous(), (h2, w2))
+        return (shortcut.float() + _conv1x1(pooled, self.out_conv).float()).to(torch.bfloat16).contiguous()  # fp32 sum
+
+
+def _bilinear(x, size):
+    """NHWC -> NHWC bilinear resize (align_corners=True) through the channels-last view: no layout copy."""
+    if tuple(x.shape[1:3]) == tuple(size):
+        return x
+    y = F.interpolate(x.permute(0, 3, 1, 2), size=size, mode="bilinear", align_corners=True)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def _conv1x1(x, conv):
+    """nn.Conv2d(k = 1) parameters on an NHWC bf16 tensor: the implicit-GEMM kernel where the image tiles, else a matmul."""
+    x = x.to(torch.bfloat16)
+    if _conv_tiles(x.shape[1], x.shape[2]) and x.shape[-1] % 8 == 0:
+        return AF.conv2d(x.contiguous(), conv.weight, conv.bias)
+    return F.linear(x, conv.weight.flatten(1).to(x.dtype), conv.bias.to(x.dtype) if conv.bias is not None else None)
 
 
 class RelationNet(nn.Module):
@@ -211,7 +238,11 @@ class RelationNet(nn.Module):
                                 window_size2=window_size2, dropout=0.1) for _ in range(layers))
 
     def forward(self, cond, feat):
-        cond, feat = self.input_conv1(cond), self.input_conv2(feat)
+        """cond, feat: NHWC bf16.  1x1 conv on the kernels, BatchNorm on the channels-last view."""
+        def stem(seq, x):
+            y = seq[1](_nchw(_conv1x1(x, seq[0])))
+            return y.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
+        cond, feat = stem(self.input_conv1, cond), stem(self.input_conv2, feat)
         for att in self.attentions:
             feat = att(cond, feat)
         return feat
@@ -632,10 +663,10 @@ class Unet(nn.Module):
         print("==>Load Unet Info: ", msg)
 
     @staticmethod
-    def _relate(layer, cond_nchw, x):
-        """RelationNet runs in PyTorch on the channels-last view of the NHWC trunk tensor."""
+    def _relate(layer, cond, x):
+        """RelationNet on NHWC bf16 tensors (cond: the projected Swin feature map of this level, converted once)."""
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=SIDE_DTYPE == torch.bfloat16):
-            return _nhwc(layer(_side(cond_nchw), _side(_nchw(x))))
+            return layer(cond, x).to(torch.bfloat16)
 
     def _decoder(self, x, ups, relations, skips, hms, r, final_block, final_conv, t):
         skips, hms = list(skips), list(hms)
@@ -668,7 +699,7 @@ class Unet(nn.Module):
             up0 = F.interpolate(hm[0].float().contiguous(memory_format=torch.channels_last), size=x.shape[-2:],
                                 mode="bilinear")
             stem_in = torch.cat([x, up0], dim=1)
-            hm = [proj(f) for proj, f in zip(self.projects, hm)]
+            hm = [_nhwc(proj(f)) for proj, f in zip(self.projects, hm)]  # NHWC bf16, shared by encoder and both decoders
         # 7x7 stem (cond_unet.py:656, 7 % of the FLOPs): the implicit-GEMM conv with 49 taps; the 131 input channels are
         # zero-padded to a multiple of 8 on the activation and on the weight
         stem, sx = self.init_conv[0], _nhwc(stem_in)
