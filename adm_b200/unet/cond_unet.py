@@ -176,8 +176,10 @@ class BasicAttetnionLayer(nn.Module):
         bilinear resizes stay torch ops on channels-last views of the same tensors (no layout copies)."""
         b, _, _, c1 = x1.shape
         _, h2, w2, c2 = x2.shape
+        x2r = x2.float()            # the residual stream of the stacked relation layers stays fp32 between layers
+        x2 = x2.to(torch.bfloat16)  # what the convs / pooling read
         up = _bilinear(x1, (h2, w2))
-        pre = x2.float() + _conv1x1(torch.cat([up, x2], dim=-1), self.concat_conv).float()
+        pre = x2r + _conv1x1(torch.cat([up.to(torch.bfloat16), x2], dim=-1), self.concat_conv).float()
         if os.environ.get("ADM_REL_GN", "torch") == "torch":
             # fp32 GroupNorm on the channels-last view: the residual stream of the relation layer stays fp32 end to end, as
             # under the reference's fp32 arithmetic (with the bf16 kernel here one Downsample weight gradient of the golden
@@ -203,7 +205,7 @@ class BasicAttetnionLayer(nn.Module):
         hid = m.drop(m.act(F.linear(pooled, m.fc1.weight.flatten(1), m.fc1.bias)))  # the Mlp's 1x1 convs on [b, hq, wq, c]
         pooled = pooled + m.drop(F.linear(hid, m.fc2.weight.flatten(1), m.fc2.bias)).to(pooled.dtype)
         pooled = _bilinear(pooled.to(torch.bfloat16).contiguous(), (h2, w2))
-        return (shortcut.float() + _conv1x1(pooled, self.out_conv).float()).to(torch.bfloat16).contiguous()  # fp32 sum
+        return shortcut.float() + _conv1x1(pooled, self.out_conv).float()  # fp32 (rounded once, by RelationNet.forward)
 
 
 def _bilinear(x, size):
@@ -245,7 +247,7 @@ class RelationNet(nn.Module):
         cond, feat = stem(self.input_conv1, cond), stem(self.input_conv2, feat)
         for att in self.attentions:
             feat = att(cond, feat)
-        return feat
+        return feat.to(torch.bfloat16).contiguous()
 
 
 # ------------------------------------------------------------------------------------------------ Swin-B condition encoder
