@@ -420,12 +420,12 @@ __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __re
                                                                __nv_bfloat16* __restrict__ o, int cout, int c1, int c2,
                                                                int kk, int p1, int kpad,
                                                                const int* __restrict__ row_perm) {
-    const long long total = 1LL * cout * kk * kpad;
+    const unsigned total = static_cast<unsigned>(cout) * kk * kpad;  // < 2^31 (checked by the launcher): 32-bit divisions
     const int cin = c1 + c2;
-    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int kc = static_cast<int>(i % kpad);
         const int tap = static_cast<int>((i / kpad) % kk);
-        const int co = static_cast<int>(i / (1LL * kpad * kk));
+        const int co = static_cast<int>(i / (static_cast<unsigned>(kpad) * kk));
         int ci = -1;
         if (kc < c1) ci = kc;
         else if (kc >= p1 && kc - p1 < c2) ci = c1 + kc - p1;
@@ -489,11 +489,11 @@ __global__ void __launch_bounds__(256) unpack_conv_wgrad_kernel(const float* __r
                                                                 int cout, int c1, int c2, int kk, int p1, int kpad,
                                                                 int accumulate, const int* __restrict__ row_perm) {
     const int cin = c1 + c2;
-    const long long total = 1LL * cout * cin * kk;
-    for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const unsigned total = static_cast<unsigned>(cout) * cin * kk;  // < 2^31 (checked by the launcher): 32-bit divisions
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int tap = static_cast<int>(i % kk);
         const int ci = static_cast<int>((i / kk) % cin);
-        const int co = static_cast<int>(i / (1LL * kk * cin));
+        const int co = static_cast<int>(i / (static_cast<unsigned>(kk) * cin));
         const int kc = ci < c1 ? ci : p1 + (ci - c1);
         const float v = g[(1LL * co * kk + tap) * kpad + kc];
         const long long dst = row_perm != nullptr ? ((1LL * row_perm[co] * cin + ci) * kk + tap) : i;
@@ -631,6 +631,7 @@ int adm_pack_conv_weight(const float* w, void* wpk, int cout, int c1, int c2, in
                          void* stream) {
     const int p1 = (c1 + 63) / 64 * 64;
     const int kpad = p1 + (c2 > 0 ? (c2 + 63) / 64 * 64 : 0);
+    if (1LL * cout * ksize * ksize * kpad >= (1LL << 31)) { set_error("pack_conv_weight: weight too large"); return ADM_ERR_SHAPE; }
     pack_conv_weight_kernel<<<ew_grid(1LL * cout * ksize * ksize * kpad, 256, 8), 256, 0,
                               static_cast<cudaStream_t>(stream)>>>(w, static_cast<__nv_bfloat16*>(wpk), cout, c1, c2,
                                                                    ksize * ksize, p1, kpad, row_perm);
@@ -642,6 +643,7 @@ int adm_unpack_conv_wgrad(const float* dw_packed, float* dw, int cout, int c1, i
                           const int* row_perm, void* stream) {
     const int p1 = (c1 + 63) / 64 * 64;
     const int kpad = p1 + (c2 > 0 ? (c2 + 63) / 64 * 64 : 0);
+    if (1LL * cout * ksize * ksize * kpad >= (1LL << 31)) { set_error("unpack_conv_wgrad: weight too large"); return ADM_ERR_SHAPE; }
     unpack_conv_wgrad_kernel<<<ew_grid(1LL * cout * (c1 + c2) * ksize * ksize, 256, 8), 256, 0,
                                static_cast<cudaStream_t>(stream)>>>(dw_packed, dw, cout, c1, c2, ksize * ksize, p1,
                                                                     kpad, accumulate, row_perm);
