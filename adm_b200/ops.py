@@ -324,20 +324,22 @@ def gemm_nt(a, b, bias=None, out_dtype=F32, alpha=1.0, out=None):
     return out
 
 
-def gemm_nn(a, b, out_dtype=F32, alpha=1.0, out=None):
-    """C[M,N] = alpha * A[M,K] @ B[K,N]; B row-major (N contiguous) consumed as an MN-major operand."""
+def gemm_nn(a, b, out_dtype=F32, alpha=1.0, out=None, splits=1):
+    """C[M,N] = alpha * A[M,K] @ B[K,N]; B row-major (N contiguous) consumed as an MN-major operand.
+    splits > 1: split K over that many tiles (fp32 atomics into a zeroed fp32 output) — for a long K with few output tiles."""
     _need_cuda(a, b)
     assert a.dtype == BF16 and b.dtype == BF16 and a.stride(1) == 1 and b.stride(1) == 1
     m, k = a.shape
     k2, n = b.shape
     assert k == k2
     if out is None:
-        out = torch.empty(m, n, device=a.device, dtype=out_dtype)
+        out = (torch.zeros if splits > 1 else torch.empty)(m, n, device=a.device, dtype=F32 if splits > 1 else out_dtype)
+    assert splits == 1 or out.dtype == F32
     d = GemmDesc()
     d.a = _operand(a, 0, (k, m, 1), (a.stride(0), a.stride(0) * m))
     d.b = _operand(b, 1, (n, k, 1), (b.stride(0), b.stride(0) * k))
-    d.m, d.n, d.k, d.batches, d.bdiv, d.splits = m, n, k, 1, 1, 1
-    d.c, d.out_mode, d.ldc = out.data_ptr(), 0 if out.dtype == BF16 else 1, out.stride(0)
+    d.m, d.n, d.k, d.batches, d.bdiv, d.splits = m, n, k, 1, 1, splits
+    d.c, d.out_mode, d.ldc = out.data_ptr(), (2 if splits > 1 else (0 if out.dtype == BF16 else 1)), out.stride(0)
     d.alpha = float(alpha)
     check(_lib.load().adm_gemm_batched(d, _stream()), "gemm_nn")
     return out

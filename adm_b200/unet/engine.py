@@ -594,7 +594,10 @@ class UNetEngine:
                 ops.unpack_conv_wgrad(dwall[off:off + o], net.emb_channels, 0, 1, out=self._grad(m.affine.weight),
                                       accumulate=True)
                 ops.col_sums(dpb[:, off:off + o], self._grad(m.affine.bias))
-        demb = ops.gemm_nn(dpb, wall)
+        # [B, sum 2*Cout] x [sum 2*Cout, emb]: K = 45 k with three output tiles -> split K over the idle SMs
+        # (ADM_DEMB_SPLIT=0: A/B timing)
+        splits = 1 if os.environ.get("ADM_DEMB_SPLIT", "1") == "0" else max(1, min(40, wall.shape[0] // 1024))
+        demb = ops.gemm_nn(dpb, wall, splits=splits)
         _, de1b = ops.silu_bwd(e.e1, demb, want_f32=False)
         self._linear_grads(net.map_layer1, de1b, e.s0b)
         ds0 = ops.gemm_nn(de1b, self.lin_w(net.map_layer1))
