@@ -98,6 +98,14 @@ SIGNATURES = {
     "adm_chan_layernorm_ok": (c_i, [c_i]),
     "adm_chan_layernorm_fwd": (c_i, [c_p, c_ll, c_ll, c_i, c_p, c_f, c_p, c_ll, c_p]),
     "adm_chan_layernorm_bwd": (c_i, [c_p, c_ll, c_p, c_ll, c_ll, c_i, c_p, c_f, c_p, c_ll, c_p, c_p]),
+    "adm_rel_gn_ok": (c_i, [c_i, c_i, c_i, c_i, c_i]),
+    "adm_rel_gn_chunks": (c_i, [c_i, c_i, c_i, c_i]),
+    "adm_rel_gn_fwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_f, c_p, c_i, c_p, c_p, c_p]),
+    "adm_rel_gn_bwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "adm_bilinear_fwd": (c_i, [c_p, c_ll, c_i, c_i, c_i, c_i, c_p, c_ll, c_i, c_i, c_i, c_i, c_p]),
+    "adm_bilinear_bwd": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "adm_avgpool_fwd": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "adm_avgpool_bwd": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "adm_linattn_workspace": (c_i, [c_i, c_i, c_i, C.POINTER(c_ll)]),
     "adm_linattn_fwd": (c_i, [c_p, c_ll, c_i, c_i, c_i, c_i, c_f, c_p, c_ll, c_p, c_p, c_p, c_p]),
     "adm_linattn_bwd": (c_i, [c_p, c_ll, c_i, c_i, c_i, c_i, c_f, c_p, c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_p]),

@@ -192,3 +192,68 @@ class _ChanLayerNormFn(torch.autograd.Function):
 
 def channel_layer_norm(x, g, eps=1e-5):
     return _ChanLayerNormFn.apply(x, g, eps)
+
+
+class _RelationTailFn(torch.autograd.Function):
+    """Tail of a relation layer (cond_unet.py:236-251): GroupNorm(x + y) + bilinear(z) with x the trunk features, y the
+    concat_conv output and z the out_conv of the pooled tokens.  The sum, the statistics and the normalised value live in
+    fp32 registers (the reference's fp32 residual stream) and one bf16 tensor is written; the backward re-derives them."""
+
+    @staticmethod
+    def forward(ctx, x, y, z, gamma, beta, groups, eps):
+        x, y = _nhwc(x), _nhwc(y)
+        zf = z.detach().float().contiguous()
+        gf, bf = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        out, stats = ops.rel_gn_fwd(x, y, zf, gf, bf, groups, eps)
+        ctx.save_for_backward(x, y, gf, stats)
+        ctx.groups, ctx.z_shape, ctx.z_dtype = groups, z.shape, z.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y, gf, stats = ctx.saved_tensors
+        dout = _nhwc(dout)
+        dpre, dgamma, dbeta = ops.rel_gn_bwd(dout, x, y, gf, stats, ctx.groups)
+        dz = ops.bilinear_bwd(dout, ctx.z_shape[1:3]).to(ctx.z_dtype) if ctx.needs_input_grad[2] else None
+        return dpre, dpre, dz, dgamma, dbeta, None, None
+
+
+def relation_tail(x, y, z, gamma, beta, groups, eps=1e-5):
+    return _RelationTailFn.apply(x, y, z, gamma, beta, groups, eps)
+
+
+class _BilinearFn(torch.autograd.Function):
+    """F.interpolate(mode='bilinear', align_corners=True) on an NHWC bf16 map (cond_unet.py:184, :248)."""
+
+    @staticmethod
+    def forward(ctx, x, size):
+        x = _nhwc(x)
+        ctx.size_in = x.shape[1:3]
+        return ops.bilinear_fwd(x, size)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.bilinear_bwd(_nhwc(dy), ctx.size_in).to(BF16), None
+
+
+def bilinear_resize(x, size):
+    return _BilinearFn.apply(x, tuple(int(v) for v in size))
+
+
+class _AvgPoolFn(torch.autograd.Function):
+    """F.pad to a multiple of the window + nn.AvgPool2d(window) on an NHWC bf16 map (cond_unet.py:190-200)."""
+
+    @staticmethod
+    def forward(ctx, x, window):
+        x = _nhwc(x)
+        ctx.shape, ctx.window = tuple(x.shape), window
+        return ops.avgpool_fwd(x, window)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.avgpool_bwd(_nhwc(dy), ctx.shape, ctx.window), None
+
+
+def avg_pool_window(x, window):
+    window = (int(window[0]), int(window[1]))
+    return x if window == (1, 1) else _AvgPoolFn.apply(x, window)

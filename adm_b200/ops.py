@@ -791,6 +791,94 @@ def chan_layernorm_bwd(dy, x, g, eps=1e-5):
     return dx, dg
 
 
+# ------------------------------------------------------------------------------------------------ relation layers
+def rel_gn_ok(x, groups):
+    """True when the fused relation-layer tail takes this NHWC bf16 map (cond_unet.py:236-251)."""
+    b, h, w, c = x.shape
+    return bool(_lib.load().adm_rel_gn_ok(int(b), int(h), int(w), int(c), int(groups)))
+
+
+def _rel_work(b, h, w, c, groups, device):
+    chunks = _lib.load().adm_rel_gn_chunks(int(b), int(h), int(w), int(c))
+    return torch.empty(b, chunks, max(groups, c), 2, device=device, dtype=F32), chunks
+
+
+def rel_gn_fwd(x, y, z, gamma, beta, groups, eps=1e-5, out_dtype=BF16):
+    """out = GroupNorm(x + y) * gamma + beta + bilinear(z) with the sum in fp32 registers; x, y NHWC bf16 [B,H,W,C],
+    z fp32 [B,hq,wq,C].  Returns (out, stats fp32 [B,groups,2])."""
+    _need_cuda(x, y, z, gamma, beta)
+    assert x.dtype == BF16 and y.dtype == BF16 and x.is_contiguous() and y.is_contiguous() and x.shape == y.shape
+    assert z.dtype == F32 and z.is_contiguous() and z.shape[0] == x.shape[0] and z.shape[-1] == x.shape[-1]
+    assert gamma.dtype == F32 and beta.dtype == F32 and gamma.is_contiguous() and beta.is_contiguous()
+    b, h, w, c = x.shape
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    stats = torch.empty(b, groups, 2, device=x.device, dtype=F32)
+    work, _ = _rel_work(b, h, w, c, groups, x.device)
+    check(_lib.load().adm_rel_gn_fwd(_ptr(x), _ptr(y), _ptr(z), b, h, w, c, int(z.shape[1]), int(z.shape[2]), int(groups),
+                                     _ptr(gamma), _ptr(beta), float(eps), _ptr(out), int(out_dtype == F32), _ptr(stats),
+                                     _ptr(work), _stream()), "rel_gn_fwd")
+    return out, stats
+
+
+def rel_gn_bwd(dout, x, y, gamma, stats, groups):
+    """Returns (dpre bf16 like x, dgamma fp32 [C], dbeta fp32 [C])."""
+    _need_cuda(dout, x, y, gamma, stats)
+    assert dout.dtype == BF16 and dout.is_contiguous() and dout.shape == x.shape
+    b, h, w, c = x.shape
+    dpre = torch.empty(x.shape, device=x.device, dtype=BF16)
+    work, chunks = _rel_work(b, h, w, c, groups, x.device)
+    check(_lib.load().adm_rel_gn_bwd(_ptr(dout), _ptr(x), _ptr(y), b, h, w, c, int(groups), _ptr(gamma), _ptr(stats),
+                                     _ptr(dpre), _ptr(work), _stream()), "rel_gn_bwd")
+    sums = work.view(-1)[:b * chunks * c * 2].view(b * chunks, c, 2).sum(0)
+    return dpre, sums[:, 0].contiguous(), sums[:, 1].contiguous()
+
+
+def bilinear_fwd(x, size, out_dtype=None):
+    """NHWC bilinear resize, align_corners=True (F.interpolate, cond_unet.py:184, :248); x bf16 or fp32, last dim dense."""
+    _need_cuda(x)
+    assert x.dtype in (BF16, F32) and x.dim() == 4 and x.stride(-1) == 1
+    b, h, w, c = x.shape
+    assert x.stride(1) == w * x.stride(2) and x.stride(0) == h * x.stride(1)
+    out_dtype = out_dtype or x.dtype
+    y = torch.empty(b, int(size[0]), int(size[1]), c, device=x.device, dtype=out_dtype)
+    check(_lib.load().adm_bilinear_fwd(_ptr(x), x.stride(2), b, h, w, c, _ptr(y), c, int(size[0]), int(size[1]),
+                                       int(x.dtype == F32), int(out_dtype == F32), _stream()), "bilinear_fwd")
+    return y
+
+
+def bilinear_bwd(dy, size_in):
+    """dy bf16 [B,hout,wout,C] contiguous -> dx fp32 [B,hin,win,C]."""
+    _need_cuda(dy)
+    assert dy.dtype == BF16 and dy.is_contiguous()
+    b, ho, wo, c = dy.shape
+    hin, win = int(size_in[0]), int(size_in[1])
+    tmp = torch.empty(b, hin, wo, c, device=dy.device, dtype=F32)
+    dx = torch.empty(b, hin, win, c, device=dy.device, dtype=F32)
+    check(_lib.load().adm_bilinear_bwd(_ptr(dy), b, ho, wo, c, hin, win, _ptr(tmp), _ptr(dx), _stream()), "bilinear_bwd")
+    return dx
+
+
+def avgpool_fwd(x, window):
+    """F.pad to a multiple of the window + nn.AvgPool2d(window) on an NHWC bf16 map (cond_unet.py:190-200)."""
+    _need_cuda(x)
+    assert x.dtype == BF16 and x.is_contiguous()
+    b, h, w, c = x.shape
+    kh, kw = int(window[0]), int(window[1])
+    out = torch.empty(b, -(-h // kh), -(-w // kw), c, device=x.device, dtype=BF16)
+    check(_lib.load().adm_avgpool_fwd(_ptr(x), b, h, w, c, kh, kw, _ptr(out), _stream()), "avgpool_fwd")
+    return out
+
+
+def avgpool_bwd(dy, shape, window):
+    _need_cuda(dy)
+    assert dy.dtype == BF16 and dy.is_contiguous()
+    b, h, w, c = shape
+    dx = torch.empty(b, h, w, c, device=dy.device, dtype=BF16)
+    check(_lib.load().adm_avgpool_bwd(_ptr(dy), b, h, w, c, int(window[0]), int(window[1]), _ptr(dx), _stream()),
+          "avgpool_bwd")
+    return dx
+
+
 # ------------------------------------------------------------------------------------------------ AugmentPipe warp
 def augment_warp(x, theta, flips, margins):
     """x fp32 [N,C,H,W] (CUDA) -> flipped + warped batch (ddm/augment.py:153-328); theta fp32 [N,6], flips int32 [N,2],

@@ -170,29 +170,38 @@ class BasicAttetnionLayer(nn.Module):
         self.out_conv = nn.Conv2d(embed_dim, embed_dim, 1)
         _init_like_reference(self)
 
-    def forward(self, x1, x2):
-        """x1 (condition features) and x2 (trunk features): NHWC bf16.  The full-resolution work — the two 1x1 convs and
-        the GroupNorm — runs on the sm_100a kernels; the window-pooled cross attention (a few hundred tokens) and the
-        bilinear resizes stay torch ops on channels-last views of the same tensors (no layout copies)."""
+    def forward(self, x1, x2, last=True):
+        """x1 (condition features) and x2 (trunk features): NHWC bf16.  Everything at full resolution runs on the sm_100a
+        kernels: the concat 1x1 conv on the GEMM engine, the window average pools, and — for the last layer of a stack
+        (every layer of the shipped configs: layers = 1) — the whole tail ``GroupNorm(x2 + conv) + out_conv(up(pooled))``
+        as one fused pass (``AF.relation_tail``): the 1x1 ``out_conv`` commutes with the bilinear resize (per-pixel
+        linear map, resize weights sum to one), so it runs on the pooled tokens and the resize + residual GroupNorm is a
+        single read of x2 / conv and a single bf16 write with the sum in fp32 registers.  The window-pooled cross
+        attention itself (a few hundred tokens) stays torch ops.  ``ADM_REL_FUSED=0`` keeps the unfused path."""
         b, _, _, c1 = x1.shape
         _, h2, w2, c2 = x2.shape
-        x2r = x2.float()            # the residual stream of the stacked relation layers stays fp32 between layers
-        x2 = x2.to(torch.bfloat16)  # what the convs / pooling read
+        gn = self.gn
+        fused = (last and _REL_FUSED and x2.is_cuda and x2.dtype == torch.bfloat16 and c2 % 8 == 0
+                 and ops.rel_gn_ok(x2, gn.num_groups))
+        x2r = None if fused else x2.float()  # unfused: the residual stream of stacked relation layers stays fp32
+        x2 = x2.to(torch.bfloat16)           # what the convs / pooling read
         up = _bilinear(x1, (h2, w2))
-        pre = x2r + _conv1x1(torch.cat([up.to(torch.bfloat16), x2], dim=-1), self.concat_conv).float()
-        if os.environ.get("ADM_REL_GN", "torch") == "torch":
+        y = _conv1x1(torch.cat([up.to(torch.bfloat16), x2], dim=-1), self.concat_conv)
+        if fused:
+            shortcut = None
+        elif os.environ.get("ADM_REL_GN", "torch") == "torch":
             # fp32 GroupNorm on the channels-last view: the residual stream of the relation layer stays fp32 end to end, as
             # under the reference's fp32 arithmetic (with the bf16 kernel here one Downsample weight gradient of the golden
             # check drops from cosine 0.9995 to 0.9983)
-            shortcut = F.group_norm(_nchw(pre), self.gn.num_groups, self.gn.weight, self.gn.bias, self.gn.eps).permute(0, 2, 3, 1)
+            pre = x2r + y.float()
+            shortcut = F.group_norm(_nchw(pre), gn.num_groups, gn.weight, gn.bias, gn.eps).permute(0, 2, 3, 1)
         else:
-            shortcut = AF.group_norm_act(pre.to(torch.bfloat16), self.gn.weight, self.gn.bias, self.gn.num_groups,
-                                         self.gn.eps, act=False)
-        x1p, x2p = _pad_to(_nchw(x1), self.window_size1), _pad_to(_nchw(x2), self.window_size2)
-        pooled = self.avgpool_q(x1p).permute(0, 2, 3, 1)            # [b, hq, wq, c] (channels-last view)
+            pre = x2r + y.float()
+            shortcut = AF.group_norm_act(pre.to(torch.bfloat16), gn.weight, gn.bias, gn.num_groups, gn.eps, act=False)
+        pooled = _window_pool(x1, self.window_size1, self.avgpool_q)  # [b, hq, wq, c]
         hq, wq = pooled.shape[1:3]
         q = (pooled + self.pos_enc(pooled).to(pooled.dtype)).reshape(b, -1, c2)
-        k = self.avgpool_k(x2p).permute(0, 2, 3, 1)
+        k = _window_pool(x2, self.window_size2, self.avgpool_k)
         k = (k + self.pos_enc(k).to(k.dtype)).reshape(b, -1, c1)
         nq, nk, hd = q.shape[1], k.shape[1], c1 // self.nhead
         qh = self.q_lin(q).reshape(b, nq, self.nhead, hd).permute(0, 2, 1, 3)
@@ -204,14 +213,29 @@ class BasicAttetnionLayer(nn.Module):
         m = self.mlp
         hid = m.drop(m.act(F.linear(pooled, m.fc1.weight.flatten(1), m.fc1.bias)))  # the Mlp's 1x1 convs on [b, hq, wq, c]
         pooled = pooled + m.drop(F.linear(hid, m.fc2.weight.flatten(1), m.fc2.bias)).to(pooled.dtype)
+        if fused:
+            z = F.linear(pooled, self.out_conv.weight.flatten(1), self.out_conv.bias)  # out_conv on the pooled tokens
+            return AF.relation_tail(x2, y, z, gn.weight, gn.bias, gn.num_groups, gn.eps)  # bf16
         pooled = _bilinear(pooled.to(torch.bfloat16).contiguous(), (h2, w2))
         return shortcut.float() + _conv1x1(pooled, self.out_conv).float()  # fp32 (rounded once, by RelationNet.forward)
+
+
+_REL_FUSED = os.environ.get("ADM_REL_FUSED", "1") != "0"
+
+
+def _window_pool(x, window, pool):
+    """F.pad to a multiple of the window + AvgPool2d on an NHWC map -> [b, ceil(h / kh), ceil(w / kw), c]."""
+    if x.is_cuda and x.dtype == torch.bfloat16 and x.shape[-1] % 8 == 0:
+        return AF.avg_pool_window(x, window)
+    return pool(_pad_to(_nchw(x), window)).permute(0, 2, 3, 1)
 
 
 def _bilinear(x, size):
     """NHWC -> NHWC bilinear resize (align_corners=True) through the channels-last view: no layout copy."""
     if tuple(x.shape[1:3]) == tuple(size):
         return x
+    if x.is_cuda and x.dtype == torch.bfloat16 and x.shape[-1] % 8 == 0:
+        return AF.bilinear_resize(x, size)
     y = F.interpolate(x.permute(0, 3, 1, 2), size=size, mode="bilinear", align_corners=True)
     return y.permute(0, 2, 3, 1).contiguous()
 
@@ -245,8 +269,8 @@ class RelationNet(nn.Module):
             y = seq[1](_nchw(_conv1x1(x, seq[0])))
             return y.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
         cond, feat = stem(self.input_conv1, cond), stem(self.input_conv2, feat)
-        for att in self.attentions:
-            feat = att(cond, feat)
+        for i, att in enumerate(self.attentions):
+            feat = att(cond, feat, last=i == len(self.attentions) - 1)
         return feat.to(torch.bfloat16).contiguous()
 
 

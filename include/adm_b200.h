@@ -315,6 +315,37 @@ int adm_linattn_bwd(const void* qkv, long long ld, int batch, int n_pix, int hea
                     const void* dout, long long ldd, const float* ctx, const float* kstat, float* dctx, float* r,
                     float* work, void* dqkv, long long ldg, void* stream);
 
+/* ---------------------------------------------------------------- relation layers (conditional UNet)
+ * BasicAttetnionLayer (unet/cond_unet.py:160-252), the full-resolution tail
+ *     out = GroupNorm(x + y) + resize(z),   x = trunk features, y = concat_conv output (:236-240),
+ *     z = out_conv applied to the pooled tokens (:248-251; a 1x1 conv commutes with the bilinear resize, whose weights
+ *     sum to one), resize = F.interpolate(mode='bilinear', align_corners=True)
+ * as one statistics pass + one apply pass over NHWC bf16 x, y [batch][h][w][c] with the sum held in fp32 registers.
+ * z fp32 [batch][hq][wq][c]; out bf16 (or fp32 with out_fp32); stats fp32 [batch][groups][2] = (mean, rstd) is written
+ * for the backward; work: fp32 scratch of batch * adm_rel_gn_chunks() * max(groups, c) * 2 floats.
+ * Shapes: c % 8 == 0, (c / groups) % 8 == 0, c / 8 divides 256 (adm_rel_gn_ok).
+ * backward: dpre bf16 = d loss / d (x + y) (the gradient of both addends); work then holds per-(sample, chunk, channel)
+ * (sum dout * xhat, sum dout), whose sums over samples and chunks are d gamma / d beta.  d z is adm_bilinear_bwd(dout). */
+int adm_rel_gn_ok(int batch, int h, int w, int c, int groups);
+int adm_rel_gn_chunks(int batch, int h, int w, int c);
+int adm_rel_gn_fwd(const void* x, const void* y, const float* z, int batch, int h, int w, int c, int hq, int wq,
+                   int groups, const float* gamma, const float* beta, float eps, void* out, int out_fp32, float* stats,
+                   float* work, void* stream);
+int adm_rel_gn_bwd(const void* dout, const void* x, const void* y, int batch, int h, int w, int c, int groups,
+                   const float* gamma, const float* stats, void* dpre, float* work, void* stream);
+/* NHWC bilinear resize with align_corners=True (F.interpolate at unet/cond_unet.py:184, :248): x [batch][hin][win][c]
+ * with pixel stride ldx -> y [batch][hout][wout][c] with pixel stride ldy; bf16 or fp32 on either side.  backward:
+ * dy bf16 contiguous -> dx fp32 [batch][hin][win][c] as two separable axis reductions (rows into tmp fp32
+ * [batch][hin][wout][c], then columns); the weights are re-derived exactly as the forward computes them.        */
+int adm_bilinear_fwd(const void* x, long long ldx, int batch, int hin, int win, int c, void* y, long long ldy, int hout,
+                     int wout, int in_fp32, int out_fp32, void* stream);
+int adm_bilinear_bwd(const void* dy, int batch, int hout, int wout, int c, int hin, int win, float* tmp, float* dx,
+                     void* stream);
+/* Window average pool of an NHWC bf16 map, zero padded at the far edges to a multiple of the window
+ * (F.pad + nn.AvgPool2d(window), unet/cond_unet.py:190-200): out [batch][ceil(h/kh)][ceil(w/kw)][c].           */
+int adm_avgpool_fwd(const void* x, int batch, int h, int w, int c, int kh, int kw, void* out, void* stream);
+int adm_avgpool_bwd(const void* dy, int batch, int h, int w, int c, int kh, int kw, void* dx, void* stream);
+
 /* ---------------------------------------------------------------- optimizer over the flat parameter arena
  * train_uncond_dpm.py:292 (clip_grad_norm_ 1.0) + :179-180,296 (AdamW).  out += sum g^2.                      */
 int adm_sq_norm(const float* g, long long numel, float* out, void* stream);

@@ -189,6 +189,84 @@ def resnet_block():
     return ok
 
 
+@case
+def relation_tail():
+    """Fused tail of a relation layer (cond_unet.py:236-251): GroupNorm(x + y) + bilinear(z), forward and backward,
+    against the torch composition in fp32 on the same bf16 inputs."""
+    import torch
+    import torch.nn.functional as F
+    from adm_b200 import functional as AF
+    torch.manual_seed(11)
+    ok = True
+    for (b, h, w, c, hq, wq) in [(2, 32, 32, 128, 4, 4), (1, 16, 16, 512, 16, 16), (2, 24, 40, 256, 3, 5),
+                                 (1, 8, 8, 64, 1, 1), (3, 64, 64, 128, 8, 8)]:
+        G = 8
+        x = (torch.randn(b, h, w, c, device="cuda") * 1.5 + 0.4).bfloat16()
+        y = torch.randn(b, h, w, c, device="cuda").bfloat16()
+        z = torch.randn(b, hq, wq, c, device="cuda")
+        gamma = (torch.rand(c, device="cuda") + 0.5)
+        beta = torch.randn(c, device="cuda") * 0.1
+        dout = torch.randn(b, h, w, c, device="cuda").bfloat16()
+        xr, yr, zr = (t.float().clone().requires_grad_(True) for t in (x, y, z))
+        gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        sc = F.group_norm((xr + yr).permute(0, 3, 1, 2), G, gr, br, 1e-5)
+        up = F.interpolate(zr.permute(0, 3, 1, 2), size=(h, w), mode="bilinear", align_corners=True)
+        ref = (sc + up).permute(0, 2, 3, 1)
+        ref.backward(dout.float())
+        xo, yo, zo = (t.clone().requires_grad_(True) for t in (x, y, z))
+        go, bo = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        out = AF.relation_tail(xo, yo, zo, go, bo, G, 1e-5)
+        out.backward(dout)
+        torch.cuda.synchronize()
+        tag = f"{b}x{h}x{w}x{c} <- {hq}x{wq}"
+        ok &= _report(f"rel tail fwd {tag}", out, ref, 4e-3)
+        ok &= _report("rel tail dx", xo.grad, xr.grad, 5e-3)
+        ok &= _report("rel tail dy", yo.grad, yr.grad, 5e-3)
+        ok &= _report("rel tail dz", zo.grad, zr.grad, 1e-4)
+        ok &= _report("rel tail dgamma", go.grad, gr.grad, 1e-4)
+        ok &= _report("rel tail dbeta", bo.grad, br.grad, 1e-4)
+    return ok
+
+
+@case
+def resize_and_pool():
+    """NHWC bilinear resize (align_corners=True) and the zero-padded window average pool, both directions, vs torch."""
+    import torch
+    import torch.nn.functional as F
+    from adm_b200 import functional as AF
+    torch.manual_seed(12)
+    ok = True
+    for (b, h, w, c, ho, wo) in [(2, 4, 4, 128, 32, 32), (1, 16, 16, 64, 16, 24), (2, 20, 12, 32, 7, 5),
+                                 (1, 1, 1, 8, 9, 9), (2, 16, 16, 256, 128, 128)]:
+        x = torch.randn(b, h, w, c, device="cuda").bfloat16()
+        dy = torch.randn(b, ho, wo, c, device="cuda").bfloat16()
+        xr = x.float().requires_grad_(True)
+        ref = F.interpolate(xr.permute(0, 3, 1, 2), size=(ho, wo), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+        ref.backward(dy.float())
+        xo = x.clone().requires_grad_(True)
+        out = AF.bilinear_resize(xo, (ho, wo))
+        out.backward(dy)
+        torch.cuda.synchronize()
+        ok &= _report(f"bilinear fwd {b}x{h}x{w}x{c} -> {ho}x{wo}", out, ref, 4e-3)
+        ok &= _report("bilinear dx", xo.grad, xr.grad, 4e-3)
+    for (b, h, w, c, win) in [(2, 32, 32, 128, (8, 8)), (1, 10, 7, 64, (4, 4)), (2, 16, 16, 256, (2, 2)),
+                              (1, 9, 9, 8, (2, 4))]:
+        x = torch.randn(b, h, w, c, device="cuda").bfloat16()
+        xr = x.float().requires_grad_(True)
+        ph, pw = (-h) % win[0], (-w) % win[1]
+        ref = F.avg_pool2d(F.pad(xr.permute(0, 3, 1, 2), (0, pw, 0, ph)), win).permute(0, 2, 3, 1)
+        dy = torch.randn_like(ref).bfloat16()
+        ref.backward(dy.float())
+        xo = x.clone().requires_grad_(True)
+        out = AF.avg_pool_window(xo, win)
+        out.backward(dy)
+        torch.cuda.synchronize()
+        ok &= tuple(out.shape) == tuple(ref.shape)
+        ok &= _report(f"avgpool fwd {b}x{h}x{w}x{c} / {win}", out, ref, 4e-3)
+        ok &= _report("avgpool dx", xo.grad, xr.grad, 4e-3)
+    return ok
+
+
 def _golden():
     import torch
     gd = os.path.join(ROOT, "tests", "golden")

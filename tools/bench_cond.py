@@ -98,5 +98,5 @@ if os.environ.get("ADM_PROFILE"):
             tot[nm][1] += ev.device_time_total
     allt = sum(v[1] for v in tot.values())
     print(f"kernel time of one training step: {allt / 1000:.1f} ms")
-    for nm, (c, us) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:28]:
+    for nm, (c, us) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:45]:
         print(f"{us / 1000:8.2f} ms {100 * us / allt:5.1f}%  n={c:5d}  {nm}")
