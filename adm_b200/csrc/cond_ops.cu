@@ -309,25 +309,19 @@ __global__ void linattn_bwd_q_kernel(const __nv_bfloat16* __restrict__ qkv, long
     for (int e = 0; e < LA_D; ++e) dst[e] = acc[e];
 }
 
-// Combine for backward.  grid (B*heads), 32 threads (lane = d): dctx [B*heads][32][32]; r[d] = sum_e dctx[d][e] ctx[d][e].
-__global__ void linattn_dctx_combine_kernel(const float* __restrict__ dpart, int chunks, const float* __restrict__ ctx,
-                                            float* __restrict__ dctx, float* __restrict__ r) {
-    const int bh = blockIdx.x, lane = threadIdx.x;
-    float out[LA_D];
-#pragma unroll
-    for (int e = 0; e < LA_D; ++e) out[e] = 0.f;
-    for (int c = 0; c < chunks; ++c) {
-        const float* src = dpart + ((1LL * bh * chunks + c) * LA_D + lane) * LA_D;
-#pragma unroll
-        for (int e = 0; e < LA_D; ++e) out[e] += src[e];
-    }
-    float rr = 0.f;
-#pragma unroll
-    for (int e = 0; e < LA_D; ++e) {
-        dctx[(1LL * bh * LA_D + lane) * LA_D + e] = out[e];
-        rr = fmaf(out[e], ctx[(1LL * bh * LA_D + lane) * LA_D + e], rr);
-    }
-    r[1LL * bh * LA_D + lane] = rr;
+// Combine for backward.  grid (B*heads), 1024 threads (warp = d, lane = e): dctx [B*heads][32][32] = sum over the chunk
+// partials (coalesced: consecutive threads read consecutive floats of one partial); r[d] = sum_e dctx[d][e] ctx[d][e].
+__global__ void __launch_bounds__(LA_D * LA_D) linattn_dctx_combine_kernel(const float* __restrict__ dpart, int chunks,
+                                                                          const float* __restrict__ ctx,
+                                                                          float* __restrict__ dctx, float* __restrict__ r) {
+    const int bh = blockIdx.x, t = threadIdx.x;
+    const float* src = dpart + 1LL * bh * chunks * (LA_D * LA_D) + t;
+    float out = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < chunks; ++c) out += src[1LL * c * (LA_D * LA_D)];
+    dctx[1LL * bh * LA_D * LA_D + t] = out;
+    const float rr = warp_sum(out * ctx[1LL * bh * LA_D * LA_D + t]);
+    if ((t & 31) == 0) r[1LL * bh * LA_D + (t >> 5)] = rr;
 }
 
 // Backward pass B2.  grid (pixel blocks, B), blockDim = heads*32: warp = head, lane = d for dk and = e for dv.
@@ -573,9 +567,22 @@ static int la_chunks(int n_pix, int batch_heads) {
     return static_cast<int>(want);
 }
 
+// Backward pass B1 runs one CTA of `heads` warps per (pixel chunk, sample): enough chunks for ~8 CTAs per SM, at least
+// 16 iterations of LA_U pixels each.
+static int la_chunks_q(int n_pix, int batch) {
+    long long want = (8LL * num_sms() + batch - 1) / batch;
+    long long max_chunks = (n_pix + 16 * LA_U - 1) / (16 * LA_U);
+    if (want > max_chunks) want = max_chunks;
+    if (want > 256) want = 256;
+    if (want < 1) want = 1;
+    return static_cast<int>(want);
+}
+
 int adm_linattn_workspace(int batch, int heads, int n_pix, long long* floats) {
     const int chunks = la_chunks(n_pix, batch * heads);
-    *floats = 1LL * batch * heads * chunks * LA_D * (LA_D + 2);
+    const long long fwd = 1LL * batch * heads * chunks * LA_D * (LA_D + 2);
+    const long long bwd = 1LL * batch * heads * la_chunks_q(n_pix, batch) * LA_D * LA_D;
+    *floats = fwd > bwd ? fwd : bwd;
     return chunks;
 }
 
@@ -608,12 +615,12 @@ int adm_linattn_bwd(const void* qkv, long long ld, int batch, int n_pix, int hea
     if (dim_head != LA_D) { set_error("linattn: dim_head must be 32 (got %d)", dim_head); return ADM_ERR_SHAPE; }
     if (heads < 1 || heads > 32 || batch <= 0 || n_pix <= 0) { set_error("linattn: bad shape"); return ADM_ERR_SHAPE; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int chunks = la_chunks(n_pix, batch * heads);
+    const int chunks = la_chunks_q(n_pix, batch);
     linattn_bwd_q_kernel<<<dim3(chunks, batch), heads * 32, heads * LA_U * LA_D * sizeof(float), s>>>(
         static_cast<const bf16*>(qkv), ld, n_pix, heads, ctx, scale, static_cast<const bf16*>(dout), ldd,
         static_cast<bf16*>(dqkv), ldg, work);
     ADM_CHECK_LAUNCH("linattn_bwd_q");
-    linattn_dctx_combine_kernel<<<batch * heads, 32, 0, s>>>(work, chunks, ctx, dctx, r);
+    linattn_dctx_combine_kernel<<<batch * heads, LA_D * LA_D, 0, s>>>(work, chunks, ctx, dctx, r);
     ADM_CHECK_LAUNCH("linattn_dctx_combine");
     int blocks = (8 * num_sms() + batch - 1) / batch;
     int ppb = (n_pix + blocks - 1) / blocks;

@@ -18,6 +18,7 @@ Deviations from the reference, all documented in DESIGN.md:
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -433,20 +434,79 @@ class LatentDiffusion(DDPM):
         return x_rec
 
     @torch.no_grad()
-    def sample_fn_latent(self, shape, cond=None, x_T=None):
+    def sample_fn_latent(self, shape, cond=None, x_T=None, use_graph=None):
         """ddm_const.py:868-888: x' = x + (t'-t) * (C + eps / (sqrt(t) + sqrt(t'))) == x0 + C t' + sqrt(t') eps with
-        x0 = x - C t - sqrt(t) eps and no clamp — K3 with do_clip = 0."""
+        x0 = x - C t - sqrt(t) eps and no clamp — K3 with do_clip = 0.  On CUDA the whole N-step loop (N UNet forwards,
+        conditional or not, + N fused updates) is captured once per (shape, N, condition shape) into a CUDA graph and
+        replayed with the start noise and the condition copied into its static inputs (``ADM_SAMPLE_GRAPH=0``: eager)."""
         device = self.eps.device
         ts = self.t_steps()
         if x_T is None:
             x_T = torch.randn(shape, device=device, dtype=torch.float64)
-        x = (x_T.to(device=device, dtype=torch.float64) * ts[0]).contiguous()
-        t_dev = torch.tensor(ts, device=device, dtype=torch.float64)
+        x_T = x_T.to(device=device, dtype=torch.float64)
+        if use_graph is None:
+            use_graph = (x_T.is_cuda and not torch.cuda.is_current_stream_capturing()
+                         and os.environ.get("ADM_SAMPLE_GRAPH", "1") != "0" and not self.__dict__.get("_latent_graph_off"))
         was_training = self.model.training
         self.model.eval()
+        try:
+            if use_graph:
+                try:
+                    return self._sample_latent_graph(x_T, ts, cond)
+                except RuntimeError as e:  # an op of the network that cannot be captured: run the loop eagerly from now on
+                    self.__dict__["_latent_graph_off"] = True
+                    self.__dict__.pop("_latent_graphs", None)
+                    torch.cuda.synchronize()
+                    print(f"[adm_b200] latent sampler: CUDA graph capture failed ({str(e)[:200]}); running eagerly")
+            t_dev = torch.tensor(ts, device=device, dtype=torch.float64)
+            return self._sample_latent_loop(x_T, ts, t_dev, cond)
+        finally:
+            self.model.train(was_training)
+
+    def _sample_latent_loop(self, x_T, ts, t_dev, cond):
+        x = (x_T * ts[0]).contiguous()
         for i, (t_cur, t_next) in enumerate(zip(ts[:-1], ts[1:])):
             pred = self.model(x, t_dev[i], cond) if cond is not None else self.model(x, t_dev[i])
             c, noise = pred[:2]
             x = ops.sampler_step(x, c.float(), noise.float(), t_cur, t_next, 1.0, False, False, 1.0)
-        self.model.train(was_training)
         return x
+
+    def _latent_pointers(self):
+        """What a captured loop reads through raw pointers: the engine's cached operands where the network has a fused
+        engine, else the parameters / buffers themselves (module graphs re-derive their packed operands from them inside
+        every forward, so in-place optimizer or EMA updates need no re-capture; re-homed storage does)."""
+        ptrs = self._model_pointers()
+        if ptrs is not None:
+            return ptrs
+        return tuple(t.data_ptr() for t in list(self.model.parameters()) + list(self.model.buffers()))
+
+    def _sample_latent_graph(self, x_T, ts, cond):
+        key = (tuple(x_T.shape), tuple(ts), None if cond is None else (tuple(cond.shape), cond.dtype))
+        cache = self.__dict__.setdefault("_latent_graphs", {})
+        ent = cache.get(key)
+        sig, ptrs = self._model_signature(), self._latent_pointers()
+        if ent is not None and ent["ptrs"] != ptrs:
+            ent = None
+        if ent is None:
+            t_dev = torch.tensor(ts, device=x_T.device, dtype=torch.float64)
+            static_in = x_T.clone()
+            static_cond = None if cond is None else cond.detach().clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up outside capture (weight caches, lazy initialisation)
+                self._sample_latent_loop(static_in, ts[:2] + [0.0] if len(ts) > 2 else ts, t_dev, static_cond)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = self._sample_latent_loop(static_in, ts, t_dev, static_cond)
+            ent = cache[key] = dict(graph=g, x=static_in, cond=static_cond, out=static_out, t=t_dev, sig=sig, ptrs=ptrs)
+        elif ent["sig"] != sig:
+            # engine parameters changed since capture: one eager forward re-derives the cached bf16 operands in place
+            self.model(ent["x"], ent["t"][0], ent["cond"]) if cond is not None else self.model(ent["x"], ent["t"][0])
+            ent["sig"] = sig
+        ent["x"].copy_(x_T)
+        if cond is not None:
+            ent["cond"].copy_(cond)
+        ent["graph"].replay()
+        return ent["out"].clone()

@@ -35,15 +35,16 @@ def _engines(model):
 def _detached_copy(model):
     """deepcopy that leaves training-arena plumbing behind: CUDA graphs are not copyable, and parameters re-homed in a
     TrainStep arena carry bf16-shadow attributes that must not follow the copy."""
-    stash = [(m, m.__dict__.pop("_sample_graphs")) for m in model.modules() if "_sample_graphs" in m.__dict__]
+    stash = [(m, k, m.__dict__.pop(k)) for m in model.modules() for k in ("_sample_graphs", "_latent_graphs")
+             if k in m.__dict__]
     hooks = [(e, e.grad_hook, e.affine_pack, e._cache, e.seed_counter) for e in _engines(model)]
     for e, *_ in hooks:
         e.grad_hook, e.affine_pack, e._cache, e.seed_counter = None, None, {}, None
     try:
         new = copy.deepcopy(model)
     finally:
-        for m, g in stash:
-            m.__dict__["_sample_graphs"] = g
+        for m, k, g in stash:
+            m.__dict__[k] = g
         for e, h, a, c, s in hooks:
             e.grad_hook, e.affine_pack, e._cache, e.seed_counter = h, a, c, s
     for p in new.parameters():

@@ -156,9 +156,12 @@ def build_model(device):
     return dpm
 
 
-def conv_roofline(device, iters=30):
+def conv_roofline(device, iters=10, groups=5):
     """Times the dominant kernel shape alone (conv3x3 384->384 @16x16, batch 128: 15 such convs per forward) with CUDA
-    events on the launching stream, rotating over input buffers that together exceed L2."""
+    events on the launching stream, rotating over input buffers that together exceed L2.  The denominator is the BURST
+    figure of MEASURED_PEAKS.json (best of 10 short runs on an idle board), so the kernel is timed the same way: `groups`
+    bursts of `iters` launches, each after a short idle gap so that the board is not still power-capped by the preceding
+    training / sampling loops.  Returns (TFLOP/s over ALL timed launches, their mean ms, TFLOP/s of the best burst)."""
     import torch
     from adm_b200 import ops
     n, hw, c = 128, 16, 384
@@ -170,15 +173,20 @@ def conv_roofline(device, iters=30):
     for i in range(3):
         ops.conv_fprop(xs[i % nbuf], w, bias=bias, out=outs[i % nbuf])
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(iters):
-        ops.conv_fprop(xs[i % nbuf], w, bias=bias, out=outs[i % nbuf])
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+    times = []
+    for _ in range(groups):
+        time.sleep(0.5)
+        ops.conv_fprop(xs[0], w, bias=bias, out=outs[0])  # one untimed launch: clocks up after the idle gap
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            ops.conv_fprop(xs[(i + 1) % nbuf], w, bias=bias, out=outs[(i + 1) % nbuf])
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1) / iters)
+    ms = sum(times) / len(times)
     flops = 2.0 * n * hw * hw * c * c * 9
-    return flops / (ms * 1e-3) / 1e12, ms
+    return flops / (ms * 1e-3) / 1e12, ms, flops / (min(times) * 1e-3) / 1e12
 
 
 def sampler_sweep(dpm, B, device, steps_list=(1, 10, 50)):
@@ -477,7 +485,7 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     pk = peaks()
-    conv_tf, conv_ms = conv_roofline(device)
+    conv_tf, conv_ms, conv_tf_best = conv_roofline(device)
     value = B * world / (ms / 1000)
     step_tf = TRAIN_GFLOP_PER_IMG * B / ms  # GFLOP / ms = TFLOP/s per GPU
     cpu = None
@@ -514,6 +522,9 @@ def run_ours(args):
                                        "(profiles/r02_conv_ncu_full.txt); not re-measured by this run",
                      "algorithmic_flops_per_launch": 2.0 * 128 * 16 * 16 * 384 * 384 * 9,
                      "kernel": "tc_conv_halo_kernel conv3x3 384->384 @16x16 x128 (dominant shape), timed alone",
+                     "timing": "mean of 5 bursts x 10 launches (CUDA events, 0.5 s idle before each burst, inputs rotate "
+                               "over 8 buffers > L2); the peak is the burst figure, best of 10 short runs",
+                     "achieved_best_burst": conv_tf_best,
                      "ms_per_launch": conv_ms, "peak_source": pk["src"],
                      "step_tflops_per_gpu": step_tf, "step_frac_of_sustained_peak": step_tf / pk["tf_sust"]},
         "sample": {"metric": "sample10_img_per_s", "value": B * world / (ms_sample / 1000), "unit": "img/s",
