@@ -141,12 +141,12 @@ rel_gn_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y, cons
     const int p0 = chunk * per, p1 = min(npix, p0 + per);
     const size_t base = (static_cast<size_t>(b) * npix) * c + cv * 8;
     const float* zb = z + (static_cast<size_t>(b) * hq * wq) * c + cv * 8;
+    int ph = (p0 + pl) / w, pw = (p0 + pl) - ph * w;  // (row, column) of the thread's pixel, advanced without divisions
 #pragma unroll 2
     for (int p = p0 + pl; p < p1; p += ppi) {
         float xv[8], yv[8], o[8];
         ld8(x + base + static_cast<size_t>(p) * c, xv);
         ld8(y + base + static_cast<size_t>(p) * c, yv);
-        const int ph = p / w, pw = p - ph * w;
         int h0, h1, w0, w1;
         float lh, lw;
         lerp_coord(ph, sh, hq, h0, h1, lh);
@@ -163,6 +163,11 @@ rel_gn_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y, cons
             o[i] = fmaf(xv[i] + yv[i], ga[i], be[i]) + up;
         }
         st8(out + base + static_cast<size_t>(p) * c, o);
+        pw += ppi;
+        while (pw >= w) {
+            pw -= w;
+            ++ph;
+        }
     }
 }
 
@@ -269,11 +274,11 @@ rel_gn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ 
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256) bilinear_fwd_kernel(const TIn* __restrict__ x, long long ldx, int hin, int win,
                                                            int c, TOut* __restrict__ y, long long ldy, int hout,
-                                                           int wout, float sh, float sw, long long total) {
-    const int lanes = c >> 3;
-    for (long long t = blockIdx.x * 256LL + threadIdx.x; t < total; t += gridDim.x * 256LL) {
+                                                           int wout, float sh, float sw, unsigned total) {
+    const unsigned lanes = c >> 3;  // 32-bit index math: a 64-bit division costs ~100 instructions on the SM
+    for (unsigned t = blockIdx.x * 256u + threadIdx.x; t < total; t += gridDim.x * 256u) {
         const int cv = static_cast<int>(t % lanes);
-        long long p = t / lanes;
+        unsigned p = t / lanes;
         const int ow = static_cast<int>(p % wout);
         p /= wout;
         const int oh = static_cast<int>(p % hout);
@@ -301,12 +306,13 @@ __global__ void __launch_bounds__(256) bilinear_fwd_kernel(const TIn* __restrict
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256) lerp_axis_bwd_kernel(const TIn* __restrict__ src, TOut* __restrict__ dst,
                                                             int n_out, int n_in, long long inner, float scale,
-                                                            long long total) {
-    const long long iv = inner >> 3;
-    for (long long t = blockIdx.x * 256LL + threadIdx.x; t < total; t += gridDim.x * 256LL) {
+                                                            unsigned total) {
+    const unsigned iv = static_cast<unsigned>(inner >> 3);
+    for (unsigned t = blockIdx.x * 256u + threadIdx.x; t < total; t += gridDim.x * 256u) {
         const long long kv = t % iv;
-        const int i = static_cast<int>((t / iv) % n_in);
-        const long long o = t / (iv * n_in);
+        const unsigned q = t / iv;
+        const int i = static_cast<int>(q % n_in);
+        const long long o = q / n_in;
         int plo = 0, phi = n_out - 1;
         if (scale > 0.f) {
             plo = max(0, static_cast<int>(floorf((i - 1) / scale)) - 1);
@@ -334,12 +340,12 @@ __global__ void __launch_bounds__(256) lerp_axis_bwd_kernel(const TIn* __restric
 // ------------------------------------------------------------------------------------------------ window average pool
 // out[b][i][j][:] = sum over the kh x kw window (pixels past the edge count as zero) / (kh * kw)
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const bf16* __restrict__ x, int h, int w, int c, int kh, int kw,
-                                                          int ho, int wo, bf16* __restrict__ out, long long total) {
-    const int lanes = c >> 3;
+                                                          int ho, int wo, bf16* __restrict__ out, unsigned total) {
+    const unsigned lanes = c >> 3;
     const float inv = 1.f / (kh * kw);
-    for (long long t = blockIdx.x * 256LL + threadIdx.x; t < total; t += gridDim.x * 256LL) {
+    for (unsigned t = blockIdx.x * 256u + threadIdx.x; t < total; t += gridDim.x * 256u) {
         const int cv = static_cast<int>(t % lanes);
-        long long p = t / lanes;
+        unsigned p = t / lanes;
         const int j = static_cast<int>(p % wo);
         p /= wo;
         const int i = static_cast<int>(p % ho);
@@ -366,12 +372,12 @@ __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const bf16* __restrict
 
 // dx[b][r][cc][:] = dy[b][r / kh][cc / kw][:] / (kh * kw)
 __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const bf16* __restrict__ dy, int h, int w, int c, int kh, int kw,
-                                                          int ho, int wo, bf16* __restrict__ dx, long long total) {
-    const int lanes = c >> 3;
+                                                          int ho, int wo, bf16* __restrict__ dx, unsigned total) {
+    const unsigned lanes = c >> 3;
     const float inv = 1.f / (kh * kw);
-    for (long long t = blockIdx.x * 256LL + threadIdx.x; t < total; t += gridDim.x * 256LL) {
+    for (unsigned t = blockIdx.x * 256u + threadIdx.x; t < total; t += gridDim.x * 256u) {
         const int cv = static_cast<int>(t % lanes);
-        long long p = t / lanes;
+        unsigned p = t / lanes;
         const int cc = static_cast<int>(p % w);
         p /= w;
         const int r = static_cast<int>(p % h);
@@ -394,12 +400,18 @@ static int rel_shape_ok(int batch, int h, int w, int c, int groups) {
 
 static int rel_chunks(int batch, long long npix, int c) {
     const long long ppi = REL_THREADS / (c / 8);
-    long long want = (4LL * num_sms() + batch - 1) / batch;
+    long long want = (8LL * num_sms() + batch - 1) / batch;  // 64 warps per SM in flight for the statistics passes
     const long long most = (npix + 4 * ppi - 1) / (4 * ppi);  // at least four iterations per thread
     if (want > most) want = most;
     if (want > 256) want = 256;
     if (want < 1) want = 1;
     return static_cast<int>(want);
+}
+
+static bool flat_ok(long long total, const char* what) {  // the flat kernels index with 32 bits
+    if (total > 0 && total < (1LL << 31)) return true;
+    set_error("%s: %lld vectors of 8 channels do not fit the 32-bit index space", what, total);
+    return false;
 }
 
 static unsigned flat_grid(long long total) {
@@ -472,20 +484,21 @@ int adm_bilinear_fwd(const void* x, long long ldx, int batch, int hin, int win, 
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const long long total = 1LL * batch * hout * wout * (c / 8);
+    if (!flat_ok(total, "bilinear_fwd")) return ADM_ERR_SHAPE;
     const float sh = lerp_scale(hin, hout), sw = lerp_scale(win, wout);
     const unsigned grid = flat_grid(total);
     if (in_fp32 && out_fp32)
         bilinear_fwd_kernel<float, float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), ldx, hin, win, c,
-                                                               static_cast<float*>(y), ldy, hout, wout, sh, sw, total);
+                                                               static_cast<float*>(y), ldy, hout, wout, sh, sw, static_cast<unsigned>(total));
     else if (in_fp32)
         bilinear_fwd_kernel<float, bf16><<<grid, 256, 0, s>>>(static_cast<const float*>(x), ldx, hin, win, c,
-                                                              static_cast<bf16*>(y), ldy, hout, wout, sh, sw, total);
+                                                              static_cast<bf16*>(y), ldy, hout, wout, sh, sw, static_cast<unsigned>(total));
     else if (out_fp32)
         bilinear_fwd_kernel<bf16, float><<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), ldx, hin, win, c,
-                                                              static_cast<float*>(y), ldy, hout, wout, sh, sw, total);
+                                                              static_cast<float*>(y), ldy, hout, wout, sh, sw, static_cast<unsigned>(total));
     else
         bilinear_fwd_kernel<bf16, bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), ldx, hin, win, c,
-                                                             static_cast<bf16*>(y), ldy, hout, wout, sh, sw, total);
+                                                             static_cast<bf16*>(y), ldy, hout, wout, sh, sw, static_cast<unsigned>(total));
     ADM_CHECK_LAUNCH("bilinear_fwd");
     return 0;
 }
@@ -500,12 +513,13 @@ int adm_bilinear_bwd(const void* dy, int batch, int hout, int wout, int c, int h
     // rows first: [batch][hout][wout * c] -> tmp [batch][hin][wout * c] (fp32), then columns: [batch * hin][wout][c] -> dx
     const long long inner1 = 1LL * wout * c;
     const long long total1 = 1LL * batch * hin * (inner1 / 8);
+    if (!flat_ok(total1, "bilinear_bwd") || !flat_ok(1LL * batch * hout * (inner1 / 8), "bilinear_bwd")) return ADM_ERR_SHAPE;
     lerp_axis_bwd_kernel<bf16, float><<<flat_grid(total1), 256, 0, s>>>(static_cast<const bf16*>(dy), tmp, hout, hin,
-                                                                        inner1, lerp_scale(hin, hout), total1);
+                                                                        inner1, lerp_scale(hin, hout), static_cast<unsigned>(total1));
     ADM_CHECK_LAUNCH("lerp_axis_bwd(rows)");
     const long long total2 = 1LL * batch * hin * win * (c / 8);
     lerp_axis_bwd_kernel<float, float><<<flat_grid(total2), 256, 0, s>>>(tmp, dx, wout, win, c, lerp_scale(win, wout),
-                                                                         total2);
+                                                                         static_cast<unsigned>(total2));
     ADM_CHECK_LAUNCH("lerp_axis_bwd(cols)");
     return 0;
 }
@@ -517,8 +531,9 @@ int adm_avgpool_fwd(const void* x, int batch, int h, int w, int c, int kh, int k
     }
     const int ho = (h + kh - 1) / kh, wo = (w + kw - 1) / kw;
     const long long total = 1LL * batch * ho * wo * (c / 8);
+    if (!flat_ok(total, "avgpool_fwd")) return ADM_ERR_SHAPE;
     avgpool_fwd_kernel<<<flat_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const bf16*>(x), h, w, c, kh, kw, ho, wo, static_cast<bf16*>(out), total);
+        static_cast<const bf16*>(x), h, w, c, kh, kw, ho, wo, static_cast<bf16*>(out), static_cast<unsigned>(total));
     ADM_CHECK_LAUNCH("avgpool_fwd");
     return 0;
 }
@@ -530,8 +545,9 @@ int adm_avgpool_bwd(const void* dy, int batch, int h, int w, int c, int kh, int 
     }
     const int ho = (h + kh - 1) / kh, wo = (w + kw - 1) / kw;
     const long long total = 1LL * batch * h * w * (c / 8);
+    if (!flat_ok(total, "avgpool_bwd")) return ADM_ERR_SHAPE;
     avgpool_bwd_kernel<<<flat_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const bf16*>(dy), h, w, c, kh, kw, ho, wo, static_cast<bf16*>(dx), total);
+        static_cast<const bf16*>(dy), h, w, c, kh, kw, ho, wo, static_cast<bf16*>(dx), static_cast<unsigned>(total));
     ADM_CHECK_LAUNCH("avgpool_bwd");
     return 0;
 }

@@ -465,8 +465,13 @@ class LatentDiffusion(DDPM):
 
     def _sample_latent_loop(self, x_T, ts, t_dev, cond):
         x = (x_T * ts[0]).contiguous()
+        kw = {}
+        if cond is not None and hasattr(self.model, "encode_condition"):
+            # the condition is the same at every step (ddm_const.py:868-888 passes `cond` unchanged): its encoder
+            # (Swin-B + projections, a third of the conditional UNet's forward time) runs once per sample() call
+            kw["cond_feats"] = self.model.encode_condition(cond, x.shape[-2:])
         for i, (t_cur, t_next) in enumerate(zip(ts[:-1], ts[1:])):
-            pred = self.model(x, t_dev[i], cond) if cond is not None else self.model(x, t_dev[i])
+            pred = self.model(x, t_dev[i], cond, **kw) if cond is not None else self.model(x, t_dev[i])
             c, noise = pred[:2]
             x = ops.sampler_step(x, c.float(), noise.float(), t_cur, t_next, 1.0, False, False, 1.0)
         return x

@@ -705,7 +705,19 @@ class Unet(nn.Module):
         x = final_block(torch.cat((x, r), dim=-1), t)
         return final_conv(x)
 
-    def forward(self, x, time, mask, x_self_cond=None, sigma_max=1, *args, **kwargs):
+    def encode_condition(self, mask, size):
+        """The part of ``forward`` that depends on the condition only (cond_unet.py:724-733): Swin-B features of the
+        condition image, their 1x1 projections (NHWC bf16, shared by the encoder and both decoders) and the bilinear
+        resize of the first feature map that is concatenated to the input of the stem.  A sampler whose condition is
+        fixed over its N steps computes it once and passes it back as ``forward(..., cond_feats=...)``."""
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=SIDE_DTYPE == torch.bfloat16):
+            hm = self.init_conv_mask(mask.to(torch.float32))
+            up0 = F.interpolate(hm[0].float().contiguous(memory_format=torch.channels_last), size=tuple(size),
+                                mode="bilinear")
+            hm = [_nhwc(proj(f)) for proj, f in zip(self.projects, hm)]
+        return up0, hm
+
+    def forward(self, x, time, mask, x_self_cond=None, sigma_max=1, *args, cond_feats=None, **kwargs):
         if not x.is_cuda:
             raise RuntimeError("adm_b200: the conditional UNet runs on CUDA (sm_100a) only; there is no CPU fallback")
         x = x.to(torch.float32)
@@ -720,12 +732,8 @@ class Unet(nn.Module):
         c_out1, c_out2 = t4 / (t4 + 1).sqrt(), (1 - t4).sqrt() / (1 + t4).sqrt()
         c_noise = time.log()
         x_in = x
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=SIDE_DTYPE == torch.bfloat16):
-            hm = self.init_conv_mask(mask.to(torch.float32))
-            up0 = F.interpolate(hm[0].float().contiguous(memory_format=torch.channels_last), size=x.shape[-2:],
-                                mode="bilinear")
-            stem_in = torch.cat([x, up0], dim=1)
-            hm = [_nhwc(proj(f)) for proj, f in zip(self.projects, hm)]  # NHWC bf16, shared by encoder and both decoders
+        up0, hm = cond_feats if cond_feats is not None else self.encode_condition(mask, x.shape[-2:])
+        stem_in = torch.cat([x, up0], dim=1)
         # 7x7 stem (cond_unet.py:656, 7 % of the FLOPs): the implicit-GEMM conv with 49 taps; the 131 input channels are
         # zero-padded to a multiple of 8 on the activation and on the weight
         stem, sx = self.init_conv[0], _nhwc(stem_in)
