@@ -109,23 +109,33 @@ rel_gn_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y, cons
     const int lanes = c >> 3, ppi = REL_THREADS / lanes;
     const int cv = threadIdx.x % lanes, pl = threadIdx.x / lanes;
     const int chunk = blockIdx.x, chunks = gridDim.x, b = blockIdx.y;
-    if (threadIdx.x < groups) {
+    // chunk partials -> (mean, rstd): one warp per group, lanes over the chunks (every CTA of the sample repeats this, so it
+    // must not be a serial walk over the chunks)
+    for (int gg = threadIdx.x >> 5; gg < groups; gg += REL_THREADS / 32) {
+        const int lane = threadIdx.x & 31;
         double s = 0.0, q = 0.0;
-        const float* wk = work + (static_cast<size_t>(b) * chunks * groups + threadIdx.x) * 2;
-        for (int k = 0; k < chunks; ++k) {
+        const float* wk = work + (static_cast<size_t>(b) * chunks * groups + gg) * 2;
+        for (int k = lane; k < chunks; k += 32) {
             s += wk[static_cast<size_t>(k) * groups * 2];
             q += wk[static_cast<size_t>(k) * groups * 2 + 1];
         }
-        const double n = static_cast<double>(npix) * (c / groups);
-        const double mean = s / n;
-        double var = q / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        const float rstd = rsqrtf(static_cast<float>(var) + eps);
-        sm[threadIdx.x][0] = static_cast<float>(mean);
-        sm[threadIdx.x][1] = rstd;
-        if (chunk == 0) {
-            stats[(static_cast<size_t>(b) * groups + threadIdx.x) * 2] = static_cast<float>(mean);
-            stats[(static_cast<size_t>(b) * groups + threadIdx.x) * 2 + 1] = rstd;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (lane == 0) {
+            const double n = static_cast<double>(npix) * (c / groups);
+            const double mean = s / n;
+            double var = q / n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const float rstd = rsqrtf(static_cast<float>(var) + eps);
+            sm[gg][0] = static_cast<float>(mean);
+            sm[gg][1] = rstd;
+            if (chunk == 0) {
+                stats[(static_cast<size_t>(b) * groups + gg) * 2] = static_cast<float>(mean);
+                stats[(static_cast<size_t>(b) * groups + gg) * 2 + 1] = rstd;
+            }
         }
     }
     __syncthreads();
@@ -228,7 +238,8 @@ rel_gn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ 
     for (int i = threadIdx.x; i < 2 * c; i += REL_THREADS) {
         const float* wk = work + static_cast<size_t>(b) * chunks * c * 2 + i;
         float s = 0.f;
-        for (int k = 0; k < chunks; ++k) s += wk[static_cast<size_t>(k) * c * 2];
+#pragma unroll 8
+        for (int k = 0; k < chunks; ++k) s += wk[static_cast<size_t>(k) * c * 2];  // eight loads in flight
         sc[i] = s;
     }
     __syncthreads();
@@ -400,7 +411,7 @@ static int rel_shape_ok(int batch, int h, int w, int c, int groups) {
 
 static int rel_chunks(int batch, long long npix, int c) {
     const long long ppi = REL_THREADS / (c / 8);
-    long long want = (8LL * num_sms() + batch - 1) / batch;  // 64 warps per SM in flight for the statistics passes
+    long long want = (4LL * num_sms() + batch - 1) / batch;  // (8 CTAs per SM measured slower: the chunk combine grows)
     const long long most = (npix + 4 * ppi - 1) / (4 * ppi);  // at least four iterations per thread
     if (want > most) want = most;
     if (want > 256) want = 256;

@@ -41,8 +41,9 @@ LATENT_CONFIGS = {
                   "fwd+bwd+AdamW"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel from `ncu --set full`
-# (profiles/r02_conv_ncu_full.txt): the 25 MB input is read once, weights 2.6 MB, the output stays in L2.
-CONV_DRAM_TRAFFIC_BYTES = 28.1e6
+# (profiles/r05_conv_ncu_full.txt, final build: 27.91 MB read + 0.34 MB written): the 25 MB input is read once, weights
+# 2.6 MB, the output is still in L2 when the kernel ends.
+CONV_DRAM_TRAFFIC_BYTES = 28.25e6
 
 
 def peaks():
@@ -528,7 +529,7 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": conv_tf, "peak": pk["tf_burst"], "unit": "TFLOP/s",
                      "frac": conv_tf / pk["tf_burst"], "traffic": CONV_DRAM_TRAFFIC_BYTES,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                       "(profiles/r02_conv_ncu_full.txt); not re-measured by this run",
+                                       "(profiles/r05_conv_ncu_full.txt); not re-measured by this run",
                      "algorithmic_flops_per_launch": 2.0 * 128 * 16 * 16 * 384 * 384 * 9,
                      "kernel": "tc_conv_halo_kernel conv3x3 384->384 @16x16 x128 (dominant shape), timed alone",
                      "timing": "mean of 5 bursts x 10 launches, each burst one CUDA graph replay between CUDA events (0.5 s idle "

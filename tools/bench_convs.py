@@ -13,6 +13,7 @@ SHAPES = [  # (count, cin, cout, res, k)
     (1, 192, 384, 16, 1),
 ]
 
+SHAPES = SHAPES[:int(os.environ.get("ADM_BENCH_SHAPES", len(SHAPES)))]  # first k shapes only
 
 from tools.bench_convs_lib import timeit  # noqa: E402
 
