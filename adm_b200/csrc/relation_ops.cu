@@ -151,12 +151,13 @@ rel_gn_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y, cons
     const int p0 = chunk * per, p1 = min(npix, p0 + per);
     const size_t base = (static_cast<size_t>(b) * npix) * c + cv * 8;
     const float* zb = z + (static_cast<size_t>(b) * hq * wq) * c + cv * 8;
-    int ph = (p0 + pl) / w, pw = (p0 + pl) - ph * w;  // (row, column) of the thread's pixel, advanced without divisions
 #pragma unroll 2
     for (int p = p0 + pl; p < p1; p += ppi) {
         float xv[8], yv[8], o[8];
         ld8(x + base + static_cast<size_t>(p) * c, xv);
         ld8(y + base + static_cast<size_t>(p) * c, yv);
+        const int ph = p / w, pw = p - ph * w;  // (an incrementally advanced (row, column) pair measured 25 % slower: the
+                                                //  loop-carried update keeps the compiler from batching the loads)
         int h0, h1, w0, w1;
         float lh, lw;
         lerp_coord(ph, sh, hq, h0, h1, lh);
@@ -173,11 +174,6 @@ rel_gn_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y, cons
             o[i] = fmaf(xv[i] + yv[i], ga[i], be[i]) + up;
         }
         st8(out + base + static_cast<size_t>(p) * c, o);
-        pw += ppi;
-        while (pw >= w) {
-            pw -= w;
-            ++ph;
-        }
     }
 }
 

@@ -283,11 +283,14 @@ class DDPM(nn.Module):
         self.model.eval()
         clip = 1. * self.scale_input
         cur = 1.0
+        kw = {}
+        if cond is not None and hasattr(self.model, "encode_condition"):
+            kw["cond_feats"] = self.model.encode_condition(cond, img.shape[-2:])  # fixed over the steps: encoded once
         for i, s in enumerate(steps):
             if i == n - 1:
                 s = cur
             tc = torch.tensor(cur, device=device, dtype=torch.float64)
-            pred = self.model(img, tc, cond) if cond is not None else self.model(img, tc)
+            pred = self.model(img, tc, cond, **kw) if cond is not None else self.model(img, tc)
             c, noise = pred[:2]
             z = z_list[i].to(device) if z_list is not None else torch.randn_like(img)
             img = ops.sampler_step_stochastic(img, c, noise, z, cur, s, clip, self.clip_x_start)
