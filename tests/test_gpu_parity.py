@@ -260,7 +260,7 @@ from tests.gpu_checks import check_cond as CC  # noqa: E402
 
 
 @pytest.mark.parametrize("case", ["ws_pack", "channel_layernorm", "linear_attention", "attention_padded_heads",
-                                  "resnet_block", "relation_tail", "resize_and_pool"])
+                                  "resnet_block", "relation_tail", "resize_and_pool", "relation_layer_golden"])
 def test_cond_unet_kernels(case):
     """K11 weight-standardise+pack, K12 fused LinearAttention, padded-head Attention, ResnetBlock fwd/bwd vs torch."""
     assert CC.CASES[case]()

@@ -159,3 +159,64 @@ def test_oracle_song_unet_vs_reference_golden(golden_dir, name):
         assert torch.allclose(sd[k].grad, ref, rtol=1e-3, atol=1e-4 * float(ref.abs().max()) + 1e-6), k
     for k, n in g["grad_norms"].items():
         assert abs(float(sd[k].grad.norm()) - n) <= 1e-3 * n + 1e-6, k
+
+
+# ---------------------------------------------------------------- relation layer of the conditional UNet (row f-3)
+from oracle import relation_oracle as R  # noqa: E402
+
+
+def _relation_golden(golden_dir):
+    return torch.load(os.path.join(golden_dir, "relation_layer.pt"))
+
+
+@pytest.mark.parametrize("commute", [False, True])
+def test_relation_layer_oracle_matches_reference(golden_dir, commute):
+    """oracle.relation_layer (cond_unet.py:192-252) against the unmodified reference module's output and gradients
+    (tests/golden/make_golden_relation.py) — in the reference's op order, and with out_conv applied to the pooled tokens
+    before the bilinear resize (the order the fused sm_100a path uses): the same linear map."""
+    for name, g in _relation_golden(golden_dir).items():
+        spec = g["spec"]
+        x1, x2 = g["x1"].clone().requires_grad_(True), g["x2"].clone().requires_grad_(True)
+        sd = {k: v.clone().requires_grad_(True) for k, v in g["state_dict"].items()}
+        out = R.relation_layer(sd, x1, x2, spec["nhead"], spec["window_size1"], spec["window_size2"],
+                               commute_out_conv=commute)
+        assert torch.allclose(out, g["out"], rtol=1e-4, atol=2e-5), (name, (out - g["out"]).abs().max())
+        (out * g["probe"]).sum().backward()
+        for key, got, ref in ([("x1", x1.grad, g["dx1"]), ("x2", x2.grad, g["dx2"])]
+                              + [(k, sd[k].grad, g["grads"][k]) for k in g["grads"]]):
+            # k_lin.bias shifts every logit of a query by the same amount, so its gradient is exactly zero in real
+            # arithmetic and rounding noise (1e-5) in both implementations: hence the absolute floor
+            assert (got - ref).norm() <= 2e-4 * ref.norm() + 2e-4, (name, key, (got - ref).norm(), ref.norm())
+
+
+def test_relation_kernel_algorithms_match_autograd():
+    """The algorithms of csrc/relation_ops.cu restated on the CPU (fp64) against torch: separable transposed resize,
+    zero-padded window pool, and the closed-form backward of GroupNorm(x + y) + resize(z)."""
+    import torch.nn.functional as F
+    torch.manual_seed(4)
+    for (h, w, ho, wo) in [(4, 4, 16, 16), (3, 5, 24, 40), (16, 16, 16, 16), (20, 12, 7, 5), (1, 1, 9, 9)]:
+        x = torch.randn(2, h, w, 8, dtype=torch.float64, requires_grad=True)
+        ref = F.interpolate(x.permute(0, 3, 1, 2), size=(ho, wo), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+        assert torch.allclose(R.bilinear_fwd(x.detach(), (ho, wo)), ref, atol=1e-5)  # fp32 coordinates, as ATen
+        dy = torch.randn_like(ref)
+        ref.backward(dy)
+        assert torch.allclose(R.bilinear_bwd_separable(dy, (h, w)), x.grad, atol=1e-4)
+    for (h, w, win) in [(32, 32, (8, 8)), (10, 7, (4, 4)), (9, 9, (2, 4))]:
+        x = torch.randn(2, h, w, 8, dtype=torch.float64)
+        ph, pw = (-h) % win[0], (-w) % win[1]
+        ref = F.avg_pool2d(F.pad(x.permute(0, 3, 1, 2), (0, pw, 0, ph)), win).permute(0, 2, 3, 1)
+        assert torch.allclose(R.window_pool(x, win), ref, atol=1e-12)
+    b, h, w, c, G = 2, 12, 10, 32, 8
+    x, y = (torch.randn(b, h, w, c, dtype=torch.float64, requires_grad=True) for _ in range(2))
+    z = torch.randn(b, 3, 5, c, dtype=torch.float64)
+    gamma = (torch.rand(c, dtype=torch.float64) + 0.5).requires_grad_(True)
+    beta = torch.randn(c, dtype=torch.float64, requires_grad=True)
+    ref = (F.group_norm((x + y).permute(0, 3, 1, 2), G, gamma, beta, 1e-5)
+           + F.interpolate(z.permute(0, 3, 1, 2), size=(h, w), mode="bilinear", align_corners=True)).permute(0, 2, 3, 1)
+    out, _, _ = R.relation_tail(x.detach(), y.detach(), z, gamma.detach(), beta.detach(), G)
+    assert torch.allclose(out, ref, atol=1e-5)
+    dout = torch.randn_like(ref)
+    ref.backward(dout)
+    dpre, dgamma, dbeta = R.relation_tail_bwd(dout, x.detach(), y.detach(), gamma.detach(), G)
+    assert torch.allclose(dpre, x.grad, atol=1e-9) and torch.allclose(dpre, y.grad, atol=1e-9)
+    assert torch.allclose(dgamma, gamma.grad, atol=1e-9) and torch.allclose(dbeta, beta.grad, atol=1e-9)
