@@ -276,13 +276,23 @@ def run_latent(args):
     """BASELINE configs 4 / 5 on ONE GPU: AE encode (no grad) -> DDM-const step on latents.  Reported lines, not the headline."""
     import torch
     from adm_b200 import _lib
+    import torch.distributed as dist
     spec = LATENT_CONFIGS[args.config]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
     device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(device)
+    if world > 1:
+        # data parallel over the ranks of one node through TrainStep's bucketed all-reduce (the CelebAHQ config trains
+        # through TrainStep; the conditional UNet is a torch-autograd module graph with a torch optimizer: one GPU only)
+        if args.config != "celebahq":
+            raise SystemExit(f"bench.py --config {args.config} runs on one GPU; data parallel is wired for cifar and celebahq")
+        dist.init_process_group("nccl", device_id=device)
     torch.manual_seed(0)
     ldm, cfg = build_from_yaml(spec["yaml"], device)
     B = args.batch if args.batch != 128 else spec["batch"]
     size = cfg["model"]["image_size"]
+    torch.manual_seed(1234 + rank)  # identical weights (seed 0 above, then TrainStep broadcasts rank 0's), per-rank data
     x = 2 * torch.rand(B, 3, *size, device=device) - 1
     batch = {"image": x}
     down = ldm.first_stage_model.down_ratio
@@ -307,9 +317,13 @@ def run_latent(args):
             return loss
         if not args.no_graph:  # frozen AE encode eagerly, then the DDM step (fwd, bwd, clip, AdamW) as ONE CUDA graph
             try:
-                step.capture(encode())
+                if world > 1:
+                    step.capture_dp(encode())
+                    launch = "AE encode eager + a chain of CUDA graphs per DDM step cut at the gradient buckets, NCCL all-reduce between them"
+                else:
+                    step.capture(encode())
+                    launch = "AE encode eager + one CUDA graph per DDM step"
                 graph_launches = step.launches_per_step
-                launch = "AE encode eager + one CUDA graph per DDM step"
 
                 def one():  # noqa: F811
                     return step.replay(encode())
@@ -353,17 +367,27 @@ def run_latent(args):
                 print(f"[bench] CUDA graph capture failed ({e!r}); running eagerly", file=sys.stderr, flush=True)
                 torch.cuda.synchronize()
                 one = eager_step
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     for _ in range(max(2, args.warmup)):
         loss = one()
-    torch.cuda.synchronize()
+    barrier()
     l0 = lib.adm_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     e0.record()
     for _ in range(args.steps):
         loss = one()
     e1.record()
-    torch.cuda.synchronize()
+    barrier()
     ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:  # max over ranks
+        tms = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
     launches = (lib.adm_launch_count() - l0) // args.steps + graph_launches
     ldm.eval()
     with torch.no_grad():
@@ -376,20 +400,30 @@ def run_latent(args):
         s1.record()
         torch.cuda.synchronize()
     ms_s = s0.elapsed_time(s1)
+    if world > 1:  # sampling shards by batch with no communication: the slowest rank sets the time
+        tms = torch.tensor([ms_s], device=device, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms_s = float(tms.item())
+        dist.barrier()
+        if rank != 0:
+            dist.destroy_process_group()
+            return
     pk = peaks()
     tf = (spec["gflop_train"] + spec["gflop_ae"]) * B / ms
-    line = {"metric": METRIC, "value": B / (ms / 1000), "unit": "img/s", "n_gpus": 1, "steps": args.steps,
+    line = {"metric": METRIC, "value": B * world / (ms / 1000), "unit": "img/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": spec["workload"], "yaml": spec["yaml"], "global_batch": B, "batch_per_gpu": B,
-                       "parallelism": "dp1", "launch": launch, "timing": "cuda events"},
+            "config": {"workload": spec["workload"], "yaml": spec["yaml"], "global_batch": B * world, "batch_per_gpu": B,
+                       "parallelism": f"dp{world}", "launch": launch, "timing": "cuda events, max over ranks"},
             "gpu_launches": int(launches), "last_loss": float(loss),
             "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": tf / pk["tf_sust"],
                          "traffic": None, "kernel": "whole step: (UNet train + frozen AE encode) algorithmic GFLOP per image x "
                          "batch / step time, against the sustained bf16 figure", "peak_source": pk["src"]},
-            "sample": {"metric": "sample10_img_per_s", "value": B / (ms_s / 1000), "unit": "img/s", "ms_per_batch": ms_s,
-                       "steps": 10, "batch_per_gpu": B, "includes": "10 UNet steps + AE decode"}}
+            "sample": {"metric": "sample10_img_per_s", "value": B * world / (ms_s / 1000), "unit": "img/s",
+                       "ms_per_batch": ms_s, "steps": 10, "batch_per_gpu": B, "includes": "10 UNet steps + AE decode"}}
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_ours(args):
