@@ -594,7 +594,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--config", default="cifar", choices=["cifar"] + sorted(LATENT_CONFIGS),
-                    help="cifar = the headline (BASELINE configs 2 and 3); celebahq / div2k = configs 4 / 5, one GPU")
+                    help="cifar = the headline (BASELINE configs 2 and 3); celebahq / div2k = configs 4 / 5 (celebahq also data parallel under torchrun; div2k one GPU)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
