@@ -509,6 +509,8 @@ class LatentDiffusion(DDPM):
             with torch.cuda.graph(g):
                 static_out = self._sample_latent_loop(static_in, ts, t_dev, static_cond)
             ent = cache[key] = dict(graph=g, x=static_in, cond=static_cond, out=static_out, t=t_dev, sig=sig, ptrs=ptrs)
+            while len(cache) > 3:  # each graph pins a private activation pool: keep the three most recent shapes
+                cache.pop(next(iter(cache)))
         elif ent["sig"] != sig:
             # engine parameters changed since capture: one eager forward re-derives the cached bf16 operands in place
             self.model(ent["x"], ent["t"][0], ent["cond"]) if cond is not None else self.model(ent["x"], ent["t"][0])
