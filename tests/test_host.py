@@ -276,3 +276,34 @@ def test_song_unet_state_dict_layout_matches_reference(golden_dir, name):
     assert not unexpected and all(k.endswith("resample_filter") for k in missing)
     with pytest.raises(RuntimeError):  # no CPU fallback
         net(torch.zeros(1, 3, 16, 16), torch.ones(1))
+
+
+def test_latent_loader_scales_and_cycles():
+    """scripts/train_uncond_ldm.py: the loader wrapper applies the frozen first stage + scale factor
+    (ddm_const_2.py:494-524) and can be iterated again when a finite loader is exhausted."""
+    import importlib.util
+    import os
+
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("train_uncond_ldm", os.path.join(root, "scripts", "train_uncond_ldm.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    class FakeLDM:
+        scale_by_softsign, scale_by_std, scale_factor = False, True, 0.5
+        started = 0
+
+        def on_train_batch_start(self, batch):
+            self.started += 1
+
+        def get_input(self, batch):
+            return [batch["image"] * 2.0, None, batch["image"]]
+
+    ldm = FakeLDM()
+    data = [{"image": torch.full((2, 3, 4, 4), float(i))} for i in (1, 2)]
+    loader = mod.LatentLoader(ldm, data, torch.device("cpu"))
+    for _ in range(2):  # a second pass over the exhausted loader yields the same batches
+        out = [b["image"] for b in loader]
+        assert len(out) == 2 and torch.equal(out[0], torch.full((2, 3, 4, 4), 1.0)) and torch.equal(out[1], torch.full((2, 3, 4, 4), 2.0))
+    assert ldm.started == 1  # std-rescaling hook runs on the first batch only
