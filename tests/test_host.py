@@ -307,3 +307,49 @@ def test_latent_loader_scales_and_cycles():
         out = [b["image"] for b in loader]
         assert len(out) == 2 and torch.equal(out[0], torch.full((2, 3, 4, 4), 1.0)) and torch.equal(out[1], torch.full((2, 3, 4, 4), 2.0))
     assert ldm.started == 1  # std-rescaling hook runs on the first batch only
+
+
+def test_cond_trainer_loop_schedule_and_resume(tmp_path):
+    """scripts/train_cond_ldm.py CondTrainer (train_cond_ldm.py:96-330): accumulation, warm-up schedule through the device
+    learning-rate scalar, checkpoint keys and resume — on a stand-in module (the real one needs the GPU)."""
+    import importlib.util
+    import os
+
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("train_cond_ldm", os.path.join(root, "scripts", "train_cond_ldm.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    class Toy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(4, 4)
+
+        def training_step(self, batch):
+            loss = ((self.lin(batch["cond"]) - batch["image"]) ** 2).mean()
+            return loss, {"train/loss": loss.detach()}
+
+    def loader():
+        g = torch.Generator().manual_seed(0)
+        while True:
+            yield {"image": torch.randn(8, 4, generator=g), "cond": torch.randn(8, 4, generator=g)}
+
+    cfg = {"trainer": {"warmup_iter": 4, "min_lr": 1e-6, "ema_update_after_step": 1, "ema_update_every": 1}}
+    torch.manual_seed(0)
+    tr = mod.CondTrainer(Toy(), loader(), gradient_accumulate_every=2, train_lr=1e-2, train_num_steps=6,
+                         save_and_sample_every=3, results_folder=str(tmp_path), log_freq=100, cfg=cfg)
+    w0 = tr.model.lin.weight.detach().clone()
+    tr.train()
+    assert tr.step == 6 and not torch.equal(w0, tr.model.lin.weight)
+    assert abs(tr.lr_t.item() - 1e-2 * tr.lr_lambda(5)) < 1e-9  # the value the last step ran with
+    ck = torch.load(str(tmp_path / "model-2.pt"), weights_only=False)
+    assert set(ck) == {"step", "model", "opt", "lr_scheduler", "ema", "scaler"} and ck["step"] == 6
+    assert any(k.startswith("ema_model.") for k in ck["ema"]) and any(k.startswith("online_model.") for k in ck["ema"])
+    torch.manual_seed(1)
+    tr2 = mod.CondTrainer(Toy(), loader(), gradient_accumulate_every=2, train_lr=1e-2, train_num_steps=8,
+                          save_and_sample_every=100, results_folder=str(tmp_path), log_freq=100, resume_milestone=2, cfg=cfg)
+    assert tr2.step == 6 and torch.equal(tr2.model.lin.weight, tr.model.lin.weight)
+    assert tr2.opt.param_groups[0]["lr"] is tr2.lr_t
+    tr2.train()
+    assert tr2.step == 8
