@@ -276,37 +276,39 @@ def relation_layer_golden():
     import adm_b200.unet.cond_unet as CU
     g = torch.load(os.path.join(ROOT, "tests", "golden", "relation_layer.pt"))
     ok = True
-    for name, rec in g.items():
-        spec = rec["spec"]
-        for fused in (True, False):
-            CU._REL_FUSED = fused
-            layer = CU.BasicAttetnionLayer(embed_dim=spec["embed_dim"], nhead=spec["nhead"], ffn_dim=spec["ffn_dim"],
-                                           window_size1=spec["window_size1"], window_size2=spec["window_size2"])
-            layer.load_state_dict(rec["state_dict"], strict=True)
-            layer = layer.cuda().eval()
-            x1 = rec["x1"].cuda().permute(0, 2, 3, 1).to(torch.bfloat16).contiguous().requires_grad_(True)
-            x2 = rec["x2"].cuda().permute(0, 2, 3, 1).to(torch.bfloat16).contiguous().requires_grad_(True)
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                out = layer(x1, x2)
-            probe = rec["probe"].cuda().permute(0, 2, 3, 1)
-            (out.float() * probe).sum().backward()
-            torch.cuda.synchronize()
-            tag = f"{name} {'fused' if fused else 'torch tail'}"
-            ok &= _report(f"relation layer out [{tag}]", out.permute(0, 3, 1, 2), rec["out"].cuda(), 1.5e-2)
-            ok &= _report(f"relation layer dx1 [{tag}]", x1.grad.permute(0, 3, 1, 2), rec["dx1"].cuda(), 4e-2)
-            ok &= _report(f"relation layer dx2 [{tag}]", x2.grad.permute(0, 3, 1, 2), rec["dx2"].cuda(), 4e-2)
-            worst, wk = 1.0, ""
-            for k, p in layer.named_parameters():
-                ref = rec["grads"][k].cuda().flatten().double()
-                if ref.norm() < 1e-3:  # k_lin.bias: zero gradient in real arithmetic (softmax shift invariance)
-                    continue
-                a = p.grad.flatten().double()
-                cos = (torch.dot(a, ref) / (a.norm() * ref.norm())).item()
-                if cos < worst:
-                    worst, wk = cos, k
-            print(f"  relation layer [{tag}]: min parameter-gradient cosine {worst:.5f} ({wk})", flush=True)
-            ok &= worst > 0.999
-    CU._REL_FUSED = True
+    try:
+        for name, rec in g.items():
+            spec = rec["spec"]
+            for fused in (True, False):
+                CU._REL_FUSED = fused
+                layer = CU.BasicAttetnionLayer(embed_dim=spec["embed_dim"], nhead=spec["nhead"], ffn_dim=spec["ffn_dim"],
+                                               window_size1=spec["window_size1"], window_size2=spec["window_size2"])
+                layer.load_state_dict(rec["state_dict"], strict=True)
+                layer = layer.cuda().eval()
+                x1 = rec["x1"].cuda().permute(0, 2, 3, 1).to(torch.bfloat16).contiguous().requires_grad_(True)
+                x2 = rec["x2"].cuda().permute(0, 2, 3, 1).to(torch.bfloat16).contiguous().requires_grad_(True)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    out = layer(x1, x2)
+                probe = rec["probe"].cuda().permute(0, 2, 3, 1)
+                (out.float() * probe).sum().backward()
+                torch.cuda.synchronize()
+                tag = f"{name} {'fused' if fused else 'torch tail'}"
+                ok &= _report(f"relation layer out [{tag}]", out.permute(0, 3, 1, 2), rec["out"].cuda(), 1.5e-2)
+                ok &= _report(f"relation layer dx1 [{tag}]", x1.grad.permute(0, 3, 1, 2), rec["dx1"].cuda(), 4e-2)
+                ok &= _report(f"relation layer dx2 [{tag}]", x2.grad.permute(0, 3, 1, 2), rec["dx2"].cuda(), 4e-2)
+                worst, wk = 1.0, ""
+                for k, p in layer.named_parameters():
+                    ref = rec["grads"][k].cuda().flatten().double()
+                    if ref.norm() < 1e-3:  # k_lin.bias: zero gradient in real arithmetic (softmax shift invariance)
+                        continue
+                    a = p.grad.flatten().double()
+                    cos = (torch.dot(a, ref) / (a.norm() * ref.norm())).item()
+                    if cos < worst:
+                        worst, wk = cos, k
+                print(f"  relation layer [{tag}]: min parameter-gradient cosine {worst:.5f} ({wk})", flush=True)
+                ok &= worst > 0.999
+    finally:
+        CU._REL_FUSED = True
     return ok
 
 
